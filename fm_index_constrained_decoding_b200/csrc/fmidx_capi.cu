@@ -1,0 +1,568 @@
+// fmidx_capi.cu -- the extern "C" boundary declared in include/fmidx.h.
+// Replaces the SWIG wrapper generated from cpp_modules_linux/fm_index.i:7-21 of the reference.
+#include <cerrno>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <memory>
+
+#include "fmidx_internal.h"
+
+std::atomic<uint64_t> g_fm_launches{0};
+static thread_local char g_err[512] = "";
+
+void fm_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int fm_dev_alloc(fmidx *h, void **out, size_t bytes, bool owned) {
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 16);
+    if (e != cudaSuccess) {
+        fm_set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        return FMIDX_ECUDA;
+    }
+    if (owned) {
+        h->owned.push_back(*out);
+        h->dev_bytes += bytes;
+    }
+    return FMIDX_OK;
+}
+
+int fm_scratch(fmidx *h, FmBuf &b, size_t bytes, bool pinned_host) {
+    (void)h;
+    if (bytes <= b.cap && b.p) return FMIDX_OK;
+    if (b.p) {
+        if (b.pinned_host) cudaFreeHost(b.p); else cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes < 4096 ? 4096 : bytes + bytes / 4;
+    cudaError_t e = pinned_host ? cudaMallocHost(&b.p, want) : cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        fm_set_error("scratch allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+        return FMIDX_ECUDA;
+    }
+    b.cap = want;
+    b.pinned_host = pinned_host;
+    return FMIDX_OK;
+}
+
+void fm_release_index(fmidx *h) {
+    for (void *p : h->owned) cudaFree(p);
+    h->owned.clear();
+    h->dev_bytes = 0;
+    h->dev = FmDev{};
+    h->ready = false;
+}
+
+static int enter(fmidx *h, bool need_ready) {
+    if (!h) {
+        fm_set_error("null handle");
+        return FMIDX_EINVAL;
+    }
+    FM_CUDA(cudaSetDevice(h->device));
+    if (need_ready && !h->ready) {
+        fm_set_error("index is not initialised");
+        return FMIDX_ESTATE;
+    }
+    return FMIDX_OK;
+}
+
+extern "C" {
+
+const char *fmidx_last_error(void) { return g_err; }
+int fmidx_abi_version(void) { return 1; }
+uint64_t fmidx_launch_count(void) { return g_fm_launches.load(); }
+
+int fmidx_new(int device, fmidx_t **out) {
+    if (!out) { fm_set_error("out is NULL"); return FMIDX_EINVAL; }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        fm_set_error("no CUDA device available (%s): libfmidx has no CPU fallback",
+                     e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        return FMIDX_ECUDA;
+    }
+    if (device < 0 || device >= ndev) { fm_set_error("device %d out of range [0,%d)", device, ndev); return FMIDX_EINVAL; }
+    FM_CUDA(cudaSetDevice(device));
+    std::unique_ptr<fmidx> h(new fmidx());
+    h->device = device;
+    FM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    int sms = 0;
+    FM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    h->sm_count = sms > 0 ? sms : 148;
+    *out = h.release();
+    return FMIDX_OK;
+}
+
+void fmidx_free(fmidx_t *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    fm_release_index(h);
+    for (auto &b : h->d_scratch) if (b.p) cudaFree(b.p);
+    for (auto &b : h->h_scratch) if (b.p) cudaFreeHost(b.p);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int fmidx_set_options(fmidx_t *h, uint32_t sa_dens, uint32_t isa_dens, int keep_text) {
+    if (!h) { fm_set_error("null handle"); return FMIDX_EINVAL; }
+    if (sa_dens == 0 || isa_dens == 0) { fm_set_error("sample densities must be >= 1"); return FMIDX_EINVAL; }
+    h->opt_sa_dens = sa_dens;
+    h->opt_isa_dens = isa_dens;
+    h->opt_keep_text = keep_text ? 1 : 0;
+    return FMIDX_OK;
+}
+
+// ---- build ------------------------------------------------------------------------------------------
+static int build_from_host_u32(fmidx *h, const std::vector<uint32_t> &sym) {
+    uint32_t *d = nullptr;
+    FM_CUDA(cudaMalloc((void **)&d, sym.size() * 4 + 16));
+    cudaError_t e = cudaMemcpyAsync(d, sym.data(), sym.size() * 4, cudaMemcpyHostToDevice, h->stream);
+    int rc = FMIDX_OK;
+    if (e != cudaSuccess) {
+        fm_set_error("H2D copy of the text failed: %s", cudaGetErrorString(e));
+        rc = FMIDX_ECUDA;
+    } else {
+        rc = fm_build_from_device_text(h, d, sym.size(), h->stream);
+    }
+    cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    return rc;
+}
+
+int fmidx_initialize(fmidx_t *h, const uint64_t *data, size_t n) {
+    FM_TRY(enter(h, false));
+    if (n && !data) { fm_set_error("data is NULL"); return FMIDX_EINVAL; }
+    std::vector<uint32_t> sym(n);
+    for (size_t i = 0; i < n; ++i) {
+        if (data[i] == 0) { fm_set_error("text contains the reserved symbol 0 at position %zu", i); return FMIDX_EZERO; }
+        if (data[i] >> (4 * FMIDX_MAX_LEVELS)) { fm_set_error("symbol %llu at position %zu does not fit %d bits", (unsigned long long)data[i], i, 4 * FMIDX_MAX_LEVELS); return FMIDX_ERANGE; }
+        sym[i] = (uint32_t)data[i];
+    }
+    return build_from_host_u32(h, sym);
+}
+
+int fmidx_initialize_from_file(fmidx_t *h, const char *path, int width) {
+    FM_TRY(enter(h, false));
+    if (!path) { fm_set_error("path is NULL"); return FMIDX_EINVAL; }
+    if (width != 1 && width != 2 && width != 4 && width != 8) {
+        fm_set_error("initialize_from_file: width %d unsupported (1, 2, 4 or 8 bytes per symbol)", width);
+        return FMIDX_EINVAL;
+    }
+    FILE *f = fopen(path, "rb");
+    if (!f) { fm_set_error("cannot open %s: %s", path, strerror(errno)); return FMIDX_EIO; }
+    fseek(f, 0, SEEK_END);
+    long long bytes = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    size_t n = (size_t)bytes / (size_t)width;
+    std::vector<unsigned char> raw((size_t)bytes);
+    if (bytes && fread(raw.data(), 1, (size_t)bytes, f) != (size_t)bytes) {
+        fclose(f);
+        fm_set_error("short read on %s", path);
+        return FMIDX_EIO;
+    }
+    fclose(f);
+    std::vector<uint32_t> sym(n);
+    for (size_t i = 0; i < n; ++i) {
+        uint64_t v = 0;
+        memcpy(&v, raw.data() + i * (size_t)width, (size_t)width);  // little-endian, like sdsl's int reader
+        if (v == 0) { fm_set_error("file %s contains the reserved symbol 0 at position %zu", path, i); return FMIDX_EZERO; }
+        if (v >> (4 * FMIDX_MAX_LEVELS)) { fm_set_error("symbol %llu does not fit %d bits", (unsigned long long)v, 4 * FMIDX_MAX_LEVELS); return FMIDX_ERANGE; }
+        sym[i] = (uint32_t)v;
+    }
+    return build_from_host_u32(h, sym);
+}
+
+int fmidx_initialize_device(fmidx_t *h, const uint32_t *d_symbols, size_t n, void *stream) {
+    FM_TRY(enter(h, false));
+    if (n && !d_symbols) { fm_set_error("d_symbols is NULL"); return FMIDX_EINVAL; }
+    return fm_build_from_device_text(h, d_symbols, n, (cudaStream_t)stream);
+}
+
+// ---- persistence ------------------------------------------------------------------------------------
+static const char FM_MAGIC[8] = {'F', 'M', 'I', 'D', 'X', 'B', '2', '\0'};
+struct FmFileHeader {
+    char magic[8];
+    uint32_t version, levels, max_sym, sa_dens, isa_dens, keep_text, nblocks, reserved;
+    uint64_t n;
+    uint64_t bytes[8];  // cells, C, D, sa_marks, sa_samples, isa_samples, text, 0
+};
+
+static void section_sizes(const FmDev &d, uint64_t b[8]) {
+    const uint64_t N = d.n;
+    b[0] = (uint64_t)d.levels * d.nblocks * 128;
+    b[1] = ((uint64_t)d.max_sym + 2) * 4;
+    b[2] = ((uint64_t)d.max_sym + 1) * 4;
+    b[3] = d.sa_dens == 1 ? 0 : ((N + 31) / 32) * 8;
+    b[4] = d.sa_dens == 1 ? N * 4 : ((N - 1) / d.sa_dens + 1) * 4;
+    b[5] = ((N - 1) / d.isa_dens + 1) * 4;
+    b[6] = d.text ? N * 4 : 0;
+    b[7] = 0;
+}
+
+int fmidx_save(fmidx_t *h, const char *path) {
+    FM_TRY(enter(h, true));
+    if (!path) { fm_set_error("path is NULL"); return FMIDX_EINVAL; }
+    FILE *f = fopen(path, "wb");
+    if (!f) { fm_set_error("cannot open %s for writing: %s", path, strerror(errno)); return FMIDX_EIO; }
+    FmFileHeader hd{};
+    memcpy(hd.magic, FM_MAGIC, 8);
+    const FmDev &d = h->dev;
+    hd.version = 1; hd.levels = d.levels; hd.max_sym = d.max_sym; hd.sa_dens = d.sa_dens; hd.isa_dens = d.isa_dens;
+    hd.keep_text = d.text ? 1 : 0; hd.nblocks = d.nblocks; hd.n = d.n;
+    section_sizes(d, hd.bytes);
+    const void *src[7] = {d.cells, d.C, d.D, d.sa_marks, d.sa_samples, d.isa_samples, d.text};
+    int rc = FMIDX_OK;
+    if (fwrite(&hd, sizeof(hd), 1, f) != 1) rc = FMIDX_EIO;
+    const size_t CH = 64u << 20;
+    std::vector<unsigned char> buf(CH);
+    for (int sct = 0; sct < 7 && rc == FMIDX_OK; ++sct) {
+        for (uint64_t off = 0; off < hd.bytes[sct] && rc == FMIDX_OK; off += CH) {
+            size_t len = (size_t)std::min<uint64_t>(CH, hd.bytes[sct] - off);
+            cudaError_t e = cudaMemcpy(buf.data(), (const char *)src[sct] + off, len, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) { fm_set_error("D2H failed while saving: %s", cudaGetErrorString(e)); rc = FMIDX_ECUDA; }
+            else if (fwrite(buf.data(), 1, len, f) != len) rc = FMIDX_EIO;
+        }
+    }
+    if (fclose(f) != 0 && rc == FMIDX_OK) rc = FMIDX_EIO;
+    if (rc == FMIDX_EIO) fm_set_error("write error on %s", path);
+    return rc;
+}
+
+int fmidx_load(const char *path, int device, fmidx_t **out) {
+    if (!path || !out) { fm_set_error("null argument"); return FMIDX_EINVAL; }
+    *out = nullptr;
+    fmidx_t *h = nullptr;
+    FM_TRY(fmidx_new(device, &h));
+    FILE *f = fopen(path, "rb");
+    if (!f) { fm_set_error("cannot open %s: %s", path, strerror(errno)); fmidx_free(h); return FMIDX_EIO; }
+    FmFileHeader hd{};
+    int rc = FMIDX_OK;
+    if (fread(&hd, sizeof(hd), 1, f) != 1 || memcmp(hd.magic, FM_MAGIC, 8) != 0 || hd.version != 1) {
+        fm_set_error("%s is not an fmidx-b200 index file (bad magic/version)", path);
+        rc = FMIDX_EIO;
+    }
+    if (rc == FMIDX_OK) {
+        FmDev d{};
+        d.levels = hd.levels; d.max_sym = hd.max_sym; d.sa_dens = hd.sa_dens; d.isa_dens = hd.isa_dens;
+        d.nblocks = hd.nblocks; d.n = (uint32_t)hd.n; d.level_stride = (uint64_t)hd.nblocks * FMIDX_CELL_U4;
+        uint64_t expect[8];
+        FmDev probe = d;
+        probe.text = hd.keep_text ? (const uint32_t *)1 : nullptr;
+        section_sizes(probe, expect);
+        for (int i = 0; i < 7; ++i) if (expect[i] != hd.bytes[i]) { fm_set_error("%s: corrupt section table", path); rc = FMIDX_EIO; }
+        void *dst[7] = {nullptr};
+        const size_t CH = 64u << 20;
+        std::vector<unsigned char> buf(CH);
+        for (int sct = 0; sct < 7 && rc == FMIDX_OK; ++sct) {
+            if (!hd.bytes[sct]) continue;
+            rc = fm_dev_alloc(h, &dst[sct], hd.bytes[sct], true);
+            for (uint64_t off = 0; off < hd.bytes[sct] && rc == FMIDX_OK; off += CH) {
+                size_t len = (size_t)std::min<uint64_t>(CH, hd.bytes[sct] - off);
+                if (fread(buf.data(), 1, len, f) != len) { fm_set_error("%s: truncated file", path); rc = FMIDX_EIO; break; }
+                cudaError_t e = cudaMemcpy((char *)dst[sct] + off, buf.data(), len, cudaMemcpyHostToDevice);
+                if (e != cudaSuccess) { fm_set_error("H2D failed while loading: %s", cudaGetErrorString(e)); rc = FMIDX_ECUDA; }
+            }
+        }
+        if (rc == FMIDX_OK) {
+            d.cells = (const uint4 *)dst[0]; d.C = (const uint32_t *)dst[1]; d.D = (const uint32_t *)dst[2];
+            d.sa_marks = (const uint2 *)dst[3]; d.sa_samples = (const uint32_t *)dst[4];
+            d.isa_samples = (const uint32_t *)dst[5]; d.text = (const uint32_t *)dst[6];
+            h->dev = d;
+            h->opt_sa_dens = d.sa_dens; h->opt_isa_dens = d.isa_dens; h->opt_keep_text = hd.keep_text;
+            h->ready = true;
+        }
+    }
+    fclose(f);
+    if (rc != FMIDX_OK) { fmidx_free(h); return rc; }
+    *out = h;
+    return FMIDX_OK;
+}
+
+// ---- scalar queries -----------------------------------------------------------------------------------
+int fmidx_size(fmidx_t *h, uint64_t *out) {
+    if (!h || !out) { fm_set_error("null argument"); return FMIDX_EINVAL; }
+    if (!h->ready) { fm_set_error("index is not initialised"); return FMIDX_ESTATE; }
+    *out = h->dev.n;
+    return FMIDX_OK;
+}
+
+int fmidx_info(fmidx_t *h, uint64_t info[8]) {
+    if (!h || !info) { fm_set_error("null argument"); return FMIDX_EINVAL; }
+    if (!h->ready) { fm_set_error("index is not initialised"); return FMIDX_ESTATE; }
+    info[0] = h->dev.n; info[1] = h->dev.levels; info[2] = h->dev.max_sym; info[3] = h->dev.sa_dens;
+    info[4] = h->dev.isa_dens; info[5] = h->dev_bytes; info[6] = (uint64_t)h->dev.nblocks * 128; info[7] = h->dev.text ? 1 : 0;
+    return FMIDX_OK;
+}
+
+int fmidx_debug_copy_sa(fmidx_t *h, uint32_t *out, size_t cap) {
+    FM_TRY(enter(h, true));
+    if (h->dev.sa_dens != 1) { fm_set_error("debug_copy_sa needs sa_dens == 1"); return FMIDX_ESTATE; }
+    if (cap < h->dev.n) { fm_set_error("buffer too small"); return FMIDX_ERANGE; }
+    FM_CUDA(cudaMemcpy(out, h->dev.sa_samples, (size_t)h->dev.n * 4, cudaMemcpyDeviceToHost));
+    return FMIDX_OK;
+}
+
+int fmidx_backward_search_step(fmidx_t *h, uint64_t symbol, uint64_t low, uint64_t high, uint64_t out[2]) {
+    FM_TRY(enter(h, true));
+    FM_TRY(fm_scratch(h, h->d_scratch[0], 64, false));
+    FM_TRY(fm_scratch(h, h->h_scratch[0], 64, true));
+    uint64_t *hp = (uint64_t *)h->h_scratch[0].p, *dp = (uint64_t *)h->d_scratch[0].p;
+    hp[0] = symbol; hp[1] = low; hp[2] = high;
+    FM_CUDA(cudaMemcpyAsync(dp, hp, 24, cudaMemcpyHostToDevice, h->stream));
+    FM_TRY(fm_launch_step(h, dp, dp + 1, dp + 2, 1, dp + 4, dp + 5, h->stream));
+    FM_CUDA(cudaMemcpyAsync(hp + 4, dp + 4, 16, cudaMemcpyDeviceToHost, h->stream));
+    FM_CUDA(cudaStreamSynchronize(h->stream));
+    out[0] = hp[4]; out[1] = hp[5];
+    return FMIDX_OK;
+}
+
+int fmidx_backward_search_multi(fmidx_t *h, const uint64_t *query, size_t n, uint64_t out[2]) {
+    FM_TRY(enter(h, true));
+    const size_t tb = (n + 4) * 4;
+    FM_TRY(fm_scratch(h, h->d_scratch[0], tb + 64, false));
+    FM_TRY(fm_scratch(h, h->h_scratch[0], tb + 64, true));
+    char *hp = (char *)h->h_scratch[0].p, *dp = (char *)h->d_scratch[0].p;
+    int64_t *hoffs = (int64_t *)hp;             // [2]
+    uint64_t *hres = (uint64_t *)(hp + 16);     // [2]
+    int32_t *htok = (int32_t *)(hp + 32);       // [n]
+    hoffs[0] = 0; hoffs[1] = (int64_t)n;
+    for (size_t i = 0; i < n; ++i) htok[i] = query[i] > 0x7FFFFFFFull ? -1 : (int32_t)query[i];  // -1: absent
+    FM_CUDA(cudaMemcpyAsync(dp, hp, 32 + n * 4, cudaMemcpyHostToDevice, h->stream));
+    FM_TRY(fm_launch_search(h, (int32_t *)(dp + 32), (int64_t *)dp, 1, 0, (uint64_t *)(dp + 16), (uint64_t *)(dp + 24), 1, h->stream));
+    FM_CUDA(cudaMemcpyAsync(hres, dp + 16, 16, cudaMemcpyDeviceToHost, h->stream));
+    FM_CUDA(cudaStreamSynchronize(h->stream));
+    out[0] = hres[0]; out[1] = hres[1];
+    return FMIDX_OK;
+}
+
+// ranges -> per-range sparse (symbol,count) lists on the raw symbol axis, via bitmap + compaction
+static int distinct_lists(fmidx *h, const uint64_t *lows, const uint64_t *highs, size_t nr, bool with_counts,
+                          std::vector<uint64_t> &flat, std::vector<uint64_t> &offsets) {
+    const uint32_t vocab = h->dev.max_sym + 1;
+    const uint32_t words = (vocab + 31) / 32;
+    offsets.assign(nr + 1, 0);
+    flat.clear();
+    size_t chunk = (size_t)((256ull << 20) / ((uint64_t)vocab * 4));
+    if (chunk < 1) chunk = 1;
+    if (chunk > 16384) chunk = 16384;
+    cudaStream_t s = h->stream;
+    for (size_t r0 = 0; r0 < nr; r0 += chunk) {
+        const size_t rn = std::min(chunk, nr - r0);
+        FM_TRY(fm_scratch(h, h->d_scratch[1], rn * 16, false));                       // sp | ep
+        FM_TRY(fm_scratch(h, h->d_scratch[2], rn * (size_t)words * 4, false));         // bitmaps
+        FM_TRY(fm_scratch(h, h->d_scratch[3], rn * (size_t)vocab * 4, false));         // counts
+        FM_TRY(fm_scratch(h, h->d_scratch[4], (rn + 1) * 8 + rn * 4, false));          // offsets | n
+        uint64_t *d_sp = (uint64_t *)h->d_scratch[1].p, *d_ep = d_sp + rn;
+        uint32_t *d_mask = (uint32_t *)h->d_scratch[2].p, *d_counts = (uint32_t *)h->d_scratch[3].p;
+        uint64_t *d_off = (uint64_t *)h->d_scratch[4].p;
+        uint32_t *d_n = (uint32_t *)(d_off + rn + 1);
+        FM_CUDA(cudaMemcpyAsync(d_sp, lows + r0, rn * 8, cudaMemcpyHostToDevice, s));
+        FM_CUDA(cudaMemcpyAsync(d_ep, highs + r0, rn * 8, cudaMemcpyHostToDevice, s));
+        FM_TRY(fm_launch_mask(h, d_sp, d_ep, rn, 0, vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, d_mask,
+                              with_counts ? d_counts : nullptr, s));
+        FM_TRY(fm_launch_popcount(h, d_mask, rn, vocab, d_n, s));
+        std::vector<uint32_t> hn(rn);
+        FM_CUDA(cudaMemcpyAsync(hn.data(), d_n, rn * 4, cudaMemcpyDeviceToHost, s));
+        FM_CUDA(cudaStreamSynchronize(s));
+        std::vector<uint64_t> hoff(rn + 1, 0);
+        for (size_t i = 0; i < rn; ++i) hoff[i + 1] = hoff[i] + hn[i];
+        const uint64_t total = hoff[rn];
+        FM_TRY(fm_scratch(h, h->d_scratch[5], (total + 1) * 16, false));
+        int64_t *d_tok = (int64_t *)h->d_scratch[5].p;
+        uint64_t *d_cnt = (uint64_t *)(d_tok + total + 1);
+        FM_CUDA(cudaMemcpyAsync(d_off, hoff.data(), (rn + 1) * 8, cudaMemcpyHostToDevice, s));
+        FM_TRY(fm_launch_compact(h, d_mask, with_counts ? d_counts : nullptr, rn, vocab, d_off, d_tok,
+                                 with_counts ? d_cnt : nullptr, s));
+        std::vector<int64_t> htok(total);
+        std::vector<uint64_t> hcnt(with_counts ? total : 0);
+        if (total) {
+            FM_CUDA(cudaMemcpyAsync(htok.data(), d_tok, total * 8, cudaMemcpyDeviceToHost, s));
+            if (with_counts) FM_CUDA(cudaMemcpyAsync(hcnt.data(), d_cnt, total * 8, cudaMemcpyDeviceToHost, s));
+        }
+        FM_CUDA(cudaStreamSynchronize(s));
+        for (size_t i = 0; i < rn; ++i) {
+            for (uint64_t k = hoff[i]; k < hoff[i + 1]; ++k) {
+                flat.push_back((uint64_t)htok[k]);
+                if (with_counts) flat.push_back(hcnt[k]);
+            }
+            offsets[r0 + i + 1] = flat.size();
+        }
+    }
+    return FMIDX_OK;
+}
+
+static int distinct_one(fmidx_t *h, uint64_t low, uint64_t high, bool with_counts, uint64_t *out, size_t cap, size_t *k) {
+    FM_TRY(enter(h, true));
+    if (!k) { fm_set_error("k is NULL"); return FMIDX_EINVAL; }
+    std::vector<uint64_t> flat, offs;
+    FM_TRY(distinct_lists(h, &low, &high, 1, with_counts, flat, offs));
+    *k = flat.size();
+    if (flat.size() > cap) { fm_set_error("output buffer too small: need %zu", flat.size()); return FMIDX_ERANGE; }
+    if (!flat.empty()) memcpy(out, flat.data(), flat.size() * 8);
+    return FMIDX_OK;
+}
+
+int fmidx_distinct(fmidx_t *h, uint64_t low, uint64_t high, uint64_t *out, size_t cap, size_t *k) {
+    return distinct_one(h, low, high, false, out, cap, k);
+}
+int fmidx_distinct_count(fmidx_t *h, uint64_t low, uint64_t high, uint64_t *out, size_t cap, size_t *k) {
+    return distinct_one(h, low, high, true, out, cap, k);
+}
+
+int fmidx_distinct_count_multi(fmidx_t *h, const uint64_t *lows, const uint64_t *highs, size_t nr, uint64_t *out,
+                               size_t cap, uint64_t *offsets) {
+    FM_TRY(enter(h, true));
+    if (!offsets || (nr && (!lows || !highs))) { fm_set_error("null argument"); return FMIDX_EINVAL; }
+    std::vector<uint64_t> flat, offs;
+    FM_TRY(distinct_lists(h, lows, highs, nr, true, flat, offs));
+    memcpy(offsets, offs.data(), (nr + 1) * 8);
+    if (flat.size() > cap) { fm_set_error("output buffer too small: need %zu", flat.size()); return FMIDX_ERANGE; }
+    if (!flat.empty()) memcpy(out, flat.data(), flat.size() * 8);
+    return FMIDX_OK;
+}
+
+int fmidx_locate(fmidx_t *h, uint64_t row, uint64_t *out) {
+    FM_TRY(enter(h, true));
+    FM_TRY(fm_scratch(h, h->d_scratch[0], 64, false));
+    FM_TRY(fm_scratch(h, h->h_scratch[0], 64, true));
+    uint64_t *hp = (uint64_t *)h->h_scratch[0].p, *dp = (uint64_t *)h->d_scratch[0].p;
+    hp[0] = row;
+    FM_CUDA(cudaMemcpyAsync(dp, hp, 8, cudaMemcpyHostToDevice, h->stream));
+    FM_TRY(fm_launch_locate(h, dp, 1, dp + 1, h->stream));
+    FM_CUDA(cudaMemcpyAsync(hp + 1, dp + 1, 8, cudaMemcpyDeviceToHost, h->stream));
+    FM_CUDA(cudaStreamSynchronize(h->stream));
+    *out = hp[1];
+    return FMIDX_OK;
+}
+
+int fmidx_extract_text(fmidx_t *h, uint64_t begin, uint64_t end, uint64_t *out, size_t cap, size_t *k) {
+    FM_TRY(enter(h, true));
+    if (!k) { fm_set_error("k is NULL"); return FMIDX_EINVAL; }
+    uint64_t e2 = end > h->dev.n ? h->dev.n : end;
+    uint64_t m = e2 > begin ? e2 - begin : 0;
+    *k = (size_t)m;
+    if (m == 0) return FMIDX_OK;
+    if (m > cap) { fm_set_error("output buffer too small: need %llu", (unsigned long long)m); return FMIDX_ERANGE; }
+    FM_TRY(fm_scratch(h, h->d_scratch[0], 64 + m * 8, false));
+    FM_TRY(fm_scratch(h, h->h_scratch[0], 64, true));
+    uint64_t *hp = (uint64_t *)h->h_scratch[0].p, *dp = (uint64_t *)h->d_scratch[0].p;
+    hp[0] = begin; hp[1] = end;
+    FM_CUDA(cudaMemcpyAsync(dp, hp, 16, cudaMemcpyHostToDevice, h->stream));
+    FM_TRY(fm_launch_extract(h, dp, dp + 1, 1, m, dp + 8, dp + 2, h->stream));
+    FM_CUDA(cudaMemcpyAsync(out, dp + 8, m * 8, cudaMemcpyDeviceToHost, h->stream));
+    FM_CUDA(cudaStreamSynchronize(h->stream));
+    return FMIDX_OK;
+}
+
+// ---- batched device entry points ------------------------------------------------------------------------
+int fmidx_search_batch(fmidx_t *h, const int32_t *d_toks, const int64_t *d_offs, size_t B, int64_t shift,
+                       uint64_t *d_sp, uint64_t *d_ep, void *stream) {
+    FM_TRY(enter(h, true));
+    return fm_launch_search(h, d_toks, d_offs, B, shift, d_sp, d_ep, 0, (cudaStream_t)stream);
+}
+
+int fmidx_step_batch(fmidx_t *h, const uint64_t *d_symbols, const uint64_t *d_lows, const uint64_t *d_highs, size_t B,
+                     uint64_t *d_sp, uint64_t *d_ep, void *stream) {
+    FM_TRY(enter(h, true));
+    return fm_launch_step(h, d_symbols, d_lows, d_highs, B, d_sp, d_ep, (cudaStream_t)stream);
+}
+
+int fmidx_distinct_mask_batch(fmidx_t *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, int64_t shift,
+                              uint32_t vocab, uint32_t *d_mask, uint32_t *d_counts, void *stream) {
+    FM_TRY(enter(h, true));
+    if (!d_mask) { fm_set_error("d_mask is NULL"); return FMIDX_EINVAL; }
+    return fm_launch_mask(h, d_sp, d_ep, B, shift, vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, d_mask, d_counts,
+                          (cudaStream_t)stream);
+}
+
+int fmidx_mask_logits(fmidx_t *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, int64_t shift, uint32_t vocab,
+                      const void *d_logits, void *d_out, int dtype, int64_t row_stride, const int32_t *d_override_tok,
+                      int32_t always_allow, const uint32_t *d_extra_masks, uint32_t n_extra, uint32_t *d_mask_out,
+                      void *stream) {
+    FM_TRY(enter(h, true));
+    if (!d_logits || !d_out) { fm_set_error("logits pointers are NULL"); return FMIDX_EINVAL; }
+    if (dtype != FMIDX_F32 && dtype != FMIDX_BF16 && dtype != FMIDX_F16) { fm_set_error("unknown dtype %d", dtype); return FMIDX_EINVAL; }
+    return fm_launch_mask(h, d_sp, d_ep, B, shift, vocab, d_logits, d_out, dtype, row_stride, d_override_tok, always_allow,
+                          d_extra_masks, n_extra, d_mask_out, nullptr, (cudaStream_t)stream);
+}
+
+int fmidx_mask_popcount(fmidx_t *h, const uint32_t *d_mask, size_t B, uint32_t vocab, uint32_t *d_n, void *stream) {
+    FM_TRY(enter(h, false));
+    return fm_launch_popcount(h, d_mask, B, vocab, d_n, (cudaStream_t)stream);
+}
+
+int fmidx_mask_compact(fmidx_t *h, const uint32_t *d_mask, const uint32_t *d_counts, size_t B, uint32_t vocab,
+                       const uint64_t *d_list_offsets, int64_t *d_tokens, uint64_t *d_cnts, void *stream) {
+    FM_TRY(enter(h, false));
+    return fm_launch_compact(h, d_mask, d_counts, B, vocab, d_list_offsets, d_tokens, d_cnts, (cudaStream_t)stream);
+}
+
+int fmidx_locate_batch(fmidx_t *h, const uint64_t *d_rows, size_t n, uint64_t *d_pos, void *stream) {
+    FM_TRY(enter(h, true));
+    return fm_launch_locate(h, d_rows, n, d_pos, (cudaStream_t)stream);
+}
+
+int fmidx_extract_batch(fmidx_t *h, const uint64_t *d_begin, const uint64_t *d_end, size_t n, uint64_t max_len,
+                        uint64_t *d_out, uint64_t *d_len, void *stream) {
+    FM_TRY(enter(h, true));
+    if (max_len == 0) { fm_set_error("max_len is 0"); return FMIDX_EINVAL; }
+    return fm_launch_extract(h, d_begin, d_end, n, max_len, d_out, d_len, (cudaStream_t)stream);
+}
+
+// ---- host-buffer batch calls ----------------------------------------------------------------------------
+int fmidx_query_host(fmidx_t *h, const int32_t *toks, const int64_t *offs, size_t B, int64_t shift, uint32_t vocab,
+                     uint64_t *sp, uint64_t *ep, uint32_t *mask) {
+    FM_TRY(enter(h, true));
+    if (B == 0) return FMIDX_OK;
+    if (!toks || !offs || !sp || !ep) { fm_set_error("null argument"); return FMIDX_EINVAL; }
+    const size_t ntok = (size_t)(offs[B] - offs[0]);
+    if (offs[0] != 0) { fm_set_error("offs[0] must be 0"); return FMIDX_EINVAL; }
+    const uint32_t words = (vocab + 31) / 32;
+    cudaStream_t s = h->stream;
+    FM_TRY(fm_scratch(h, h->d_scratch[6], ntok * 4 + 16 + (B + 1) * 8 + B * 16, false));
+    char *dp = (char *)h->d_scratch[6].p;
+    int64_t *d_offs = (int64_t *)dp;
+    uint64_t *d_sp = (uint64_t *)(dp + (B + 1) * 8), *d_ep = d_sp + B;
+    int32_t *d_toks = (int32_t *)(d_ep + B);
+    FM_CUDA(cudaMemcpyAsync(d_offs, offs, (B + 1) * 8, cudaMemcpyHostToDevice, s));
+    if (ntok) FM_CUDA(cudaMemcpyAsync(d_toks, toks, ntok * 4, cudaMemcpyHostToDevice, s));
+    FM_TRY(fm_launch_search(h, d_toks, d_offs, B, shift, d_sp, d_ep, 0, s));
+    uint32_t *d_mask = nullptr;
+    if (mask) {
+        FM_TRY(fm_scratch(h, h->d_scratch[7], B * (size_t)words * 4, false));
+        d_mask = (uint32_t *)h->d_scratch[7].p;
+        FM_TRY(fm_launch_mask(h, d_sp, d_ep, B, shift, vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, d_mask, nullptr, s));
+    }
+    FM_CUDA(cudaMemcpyAsync(sp, d_sp, B * 8, cudaMemcpyDeviceToHost, s));
+    FM_CUDA(cudaMemcpyAsync(ep, d_ep, B * 8, cudaMemcpyDeviceToHost, s));
+    if (mask) FM_CUDA(cudaMemcpyAsync(mask, d_mask, B * (size_t)words * 4, cudaMemcpyDeviceToHost, s));
+    FM_CUDA(cudaStreamSynchronize(s));
+    return FMIDX_OK;
+}
+
+int fmidx_search_host(fmidx_t *h, const int32_t *toks, const int64_t *offs, size_t B, int64_t shift, uint64_t *sp,
+                      uint64_t *ep) {
+    return fmidx_query_host(h, toks, offs, B, shift, 0, sp, ep, nullptr);
+}
+
+int fmidx_locate_host(fmidx_t *h, const uint64_t *rows, size_t n, uint64_t *pos) {
+    FM_TRY(enter(h, true));
+    if (n == 0) return FMIDX_OK;
+    cudaStream_t s = h->stream;
+    FM_TRY(fm_scratch(h, h->d_scratch[6], n * 16, false));
+    uint64_t *d_rows = (uint64_t *)h->d_scratch[6].p, *d_pos = d_rows + n;
+    FM_CUDA(cudaMemcpyAsync(d_rows, rows, n * 8, cudaMemcpyHostToDevice, s));
+    FM_TRY(fm_launch_locate(h, d_rows, n, d_pos, s));
+    FM_CUDA(cudaMemcpyAsync(pos, d_pos, n * 8, cudaMemcpyDeviceToHost, s));
+    FM_CUDA(cudaStreamSynchronize(s));
+    return FMIDX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+// fmidx_internal.h -- host-side handle and helpers shared by the builder, the kernel
+// launchers and the C ABI (include/fmidx.h).
+#pragma once
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/fmidx.h"
+#include "fmidx_layout.cuh"
+
+void fm_set_error(const char *fmt, ...);
+extern std::atomic<uint64_t> g_fm_launches;
+
+#define FM_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            fm_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return FMIDX_ECUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+#define FM_TRY(expr)            \
+    do {                        \
+        int _r = (expr);        \
+        if (_r != FMIDX_OK) return _r; \
+    } while (0)
+
+// every kernel launch of this library goes through this macro (gpu_launches accounting)
+#define FM_LAUNCH(kernel, grid, block, smem, stream, ...)                    \
+    do {                                                                     \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);          \
+        g_fm_launches.fetch_add(1, std::memory_order_relaxed);               \
+    } while (0)
+
+struct FmBuf {  // growable device / pinned-host scratch
+    void *p = nullptr;
+    size_t cap = 0;
+    bool pinned_host = false;
+};
+
+struct fmidx {
+    int device = 0;
+    bool ready = false;
+    FmDev dev{};
+    uint32_t opt_sa_dens = 32;   // csa_wt_int<> default t_dens
+    uint32_t opt_isa_dens = 64;  // csa_wt_int<> default t_inv_dens
+    int opt_keep_text = 0;
+    std::vector<void *> owned;   // device allocations that make up the index
+    size_t dev_bytes = 0;
+    cudaStream_t stream = nullptr;  // private stream of the synchronous host-style calls
+    FmBuf d_scratch[8];
+    FmBuf h_scratch[4];
+    int sm_count = 148;
+};
+
+int fm_dev_alloc(fmidx *h, void **out, size_t bytes, bool owned);
+int fm_scratch(fmidx *h, FmBuf &b, size_t bytes, bool pinned_host);
+void fm_release_index(fmidx *h);
+
+// builder (fmidx_build.cu)
+int fm_build_from_device_text(fmidx *h, const uint32_t *d_symbols, size_t n_data, cudaStream_t s);
+
+// kernel launchers (fmidx_kernels.cu); all enqueue on `s`
+int fm_launch_search(fmidx *h, const int32_t *d_toks, const int64_t *d_offs, size_t B, int64_t shift, uint64_t *d_sp,
+                     uint64_t *d_ep, int raw, cudaStream_t s);
+int fm_launch_step(fmidx *h, const uint64_t *d_sym, const uint64_t *d_lo, const uint64_t *d_hi, size_t B,
+                   uint64_t *d_sp, uint64_t *d_ep, cudaStream_t s);
+int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, int64_t shift, uint32_t vocab,
+                   const void *d_logits, void *d_out, int dtype, int64_t row_stride, const int32_t *d_override,
+                   int32_t always_allow, const uint32_t *d_extra, uint32_t n_extra, uint32_t *d_mask,
+                   uint32_t *d_counts, cudaStream_t s);
+int fm_launch_popcount(fmidx *h, const uint32_t *d_mask, size_t B, uint32_t vocab, uint32_t *d_n, cudaStream_t s);
+int fm_launch_compact(fmidx *h, const uint32_t *d_mask, const uint32_t *d_counts, size_t B, uint32_t vocab,
+                      const uint64_t *d_offs, int64_t *d_tokens, uint64_t *d_cnts, cudaStream_t s);
+int fm_launch_locate(fmidx *h, const uint64_t *d_rows, size_t n, uint64_t *d_pos, cudaStream_t s);
+int fm_launch_extract(fmidx *h, const uint64_t *d_begin, const uint64_t *d_end, size_t n, uint64_t max_len,
+                      uint64_t *d_out, uint64_t *d_len, cudaStream_t s);

@@ -1,0 +1,582 @@
+// fmidx_kernels.cu -- the sm_100a query kernels of the FM-index hot path.
+//
+//   K1  k_search   batched backward search         index.py:103-114 over fm_index.cpp:67-97
+//       k_step     batched single LF/backward step  fm_index.cpp:67-97
+//   K2  k_mask     distinct next tokens of [sp,ep) -> vocab bitmap (+counts), fused with the
+//                  -inf masking of the beam's logits row
+//                  fm_index.cpp:119-166 + index.py:147-174 + document_constrained_generation_vllm.py:52,105-137
+//       k_popcount / k_compact   bitmap(+counts) -> ascending (token,count) lists
+//   K3  k_locate   SA-sample locate                 fm_index.cpp:168-172
+//   K4  k_extract  text extraction                  fm_index.cpp:174-194 (as written: isa[end-1])
+//
+// All of it is random-access integer work bounded by HBM/L2 latency and sector throughput; no
+// tensor cores.  Thread mapping: an aligned OCTET of lanes owns one rank probe (one 128-B cell,
+// one LDG.128 per lane, 3-step xor-shuffle popcount reduction); a half-warp owns one query
+// (sp octet + ep octet) or one enumeration node.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "fmidx_internal.h"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// =================================================================================================
+// K1: backward search.  16 lanes per prefix: octet 0 chases sp, octet 1 chases ep, both through
+// the same `levels` cells per token; D[c] and the next token are fetched ahead of the descent.
+// RAW=false : index.FMIndex.get_range semantics (early exit with (0,0), index.py:111-112)
+// RAW=true  : FMIndex::backward_search_multi semantics (fm_index.cpp:55-65; no guards, an absent
+//             symbol gives l=1,r=0 and the arithmetic just continues)
+// =================================================================================================
+template <bool RAW>
+__global__ void __launch_bounds__(128) k_search(FmDev ix, const int32_t *__restrict__ toks,
+                                                const int64_t *__restrict__ offs, uint32_t B, int64_t shift,
+                                                uint64_t *__restrict__ sp, uint64_t *__restrict__ ep) {
+    const int lane = threadIdx.x & 31, sub = lane & 7, half = (lane >> 3) & 1;
+    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const bool valid = q < B;
+    int64_t o0 = 0;
+    int len = 0;
+    if (valid) {
+        o0 = offs[q];
+        len = (int)(offs[q + 1] - o0);
+    }
+    const int other_len = __shfl_xor_sync(FULL, len, 16);
+    const int maxlen = len > other_len ? len : other_len;
+    uint32_t lo = 0, hi = ix.n;
+    bool alive = valid;
+    int32_t tok_next = (valid && len > 0) ? toks[o0] : 0;
+    for (int t = 0; t < maxlen; ++t) {
+        const bool act = alive && t < len;
+        const int64_t sym = (int64_t)tok_next + shift;
+        if (act && t + 1 < len) tok_next = toks[o0 + t + 1];
+        const bool symok = act && sym >= 0 && sym <= (int64_t)ix.max_sym;
+        const uint32_t c = symok ? (uint32_t)sym : 0u;
+        // RAW: sdsl::backward_search answers l=1,r=0 for a symbol that is not in the text
+        const bool present = RAW ? (symok && ix.C[c + 1] > ix.C[c]) : symok;
+        uint32_t nlo, nhi;
+        if (t == 0) {
+            // whole range: sdsl::backward_search's (l==0 && r+1==size) shortcut -> [C[c], C[c+1])
+            nlo = present ? ix.C[c] : 1u;
+            nhi = present ? ix.C[c + 1] : 1u;
+        } else {
+            const uint32_t Dc = symok ? ix.D[c] : 0u;
+            uint32_t pos = half ? hi : lo;
+            for (uint32_t l = 0; l < ix.levels; ++l)
+                pos = fm_step8(ix.cells + l * ix.level_stride, pos, fm_digit(c, ix.levels, l), sub, symok);
+            const uint32_t res = present ? Dc + pos : 1u;
+            const uint32_t oth = __shfl_xor_sync(FULL, res, 8);
+            nlo = half ? oth : res;
+            nhi = half ? res : oth;
+        }
+        if (act) {
+            if (RAW) {
+                lo = nlo;
+                hi = nhi;
+            } else if (!symok || nlo >= nhi) {
+                lo = 0;
+                hi = 0;
+                alive = false;
+            } else {
+                lo = nlo;
+                hi = nhi;
+            }
+        }
+    }
+    if (valid && (lane & 15) == 0) {
+        sp[q] = lo;
+        ep[q] = hi;
+    }
+}
+
+// B independent FMIndex::backward_search_step calls (inclusive [low,high] in, half-open out).
+__global__ void __launch_bounds__(128) k_step(FmDev ix, const uint64_t *__restrict__ syms,
+                                              const uint64_t *__restrict__ lows, const uint64_t *__restrict__ highs,
+                                              uint32_t B, uint64_t *__restrict__ sp, uint64_t *__restrict__ ep) {
+    const int lane = threadIdx.x & 31, sub = lane & 7, half = (lane >> 3) & 1;
+    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const bool valid = q < B;
+    uint64_t sym = 0, low = 1, high = 0;
+    if (valid) {
+        sym = syms[q];
+        low = lows[q];
+        high = highs[q];
+        if (high >= ix.n) high = (uint64_t)ix.n - 1;  // fm_index.cpp:74-76
+    }
+    const bool ok = valid && low <= high && sym <= ix.max_sym;  // fm_index.cpp:77-82 ; absent symbol
+    const uint32_t c = ok ? (uint32_t)sym : 0u;
+    const uint32_t Dc = ok ? ix.D[c] : 0u;
+    uint32_t pos = ok ? (half ? (uint32_t)high + 1u : (uint32_t)low) : 0u;
+    for (uint32_t l = 0; l < ix.levels; ++l)
+        pos = fm_step8(ix.cells + l * ix.level_stride, pos, fm_digit(c, ix.levels, l), sub, ok);
+    const uint32_t res = Dc + pos;
+    const uint32_t oth = __shfl_xor_sync(FULL, res, 8);
+    const uint32_t nlo = half ? oth : res, nhi = half ? res : oth;
+    if (valid && (lane & 15) == 0) {
+        const bool hit = ok && nlo < nhi;  // fm_index.cpp:87-92
+        sp[q] = hit ? nlo : 0;
+        ep[q] = hit ? nhi : 0;
+    }
+}
+
+// =================================================================================================
+// K2: distinct-symbol enumeration of BWT[sp,ep) restricted to one 4096-token slice of the vocab,
+// into a shared-memory bitmap, fused with the masking of that slice of the beam's logits row.
+// grid = ceil(vocab/4096) * B CTAs (slice-fastest), 128 threads.  The slice's logits are loaded into registers
+// BEFORE the tree walk so the walk's dependent-load latency overlaps the streaming traffic.
+// The walk is a level-synchronous BFS over the 16-ary wavelet matrix, one half-warp per node
+// (octet 0 loads the cell of lo, octet 1 the cell of hi, lane d evaluates child d), pruned to
+// the slice's symbol interval, so slices need no communication and no atomics on global memory.
+// =================================================================================================
+constexpr int SLICE = 4096;        // tokens per CTA
+constexpr int MASK_THREADS = 128;
+constexpr int MAXF = 288;          // frontier capacity: <= SLICE/16 + 2 nodes at the deepest inner level
+
+template <int DT> struct Elem;
+template <> struct Elem<FMIDX_F32> { using T = float; static constexpr int VEC = 4; };
+template <> struct Elem<FMIDX_BF16> { using T = __nv_bfloat16; static constexpr int VEC = 8; };
+template <> struct Elem<FMIDX_F16> { using T = __half; static constexpr int VEC = 8; };
+
+__device__ __forceinline__ float fm_add_mask(float x, bool allowed) { return x + (allowed ? 0.0f : -INFINITY); }
+__device__ __forceinline__ __nv_bfloat16 fm_add_mask(__nv_bfloat16 x, bool allowed) {
+    return __float2bfloat16_rn(__bfloat162float(x) + (allowed ? 0.0f : -INFINITY));
+}
+__device__ __forceinline__ __half fm_add_mask(__half x, bool allowed) {
+    return __float2half_rn(__half2float(x) + (allowed ? 0.0f : -INFINITY));
+}
+
+// header value hdr[d] + matches of digit d below `off` in a staged cell (8 x uint4 in smem)
+__device__ __forceinline__ uint32_t fm_rank_staged(const uint4 *cell, uint32_t d, int off) {
+    uint32_t v = reinterpret_cast<const uint32_t *>(cell)[d];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int nb = off - 32 * g;
+        if (nb > 0) v += __popc(fm_match(cell[4 + g], d) & fm_below(nb));
+    }
+    return v;
+}
+
+// DT: FMIDX_F32/BF16/F16, or 3 = bitmap/counts only.   VECTOR: 16-byte accesses are legal.
+template <int DT, bool VECTOR>
+__global__ void __launch_bounds__(MASK_THREADS)
+k_mask(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict__ ep, int64_t shift, uint32_t vocab,
+       const void *logits_v, void *out_v, int64_t row_stride,
+       const int32_t *__restrict__ override_tok, int32_t always_allow, const uint32_t *__restrict__ extra,
+       uint32_t n_extra, uint32_t B, uint32_t *__restrict__ mask_out, uint32_t *__restrict__ counts_out) {
+    __shared__ uint32_t bm[SLICE / 32];
+    __shared__ uint32_t fr[2][MAXF][3];
+    __shared__ uint32_t fcount[2];
+    __shared__ uint4 stage[MASK_THREADS / 16][16];
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t nslices = (vocab + SLICE - 1) / SLICE;
+    const uint32_t b = blockIdx.x / nslices;
+    const uint32_t t0 = (blockIdx.x % nslices) * SLICE;
+    const uint32_t t1 = min(t0 + (uint32_t)SLICE, vocab);
+    const uint32_t mask_words = (vocab + 31u) >> 5;
+
+    // ---- 1. issue the logits loads for this slice ------------------------------------------------
+    constexpr bool HAS_LOGITS = DT != 3;
+    using ET = typename Elem<HAS_LOGITS ? DT : 0>::T;
+    constexpr int VEC = Elem<HAS_LOGITS ? DT : 0>::VEC;
+    constexpr int NV = SLICE / (MASK_THREADS * VEC);  // vectors per thread
+    uint4 regs[HAS_LOGITS && VECTOR ? NV : 1];
+    const ET *row_in = nullptr;
+    ET *row_out = nullptr;
+    if (HAS_LOGITS) {
+        row_in = reinterpret_cast<const ET *>(logits_v) + (size_t)b * row_stride;
+        row_out = reinterpret_cast<ET *>(out_v) + (size_t)b * row_stride;
+        if (VECTOR) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const uint32_t e = t0 + (uint32_t)(i * MASK_THREADS + tid) * VEC;
+                if (e < t1) regs[i] = __ldcs(reinterpret_cast<const uint4 *>(row_in + e));
+            }
+        }
+    }
+
+    // ---- 2. bitmap of the slice --------------------------------------------------------------------
+    for (int w = tid; w < SLICE / 32; w += MASK_THREADS) bm[w] = 0;
+    const int32_t ovr = override_tok ? override_tok[b] : -1;
+    const uint32_t L = ix.levels;
+    // symbol interval of the slice, clipped to the alphabet
+    int64_t a64 = (int64_t)t0 + shift, e64 = (int64_t)t1 + shift;
+    if (a64 < 0) a64 = 0;
+    if (e64 > (int64_t)ix.max_sym + 1) e64 = (int64_t)ix.max_sym + 1;
+    const uint32_t sa = (uint32_t)a64, se = e64 > a64 ? (uint32_t)e64 : (uint32_t)a64;
+    if (tid == 0) {
+        uint64_t s = sp[b], e = ep[b];
+        if (e > ix.n) e = ix.n;  // fm_index.cpp:130-132
+        const bool go = ovr < 0 && s < e && sa < se;  // fm_index.cpp:127,133
+        fr[0][0][0] = (uint32_t)s;
+        fr[0][0][1] = (uint32_t)e;
+        fr[0][0][2] = 0;
+        fcount[0] = go ? 1u : 0u;
+        fcount[1] = 0;
+    }
+    __syncthreads();
+    const int hw = tid >> 4, hl = tid & 15;
+    for (uint32_t l = 0; l < L; ++l) {
+        const int cur = l & 1, nxt = cur ^ 1;
+        const uint32_t n_nodes = fcount[cur];
+        __syncthreads();
+        if (n_nodes == 0) break;
+        if (tid == 0) fcount[nxt] = 0;
+        __syncthreads();
+        const uint4 *lc = ix.cells + l * ix.level_stride;
+        const uint32_t csh = 4u * (L - 1u - l);  // bits below a child's prefix
+        const bool leaf = (l + 1 == L);
+        for (uint32_t base = 0; base < n_nodes; base += MASK_THREADS / 16) {
+            const uint32_t node = base + hw;
+            const bool has = node < n_nodes;
+            uint32_t lo = 0, hi = 0, prefix = 0;
+            if (has) {
+                lo = fr[cur][node][0];
+                hi = fr[cur][node][1];
+                prefix = fr[cur][node][2];
+            }
+            const uint32_t pos = hl < 8 ? lo : hi;
+            if (has) stage[hw][hl] = fm_ldg(lc + (size_t)(pos >> 7) * FMIDX_CELL_U4 + (hl & 7));
+            __syncwarp();
+            uint32_t r_lo = 0, r_hi = 0;
+            if (has) {
+                r_lo = fm_rank_staged(&stage[hw][0], (uint32_t)hl, (int)(lo & 127u));
+                r_hi = fm_rank_staged(&stage[hw][8], (uint32_t)hl, (int)(hi & 127u));
+            }
+            __syncwarp();
+            const uint32_t cp = (prefix << 4) | (uint32_t)hl;
+            const uint64_t c_lo = (uint64_t)cp << csh, c_hi = ((uint64_t)cp + 1) << csh;
+            const bool exists = has && r_hi > r_lo && c_lo < se && c_hi > sa;
+            if (leaf) {
+                if (exists) {  // cp is a symbol of the slice
+                    const uint32_t tk = (uint32_t)((int64_t)cp - shift);
+                    atomicOr(&bm[(tk - t0) >> 5], 1u << ((tk - t0) & 31u));
+                    if (counts_out) counts_out[(size_t)b * vocab + tk] = r_hi - r_lo;
+                }
+            } else {
+                const uint32_t bal = (__ballot_sync(FULL, exists) >> (lane & 16)) & 0xffffu;
+                uint32_t slot = 0;
+                if (hl == 0 && bal) slot = atomicAdd(&fcount[nxt], (uint32_t)__popc(bal));
+                slot = __shfl_sync(FULL, slot, lane & 16);
+                if (exists) {
+                    const uint32_t idx = slot + __popc(bal & ((1u << hl) - 1u));
+                    if (idx < MAXF) {
+                        fr[nxt][idx][0] = r_lo;
+                        fr[nxt][idx][1] = r_hi;
+                        fr[nxt][idx][2] = cp;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    // ---- 3. per-shard masks of the other GPUs, override rows, always-allowed token --------------
+    if (ovr >= 0) {
+        for (int w = tid; w < SLICE / 32; w += MASK_THREADS) bm[w] = 0;
+        __syncthreads();
+        if (tid == 0 && (uint32_t)ovr >= t0 && (uint32_t)ovr < t1) bm[((uint32_t)ovr - t0) >> 5] = 1u << (((uint32_t)ovr - t0) & 31u);
+    } else if (n_extra) {
+        const uint32_t nw = (t1 - t0 + 31u) >> 5;
+        for (uint32_t w = tid; w < nw; w += MASK_THREADS) {
+            uint32_t acc = bm[w];
+            for (uint32_t x = 0; x < n_extra; ++x) acc |= extra[((size_t)x * B + b) * mask_words + (t0 >> 5) + w];
+            bm[w] = acc;
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && always_allow >= 0 && (uint32_t)always_allow >= t0 && (uint32_t)always_allow < t1)
+        bm[((uint32_t)always_allow - t0) >> 5] |= 1u << (((uint32_t)always_allow - t0) & 31u);
+    __syncthreads();
+    if (mask_out) {
+        const uint32_t nw = (t1 - t0 + 31u) >> 5;
+        for (uint32_t w = tid; w < nw; w += MASK_THREADS) mask_out[(size_t)b * mask_words + (t0 >> 5) + w] = bm[w];
+    }
+    // ---- 4. stream the slice of the logits row -----------------------------------------------------
+    if (HAS_LOGITS) {
+        if (VECTOR) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const uint32_t rel = (uint32_t)(i * MASK_THREADS + tid) * VEC;
+                const uint32_t e = t0 + rel;
+                if (e < t1) {
+                    const uint32_t bits = (bm[rel >> 5] >> (rel & 31u)) & ((1u << VEC) - 1u);
+                    ET *x = reinterpret_cast<ET *>(&regs[i]);
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) x[k] = fm_add_mask(x[k], (bits >> k) & 1u);
+                    __stcs(reinterpret_cast<uint4 *>(row_out + e), regs[i]);
+                }
+            }
+        } else {
+            for (uint32_t e = t0 + tid; e < t1; e += MASK_THREADS) {
+                const uint32_t rel = e - t0;
+                row_out[e] = fm_add_mask(row_in[e], (bm[rel >> 5] >> (rel & 31u)) & 1u);
+            }
+        }
+    }
+}
+
+// ---- bitmap -> sparse lists --------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_popcount(const uint32_t *__restrict__ mask, uint32_t mask_words,
+                                                  uint32_t *__restrict__ n_out) {
+    __shared__ uint32_t part[8];
+    const uint32_t b = blockIdx.x;
+    uint32_t s = 0;
+    for (uint32_t w = threadIdx.x; w < mask_words; w += 256) s += __popc(mask[(size_t)b * mask_words + w]);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < 8; ++i) t += part[i];
+        n_out[b] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_compact(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ counts,
+                                                 uint32_t mask_words, uint32_t vocab,
+                                                 const uint64_t *__restrict__ offs, int64_t *__restrict__ tokens,
+                                                 uint64_t *__restrict__ cnts) {
+    __shared__ uint32_t wsum[8];
+    __shared__ uint32_t running;
+    const uint32_t b = blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    const uint64_t out0 = offs[b];
+    for (uint32_t w0 = 0; w0 < mask_words; w0 += 256) {
+        const uint32_t w = w0 + threadIdx.x;
+        uint32_t word = w < mask_words ? mask[(size_t)b * mask_words + w] : 0u;
+        uint32_t c = __popc(word), inc = c;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        uint32_t before = running;
+        for (int i = 0; i < wid; ++i) before += wsum[i];
+        uint32_t idx = before + inc - c;
+        while (word) {
+            const int bit = __ffs(word) - 1;
+            word &= word - 1;
+            const uint32_t tk = w * 32u + (uint32_t)bit;
+            tokens[out0 + idx] = (int64_t)tk;
+            if (cnts) cnts[out0 + idx] = counts ? (uint64_t)counts[(size_t)b * vocab + tk] : 0ull;
+            ++idx;
+        }
+        __syncthreads();
+        if (threadIdx.x == 255) running = before + inc;
+        __syncthreads();
+    }
+}
+
+// =================================================================================================
+// K3 / K4: LF walks.  One octet per walker; an LF step is `levels` access+rank probes.
+// =================================================================================================
+__device__ __forceinline__ uint32_t fm_lf8(const FmDev &ix, uint32_t row, int sub, bool act, uint32_t &sym_out) {
+    uint32_t pos = row, c = 0;
+    for (uint32_t l = 0; l < ix.levels; ++l) {
+        uint32_t dig;
+        pos = fm_access_step8(ix.cells + l * ix.level_stride, pos, sub, act, dig);
+        c = (c << 4) | dig;
+    }
+    sym_out = c;
+    return act ? ix.D[c <= ix.max_sym ? c : 0u] + pos : 0u;
+}
+
+__global__ void __launch_bounds__(256) k_locate_full(FmDev ix, const uint64_t *__restrict__ rows, size_t n,
+                                                     uint64_t *__restrict__ pos) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t r = rows[i];
+    pos[i] = r >= ix.n ? ~0ull : (uint64_t)ix.sa_samples[r];  // fm_index.cpp:170
+}
+
+__global__ void __launch_bounds__(128) k_locate(FmDev ix, const uint64_t *__restrict__ rows, size_t n,
+                                                uint64_t *__restrict__ out) {
+    const int sub = threadIdx.x & 7;
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const bool valid = i < n;
+    uint64_t r64 = valid ? rows[i] : 0;
+    bool act = valid && r64 < ix.n;
+    uint32_t row = act ? (uint32_t)r64 : 0u, steps = 0;
+    uint64_t result = ~0ull;  // fm_index.cpp:170 : (size_type)-1
+    while (__any_sync(FULL, act)) {
+        if (act) {
+            const uint2 m = __ldg(ix.sa_marks + (row >> 5));
+            if ((m.y >> (row & 31u)) & 1u) {
+                result = (uint64_t)ix.sa_samples[m.x + __popc(m.y & ((1u << (row & 31u)) - 1u))] + steps;
+                act = false;
+            }
+        }
+        uint32_t sym;
+        const uint32_t nrow = fm_lf8(ix, row, sub, act, sym);
+        if (act) {
+            row = nrow;
+            ++steps;
+        }
+    }
+    if (valid && sub == 0) out[i] = result;
+}
+
+// isa[p] from text-order samples, then emit BWT[row], row = LF(row), ...
+__global__ void __launch_bounds__(128) k_extract(FmDev ix, const uint64_t *__restrict__ begins,
+                                                 const uint64_t *__restrict__ ends, size_t n, uint64_t max_len,
+                                                 uint64_t *__restrict__ out, uint64_t *__restrict__ lens) {
+    const int sub = threadIdx.x & 7;
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const bool valid = i < n;
+    uint64_t begin = 0, end = 0;
+    if (valid) {
+        begin = begins[i];
+        end = ends[i];
+        if (end > ix.n) end = ix.n;  // fm_index.cpp:178
+    }
+    uint64_t m = (valid && end > begin) ? end - begin : 0;  // fm_index.cpp:177
+    if (m > max_len) m = max_len;
+    uint32_t row = 0, walk = 0;
+    if (m) {
+        const uint32_t p = (uint32_t)(end - 1);
+        uint64_t q = ((uint64_t)p + ix.isa_dens - 1) / ix.isa_dens * ix.isa_dens;
+        if (q >= ix.n) {
+            q = (uint64_t)ix.n - 1;  // ISA[n-1] = 0
+            row = 0;
+        } else {
+            row = ix.isa_samples[q / ix.isa_dens];
+        }
+        walk = (uint32_t)(q - p);
+    }
+    uint64_t total = (uint64_t)walk + m, k = 0;
+    while (__any_sync(FULL, k < total)) {
+        const bool act = k < total;
+        uint32_t sym;
+        const uint32_t nrow = fm_lf8(ix, row, sub, act, sym);
+        if (act) {
+            if (k >= walk && sub == 0) out[i * max_len + (k - walk)] = sym;
+            row = nrow;
+            ++k;
+        }
+    }
+    if (valid && sub == 0) lens[i] = m;
+}
+
+// resident-text fast path: extract_text(begin,end)[k] = T[(end-2-k) mod n]
+__global__ void __launch_bounds__(256) k_extract_text(FmDev ix, const uint64_t *__restrict__ begins,
+                                                      const uint64_t *__restrict__ ends, size_t n, uint64_t max_len,
+                                                      uint64_t *__restrict__ out, uint64_t *__restrict__ lens) {
+    const size_t i = blockIdx.x;
+    uint64_t begin = begins[i], end = ends[i];
+    if (end > ix.n) end = ix.n;
+    uint64_t m = end > begin ? end - begin : 0;
+    if (m > max_len) m = max_len;
+    for (uint64_t k = threadIdx.x; k < m; k += blockDim.x) {
+        const uint64_t p = (end + (uint64_t)ix.n - 2 - k) % ix.n;
+        out[i * max_len + k] = ix.text[p];
+    }
+    if (threadIdx.x == 0) lens[i] = m;
+}
+
+}  // namespace
+
+// =================================================================================================
+// launchers
+// =================================================================================================
+static int check_ready(fmidx *h) {
+    if (!h || !h->ready) {
+        fm_set_error("index is not initialised");
+        return FMIDX_ESTATE;
+    }
+    return FMIDX_OK;
+}
+
+int fm_launch_search(fmidx *h, const int32_t *d_toks, const int64_t *d_offs, size_t B, int64_t shift, uint64_t *d_sp,
+                     uint64_t *d_ep, int raw, cudaStream_t s) {
+    FM_TRY(check_ready(h));
+    if (B == 0) return FMIDX_OK;
+    if (B > 0x0FFFFFFFull) { fm_set_error("batch too large"); return FMIDX_EINVAL; }
+    const unsigned grid = (unsigned)((B * 16 + 127) / 128);
+    if (raw) FM_LAUNCH(k_search<true>, grid, 128, 0, s, h->dev, d_toks, d_offs, (uint32_t)B, shift, d_sp, d_ep);
+    else FM_LAUNCH(k_search<false>, grid, 128, 0, s, h->dev, d_toks, d_offs, (uint32_t)B, shift, d_sp, d_ep);
+    FM_CUDA(cudaGetLastError());
+    return FMIDX_OK;
+}
+
+int fm_launch_step(fmidx *h, const uint64_t *d_sym, const uint64_t *d_lo, const uint64_t *d_hi, size_t B,
+                   uint64_t *d_sp, uint64_t *d_ep, cudaStream_t s) {
+    FM_TRY(check_ready(h));
+    if (B == 0) return FMIDX_OK;
+    if (B > 0x0FFFFFFFull) { fm_set_error("batch too large"); return FMIDX_EINVAL; }
+    FM_LAUNCH(k_step, (unsigned)((B * 16 + 127) / 128), 128, 0, s, h->dev, d_sym, d_lo, d_hi, (uint32_t)B, d_sp, d_ep);
+    FM_CUDA(cudaGetLastError());
+    return FMIDX_OK;
+}
+
+int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, int64_t shift, uint32_t vocab,
+                   const void *d_logits, void *d_out, int dtype, int64_t row_stride, const int32_t *d_override,
+                   int32_t always_allow, const uint32_t *d_extra, uint32_t n_extra, uint32_t *d_mask,
+                   uint32_t *d_counts, cudaStream_t s) {
+    FM_TRY(check_ready(h));
+    if (B == 0 || vocab == 0) return FMIDX_OK;
+    const size_t nblk = (size_t)((vocab + SLICE - 1) / SLICE) * B;
+    if (nblk > 0x7FFFFFFFull) { fm_set_error("mask batch too large: split the call"); return FMIDX_EINVAL; }
+    const unsigned grid = (unsigned)nblk;
+    const bool has = d_logits != nullptr;
+    if (has && !d_out) { fm_set_error("d_out is NULL"); return FMIDX_EINVAL; }
+    if (!has) dtype = 3;
+    auto aligned = [&](int esz) {
+        const int vec = 16 / esz;
+        return ((uintptr_t)d_logits % 16 == 0) && ((uintptr_t)d_out % 16 == 0) && (row_stride % vec == 0) &&
+               (vocab % vec == 0);
+    };
+#define FM_MASK_CASE(DT, VECT)                                                                                     \
+    FM_LAUNCH((k_mask<DT, VECT>), grid, MASK_THREADS, 0, s, h->dev, d_sp, d_ep, shift, vocab, d_logits, d_out,     \
+              row_stride, d_override, always_allow, d_extra, n_extra, (uint32_t)B, d_mask, d_counts)
+    switch (dtype) {
+        case FMIDX_F32: if (aligned(4)) FM_MASK_CASE(FMIDX_F32, true); else FM_MASK_CASE(FMIDX_F32, false); break;
+        case FMIDX_BF16: if (aligned(2)) FM_MASK_CASE(FMIDX_BF16, true); else FM_MASK_CASE(FMIDX_BF16, false); break;
+        case FMIDX_F16: if (aligned(2)) FM_MASK_CASE(FMIDX_F16, true); else FM_MASK_CASE(FMIDX_F16, false); break;
+        case 3: FM_MASK_CASE(3, false); break;
+        default: fm_set_error("unknown logits dtype %d", dtype); return FMIDX_EINVAL;
+    }
+#undef FM_MASK_CASE
+    FM_CUDA(cudaGetLastError());
+    return FMIDX_OK;
+}
+
+int fm_launch_popcount(fmidx *h, const uint32_t *d_mask, size_t B, uint32_t vocab, uint32_t *d_n, cudaStream_t s) {
+    (void)h;
+    if (B == 0) return FMIDX_OK;
+    FM_LAUNCH(k_popcount, (unsigned)B, 256, 0, s, d_mask, (vocab + 31u) >> 5, d_n);
+    FM_CUDA(cudaGetLastError());
+    return FMIDX_OK;
+}
+
+int fm_launch_compact(fmidx *h, const uint32_t *d_mask, const uint32_t *d_counts, size_t B, uint32_t vocab,
+                      const uint64_t *d_offs, int64_t *d_tokens, uint64_t *d_cnts, cudaStream_t s) {
+    (void)h;
+    if (B == 0) return FMIDX_OK;
+    FM_LAUNCH(k_compact, (unsigned)B, 256, 0, s, d_mask, d_counts, (vocab + 31u) >> 5, vocab, d_offs, d_tokens, d_cnts);
+    FM_CUDA(cudaGetLastError());
+    return FMIDX_OK;
+}
+
+int fm_launch_locate(fmidx *h, const uint64_t *d_rows, size_t n, uint64_t *d_pos, cudaStream_t s) {
+    FM_TRY(check_ready(h));
+    if (n == 0) return FMIDX_OK;
+    if (h->dev.sa_dens == 1) FM_LAUNCH(k_locate_full, (unsigned)((n + 255) / 256), 256, 0, s, h->dev, d_rows, n, d_pos);
+    else FM_LAUNCH(k_locate, (unsigned)((n * 8 + 127) / 128), 128, 0, s, h->dev, d_rows, n, d_pos);
+    FM_CUDA(cudaGetLastError());
+    return FMIDX_OK;
+}
+
+int fm_launch_extract(fmidx *h, const uint64_t *d_begin, const uint64_t *d_end, size_t n, uint64_t max_len,
+                      uint64_t *d_out, uint64_t *d_len, cudaStream_t s) {
+    FM_TRY(check_ready(h));
+    if (n == 0) return FMIDX_OK;
+    if (h->dev.text) FM_LAUNCH(k_extract_text, (unsigned)n, 256, 0, s, h->dev, d_begin, d_end, n, max_len, d_out, d_len);
+    else FM_LAUNCH(k_extract, (unsigned)((n * 8 + 127) / 128), 128, 0, s, h->dev, d_begin, d_end, n, max_len, d_out, d_len);
+    FM_CUDA(cudaGetLastError());
+    return FMIDX_OK;
+}

@@ -1,0 +1,146 @@
+/*
+ * fmidx.h -- C ABI of libfmidx.so: the B200-native FM-index query path.
+ *
+ * Drop-in boundary for the SWIG + sdsl-lite binding of the reference
+ * (cpp_modules_linux/fm_index.i:7-21 exporting cpp_modules_linux/fm_index.hpp:20-44).
+ * Plain pointers and sizes only; no exceptions and no torch types cross this boundary.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative FMIDX_E* code on failure;
+ *     fmidx_last_error() returns a thread-local message for the last failure.
+ *   - "host" pointers are ordinary CPU memory, "d_" pointers are CUDA device pointers on the
+ *     index's device; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - batched device entry points only ENQUEUE work on `stream`; they do not synchronise.
+ *   - rows / positions are uint64_t at the ABI like the reference's `unsigned long`
+ *     (fm_index.hpp:16-18); one index holds fewer than 2^32 symbols (shard larger corpora).
+ *   - there is NO CPU fallback: without a CUDA device every call fails with FMIDX_ECUDA.
+ */
+#ifndef FMIDX_H
+#define FMIDX_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fmidx fmidx_t;
+
+#define FMIDX_OK 0
+#define FMIDX_EINVAL (-1)  /* bad argument */
+#define FMIDX_ECUDA (-2)   /* CUDA runtime error / no device */
+#define FMIDX_EIO (-3)     /* file error */
+#define FMIDX_ESTATE (-4)  /* index not initialised */
+#define FMIDX_ERANGE (-5)  /* output buffer too small / symbol too large */
+#define FMIDX_EZERO (-6)   /* text contains the reserved symbol 0 (sdsl construct rejects it) */
+
+#define FMIDX_F32 0
+#define FMIDX_BF16 1
+#define FMIDX_F16 2
+
+const char *fmidx_last_error(void);
+int fmidx_abi_version(void);
+
+/* ---- lifecycle: FMIndex::FMIndex / ~FMIndex (fm_index.cpp:27-31) ------------------------- */
+int fmidx_new(int device, fmidx_t **out);
+void fmidx_free(fmidx_t *h);
+/* build options, set before initialize/load: sa_dens 1 = full SA resident (locate is one
+ * gather), >1 = text-order SA samples (reference default 32, csa_wt_int<>); isa_dens likewise
+ * (reference default 64); keep_text keeps the symbol text resident so extract is a gather. */
+int fmidx_set_options(fmidx_t *h, uint32_t sa_dens, uint32_t isa_dens, int keep_text);
+
+/* ---- build: FMIndex::initialize (fm_index.cpp:33-41), initialize_from_file (:43-48) ------- */
+int fmidx_initialize(fmidx_t *h, const uint64_t *data, size_t n);
+int fmidx_initialize_from_file(fmidx_t *h, const char *path, int width);
+/* same, text already on the device as u32 symbols (synthetic corpora generated on the GPU) */
+int fmidx_initialize_device(fmidx_t *h, const uint32_t *d_symbols, size_t n, void *stream);
+
+/* ---- persistence: FMIndex::save (fm_index.cpp:196-199), load_FMIndex (:201-209) ----------- */
+int fmidx_save(fmidx_t *h, const char *path);
+int fmidx_load(const char *path, int device, fmidx_t **out);
+
+/* ---- scalar queries, host in/out, synchronous --------------------------------------------- */
+/* FMIndex::size (fm_index.cpp:50-52) */
+int fmidx_size(fmidx_t *h, uint64_t *out);
+/* FMIndex::backward_search_step (fm_index.cpp:67-97): inclusive [low,high] in, half-open out,
+ * (0,0) when invalid/empty */
+int fmidx_backward_search_step(fmidx_t *h, uint64_t symbol, uint64_t low, uint64_t high, uint64_t out[2]);
+/* FMIndex::backward_search_multi (fm_index.cpp:55-65): returns (l, r+1) with no guards */
+int fmidx_backward_search_multi(fmidx_t *h, const uint64_t *query, size_t n, uint64_t out[2]);
+/* FMIndex::distinct (fm_index.cpp:99-117): ascending symbols of BWT[low,high) */
+int fmidx_distinct(fmidx_t *h, uint64_t low, uint64_t high, uint64_t *out, size_t cap, size_t *k);
+/* FMIndex::distinct_count (fm_index.cpp:119-144): interleaved [s0,c0,s1,c1,...]; *k = #u64 */
+int fmidx_distinct_count(fmidx_t *h, uint64_t low, uint64_t high, uint64_t *out, size_t cap, size_t *k);
+/* FMIndex::distinct_count_multi (fm_index.cpp:146-166): ranges in one device batch; interleaved
+ * lists concatenated in `out`, list r occupying out[offsets[r] .. offsets[r+1]).  If cap is too
+ * small returns FMIDX_ERANGE with offsets[nr] = required size. */
+int fmidx_distinct_count_multi(fmidx_t *h, const uint64_t *lows, const uint64_t *highs, size_t nr,
+                               uint64_t *out, size_t cap, uint64_t *offsets);
+/* FMIndex::locate (fm_index.cpp:168-172): SA[row], or 2^64-1 when row >= size */
+int fmidx_locate(fmidx_t *h, uint64_t row, uint64_t *out);
+/* FMIndex::extract_text (fm_index.cpp:174-194), as written (starts from isa[end-1]) */
+int fmidx_extract_text(fmidx_t *h, uint64_t begin, uint64_t end, uint64_t *out, size_t cap, size_t *k);
+
+/* ---- batched device entry points (the hot path) -------------------------------------------- */
+/* index.FMIndex.get_range (index.py:103-114) for B ragged prefixes: prefix b is
+ * d_toks[d_offs[b] .. d_offs[b+1]); symbols are token + shift.  d_sp/d_ep receive [sp,ep). */
+int fmidx_search_batch(fmidx_t *h, const int32_t *d_toks, const int64_t *d_offs, size_t B, int64_t shift,
+                       uint64_t *d_sp, uint64_t *d_ep, void *stream);
+/* B independent FMIndex::backward_search_step calls (incremental decoding: one LF step per
+ * beam per generated token instead of re-searching the history). Inclusive highs in. */
+int fmidx_step_batch(fmidx_t *h, const uint64_t *d_symbols, const uint64_t *d_lows, const uint64_t *d_highs,
+                     size_t B, uint64_t *d_sp, uint64_t *d_ep, void *stream);
+/* index.FMIndex.get_distinct_count_multi (index.py:161-174) as bitmaps: for each half-open
+ * range, bit v of row b of d_mask ([B, ceil(vocab/32)] u32) is set iff symbol v+shift occurs in
+ * BWT[sp,ep) and 0 <= v < vocab (the sentinel and symbols < shift are dropped like index.py's
+ * `d > 0` filter).  d_counts (optional, [B, vocab] u32) receives the occurrence count at every
+ * SET position (other entries are left untouched). */
+int fmidx_distinct_mask_batch(fmidx_t *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, int64_t shift,
+                              uint32_t vocab, uint32_t *d_mask, uint32_t *d_counts, void *stream);
+/* Fused constrained-decoding step (document_constrained_generation_vllm.py:52,105-137):
+ *   out[b,v] = logits[b,v] + (v in S_b ? 0.0 : -inf)
+ * S_b = distinct next tokens of [sp_b,ep_b); replaced by {override_tok[b]} when
+ * d_override_tok != NULL and override_tok[b] >= 0 (the eos/pad/stop_at_count rows); token
+ * `always_allow` (>= 0) is additionally allowed in every row (always_allow_eos).
+ * d_extra_masks (optional): n_extra bitmaps [n_extra][B][ceil(vocab/32)] OR-ed into S_b (the
+ * per-shard masks gathered from the other GPUs).  d_out may alias d_logits (in place).
+ * row_stride in elements.  d_mask_out (optional) receives the final bitmap S_b. */
+int fmidx_mask_logits(fmidx_t *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, int64_t shift,
+                      uint32_t vocab, const void *d_logits, void *d_out, int dtype, int64_t row_stride,
+                      const int32_t *d_override_tok, int32_t always_allow, const uint32_t *d_extra_masks,
+                      uint32_t n_extra, uint32_t *d_mask_out, void *stream);
+/* bitmap + counts -> sparse ascending (token,count) lists (index.py:161-174 return shape).
+ * d_list_offsets [B+1] must hold the exclusive prefix sums of the per-row popcounts, which
+ * fmidx_mask_popcount computes into d_n ([B] u32). */
+int fmidx_mask_popcount(fmidx_t *h, const uint32_t *d_mask, size_t B, uint32_t vocab, uint32_t *d_n, void *stream);
+int fmidx_mask_compact(fmidx_t *h, const uint32_t *d_mask, const uint32_t *d_counts, size_t B, uint32_t vocab,
+                       const uint64_t *d_list_offsets, int64_t *d_tokens, uint64_t *d_cnts, void *stream);
+/* FMIndex::locate for n rows */
+int fmidx_locate_batch(fmidx_t *h, const uint64_t *d_rows, size_t n, uint64_t *d_pos, void *stream);
+/* FMIndex::extract_text for n (begin,end) pairs; row i of d_out ([n, max_len] u64) receives
+ * min(len_i, max_len) symbols, d_len[i] the count */
+int fmidx_extract_batch(fmidx_t *h, const uint64_t *d_begin, const uint64_t *d_end, size_t n, uint64_t max_len,
+                        uint64_t *d_out, uint64_t *d_len, void *stream);
+
+/* ---- host-buffer batch calls (what a non-CUDA caller binds; copies are inside the call) ---- */
+int fmidx_search_host(fmidx_t *h, const int32_t *toks, const int64_t *offs, size_t B, int64_t shift,
+                      uint64_t *sp, uint64_t *ep);
+/* search + distinct-token bitmaps in one call; mask [B, ceil(vocab/32)] may be NULL */
+int fmidx_query_host(fmidx_t *h, const int32_t *toks, const int64_t *offs, size_t B, int64_t shift,
+                     uint32_t vocab, uint64_t *sp, uint64_t *ep, uint32_t *mask);
+int fmidx_locate_host(fmidx_t *h, const uint64_t *rows, size_t n, uint64_t *pos);
+
+/* ---- introspection -------------------------------------------------------------------------- */
+/* info[0]=size n, [1]=levels, [2]=max_sym, [3]=sa_dens, [4]=isa_dens, [5]=device bytes,
+ * [6]=cell bytes per level, [7]=keep_text */
+int fmidx_info(fmidx_t *h, uint64_t info[8]);
+/* copy the suffix array / BWT of the last build to the host (testing the builder); the SA is
+ * only available when sa_dens == 1 */
+int fmidx_debug_copy_sa(fmidx_t *h, uint32_t *out, size_t cap);
+/* number of kernels this library has launched in this process (bench.py gpu_launches) */
+uint64_t fmidx_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
