@@ -1,0 +1,449 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the FM-index query path (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--tokens 100000000] [--batch 4096]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One STEP = one batch of `--batch` ragged prefixes (length 1..32, substrings of corpus documents)
+pushed through the hot path on a device-resident index of a synthetic `--tokens`-token corpus
+(vocab 128,256): K1 batched backward search -> [sp,ep), then K2 distinct-next-token enumeration
+-> one 128,256-bit vocab mask per prefix.  `value` = prefixes/s with inputs resident in HBM;
+`e2e` = the same through the host-buffer C-ABI call (H2D of the prefixes, D2H of ranges and the
+per-prefix distinct counts inside the timed region).  Multi-GPU (N>1): the corpus is sharded by
+document, one 100M-token shard per GPU (weak scaling), prefixes are replicated, per-shard masks
+are OR-reduced with an all-to-all over NCCL so that rank r ends up owning the final masks of
+its 1/N of the prefixes.
+
+--impl reference times the CPU oracle (oracle/fm_oracle.c: sdsl-semantics restatement; the real
+reference needs sdsl-lite and cannot be built here) on all host threads on the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+VOCAB, EOS, SHIFT = 128256, 128009, 10
+BYTES_PER_SEARCH_STEP = 1088      # 2 boundaries x 17 levels x 32-B rank cell
+MASK_BYTES = 16032                # one 128,256-bit vocab mask
+N_QUERY_SETS = 8                  # distinct prefix batches rotated through the timed steps
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons during the timed region (pynvml)."""
+
+    def __init__(self, dev):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(dev)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv = None
+            log("clock sampling unavailable:", e)
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10, "display_clock_setting": 0x100}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def build_workload(args, rank, device):
+    """Synthetic corpus shard + query batches for this rank."""
+    from fm_index_constrained_decoding_b200 import synth
+    # every rank owns a different 100M-token shard (seed differs); queries come from shard 0's
+    # generator on every rank (replicated prefixes) so rank 0's positives are real matches there
+    toks, beg = synth.zipf_corpus(args.tokens, seed=1000 * rank, device=device)
+    q_src, q_beg = (toks, beg) if rank == 0 else synth.zipf_corpus(args.tokens, seed=0, device=device)
+    qsets = [synth.sample_queries(q_src, args.batch, seed=100 + i, beginnings=q_beg) for i in range(N_QUERY_SETS)]
+    del q_src
+    return toks, beg, qsets
+
+
+def reversed_symbols(toks, beg):
+    """The text handed to FMIndex::initialize: per-document reversal + SHIFT (index.py:52,62)."""
+    n = toks.numel()
+    pos = torch.arange(n, device=toks.device, dtype=torch.int64)
+    doc = torch.searchsorted(beg, pos, right=True) - 1
+    src = beg[doc] + beg[doc + 1] - 1 - pos
+    return (toks.long()[src] + SHIFT).to(torch.int32)
+
+
+def oracle_from_gpu_sa(toks, beg, device_index):
+    """CPU oracle over the SAME corpus.  Suffix-sorting 100M tokens on one host core would take
+    longer than the whole bench, so the oracle's structures are built from the suffix array the
+    GPU builder produced (the oracle's own SA-IS is cross-checked against it in tests/)."""
+    from fm_index_constrained_decoding_b200 import _native, fm_index
+    from oracle.oracle import NativeOracle
+    sym = reversed_symbols(toks, beg)
+    tmp = fm_index.FMIndex(device=device_index, sa_dens=1, isa_dens=1 << 20)
+    _native.check(_native.lib().fmidx_initialize_device(tmp._h, C.c_void_p(sym.data_ptr()), sym.numel(),
+                                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    sa = np.empty(sym.numel() + 1, dtype=np.uint32)
+    _native.check(_native.lib().fmidx_debug_copy_sa(tmp._h, sa.ctypes.data_as(C.c_void_p), sa.size))
+    del tmp
+    text = np.concatenate([sym.cpu().numpy().astype(np.uint32), np.zeros(1, np.uint32)])
+    o = NativeOracle()
+    o.initialize_from_sa(text, sa)
+    return o
+
+
+def cpu_step(o, toks_np, offs_np, nthreads):
+    t0 = time.perf_counter()
+    o.query_batch(toks_np, offs_np, shift=SHIFT, want_mask=True, vocab=VOCAB, nthreads=nthreads)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    if not torch.cuda.is_available():
+        print(json.dumps({"impl": "reference", "unavailable": "needs the GPU-built suffix array of the 100M-token corpus"}))
+        return
+    device = torch.device("cuda", 0)
+    torch.cuda.set_device(device)
+    os.environ.setdefault("FMIDX_DEVICE", "0")
+    nthreads = os.cpu_count() or 1
+    toks, beg, qsets = build_workload(args, 0, device)
+    t0 = time.time()
+    o = oracle_from_gpu_sa(toks, beg, 0)
+    log("oracle built in %.1fs" % (time.time() - t0))
+    # bounded sample: each step = the first `cpu_batch` prefixes of the step's batch
+    cpu_batch = min(args.batch, args.cpu_batch)
+    host = []
+    for q, offs in qsets:
+        qn, on = q.cpu().numpy(), offs.cpu().numpy()
+        host.append((qn[:on[cpu_batch]].copy(), on[:cpu_batch + 1].copy()))
+    for w in range(args.warmup):
+        cpu_step(o, *host[w % len(host)], nthreads)
+    t = 0.0
+    for k in range(args.steps):
+        t += cpu_step(o, *host[k % len(host)], nthreads)
+    value = cpu_batch * args.steps / t
+    line = {
+        "impl": "reference", "metric": "prefix_queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": workload_config(args, cpu_batch),
+        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": nthreads, "kind": "port",
+                         "sample": "%d of the %d prefixes of each step (search + distinct-token mask), oracle/fm_oracle.c "
+                                   "(sdsl-semantics restatement, not sdsl-lite), pthread pool" % (cpu_batch, args.batch)},
+        "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, batch):
+    return {"workload": "configs[1]: synthetic %dM-token corpus per GPU, vocab 128256, batch %d prefixes of length 1-32: "
+                        "backward search + distinct next-token mask" % (args.tokens // 1_000_000, batch),
+            "tokens_per_gpu": args.tokens, "batch": batch, "prefix_len": "U{1..32} clipped at document end",
+            "corpus": "Zipf(1.1) token ids, docs U[64,1024] ending in EOS 128009, 1% planted repeats",
+            "l2": "index (>=5x L2) larger than L2; %d distinct prefix batches rotated" % N_QUERY_SETS,
+            "sharding": "by document, one shard per GPU, prefixes replicated, masks OR-reduced (all-to-all + OR)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--tokens", type=int, default=100_000_000)
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--cpu-batch", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the FM-index path has no CPU fallback")
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    os.environ["FMIDX_DEVICE"] = str(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    from fm_index_constrained_decoding_b200 import FMIndex, _native
+    L = _native.lib()
+    t0 = time.time()
+    toks, beg, qsets = build_workload(args, rank, device)
+    torch.cuda.synchronize()
+    t_gen = time.time() - t0
+    t0 = time.time()
+    ix = FMIndex(device=local)
+    ix.initialize_from_device_tokens(toks, beg)
+    torch.cuda.synchronize()
+    t_build = time.time() - t0
+    info = ix.info()
+    log("rank %d: corpus %.1fs, index build %.1fs, %d levels, %.0f MB on device" %
+        (rank, t_gen, t_build, info["levels"], info["device_bytes"] / 1e6))
+
+    B = args.batch
+    words = (VOCAB + 31) // 32
+    stream = torch.cuda.current_stream()
+    sptr = C.c_void_p(stream.cuda_stream)
+    sp = torch.empty(B, dtype=torch.int64, device=device)
+    ep = torch.empty(B, dtype=torch.int64, device=device)
+    mask = torch.empty((B, words), dtype=torch.int32, device=device)
+    own = B // world  # prefixes whose final mask this rank owns
+    recv = torch.empty((world, own, words), dtype=torch.int32, device=device) if world > 1 else None
+    final = torch.empty((own, words), dtype=torch.int32, device=device) if world > 1 else None
+    cnt = torch.empty(B, dtype=torch.int64, device=device)
+    cnt_sum = torch.empty(B, dtype=torch.int64, device=device)
+
+    # the OR of the gathered pieces (bitwise_or reduction over dim 0)
+    def or_reduce():
+        acc = recv[0]
+        for r in range(1, world):
+            acc = torch.bitwise_or(acc, recv[r])
+        final.copy_(acc)
+
+    def step_full(k, ev=None):
+        q, offs = qsets[k % N_QUERY_SETS]
+        if ev:
+            ev[0].record(stream)
+        _native.check(L.fmidx_search_batch(ix._h, C.c_void_p(q.data_ptr()), C.c_void_p(offs.data_ptr()), B, SHIFT,
+                                           C.c_void_p(sp.data_ptr()), C.c_void_p(ep.data_ptr()), sptr))
+        if ev:
+            ev[1].record(stream)
+        _native.check(L.fmidx_distinct_mask_batch(ix._h, C.c_void_p(sp.data_ptr()), C.c_void_p(ep.data_ptr()), B, SHIFT, VOCAB,
+                                                  C.c_void_p(mask.data_ptr()), None, sptr))
+        if ev:
+            ev[2].record(stream)
+        if world > 1:
+            dist.all_to_all_single(recv.view(-1), mask[:own * world].view(-1))
+            or_reduce()
+            torch.sub(ep, sp, out=cnt)
+            cnt_sum.copy_(cnt)
+            dist.all_reduce(cnt_sum)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(args.warmup):
+        step_full(w)
+    barrier()
+    launches0 = L.fmidx_launch_count()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    barrier()
+    e_start.record(stream)
+    for k in range(args.steps):
+        step_full(k, evs[k])
+    e_end.record(stream)
+    barrier()
+    total_ms = e_start.elapsed_time(e_end)
+    launches = L.fmidx_launch_count() - launches0
+    if sampler and total_ms < 500:  # region too short for NVML's sampling period: keep the same load running
+        t_end = time.time() + 0.6
+        k = 0
+        while time.time() < t_end:
+            step_full(k)
+            k += 1
+            if k % 50 == 0:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    if clocks is not None and total_ms < 500:
+        clocks["note"] = "timed region %.0f ms is shorter than NVML's sampling period; sampled while the same step kept running" % total_ms
+    t_search = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    t_mask = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    if world > 1:
+        tt = torch.tensor([total_ms, t_search, t_mask], device=device, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms, t_search, t_mask = tt.tolist()
+
+    # ---- algorithmic bytes of one step, from the actual results ------------------------
+    # K1: 1,088 B per executed backward-search step (2 boundaries x 17 levels x 32-B cell: the figure
+    #     SURVEY.md 8(d) fixes; our 5-level layout actually needs <= 2 x 5 x 128 B = 1,280 B of cells).
+    # K2: SURVEY.md 8(d) bounds the enumeration by "visited nodes <= min(2^l, k) per level, 2 cells of
+    #     32 B each" over the 17 binary levels; we count exactly that sum per prefix from the result
+    #     masks (distinct binary prefixes per level), plus the 16,032-B mask each prefix writes.
+    search_steps, enum_nodes_bin, enum_nodes_own, distinct_total = 0, 0, 0, 0
+    for q, offs in qsets:
+        L.fmidx_search_batch(ix._h, C.c_void_p(q.data_ptr()), C.c_void_p(offs.data_ptr()), B, SHIFT,
+                             C.c_void_p(sp.data_ptr()), C.c_void_p(ep.data_ptr()), sptr)
+        L.fmidx_distinct_mask_batch(ix._h, C.c_void_p(sp.data_ptr()), C.c_void_p(ep.data_ptr()), B, SHIFT, VOCAB,
+                                    C.c_void_p(mask.data_ptr()), None, sptr)
+        torch.cuda.synchronize()
+        search_steps += int((offs[1:] - offs[:-1]).sum())  # positive prefixes: every step executes
+        sh = torch.arange(32, device=device, dtype=torch.int32)
+        for r0 in range(0, B, 256):
+            bits = ((mask[r0:r0 + 256].unsqueeze(-1) >> sh) & 1).bool().view(-1, words * 32)[:, :VOCAB]
+            symb = torch.zeros((bits.shape[0], 1 << 17), dtype=torch.bool, device=device)
+            symb[:, SHIFT:SHIFT + VOCAB] = bits  # symbol axis = token + SHIFT
+            distinct_total += int(bits.sum())
+            lvl = symb
+            for l in range(17, 0, -1):          # nodes at binary depth l-1 = distinct (l-1)-bit prefixes
+                lvl = lvl.view(lvl.shape[0], -1, 2).any(-1)
+                enum_nodes_bin += int(lvl.sum())
+                if (17 - (l - 1)) % 4 == 0 or l == 1:  # depths 13,9,5,1,0 = the 16-ary matrix's inner nodes
+                    enum_nodes_own += int(lvl.sum())
+    search_steps /= N_QUERY_SETS
+    enum_nodes_bin /= N_QUERY_SETS
+    enum_nodes_own /= N_QUERY_SETS
+    distinct_total /= N_QUERY_SETS
+    bytes_search = BYTES_PER_SEARCH_STEP * search_steps
+    bytes_mask = 2 * 32 * enum_nodes_bin + MASK_BYTES * B
+    bytes_mask_own = 2 * 128 * enum_nodes_own + MASK_BYTES * B
+    peak, peak_src = measured_peaks()
+    if t_mask >= t_search:
+        dom = {"kernel": "k_mask (distinct-token enumeration -> vocab bitmap)", "bound": "hbm",
+               "achieved": bytes_mask / (t_mask * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "traffic": None,
+               "algorithmic_bytes_per_launch": bytes_mask, "avg_launch_ms": t_mask,
+               "per_unit": "64 B per visited node of the 17-level binary tree (sum over levels of distinct prefixes, "
+                           "SURVEY 8(d)) + 16,032 B mask per prefix",
+               "own_layout_bytes_per_launch": bytes_mask_own, "distinct_symbols_per_launch": distinct_total}
+    else:
+        dom = {"kernel": "k_search (batched backward search)", "bound": "hbm",
+               "achieved": bytes_search / (t_search * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "traffic": None,
+               "algorithmic_bytes_per_launch": bytes_search, "avg_launch_ms": t_search,
+               "per_unit": "1,088 B per executed backward-search step (2 x 17 x 32 B)",
+               "own_layout_bytes_per_launch": 1280 * search_steps}
+    dom["frac"] = dom["achieved"] / peak
+    dom["peak_source"] = peak_src
+    dom["other_kernel_ms"] = {"k_search": t_search, "k_mask": t_mask}
+    dom["search_GBps_algorithmic"] = bytes_search / (t_search * 1e-3) / 1e9
+    dom["mask_GBps_algorithmic"] = bytes_mask / (t_mask * 1e-3) / 1e9
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region -----------------------------
+    e2e = None
+    if rank == 0 or world > 1:
+        hq = [(q.cpu().pin_memory(), offs.cpu().pin_memory()) for q, offs in qsets]
+        hsp = torch.empty(B, dtype=torch.int64).pin_memory()
+        hep = torch.empty(B, dtype=torch.int64).pin_memory()
+        hnd = torch.empty(B, dtype=torch.int32).pin_memory()
+
+        def e2e_step(k):
+            q, offs = hq[k % N_QUERY_SETS]
+            _native.check(L.fmidx_query_host_summary(ix._h, C.c_void_p(q.data_ptr()), C.c_void_p(offs.data_ptr()), B, SHIFT,
+                                                     VOCAB, C.c_void_p(hsp.data_ptr()), C.c_void_p(hep.data_ptr()),
+                                                     C.c_void_p(hnd.data_ptr())))
+        for w in range(args.warmup):
+            e2e_step(w)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            e2e_step(k)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dt], device=device, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt[0])
+        h2d = int(np.mean([q.numel() * 4 + offs.numel() * 8 for q, offs in hq]))
+        e2e = {"value": B * args.steps / dt, "unit": "queries/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": B * (8 + 8 + 4), "ms_per_step": 1e3 * dt / args.steps,
+               "api": "fmidx_query_host_summary (pinned host prefixes in; ranges + distinct-token counts out; masks stay in HBM)"}
+
+    # ---- CPU baseline beside the GPU numbers (rank 0, N=1) ---------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            nthreads = os.cpu_count() or 1
+            t0 = time.time()
+            o = oracle_from_gpu_sa(toks, beg, local)
+            log("oracle built in %.1fs" % (time.time() - t0))
+            q, offs = qsets[0]
+            qn, on = q.cpu().numpy(), offs.cpu().numpy()
+            cb = min(B, args.cpu_batch)
+            qn, on = qn[:on[cb]], on[:cb + 1]
+            # parity spot check of the product against the oracle on this very batch
+            osp, oep, omask, _ = o.query_batch(qn, on, shift=SHIFT, want_mask=True, vocab=VOCAB, nthreads=nthreads)
+            step_full(0)
+            torch.cuda.synchronize()
+            ok = bool((sp[:cb].cpu().numpy().astype(np.uint64) == osp).all() and (ep[:cb].cpu().numpy().astype(np.uint64) == oep).all()
+                      and (mask[:cb].cpu().numpy().view(np.uint32) == omask).all())
+            tt = min(cpu_step(o, qn, on, nthreads) for _ in range(2))
+            t1 = cpu_step(o, qn[:on[256]], on[:257], 1)
+            cpu = {"value": cb / tt, "unit": "queries/s", "cores": nthreads, "kind": "port",
+                   "sample": "one batch of %d prefixes (search + distinct-token mask), best of 2, oracle/fm_oracle.c "
+                             "(sdsl-semantics restatement, not sdsl-lite) on a pthread pool" % cb,
+                   "single_thread_queries_per_sec": 256 / t1, "parity_vs_gpu_on_sample": ok}
+            del o
+        except Exception as e:  # the baseline must never take the bench line down
+            cpu = {"value": None, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
+
+    if rank == 0:
+        value = B * args.steps / (total_ms * 1e-3)
+        line = {
+            "metric": "prefix_queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": workload_config(args, B),
+            "masks_per_sec": value, "roofline": dom, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "index": {"build_s": t_build, "device_mb": info["device_bytes"] / 1e6, "levels": info["levels"],
+                                        "layout": "16-ary wavelet matrix, 128-B cells"},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -37,6 +37,7 @@ SIGNATURES = {
     "fmidx_extract_batch": (C.c_int, [p, p, p, sz, u64, p, p, p]),
     "fmidx_search_host": (C.c_int, [p, p, p, sz, i64, p, p]),
     "fmidx_query_host": (C.c_int, [p, p, p, sz, i64, u32, p, p, p]),
+    "fmidx_query_host_summary": (C.c_int, [p, p, p, sz, i64, u32, p, p, p]),
     "fmidx_locate_host": (C.c_int, [p, p, sz, p]),
     "fmidx_info": (C.c_int, [p, C.POINTER(u64)]),
     "fmidx_debug_copy_sa": (C.c_int, [p, p, sz]),

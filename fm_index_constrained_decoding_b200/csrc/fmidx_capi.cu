@@ -517,34 +517,49 @@ int fmidx_extract_batch(fmidx_t *h, const uint64_t *d_begin, const uint64_t *d_e
 }
 
 // ---- host-buffer batch calls ----------------------------------------------------------------------------
-int fmidx_query_host(fmidx_t *h, const int32_t *toks, const int64_t *offs, size_t B, int64_t shift, uint32_t vocab,
-                     uint64_t *sp, uint64_t *ep, uint32_t *mask) {
+static int query_host_impl(fmidx_t *h, const int32_t *toks, const int64_t *offs, size_t B, int64_t shift, uint32_t vocab,
+                           uint64_t *sp, uint64_t *ep, uint32_t *mask, uint32_t *n_distinct) {
     FM_TRY(enter(h, true));
     if (B == 0) return FMIDX_OK;
     if (!toks || !offs || !sp || !ep) { fm_set_error("null argument"); return FMIDX_EINVAL; }
-    const size_t ntok = (size_t)(offs[B] - offs[0]);
     if (offs[0] != 0) { fm_set_error("offs[0] must be 0"); return FMIDX_EINVAL; }
+    const size_t ntok = (size_t)offs[B];
     const uint32_t words = (vocab + 31) / 32;
+    const bool want_mask = mask || n_distinct;
     cudaStream_t s = h->stream;
-    FM_TRY(fm_scratch(h, h->d_scratch[6], ntok * 4 + 16 + (B + 1) * 8 + B * 16, false));
+    FM_TRY(fm_scratch(h, h->d_scratch[6], ntok * 4 + 16 + (B + 1) * 8 + B * 16 + B * 4, false));
     char *dp = (char *)h->d_scratch[6].p;
     int64_t *d_offs = (int64_t *)dp;
     uint64_t *d_sp = (uint64_t *)(dp + (B + 1) * 8), *d_ep = d_sp + B;
-    int32_t *d_toks = (int32_t *)(d_ep + B);
+    uint32_t *d_n = (uint32_t *)(d_ep + B);
+    int32_t *d_toks = (int32_t *)(d_n + B);
     FM_CUDA(cudaMemcpyAsync(d_offs, offs, (B + 1) * 8, cudaMemcpyHostToDevice, s));
     if (ntok) FM_CUDA(cudaMemcpyAsync(d_toks, toks, ntok * 4, cudaMemcpyHostToDevice, s));
     FM_TRY(fm_launch_search(h, d_toks, d_offs, B, shift, d_sp, d_ep, 0, s));
     uint32_t *d_mask = nullptr;
-    if (mask) {
+    if (want_mask) {
         FM_TRY(fm_scratch(h, h->d_scratch[7], B * (size_t)words * 4, false));
         d_mask = (uint32_t *)h->d_scratch[7].p;
         FM_TRY(fm_launch_mask(h, d_sp, d_ep, B, shift, vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, d_mask, nullptr, s));
+        if (n_distinct) FM_TRY(fm_launch_popcount(h, d_mask, B, vocab, d_n, s));
     }
     FM_CUDA(cudaMemcpyAsync(sp, d_sp, B * 8, cudaMemcpyDeviceToHost, s));
     FM_CUDA(cudaMemcpyAsync(ep, d_ep, B * 8, cudaMemcpyDeviceToHost, s));
     if (mask) FM_CUDA(cudaMemcpyAsync(mask, d_mask, B * (size_t)words * 4, cudaMemcpyDeviceToHost, s));
+    if (n_distinct) FM_CUDA(cudaMemcpyAsync(n_distinct, d_n, B * 4, cudaMemcpyDeviceToHost, s));
     FM_CUDA(cudaStreamSynchronize(s));
     return FMIDX_OK;
+}
+
+int fmidx_query_host(fmidx_t *h, const int32_t *toks, const int64_t *offs, size_t B, int64_t shift, uint32_t vocab,
+                     uint64_t *sp, uint64_t *ep, uint32_t *mask) {
+    return query_host_impl(h, toks, offs, B, shift, vocab, sp, ep, mask, nullptr);
+}
+
+int fmidx_query_host_summary(fmidx_t *h, const int32_t *toks, const int64_t *offs, size_t B, int64_t shift,
+                             uint32_t vocab, uint64_t *sp, uint64_t *ep, uint32_t *n_distinct) {
+    if (!n_distinct) { fm_set_error("n_distinct is NULL"); return FMIDX_EINVAL; }
+    return query_host_impl(h, toks, offs, B, shift, vocab, sp, ep, nullptr, n_distinct);
 }
 
 int fmidx_search_host(fmidx_t *h, const int32_t *toks, const int64_t *offs, size_t B, int64_t shift, uint64_t *sp,

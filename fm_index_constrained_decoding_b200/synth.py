@@ -55,8 +55,10 @@ def zipf_corpus(n_tokens, vocab=VOCAB, seed=0, device="cpu", eos=EOS, doc_min=64
     return toks, beginnings
 
 
-def sample_queries(tokens, n_queries, len_min=1, len_max=32, seed=1, negative_frac=0.0, vocab=VOCAB):
-    """Ragged query batch: each prefix is a substring of the token stream (positive); a fraction
+def sample_queries(tokens, n_queries, len_min=1, len_max=32, seed=1, negative_frac=0.0, vocab=VOCAB, beginnings=None):
+    """Ragged query batch: each prefix is a substring of one document (positive; with
+    `beginnings` the length is clipped at the document end, because the index concatenates the
+    documents REVERSED, so a forward substring crossing a boundary need not occur); a fraction
     has one position replaced by a random token (mostly negative -> early exit).
     Returns (toks int32 [total], offs int64 [n_queries+1]) on tokens.device."""
     dev = tokens.device
@@ -65,6 +67,10 @@ def sample_queries(tokens, n_queries, len_min=1, len_max=32, seed=1, negative_fr
     n = tokens.numel()
     lens = torch.randint(len_min, len_max + 1, (n_queries,), generator=g, device=dev)
     starts = torch.randint(0, max(1, n - len_max), (n_queries,), generator=g, device=dev)
+    if beginnings is not None:
+        beg = beginnings.to(dev)
+        doc_end = beg[torch.searchsorted(beg, starts, right=True)]
+        lens = torch.minimum(lens, doc_end - starts)
     offs = torch.zeros(n_queries + 1, dtype=torch.int64, device=dev)
     offs[1:] = torch.cumsum(lens, 0)
     total = int(offs[-1])

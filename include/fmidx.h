@@ -128,6 +128,10 @@ int fmidx_search_host(fmidx_t *h, const int32_t *toks, const int64_t *offs, size
 /* search + distinct-token bitmaps in one call; mask [B, ceil(vocab/32)] may be NULL */
 int fmidx_query_host(fmidx_t *h, const int32_t *toks, const int64_t *offs, size_t B, int64_t shift,
                      uint32_t vocab, uint64_t *sp, uint64_t *ep, uint32_t *mask);
+/* same, but the masks stay in device memory (where the logits kernel consumes them); the host
+ * receives the ranges and n_distinct[b] = number of distinct next tokens of prefix b */
+int fmidx_query_host_summary(fmidx_t *h, const int32_t *toks, const int64_t *offs, size_t B, int64_t shift,
+                             uint32_t vocab, uint64_t *sp, uint64_t *ep, uint32_t *n_distinct);
 int fmidx_locate_host(fmidx_t *h, const uint64_t *rows, size_t n, uint64_t *pos);
 
 /* ---- introspection -------------------------------------------------------------------------- */

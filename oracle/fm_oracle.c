@@ -306,23 +306,30 @@ static void fmo_build_from_text_sa(fmo_t *f, const i32 *s, const i32 *SA, u64 n)
     /* wt_int: level k bits at [k*n,(k+1)*n); nodes ordered by prefix, stable inside nodes. */
     f->tree_bits = (u64)f->max_level * n;
     f->tree = (u64 *)calloc((size_t)((f->tree_bits + 63) / 64 + 1), sizeof(u64));
-    u64 nb = (u64)1 << f->max_level;
-    u64 *starts = (u64 *)malloc((size_t)(nb + 1) * sizeof(u64));
     for (u32 k = 0; k < f->max_level; k++) {
         u32 shift = f->max_level - 1 - k;
         u64 base = (u64)k * n;
-        for (u64 p = 0; p < n; p++)
-            if ((cur[p] >> shift) & 1) f->tree[(base + p) >> 6] |= 1ULL << ((base + p) & 63);
-        if (k + 1 < f->max_level) {
-            u64 buckets = (u64)1 << (k + 1);
-            memset(starts, 0, (size_t)(buckets + 1) * sizeof(u64));
-            for (u64 p = 0; p < n; p++) starts[(cur[p] >> shift) + 1]++;
-            for (u64 b = 0; b < buckets; b++) starts[b + 1] += starts[b];
-            for (u64 p = 0; p < n; p++) nxt[starts[cur[p] >> shift]++] = cur[p];
-            u32 *tmp = cur; cur = nxt; nxt = tmp;
+        /* nodes of level k are the maximal runs of equal top-k-bit prefix; inside a node the
+         * 0-children keep their order and precede the 1-children (stable partition). */
+        for (u64 s0 = 0; s0 < n;) {
+            u64 pre = (k == 0) ? 0 : (cur[s0] >> (shift + 1));
+            u64 e0 = s0, zeros = 0;
+            while (e0 < n && ((k == 0) ? 0 : (cur[e0] >> (shift + 1))) == pre) {
+                zeros += !((cur[e0] >> shift) & 1);
+                e0++;
+            }
+            u64 zi = s0, oi = s0 + zeros;
+            for (u64 p = s0; p < e0; p++) {
+                if ((cur[p] >> shift) & 1) {
+                    f->tree[(base + p) >> 6] |= 1ULL << ((base + p) & 63);
+                    nxt[oi++] = cur[p];
+                } else nxt[zi++] = cur[p];
+            }
+            s0 = e0;
         }
+        u32 *tmp = cur; cur = nxt; nxt = tmp;
     }
-    free(starts); free(cur); free(nxt);
+    free(cur); free(nxt);
     rank_v_build(f);
 }
 

@@ -315,7 +315,7 @@ def test_large_properties(cuda):
     ix.initialize_from_device_tokens(toks, beg)
     n = toks.numel()
     assert ix.size() == n + 1 and len(ix) == n
-    q, offs = synth.sample_queries(toks, 4096, seed=1)
+    q, offs = synth.sample_queries(toks, 4096, seed=1, beginnings=beg)
     sp, ep = ix.get_range_batch(q, offs)
     assert (ep > sp).all()  # positive queries always match
     # (1) range width == brute-force occurrence count for short patterns (direct scan of the stream)

@@ -28,8 +28,8 @@ def test_zipf_corpus_shape_and_determinism():
 
 
 def test_sample_queries():
-    t, _ = synth.zipf_corpus(20_000, seed=2)
-    q, offs = synth.sample_queries(t, 100, seed=1)
+    t, beg = synth.zipf_corpus(20_000, seed=2)
+    q, offs = synth.sample_queries(t, 100, seed=1, beginnings=beg)
     lens = offs[1:] - offs[:-1]
     assert lens.min() >= 1 and lens.max() <= 32 and offs[-1] == q.numel()
     # positive queries are substrings of the stream
@@ -37,5 +37,8 @@ def test_sample_queries():
     for k in range(5):
         pat = q[offs[k]:offs[k + 1]].tolist()
         assert any(s[i:i + len(pat)] == pat for i in range(len(s) - len(pat) + 1))
-    qn, _ = synth.sample_queries(t, 100, seed=1, negative_frac=0.5)
+    # and never cross a document boundary (EOS can only be the last token)
+    for k in range(100):
+        assert synth.EOS not in q[offs[k]:offs[k + 1] - 1].tolist()
+    qn, _ = synth.sample_queries(t, 100, seed=1, negative_frac=0.5, beginnings=beg)
     assert (qn != q).any()
