@@ -247,20 +247,11 @@ def main():
     ep = torch.empty(B, dtype=torch.int64, device=device)
     mask = torch.empty((B, words), dtype=torch.int32, device=device)
     own = B // world  # prefixes whose final mask this rank owns
-    recv = torch.empty((world, own, words), dtype=torch.int32, device=device) if world > 1 else None
-    final = torch.empty((own, words), dtype=torch.int32, device=device) if world > 1 else None
-    cnt = torch.empty(B, dtype=torch.int64, device=device)
-    cnt_sum = torch.empty(B, dtype=torch.int64, device=device)
+    from fm_index_constrained_decoding_b200 import sharded
+    result = {}
 
-    # the OR of the gathered pieces (bitwise_or reduction over dim 0)
-    def or_reduce():
-        acc = recv[0]
-        for r in range(1, world):
-            acc = torch.bitwise_or(acc, recv[r])
-        final.copy_(acc)
-
-    def step_full(k, ev=None):
-        q, offs = qsets[k % N_QUERY_SETS]
+    def step_full(k, ev=None, q_off=None):
+        q, offs = q_off if q_off is not None else qsets[k % N_QUERY_SETS]
         if ev:
             ev[0].record(stream)
         _native.check(L.fmidx_search_batch(ix._h, C.c_void_p(q.data_ptr()), C.c_void_p(offs.data_ptr()), B, SHIFT,
@@ -272,11 +263,12 @@ def main():
         if ev:
             ev[2].record(stream)
         if world > 1:
-            dist.all_to_all_single(recv.view(-1), mask[:own * world].view(-1))
-            or_reduce()
-            torch.sub(ep, sp, out=cnt)
-            cnt_sum.copy_(cnt)
-            dist.all_reduce(cnt_sum)
+            # OR-reduce-scatter of the per-shard masks (all-to-all + fmidx_mask_or): rank r ends up owning the
+            # final masks of prefixes [r*B/W, (r+1)*B/W); total occurrence counts all-reduced (sum)
+            result["mask"] = sharded.or_reduce_scatter(mask, index=ix)[1]
+            result["count"] = sharded.sum_counts(sp, ep)
+        else:
+            result["mask"] = mask
 
     def barrier():
         if world > 1:
@@ -380,11 +372,30 @@ def main():
         hep = torch.empty(B, dtype=torch.int64).pin_memory()
         hnd = torch.empty(B, dtype=torch.int32).pin_memory()
 
+        dq = [(torch.empty_like(q, device=device), torch.empty_like(offs, device=device)) for q, offs in hq[:1]]
+        n32 = torch.empty(own, dtype=torch.int32, device=device)
+        hcnt = torch.empty(B, dtype=torch.int64).pin_memory()
+
         def e2e_step(k):
             q, offs = hq[k % N_QUERY_SETS]
-            _native.check(L.fmidx_query_host_summary(ix._h, C.c_void_p(q.data_ptr()), C.c_void_p(offs.data_ptr()), B, SHIFT,
-                                                     VOCAB, C.c_void_p(hsp.data_ptr()), C.c_void_p(hep.data_ptr()),
-                                                     C.c_void_p(hnd.data_ptr())))
+            if world == 1:
+                _native.check(L.fmidx_query_host_summary(ix._h, C.c_void_p(q.data_ptr()), C.c_void_p(offs.data_ptr()), B, SHIFT,
+                                                         VOCAB, C.c_void_p(hsp.data_ptr()), C.c_void_p(hep.data_ptr()),
+                                                         C.c_void_p(hnd.data_ptr())))
+                return
+            # N > 1: pinned host prefixes -> device, search + masks + cross-shard exchange, results -> host
+            dtok = torch.empty(q.numel(), dtype=torch.int32, device=device)
+            dtok.copy_(q, non_blocking=True)
+            doff = dq[0][1]
+            doff.copy_(offs, non_blocking=True)
+            step_full(k, q_off=(dtok, doff))
+            _native.check(L.fmidx_mask_popcount(ix._h, C.c_void_p(result["mask"].data_ptr()), own, VOCAB, C.c_void_p(n32.data_ptr()), sptr))
+            hsp.copy_(sp, non_blocking=True)
+            hep.copy_(ep, non_blocking=True)
+            hcnt.copy_(result["count"], non_blocking=True)
+            hnd[:own].copy_(n32, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
         for w in range(args.warmup):
             e2e_step(w)
         barrier()
@@ -399,8 +410,10 @@ def main():
             dt = float(tt[0])
         h2d = int(np.mean([q.numel() * 4 + offs.numel() * 8 for q, offs in hq]))
         e2e = {"value": B * args.steps / dt, "unit": "queries/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": B * (8 + 8 + 4), "ms_per_step": 1e3 * dt / args.steps,
-               "api": "fmidx_query_host_summary (pinned host prefixes in; ranges + distinct-token counts out; masks stay in HBM)"}
+               "d2h_bytes_per_step": B * (8 + 8 + 4) if world == 1 else B * 24 + own * 4, "ms_per_step": 1e3 * dt / args.steps,
+               "api": "fmidx_query_host_summary (pinned host prefixes in; ranges + distinct-token counts out; masks stay in HBM)"
+                      if world == 1 else "pinned host prefixes -> H2D -> fmidx_search_batch + fmidx_distinct_mask_batch -> all-to-all + "
+                      "fmidx_mask_or + all-reduce -> D2H of ranges, total counts and distinct counts of the owned prefixes"}
 
     # ---- CPU baseline beside the GPU numbers (rank 0, N=1) ---------------------------------------------------
     cpu = None

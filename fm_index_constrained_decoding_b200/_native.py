@@ -31,6 +31,7 @@ SIGNATURES = {
     "fmidx_step_batch": (C.c_int, [p, p, p, p, sz, p, p, p]),
     "fmidx_distinct_mask_batch": (C.c_int, [p, p, p, sz, i64, u32, p, p, p]),
     "fmidx_mask_logits": (C.c_int, [p, p, p, sz, i64, u32, p, p, C.c_int, i64, p, i32, p, u32, p, p]),
+    "fmidx_mask_or": (C.c_int, [p, p, u32, sz, p, p]),
     "fmidx_mask_popcount": (C.c_int, [p, p, sz, u32, p, p]),
     "fmidx_mask_compact": (C.c_int, [p, p, p, sz, u32, p, p, p, p]),
     "fmidx_locate_batch": (C.c_int, [p, p, sz, p, p]),

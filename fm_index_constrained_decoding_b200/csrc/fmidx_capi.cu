@@ -105,6 +105,7 @@ void fmidx_free(fmidx_t *h) {
     cudaSetDevice(h->device);
     fm_release_index(h);
     for (auto &b : h->d_scratch) if (b.p) cudaFree(b.p);
+    if (h->mask_ws.p) cudaFree(h->mask_ws.p);
     for (auto &b : h->h_scratch) if (b.p) cudaFreeHost(b.p);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -491,6 +492,12 @@ int fmidx_mask_logits(fmidx_t *h, const uint64_t *d_sp, const uint64_t *d_ep, si
     if (dtype != FMIDX_F32 && dtype != FMIDX_BF16 && dtype != FMIDX_F16) { fm_set_error("unknown dtype %d", dtype); return FMIDX_EINVAL; }
     return fm_launch_mask(h, d_sp, d_ep, B, shift, vocab, d_logits, d_out, dtype, row_stride, d_override_tok, always_allow,
                           d_extra_masks, n_extra, d_mask_out, nullptr, (cudaStream_t)stream);
+}
+
+int fmidx_mask_or(fmidx_t *h, const uint32_t *d_pieces, uint32_t n_pieces, size_t n_words, uint32_t *d_out, void *stream) {
+    FM_TRY(enter(h, false));
+    if (!d_pieces || !d_out) { fm_set_error("null argument"); return FMIDX_EINVAL; }
+    return fm_launch_or(h, d_pieces, n_pieces, n_words, d_out, (cudaStream_t)stream);
 }
 
 int fmidx_mask_popcount(fmidx_t *h, const uint32_t *d_mask, size_t B, uint32_t vocab, uint32_t *d_n, void *stream) {

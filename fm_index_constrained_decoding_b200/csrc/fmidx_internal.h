@@ -55,6 +55,7 @@ struct fmidx {
     size_t dev_bytes = 0;
     cudaStream_t stream = nullptr;  // private stream of the synchronous host-style calls
     FmBuf d_scratch[8];
+    FmBuf mask_ws;               // node tables + work list of the mask kernels
     FmBuf h_scratch[4];
     int sm_count = 148;
 };
@@ -75,6 +76,7 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
                    const void *d_logits, void *d_out, int dtype, int64_t row_stride, const int32_t *d_override,
                    int32_t always_allow, const uint32_t *d_extra, uint32_t n_extra, uint32_t *d_mask,
                    uint32_t *d_counts, cudaStream_t s);
+int fm_launch_or(fmidx *h, const uint32_t *d_pieces, uint32_t n_pieces, size_t n_words, uint32_t *d_out, cudaStream_t s);
 int fm_launch_popcount(fmidx *h, const uint32_t *d_mask, size_t B, uint32_t vocab, uint32_t *d_n, cudaStream_t s);
 int fm_launch_compact(fmidx *h, const uint32_t *d_mask, const uint32_t *d_counts, size_t B, uint32_t vocab,
                       const uint64_t *d_offs, int64_t *d_tokens, uint64_t *d_cnts, cudaStream_t s);

@@ -16,6 +16,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <algorithm>
+
 #include "fmidx_internal.h"
 
 namespace {
@@ -121,17 +123,27 @@ __global__ void __launch_bounds__(128) k_step(FmDev ix, const uint64_t *__restri
 }
 
 // =================================================================================================
-// K2: distinct-symbol enumeration of BWT[sp,ep) restricted to one 4096-token slice of the vocab,
-// into a shared-memory bitmap, fused with the masking of that slice of the beam's logits row.
-// grid = ceil(vocab/4096) * B CTAs (slice-fastest), 128 threads.  The slice's logits are loaded into registers
-// BEFORE the tree walk so the walk's dependent-load latency overlaps the streaming traffic.
-// The walk is a level-synchronous BFS over the 16-ary wavelet matrix, one half-warp per node
-// (octet 0 loads the cell of lo, octet 1 the cell of hi, lane d evaluates child d), pruned to
-// the slice's symbol interval, so slices need no communication and no atomics on global memory.
+// K2: distinct-symbol enumeration of BWT[sp,ep) -> vocab bitmap (+counts), fused with the -inf
+// masking of the beam's logits row.  Two phases:
+//
+//  k_mask_top    one warp per range: descend the top LT = levels-3 levels of the 16-ary matrix
+//                ONCE per range and leave, per range, the dense table of the <= 256 depth-LT nodes
+//                (each covers 4096 symbols = one vocab slice); for the bitmap-only entry point it
+//                also appends the non-empty (range, slice) pairs to a work list, so ranges with a
+//                handful of continuations cost a handful of CTAs instead of vocab/4096.
+//  k_mask_items  persistent CTAs pull (range, slice) items and finish the walk inside the slice;
+//  k_mask_logits one CTA per (beam, slice): issues the slice's logits loads FIRST (registers), then
+//                finishes the walk (its latency overlaps the streaming traffic), ORs the per-shard
+//                masks of the other GPUs, applies override / always-allowed tokens, streams out.
+//
+// Inside a slice: if the seed nodes hold <= 32 BWT positions, one warp resolves them by direct
+// per-position access (no tree bookkeeping at all); otherwise a level-synchronous BFS, one
+// half-warp per node (octet 0 loads the cell of lo, octet 1 the cell of hi, lane d evaluates
+// child d), pruned to the slice's symbol interval.  Slices never communicate.
 // =================================================================================================
 constexpr int SLICE = 4096;        // tokens per CTA
 constexpr int MASK_THREADS = 128;
-constexpr int MAXF = 288;          // frontier capacity: <= SLICE/16 + 2 nodes at the deepest inner level
+constexpr int MAXF = 288;          // BFS frontier capacity: <= SLICE/16 + 2 nodes at the deepest inner level
 
 template <int DT> struct Elem;
 template <> struct Elem<FMIDX_F32> { using T = float; static constexpr int VEC = 4; };
@@ -157,92 +169,219 @@ __device__ __forceinline__ uint32_t fm_rank_staged(const uint4 *cell, uint32_t d
     return v;
 }
 
-// DT: FMIDX_F32/BF16/F16, or 3 = bitmap/counts only.   VECTOR: 16-byte accesses are legal.
-template <int DT, bool VECTOR>
-__global__ void __launch_bounds__(MASK_THREADS)
-k_mask(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict__ ep, int64_t shift, uint32_t vocab,
-       const void *logits_v, void *out_v, int64_t row_stride,
-       const int32_t *__restrict__ override_tok, int32_t always_allow, const uint32_t *__restrict__ extra,
-       uint32_t n_extra, uint32_t B, uint32_t *__restrict__ mask_out, uint32_t *__restrict__ counts_out) {
-    __shared__ uint32_t bm[SLICE / 32];
-    __shared__ uint32_t fr[2][MAXF][3];
-    __shared__ uint32_t fcount[2];
-    __shared__ uint4 stage[MASK_THREADS / 16][16];
+// single-thread access+rank at one level: returns the next-level position of the element AT pos
+__device__ __forceinline__ uint32_t fm_access1(const uint4 *__restrict__ level_cells, uint32_t pos, uint32_t &dig_out) {
+    const uint4 *cell = level_cells + (size_t)(pos >> 7) * FMIDX_CELL_U4;
+    const int off = (int)(pos & 127u), g = off >> 5, t = off & 31;
+    // the header quarter is only known after the digit: fetch all four speculatively so the level
+    // costs one memory round trip (the line is fetched once anyway)
+    const uint4 h0 = fm_ldg(cell), h1 = fm_ldg(cell + 1), h2 = fm_ldg(cell + 2), h3 = fm_ldg(cell + 3);
+    const uint4 p = fm_ldg(cell + 4 + g);
+    const uint32_t dig = ((p.x >> t) & 1u) | (((p.y >> t) & 1u) << 1) | (((p.z >> t) & 1u) << 2) | (((p.w >> t) & 1u) << 3);
+    const uint4 hq = (dig >> 2) == 0 ? h0 : ((dig >> 2) == 1 ? h1 : ((dig >> 2) == 2 ? h2 : h3));
+    uint32_t v = fm_pick(hq, dig & 3u) + __popc(fm_match(p, dig) & ((1u << t) - 1u));
+    for (int g2 = 0; g2 < g; ++g2) v += __popc(fm_match(fm_ldg(cell + 4 + g2), dig));
+    dig_out = dig;
+    return v;
+}
 
-    const int tid = threadIdx.x, lane = tid & 31;
-    const uint32_t nslices = (vocab + SLICE - 1) / SLICE;
-    const uint32_t b = blockIdx.x / nslices;
-    const uint32_t t0 = (blockIdx.x % nslices) * SLICE;
-    const uint32_t t1 = min(t0 + (uint32_t)SLICE, vocab);
-    const uint32_t mask_words = (vocab + 31u) >> 5;
+struct EnumSmem {
+    uint32_t bm[SLICE / 32];
+    uint32_t fr[2][MAXF][3];
+    uint32_t fcount[2];
+    uint32_t width;
+    uint4 stage[MASK_THREADS / 16][16];
+};
 
-    // ---- 1. issue the logits loads for this slice ------------------------------------------------
-    constexpr bool HAS_LOGITS = DT != 3;
-    using ET = typename Elem<HAS_LOGITS ? DT : 0>::T;
-    constexpr int VEC = Elem<HAS_LOGITS ? DT : 0>::VEC;
-    constexpr int NV = SLICE / (MASK_THREADS * VEC);  // vectors per thread
-    uint4 regs[HAS_LOGITS && VECTOR ? NV : 1];
-    const ET *row_in = nullptr;
-    ET *row_out = nullptr;
-    if (HAS_LOGITS) {
-        row_in = reinterpret_cast<const ET *>(logits_v) + (size_t)b * row_stride;
-        row_out = reinterpret_cast<ET *>(out_v) + (size_t)b * row_stride;
-        if (VECTOR) {
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const uint32_t e = t0 + (uint32_t)(i * MASK_THREADS + tid) * VEC;
-                if (e < t1) regs[i] = __ldcs(reinterpret_cast<const uint4 *>(row_in + e));
+// number of depth-l nodes that can hold symbols <= max_sym
+__device__ __host__ __forceinline__ uint32_t fm_nodes_at(uint32_t max_sym, uint32_t levels, uint32_t l) {
+    return (max_sym >> (4u * (levels - l))) + 1u;
+}
+
+// ---- phase A --------------------------------------------------------------------------------------
+// lvl = concatenated dense node tables, level l at offset B * sum_{j<l} P_j, row b = P_l entries.
+__global__ void __launch_bounds__(128)
+k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict__ ep, uint32_t B, uint32_t LT,
+           uint2 *__restrict__ lvl, const int32_t *__restrict__ override_tok, int64_t shift, uint32_t vocab,
+           uint32_t *__restrict__ work_items, uint32_t *__restrict__ work_count) {
+    __shared__ uint4 stage[8][16];
+    const int lane = threadIdx.x & 31, hw = (threadIdx.x >> 4) & 1, hl = threadIdx.x & 15;
+    const int wslot = threadIdx.x >> 4;  // half-warp slot in the CTA
+    const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= B) return;  // whole warp
+    const uint32_t L = ix.levels;
+    uint2 *cur = lvl + b;
+    if (lane == 0) {
+        uint64_t s = sp[b], e = ep[b];
+        if (e > ix.n) e = ix.n;                                          // fm_index.cpp:130-132
+        const bool go = s < e && !(override_tok && override_tok[b] >= 0);  // fm_index.cpp:127,133
+        cur[0] = go ? make_uint2((uint32_t)s, (uint32_t)e) : make_uint2(0u, 0u);
+    }
+    __syncwarp();
+    size_t base = B;
+    uint32_t P_cur = 1;
+    for (uint32_t l = 0; l < LT; ++l) {
+        const uint32_t P_next = fm_nodes_at(ix.max_sym, L, l + 1);
+        uint2 *nxt = lvl + base + (size_t)b * P_next;
+        const uint4 *lc = ix.cells + l * ix.level_stride;
+        for (uint32_t p0 = 0; p0 < P_cur; p0 += 2) {
+            const uint32_t p = p0 + hw;
+            const bool has = p < P_cur;
+            const uint2 node = has ? cur[p] : make_uint2(0u, 0u);
+            const bool ne = node.y > node.x;
+            const uint32_t pos = hl < 8 ? node.x : node.y;
+            if (ne) stage[wslot][hl] = fm_ldg(lc + (size_t)(pos >> 7) * FMIDX_CELL_U4 + (hl & 7));
+            __syncwarp();
+            uint32_t r_lo = 0, r_hi = 0;
+            if (ne) {
+                r_lo = fm_rank_staged(&stage[wslot][0], (uint32_t)hl, (int)(node.x & 127u));
+                r_hi = fm_rank_staged(&stage[wslot][8], (uint32_t)hl, (int)(node.y & 127u));
             }
+            __syncwarp();
+            const uint32_t cp = (p << 4) | (uint32_t)hl;
+            if (has && cp < P_next) nxt[cp] = (r_hi > r_lo) ? make_uint2(r_lo, r_hi) : make_uint2(0u, 0u);
+        }
+        __syncwarp();
+        cur = nxt;
+        P_cur = P_next;
+        base += (size_t)B * P_next;
+    }
+    if (work_items) {
+        const uint32_t nslices = (vocab + SLICE - 1) / SLICE;
+        const uint32_t span_bits = 4u * (L - LT);
+        for (uint32_t s0 = 0; s0 < nslices; s0 += 32) {
+            const uint32_t s = s0 + lane;
+            bool ne = false;
+            if (s < nslices) {
+                int64_t a64 = (int64_t)s * SLICE + shift, e64 = (int64_t)min((s + 1) * (uint32_t)SLICE, vocab) + shift;
+                if (a64 < 0) a64 = 0;
+                if (e64 > (int64_t)ix.max_sym + 1) e64 = (int64_t)ix.max_sym + 1;
+                if (a64 < e64)
+                    for (uint32_t p = (uint32_t)a64 >> span_bits; p <= ((uint32_t)e64 - 1u) >> span_bits; ++p) {
+                        const uint2 nd = cur[p];
+                        ne |= nd.y > nd.x;
+                    }
+            }
+            const uint32_t bal = __ballot_sync(FULL, ne);
+            uint32_t slot = 0;
+            if (lane == 0 && bal) slot = atomicAdd(work_count, (uint32_t)__popc(bal));
+            slot = __shfl_sync(FULL, slot, 0);
+            if (ne) work_items[slot + __popc(bal & ((1u << lane) - 1u))] = b * nslices + s;
         }
     }
+}
 
-    // ---- 2. bitmap of the slice --------------------------------------------------------------------
-    for (int w = tid; w < SLICE / 32; w += MASK_THREADS) bm[w] = 0;
-    const int32_t ovr = override_tok ? override_tok[b] : -1;
+// ---- the walk inside one slice (whole CTA) ---------------------------------------------------------
+// top_b: this range's depth-LT node table; [sa,se): the slice's symbol interval; bm (zeroed by the
+// caller) receives bit (symbol - shift - t0); counts_row (nullable) is indexed by token.
+__device__ __forceinline__ void fm_enum_slice(const FmDev &ix, const uint2 *__restrict__ top_b, uint32_t LT, uint32_t sa,
+                                              uint32_t se, int64_t shift, uint32_t t0, EnumSmem &S,
+                                              uint32_t *__restrict__ counts_row) {
+    const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t L = ix.levels;
-    // symbol interval of the slice, clipped to the alphabet
-    int64_t a64 = (int64_t)t0 + shift, e64 = (int64_t)t1 + shift;
-    if (a64 < 0) a64 = 0;
-    if (e64 > (int64_t)ix.max_sym + 1) e64 = (int64_t)ix.max_sym + 1;
-    const uint32_t sa = (uint32_t)a64, se = e64 > a64 ? (uint32_t)e64 : (uint32_t)a64;
+    const uint32_t span_bits = 4u * (L - LT);
+    const int c0 = LT & 1;
     if (tid == 0) {
-        uint64_t s = sp[b], e = ep[b];
-        if (e > ix.n) e = ix.n;  // fm_index.cpp:130-132
-        const bool go = ovr < 0 && s < e && sa < se;  // fm_index.cpp:127,133
-        fr[0][0][0] = (uint32_t)s;
-        fr[0][0][1] = (uint32_t)e;
-        fr[0][0][2] = 0;
-        fcount[0] = go ? 1u : 0u;
-        fcount[1] = 0;
+        uint32_t n = 0, W = 0;
+        if (sa < se)
+            for (uint32_t p = sa >> span_bits; p <= (se - 1u) >> span_bits && n < MAXF; ++p) {
+                const uint2 nd = top_b[p];
+                if (nd.y > nd.x) {
+                    S.fr[c0][n][0] = nd.x;
+                    S.fr[c0][n][1] = nd.y;
+                    S.fr[c0][n][2] = p;
+                    ++n;
+                    W += nd.y - nd.x;
+                }
+            }
+        S.fcount[c0] = n;
+        S.fcount[c0 ^ 1] = 0;
+        S.width = W;
     }
     __syncthreads();
+    const uint32_t n_seed = S.fcount[c0], W = S.width;
+    if (n_seed == 0) return;
+    if (W <= 32u) {
+        // narrow: one lane per BWT position, straight access down the remaining levels
+        if (tid < 32) {
+            const bool valid = (uint32_t)lane < W;
+            uint32_t pos = 0, c = 0, acc = 0;
+            bool found = false;
+            for (uint32_t i = 0; i < n_seed; ++i) {
+                const uint32_t lo = S.fr[c0][i][0], w = S.fr[c0][i][1] - lo;
+                if (!found && (uint32_t)lane < acc + w) {
+                    pos = lo + ((uint32_t)lane - acc);
+                    c = S.fr[c0][i][2];
+                    found = true;
+                }
+                acc += w;
+            }
+            if (valid)
+                for (uint32_t l = LT; l < L; ++l) {
+                    uint32_t dig;
+                    pos = fm_access1(ix.cells + l * ix.level_stride, pos, dig);
+                    c = (c << 4) | dig;
+                }
+            const bool inside = valid && c >= sa && c < se;
+            if (inside) {
+                const uint32_t rel = (uint32_t)((int64_t)c - shift) - t0;
+                atomicOr(&S.bm[rel >> 5], 1u << (rel & 31u));
+            }
+            if (counts_row) {
+                const uint32_t same = __match_any_sync(FULL, inside ? c : (0xFFFFFF00u + (uint32_t)lane));
+                if (inside) counts_row[(uint32_t)((int64_t)c - shift)] = (uint32_t)__popc(same);
+            }
+        }
+        return;
+    }
     const int hw = tid >> 4, hl = tid & 15;
-    for (uint32_t l = 0; l < L; ++l) {
+    for (uint32_t l = LT; l < L; ++l) {
         const int cur = l & 1, nxt = cur ^ 1;
-        const uint32_t n_nodes = fcount[cur];
+        const uint32_t n_nodes = S.fcount[cur];
         __syncthreads();
         if (n_nodes == 0) break;
-        if (tid == 0) fcount[nxt] = 0;
+        if (tid == 0) S.fcount[nxt] = 0;
         __syncthreads();
         const uint4 *lc = ix.cells + l * ix.level_stride;
         const uint32_t csh = 4u * (L - 1u - l);  // bits below a child's prefix
         const bool leaf = (l + 1 == L);
         for (uint32_t base = 0; base < n_nodes; base += MASK_THREADS / 16) {
             const uint32_t node = base + hw;
-            const bool has = node < n_nodes;
+            bool has = node < n_nodes;
             uint32_t lo = 0, hi = 0, prefix = 0;
             if (has) {
-                lo = fr[cur][node][0];
-                hi = fr[cur][node][1];
-                prefix = fr[cur][node][2];
+                lo = S.fr[cur][node][0];
+                hi = S.fr[cur][node][1];
+                prefix = S.fr[cur][node][2];
+            }
+            if (leaf && !counts_row) {
+                // deepest level, narrow node: the distinct digits of <= 64 positions are cheaper to read
+                // off the bit-planes directly than to rank all 16 digits at both ends
+                const uint32_t w = hi - lo;
+                if (has && w <= 64u) {
+                    for (uint32_t t = (uint32_t)hl; t < w; t += 16) {
+                        const uint32_t q = lo + t;
+                        const uint4 pl = fm_ldg(lc + (size_t)(q >> 7) * FMIDX_CELL_U4 + 4 + ((q & 127u) >> 5));
+                        const uint32_t bt = q & 31u;
+                        const uint32_t dg = ((pl.x >> bt) & 1u) | (((pl.y >> bt) & 1u) << 1) | (((pl.z >> bt) & 1u) << 2) |
+                                            (((pl.w >> bt) & 1u) << 3);
+                        const uint32_t sy = (prefix << 4) | dg;
+                        if (sy >= sa && sy < se) {
+                            const uint32_t rel = (uint32_t)((int64_t)sy - shift) - t0;
+                            atomicOr(&S.bm[rel >> 5], 1u << (rel & 31u));
+                        }
+                    }
+                    has = false;
+                }
+                if (!__any_sync(FULL, has)) continue;
             }
             const uint32_t pos = hl < 8 ? lo : hi;
-            if (has) stage[hw][hl] = fm_ldg(lc + (size_t)(pos >> 7) * FMIDX_CELL_U4 + (hl & 7));
+            if (has) S.stage[hw][hl] = fm_ldg(lc + (size_t)(pos >> 7) * FMIDX_CELL_U4 + (hl & 7));
             __syncwarp();
             uint32_t r_lo = 0, r_hi = 0;
             if (has) {
-                r_lo = fm_rank_staged(&stage[hw][0], (uint32_t)hl, (int)(lo & 127u));
-                r_hi = fm_rank_staged(&stage[hw][8], (uint32_t)hl, (int)(hi & 127u));
+                r_lo = fm_rank_staged(&S.stage[hw][0], (uint32_t)hl, (int)(lo & 127u));
+                r_hi = fm_rank_staged(&S.stage[hw][8], (uint32_t)hl, (int)(hi & 127u));
             }
             __syncwarp();
             const uint32_t cp = (prefix << 4) | (uint32_t)hl;
@@ -251,73 +390,158 @@ k_mask(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict__ e
             if (leaf) {
                 if (exists) {  // cp is a symbol of the slice
                     const uint32_t tk = (uint32_t)((int64_t)cp - shift);
-                    atomicOr(&bm[(tk - t0) >> 5], 1u << ((tk - t0) & 31u));
-                    if (counts_out) counts_out[(size_t)b * vocab + tk] = r_hi - r_lo;
+                    atomicOr(&S.bm[(tk - t0) >> 5], 1u << ((tk - t0) & 31u));
+                    if (counts_row) counts_row[tk] = r_hi - r_lo;
                 }
             } else {
                 const uint32_t bal = (__ballot_sync(FULL, exists) >> (lane & 16)) & 0xffffu;
                 uint32_t slot = 0;
-                if (hl == 0 && bal) slot = atomicAdd(&fcount[nxt], (uint32_t)__popc(bal));
+                if (hl == 0 && bal) slot = atomicAdd(&S.fcount[nxt], (uint32_t)__popc(bal));
                 slot = __shfl_sync(FULL, slot, lane & 16);
                 if (exists) {
                     const uint32_t idx = slot + __popc(bal & ((1u << hl) - 1u));
                     if (idx < MAXF) {
-                        fr[nxt][idx][0] = r_lo;
-                        fr[nxt][idx][1] = r_hi;
-                        fr[nxt][idx][2] = cp;
+                        S.fr[nxt][idx][0] = r_lo;
+                        S.fr[nxt][idx][1] = r_hi;
+                        S.fr[nxt][idx][2] = cp;
                     }
                 }
             }
         }
         __syncthreads();
     }
-    __syncthreads();
-    // ---- 3. per-shard masks of the other GPUs, override rows, always-allowed token --------------
-    if (ovr >= 0) {
-        for (int w = tid; w < SLICE / 32; w += MASK_THREADS) bm[w] = 0;
+}
+
+__device__ __forceinline__ void fm_slice_interval(const FmDev &ix, uint32_t t0, uint32_t t1, int64_t shift, uint32_t &sa,
+                                                  uint32_t &se) {
+    int64_t a64 = (int64_t)t0 + shift, e64 = (int64_t)t1 + shift;
+    if (a64 < 0) a64 = 0;
+    if (e64 > (int64_t)ix.max_sym + 1) e64 = (int64_t)ix.max_sym + 1;
+    sa = (uint32_t)a64;
+    se = e64 > a64 ? (uint32_t)e64 : (uint32_t)a64;
+}
+
+// ---- phase B, bitmap only: persistent CTAs over the work list ------------------------------------------
+__global__ void __launch_bounds__(MASK_THREADS)
+k_mask_items(FmDev ix, const uint2 *__restrict__ top, uint32_t P_top, uint32_t LT, int64_t shift, uint32_t vocab,
+             const uint32_t *__restrict__ items, const uint32_t *__restrict__ n_items_ptr, uint32_t *__restrict__ next_ptr,
+             uint32_t *__restrict__ mask_out, uint32_t *__restrict__ counts_out) {
+    __shared__ EnumSmem S;
+    __shared__ uint32_t cur_item;
+    const int tid = threadIdx.x;
+    const uint32_t n_items = *n_items_ptr;
+    const uint32_t nslices = (vocab + SLICE - 1) / SLICE, mask_words = (vocab + 31u) >> 5;
+    for (;;) {
         __syncthreads();
-        if (tid == 0 && (uint32_t)ovr >= t0 && (uint32_t)ovr < t1) bm[((uint32_t)ovr - t0) >> 5] = 1u << (((uint32_t)ovr - t0) & 31u);
+        if (tid == 0) cur_item = atomicAdd(next_ptr, 1u);
+        for (int w = tid; w < SLICE / 32; w += MASK_THREADS) S.bm[w] = 0;
+        __syncthreads();
+        const uint32_t it = cur_item;
+        if (it >= n_items) break;
+        const uint32_t v = items[it], b = v / nslices, t0 = (v % nslices) * SLICE, t1 = min(t0 + (uint32_t)SLICE, vocab);
+        uint32_t sa, se;
+        fm_slice_interval(ix, t0, t1, shift, sa, se);
+        fm_enum_slice(ix, top + (size_t)b * P_top, LT, sa, se, shift, t0, S, counts_out ? counts_out + (size_t)b * vocab : nullptr);
+        __syncthreads();
+        const uint32_t nw = (t1 - t0 + 31u) >> 5;
+        for (uint32_t w = tid; w < nw; w += MASK_THREADS) mask_out[(size_t)b * mask_words + (t0 >> 5) + w] = S.bm[w];
+    }
+}
+
+// ---- phase B, fused with the logits row -------------------------------------------------------------------
+// DT: FMIDX_F32/BF16/F16.   VECTOR: 16-byte accesses are legal.   grid = ceil(vocab/4096) * B, slice-fastest.
+template <int DT, bool VECTOR>
+__global__ void __launch_bounds__(MASK_THREADS)
+k_mask_logits(FmDev ix, const uint2 *__restrict__ top, uint32_t P_top, uint32_t LT, int64_t shift, uint32_t vocab,
+              const void *logits_v, void *out_v, int64_t row_stride, const int32_t *__restrict__ override_tok,
+              int32_t always_allow, const uint32_t *__restrict__ extra, uint32_t n_extra, uint32_t B,
+              uint32_t *__restrict__ mask_out) {
+    __shared__ EnumSmem S;
+    const int tid = threadIdx.x;
+    const uint32_t nslices = (vocab + SLICE - 1) / SLICE;
+    const uint32_t b = blockIdx.x / nslices;
+    const uint32_t t0 = (blockIdx.x % nslices) * SLICE;
+    const uint32_t t1 = min(t0 + (uint32_t)SLICE, vocab);
+    const uint32_t mask_words = (vocab + 31u) >> 5;
+
+    // 1. issue the logits loads for this slice
+    using ET = typename Elem<DT>::T;
+    constexpr int VEC = Elem<DT>::VEC;
+    constexpr int NV = SLICE / (MASK_THREADS * VEC);  // vectors per thread
+    uint4 regs[VECTOR ? NV : 1];
+    const ET *row_in = reinterpret_cast<const ET *>(logits_v) + (size_t)b * row_stride;
+    ET *row_out = reinterpret_cast<ET *>(out_v) + (size_t)b * row_stride;
+    if (VECTOR) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const uint32_t e = t0 + (uint32_t)(i * MASK_THREADS + tid) * VEC;
+            if (e < t1) regs[i] = __ldcs(reinterpret_cast<const uint4 *>(row_in + e));
+        }
+    }
+    // 2. bitmap of the slice
+    for (int w = tid; w < SLICE / 32; w += MASK_THREADS) S.bm[w] = 0;
+    const int32_t ovr = override_tok ? override_tok[b] : -1;
+    uint32_t sa, se;
+    fm_slice_interval(ix, t0, t1, shift, sa, se);
+    if (ovr < 0) fm_enum_slice(ix, top + (size_t)b * P_top, LT, sa, se, shift, t0, S, nullptr);  // (k_mask_top left override rows empty)
+    __syncthreads();
+    // 3. per-shard masks of the other GPUs, override rows, always-allowed token
+    if (ovr >= 0) {
+        if (tid == 0 && (uint32_t)ovr >= t0 && (uint32_t)ovr < t1) S.bm[((uint32_t)ovr - t0) >> 5] = 1u << (((uint32_t)ovr - t0) & 31u);
     } else if (n_extra) {
         const uint32_t nw = (t1 - t0 + 31u) >> 5;
         for (uint32_t w = tid; w < nw; w += MASK_THREADS) {
-            uint32_t acc = bm[w];
+            uint32_t acc = S.bm[w];
             for (uint32_t x = 0; x < n_extra; ++x) acc |= extra[((size_t)x * B + b) * mask_words + (t0 >> 5) + w];
-            bm[w] = acc;
+            S.bm[w] = acc;
         }
     }
     __syncthreads();
     if (tid == 0 && always_allow >= 0 && (uint32_t)always_allow >= t0 && (uint32_t)always_allow < t1)
-        bm[((uint32_t)always_allow - t0) >> 5] |= 1u << (((uint32_t)always_allow - t0) & 31u);
+        S.bm[((uint32_t)always_allow - t0) >> 5] |= 1u << (((uint32_t)always_allow - t0) & 31u);
     __syncthreads();
     if (mask_out) {
         const uint32_t nw = (t1 - t0 + 31u) >> 5;
-        for (uint32_t w = tid; w < nw; w += MASK_THREADS) mask_out[(size_t)b * mask_words + (t0 >> 5) + w] = bm[w];
+        for (uint32_t w = tid; w < nw; w += MASK_THREADS) mask_out[(size_t)b * mask_words + (t0 >> 5) + w] = S.bm[w];
     }
-    // ---- 4. stream the slice of the logits row -----------------------------------------------------
-    if (HAS_LOGITS) {
-        if (VECTOR) {
+    // 4. stream the slice of the logits row
+    if (VECTOR) {
 #pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const uint32_t rel = (uint32_t)(i * MASK_THREADS + tid) * VEC;
-                const uint32_t e = t0 + rel;
-                if (e < t1) {
-                    const uint32_t bits = (bm[rel >> 5] >> (rel & 31u)) & ((1u << VEC) - 1u);
-                    ET *x = reinterpret_cast<ET *>(&regs[i]);
+        for (int i = 0; i < NV; ++i) {
+            const uint32_t rel = (uint32_t)(i * MASK_THREADS + tid) * VEC;
+            const uint32_t e = t0 + rel;
+            if (e < t1) {
+                const uint32_t bits = (S.bm[rel >> 5] >> (rel & 31u)) & ((1u << VEC) - 1u);
+                ET *x = reinterpret_cast<ET *>(&regs[i]);
 #pragma unroll
-                    for (int k = 0; k < VEC; ++k) x[k] = fm_add_mask(x[k], (bits >> k) & 1u);
-                    __stcs(reinterpret_cast<uint4 *>(row_out + e), regs[i]);
-                }
+                for (int k = 0; k < VEC; ++k) x[k] = fm_add_mask(x[k], (bits >> k) & 1u);
+                __stcs(reinterpret_cast<uint4 *>(row_out + e), regs[i]);
             }
-        } else {
-            for (uint32_t e = t0 + tid; e < t1; e += MASK_THREADS) {
-                const uint32_t rel = e - t0;
-                row_out[e] = fm_add_mask(row_in[e], (bm[rel >> 5] >> (rel & 31u)) & 1u);
-            }
+        }
+    } else {
+        for (uint32_t e = t0 + tid; e < t1; e += MASK_THREADS) {
+            const uint32_t rel = e - t0;
+            row_out[e] = fm_add_mask(row_in[e], (S.bm[rel >> 5] >> (rel & 31u)) & 1u);
         }
     }
 }
 
 // ---- bitmap -> sparse lists --------------------------------------------------------------------------
+// OR of the per-shard bitmap pieces gathered from the other GPUs (NCCL has no bitwise-OR reduction)
+__global__ void __launch_bounds__(256) k_or_pieces(const uint4 *__restrict__ pieces, uint32_t n_pieces, size_t n_vec,
+                                                   uint4 *__restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n_vec; i += stride) {
+        uint4 acc = __ldcs(pieces + i);
+        for (uint32_t p = 1; p < n_pieces; ++p) {
+            const uint4 v = __ldcs(pieces + (size_t)p * n_vec + i);
+            acc.x |= v.x; acc.y |= v.y; acc.z |= v.z; acc.w |= v.w;
+        }
+        out[i] = acc;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_popcount(const uint32_t *__restrict__ mask, uint32_t mask_words,
                                                   uint32_t *__restrict__ n_out) {
     __shared__ uint32_t part[8];
@@ -519,28 +743,70 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
                    uint32_t *d_counts, cudaStream_t s) {
     FM_TRY(check_ready(h));
     if (B == 0 || vocab == 0) return FMIDX_OK;
-    const size_t nblk = (size_t)((vocab + SLICE - 1) / SLICE) * B;
+    const uint32_t nslices = (vocab + SLICE - 1) / SLICE;
+    const size_t nblk = (size_t)nslices * B;
     if (nblk > 0x7FFFFFFFull) { fm_set_error("mask batch too large: split the call"); return FMIDX_EINVAL; }
-    const unsigned grid = (unsigned)nblk;
     const bool has = d_logits != nullptr;
     if (has && !d_out) { fm_set_error("d_out is NULL"); return FMIDX_EINVAL; }
-    if (!has) dtype = 3;
+    if (!has && !d_mask) { fm_set_error("d_mask is NULL"); return FMIDX_EINVAL; }
+    // workspace: dense node tables of levels 0..LT, then the work list and its two counters
+    const FmDev &ix = h->dev;
+    const uint32_t L = ix.levels, LT = L > 3 ? L - 3 : 0;
+    size_t n_nodes = 0, top_off = 0;
+    for (uint32_t l = 0; l <= LT; ++l) {
+        if (l == LT) top_off = n_nodes;
+        n_nodes += (size_t)B * fm_nodes_at(ix.max_sym, L, l);
+    }
+    const uint32_t P_top = fm_nodes_at(ix.max_sym, L, LT);
+    const size_t lvl_bytes = n_nodes * sizeof(uint2);
+    const size_t items_bytes = has ? 0 : nblk * 4;
+    FM_TRY(fm_scratch(h, h->mask_ws, lvl_bytes + items_bytes + 64, false));
+    uint2 *lvl = (uint2 *)h->mask_ws.p;
+    uint32_t *items = has ? nullptr : (uint32_t *)((char *)h->mask_ws.p + lvl_bytes);
+    uint32_t *ctr = (uint32_t *)((char *)h->mask_ws.p + lvl_bytes + items_bytes);  // [0]=count [1]=next
+    if (!has) {
+        FM_CUDA(cudaMemsetAsync(ctr, 0, 8, s));
+        FM_CUDA(cudaMemsetAsync(d_mask, 0, B * (size_t)((vocab + 31) / 32) * 4, s));
+    }
+    FM_LAUNCH(k_mask_top, (unsigned)((B * 32 + 127) / 128), 128, 0, s, ix, d_sp, d_ep, (uint32_t)B, LT, lvl, d_override, shift,
+              vocab, items, ctr);
+    if (!has) {
+        const unsigned grid = (unsigned)std::min<size_t>(nblk, (size_t)h->sm_count * 16);
+        FM_LAUNCH(k_mask_items, grid, MASK_THREADS, 0, s, ix, lvl + top_off, P_top, LT, shift, vocab, items, ctr, ctr + 1,
+                  d_mask, d_counts);
+        FM_CUDA(cudaGetLastError());
+        return FMIDX_OK;
+    }
     auto aligned = [&](int esz) {
         const int vec = 16 / esz;
         return ((uintptr_t)d_logits % 16 == 0) && ((uintptr_t)d_out % 16 == 0) && (row_stride % vec == 0) &&
                (vocab % vec == 0);
     };
+    const unsigned grid = (unsigned)nblk;
 #define FM_MASK_CASE(DT, VECT)                                                                                     \
-    FM_LAUNCH((k_mask<DT, VECT>), grid, MASK_THREADS, 0, s, h->dev, d_sp, d_ep, shift, vocab, d_logits, d_out,     \
-              row_stride, d_override, always_allow, d_extra, n_extra, (uint32_t)B, d_mask, d_counts)
+    FM_LAUNCH((k_mask_logits<DT, VECT>), grid, MASK_THREADS, 0, s, ix, lvl + top_off, P_top, LT, shift, vocab, d_logits, \
+              d_out, row_stride, d_override, always_allow, d_extra, n_extra, (uint32_t)B, d_mask)
     switch (dtype) {
         case FMIDX_F32: if (aligned(4)) FM_MASK_CASE(FMIDX_F32, true); else FM_MASK_CASE(FMIDX_F32, false); break;
         case FMIDX_BF16: if (aligned(2)) FM_MASK_CASE(FMIDX_BF16, true); else FM_MASK_CASE(FMIDX_BF16, false); break;
         case FMIDX_F16: if (aligned(2)) FM_MASK_CASE(FMIDX_F16, true); else FM_MASK_CASE(FMIDX_F16, false); break;
-        case 3: FM_MASK_CASE(3, false); break;
         default: fm_set_error("unknown logits dtype %d", dtype); return FMIDX_EINVAL;
     }
 #undef FM_MASK_CASE
+    FM_CUDA(cudaGetLastError());
+    return FMIDX_OK;
+}
+
+int fm_launch_or(fmidx *h, const uint32_t *d_pieces, uint32_t n_pieces, size_t n_words, uint32_t *d_out, cudaStream_t s) {
+    if (n_words == 0 || n_pieces == 0) return FMIDX_OK;
+    if ((n_words & 3) || ((uintptr_t)d_pieces & 15) || ((uintptr_t)d_out & 15)) {
+        fm_set_error("mask_or: word count must be a multiple of 4 and the buffers 16-byte aligned");
+        return FMIDX_EINVAL;
+    }
+    const size_t n_vec = n_words / 4;
+    const size_t cap = (size_t)h->sm_count * 8;
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((n_vec + 255) / 256, cap));
+    FM_LAUNCH(k_or_pieces, grid, 256, 0, s, (const uint4 *)d_pieces, n_pieces, n_vec, (uint4 *)d_out);
     FM_CUDA(cudaGetLastError());
     return FMIDX_OK;
 }

@@ -233,15 +233,17 @@ class FMIndex(_FMIndex):
         N.check(N.lib().fmidx_step_batch(self._h, _ptr(symbols), _ptr(lows), _ptr(highs), B, _ptr(out[0]), _ptr(out[1]), _stream(torch)))
         return out[0, :B], out[1, :B]
 
-    def distinct_mask_batch(self, sp, ep, vocab, shift=SHIFT, want_counts=False):
+    def distinct_mask_batch(self, sp, ep, vocab, shift=SHIFT, want_counts=False, out=None):
         """Allowed-token bitmaps [B, ceil(vocab/32)] int32 (+ optional counts [B, vocab] int32,
-        defined at set bits only)."""
+        defined at set bits only).  out: optional preallocated contiguous [B, words] int32."""
         torch = _torch()
         B = sp.numel()
         words = (vocab + 31) // 32
-        mask = torch.empty((B, words), dtype=torch.int32, device=sp.device)
+        mask = torch.empty((B, words), dtype=torch.int32, device=sp.device) if out is None else out
+        assert mask.is_contiguous() and mask.shape == (B, words) and mask.dtype == torch.int32
         counts = torch.empty((B, vocab), dtype=torch.int32, device=sp.device) if want_counts else None
-        N.check(N.lib().fmidx_distinct_mask_batch(self._h, _ptr(sp), _ptr(ep), B, shift, vocab, _ptr(mask), _ptr(counts), _stream(torch)))
+        if B:
+            N.check(N.lib().fmidx_distinct_mask_batch(self._h, _ptr(sp), _ptr(ep), B, shift, vocab, _ptr(mask), _ptr(counts), _stream(torch)))
         return (mask, counts) if want_counts else mask
 
     def mask_logits(self, sp, ep, logits, out=None, override_tok=None, always_allow=-1, extra_masks=None,

@@ -112,6 +112,9 @@ int fmidx_mask_logits(fmidx_t *h, const uint64_t *d_sp, const uint64_t *d_ep, si
 /* bitmap + counts -> sparse ascending (token,count) lists (index.py:161-174 return shape).
  * d_list_offsets [B+1] must hold the exclusive prefix sums of the per-row popcounts, which
  * fmidx_mask_popcount computes into d_n ([B] u32). */
+/* out[i] = OR over p < n_pieces of pieces[p][i], i < n_words (n_words % 4 == 0): the local half of
+ * the cross-shard mask OR-reduction (NCCL has no bitwise-OR op; the pieces arrive by all-to-all) */
+int fmidx_mask_or(fmidx_t *h, const uint32_t *d_pieces, uint32_t n_pieces, size_t n_words, uint32_t *d_out, void *stream);
 int fmidx_mask_popcount(fmidx_t *h, const uint32_t *d_mask, size_t B, uint32_t vocab, uint32_t *d_n, void *stream);
 int fmidx_mask_compact(fmidx_t *h, const uint32_t *d_mask, const uint32_t *d_counts, size_t B, uint32_t vocab,
                        const uint64_t *d_list_offsets, int64_t *d_tokens, uint64_t *d_cnts, void *stream);
