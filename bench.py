@@ -119,16 +119,18 @@ def reversed_symbols(toks, beg):
     return (toks.long()[src] + SHIFT).to(torch.int32)
 
 
-def oracle_from_gpu_sa(toks, beg, device_index):
+def oracle_from_gpu_sa(toks, beg, device_index, ix=None):
     """CPU oracle over the SAME corpus.  Suffix-sorting 100M tokens on one host core would take
     longer than the whole bench, so the oracle's structures are built from the suffix array the
     GPU builder produced (the oracle's own SA-IS is cross-checked against it in tests/)."""
     from fm_index_constrained_decoding_b200 import _native, fm_index
     from oracle.oracle import NativeOracle
     sym = reversed_symbols(toks, beg)
-    tmp = fm_index.FMIndex(device=device_index, sa_dens=1, isa_dens=1 << 20)
-    _native.check(_native.lib().fmidx_initialize_device(tmp._h, C.c_void_p(sym.data_ptr()), sym.numel(),
-                                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    tmp = ix if (ix is not None and ix.info()["sa_dens"] == 1) else None
+    if tmp is None:
+        tmp = fm_index.FMIndex(device=device_index, sa_dens=1, isa_dens=1 << 20, keep_text=False)
+        _native.check(_native.lib().fmidx_initialize_device(tmp._h, C.c_void_p(sym.data_ptr()), sym.numel(),
+                                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     sa = np.empty(sym.numel() + 1, dtype=np.uint32)
     _native.check(_native.lib().fmidx_debug_copy_sa(tmp._h, sa.ctypes.data_as(C.c_void_p), sa.size))
     del tmp
@@ -204,6 +206,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--cpu-batch", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layout", default="resident", choices=["resident", "sampled"])
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -231,7 +234,7 @@ def main():
     torch.cuda.synchronize()
     t_gen = time.time() - t0
     t0 = time.time()
-    ix = FMIndex(device=local)
+    ix = FMIndex(device=local, layout=args.layout)
     ix.initialize_from_device_tokens(toks, beg)
     torch.cuda.synchronize()
     t_build = time.time() - t0
@@ -295,8 +298,12 @@ def main():
     if sampler and total_ms < 500:  # region too short for NVML's sampling period: keep the same load running
         t_end = time.time() + 0.6
         k = 0
-        while time.time() < t_end:
-            step_full(k)
+        while time.time() < t_end:  # local kernels only: the other ranks are not in this loop
+            q, offs = qsets[k % N_QUERY_SETS]
+            L.fmidx_search_batch(ix._h, C.c_void_p(q.data_ptr()), C.c_void_p(offs.data_ptr()), B, SHIFT,
+                                 C.c_void_p(sp.data_ptr()), C.c_void_p(ep.data_ptr()), sptr)
+            L.fmidx_distinct_mask_batch(ix._h, C.c_void_p(sp.data_ptr()), C.c_void_p(ep.data_ptr()), B, SHIFT, VOCAB,
+                                        C.c_void_p(mask.data_ptr()), None, sptr)
             k += 1
             if k % 50 == 0:
                 torch.cuda.synchronize()
@@ -421,7 +428,7 @@ def main():
         try:
             nthreads = os.cpu_count() or 1
             t0 = time.time()
-            o = oracle_from_gpu_sa(toks, beg, local)
+            o = oracle_from_gpu_sa(toks, beg, local, ix)
             log("oracle built in %.1fs" % (time.time() - t0))
             q, offs = qsets[0]
             qn, on = q.cpu().numpy(), offs.cpu().numpy()
@@ -451,7 +458,7 @@ def main():
             "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": workload_config(args, B),
             "masks_per_sec": value, "roofline": dom, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "index": {"build_s": t_build, "device_mb": info["device_bytes"] / 1e6, "levels": info["levels"],
-                                        "layout": "16-ary wavelet matrix, 128-B cells"},
+                                        "layout": "16-ary wavelet matrix, 128-B cells; %s (sa_dens %d, isa_dens %d, text %s)" % (args.layout, info["sa_dens"], info["isa_dens"], bool(info["keep_text"]))},
         }
         print(json.dumps(line))
     if world > 1:

@@ -48,9 +48,18 @@ __global__ void __launch_bounds__(128) k_search(FmDev ix, const int32_t *__restr
     const int maxlen = len > other_len ? len : other_len;
     uint32_t lo = 0, hi = ix.n;
     bool alive = valid;
+    // When the full SA, the full ISA and the text are resident, a range that has narrowed to <= 16 rows
+    // is finished without further rank probes: lane i of the query's half-warp takes row lo+i, whose
+    // suffix starts at p_i = SA[lo+i]; the remaining tokens must equal T[p_i-1], T[p_i-2], ...
+    // (BWT[row] = T[SA[row]-1], LF(row) = ISA[SA[row]-1]); the surviving occurrences' final rows
+    // ISA[p_i - remaining] form the (contiguous) answer range.  ~4 dependent round trips instead of
+    // 5 per remaining token.
+    const bool accel = !RAW && ix.text != nullptr && ix.sa_dens == 1 && ix.isa_dens == 1;
+    int t_stop = -1;  // >= 0: range fell to <= 16 rows after token t_stop-1; tokens t_stop.. are pending
     int32_t tok_next = (valid && len > 0) ? toks[o0] : 0;
     for (int t = 0; t < maxlen; ++t) {
         const bool act = alive && t < len;
+        if (!__any_sync(FULL, act)) break;
         const int64_t sym = (int64_t)tok_next + shift;
         if (act && t + 1 < len) tok_next = toks[o0 + t + 1];
         const bool symok = act && sym >= 0 && sym <= (int64_t)ix.max_sym;
@@ -83,6 +92,40 @@ __global__ void __launch_bounds__(128) k_search(FmDev ix, const int32_t *__restr
             } else {
                 lo = nlo;
                 hi = nhi;
+                if (accel && hi - lo <= 16u && t + 1 < len) {
+                    t_stop = t + 1;
+                    alive = false;
+                }
+            }
+        }
+    }
+    if (accel) {
+        const bool pend = t_stop >= 0;  // uniform inside the query's 16 lanes
+        const int hl = lane & 15;
+        const int rem = pend ? len - t_stop : 0;
+        const uint32_t n = ix.n;
+        bool ok = pend && (uint32_t)hl < hi - lo;
+        uint32_t p = 0;
+        if (ok) p = ix.sa_samples[lo + (uint32_t)hl];
+        for (int j = 0; j < rem && ok; ++j) {
+            const int64_t sym = (int64_t)toks[o0 + t_stop + j] + shift;
+            const uint32_t at = (uint32_t)(((uint64_t)p + n - 1u - ((uint32_t)j % n)) % n);  // (p-1-j) mod n: the text is cyclic under LF
+            ok = sym >= 0 && sym <= 0xFFFFFFFFll && (uint32_t)sym == ix.text[at];
+        }
+        uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+        if (ok) mn = mx = ix.isa_samples[(uint32_t)(((uint64_t)p + n - ((uint32_t)rem % n)) % n)];
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            mn = min(mn, __shfl_xor_sync(FULL, mn, o));
+            mx = max(mx, __shfl_xor_sync(FULL, mx, o));
+        }
+        if (pend) {
+            if (mn == 0xFFFFFFFFu) {
+                lo = 0;
+                hi = 0;
+            } else {
+                lo = mn;
+                hi = mx + 1u;
             }
         }
     }

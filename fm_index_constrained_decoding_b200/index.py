@@ -50,8 +50,8 @@ def ragged(sequences):
 
 
 class FMIndex(_FMIndex):
-    def __init__(self, device=None, sa_dens=None, isa_dens=None, keep_text=None):
-        super().__init__(device=device, sa_dens=sa_dens, isa_dens=isa_dens, keep_text=keep_text)
+    def __init__(self, device=None, sa_dens=None, isa_dens=None, keep_text=None, layout=None):
+        super().__init__(device=device, sa_dens=sa_dens, isa_dens=isa_dens, keep_text=keep_text, layout=layout)
         self._devidx = N.default_device() if device is None else int(device)
         self._init_side_data()
 

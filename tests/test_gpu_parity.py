@@ -40,9 +40,9 @@ def random_docs(rng, V, ndocs, lo, hi, repeats=True):
 
 
 @pytest.mark.parametrize("case", golden_cases(), ids=lambda c: "n%d" % c["size"])
-@pytest.mark.parametrize("dens", [(32, 64), (1, 1), (4, 2)])
+@pytest.mark.parametrize("dens", [(32, 64, False), (1, 1, True), (4, 2, False)])
 def test_golden_scalar_surface(cuda, case, dens):
-    ix = make(case["docs"], sa_dens=dens[0], isa_dens=dens[1])
+    ix = make(case["docs"], sa_dens=dens[0], isa_dens=dens[1], keep_text=dens[2])
     N = case["size"]
     assert ix.size() == N and ix.beginnings == case["beginnings"] and len(ix) == N - 1
     assert [ix.locate(r) for r in range(N)] == case["SA"]
@@ -81,12 +81,13 @@ def test_builder_suffix_array_vs_oracle(cuda):
     assert (got == ref).all()
 
 
+@pytest.mark.parametrize("layout", ["resident", "sampled"])
 @pytest.mark.parametrize("V,ndocs,lo,hi", [(3, 40, 1, 200), (300, 200, 5, 300), (128256, 300, 20, 400)])
-def test_batched_search_and_masks_vs_oracle(cuda, V, ndocs, lo, hi):
+def test_batched_search_and_masks_vs_oracle(cuda, V, ndocs, lo, hi, layout):
     from fm_index_constrained_decoding_b200.index import ragged
     rng = random.Random(V)
     docs = random_docs(rng, V, ndocs, lo, hi)
-    ix, o = make(docs), oracle(docs)
+    ix, o = make(docs, layout=layout), oracle(docs)
     seqs = [[]]
     for _ in range(1500):
         d = rng.choice(docs)
@@ -227,11 +228,11 @@ def test_mask_logits_unaligned_and_inplace(cuda):
         assert bits == allowed
 
 
-@pytest.mark.parametrize("dens", [(32, 64), (1, 1), (8, 16)])
+@pytest.mark.parametrize("dens", [(32, 64, False), (1, 1, True), (8, 16, False), (1, 1, False)])
 def test_locate_extract_batches(cuda, dens):
     rng = random.Random(4)
     docs = random_docs(rng, 2000, 120, 10, 200)
-    ix, o = make(docs, sa_dens=dens[0], isa_dens=dens[1]), oracle(docs)
+    ix, o = make(docs, sa_dens=dens[0], isa_dens=dens[1], keep_text=dens[2]), oracle(docs)
     N = o.size()
     rows = [rng.randrange(N + 3) for _ in range(4000)]
     pos = ix.locate_batch(torch.tensor(rows, dtype=torch.int64, device="cuda")).cpu().numpy().astype(np.uint64)
@@ -311,7 +312,7 @@ def test_large_properties(cuda):
     properties + oracle spot checks through build-from-device."""
     from fm_index_constrained_decoding_b200 import FMIndex, synth
     toks, beg = synth.zipf_corpus(4_000_000, seed=0, device="cuda")
-    ix = FMIndex(sa_dens=32)
+    ix = FMIndex(layout="sampled")
     ix.initialize_from_device_tokens(toks, beg)
     n = toks.numel()
     assert ix.size() == n + 1 and len(ix) == n
