@@ -39,8 +39,17 @@ MASK_BYTES = 16032                # one 128,256-bit vocab mask
 N_QUERY_SETS = 8                  # distinct prefix batches rotated through the timed steps
 
 
+_JSON_OUT = None
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def measured_peaks():
@@ -151,19 +160,32 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    if not torch.cuda.is_available():
-        print(json.dumps({"impl": "reference", "unavailable": "needs the GPU-built suffix array of the 100M-token corpus"}))
-        return
-    device = torch.device("cuda", 0)
-    torch.cuda.set_device(device)
-    os.environ.setdefault("FMIDX_DEVICE", "0")
     nthreads = os.cpu_count() or 1
-    toks, beg, qsets = build_workload(args, 0, device)
-    t0 = time.time()
-    o = oracle_from_gpu_sa(toks, beg, 0)
-    log("oracle built in %.1fs" % (time.time() - t0))
-    # bounded sample: each step = the first `cpu_batch` prefixes of the step's batch
-    cpu_batch = min(args.batch, args.cpu_batch)
+    from fm_index_constrained_decoding_b200 import synth
+    note = ""
+    if torch.cuda.is_available():
+        device = torch.device("cuda", 0)
+        torch.cuda.set_device(device)
+        os.environ.setdefault("FMIDX_DEVICE", "0")
+        toks, beg, qsets = build_workload(args, 0, device)
+        t0 = time.time()
+        o = oracle_from_gpu_sa(toks, beg, 0)
+        log("oracle built in %.1fs" % (time.time() - t0))
+    else:
+        # no GPU: the oracle suffix-sorts itself (SA-IS, one core), on a corpus cut to 10M tokens
+        from oracle.oracle import NativeOracle
+        args.tokens = min(args.tokens, 10_000_000)
+        note = " [no GPU: corpus cut to %d tokens, oracle's own SA-IS]" % args.tokens
+        toks, beg = synth.zipf_corpus(args.tokens, seed=0, device="cpu")
+        qsets = [synth.sample_queries(toks, args.batch, seed=100 + i, beginnings=beg) for i in range(N_QUERY_SETS)]
+        o = NativeOracle()
+        o.initialize(reversed_symbols(toks, beg).numpy().astype(np.uint64))
+    # bounded sample: each step = the first `cpu_batch` prefixes of the step's batch, sized from a probe so
+    # that warm-up + steps stay within ~2 minutes of host time
+    qn, on = qsets[0][0].cpu().numpy(), qsets[0][1].cpu().numpy()
+    t_probe = cpu_step(o, qn[:on[256]], on[:257], nthreads) / 256
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    cpu_batch = int(max(64, min(args.batch, args.cpu_batch, budget / max(t_probe, 1e-9))))
     host = []
     for q, offs in qsets:
         qn, on = q.cpu().numpy(), offs.cpu().numpy()
@@ -181,10 +203,10 @@ def run_reference(args):
         "config": workload_config(args, cpu_batch),
         "cpu_baseline": {"value": value, "unit": "queries/s", "cores": nthreads, "kind": "port",
                          "sample": "%d of the %d prefixes of each step (search + distinct-token mask), oracle/fm_oracle.c "
-                                   "(sdsl-semantics restatement, not sdsl-lite), pthread pool" % (cpu_batch, args.batch)},
+                                   "(sdsl-semantics restatement, not sdsl-lite), pthread pool%s" % (cpu_batch, args.batch, note)},
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, batch):
@@ -210,6 +232,12 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    # the one JSON line must be the only thing on stdout: NCCL / library banners that print to fd 1
+    # are sent to stderr, the line itself goes to the saved descriptor
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -460,7 +488,7 @@ def main():
             "clocks": clocks, "index": {"build_s": t_build, "device_mb": info["device_bytes"] / 1e6, "levels": info["levels"],
                                         "layout": "16-ary wavelet matrix, 128-B cells; %s (sa_dens %d, isa_dens %d, text %s)" % (args.layout, info["sa_dens"], info["isa_dens"], bool(info["keep_text"]))},
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -65,7 +65,8 @@ def main():
     if "decode" in what:
         B = 256
         qs = [synth.sample_queries(toks, B, seed=300 + i, beginnings=beg) for i in range(8)]
-        for dtype in (torch.float32, torch.bfloat16):
+        for dtype, path in ((torch.float32, "pipe"), (torch.float32, "tma"), (torch.float32, "regs"), (torch.bfloat16, "pipe"), (torch.bfloat16, "regs")):
+            os.environ["FMIDX_LOGITS_PATH"] = path
             g = torch.Generator(device=dev).manual_seed(3)
             # 8 distinct logits buffers (8 x 131 MB fp32 > L2) rotated so no step re-reads a cached row
             logits = [torch.randn(B, VOCAB, generator=g, device=dev).to(dtype) for _ in range(8)]
@@ -84,10 +85,14 @@ def main():
             ms = timed(step, args.steps)
             sp0, ep0 = ix.get_range_batch(*qs[0])
             ms_mask = timed(mask_only, args.steps)
+            # the same kernel when every beam has >= 8 tokens of history (narrow ranges only)
+            sp0, ep0 = ix.get_range_batch(*synth.sample_queries(toks, B, len_min=8, seed=999, beginnings=beg))
+            ms_mask_narrow = timed(mask_only, args.steps)
+            sp0, ep0 = ix.get_range_batch(*qs[0])
             nbytes = 2 * B * VOCAB * logits[0].element_size() + B * 16032
-            print(json.dumps({"config": "configs[3] fused decode step: 256 beams x 128256 logits", "dtype": str(dtype), **base,
+            print(json.dumps({"config": "configs[3] fused decode step: 256 beams x 128256 logits", "dtype": str(dtype), "logits_staging": path, **base,
                               "ms_per_step": ms, "steps_per_sec": 1e3 / ms, "beams_per_sec": B * 1e3 / ms,
-                              "mask_logits_kernel_ms": ms_mask, "algorithmic_bytes": nbytes,
+                              "mask_logits_kernel_ms": ms_mask, "mask_logits_kernel_ms_narrow_beams": ms_mask_narrow, "algorithmic_bytes": nbytes,
                               "mask_logits_GBps": nbytes / (ms_mask * 1e-3) / 1e9, "frac_of_measured_hbm": nbytes / (ms_mask * 1e-3) / 1e9 / peak,
                               "floor_ms_at_peak": nbytes / (peak * 1e9) * 1e3}), flush=True)
             del logits, out

@@ -17,6 +17,8 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 #include "fmidx_internal.h"
 
@@ -212,6 +214,21 @@ __device__ __forceinline__ uint32_t fm_rank_staged(const uint4 *cell, uint32_t d
     return v;
 }
 
+// same with the lane's plane XOR masks precomputed and branch-free position masks (BFS inner loop)
+__device__ __forceinline__ uint32_t fm_rank_fast(const uint4 *cell, uint32_t d, uint32_t off, uint32_t x0, uint32_t x1,
+                                                 uint32_t x2, uint32_t x3) {
+    const uint64_t mlo = off >= 64u ? ~0ull : ((1ull << off) - 1ull);          // positions 0..63 below off
+    const uint64_t mhi = off <= 64u ? 0ull : ((1ull << (off - 64u)) - 1ull);   // positions 64..127 below off
+    const uint32_t mg[4] = {(uint32_t)mlo, (uint32_t)(mlo >> 32), (uint32_t)mhi, (uint32_t)(mhi >> 32)};
+    uint32_t v = reinterpret_cast<const uint32_t *>(cell)[d];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const uint4 p = cell[4 + g];
+        v += __popc((p.x ^ x0) & mg[g] & (p.y ^ x1) & (p.z ^ x2) & (p.w ^ x3));
+    }
+    return v;
+}
+
 // single-thread access+rank at one level: returns the next-level position of the element AT pos
 __device__ __forceinline__ uint32_t fm_access1(const uint4 *__restrict__ level_cells, uint32_t pos, uint32_t &dig_out) {
     const uint4 *cell = level_cells + (size_t)(pos >> 7) * FMIDX_CELL_U4;
@@ -246,13 +263,40 @@ __device__ __host__ __forceinline__ uint32_t fm_nodes_at(uint32_t max_sym, uint3
 __global__ void __launch_bounds__(128)
 k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict__ ep, uint32_t B, uint32_t LT,
            uint2 *__restrict__ lvl, const int32_t *__restrict__ override_tok, int64_t shift, uint32_t vocab,
-           uint32_t *__restrict__ work_items, uint32_t *__restrict__ work_count) {
+           uint32_t *__restrict__ work_items, uint32_t *__restrict__ work_count, uint32_t *__restrict__ mask_out,
+           uint32_t *__restrict__ counts_out) {
     __shared__ uint4 stage[8][16];
     const int lane = threadIdx.x & 31, hw = (threadIdx.x >> 4) & 1, hl = threadIdx.x & 15;
     const int wslot = threadIdx.x >> 4;  // half-warp slot in the CTA
     const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (b >= B) return;  // whole warp
     const uint32_t L = ix.levels;
+    if (work_items) {
+        // bitmap-only mode, range of <= 32 rows (the common case once a prefix has a few tokens): this
+        // warp reads the rows' symbols straight off the matrix (one lane per row, `levels` access probes)
+        // and sets the bits in the pre-zeroed mask row; no node table, no work item.
+        uint64_t s = sp[b], e = ep[b];
+        if (e > ix.n) e = ix.n;
+        if (s >= e) return;
+        if (e - s <= 32u) {
+            const bool valid = (uint64_t)lane < e - s;
+            uint32_t pos = (uint32_t)s + (uint32_t)lane, c = 0;
+            if (valid)
+                for (uint32_t l = 0; l < L; ++l) {
+                    uint32_t dig;
+                    pos = fm_access1(ix.cells + l * ix.level_stride, pos, dig);
+                    c = (c << 4) | dig;
+                }
+            const int64_t tk = (int64_t)c - shift;
+            const bool inside = valid && tk >= 0 && tk < (int64_t)vocab;
+            if (inside) atomicOr(&mask_out[(size_t)b * ((vocab + 31u) >> 5) + ((uint32_t)tk >> 5)], 1u << ((uint32_t)tk & 31u));
+            if (counts_out) {
+                const uint32_t same = __match_any_sync(FULL, inside ? c : (0xFFFFFF00u + (uint32_t)lane));
+                if (inside) counts_out[(size_t)b * vocab + (uint32_t)tk] = (uint32_t)__popc(same);
+            }
+            return;
+        }
+    }
     uint2 *cur = lvl + b;
     if (lane == 0) {
         uint64_t s = sp[b], e = ep[b];
@@ -378,6 +422,8 @@ __device__ __forceinline__ void fm_enum_slice(const FmDev &ix, const uint2 *__re
         return;
     }
     const int hw = tid >> 4, hl = tid & 15;
+    // lane hl evaluates child digit hl: its bit-plane XOR masks are loop invariants
+    const uint32_t x0 = (hl & 1) ? 0u : ~0u, x1 = (hl & 2) ? 0u : ~0u, x2 = (hl & 4) ? 0u : ~0u, x3 = (hl & 8) ? 0u : ~0u;
     for (uint32_t l = LT; l < L; ++l) {
         const int cur = l & 1, nxt = cur ^ 1;
         const uint32_t n_nodes = S.fcount[cur];
@@ -388,68 +434,90 @@ __device__ __forceinline__ void fm_enum_slice(const FmDev &ix, const uint2 *__re
         const uint4 *lc = ix.cells + l * ix.level_stride;
         const uint32_t csh = 4u * (L - 1u - l);  // bits below a child's prefix
         const bool leaf = (l + 1 == L);
+        const bool allow_direct = leaf && !counts_row;
+        // software pipeline: the two cells of the NEXT node are already in flight (one uint4 per lane)
+        // while the current node is evaluated
+        uint32_t lo = 0, hi = 0, prefix = 0;
+        bool has = (uint32_t)hw < n_nodes;
+        if (has) {
+            lo = S.fr[cur][hw][0];
+            hi = S.fr[cur][hw][1];
+            prefix = S.fr[cur][hw][2];
+        }
+        bool heavy = has && !(allow_direct && hi - lo <= 64u);
+        uint4 pre = make_uint4(0, 0, 0, 0);
+        if (heavy) pre = fm_ldg(lc + (size_t)((hl < 8 ? lo : hi) >> 7) * FMIDX_CELL_U4 + (hl & 7));
         for (uint32_t base = 0; base < n_nodes; base += MASK_THREADS / 16) {
-            const uint32_t node = base + hw;
-            bool has = node < n_nodes;
-            uint32_t lo = 0, hi = 0, prefix = 0;
-            if (has) {
-                lo = S.fr[cur][node][0];
-                hi = S.fr[cur][node][1];
-                prefix = S.fr[cur][node][2];
+            const uint32_t nnode = base + MASK_THREADS / 16 + hw;
+            uint32_t nlo = 0, nhi = 0, npf = 0;
+            const bool nhas = nnode < n_nodes;
+            if (nhas) {
+                nlo = S.fr[cur][nnode][0];
+                nhi = S.fr[cur][nnode][1];
+                npf = S.fr[cur][nnode][2];
             }
-            if (leaf && !counts_row) {
+            const bool nheavy = nhas && !(allow_direct && nhi - nlo <= 64u);
+            uint4 npre = make_uint4(0, 0, 0, 0);
+            if (nheavy) npre = fm_ldg(lc + (size_t)((hl < 8 ? nlo : nhi) >> 7) * FMIDX_CELL_U4 + (hl & 7));
+
+            if (has && !heavy) {
                 // deepest level, narrow node: the distinct digits of <= 64 positions are cheaper to read
                 // off the bit-planes directly than to rank all 16 digits at both ends
                 const uint32_t w = hi - lo;
-                if (has && w <= 64u) {
-                    for (uint32_t t = (uint32_t)hl; t < w; t += 16) {
-                        const uint32_t q = lo + t;
-                        const uint4 pl = fm_ldg(lc + (size_t)(q >> 7) * FMIDX_CELL_U4 + 4 + ((q & 127u) >> 5));
-                        const uint32_t bt = q & 31u;
-                        const uint32_t dg = ((pl.x >> bt) & 1u) | (((pl.y >> bt) & 1u) << 1) | (((pl.z >> bt) & 1u) << 2) |
-                                            (((pl.w >> bt) & 1u) << 3);
-                        const uint32_t sy = (prefix << 4) | dg;
-                        if (sy >= sa && sy < se) {
-                            const uint32_t rel = (uint32_t)((int64_t)sy - shift) - t0;
-                            atomicOr(&S.bm[rel >> 5], 1u << (rel & 31u));
+                for (uint32_t t = (uint32_t)hl; t < w; t += 16) {
+                    const uint32_t q = lo + t;
+                    const uint4 pl = fm_ldg(lc + (size_t)(q >> 7) * FMIDX_CELL_U4 + 4 + ((q & 127u) >> 5));
+                    const uint32_t bt = q & 31u;
+                    const uint32_t dg = ((pl.x >> bt) & 1u) | (((pl.y >> bt) & 1u) << 1) | (((pl.z >> bt) & 1u) << 2) |
+                                        (((pl.w >> bt) & 1u) << 3);
+                    const uint32_t sy = (prefix << 4) | dg;
+                    if (sy >= sa && sy < se) {
+                        const uint32_t rel = (uint32_t)((int64_t)sy - shift) - t0;
+                        atomicOr(&S.bm[rel >> 5], 1u << (rel & 31u));
+                    }
+                }
+            }
+            if (__any_sync(FULL, heavy)) {
+                if (heavy) S.stage[hw][hl] = pre;
+                __syncwarp();
+                uint32_t r_lo = 0, r_hi = 0;
+                if (heavy) {
+                    r_lo = fm_rank_fast(&S.stage[hw][0], (uint32_t)hl, lo & 127u, x0, x1, x2, x3);
+                    r_hi = fm_rank_fast(&S.stage[hw][8], (uint32_t)hl, hi & 127u, x0, x1, x2, x3);
+                }
+                __syncwarp();
+                const uint32_t cp = (prefix << 4) | (uint32_t)hl;
+                const uint64_t c_lo = (uint64_t)cp << csh, c_hi = ((uint64_t)cp + 1) << csh;
+                const bool exists = heavy && r_hi > r_lo && c_lo < se && c_hi > sa;
+                const uint32_t bal = (__ballot_sync(FULL, exists) >> (lane & 16)) & 0xffffu;
+                if (leaf) {
+                    // the 16 children are 16 consecutive symbols: one lane ORs the whole presence mask
+                    if (hl == 0 && bal) {
+                        const int64_t r = (int64_t)((uint64_t)prefix << 4) - shift - (int64_t)t0;  // bit of digit 0
+                        if (r >= 0) {
+                            const uint64_t v = (uint64_t)bal << (r & 31);
+                            atomicOr(&S.bm[r >> 5], (uint32_t)v);
+                            if (v >> 32) atomicOr(&S.bm[(r >> 5) + 1], (uint32_t)(v >> 32));
+                        } else {
+                            atomicOr(&S.bm[0], bal >> (uint32_t)(-r));
                         }
                     }
-                    has = false;
-                }
-                if (!__any_sync(FULL, has)) continue;
-            }
-            const uint32_t pos = hl < 8 ? lo : hi;
-            if (has) S.stage[hw][hl] = fm_ldg(lc + (size_t)(pos >> 7) * FMIDX_CELL_U4 + (hl & 7));
-            __syncwarp();
-            uint32_t r_lo = 0, r_hi = 0;
-            if (has) {
-                r_lo = fm_rank_staged(&S.stage[hw][0], (uint32_t)hl, (int)(lo & 127u));
-                r_hi = fm_rank_staged(&S.stage[hw][8], (uint32_t)hl, (int)(hi & 127u));
-            }
-            __syncwarp();
-            const uint32_t cp = (prefix << 4) | (uint32_t)hl;
-            const uint64_t c_lo = (uint64_t)cp << csh, c_hi = ((uint64_t)cp + 1) << csh;
-            const bool exists = has && r_hi > r_lo && c_lo < se && c_hi > sa;
-            if (leaf) {
-                if (exists) {  // cp is a symbol of the slice
-                    const uint32_t tk = (uint32_t)((int64_t)cp - shift);
-                    atomicOr(&S.bm[(tk - t0) >> 5], 1u << ((tk - t0) & 31u));
-                    if (counts_row) counts_row[tk] = r_hi - r_lo;
-                }
-            } else {
-                const uint32_t bal = (__ballot_sync(FULL, exists) >> (lane & 16)) & 0xffffu;
-                uint32_t slot = 0;
-                if (hl == 0 && bal) slot = atomicAdd(&S.fcount[nxt], (uint32_t)__popc(bal));
-                slot = __shfl_sync(FULL, slot, lane & 16);
-                if (exists) {
-                    const uint32_t idx = slot + __popc(bal & ((1u << hl) - 1u));
-                    if (idx < MAXF) {
-                        S.fr[nxt][idx][0] = r_lo;
-                        S.fr[nxt][idx][1] = r_hi;
-                        S.fr[nxt][idx][2] = cp;
+                    if (counts_row && exists) counts_row[(uint32_t)((int64_t)cp - shift)] = r_hi - r_lo;
+                } else {
+                    uint32_t slot = 0;
+                    if (hl == 0 && bal) slot = atomicAdd(&S.fcount[nxt], (uint32_t)__popc(bal));
+                    slot = __shfl_sync(FULL, slot, lane & 16);
+                    if (exists) {
+                        const uint32_t idx = slot + __popc(bal & ((1u << hl) - 1u));
+                        if (idx < MAXF) {
+                            S.fr[nxt][idx][0] = r_lo;
+                            S.fr[nxt][idx][1] = r_hi;
+                            S.fr[nxt][idx][2] = cp;
+                        }
                     }
                 }
             }
+            lo = nlo; hi = nhi; prefix = npf; has = nhas; heavy = nheavy; pre = npre;
         }
         __syncthreads();
     }
@@ -489,6 +557,221 @@ k_mask_items(FmDev ix, const uint2 *__restrict__ top, uint32_t P_top, uint32_t L
         const uint32_t nw = (t1 - t0 + 31u) >> 5;
         for (uint32_t w = tid; w < nw; w += MASK_THREADS) mask_out[(size_t)b * mask_words + (t0 >> 5) + w] = S.bm[w];
     }
+}
+
+// ---- phase B, fused with the logits row: TMA-staged variant ---------------------------------------------
+// The slice of the logits row (16 KB fp32 / 8 KB bf16) is brought into shared memory by ONE bulk async
+// copy (cp.async.bulk global->shared, completion on an mbarrier; SASS UBLKCP) issued before the tree
+// walk, masked in place in shared memory, and written back by ONE bulk async store.  No registers hold
+// logits, so ~8 CTAs (128 KB of loads) are in flight per SM while walks are waiting on their probes.
+__device__ __forceinline__ uint32_t fm_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int DT>
+__global__ void __launch_bounds__(MASK_THREADS)
+k_mask_logits_tma(FmDev ix, const uint2 *__restrict__ top, uint32_t P_top, uint32_t LT, int64_t shift, uint32_t vocab,
+                  const void *logits_v, void *out_v, int64_t row_stride, const int32_t *__restrict__ override_tok,
+                  int32_t always_allow, const uint32_t *__restrict__ extra, uint32_t n_extra, uint32_t B,
+                  uint32_t *__restrict__ mask_out) {
+    using ET = typename Elem<DT>::T;
+    constexpr int VEC = Elem<DT>::VEC;
+    __shared__ __align__(128) uint4 buf[SLICE / VEC];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ EnumSmem S;
+    const int tid = threadIdx.x;
+    const uint32_t nslices = (vocab + SLICE - 1) / SLICE;
+    const uint32_t b = blockIdx.x / nslices;
+    const uint32_t t0 = (blockIdx.x % nslices) * SLICE;
+    const uint32_t t1 = min(t0 + (uint32_t)SLICE, vocab);
+    const uint32_t mask_words = (vocab + 31u) >> 5;
+    const uint32_t bytes = (t1 - t0) * (uint32_t)sizeof(ET);  // multiple of 16 (checked by the launcher)
+    const ET *row_in = reinterpret_cast<const ET *>(logits_v) + (size_t)b * row_stride + t0;
+    ET *row_out = reinterpret_cast<ET *>(out_v) + (size_t)b * row_stride + t0;
+    const uint32_t mb = fm_smem_u32(&mbar), sb = fm_smem_u32(buf);
+
+    // 1. one thread arms the barrier and launches the bulk load of the whole slice
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(sb), "l"(row_in), "r"(bytes), "r"(mb) : "memory");
+    }
+    // 2. bitmap of the slice (the walk overlaps the copy)
+    for (int w = tid; w < SLICE / 32; w += MASK_THREADS) S.bm[w] = 0;
+    const int32_t ovr = override_tok ? override_tok[b] : -1;
+    uint32_t sa, se;
+    fm_slice_interval(ix, t0, t1, shift, sa, se);
+    if (ovr < 0) fm_enum_slice(ix, top + (size_t)b * P_top, LT, sa, se, shift, t0, S, nullptr);
+    __syncthreads();
+    if (ovr >= 0) {
+        if (tid == 0 && (uint32_t)ovr >= t0 && (uint32_t)ovr < t1) S.bm[((uint32_t)ovr - t0) >> 5] = 1u << (((uint32_t)ovr - t0) & 31u);
+    } else if (n_extra) {
+        const uint32_t nw = (t1 - t0 + 31u) >> 5;
+        for (uint32_t w = tid; w < nw; w += MASK_THREADS) {
+            uint32_t acc = S.bm[w];
+            for (uint32_t x = 0; x < n_extra; ++x) acc |= extra[((size_t)x * B + b) * mask_words + (t0 >> 5) + w];
+            S.bm[w] = acc;
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && always_allow >= 0 && (uint32_t)always_allow >= t0 && (uint32_t)always_allow < t1)
+        S.bm[((uint32_t)always_allow - t0) >> 5] |= 1u << (((uint32_t)always_allow - t0) & 31u);
+    __syncthreads();
+    if (mask_out) {
+        const uint32_t nw = (t1 - t0 + 31u) >> 5;
+        for (uint32_t w = tid; w < nw; w += MASK_THREADS) mask_out[(size_t)b * mask_words + (t0 >> 5) + w] = S.bm[w];
+    }
+    // 3. wait for the slice, mask it in shared memory
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "FM_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra FM_DONE;\n"
+        "bra FM_WAIT;\n"
+        "FM_DONE:\n"
+        "}\n" ::"r"(mb) : "memory");
+    const uint32_t nvec = (t1 - t0) / VEC;
+    for (uint32_t v = tid; v < nvec; v += MASK_THREADS) {
+        const uint32_t rel = v * VEC;
+        const uint32_t bits = (S.bm[rel >> 5] >> (rel & 31u)) & ((1u << VEC) - 1u);
+        uint4 r = buf[v];
+        ET *x = reinterpret_cast<ET *>(&r);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) x[k] = fm_add_mask(x[k], (bits >> k) & 1u);
+        buf[v] = r;
+    }
+    // 4. make the generic-proxy writes visible to the async proxy, then one bulk store
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(row_out), "r"(sb), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+}
+
+// ---- phase B, fused with the logits row: persistent, multi-stage TMA pipeline ---------------------------
+// One-shot CTAs keep only ~16 KB of logits in flight per resident CTA for the whole CTA lifetime (issue
+// loads -> walk -> stores -> exit -> relaunch), which caps the stream at about half of HBM bandwidth.
+// Here PIPE_CTAS_PER_SM persistent CTAs per SM each own a PIPE_STAGES-deep ring of slice buffers in
+// shared memory: the bulk loads of the next (beam, slice) items are already in flight while the current
+// item is walked, masked in shared memory and bulk-stored.  Items are claimed from a global counter
+// (one atomicAdd per item, at load-issue time) so that the few heavy walks do not pile up on one CTA.
+constexpr int PIPE_STAGES = 2;
+constexpr int PIPE_CTAS_PER_SM = 5;
+
+template <int DT>
+__global__ void __launch_bounds__(MASK_THREADS)
+k_mask_logits_pipe(FmDev ix, const uint2 *__restrict__ top, uint32_t P_top, uint32_t LT, int64_t shift, uint32_t vocab,
+                   const void *logits_v, void *out_v, int64_t row_stride, const int32_t *__restrict__ override_tok,
+                   int32_t always_allow, const uint32_t *__restrict__ extra, uint32_t n_extra, uint32_t B,
+                   uint32_t *__restrict__ mask_out, uint32_t n_items, uint32_t *__restrict__ next_ptr) {
+    using ET = typename Elem<DT>::T;
+    constexpr int VEC = Elem<DT>::VEC;
+    constexpr uint32_t STAGE_BYTES = SLICE * sizeof(ET);
+    __shared__ uint32_t q_item[PIPE_STAGES];  // item claimed for each stage (claims are dynamic: heavy walks must not pile up)
+    extern __shared__ __align__(128) unsigned char ring[];  // PIPE_STAGES x STAGE_BYTES
+    __shared__ __align__(8) uint64_t mbar[PIPE_STAGES];
+    __shared__ EnumSmem S;
+    const int tid = threadIdx.x;
+    const uint32_t nslices = (vocab + SLICE - 1) / SLICE;
+    const uint32_t mask_words = (vocab + 31u) >> 5;
+    const ET *in_base = reinterpret_cast<const ET *>(logits_v);
+    ET *out_base = reinterpret_cast<ET *>(out_v);
+
+    auto issue_load = [&](uint32_t item, int stage) {  // thread 0 only
+        const uint32_t b = item / nslices, t0 = (item % nslices) * SLICE, t1 = min(t0 + (uint32_t)SLICE, vocab);
+        const uint32_t bytes = (t1 - t0) * (uint32_t)sizeof(ET);
+        const uint32_t mb = fm_smem_u32(&mbar[stage]), sb = fm_smem_u32(ring + (size_t)stage * STAGE_BYTES);
+        const ET *src = in_base + (size_t)b * row_stride + t0;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(sb), "l"(src), "r"(bytes), "r"(mb) : "memory");
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < PIPE_STAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fm_smem_u32(&mbar[s])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < PIPE_STAGES; ++s) {
+            const uint32_t item = atomicAdd(next_ptr, 1u);
+            q_item[s] = item;
+            if (item < n_items) issue_load(item, s);
+        }
+    }
+    for (uint32_t k = 0;; ++k) {
+        const int stage = (int)(k % PIPE_STAGES);
+        __syncthreads();
+        const uint32_t item = q_item[stage];
+        if (item >= n_items) break;  // claims are handed out in order: nothing left for this CTA
+        const uint32_t parity = (k / PIPE_STAGES) & 1u;
+        const uint32_t b = item / nslices, t0 = (item % nslices) * SLICE, t1 = min(t0 + (uint32_t)SLICE, vocab);
+        // bitmap of the slice (overlaps the loads in flight)
+        for (int w = tid; w < SLICE / 32; w += MASK_THREADS) S.bm[w] = 0;
+        const int32_t ovr = override_tok ? override_tok[b] : -1;
+        uint32_t sa, se;
+        fm_slice_interval(ix, t0, t1, shift, sa, se);
+        if (ovr < 0) fm_enum_slice(ix, top + (size_t)b * P_top, LT, sa, se, shift, t0, S, nullptr);
+        __syncthreads();
+        if (ovr >= 0) {
+            if (tid == 0 && (uint32_t)ovr >= t0 && (uint32_t)ovr < t1) S.bm[((uint32_t)ovr - t0) >> 5] = 1u << (((uint32_t)ovr - t0) & 31u);
+        } else if (n_extra) {
+            const uint32_t nw = (t1 - t0 + 31u) >> 5;
+            for (uint32_t w = tid; w < nw; w += MASK_THREADS) {
+                uint32_t acc = S.bm[w];
+                for (uint32_t x = 0; x < n_extra; ++x) acc |= extra[((size_t)x * B + b) * mask_words + (t0 >> 5) + w];
+                S.bm[w] = acc;
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && always_allow >= 0 && (uint32_t)always_allow >= t0 && (uint32_t)always_allow < t1)
+            S.bm[((uint32_t)always_allow - t0) >> 5] |= 1u << (((uint32_t)always_allow - t0) & 31u);
+        __syncthreads();
+        if (mask_out) {
+            const uint32_t nw = (t1 - t0 + 31u) >> 5;
+            for (uint32_t w = tid; w < nw; w += MASK_THREADS) mask_out[(size_t)b * mask_words + (t0 >> 5) + w] = S.bm[w];
+        }
+        // wait for this stage's slice, mask it in shared memory
+        const uint32_t mb = fm_smem_u32(&mbar[stage]);
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "FM_PWAIT:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra FM_PDONE;\n"
+            "bra FM_PWAIT;\n"
+            "FM_PDONE:\n"
+            "}\n" ::"r"(mb), "r"(parity) : "memory");
+        uint4 *buf = reinterpret_cast<uint4 *>(ring + (size_t)stage * STAGE_BYTES);
+        const uint32_t nvec = (t1 - t0) / VEC;
+        for (uint32_t v = tid; v < nvec; v += MASK_THREADS) {
+            const uint32_t rel = v * VEC;
+            const uint32_t bits = (S.bm[rel >> 5] >> (rel & 31u)) & ((1u << VEC) - 1u);
+            uint4 r = buf[v];
+            ET *x = reinterpret_cast<ET *>(&r);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) x[e] = fm_add_mask(x[e], (bits >> e) & 1u);
+            buf[v] = r;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t bytes = (t1 - t0) * (uint32_t)sizeof(ET);
+            ET *dst = out_base + (size_t)b * row_stride + t0;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(fm_smem_u32(buf)), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            // a stage may be refilled once its store has READ it (not once the write has landed): allow
+            // this item's store to stay outstanding and refill the PREVIOUS item's stage
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            if (k > 0) {
+                const int ps = (int)((k - 1) % PIPE_STAGES);
+                const uint32_t nxt = atomicAdd(next_ptr, 1u);
+                q_item[ps] = nxt;
+                if (nxt < n_items) issue_load(nxt, ps);
+            }
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the last store's read
 }
 
 // ---- phase B, fused with the logits row -------------------------------------------------------------------
@@ -812,7 +1095,7 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
         FM_CUDA(cudaMemsetAsync(d_mask, 0, B * (size_t)((vocab + 31) / 32) * 4, s));
     }
     FM_LAUNCH(k_mask_top, (unsigned)((B * 32 + 127) / 128), 128, 0, s, ix, d_sp, d_ep, (uint32_t)B, LT, lvl, d_override, shift,
-              vocab, items, ctr);
+              vocab, items, ctr, has ? nullptr : d_mask, has ? nullptr : d_counts);
     if (!has) {
         const unsigned grid = (unsigned)std::min<size_t>(nblk, (size_t)h->sm_count * 16);
         FM_LAUNCH(k_mask_items, grid, MASK_THREADS, 0, s, ix, lvl + top_off, P_top, LT, shift, vocab, items, ctr, ctr + 1,
@@ -829,12 +1112,56 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
 #define FM_MASK_CASE(DT, VECT)                                                                                     \
     FM_LAUNCH((k_mask_logits<DT, VECT>), grid, MASK_THREADS, 0, s, ix, lvl + top_off, P_top, LT, shift, vocab, d_logits, \
               d_out, row_stride, d_override, always_allow, d_extra, n_extra, (uint32_t)B, d_mask)
+#define FM_MASK_TMA(DT)                                                                                            \
+    FM_LAUNCH((k_mask_logits_tma<DT>), grid, MASK_THREADS, 0, s, ix, lvl + top_off, P_top, LT, shift, vocab, d_logits,   \
+              d_out, row_stride, d_override, always_allow, d_extra, n_extra, (uint32_t)B, d_mask)
+    // FMIDX_LOGITS_PATH = pipe (default: persistent multi-stage TMA pipeline) | tma (one-shot CTAs, one bulk
+    // copy each) | regs (one-shot CTAs, register staging); the last two are kept for A/B timing and tests
+    const char *path = getenv("FMIDX_LOGITS_PATH");
+    const bool tma = !(path && strcmp(path, "regs") == 0);
+    const bool pipe = !path || strcmp(path, "pipe") == 0;
+    const int esz = dtype == FMIDX_F32 ? 4 : 2;
+    if (pipe && (dtype == FMIDX_F32 || dtype == FMIDX_BF16 || dtype == FMIDX_F16) && aligned(esz)) {
+        const int dyn = PIPE_STAGES * SLICE * esz;
+        const unsigned pgrid = (unsigned)std::min<size_t>(nblk, (size_t)h->sm_count * PIPE_CTAS_PER_SM);
+        FM_CUDA(cudaMemsetAsync(ctr, 0, 8, s));
+#define FM_MASK_PIPE(DT)                                                                                            \
+    do {                                                                                                            \
+        static bool attr_set = false;                                                                               \
+        if (!attr_set) {                                                                                            \
+            FM_CUDA(cudaFuncSetAttribute(k_mask_logits_pipe<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)); \
+            attr_set = true;                                                                                        \
+        }                                                                                                           \
+        FM_LAUNCH((k_mask_logits_pipe<DT>), pgrid, MASK_THREADS, dyn, s, ix, lvl + top_off, P_top, LT, shift, vocab,    \
+                  d_logits, d_out, row_stride, d_override, always_allow, d_extra, n_extra, (uint32_t)B, d_mask,     \
+                  (uint32_t)nblk, ctr + 1);                                                                                \
+    } while (0)
+        if (dtype == FMIDX_F32) FM_MASK_PIPE(FMIDX_F32);
+        else if (dtype == FMIDX_BF16) FM_MASK_PIPE(FMIDX_BF16);
+        else FM_MASK_PIPE(FMIDX_F16);
+#undef FM_MASK_PIPE
+        FM_CUDA(cudaGetLastError());
+        return FMIDX_OK;
+    }
     switch (dtype) {
-        case FMIDX_F32: if (aligned(4)) FM_MASK_CASE(FMIDX_F32, true); else FM_MASK_CASE(FMIDX_F32, false); break;
-        case FMIDX_BF16: if (aligned(2)) FM_MASK_CASE(FMIDX_BF16, true); else FM_MASK_CASE(FMIDX_BF16, false); break;
-        case FMIDX_F16: if (aligned(2)) FM_MASK_CASE(FMIDX_F16, true); else FM_MASK_CASE(FMIDX_F16, false); break;
+        case FMIDX_F32:
+            if (aligned(4) && tma) FM_MASK_TMA(FMIDX_F32);
+            else if (aligned(4)) FM_MASK_CASE(FMIDX_F32, true);
+            else FM_MASK_CASE(FMIDX_F32, false);
+            break;
+        case FMIDX_BF16:
+            if (aligned(2) && tma) FM_MASK_TMA(FMIDX_BF16);
+            else if (aligned(2)) FM_MASK_CASE(FMIDX_BF16, true);
+            else FM_MASK_CASE(FMIDX_BF16, false);
+            break;
+        case FMIDX_F16:
+            if (aligned(2) && tma) FM_MASK_TMA(FMIDX_F16);
+            else if (aligned(2)) FM_MASK_CASE(FMIDX_F16, true);
+            else FM_MASK_CASE(FMIDX_F16, false);
+            break;
         default: fm_set_error("unknown logits dtype %d", dtype); return FMIDX_EINVAL;
     }
+#undef FM_MASK_TMA
 #undef FM_MASK_CASE
     FM_CUDA(cudaGetLastError());
     return FMIDX_OK;

@@ -146,10 +146,13 @@ def test_step_batch_and_raw_multi(cuda):
         assert ix.backward_search_multi(q) == o.backward_search_multi(q), q
 
 
+@pytest.mark.parametrize("path", ["pipe", "tma", "regs"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
-def test_fused_mask_logits_vs_reference_arithmetic(cuda, dtype):
-    """document_constrained_generation_vllm.py:46-137 on a [B, V] batch (config 4 semantics)."""
+def test_fused_mask_logits_vs_reference_arithmetic(cuda, dtype, path, monkeypatch):
+    """document_constrained_generation_vllm.py:46-137 on a [B, V] batch (config 4 semantics);
+    both logits staging variants (bulk-async-copy through shared memory / registers)."""
     from oracle.oracle import hard_mask_reference
+    monkeypatch.setenv("FMIDX_LOGITS_PATH", path)
     rng = random.Random(9)
     V, eos, pad = 128256, 128009, 128004
     docs = random_docs(rng, 5000, 150, 30, 300)
