@@ -274,32 +274,51 @@ def main():
     words = (VOCAB + 31) // 32
     stream = torch.cuda.current_stream()
     sptr = C.c_void_p(stream.cuda_stream)
-    sp = torch.empty(B, dtype=torch.int64, device=device)
-    ep = torch.empty(B, dtype=torch.int64, device=device)
-    mask = torch.empty((B, words), dtype=torch.int32, device=device)
+    # two buffer sets: with N > 1 the cross-shard exchange of step k runs on its own stream while the
+    # kernels of step k+1 fill the other set
+    bufs = [(torch.empty(B, dtype=torch.int64, device=device), torch.empty(B, dtype=torch.int64, device=device),
+             torch.empty((B, words), dtype=torch.int32, device=device)) for _ in range(2 if world > 1 else 1)]
+    sp, ep, mask = bufs[0]
     own = B // world  # prefixes whose final mask this rank owns
     from fm_index_constrained_decoding_b200 import sharded
     result = {}
+    comm_stream = torch.cuda.Stream(device=device) if world > 1 else None
+    ev_kernels = [torch.cuda.Event() for _ in bufs]
+    ev_comm = [torch.cuda.Event() for _ in bufs]
 
     def step_full(k, ev=None, q_off=None):
         q, offs = q_off if q_off is not None else qsets[k % N_QUERY_SETS]
+        bi = k % len(bufs)
+        bsp, bep, bmask = bufs[bi]
+        if world > 1:
+            stream.wait_event(ev_comm[bi])  # the exchange that last read this buffer set has finished
         if ev:
             ev[0].record(stream)
         _native.check(L.fmidx_search_batch(ix._h, C.c_void_p(q.data_ptr()), C.c_void_p(offs.data_ptr()), B, SHIFT,
-                                           C.c_void_p(sp.data_ptr()), C.c_void_p(ep.data_ptr()), sptr))
+                                           C.c_void_p(bsp.data_ptr()), C.c_void_p(bep.data_ptr()), sptr))
         if ev:
             ev[1].record(stream)
-        _native.check(L.fmidx_distinct_mask_batch(ix._h, C.c_void_p(sp.data_ptr()), C.c_void_p(ep.data_ptr()), B, SHIFT, VOCAB,
-                                                  C.c_void_p(mask.data_ptr()), None, sptr))
+        _native.check(L.fmidx_distinct_mask_batch(ix._h, C.c_void_p(bsp.data_ptr()), C.c_void_p(bep.data_ptr()), B, SHIFT, VOCAB,
+                                                  C.c_void_p(bmask.data_ptr()), None, sptr))
         if ev:
             ev[2].record(stream)
         if world > 1:
             # OR-reduce-scatter of the per-shard masks (all-to-all + fmidx_mask_or): rank r ends up owning the
-            # final masks of prefixes [r*B/W, (r+1)*B/W); total occurrence counts all-reduced (sum)
-            result["mask"] = sharded.or_reduce_scatter(mask, index=ix)[1]
-            result["count"] = sharded.sum_counts(sp, ep)
+            # final masks of prefixes [r*B/W, (r+1)*B/W); total occurrence counts all-reduced (sum).  Runs on
+            # the exchange stream, overlapping the next step's kernels.
+            ev_kernels[bi].record(stream)
+            with torch.cuda.stream(comm_stream):
+                comm_stream.wait_event(ev_kernels[bi])
+                result["mask"] = sharded.or_reduce_scatter(bmask, index=ix)[1]
+                result["count"] = sharded.sum_counts(bsp, bep)
+                ev_comm[bi].record(comm_stream)
         else:
-            result["mask"] = mask
+            result["mask"] = bmask
+
+    def drain():
+        if world > 1:
+            for e in ev_comm:
+                stream.wait_event(e)
 
     def barrier():
         if world > 1:
@@ -319,6 +338,7 @@ def main():
     e_start.record(stream)
     for k in range(args.steps):
         step_full(k, evs[k])
+    drain()  # the timed region ends when the last exchange has completed
     e_end.record(stream)
     barrier()
     total_ms = e_start.elapsed_time(e_end)
@@ -424,9 +444,10 @@ def main():
             doff = dq[0][1]
             doff.copy_(offs, non_blocking=True)
             step_full(k, q_off=(dtok, doff))
+            drain()
             _native.check(L.fmidx_mask_popcount(ix._h, C.c_void_p(result["mask"].data_ptr()), own, VOCAB, C.c_void_p(n32.data_ptr()), sptr))
-            hsp.copy_(sp, non_blocking=True)
-            hep.copy_(ep, non_blocking=True)
+            hsp.copy_(bufs[k % len(bufs)][0], non_blocking=True)
+            hep.copy_(bufs[k % len(bufs)][1], non_blocking=True)
             hcnt.copy_(result["count"], non_blocking=True)
             hnd[:own].copy_(n32, non_blocking=True)
             torch.cuda.current_stream().synchronize()

@@ -43,7 +43,7 @@ def timed(fn, steps, warmup=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--tokens", type=int, default=100_000_000)
-    ap.add_argument("--what", default="decode,locate,sweep,negative")
+    ap.add_argument("--what", default="config0,decode,locate,sweep,negative")
     ap.add_argument("--steps", type=int, default=50)
     args = ap.parse_args()
     what = set(args.what.split(","))
@@ -55,6 +55,35 @@ def main():
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
         pass
+    if "config0" in what:
+        # configs[0]: sample corpus (stand-in tokenizer, tests/golden/sample_corpus.json), batch 1, through the
+        # reference-shaped scalar API: latency, not throughput (one launch + sync per call on the GPU)
+        g = json.load(open(os.path.join(ROOT, "tests", "golden", "sample_corpus.json")))
+        from oracle.oracle import OracleFMIndex
+        small = FMIndex(device=0)
+        small.initialize(g["docs"], in_memory=True)
+        o = OracleFMIndex()
+        o.initialize(g["docs"])
+        qs0 = [q["q"] for q in g["queries"]]
+
+        def run(ixx, reps):
+            t = time.perf_counter()
+            for _ in range(reps):
+                for q in qs0:
+                    r = ixx.get_range(q)
+                    ixx.get_distinct_count(*r)
+            return (time.perf_counter() - t) / (reps * len(qs0)) * 1e6
+        run(small, 2)
+        gpu_us = run(small, 10)
+        run(o, 2)
+        cpu_us = run(o, 10)
+        print(json.dumps({"config": "configs[0] sample_corpus.tsv (stand-in tokenizer), batch 1: get_range + get_distinct_count",
+                          "tokens": g["size"] - 1, "gpu_us_per_query": gpu_us, "cpu_oracle_us_per_query": cpu_us,
+                          "note": "latency-dominated: each scalar GPU call is launch + synchronise; the CPU oracle keeps the "
+                                  "reference's 3 x sigma allocation per distinct_count call"}), flush=True)
+        del small, o
+    if not (what - {"config0"}):
+        return
     toks, beg = synth.zipf_corpus(args.tokens, seed=0, device=dev)
     t0 = time.time()
     ix = FMIndex(device=0)
@@ -136,14 +165,20 @@ def main():
             rows = torch.where(valid, rows, torch.zeros_like(rows)).contiguous().view(-1)
             n_hits = int(valid.sum())
             ms_search = timed(lambda: ix2.get_range_batch(q, offs), 10)
-            ms_loc = timed(lambda: ix2.locate_batch(rows), 10)
-            pos = ix2.locate_batch(rows)
+            ms_loc_hits = timed(lambda: ix2.locate_batch(rows), 10)
+            # throughput on independent rows: most prefixes of this corpus have < 8 matches, so the hit rows above
+            # repeat row 0; uniform random rows are the honest locate/extract load
+            gr = torch.Generator(device=dev).manual_seed(11)
+            rrows = torch.randint(0, ix2.size(), (Q * K,), generator=gr, device=dev)
+            ms_loc = timed(lambda: ix2.locate_batch(rrows), 10)
+            pos = ix2.locate_batch(rrows)
             begins = pos.clamp(min=0)
             ends = (begins + M).clamp(max=ix2.size())
             ms_ext = timed(lambda: ix2.extract_batch(begins, ends, M), 10)
             print(json.dumps({"config": "configs[4] single shard: 65536 prefixes, locate K=8 + extract 32", "variant": label,
                               "tokens": args.tokens, "index_mb": ix2.info()["device_bytes"] / 1e6, "search_ms": ms_search,
-                              "search_qps": Q / ms_search * 1e3, "locate_ms": ms_loc, "rows_located": Q * K, "valid_hits": n_hits,
+                              "search_qps": Q / ms_search * 1e3, "valid_hits": n_hits, "locate_hit_rows_ms": ms_loc_hits,
+                              "locate_random_rows_ms": ms_loc, "rows_located": Q * K,
                               "locates_per_sec": Q * K / ms_loc * 1e3, "extract_ms": ms_ext,
                               "extracts_per_sec": Q * K / ms_ext * 1e3, "tokens_extracted_per_sec": Q * K * M / ms_ext * 1e3}), flush=True)
             if kw:

@@ -362,3 +362,25 @@ def test_large_properties(cuda):
     assert torch.equal(torch.isfinite(out).cpu(), bits)
     assert torch.equal(out.cpu()[bits], (logits.cpu() + 0.0)[bits])
     assert beg_l[0] == 0
+
+
+@pytest.mark.parametrize("layout", ["resident", "sampled"])
+def test_sample_corpus_config0(cuda, layout):
+    """BASELINE configs[0]: the reference's sample corpus (stand-in tokenizer), single-prefix search +
+    distinct next-token query, batch 1, through the reference-shaped API; index built via the
+    temporary int32 file exactly like index.py:57-66."""
+    from conftest import load_golden
+    from fm_index_constrained_decoding_b200 import FMIndex
+    g = load_golden("sample_corpus.json")
+    ix = FMIndex(layout=layout)
+    ix.initialize(g["docs"], in_memory=False)
+    ix.labels = g["labels"]
+    assert ix.size() == g["size"] and ix.n_docs == 10
+    for q in g["queries"]:
+        r = ix.get_range(q["q"])
+        assert list(r) == q["range"]
+        assert ix.get_distinct_count(*r) == (q["distinct"], q["counts"])
+        assert [ix.locate(x) for x in range(*r)][:16] == q["locate"]
+        assert list(ix.get_doc_indices(q["q"]))[:16] == [ix.get_doc_index(p) for p in q["locate"]]
+    assert [list(x) for x in (ix.occurring_distinct, ix.occurring_counts)] == g["occurring"]
+    assert [ix.get_doc(i) for i in range(10)] == g["get_doc"]

@@ -130,3 +130,20 @@ def test_query_batch_threads_agree():
         d, _ = o.get_distinct_count(int(sp1[k]), int(ep1[k]))
         bits = [v for v in range(320) if (m1[k, v >> 5] >> (v & 31)) & 1]
         assert bits == d
+
+
+def test_sample_corpus_config0_golden():
+    """BASELINE configs[0]: test_data/sample_corpus.tsv through a stand-in tokenizer (see
+    tests/golden/make_sample_corpus_golden.py); expectations from the brute-force model."""
+    from conftest import load_golden
+    g = load_golden("sample_corpus.json")
+    o = OracleFMIndex()
+    o.initialize(g["docs"])
+    assert o.size() == g["size"] and o.n_docs == 10
+    for q in g["queries"]:
+        r = o.get_range(q["q"])
+        assert list(r) == q["range"]
+        assert o.get_distinct_count(*r) == (q["distinct"], q["counts"])
+        assert [o.locate(x) for x in range(*r)][:16] == q["locate"]
+    assert [list(x) for x in (o.occurring_distinct, o.occurring_counts)] == g["occurring"]
+    assert [o.get_doc(i) for i in range(10)] == g["get_doc"]
