@@ -152,8 +152,8 @@ def main():
     if "locate" in what:
         Q, K, M = 65536, 8, 32
         q, offs = synth.sample_queries(toks, Q, seed=700, beginnings=beg)
-        for label, kw in [("sampled sa_dens=32 isa_dens=64 (reference defaults)", {}),
-                          ("resident sa_dens=1 isa_dens=1 keep_text", {"sa_dens": 1, "isa_dens": 1, "keep_text": True})]:
+        for label, kw in [("sampled sa_dens=32 isa_dens=64 (reference defaults)", {"layout": "sampled"}),
+                          ("resident sa_dens=1 isa_dens=1 keep_text (default)", {})]:
             if kw:
                 ix2 = FMIndex(device=0, **kw)
                 ix2.initialize_from_device_tokens(toks, beg)

@@ -181,9 +181,24 @@ class FMIndex:
 
 def load_FMIndex(path, device=None):
     """fm_index.cpp:201-209.  Returns an FMIndex whose __class__ may be re-assigned by the
-    caller exactly like the reference does (index.py:203)."""
+    caller exactly like the reference does (index.py:203).  Accepts both this library's own
+    container and an sdsl `csa_wt_int<>` dump written by the reference's FMIndex::save (converted
+    on the fly, see sdsl_format.py)."""
+    from . import sdsl_format
+    dev = N.default_device() if device is None else int(device)
+    if not sdsl_format.is_own_container(path):
+        import torch
+        tdev = torch.device("cuda", dev)
+        text, _ = sdsl_format.text_from_sdsl_file(path, tdev)
+        sym = text.to(torch.int32).contiguous()
+        obj = FMIndex(device=dev)
+        with torch.cuda.device(tdev):
+            N.check(N.lib().fmidx_initialize_device(obj._h, C.c_void_p(sym.data_ptr()), sym.numel(),
+                                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            torch.cuda.current_stream().synchronize()
+        return obj
     h = C.c_void_p()
-    N.check(N.lib().fmidx_load(str(path).encode(), N.default_device() if device is None else int(device), C.byref(h)))
+    N.check(N.lib().fmidx_load(str(path).encode(), dev, C.byref(h)))
     obj = FMIndex.__new__(FMIndex)
     obj._h = h
     return obj

@@ -559,3 +559,118 @@ void fmo_locate_batch(void *h, const u64 *rows, u64 B, u64 *pos, int nthreads) {
     for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
     free(th); free(jobs);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * store_to_file(index, path)  (FMIndex::save, fm_index.cpp:196-199) in sdsl-lite's serialisation
+ * layout AS RECALLED from sdsl-lite v2.1.1 (csa_wt::serialize -> wt_int::serialize ->
+ * int_vector / rank_support_v / select_support_mcl serialize; int_alphabet::serialize).
+ * UNVERIFIED against a real sdsl-lite build (none available): it exists so that the product's
+ * sdsl reader (fm_index_constrained_decoding_b200/sdsl_format.py) has files to parse in tests.
+ * ---------------------------------------------------------------------------------------- */
+static void w_u64(FILE *f, u64 v) { fwrite(&v, 8, 1, f); }
+static u32 bits_hi_plus1(u64 x) { u32 b = 0; while (x >> 1) { x >>= 1; b++; } return b + 1; }
+
+static void w_int_vector0(FILE *f, const u64 *vals, u64 count, unsigned width) {
+    u64 nbits = count * width;
+    w_u64(f, nbits);
+    unsigned char w8 = (unsigned char)width;
+    fwrite(&w8, 1, 1, f);
+    u64 nwords = (nbits + 63) >> 6;
+    u64 *buf = (u64 *)calloc((size_t)(nwords + 1), 8);
+    for (u64 i = 0; i < count; i++) {
+        u64 bit = i * width, v = width < 64 ? (vals[i] & ((1ULL << width) - 1)) : vals[i];
+        buf[bit >> 6] |= v << (bit & 63);
+        if ((bit & 63) + width > 64) buf[(bit >> 6) + 1] |= v >> (64 - (bit & 63));
+    }
+    fwrite(buf, 8, (size_t)nwords, f);
+    free(buf);
+}
+static void w_bit_vector(FILE *f, const u64 *words, u64 nbits) {
+    w_u64(f, nbits);
+    fwrite(words, 8, (size_t)((nbits + 63) >> 6), f);
+}
+static void w_rank_v(FILE *f, const u64 *bv, u64 nbits) { /* rank_support_v::m_basic_block : int_vector<64> */
+    u64 nsb = (nbits >> 9) + 1, nwords = (nbits + 63) >> 6, abs = 0;
+    w_u64(f, nsb * 2 * 64);
+    for (u64 sb = 0; sb < nsb; sb++) {
+        u64 rel = 0, second = 0;
+        for (u64 w = 0; w < 8; w++) {
+            if (w > 0) second |= rel << (63 - 9 * w);
+            if (sb * 8 + w < nwords) rel += (u64)__builtin_popcountll(bv[sb * 8 + w]);
+        }
+        w_u64(f, abs);
+        w_u64(f, second);
+        abs += rel;
+    }
+}
+static void w_select_mcl(FILE *f, const u64 *bv, u64 nbits, int bit) {
+    u64 cnt = 0;
+    for (u64 i = 0; i < nbits; i++) cnt += (((bv[i >> 6] >> (i & 63)) & 1) == (u64)bit);
+    w_u64(f, cnt);
+    if (!cnt) return;
+    u64 sb = (cnt + 4095) >> 12;
+    u32 logn = bits_hi_plus1(nbits);
+    u64 logn4 = (u64)logn * logn * logn * logn;
+    u64 *pos = (u64 *)malloc((size_t)cnt * 8), k = 0;
+    for (u64 i = 0; i < nbits; i++)
+        if (((bv[i >> 6] >> (i & 63)) & 1) == (u64)bit) pos[k++] = i;
+    u64 *sup = (u64 *)malloc((size_t)sb * 8), *mol = (u64 *)calloc((size_t)((sb + 63) / 64 + 1), 8);
+    for (u64 s = 0; s < sb; s++) {
+        sup[s] = pos[s * 4096];
+        u64 last = (s + 1) * 4096 - 1 < cnt ? (s + 1) * 4096 - 1 : cnt - 1;
+        if (!(pos[last] - pos[s * 4096] > logn4)) mol[s >> 6] |= 1ULL << (s & 63); /* 1 = miniblock */
+    }
+    w_int_vector0(f, sup, sb, logn);
+    w_bit_vector(f, mol, sb);
+    for (u64 s = 0; s < sb; s++) {
+        u64 first = s * 4096, last = first + 4095 < cnt ? first + 4095 : cnt - 1;
+        if ((mol[s >> 6] >> (s & 63)) & 1) {
+            u64 mini[64];
+            memset(mini, 0, sizeof(mini));
+            for (u64 j = 0; j < 64 && first + j * 64 <= last; j++) mini[j] = pos[first + j * 64] - pos[first];
+            w_int_vector0(f, mini, 64, bits_hi_plus1(pos[last] - pos[first]));
+        } else {
+            u64 *lng = (u64 *)calloc(4096, 8);
+            for (u64 j = 0; first + j <= last; j++) lng[j] = pos[first + j];
+            w_int_vector0(f, lng, 4096, bits_hi_plus1(pos[last]));
+            free(lng);
+        }
+    }
+    free(pos); free(sup); free(mol);
+}
+
+int fmo_store_sdsl(void *h, const char *path) {
+    const fmo_t *x = (const fmo_t *)h;
+    FILE *f = fopen(path, "wb");
+    if (!f) return -1;
+    /* wt_int */
+    w_u64(f, x->n);
+    w_u64(f, x->sigma);
+    w_bit_vector(f, x->tree, x->tree_bits);
+    w_rank_v(f, x->tree, x->tree_bits);
+    w_select_mcl(f, x->tree, x->tree_bits, 1);
+    w_select_mcl(f, x->tree, x->tree_bits, 0);
+    fwrite(&x->max_level, 4, 1, f);
+    /* sa / isa samples */
+    unsigned wn = bits_hi_plus1(x->n);
+    u64 nsa = (x->n + SA_DENS - 1) / SA_DENS, nisa = (x->n + ISA_DENS - 1) / ISA_DENS;
+    u64 *tmp = (u64 *)malloc((size_t)(nsa > nisa ? nsa : nisa) * 8 + 8);
+    for (u64 i = 0; i < nsa; i++) tmp[i] = x->sa_sample[i];
+    w_int_vector0(f, tmp, nsa, wn);
+    for (u64 i = 0; i < nisa; i++) tmp[i] = x->isa_sample[i];
+    w_int_vector0(f, tmp, nisa, wn);
+    free(tmp);
+    /* int_alphabet: m_char, m_char_rank, m_char_select, m_C, m_sigma */
+    u64 nchar = x->max_sym + 1;
+    u64 *cb = (u64 *)calloc((size_t)((nchar + 63) / 64 + 1), 8);
+    for (u64 c = 0; c < nchar; c++)
+        if (x->char2comp[c] >= 0) cb[c >> 6] |= 1ULL << (c & 63);
+    w_bit_vector(f, cb, nchar);
+    w_rank_v(f, cb, nchar);
+    w_select_mcl(f, cb, nchar, 1);
+    free(cb);
+    w_int_vector0(f, x->C, x->sigma + 1, wn);
+    w_u64(f, x->sigma);
+    fclose(f);
+    return 0;
+}

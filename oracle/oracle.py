@@ -54,6 +54,8 @@ def lib():
         L.fmo_get_range.argtypes = [p, p, u64, C.c_int64, p]
         L.fmo_query_batch.argtypes = [p, p, p, u64, C.c_int64, p, p, p, u64, u64, p, C.c_int]
         L.fmo_locate_batch.argtypes = [p, p, u64, p, C.c_int]
+        L.fmo_store_sdsl.restype = C.c_int
+        L.fmo_store_sdsl.argtypes = [p, C.c_char_p]
         _LIB = L
     return _LIB
 
@@ -87,6 +89,11 @@ class NativeOracle:
 
     def size(self):
         return int(lib().fmo_size(self._h))
+
+    def save(self, path):
+        """FMIndex::save (fm_index.cpp:196-199) in sdsl's layout as recalled (see fm_oracle.c)."""
+        if lib().fmo_store_sdsl(self._h, str(path).encode()) != 0:
+            raise IOError("cannot write %s" % path)
 
     def sigma(self):
         return int(lib().fmo_sigma(self._h))
