@@ -37,6 +37,10 @@ VOCAB, EOS, SHIFT = 128256, 128009, 10
 BYTES_PER_SEARCH_STEP = 1088      # 2 boundaries x 17 levels x 32-B rank cell
 MASK_BYTES = 16032                # one 128,256-bit vocab mask
 N_QUERY_SETS = 8                  # distinct prefix batches rotated through the timed steps
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of this very
+# command (profiles/r1_v1_ncu_full_summary.csv; 100M tokens, batch 4096).  k_mask = k_mask_top +
+# k_mask_items + the 65.7 MB memset of the mask rows that precedes them.
+NCU_TRAFFIC = {"k_mask": 3.25e6 + 44.33e6 + 0.72e6 + 65.7e6, "k_search": 9.25e6}
 
 
 _JSON_OUT = None
@@ -402,14 +406,16 @@ def main():
     peak, peak_src = measured_peaks()
     if t_mask >= t_search:
         dom = {"kernel": "k_mask (distinct-token enumeration -> vocab bitmap)", "bound": "hbm",
-               "achieved": bytes_mask / (t_mask * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "traffic": None,
+               "achieved": bytes_mask / (t_mask * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+               "traffic": NCU_TRAFFIC["k_mask"] if args.tokens == 100_000_000 and B == 4096 else None,
                "algorithmic_bytes_per_launch": bytes_mask, "avg_launch_ms": t_mask,
                "per_unit": "64 B per visited node of the 17-level binary tree (sum over levels of distinct prefixes, "
                            "SURVEY 8(d)) + 16,032 B mask per prefix",
                "own_layout_bytes_per_launch": bytes_mask_own, "distinct_symbols_per_launch": distinct_total}
     else:
         dom = {"kernel": "k_search (batched backward search)", "bound": "hbm",
-               "achieved": bytes_search / (t_search * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "traffic": None,
+               "achieved": bytes_search / (t_search * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+               "traffic": NCU_TRAFFIC["k_search"] if args.tokens == 100_000_000 and B == 4096 else None,
                "algorithmic_bytes_per_launch": bytes_search, "avg_launch_ms": t_search,
                "per_unit": "1,088 B per executed backward-search step (2 x 17 x 32 B)",
                "own_layout_bytes_per_launch": 1280 * search_steps}

@@ -1115,11 +1115,14 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
 #define FM_MASK_TMA(DT)                                                                                            \
     FM_LAUNCH((k_mask_logits_tma<DT>), grid, MASK_THREADS, 0, s, ix, lvl + top_off, P_top, LT, shift, vocab, d_logits,   \
               d_out, row_stride, d_override, always_allow, d_extra, n_extra, (uint32_t)B, d_mask)
-    // FMIDX_LOGITS_PATH = pipe (default: persistent multi-stage TMA pipeline) | tma (one-shot CTAs, one bulk
-    // copy each) | regs (one-shot CTAs, register staging); the last two are kept for A/B timing and tests
+    // FMIDX_LOGITS_PATH = regs (default: one-shot CTAs, logits staged in registers -- the fastest measured,
+    // 0.83 of HBM bandwidth on narrow beams) | tma (one-shot CTAs, one bulk async copy each way) | pipe
+    // (persistent CTAs, multi-stage bulk-copy ring).  The TMA variants are kept selectable: they match the
+    // register variant on narrow beams and lose ~15% when a few beams need long walks (fewer resident CTAs
+    // to overlap them); see profiles/README.md.
     const char *path = getenv("FMIDX_LOGITS_PATH");
-    const bool tma = !(path && strcmp(path, "regs") == 0);
-    const bool pipe = !path || strcmp(path, "pipe") == 0;
+    const bool tma = path && strcmp(path, "tma") == 0;
+    const bool pipe = path && strcmp(path, "pipe") == 0;
     const int esz = dtype == FMIDX_F32 ? 4 : 2;
     if (pipe && (dtype == FMIDX_F32 || dtype == FMIDX_BF16 || dtype == FMIDX_F16) && aligned(esz)) {
         const int dyn = PIPE_STAGES * SLICE * esz;
