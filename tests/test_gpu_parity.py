@@ -384,3 +384,28 @@ def test_sample_corpus_config0(cuda, layout):
         assert list(ix.get_doc_indices(q["q"]))[:16] == [ix.get_doc_index(p) for p in q["locate"]]
     assert [list(x) for x in (ix.occurring_distinct, ix.occurring_counts)] == g["occurring"]
     assert [ix.get_doc(i) for i in range(10)] == g["get_doc"]
+
+
+@pytest.mark.parametrize("V", [70_000, 1_100_000, 9_000_000])
+def test_large_alphabets_other_level_counts(cuda, V):
+    """levels = 5 (17 bits), 6 (21 bits) and 6 (24 bits): the top-descent depth and node tables change."""
+    from fm_index_constrained_decoding_b200.index import ragged
+    rng = random.Random(V)
+    docs = [[rng.randrange(V) for _ in range(rng.randint(5, 80))] for _ in range(60)]
+    docs[7] = docs[3][2:30] + docs[7]
+    docs.append([V - 1, V - 2, V - 1])
+    ix, o = make(docs), oracle(docs)
+    assert ix.info()["levels"] == (5 if V < (1 << 20) - 10 else 6)
+    seqs = [[]] + [d[i:i + k] for d in docs[:40] for i, k in ((0, 1), (1, 2), (2, 5))]
+    toks, offs = ragged(seqs)
+    sp_o, ep_o, m_o, _ = o.query_batch(toks, offs, want_mask=True, vocab=V, nthreads=4)
+    sp, ep = ix.get_range_batch(torch.from_numpy(toks).cuda(), torch.from_numpy(offs).cuda())
+    assert (sp.cpu().numpy().astype(np.uint64) == sp_o).all() and (ep.cpu().numpy().astype(np.uint64) == ep_o).all()
+    mask = ix.distinct_mask_batch(sp, ep, V)
+    assert (mask.cpu().numpy().view(np.uint32) == m_o).all()
+    assert ix.get_distinct_count(0, ix.size()) == o.get_distinct_count(0, o.size())
+    x = torch.randn(len(seqs), V)
+    y = ix.mask_logits(sp, ep, x.cuda(), out=torch.empty_like(x, device="cuda")).cpu()
+    bits = torch.from_numpy(np.unpackbits(m_o.view(np.uint8), axis=1, bitorder="little")[:, :V].astype(bool))
+    assert torch.equal(torch.isfinite(y), bits)
+    assert [ix.locate(r) for r in range(0, o.size(), 37)] == [o.locate(r) for r in range(0, o.size(), 37)]
