@@ -39,6 +39,8 @@ SIGNATURES = {
     "fmidx_search_host": (C.c_int, [p, p, p, sz, i64, p, p]),
     "fmidx_query_host": (C.c_int, [p, p, p, sz, i64, u32, p, p, p]),
     "fmidx_query_host_summary": (C.c_int, [p, p, p, sz, i64, u32, p, p, p]),
+    "fmidx_query_submit": (C.c_int, [p, C.c_int, p, p, sz, i64, u32, p, p, p]),
+    "fmidx_query_wait": (C.c_int, [p, C.c_int]),
     "fmidx_locate_host": (C.c_int, [p, p, sz, p]),
     "fmidx_info": (C.c_int, [p, C.POINTER(u64)]),
     "fmidx_debug_copy_sa": (C.c_int, [p, p, sz]),

@@ -106,6 +106,12 @@ void fmidx_free(fmidx_t *h) {
     fm_release_index(h);
     for (auto &b : h->d_scratch) if (b.p) cudaFree(b.p);
     if (h->mask_ws.p) cudaFree(h->mask_ws.p);
+    for (auto &sl : h->slots) {
+        if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
+        if (sl.in.p) cudaFree(sl.in.p);
+        if (sl.mask.p) cudaFree(sl.mask.p);
+        if (sl.ws.p) cudaFree(sl.ws.p);
+    }
     for (auto &b : h->h_scratch) if (b.p) cudaFreeHost(b.p);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -525,7 +531,7 @@ int fmidx_extract_batch(fmidx_t *h, const uint64_t *d_begin, const uint64_t *d_e
 
 // ---- host-buffer batch calls ----------------------------------------------------------------------------
 static int query_host_impl(fmidx_t *h, const int32_t *toks, const int64_t *offs, size_t B, int64_t shift, uint32_t vocab,
-                           uint64_t *sp, uint64_t *ep, uint32_t *mask, uint32_t *n_distinct) {
+                           uint64_t *sp, uint64_t *ep, uint32_t *mask, uint32_t *n_distinct, int slot = -1) {
     FM_TRY(enter(h, true));
     if (B == 0) return FMIDX_OK;
     if (!toks || !offs || !sp || !ep) { fm_set_error("null argument"); return FMIDX_EINVAL; }
@@ -533,9 +539,21 @@ static int query_host_impl(fmidx_t *h, const int32_t *toks, const int64_t *offs,
     const size_t ntok = (size_t)offs[B];
     const uint32_t words = (vocab + 31) / 32;
     const bool want_mask = mask || n_distinct;
+    // slot < 0: synchronous call on the handle's private stream; slot >= 0: one of the pipelined slots
+    // (own stream, own buffers, own mask workspace), left running -- fmidx_query_wait collects it
     cudaStream_t s = h->stream;
-    FM_TRY(fm_scratch(h, h->d_scratch[6], ntok * 4 + 16 + (B + 1) * 8 + B * 16 + B * 4, false));
-    char *dp = (char *)h->d_scratch[6].p;
+    FmBuf *in = &h->d_scratch[6], *mb = &h->d_scratch[7];
+    if (slot >= 0) {
+        fmidx::Slot &sl = h->slots[slot];
+        if (!sl.stream) FM_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        s = sl.stream;
+        in = &sl.in;
+        mb = &sl.mask;
+        h->mask_ws_override = &sl.ws;
+    }
+    struct Reset { fmidx_t *h; ~Reset() { h->mask_ws_override = nullptr; } } reset{h};
+    FM_TRY(fm_scratch(h, *in, ntok * 4 + 16 + (B + 1) * 8 + B * 16 + B * 4, false));
+    char *dp = (char *)in->p;
     int64_t *d_offs = (int64_t *)dp;
     uint64_t *d_sp = (uint64_t *)(dp + (B + 1) * 8), *d_ep = d_sp + B;
     uint32_t *d_n = (uint32_t *)(d_ep + B);
@@ -545,8 +563,8 @@ static int query_host_impl(fmidx_t *h, const int32_t *toks, const int64_t *offs,
     FM_TRY(fm_launch_search(h, d_toks, d_offs, B, shift, d_sp, d_ep, 0, s));
     uint32_t *d_mask = nullptr;
     if (want_mask) {
-        FM_TRY(fm_scratch(h, h->d_scratch[7], B * (size_t)words * 4, false));
-        d_mask = (uint32_t *)h->d_scratch[7].p;
+        FM_TRY(fm_scratch(h, *mb, B * (size_t)words * 4, false));
+        d_mask = (uint32_t *)mb->p;
         FM_TRY(fm_launch_mask(h, d_sp, d_ep, B, shift, vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, d_mask, nullptr, s));
         if (n_distinct) FM_TRY(fm_launch_popcount(h, d_mask, B, vocab, d_n, s));
     }
@@ -554,7 +572,20 @@ static int query_host_impl(fmidx_t *h, const int32_t *toks, const int64_t *offs,
     FM_CUDA(cudaMemcpyAsync(ep, d_ep, B * 8, cudaMemcpyDeviceToHost, s));
     if (mask) FM_CUDA(cudaMemcpyAsync(mask, d_mask, B * (size_t)words * 4, cudaMemcpyDeviceToHost, s));
     if (n_distinct) FM_CUDA(cudaMemcpyAsync(n_distinct, d_n, B * 4, cudaMemcpyDeviceToHost, s));
-    FM_CUDA(cudaStreamSynchronize(s));
+    if (slot < 0) FM_CUDA(cudaStreamSynchronize(s));
+    return FMIDX_OK;
+}
+
+int fmidx_query_submit(fmidx_t *h, int slot, const int32_t *toks, const int64_t *offs, size_t B, int64_t shift,
+                       uint32_t vocab, uint64_t *sp, uint64_t *ep, uint32_t *n_distinct) {
+    if (slot < 0 || slot >= 4) { fm_set_error("slot must be 0..3"); return FMIDX_EINVAL; }
+    return query_host_impl(h, toks, offs, B, shift, vocab, sp, ep, nullptr, n_distinct, slot);
+}
+
+int fmidx_query_wait(fmidx_t *h, int slot) {
+    FM_TRY(enter(h, false));
+    if (slot < 0 || slot >= 4) { fm_set_error("slot must be 0..3"); return FMIDX_EINVAL; }
+    if (h->slots[slot].stream) FM_CUDA(cudaStreamSynchronize(h->slots[slot].stream));
     return FMIDX_OK;
 }
 

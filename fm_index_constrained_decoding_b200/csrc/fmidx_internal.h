@@ -56,6 +56,11 @@ struct fmidx {
     cudaStream_t stream = nullptr;  // private stream of the synchronous host-style calls
     FmBuf d_scratch[8];
     FmBuf mask_ws;               // node tables + work list of the mask kernels
+    FmBuf *mask_ws_override = nullptr;  // set while a pipelined slot launches (its own workspace)
+    struct Slot {                // fmidx_query_submit / fmidx_query_wait: independent in-flight host batches
+        cudaStream_t stream = nullptr;
+        FmBuf in, mask, ws;
+    } slots[4];
     FmBuf h_scratch[4];
     int sm_count = 148;
 };

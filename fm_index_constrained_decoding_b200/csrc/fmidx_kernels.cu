@@ -1086,10 +1086,11 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
     const uint32_t P_top = fm_nodes_at(ix.max_sym, L, LT);
     const size_t lvl_bytes = n_nodes * sizeof(uint2);
     const size_t items_bytes = has ? 0 : nblk * 4;
-    FM_TRY(fm_scratch(h, h->mask_ws, lvl_bytes + items_bytes + 64, false));
-    uint2 *lvl = (uint2 *)h->mask_ws.p;
-    uint32_t *items = has ? nullptr : (uint32_t *)((char *)h->mask_ws.p + lvl_bytes);
-    uint32_t *ctr = (uint32_t *)((char *)h->mask_ws.p + lvl_bytes + items_bytes);  // [0]=count [1]=next
+    FmBuf &ws = h->mask_ws_override ? *h->mask_ws_override : h->mask_ws;
+    FM_TRY(fm_scratch(h, ws, lvl_bytes + items_bytes + 64, false));
+    uint2 *lvl = (uint2 *)ws.p;
+    uint32_t *items = has ? nullptr : (uint32_t *)((char *)ws.p + lvl_bytes);
+    uint32_t *ctr = (uint32_t *)((char *)ws.p + lvl_bytes + items_bytes);  // [0]=count [1]=next
     if (!has) {
         FM_CUDA(cudaMemsetAsync(ctr, 0, 8, s));
         FM_CUDA(cudaMemsetAsync(d_mask, 0, B * (size_t)((vocab + 31) / 32) * 4, s));

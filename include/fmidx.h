@@ -135,6 +135,12 @@ int fmidx_query_host(fmidx_t *h, const int32_t *toks, const int64_t *offs, size_
  * receives the ranges and n_distinct[b] = number of distinct next tokens of prefix b */
 int fmidx_query_host_summary(fmidx_t *h, const int32_t *toks, const int64_t *offs, size_t B, int64_t shift,
                              uint32_t vocab, uint64_t *sp, uint64_t *ep, uint32_t *n_distinct);
+/* pipelined form of fmidx_query_host_summary: up to 4 batches in flight, each in its own slot (own stream,
+ * buffers and workspace).  submit enqueues H2D copies, kernels and D2H copies and returns; wait blocks until the
+ * slot's host buffers (which should be pinned) hold the results.  n_distinct may be NULL (ranges only). */
+int fmidx_query_submit(fmidx_t *h, int slot, const int32_t *toks, const int64_t *offs, size_t B, int64_t shift,
+                       uint32_t vocab, uint64_t *sp, uint64_t *ep, uint32_t *n_distinct);
+int fmidx_query_wait(fmidx_t *h, int slot);
 int fmidx_locate_host(fmidx_t *h, const uint64_t *rows, size_t n, uint64_t *pos);
 
 /* ---- introspection -------------------------------------------------------------------------- */

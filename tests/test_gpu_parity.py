@@ -409,3 +409,34 @@ def test_large_alphabets_other_level_counts(cuda, V):
     bits = torch.from_numpy(np.unpackbits(m_o.view(np.uint8), axis=1, bitorder="little")[:, :V].astype(bool))
     assert torch.equal(torch.isfinite(y), bits)
     assert [ix.locate(r) for r in range(0, o.size(), 37)] == [o.locate(r) for r in range(0, o.size(), 37)]
+
+
+def test_pipelined_host_api(cuda):
+    """fmidx_query_submit / fmidx_query_wait: several host batches in flight, each bit-exact."""
+    from fm_index_constrained_decoding_b200 import _native
+    from fm_index_constrained_decoding_b200.index import ragged
+    rng = random.Random(31)
+    docs = random_docs(rng, 3000, 150, 10, 200)
+    ix, o = make(docs), oracle(docs)
+    L = _native.lib()
+    batches, outs = [], []
+    for s in range(6):
+        seqs = [rng.choice(docs)[:rng.randint(1, 20)] for _ in range(300 + 17 * s)]
+        toks, offs = ragged(seqs)
+        B = len(seqs)
+        res = (np.empty(B, np.uint64), np.empty(B, np.uint64), np.empty(B, np.uint32))
+        batches.append((toks, offs, B))
+        outs.append(res)
+    for s, (toks, offs, B) in enumerate(batches):
+        slot = s % 3
+        _native.check(L.fmidx_query_wait(ix._h, slot))
+        sp, ep, nd = outs[s]
+        _native.check(L.fmidx_query_submit(ix._h, slot, toks.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p), B, 10, 3000,
+                                           sp.ctypes.data_as(C.c_void_p), ep.ctypes.data_as(C.c_void_p), nd.ctypes.data_as(C.c_void_p)))
+    for slot in range(3):
+        _native.check(L.fmidx_query_wait(ix._h, slot))
+    for s, (toks, offs, B) in enumerate(batches):
+        osp, oep, _, ond = o.query_batch(toks, offs, want_mask=True, vocab=3000, nthreads=4)
+        assert (outs[s][0] == osp).all() and (outs[s][1] == oep).all() and (outs[s][2] == ond.astype(np.uint32)).all()
+    with pytest.raises(_native.FmidxError):
+        _native.check(L.fmidx_query_wait(ix._h, 7))
