@@ -12,6 +12,8 @@
 //           samples so a locate walk is bounded by sa_dens-1 LF steps; results are identical)
 // The suffix array of a text with a unique smallest sentinel is unique, so the index content
 // is the same function of the text as the reference's.
+#include <algorithm>
+
 #include <cub/cub.cuh>
 
 #include "fmidx_internal.h"
@@ -162,10 +164,41 @@ __global__ void k_level_scatter(const uint32_t *__restrict__ cur, uint32_t *__re
 __global__ void k_d_table(FmDev ix, uint32_t *__restrict__ D) {
     size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c > ix.max_sym) return;
-    uint32_t pos = 0;
-    for (uint32_t l = 0; l < ix.levels; ++l)
-        pos = fm_step1(ix.cells + l * ix.level_stride, pos, fm_digit((uint32_t)c, ix.levels, l));
-    D[c] = ix.C[c] - pos;
+    D[c] = ix.C[c] - fm_descend1(ix, 0u, (uint32_t)c);
+}
+
+// ---- byte level: one warp per 512-position cell -------------------------------------------------------
+__global__ void __launch_bounds__(256) k_byte_cells(const uint32_t *__restrict__ cur, size_t N, uint32_t *__restrict__ bcells,
+                                                     uint32_t *__restrict__ hist, size_t nbblocks) {
+    __shared__ uint32_t cnt[8][256];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t b = warp; b < nbblocks; b += nwarps) {
+        for (int v = lane; v < 256; v += 32) cnt[wid][v] = 0;
+        __syncwarp();
+        unsigned char *payload = reinterpret_cast<unsigned char *>(bcells + b * (FMIDX_BCELL_U4 * 4) + FMIDX_BHDR_U4 * 4);
+#pragma unroll 4
+        for (int k = 0; k < FMIDX_BBLOCK / 32; ++k) {
+            const size_t p = b * FMIDX_BBLOCK + (size_t)k * 32 + lane;
+            const bool valid = p < N;
+            const uint32_t v = valid ? (cur[p] & 255u) : 0u;
+            payload[k * 32 + lane] = (unsigned char)v;
+            if (valid) atomicAdd(&cnt[wid][v], 1u);
+        }
+        __syncwarp();
+        for (int v = lane; v < 256; v += 32) hist[(size_t)v * nbblocks + b] = cnt[wid][v];
+        __syncwarp();
+    }
+}
+
+__global__ void k_byte_hdr(const uint32_t *__restrict__ scanned, uint32_t *__restrict__ bcells, size_t nbblocks) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; t < nbblocks * 256; t += stride) {
+        size_t v = t / nbblocks, b = t - v * nbblocks;
+        bcells[b * (FMIDX_BCELL_U4 * 4) + v] = scanned[t];
+    }
 }
 
 // ---- SA / ISA samples ---------------------------------------------------------------------------
@@ -279,8 +312,7 @@ int fm_build_from_device_text(fmidx *h, const uint32_t *d_symbols, size_t n_data
         return FMIDX_ERANGE;
     }
     uint32_t sym_bits = bits_of(max_sym);
-    uint32_t levels = (sym_bits + 3) / 4;
-    if (levels == 0) levels = 1;
+    const uint32_t levels = sym_bits > 8 ? (sym_bits - 8 + 3) / 4 : 0;  // nibble levels above the byte level
 
     // ---- suffix array by prefix doubling -----------------------------------------------------------
     uint32_t *rank = nullptr, *head = nullptr, *valA = nullptr, *valB = nullptr;
@@ -339,32 +371,39 @@ int fm_build_from_device_text(fmidx *h, const uint32_t *d_symbols, size_t n_data
     uint32_t *cur = other_val, *nxt = head;  // reuse two N-sized u32 buffers for the level permutation
     FM_LAUNCH(k_bwt, grid_for(N, 256, sms), 256, 0, s, T, SA, N, cur);
 
-    // ---- wavelet matrix --------------------------------------------------------------------------------
+    // ---- wavelet matrix: `levels` nibble levels, then the byte level --------------------------------------
     const size_t nblocks = (N >> 7) + 1;
-    uint32_t *cells = nullptr, *hist = nullptr;
+    const size_t nbblocks = (N >> 9) + 1;
+    uint32_t *cells = nullptr, *bcells = nullptr, *hist = nullptr;
     FM_TRY(fm_dev_alloc(h, (void **)&cells, (size_t)levels * nblocks * 128, true));
-    FM_TRY(talloc((void **)&hist, nblocks * 16 * 4));
+    FM_TRY(fm_dev_alloc(h, (void **)&bcells, nbblocks * (size_t)FMIDX_BCELL_U4 * 16, true));
+    const size_t hist_n = std::max(nblocks * 16, nbblocks * 256);
+    FM_TRY(talloc((void **)&hist, hist_n * 4));
     {
         size_t need = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, need, hist, hist, (int64_t)(nblocks * 16), s);
+        cub::DeviceScan::ExclusiveSum(nullptr, need, hist, hist, (int64_t)hist_n, s);
         FM_TRY(cub_reserve(need));
     }
     for (uint32_t l = 0; l < levels; ++l) {
-        uint32_t shift = 4u * (levels - 1u - l);
+        uint32_t shift = 8u + 4u * (levels - 1u - l);
         uint32_t *lc = cells + (size_t)l * nblocks * 32;
         FM_LAUNCH(k_level_planes, grid_for(nblocks * 32, 256, sms), 256, 0, s, cur, N, shift, lc, hist, nblocks);
         FM_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, hist, hist, (int64_t)(nblocks * 16), s));
         g_fm_launches.fetch_add(1, std::memory_order_relaxed);
         FM_LAUNCH(k_level_hdr, grid_for(nblocks * 16, 256, sms), 256, 0, s, hist, lc, nblocks);
-        if (l + 1 < levels) {
-            FM_LAUNCH(k_level_scatter, grid_for(nblocks * 32, 256, sms), 256, 0, s, cur, nxt, N, shift, lc, nblocks);
-            uint32_t *t2 = cur; cur = nxt; nxt = t2;
-        }
+        FM_LAUNCH(k_level_scatter, grid_for(nblocks * 32, 256, sms), 256, 0, s, cur, nxt, N, shift, lc, nblocks);
+        uint32_t *t2 = cur; cur = nxt; nxt = t2;
     }
+    FM_LAUNCH(k_byte_cells, grid_for(nbblocks * 32, 256, sms), 256, 0, s, cur, N, bcells, hist, nbblocks);
+    FM_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, hist, hist, (int64_t)(nbblocks * 256), s));
+    g_fm_launches.fetch_add(1, std::memory_order_relaxed);
+    FM_LAUNCH(k_byte_hdr, grid_for(nbblocks * 256, 256, sms), 256, 0, s, hist, bcells, nbblocks);
 
     FmDev &dv = h->dev;
     dv = FmDev{};
     dv.cells = reinterpret_cast<const uint4 *>(cells);
+    dv.bcells = reinterpret_cast<const uint4 *>(bcells);
+    dv.nbblocks = (uint32_t)nbblocks;
     dv.C = C;
     dv.D = D;
     dv.level_stride = nblocks * FMIDX_CELL_U4;

@@ -196,9 +196,9 @@ int fmidx_initialize_device(fmidx_t *h, const uint32_t *d_symbols, size_t n, voi
 static const char FM_MAGIC[8] = {'F', 'M', 'I', 'D', 'X', 'B', '2', '\0'};
 struct FmFileHeader {
     char magic[8];
-    uint32_t version, levels, max_sym, sa_dens, isa_dens, keep_text, nblocks, reserved;
+    uint32_t version, levels, max_sym, sa_dens, isa_dens, keep_text, nblocks, nbblocks;
     uint64_t n;
-    uint64_t bytes[8];  // cells, C, D, sa_marks, sa_samples, isa_samples, text, 0
+    uint64_t bytes[8];  // nibble cells, C, D, sa_marks, sa_samples, isa_samples, text, byte-level cells
 };
 
 static void section_sizes(const FmDev &d, uint64_t b[8]) {
@@ -210,7 +210,7 @@ static void section_sizes(const FmDev &d, uint64_t b[8]) {
     b[4] = d.sa_dens == 1 ? N * 4 : ((N - 1) / d.sa_dens + 1) * 4;
     b[5] = ((N - 1) / d.isa_dens + 1) * 4;
     b[6] = d.text ? N * 4 : 0;
-    b[7] = 0;
+    b[7] = (uint64_t)d.nbblocks * FMIDX_BCELL_U4 * 16;
 }
 
 int fmidx_save(fmidx_t *h, const char *path) {
@@ -221,15 +221,15 @@ int fmidx_save(fmidx_t *h, const char *path) {
     FmFileHeader hd{};
     memcpy(hd.magic, FM_MAGIC, 8);
     const FmDev &d = h->dev;
-    hd.version = 1; hd.levels = d.levels; hd.max_sym = d.max_sym; hd.sa_dens = d.sa_dens; hd.isa_dens = d.isa_dens;
+    hd.version = 2; hd.nbblocks = d.nbblocks; hd.levels = d.levels; hd.max_sym = d.max_sym; hd.sa_dens = d.sa_dens; hd.isa_dens = d.isa_dens;
     hd.keep_text = d.text ? 1 : 0; hd.nblocks = d.nblocks; hd.n = d.n;
     section_sizes(d, hd.bytes);
-    const void *src[7] = {d.cells, d.C, d.D, d.sa_marks, d.sa_samples, d.isa_samples, d.text};
+    const void *src[8] = {d.cells, d.C, d.D, d.sa_marks, d.sa_samples, d.isa_samples, d.text, d.bcells};
     int rc = FMIDX_OK;
     if (fwrite(&hd, sizeof(hd), 1, f) != 1) rc = FMIDX_EIO;
     const size_t CH = 64u << 20;
     std::vector<unsigned char> buf(CH);
-    for (int sct = 0; sct < 7 && rc == FMIDX_OK; ++sct) {
+    for (int sct = 0; sct < 8 && rc == FMIDX_OK; ++sct) {
         for (uint64_t off = 0; off < hd.bytes[sct] && rc == FMIDX_OK; off += CH) {
             size_t len = (size_t)std::min<uint64_t>(CH, hd.bytes[sct] - off);
             cudaError_t e = cudaMemcpy(buf.data(), (const char *)src[sct] + off, len, cudaMemcpyDeviceToHost);
@@ -251,23 +251,23 @@ int fmidx_load(const char *path, int device, fmidx_t **out) {
     if (!f) { fm_set_error("cannot open %s: %s", path, strerror(errno)); fmidx_free(h); return FMIDX_EIO; }
     FmFileHeader hd{};
     int rc = FMIDX_OK;
-    if (fread(&hd, sizeof(hd), 1, f) != 1 || memcmp(hd.magic, FM_MAGIC, 8) != 0 || hd.version != 1) {
+    if (fread(&hd, sizeof(hd), 1, f) != 1 || memcmp(hd.magic, FM_MAGIC, 8) != 0 || hd.version != 2) {
         fm_set_error("%s is not an fmidx-b200 index file (bad magic/version)", path);
         rc = FMIDX_EIO;
     }
     if (rc == FMIDX_OK) {
         FmDev d{};
         d.levels = hd.levels; d.max_sym = hd.max_sym; d.sa_dens = hd.sa_dens; d.isa_dens = hd.isa_dens;
-        d.nblocks = hd.nblocks; d.n = (uint32_t)hd.n; d.level_stride = (uint64_t)hd.nblocks * FMIDX_CELL_U4;
+        d.nblocks = hd.nblocks; d.nbblocks = hd.nbblocks; d.n = (uint32_t)hd.n; d.level_stride = (uint64_t)hd.nblocks * FMIDX_CELL_U4;
         uint64_t expect[8];
         FmDev probe = d;
         probe.text = hd.keep_text ? (const uint32_t *)1 : nullptr;
         section_sizes(probe, expect);
-        for (int i = 0; i < 7; ++i) if (expect[i] != hd.bytes[i]) { fm_set_error("%s: corrupt section table", path); rc = FMIDX_EIO; }
-        void *dst[7] = {nullptr};
+        for (int i = 0; i < 8; ++i) if (expect[i] != hd.bytes[i]) { fm_set_error("%s: corrupt section table", path); rc = FMIDX_EIO; }
+        void *dst[8] = {nullptr};
         const size_t CH = 64u << 20;
         std::vector<unsigned char> buf(CH);
-        for (int sct = 0; sct < 7 && rc == FMIDX_OK; ++sct) {
+        for (int sct = 0; sct < 8 && rc == FMIDX_OK; ++sct) {
             if (!hd.bytes[sct]) continue;
             rc = fm_dev_alloc(h, &dst[sct], hd.bytes[sct], true);
             for (uint64_t off = 0; off < hd.bytes[sct] && rc == FMIDX_OK; off += CH) {
@@ -280,7 +280,7 @@ int fmidx_load(const char *path, int device, fmidx_t **out) {
         if (rc == FMIDX_OK) {
             d.cells = (const uint4 *)dst[0]; d.C = (const uint32_t *)dst[1]; d.D = (const uint32_t *)dst[2];
             d.sa_marks = (const uint2 *)dst[3]; d.sa_samples = (const uint32_t *)dst[4];
-            d.isa_samples = (const uint32_t *)dst[5]; d.text = (const uint32_t *)dst[6];
+            d.isa_samples = (const uint32_t *)dst[5]; d.text = (const uint32_t *)dst[6]; d.bcells = (const uint4 *)dst[7];
             h->dev = d;
             h->opt_sa_dens = d.sa_dens; h->opt_isa_dens = d.isa_dens; h->opt_keep_text = hd.keep_text;
             h->ready = true;
@@ -303,7 +303,7 @@ int fmidx_size(fmidx_t *h, uint64_t *out) {
 int fmidx_info(fmidx_t *h, uint64_t info[8]) {
     if (!h || !info) { fm_set_error("null argument"); return FMIDX_EINVAL; }
     if (!h->ready) { fm_set_error("index is not initialised"); return FMIDX_ESTATE; }
-    info[0] = h->dev.n; info[1] = h->dev.levels; info[2] = h->dev.max_sym; info[3] = h->dev.sa_dens;
+    info[0] = h->dev.n; info[1] = h->dev.levels + 1; info[2] = h->dev.max_sym; info[3] = h->dev.sa_dens;
     info[4] = h->dev.isa_dens; info[5] = h->dev_bytes; info[6] = (uint64_t)h->dev.nblocks * 128; info[7] = h->dev.text ? 1 : 0;
     return FMIDX_OK;
 }

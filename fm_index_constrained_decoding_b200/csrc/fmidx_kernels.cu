@@ -76,8 +76,7 @@ __global__ void __launch_bounds__(128) k_search(FmDev ix, const int32_t *__restr
         } else {
             const uint32_t Dc = symok ? ix.D[c] : 0u;
             uint32_t pos = half ? hi : lo;
-            for (uint32_t l = 0; l < ix.levels; ++l)
-                pos = fm_step8(ix.cells + l * ix.level_stride, pos, fm_digit(c, ix.levels, l), sub, symok);
+            pos = fm_descend8(ix, pos, c, sub, symok);
             const uint32_t res = present ? Dc + pos : 1u;
             const uint32_t oth = __shfl_xor_sync(FULL, res, 8);
             nlo = half ? oth : res;
@@ -155,8 +154,7 @@ __global__ void __launch_bounds__(128) k_step(FmDev ix, const uint64_t *__restri
     const uint32_t c = ok ? (uint32_t)sym : 0u;
     const uint32_t Dc = ok ? ix.D[c] : 0u;
     uint32_t pos = ok ? (half ? (uint32_t)high + 1u : (uint32_t)low) : 0u;
-    for (uint32_t l = 0; l < ix.levels; ++l)
-        pos = fm_step8(ix.cells + l * ix.level_stride, pos, fm_digit(c, ix.levels, l), sub, ok);
+    pos = fm_descend8(ix, pos, c, sub, ok);
     const uint32_t res = Dc + pos;
     const uint32_t oth = __shfl_xor_sync(FULL, res, 8);
     const uint32_t nlo = half ? oth : res, nhi = half ? res : oth;
@@ -171,7 +169,7 @@ __global__ void __launch_bounds__(128) k_step(FmDev ix, const uint64_t *__restri
 // K2: distinct-symbol enumeration of BWT[sp,ep) -> vocab bitmap (+counts), fused with the -inf
 // masking of the beam's logits row.  Two phases:
 //
-//  k_mask_top    one warp per range: descend the top LT = levels-3 levels of the 16-ary matrix
+//  k_mask_top    one warp per range: descend all nibble levels but the last (LT = levels-1) of the matrix
 //                ONCE per range and leave, per range, the dense table of the <= 256 depth-LT nodes
 //                (each covers 4096 symbols = one vocab slice); for the bitmap-only entry point it
 //                also appends the non-empty (range, slice) pairs to a work list, so ranges with a
@@ -247,15 +245,93 @@ __device__ __forceinline__ uint32_t fm_access1(const uint4 *__restrict__ level_c
 
 struct EnumSmem {
     uint32_t bm[SLICE / 32];
-    uint32_t fr[2][MAXF][3];
-    uint32_t fcount[2];
-    uint32_t width;
+    uint32_t seed[4][3];            // depth-LT nodes of this slice (<= 2 when a top node spans one slice)
+    uint32_t bnode[48][3];          // byte-level nodes (each covers 256 symbols): <= 16 per seed (+ overlap)
+    uint32_t n_seed, n_bnode, width;
+    int cnt[MASK_THREADS / 32][256];  // per-warp signed histogram of one byte-level node
     uint4 stage[MASK_THREADS / 16][16];
 };
 
-// number of depth-l nodes that can hold symbols <= max_sym
+// number of depth-l nodes (l nibble levels consumed) that can hold symbols <= max_sym
 __device__ __host__ __forceinline__ uint32_t fm_nodes_at(uint32_t max_sym, uint32_t levels, uint32_t l) {
-    return (max_sym >> (4u * (levels - l))) + 1u;
+    return (max_sym >> (8u + 4u * (levels - l))) + 1u;
+}
+
+// OR `bits` (nbits <= 16 consecutive symbols starting at base_sym) into the slice bitmap
+__device__ __forceinline__ void fm_or_bits(uint32_t *bm, uint32_t bits, uint32_t base_sym, int64_t shift, uint32_t t0) {
+    const int64_t r = (int64_t)base_sym - shift - (int64_t)t0;  // bit position of the first symbol
+    if (r >= 0) {
+        const uint64_t v = (uint64_t)bits << (r & 31);
+        atomicOr(&bm[r >> 5], (uint32_t)v);
+        if (v >> 32) atomicOr(&bm[(r >> 5) + 1], (uint32_t)(v >> 32));
+    } else if (-r < 32) {
+        const uint32_t v = bits >> (uint32_t)(-r);
+        if (v) atomicOr(&bm[0], v);
+    }
+}
+
+// Distinct symbols of one byte-level node (positions [lo,hi) of the last level, all sharing `prefix`),
+// by one warp: narrow nodes read their bytes directly; otherwise a 256-bin signed histogram
+//   cnt[v] = hdrB[v] - hdrA[v] - #v in A[0,a) + #v in B[0,b)        (cells A, B of lo and hi)
+// built with shared-memory atomics; lane i then owns the 8 symbols 8i..8i+7.
+__device__ __forceinline__ void fm_eval_byte_node(const FmDev &ix, uint32_t lo, uint32_t hi, uint32_t prefix, uint32_t sa,
+                                                  uint32_t se, int64_t shift, uint32_t t0, uint32_t *bm, int *cnt,
+                                                  uint32_t *__restrict__ counts_row, int lane) {
+    const uint32_t base_sym = prefix << 8;
+    const uint32_t w = hi - lo;
+    if (w <= 128u && !counts_row) {
+        for (uint32_t t = (uint32_t)lane; t < w; t += 32) {
+            const uint32_t sy = base_sym | fm_byte_at(ix.bcells, lo + t);
+            if (sy >= sa && sy < se) {
+                const uint32_t rel = (uint32_t)((int64_t)sy - shift) - t0;
+                atomicOr(&bm[rel >> 5], 1u << (rel & 31u));
+            }
+        }
+        return;
+    }
+    const uint32_t cA = lo >> 9, a = lo & 511u, cB = hi >> 9, b = hi & 511u;
+    const uint4 *cellA = ix.bcells + (size_t)cA * FMIDX_BCELL_U4, *cellB = ix.bcells + (size_t)cB * FMIDX_BCELL_U4;
+    if (cA == cB) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cnt[lane * 8 + k] = 0;
+    } else {
+        const uint4 a0 = fm_ldg(cellA + 2 * lane), a1 = fm_ldg(cellA + 2 * lane + 1);
+        const uint4 b0 = fm_ldg(cellB + 2 * lane), b1 = fm_ldg(cellB + 2 * lane + 1);
+        int *c = cnt + lane * 8;
+        c[0] = (int)(b0.x - a0.x); c[1] = (int)(b0.y - a0.y); c[2] = (int)(b0.z - a0.z); c[3] = (int)(b0.w - a0.w);
+        c[4] = (int)(b1.x - a1.x); c[5] = (int)(b1.y - a1.y); c[6] = (int)(b1.z - a1.z); c[7] = (int)(b1.w - a1.w);
+    }
+    __syncwarp();
+    auto scan = [&](const uint4 *cell, uint32_t from, uint32_t to, int sign) {  // positions [from,to) of one cell
+        const uint32_t *pw = reinterpret_cast<const uint32_t *>(cell + FMIDX_BHDR_U4);
+        for (uint32_t wi = (from >> 2) + (uint32_t)lane; wi < ((to + 3u) >> 2); wi += 32) {
+            const uint32_t word = __ldg(pw + wi);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t p = wi * 4u + (uint32_t)k;
+                if (p >= from && p < to) atomicAdd(&cnt[(word >> (8 * k)) & 255u], sign);
+            }
+        }
+    };
+    if (cA == cB) {
+        scan(cellA, a, b, 1);
+    } else {
+        scan(cellA, 0u, a, -1);
+        scan(cellB, 0u, b, 1);
+    }
+    __syncwarp();
+    uint32_t bits = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = cnt[lane * 8 + k];
+        const uint32_t sy = base_sym | (uint32_t)(lane * 8 + k);
+        if (c > 0 && sy >= sa && sy < se) {
+            bits |= 1u << k;
+            if (counts_row) counts_row[(uint32_t)((int64_t)sy - shift)] = (uint32_t)c;
+        }
+    }
+    if (bits) fm_or_bits(bm, bits, base_sym + (uint32_t)lane * 8u, shift, t0);
+    __syncwarp();
 }
 
 // ---- phase A --------------------------------------------------------------------------------------
@@ -281,12 +357,14 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
         if (e - s <= 32u) {
             const bool valid = (uint64_t)lane < e - s;
             uint32_t pos = (uint32_t)s + (uint32_t)lane, c = 0;
-            if (valid)
+            if (valid) {
                 for (uint32_t l = 0; l < L; ++l) {
                     uint32_t dig;
                     pos = fm_access1(ix.cells + l * ix.level_stride, pos, dig);
                     c = (c << 4) | dig;
                 }
+                c = (c << 8) | fm_byte_at(ix.bcells, pos);
+            }
             const int64_t tk = (int64_t)c - shift;
             const bool inside = valid && tk >= 0 && tk < (int64_t)vocab;
             if (inside) atomicOr(&mask_out[(size_t)b * ((vocab + 31u) >> 5) + ((uint32_t)tk >> 5)], 1u << ((uint32_t)tk & 31u));
@@ -335,7 +413,7 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
     }
     if (work_items) {
         const uint32_t nslices = (vocab + SLICE - 1) / SLICE;
-        const uint32_t span_bits = 4u * (L - LT);
+        const uint32_t span_bits = 8u + 4u * (L - LT);
         for (uint32_t s0 = 0; s0 < nslices; s0 += 32) {
             const uint32_t s = s0 + lane;
             bool ne = false;
@@ -359,34 +437,35 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
 }
 
 // ---- the walk inside one slice (whole CTA) ---------------------------------------------------------
-// top_b: this range's depth-LT node table; [sa,se): the slice's symbol interval; bm (zeroed by the
-// caller) receives bit (symbol - shift - t0); counts_row (nullable) is indexed by token.
+// top_b: this range's depth-LT node table (LT = levels-1 nibble levels consumed; a node covers 4096
+// symbols; with levels == 0 the single root is itself a byte-level node); [sa,se): the slice's symbol
+// interval; bm (zeroed by the caller) receives bit (symbol - shift - t0); counts_row (nullable) is
+// indexed by token.
 __device__ __forceinline__ void fm_enum_slice(const FmDev &ix, const uint2 *__restrict__ top_b, uint32_t LT, uint32_t sa,
                                               uint32_t se, int64_t shift, uint32_t t0, EnumSmem &S,
                                               uint32_t *__restrict__ counts_row) {
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t L = ix.levels;
-    const uint32_t span_bits = 4u * (L - LT);
-    const int c0 = LT & 1;
+    const uint32_t span_bits = 8u + 4u * (L - LT);
     if (tid == 0) {
         uint32_t n = 0, W = 0;
         if (sa < se)
-            for (uint32_t p = sa >> span_bits; p <= (se - 1u) >> span_bits && n < MAXF; ++p) {
+            for (uint32_t p = sa >> span_bits; p <= (se - 1u) >> span_bits && n < 4; ++p) {
                 const uint2 nd = top_b[p];
                 if (nd.y > nd.x) {
-                    S.fr[c0][n][0] = nd.x;
-                    S.fr[c0][n][1] = nd.y;
-                    S.fr[c0][n][2] = p;
+                    S.seed[n][0] = nd.x;
+                    S.seed[n][1] = nd.y;
+                    S.seed[n][2] = p;
                     ++n;
                     W += nd.y - nd.x;
                 }
             }
-        S.fcount[c0] = n;
-        S.fcount[c0 ^ 1] = 0;
+        S.n_seed = n;
+        S.n_bnode = 0;
         S.width = W;
     }
     __syncthreads();
-    const uint32_t n_seed = S.fcount[c0], W = S.width;
+    const uint32_t n_seed = S.n_seed, W = S.width;
     if (n_seed == 0) return;
     if (W <= 32u) {
         // narrow: one lane per BWT position, straight access down the remaining levels
@@ -395,20 +474,22 @@ __device__ __forceinline__ void fm_enum_slice(const FmDev &ix, const uint2 *__re
             uint32_t pos = 0, c = 0, acc = 0;
             bool found = false;
             for (uint32_t i = 0; i < n_seed; ++i) {
-                const uint32_t lo = S.fr[c0][i][0], w = S.fr[c0][i][1] - lo;
+                const uint32_t lo = S.seed[i][0], w = S.seed[i][1] - lo;
                 if (!found && (uint32_t)lane < acc + w) {
                     pos = lo + ((uint32_t)lane - acc);
-                    c = S.fr[c0][i][2];
+                    c = S.seed[i][2];
                     found = true;
                 }
                 acc += w;
             }
-            if (valid)
+            if (valid) {
                 for (uint32_t l = LT; l < L; ++l) {
                     uint32_t dig;
                     pos = fm_access1(ix.cells + l * ix.level_stride, pos, dig);
                     c = (c << 4) | dig;
                 }
+                c = (c << 8) | fm_byte_at(ix.bcells, pos);
+            }
             const bool inside = valid && c >= sa && c < se;
             if (inside) {
                 const uint32_t rel = (uint32_t)((int64_t)c - shift) - t0;
@@ -421,106 +502,55 @@ __device__ __forceinline__ void fm_enum_slice(const FmDev &ix, const uint2 *__re
         }
         return;
     }
-    const int hw = tid >> 4, hl = tid & 15;
-    // lane hl evaluates child digit hl: its bit-plane XOR masks are loop invariants
-    const uint32_t x0 = (hl & 1) ? 0u : ~0u, x1 = (hl & 2) ? 0u : ~0u, x2 = (hl & 4) ? 0u : ~0u, x3 = (hl & 8) ? 0u : ~0u;
-    for (uint32_t l = LT; l < L; ++l) {
-        const int cur = l & 1, nxt = cur ^ 1;
-        const uint32_t n_nodes = S.fcount[cur];
+    if (L == 0) {
+        // the alphabet fits one byte: the seed IS the byte-level node
+        if (wid == 0) fm_eval_byte_node(ix, S.seed[0][0], S.seed[0][1], 0u, sa, se, shift, t0, S.bm, S.cnt[0], counts_row, lane);
         __syncthreads();
-        if (n_nodes == 0) break;
-        if (tid == 0) S.fcount[nxt] = 0;
-        __syncthreads();
-        const uint4 *lc = ix.cells + l * ix.level_stride;
-        const uint32_t csh = 4u * (L - 1u - l);  // bits below a child's prefix
-        const bool leaf = (l + 1 == L);
-        const bool allow_direct = leaf && !counts_row;
-        // software pipeline: the two cells of the NEXT node are already in flight (one uint4 per lane)
-        // while the current node is evaluated
-        uint32_t lo = 0, hi = 0, prefix = 0;
-        bool has = (uint32_t)hw < n_nodes;
-        if (has) {
-            lo = S.fr[cur][hw][0];
-            hi = S.fr[cur][hw][1];
-            prefix = S.fr[cur][hw][2];
-        }
-        bool heavy = has && !(allow_direct && hi - lo <= 64u);
-        uint4 pre = make_uint4(0, 0, 0, 0);
-        if (heavy) pre = fm_ldg(lc + (size_t)((hl < 8 ? lo : hi) >> 7) * FMIDX_CELL_U4 + (hl & 7));
-        for (uint32_t base = 0; base < n_nodes; base += MASK_THREADS / 16) {
-            const uint32_t nnode = base + MASK_THREADS / 16 + hw;
-            uint32_t nlo = 0, nhi = 0, npf = 0;
-            const bool nhas = nnode < n_nodes;
-            if (nhas) {
-                nlo = S.fr[cur][nnode][0];
-                nhi = S.fr[cur][nnode][1];
-                npf = S.fr[cur][nnode][2];
-            }
-            const bool nheavy = nhas && !(allow_direct && nhi - nlo <= 64u);
-            uint4 npre = make_uint4(0, 0, 0, 0);
-            if (nheavy) npre = fm_ldg(lc + (size_t)((hl < 8 ? nlo : nhi) >> 7) * FMIDX_CELL_U4 + (hl & 7));
-
-            if (has && !heavy) {
-                // deepest level, narrow node: the distinct digits of <= 64 positions are cheaper to read
-                // off the bit-planes directly than to rank all 16 digits at both ends
-                const uint32_t w = hi - lo;
-                for (uint32_t t = (uint32_t)hl; t < w; t += 16) {
-                    const uint32_t q = lo + t;
-                    const uint4 pl = fm_ldg(lc + (size_t)(q >> 7) * FMIDX_CELL_U4 + 4 + ((q & 127u) >> 5));
-                    const uint32_t bt = q & 31u;
-                    const uint32_t dg = ((pl.x >> bt) & 1u) | (((pl.y >> bt) & 1u) << 1) | (((pl.z >> bt) & 1u) << 2) |
-                                        (((pl.w >> bt) & 1u) << 3);
-                    const uint32_t sy = (prefix << 4) | dg;
-                    if (sy >= sa && sy < se) {
-                        const uint32_t rel = (uint32_t)((int64_t)sy - shift) - t0;
-                        atomicOr(&S.bm[rel >> 5], 1u << (rel & 31u));
-                    }
-                }
-            }
-            if (__any_sync(FULL, heavy)) {
-                if (heavy) S.stage[hw][hl] = pre;
-                __syncwarp();
-                uint32_t r_lo = 0, r_hi = 0;
-                if (heavy) {
-                    r_lo = fm_rank_fast(&S.stage[hw][0], (uint32_t)hl, lo & 127u, x0, x1, x2, x3);
-                    r_hi = fm_rank_fast(&S.stage[hw][8], (uint32_t)hl, hi & 127u, x0, x1, x2, x3);
-                }
-                __syncwarp();
-                const uint32_t cp = (prefix << 4) | (uint32_t)hl;
-                const uint64_t c_lo = (uint64_t)cp << csh, c_hi = ((uint64_t)cp + 1) << csh;
-                const bool exists = heavy && r_hi > r_lo && c_lo < se && c_hi > sa;
-                const uint32_t bal = (__ballot_sync(FULL, exists) >> (lane & 16)) & 0xffffu;
-                if (leaf) {
-                    // the 16 children are 16 consecutive symbols: one lane ORs the whole presence mask
-                    if (hl == 0 && bal) {
-                        const int64_t r = (int64_t)((uint64_t)prefix << 4) - shift - (int64_t)t0;  // bit of digit 0
-                        if (r >= 0) {
-                            const uint64_t v = (uint64_t)bal << (r & 31);
-                            atomicOr(&S.bm[r >> 5], (uint32_t)v);
-                            if (v >> 32) atomicOr(&S.bm[(r >> 5) + 1], (uint32_t)(v >> 32));
-                        } else {
-                            atomicOr(&S.bm[0], bal >> (uint32_t)(-r));
-                        }
-                    }
-                    if (counts_row && exists) counts_row[(uint32_t)((int64_t)cp - shift)] = r_hi - r_lo;
-                } else {
-                    uint32_t slot = 0;
-                    if (hl == 0 && bal) slot = atomicAdd(&S.fcount[nxt], (uint32_t)__popc(bal));
-                    slot = __shfl_sync(FULL, slot, lane & 16);
-                    if (exists) {
-                        const uint32_t idx = slot + __popc(bal & ((1u << hl) - 1u));
-                        if (idx < MAXF) {
-                            S.fr[nxt][idx][0] = r_lo;
-                            S.fr[nxt][idx][1] = r_hi;
-                            S.fr[nxt][idx][2] = cp;
-                        }
-                    }
-                }
-            }
-            lo = nlo; hi = nhi; prefix = npf; has = nhas; heavy = nheavy; pre = npre;
-        }
-        __syncthreads();
+        return;
     }
+    // stage 1: the last nibble level -- one half-warp per seed, lane d evaluates child d (a byte-level node)
+    {
+        const int hw = tid >> 4, hl = tid & 15;
+        const uint32_t x0 = (hl & 1) ? 0u : ~0u, x1 = (hl & 2) ? 0u : ~0u, x2 = (hl & 4) ? 0u : ~0u, x3 = (hl & 8) ? 0u : ~0u;
+        const uint4 *lc = ix.cells + (size_t)LT * ix.level_stride;
+        if (hw < 4) {  // warps 0 and 1; n_seed <= 4
+            const bool has = (uint32_t)hw < n_seed;
+            uint32_t lo = 0, hi = 0, prefix = 0;
+            if (has) {
+                lo = S.seed[hw][0];
+                hi = S.seed[hw][1];
+                prefix = S.seed[hw][2];
+                S.stage[hw][hl] = fm_ldg(lc + (size_t)((hl < 8 ? lo : hi) >> 7) * FMIDX_CELL_U4 + (hl & 7));
+            }
+            __syncwarp();
+            uint32_t r_lo = 0, r_hi = 0;
+            if (has) {
+                r_lo = fm_rank_fast(&S.stage[hw][0], (uint32_t)hl, lo & 127u, x0, x1, x2, x3);
+                r_hi = fm_rank_fast(&S.stage[hw][8], (uint32_t)hl, hi & 127u, x0, x1, x2, x3);
+            }
+            const uint32_t cp = (prefix << 4) | (uint32_t)hl;
+            const uint64_t c_lo = (uint64_t)cp << 8, c_hi = ((uint64_t)cp + 1) << 8;
+            const bool exists = has && r_hi > r_lo && c_lo < se && c_hi > sa;
+            const uint32_t bal = (__ballot_sync(FULL, exists) >> (lane & 16)) & 0xffffu;
+            uint32_t slot = 0;
+            if (hl == 0 && bal) slot = atomicAdd(&S.n_bnode, (uint32_t)__popc(bal));
+            slot = __shfl_sync(FULL, slot, lane & 16);
+            if (exists) {
+                const uint32_t idx = slot + __popc(bal & ((1u << hl) - 1u));
+                if (idx < 48) {
+                    S.bnode[idx][0] = r_lo;
+                    S.bnode[idx][1] = r_hi;
+                    S.bnode[idx][2] = cp;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // stage 2: the byte level -- one warp per node
+    const uint32_t nb = min(S.n_bnode, 48u);
+    for (uint32_t i = (uint32_t)wid; i < nb; i += MASK_THREADS / 32)
+        fm_eval_byte_node(ix, S.bnode[i][0], S.bnode[i][1], S.bnode[i][2], sa, se, shift, t0, S.bm, S.cnt[wid], counts_row, lane);
+    __syncthreads();
 }
 
 __device__ __forceinline__ void fm_slice_interval(const FmDev &ix, uint32_t t0, uint32_t t1, int64_t shift, uint32_t &sa,
@@ -932,6 +962,9 @@ __device__ __forceinline__ uint32_t fm_lf8(const FmDev &ix, uint32_t row, int su
         pos = fm_access_step8(ix.cells + l * ix.level_stride, pos, sub, act, dig);
         c = (c << 4) | dig;
     }
+    const uint32_t v = act ? fm_byte_at(ix.bcells, pos) : 0u;  // same address in all 8 lanes
+    pos = fm_step8_byte(ix.bcells, pos, v, sub, act);
+    c = (c << 8) | v;
     sym_out = c;
     return act ? ix.D[c <= ix.max_sym ? c : 0u] + pos : 0u;
 }
@@ -1077,7 +1110,7 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
     if (!has && !d_mask) { fm_set_error("d_mask is NULL"); return FMIDX_EINVAL; }
     // workspace: dense node tables of levels 0..LT, then the work list and its two counters
     const FmDev &ix = h->dev;
-    const uint32_t L = ix.levels, LT = L > 3 ? L - 3 : 0;
+    const uint32_t L = ix.levels, LT = L > 0 ? L - 1 : 0;  // nibble levels consumed by k_mask_top
     size_t n_nodes = 0, top_off = 0;
     for (uint32_t l = 0; l <= LT; ++l) {
         if (l == LT) top_off = n_nodes;

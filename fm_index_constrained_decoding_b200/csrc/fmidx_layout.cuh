@@ -1,10 +1,12 @@
 // fmidx_layout.cuh -- device-resident FM-index layout for B200 (sm_100a) and the rank primitives.
 //
 // Replaces sdsl::csa_wt_int<> (reference cpp_modules_linux/fm_index.hpp:12,36): the level-wise
-// binary wt_int (17 levels, 3 rank probes per level) becomes a 16-ary WAVELET MATRIX over the
-// token BWT: ceil(17/4) = 5 levels for the Llama-3 alphabet (128,256 + SHIFT symbols < 2^17).
+// binary wt_int (17 levels, 3 rank probes per level) becomes a multi-ary WAVELET MATRIX over the
+// token BWT whose digits are, most significant first, `levels` NIBBLES and one final BYTE:
+// 3 nibble levels + 1 byte level = 4 dependent probes per rank for the Llama-3 alphabet
+// (128,256 + SHIFT symbols < 2^17 -> bits 16..8 as three nibbles, bits 7..0 as the byte).
 //
-// One level = an array of 128-byte RANK CELLS, one cell per 128 BWT positions, i.e. exactly one
+// Nibble level = an array of 128-byte RANK CELLS, one per 128 BWT positions, i.e. exactly one
 // L2 line / four 32-B DRAM sectors, fetched by eight lanes with one 128-bit load each:
 //
 //   u32 hdr[16]      hdr[d] = (#symbols of this level whose digit < d)              "Z_d"
@@ -17,19 +19,29 @@
 //
 //   next_pos(pos, d) = hdr[d] + popc(match_d(planes) & below(pos & 127))
 //
+// Byte level (the last one) = 1,536-byte cells, one per 512 positions: u32 hdr[256] with the same
+// meaning, then the 512 digits as plain bytes.  A rank probe reads one header word and the bytes
+// below pos (SIMD byte compare, 16 per 128-bit load); "access" is a single byte load; and -- the
+// reason this level exists -- enumerating the distinct symbols of a range needs ONE histogram
+// over at most two cells for 256 children instead of 16 sixteen-way node evaluations.
+//
 // After the last level,  C[c] + rank_c(i) = D[c] + descend_c(i)  with  D[c] = C[c] - descend_c(0)
-// (SURVEY.md section 7 identity (i), generalised from bits to nibbles), so one backward-search
-// boundary update costs `levels` dependent cell probes and one L2-resident table read.
+// (SURVEY.md section 7 identity (i), generalised from bits to digits), so one backward-search
+// boundary update costs `levels + 1` dependent cell probes and one L2-resident table read.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
 
 #define FMIDX_CELL_U4 8          // uint4 per cell (128 B)
 #define FMIDX_BLOCK 128          // BWT positions per cell
-#define FMIDX_MAX_LEVELS 6       // symbols < 2^24
+#define FMIDX_MAX_LEVELS 6       // symbols < 2^24 (4 nibble levels + the byte level)
+#define FMIDX_BBLOCK 512         // BWT positions per byte-level cell
+#define FMIDX_BCELL_U4 96        // uint4 per byte-level cell: 64 header + 32 payload
+#define FMIDX_BHDR_U4 64
 
 struct FmDev {
-    const uint4 *cells;          // [levels][nblocks][8]
+    const uint4 *cells;          // nibble levels [levels][nblocks][8]
+    const uint4 *bcells;         // byte level [nbblocks][96]
     const uint32_t *D;           // [max_sym+1]  C[c] - descend_c(0)  (mod 2^32)
     const uint32_t *C;           // [max_sym+2]  C[c] = #symbols < c ; C[max_sym+1] = n
     const uint2 *sa_marks;       // [ceil(n/32)] {ones before this word, bits}: row has SA[row] % sa_dens == 0
@@ -39,7 +51,8 @@ struct FmDev {
     uint64_t level_stride;       // uint4 per level = nblocks*8
     uint32_t n;                  // csa.size(): text length incl. the 0 sentinel
     uint32_t max_sym;
-    uint32_t levels;
+    uint32_t levels;             // number of NIBBLE levels above the byte level (0..4)
+    uint32_t nbblocks;
     uint32_t sa_dens;
     uint32_t isa_dens;
     uint32_t nblocks;
@@ -132,6 +145,76 @@ __device__ __forceinline__ uint32_t fm_step1(const uint4 *__restrict__ level_cel
     return v;
 }
 
+// nibble digit of symbol c examined at nibble level l (levels = number of nibble levels)
 __device__ __forceinline__ uint32_t fm_digit(uint32_t c, uint32_t levels, uint32_t l) {
-    return (c >> (4u * (levels - 1u - l))) & 15u;
+    return (c >> (8u + 4u * (levels - 1u - l))) & 15u;
+}
+
+// ---- byte level ----------------------------------------------------------------------------------
+// bytes equal to the replicated pattern among the first nb (0..16) bytes of a 16-byte group
+__device__ __forceinline__ uint32_t fm_count16(const uint4 &w, uint32_t pat, int nb) {
+    uint32_t m0 = __vcmpeq4(w.x, pat), m1 = __vcmpeq4(w.y, pat), m2 = __vcmpeq4(w.z, pat), m3 = __vcmpeq4(w.w, pat);
+    if (nb < 16) {
+        const int r = nb & 3, q = nb >> 2;  // q full words, then r bytes of word q
+        const uint32_t part = r ? ((1u << (8 * r)) - 1u) : 0u;
+        m0 = q > 0 ? m0 : (q == 0 ? (m0 & part) : 0u);
+        m1 = q > 1 ? m1 : (q == 1 ? (m1 & part) : 0u);
+        m2 = q > 2 ? m2 : (q == 2 ? (m2 & part) : 0u);
+        m3 = q > 3 ? m3 : (q == 3 ? (m3 & part) : 0u);
+    }
+    return (uint32_t)(__popc(m0) + __popc(m1) + __popc(m2) + __popc(m3)) >> 3;
+}
+
+// rank step at the byte level, cooperatively by an aligned lane octet: lane 0 fetches hdr[v], every
+// lane scans the 16-byte groups sub, sub+8, sub+16, sub+24 that lie below pos (all loads issued first).
+__device__ __forceinline__ uint32_t fm_step8_byte(const uint4 *__restrict__ bcells, uint32_t pos, uint32_t v, int sub,
+                                                  bool act) {
+    const uint4 *cell = bcells + (size_t)(pos >> 9) * FMIDX_BCELL_U4;
+    const int off = (int)(pos & 511u);
+    uint32_t cnt = 0;
+    if (act) {
+        uint4 w[4];
+        int nb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int j = sub + 8 * i;
+            nb[i] = min(16, off - 16 * j);
+            if (nb[i] > 0) w[i] = fm_ldg(cell + FMIDX_BHDR_U4 + j);
+        }
+        if (sub == 0) cnt = __ldg(reinterpret_cast<const uint32_t *>(cell) + v);
+        const uint32_t pat = v * 0x01010101u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (nb[i] > 0) cnt += fm_count16(w[i], pat, nb[i]);
+    }
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, 4);
+    return cnt;
+}
+
+__device__ __forceinline__ uint32_t fm_byte_at(const uint4 *__restrict__ bcells, uint32_t pos) {
+    const uint4 *cell = bcells + (size_t)(pos >> 9) * FMIDX_BCELL_U4;
+    return __ldg(reinterpret_cast<const unsigned char *>(cell + FMIDX_BHDR_U4) + (pos & 511u));
+}
+
+// single-thread rank step at the byte level (build-time D table)
+__device__ __forceinline__ uint32_t fm_step1_byte(const uint4 *__restrict__ bcells, uint32_t pos, uint32_t v) {
+    const uint4 *cell = bcells + (size_t)(pos >> 9) * FMIDX_BCELL_U4;
+    const int off = (int)(pos & 511u);
+    uint32_t cnt = __ldg(reinterpret_cast<const uint32_t *>(cell) + v);
+    const uint32_t pat = v * 0x01010101u;
+    for (int j = 0; 16 * j < off; ++j) cnt += fm_count16(fm_ldg(cell + FMIDX_BHDR_U4 + j), pat, min(16, off - 16 * j));
+    return cnt;
+}
+
+// full descend of symbol c from position pos by one thread / by an octet
+__device__ __forceinline__ uint32_t fm_descend1(const FmDev &ix, uint32_t pos, uint32_t c) {
+    for (uint32_t l = 0; l < ix.levels; ++l) pos = fm_step1(ix.cells + l * ix.level_stride, pos, fm_digit(c, ix.levels, l));
+    return fm_step1_byte(ix.bcells, pos, c & 255u);
+}
+__device__ __forceinline__ uint32_t fm_descend8(const FmDev &ix, uint32_t pos, uint32_t c, int sub, bool act) {
+    for (uint32_t l = 0; l < ix.levels; ++l)
+        pos = fm_step8(ix.cells + l * ix.level_stride, pos, fm_digit(c, ix.levels, l), sub, act);
+    return fm_step8_byte(ix.bcells, pos, c & 255u, sub, act);
 }

@@ -388,14 +388,16 @@ def test_sample_corpus_config0(cuda, layout):
 
 @pytest.mark.parametrize("V", [70_000, 1_100_000, 9_000_000])
 def test_large_alphabets_other_level_counts(cuda, V):
-    """levels = 5 (17 bits), 6 (21 bits) and 6 (24 bits): the top-descent depth and node tables change."""
+    """3, 4 and 4 nibble levels above the byte level (17-, 21- and 24-bit symbols): the top-descent depth and
+    the node tables change."""
     from fm_index_constrained_decoding_b200.index import ragged
     rng = random.Random(V)
     docs = [[rng.randrange(V) for _ in range(rng.randint(5, 80))] for _ in range(60)]
     docs[7] = docs[3][2:30] + docs[7]
     docs.append([V - 1, V - 2, V - 1])
     ix, o = make(docs), oracle(docs)
-    assert ix.info()["levels"] == (5 if V < (1 << 20) - 10 else 6)
+    bits = (V + 9).bit_length()
+    assert ix.info()["levels"] == 1 + (bits - 8 + 3) // 4
     seqs = [[]] + [d[i:i + k] for d in docs[:40] for i, k in ((0, 1), (1, 2), (2, 5))]
     toks, offs = ragged(seqs)
     sp_o, ep_o, m_o, _ = o.query_batch(toks, offs, want_mask=True, vocab=V, nthreads=4)
