@@ -185,7 +185,8 @@ __global__ void __launch_bounds__(128) k_step(FmDev ix, const uint64_t *__restri
 // child d), pruned to the slice's symbol interval.  Slices never communicate.
 // =================================================================================================
 constexpr int SLICE = 4096;        // tokens per CTA
-constexpr int MASK_THREADS = 128;
+constexpr int MASK_THREADS = 256;   // logits kernels (one CTA per slice)
+constexpr int ITEM_THREADS = 128;   // k_mask_items (bitmap-only work items): more, smaller CTAs hide the walks better
 constexpr int MAXF = 288;          // BFS frontier capacity: <= SLICE/16 + 2 nodes at the deepest inner level
 
 template <int DT> struct Elem;
@@ -291,33 +292,53 @@ __device__ __forceinline__ void fm_eval_byte_node(const FmDev &ix, uint32_t lo, 
     }
     const uint32_t cA = lo >> 9, a = lo & 511u, cB = hi >> 9, b = hi & 511u;
     const uint4 *cellA = ix.bcells + (size_t)cA * FMIDX_BCELL_U4, *cellB = ix.bcells + (size_t)cB * FMIDX_BCELL_U4;
-    if (cA == cB) {
+    const bool same = cA == cB;
+    // every load of the node is issued before anything is consumed: the two header slices of this lane's
+    // 8 symbols and the payload words of both scans (a cell has 128 words -> at most 4 per lane per scan)
+    const uint32_t fa = same ? a : 0u, ta = same ? b : a;   // scan 1: cell A, positions [fa,ta), sign +1 / -1
+    const uint32_t fb = 0u, tb = same ? 0u : b;             // scan 2: cell B, positions [0,tb),  sign +1
+    const uint32_t *pwa = reinterpret_cast<const uint32_t *>(cellA + FMIDX_BHDR_U4);
+    const uint32_t *pwb = reinterpret_cast<const uint32_t *>(cellB + FMIDX_BHDR_U4);
+    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0, b0 = a0, b1 = a0;
+    if (!same) {
+        a0 = fm_ldg(cellA + 2 * lane);
+        a1 = fm_ldg(cellA + 2 * lane + 1);
+        b0 = fm_ldg(cellB + 2 * lane);
+        b1 = fm_ldg(cellB + 2 * lane + 1);
+    }
+    uint32_t wa[4], wb[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) cnt[lane * 8 + k] = 0;
-    } else {
-        const uint4 a0 = fm_ldg(cellA + 2 * lane), a1 = fm_ldg(cellA + 2 * lane + 1);
-        const uint4 b0 = fm_ldg(cellB + 2 * lane), b1 = fm_ldg(cellB + 2 * lane + 1);
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t wi = (fa >> 2) + (uint32_t)lane + 32u * k;
+        wa[k] = wi < ((ta + 3u) >> 2) ? __ldg(pwa + wi) : 0u;
+        const uint32_t wj = (uint32_t)lane + 32u * k;
+        wb[k] = wj < ((tb + 3u) >> 2) ? __ldg(pwb + wj) : 0u;
+    }
+    {
         int *c = cnt + lane * 8;
         c[0] = (int)(b0.x - a0.x); c[1] = (int)(b0.y - a0.y); c[2] = (int)(b0.z - a0.z); c[3] = (int)(b0.w - a0.w);
         c[4] = (int)(b1.x - a1.x); c[5] = (int)(b1.y - a1.y); c[6] = (int)(b1.z - a1.z); c[7] = (int)(b1.w - a1.w);
     }
     __syncwarp();
-    auto scan = [&](const uint4 *cell, uint32_t from, uint32_t to, int sign) {  // positions [from,to) of one cell
-        const uint32_t *pw = reinterpret_cast<const uint32_t *>(cell + FMIDX_BHDR_U4);
-        for (uint32_t wi = (from >> 2) + (uint32_t)lane; wi < ((to + 3u) >> 2); wi += 32) {
-            const uint32_t word = __ldg(pw + wi);
+    const int sign_a = same ? 1 : -1;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t p = wi * 4u + (uint32_t)k;
-                if (p >= from && p < to) atomicAdd(&cnt[(word >> (8 * k)) & 255u], sign);
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t wi = (fa >> 2) + (uint32_t)lane + 32u * k;
+        if (wi < ((ta + 3u) >> 2)) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t p = wi * 4u + (uint32_t)e;
+                if (p >= fa && p < ta) atomicAdd(&cnt[(wa[k] >> (8 * e)) & 255u], sign_a);
             }
         }
-    };
-    if (cA == cB) {
-        scan(cellA, a, b, 1);
-    } else {
-        scan(cellA, 0u, a, -1);
-        scan(cellB, 0u, b, 1);
+        const uint32_t wj = (uint32_t)lane + 32u * k;
+        if (wj < ((tb + 3u) >> 2)) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t p = wj * 4u + (uint32_t)e;
+                if (p >= fb && p < tb) atomicAdd(&cnt[(wb[k] >> (8 * e)) & 255u], 1);
+            }
+        }
     }
     __syncwarp();
     uint32_t bits = 0;
@@ -548,7 +569,7 @@ __device__ __forceinline__ void fm_enum_slice(const FmDev &ix, const uint2 *__re
     __syncthreads();
     // stage 2: the byte level -- one warp per node
     const uint32_t nb = min(S.n_bnode, 48u);
-    for (uint32_t i = (uint32_t)wid; i < nb; i += MASK_THREADS / 32)
+    for (uint32_t i = (uint32_t)wid; i < nb; i += (blockDim.x >> 5))
         fm_eval_byte_node(ix, S.bnode[i][0], S.bnode[i][1], S.bnode[i][2], sa, se, shift, t0, S.bm, S.cnt[wid], counts_row, lane);
     __syncthreads();
 }
@@ -563,7 +584,7 @@ __device__ __forceinline__ void fm_slice_interval(const FmDev &ix, uint32_t t0, 
 }
 
 // ---- phase B, bitmap only: persistent CTAs over the work list ------------------------------------------
-__global__ void __launch_bounds__(MASK_THREADS)
+__global__ void __launch_bounds__(ITEM_THREADS, 1024 / ITEM_THREADS)
 k_mask_items(FmDev ix, const uint2 *__restrict__ top, uint32_t P_top, uint32_t LT, int64_t shift, uint32_t vocab,
              const uint32_t *__restrict__ items, const uint32_t *__restrict__ n_items_ptr, uint32_t *__restrict__ next_ptr,
              uint32_t *__restrict__ mask_out, uint32_t *__restrict__ counts_out) {
@@ -575,7 +596,7 @@ k_mask_items(FmDev ix, const uint2 *__restrict__ top, uint32_t P_top, uint32_t L
     for (;;) {
         __syncthreads();
         if (tid == 0) cur_item = atomicAdd(next_ptr, 1u);
-        for (int w = tid; w < SLICE / 32; w += MASK_THREADS) S.bm[w] = 0;
+        for (int w = tid; w < SLICE / 32; w += ITEM_THREADS) S.bm[w] = 0;
         __syncthreads();
         const uint32_t it = cur_item;
         if (it >= n_items) break;
@@ -585,7 +606,7 @@ k_mask_items(FmDev ix, const uint2 *__restrict__ top, uint32_t P_top, uint32_t L
         fm_enum_slice(ix, top + (size_t)b * P_top, LT, sa, se, shift, t0, S, counts_out ? counts_out + (size_t)b * vocab : nullptr);
         __syncthreads();
         const uint32_t nw = (t1 - t0 + 31u) >> 5;
-        for (uint32_t w = tid; w < nw; w += MASK_THREADS) mask_out[(size_t)b * mask_words + (t0 >> 5) + w] = S.bm[w];
+        for (uint32_t w = tid; w < nw; w += ITEM_THREADS) mask_out[(size_t)b * mask_words + (t0 >> 5) + w] = S.bm[w];
     }
 }
 
@@ -1132,7 +1153,7 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
               vocab, items, ctr, has ? nullptr : d_mask, has ? nullptr : d_counts);
     if (!has) {
         const unsigned grid = (unsigned)std::min<size_t>(nblk, (size_t)h->sm_count * 16);
-        FM_LAUNCH(k_mask_items, grid, MASK_THREADS, 0, s, ix, lvl + top_off, P_top, LT, shift, vocab, items, ctr, ctr + 1,
+        FM_LAUNCH(k_mask_items, grid, ITEM_THREADS, 0, s, ix, lvl + top_off, P_top, LT, shift, vocab, items, ctr, ctr + 1,
                   d_mask, d_counts);
         FM_CUDA(cudaGetLastError());
         return FMIDX_OK;
