@@ -108,13 +108,29 @@ __global__ void __launch_bounds__(128) k_search(FmDev ix, const int32_t *__restr
         bool ok = pend && (uint32_t)hl < hi - lo;
         uint32_t p = 0;
         if (ok) p = ix.sa_samples[lo + (uint32_t)hl];
-        for (int j = 0; j < rem && ok; ++j) {
-            const int64_t sym = (int64_t)toks[o0 + t_stop + j] + shift;
-            const uint32_t at = (uint32_t)(((uint64_t)p + n - 1u - ((uint32_t)j % n)) % n);  // (p-1-j) mod n: the text is cyclic under LF
-            ok = sym >= 0 && sym <= 0xFFFFFFFFll && (uint32_t)sym == ix.text[at];
+        const bool live = ok;
+        if (n >= 64u) {
+            // rem <= 31 < n: (p-1-j) mod n wraps at most once; the loads do not depend on `ok`, so they pipeline
+#pragma unroll 4
+            for (int j = 0; j < rem; ++j) {
+                const int64_t sym = (int64_t)toks[o0 + t_stop + j] + shift;
+                const uint32_t at = p > (uint32_t)j ? p - 1u - (uint32_t)j : p + n - 1u - (uint32_t)j;  // the text is cyclic under LF
+                const uint32_t tv = live ? ix.text[at] : 0u;
+                ok = ok && sym >= 0 && sym <= 0xFFFFFFFFll && (uint32_t)sym == tv;
+            }
+        } else {
+            for (int j = 0; j < rem && ok; ++j) {
+                const int64_t sym = (int64_t)toks[o0 + t_stop + j] + shift;
+                const uint32_t at = (uint32_t)(((uint64_t)p + n - 1u - ((uint32_t)j % n)) % n);
+                ok = sym >= 0 && sym <= 0xFFFFFFFFll && (uint32_t)sym == ix.text[at];
+            }
         }
         uint32_t mn = 0xFFFFFFFFu, mx = 0u;
-        if (ok) mn = mx = ix.isa_samples[(uint32_t)(((uint64_t)p + n - ((uint32_t)rem % n)) % n)];
+        if (ok) {
+            const uint32_t back = n >= 64u ? (p >= (uint32_t)rem ? p - (uint32_t)rem : p + n - (uint32_t)rem)
+                                           : (uint32_t)(((uint64_t)p + n - ((uint32_t)rem % n)) % n);
+            mn = mx = ix.isa_samples[back];
+        }
 #pragma unroll
         for (int o = 1; o < 16; o <<= 1) {
             mn = min(mn, __shfl_xor_sync(FULL, mn, o));
@@ -374,6 +390,12 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
         // and sets the bits in the pre-zeroed mask row; no node table, no work item.
         uint64_t s = sp[b], e = ep[b];
         if (e > ix.n) e = ix.n;
+        {   // zero this range's mask row here (the stores overlap the other warps' walks; no separate memset)
+            const uint32_t mw = (vocab + 31u) >> 5;
+            uint32_t *row = mask_out + (size_t)b * mw;
+            for (uint32_t i = (uint32_t)lane; i < mw; i += 32) row[i] = 0u;
+            __syncwarp();
+        }
         if (s >= e) return;
         if (e - s <= 32u) {
             const bool valid = (uint64_t)lane < e - s;
@@ -1146,8 +1168,7 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
     uint32_t *items = has ? nullptr : (uint32_t *)((char *)ws.p + lvl_bytes);
     uint32_t *ctr = (uint32_t *)((char *)ws.p + lvl_bytes + items_bytes);  // [0]=count [1]=next
     if (!has) {
-        FM_CUDA(cudaMemsetAsync(ctr, 0, 8, s));
-        FM_CUDA(cudaMemsetAsync(d_mask, 0, B * (size_t)((vocab + 31) / 32) * 4, s));
+        FM_CUDA(cudaMemsetAsync(ctr, 0, 8, s));  // the mask rows themselves are zeroed by k_mask_top
     }
     FM_LAUNCH(k_mask_top, (unsigned)((B * 32 + 127) / 128), 128, 0, s, ix, d_sp, d_ep, (uint32_t)B, LT, lvl, d_override, shift,
               vocab, items, ctr, has ? nullptr : d_mask, has ? nullptr : d_counts);
