@@ -219,7 +219,8 @@ def workload_config(args, batch):
             "tokens_per_gpu": args.tokens, "batch": batch, "prefix_len": "U{1..32} clipped at document end",
             "corpus": "Zipf(1.1) token ids, docs U[64,1024] ending in EOS 128009, 1% planted repeats",
             "l2": "index (>=5x L2) larger than L2; %d distinct prefix batches rotated" % N_QUERY_SETS,
-            "sharding": "by document, one shard per GPU, prefixes replicated, masks OR-reduced (all-to-all + OR)"}
+            "sharding": "by document, one shard per GPU, prefixes replicated, masks OR-reduce-scattered by pulling the occupied "
+                        "slices from peer memory over NVLink, counts all-reduced (NCCL)"}
 
 
 def main():
@@ -278,10 +279,12 @@ def main():
     words = (VOCAB + 31) // 32
     stream = torch.cuda.current_stream()
     sptr = C.c_void_p(stream.cuda_stream)
-    # two buffer sets: with N > 1 the cross-shard exchange of step k runs on its own stream while the
-    # kernels of step k+1 fill the other set
+    # N > 1: three buffer sets.  The cross-shard exchange of step k runs on its own stream while the kernels of
+    # step k+1 fill the next set; the bitmaps live in peer-visible memory and the exchange PULLS only the occupied
+    # 4096-token slices of the rows this rank owns (sharded.PeerMaskExchange), instead of an all-to-all of 16 KB rows.
+    NBUF = 3 if world > 1 else 1
     bufs = [(torch.empty(B, dtype=torch.int64, device=device), torch.empty(B, dtype=torch.int64, device=device),
-             torch.empty((B, words), dtype=torch.int32, device=device)) for _ in range(2 if world > 1 else 1)]
+             torch.empty((B, words), dtype=torch.int32, device=device) if world == 1 else None) for _ in range(NBUF)]
     sp, ep, mask = bufs[0]
     own = B // world  # prefixes whose final mask this rank owns
     from fm_index_constrained_decoding_b200 import sharded
@@ -289,32 +292,40 @@ def main():
     comm_stream = torch.cuda.Stream(device=device) if world > 1 else None
     ev_kernels = [torch.cuda.Event() for _ in bufs]
     ev_comm = [torch.cuda.Event() for _ in bufs]
+    px = sharded.PeerMaskExchange(ix, B, VOCAB, n_buffers=NBUF) if world > 1 else None
+    if world > 1:
+        mask = px.local_views[0]
+    cnt_bufs = [torch.empty(B, dtype=torch.int64, device=device) for _ in bufs]
 
     def step_full(k, ev=None, q_off=None):
         q, offs = q_off if q_off is not None else qsets[k % N_QUERY_SETS]
-        bi = k % len(bufs)
+        bi = k % NBUF
         bsp, bep, bmask = bufs[bi]
         if world > 1:
-            stream.wait_event(ev_comm[bi])  # the exchange that last read this buffer set has finished
+            # set bi was last pulled from by the peers at step k-3; this rank's exchange of step k-2 (whose
+            # all-gather every peer joins only after finishing its pull of step k-3) has to be complete
+            stream.wait_event(ev_comm[(k + 1) % NBUF])
         if ev:
             ev[0].record(stream)
         _native.check(L.fmidx_search_batch(ix._h, C.c_void_p(q.data_ptr()), C.c_void_p(offs.data_ptr()), B, SHIFT,
                                            C.c_void_p(bsp.data_ptr()), C.c_void_p(bep.data_ptr()), sptr))
         if ev:
             ev[1].record(stream)
-        _native.check(L.fmidx_distinct_mask_batch(ix._h, C.c_void_p(bsp.data_ptr()), C.c_void_p(bep.data_ptr()), B, SHIFT, VOCAB,
-                                                  C.c_void_p(bmask.data_ptr()), None, sptr))
+        if world > 1:
+            px.compute_local(bi, bsp, bep, SHIFT)
+        else:
+            _native.check(L.fmidx_distinct_mask_batch(ix._h, C.c_void_p(bsp.data_ptr()), C.c_void_p(bep.data_ptr()), B, SHIFT,
+                                                      VOCAB, C.c_void_p(bmask.data_ptr()), None, sptr))
         if ev:
             ev[2].record(stream)
         if world > 1:
-            # OR-reduce-scatter of the per-shard masks (all-to-all + fmidx_mask_or): rank r ends up owning the
-            # final masks of prefixes [r*B/W, (r+1)*B/W); total occurrence counts all-reduced (sum).  Runs on
-            # the exchange stream, overlapping the next step's kernels.
+            # rank r ends up owning the final masks of prefixes [r*B/W, (r+1)*B/W); total occurrence counts are
+            # all-reduced (sum).  Runs on the exchange stream, overlapping the next step's kernels.
             ev_kernels[bi].record(stream)
             with torch.cuda.stream(comm_stream):
                 comm_stream.wait_event(ev_kernels[bi])
-                result["mask"] = sharded.or_reduce_scatter(bmask, index=ix)[1]
-                result["count"] = sharded.sum_counts(bsp, bep)
+                result["mask"] = px.exchange(bi)              # one all-gather (occupancy + counts) + one pull kernel
+                result["count"] = px.total_counts(bi)
                 ev_comm[bi].record(comm_stream)
         else:
             result["mask"] = bmask
@@ -350,12 +361,13 @@ def main():
     if sampler and total_ms < 500:  # region too short for NVML's sampling period: keep the same load running
         t_end = time.time() + 0.6
         k = 0
+        scratch_mask = mask if world == 1 else torch.empty((B, words), dtype=torch.int32, device=device)
         while time.time() < t_end:  # local kernels only: the other ranks are not in this loop
             q, offs = qsets[k % N_QUERY_SETS]
             L.fmidx_search_batch(ix._h, C.c_void_p(q.data_ptr()), C.c_void_p(offs.data_ptr()), B, SHIFT,
                                  C.c_void_p(sp.data_ptr()), C.c_void_p(ep.data_ptr()), sptr)
             L.fmidx_distinct_mask_batch(ix._h, C.c_void_p(sp.data_ptr()), C.c_void_p(ep.data_ptr()), B, SHIFT, VOCAB,
-                                        C.c_void_p(mask.data_ptr()), None, sptr)
+                                        C.c_void_p(scratch_mask.data_ptr()), None, sptr)
             k += 1
             if k % 50 == 0:
                 torch.cuda.synchronize()
@@ -544,6 +556,7 @@ def main():
         }
         emit(line)
     if world > 1:
+        px.close()
         dist.destroy_process_group()
 
 

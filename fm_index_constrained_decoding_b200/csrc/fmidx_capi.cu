@@ -489,6 +489,122 @@ int fmidx_distinct_mask_batch(fmidx_t *h, const uint64_t *d_sp, const uint64_t *
                           (cudaStream_t)stream);
 }
 
+int fmidx_distinct_mask_batch_occ(fmidx_t *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, int64_t shift,
+                                  uint32_t vocab, uint32_t *d_mask, uint32_t *d_counts, uint32_t *d_occ, void *stream) {
+    FM_TRY(enter(h, true));
+    if (!d_mask || !d_occ) { fm_set_error("null argument"); return FMIDX_EINVAL; }
+    return fm_launch_mask(h, d_sp, d_ep, B, shift, vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, d_mask, d_counts,
+                          (cudaStream_t)stream, d_occ);
+}
+
+int fmidx_mask_pull_or(fmidx_t *h, const uint64_t *d_peer_masks, uint32_t world, const uint32_t *d_occ_all,
+                       size_t occ_stride, size_t row_lo, size_t n_rows, uint32_t vocab, uint32_t *d_out, void *stream) {
+    FM_TRY(enter(h, false));
+    if (!d_peer_masks || !d_occ_all || !d_out) { fm_set_error("null argument"); return FMIDX_EINVAL; }
+    return fm_launch_pull_or(h, (const uint32_t *const *)d_peer_masks, world, d_occ_all, occ_stride, row_lo, n_rows, vocab, d_out,
+                             (cudaStream_t)stream);
+}
+
+int fmidx_mask_pull_or_inplace(fmidx_t *h, const uint64_t *d_peer_masks, uint32_t world, uint32_t rank, const uint32_t *d_occ_all,
+                               size_t occ_stride, size_t row_lo, size_t n_rows, uint32_t vocab, void *stream) {
+    FM_TRY(enter(h, false));
+    if (!d_peer_masks || !d_occ_all || rank >= world) { fm_set_error("bad argument"); return FMIDX_EINVAL; }
+    return fm_launch_pull_or_inplace(h, (uint32_t *const *)d_peer_masks, world, rank, d_occ_all, occ_stride, row_lo, n_rows, vocab,
+                                     (cudaStream_t)stream);
+}
+
+int fmidx_xchg_publish(fmidx_t *h, const uint64_t *d_peer_inbox, const uint64_t *d_peer_flags, uint32_t world, uint32_t rank,
+                       const uint32_t *d_local, size_t xwords, uint32_t seq, void *stream) {
+    FM_TRY(enter(h, false));
+    if (!d_peer_inbox || !d_peer_flags || !d_local || rank >= world) { fm_set_error("bad argument"); return FMIDX_EINVAL; }
+    return fm_launch_xchg_publish(h, (uint32_t *const *)d_peer_inbox, (uint32_t *const *)d_peer_flags, world, rank, d_local, xwords,
+                                  seq, (cudaStream_t)stream);
+}
+
+int fmidx_xchg_wait(fmidx_t *h, const uint32_t *d_flags, uint32_t world, uint32_t seq, void *stream) {
+    FM_TRY(enter(h, false));
+    if (!d_flags || world == 0 || world > 1024) { fm_set_error("bad argument"); return FMIDX_EINVAL; }
+    return fm_launch_xchg_wait(h, d_flags, world, seq, (cudaStream_t)stream);
+}
+
+int fmidx_xchg_signal(fmidx_t *h, const uint64_t *d_peer_flags, uint32_t world, uint32_t rank, uint32_t seq, void *stream) {
+    FM_TRY(enter(h, false));
+    if (!d_peer_flags || rank >= world || world > 1024) { fm_set_error("bad argument"); return FMIDX_EINVAL; }
+    return fm_launch_xchg_signal(h, (uint32_t *const *)d_peer_flags, world, rank, seq, (cudaStream_t)stream);
+}
+
+// One host call per half of a sharded step (the Python loop was launch-bound with one call per kernel).
+// Side data layout of a shard (xwords u32): [B*ow occupancy words][B occurrence counts as u64], ow = ceil(nslices/32).
+int fmidx_xchg_local(fmidx_t *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, int64_t shift, uint32_t vocab,
+                     uint32_t *d_mask, uint32_t *d_xlocal, const uint32_t *d_ack_flags, uint32_t world, uint32_t rank,
+                     uint32_t wait_seq, void *stream) {
+    FM_TRY(enter(h, true));
+    if (rank >= world || B % world) { fm_set_error("bad rank/world/B"); return FMIDX_EINVAL; }
+    if (!d_mask || !d_xlocal || !d_ack_flags) { fm_set_error("null argument"); return FMIDX_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t ow = (((size_t)vocab + 4095) / 4096 + 31) / 32;
+    if (wait_seq) FM_TRY(fm_launch_xchg_wait(h, d_ack_flags, world, wait_seq, s));  // every shard has pulled the step that last used d_mask
+    // only the rows this rank owns come out as complete bitmaps; the others are written slice-wise (occupied slices)
+    FM_TRY(fm_launch_mask(h, d_sp, d_ep, B, shift, vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, d_mask, nullptr, s, d_xlocal,
+                          rank * (B / world), B / world));
+    return fm_launch_xchg_counts(h, d_sp, d_ep, B, (uint64_t *)(d_xlocal + B * ow), s);
+}
+
+int fmidx_xchg_round(fmidx_t *h, const uint64_t *d_peer_masks, const uint64_t *d_peer_inbox, const uint64_t *d_peer_data_flags,
+                     const uint64_t *d_peer_ack_flags, const uint32_t *d_data_flags, const uint32_t *d_inbox,
+                     const uint32_t *d_xlocal, uint32_t world, uint32_t rank, size_t B, uint32_t vocab, uint32_t seq,
+                     uint64_t *d_counts_out, void *stream) {
+    FM_TRY(enter(h, false));
+    if (!d_peer_masks || !d_peer_inbox || !d_peer_data_flags || !d_peer_ack_flags || !d_data_flags || !d_inbox || !d_xlocal ||
+        rank >= world || B % world) { fm_set_error("bad argument"); return FMIDX_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t ow = (((size_t)vocab + 4095) / 4096 + 31) / 32, xwords = B * ow + 2 * B, own = B / world;
+    FM_TRY(fm_launch_xchg_publish(h, (uint32_t *const *)d_peer_inbox, (uint32_t *const *)d_peer_data_flags, world, rank, d_xlocal, xwords, seq, s));
+    FM_TRY(fm_launch_xchg_wait(h, d_data_flags, world, seq, s));
+    FM_TRY(fm_launch_pull_or_inplace(h, (uint32_t *const *)d_peer_masks, world, rank, d_inbox, xwords, rank * own, own, vocab, s));
+    if (d_counts_out) FM_TRY(fm_launch_xchg_sum_counts(h, d_inbox, world, xwords, B * ow, B, d_counts_out, s));
+    return fm_launch_xchg_signal(h, (uint32_t *const *)d_peer_ack_flags, world, rank, seq, s);
+}
+
+// ---- peer-visible buffers (CUDA IPC) for the pull-style cross-shard exchange ------------------------------
+int fmidx_ipc_alloc(fmidx_t *h, size_t bytes, void **d_ptr, unsigned char handle[64]) {
+    FM_TRY(enter(h, false));
+    if (!d_ptr || !handle) { fm_set_error("null argument"); return FMIDX_EINVAL; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    FM_CUDA(cudaMalloc(d_ptr, bytes ? bytes : 16));
+    cudaIpcMemHandle_t hd;
+    cudaError_t e = cudaIpcGetMemHandle(&hd, *d_ptr);
+    if (e != cudaSuccess) {
+        cudaFree(*d_ptr);
+        *d_ptr = nullptr;
+        fm_set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+        return FMIDX_ECUDA;
+    }
+    memcpy(handle, &hd, 64);
+    return FMIDX_OK;
+}
+
+int fmidx_ipc_open(fmidx_t *h, const unsigned char handle[64], void **d_ptr) {
+    FM_TRY(enter(h, false));
+    if (!d_ptr || !handle) { fm_set_error("null argument"); return FMIDX_EINVAL; }
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle, 64);
+    FM_CUDA(cudaIpcOpenMemHandle(d_ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    return FMIDX_OK;
+}
+
+int fmidx_ipc_close(fmidx_t *h, void *d_ptr) {
+    FM_TRY(enter(h, false));
+    FM_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return FMIDX_OK;
+}
+
+int fmidx_ipc_free(fmidx_t *h, void *d_ptr) {
+    FM_TRY(enter(h, false));
+    FM_CUDA(cudaFree(d_ptr));
+    return FMIDX_OK;
+}
+
 int fmidx_mask_logits(fmidx_t *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, int64_t shift, uint32_t vocab,
                       const void *d_logits, void *d_out, int dtype, int64_t row_stride, const int32_t *d_override_tok,
                       int32_t always_allow, const uint32_t *d_extra_masks, uint32_t n_extra, uint32_t *d_mask_out,

@@ -80,8 +80,19 @@ int fm_launch_step(fmidx *h, const uint64_t *d_sym, const uint64_t *d_lo, const 
 int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, int64_t shift, uint32_t vocab,
                    const void *d_logits, void *d_out, int dtype, int64_t row_stride, const int32_t *d_override,
                    int32_t always_allow, const uint32_t *d_extra, uint32_t n_extra, uint32_t *d_mask,
-                   uint32_t *d_counts, cudaStream_t s);
+                   uint32_t *d_counts, cudaStream_t s, uint32_t *d_occ = nullptr, size_t dense_lo = 0, size_t dense_n = ~(size_t)0);
+int fm_launch_pull_or(fmidx *h, const uint32_t *const *d_peer_masks, uint32_t world, const uint32_t *d_occ_all,
+                      size_t occ_stride, size_t row_lo, size_t n_rows, uint32_t vocab, uint32_t *d_out, cudaStream_t s);
 int fm_launch_or(fmidx *h, const uint32_t *d_pieces, uint32_t n_pieces, size_t n_words, uint32_t *d_out, cudaStream_t s);
+int fm_launch_pull_or_inplace(fmidx *h, uint32_t *const *d_peer_masks, uint32_t world, uint32_t rank, const uint32_t *d_occ_all,
+                              size_t occ_stride, size_t row_lo, size_t n_rows, uint32_t vocab, cudaStream_t s);
+int fm_launch_xchg_counts(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, uint64_t *d_out, cudaStream_t s);
+int fm_launch_xchg_sum_counts(fmidx *h, const uint32_t *d_inbox, uint32_t world, size_t xwords, size_t count_off, size_t B,
+                              uint64_t *d_out, cudaStream_t s);
+int fm_launch_xchg_publish(fmidx *h, uint32_t *const *d_peer_inbox, uint32_t *const *d_peer_flags, uint32_t world, uint32_t rank,
+                           const uint32_t *d_local, size_t xwords, uint32_t seq, cudaStream_t s);
+int fm_launch_xchg_wait(fmidx *h, const uint32_t *d_flags, uint32_t world, uint32_t seq, cudaStream_t s);
+int fm_launch_xchg_signal(fmidx *h, uint32_t *const *d_peer_flags, uint32_t world, uint32_t rank, uint32_t seq, cudaStream_t s);
 int fm_launch_popcount(fmidx *h, const uint32_t *d_mask, size_t B, uint32_t vocab, uint32_t *d_n, cudaStream_t s);
 int fm_launch_compact(fmidx *h, const uint32_t *d_mask, const uint32_t *d_counts, size_t B, uint32_t vocab,
                       const uint64_t *d_offs, int64_t *d_tokens, uint64_t *d_cnts, cudaStream_t s);

@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(128)
 k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict__ ep, uint32_t B, uint32_t LT,
            uint2 *__restrict__ lvl, const int32_t *__restrict__ override_tok, int64_t shift, uint32_t vocab,
            uint32_t *__restrict__ work_items, uint32_t *__restrict__ work_count, uint32_t *__restrict__ mask_out,
-           uint32_t *__restrict__ counts_out) {
+           uint32_t *__restrict__ counts_out, uint32_t *__restrict__ occ_out, uint32_t dense_lo, uint32_t dense_n) {
     __shared__ uint4 stage[8][16];
     const int lane = threadIdx.x & 31, hw = (threadIdx.x >> 4) & 1, hl = threadIdx.x & 15;
     const int wslot = threadIdx.x >> 4;  // half-warp slot in the CTA
@@ -390,12 +390,20 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
         // and sets the bits in the pre-zeroed mask row; no node table, no work item.
         uint64_t s = sp[b], e = ep[b];
         if (e > ix.n) e = ix.n;
-        {   // zero this range's mask row here (the stores overlap the other warps' walks; no separate memset)
-            const uint32_t mw = (vocab + 31u) >> 5;
-            uint32_t *row = mask_out + (size_t)b * mw;
+        // Rows [dense_lo, dense_lo+dense_n) must come out as complete bitmaps and are zeroed here (the stores
+        // overlap the other warps' walks; no separate memset).  The remaining rows (sharded mode: rows whose final
+        // mask another rank assembles) are only ever read slice-wise through their occupancy bits, so only the
+        // slices that receive bits are zeroed: a prefix with a few continuations writes ~1 KB instead of 16 KB.
+        const uint32_t mw = (vocab + 31u) >> 5;
+        uint32_t *row = mask_out + (size_t)b * mw;
+        const bool dense = b - dense_lo < dense_n;
+        if (dense)
             for (uint32_t i = (uint32_t)lane; i < mw; i += 32) row[i] = 0u;
-            __syncwarp();
+        if (occ_out) {  // slice-occupancy words of this row (bit s: slice s may hold set bits)
+            const uint32_t ow = ((vocab + SLICE - 1) / SLICE + 31u) >> 5;
+            for (uint32_t i = (uint32_t)lane; i < ow; i += 32) occ_out[(size_t)b * ow + i] = 0u;
         }
+        __syncwarp();
         if (s >= e) return;
         if (e - s <= 32u) {
             const bool valid = (uint64_t)lane < e - s;
@@ -410,7 +418,24 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
             }
             const int64_t tk = (int64_t)c - shift;
             const bool inside = valid && tk >= 0 && tk < (int64_t)vocab;
-            if (inside) atomicOr(&mask_out[(size_t)b * ((vocab + 31u) >> 5) + ((uint32_t)tk >> 5)], 1u << ((uint32_t)tk & 31u));
+            const uint32_t sl = inside ? (uint32_t)tk / SLICE : 0xFFFFFFFFu;
+            if (!dense) {  // zero exactly the slices that are about to receive bits
+                uint32_t todo = __ballot_sync(FULL, inside);
+                while (todo) {
+                    const uint32_t s_cur = __shfl_sync(FULL, sl, __ffs(todo) - 1);
+                    const uint32_t w0 = s_cur * (SLICE / 32), w1 = min(w0 + SLICE / 32, mw);
+                    for (uint32_t i = w0 + (uint32_t)lane; i < w1; i += 32) row[i] = 0u;
+                    todo &= ~__ballot_sync(FULL, sl == s_cur);
+                }
+                __syncwarp();
+            }
+            if (inside) {
+                atomicOr(&row[(uint32_t)tk >> 5], 1u << ((uint32_t)tk & 31u));
+                if (occ_out) {
+                    const uint32_t ow = ((vocab + SLICE - 1) / SLICE + 31u) >> 5;
+                    atomicOr(&occ_out[(size_t)b * ow + (sl >> 5)], 1u << (sl & 31u));
+                }
+            }
             if (counts_out) {
                 const uint32_t same = __match_any_sync(FULL, inside ? c : (0xFFFFFF00u + (uint32_t)lane));
                 if (inside) counts_out[(size_t)b * vocab + (uint32_t)tk] = (uint32_t)__popc(same);
@@ -475,6 +500,7 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
             if (lane == 0 && bal) slot = atomicAdd(work_count, (uint32_t)__popc(bal));
             slot = __shfl_sync(FULL, slot, 0);
             if (ne) work_items[slot + __popc(bal & ((1u << lane) - 1u))] = b * nslices + s;
+            if (occ_out && lane == 0) occ_out[(size_t)b * ((nslices + 31u) >> 5) + (s0 >> 5)] = bal;
         }
     }
 }
@@ -941,6 +967,130 @@ __global__ void __launch_bounds__(256) k_or_pieces(const uint4 *__restrict__ pie
     }
 }
 
+// Cross-shard OR by PULLING over NVLink: the masks of the other shards live in peer memory (CUDA IPC);
+// this rank owns rows [row_lo, row_lo+n_rows) and ORs, for each of them, only the 4096-token slices that a
+// shard marked occupied -- a prefix with a handful of continuations moves a few hundred bytes per shard
+// instead of a 16 KB bitmap.  One CTA per owned row; loads from peers are coalesced 512-B segments.
+__global__ void __launch_bounds__(256)
+k_pull_or(const uint32_t *const *__restrict__ peer_masks, uint32_t world, const uint32_t *__restrict__ occ_all,
+          size_t occ_stride, uint32_t row_lo, uint32_t vocab, uint32_t *__restrict__ out) {
+    const uint32_t mask_words = (vocab + 31u) >> 5;
+    const uint32_t nslices = (vocab + SLICE - 1) / SLICE, ow = (nslices + 31u) >> 5;
+    const uint32_t r = blockIdx.x, row = row_lo + r;
+    for (uint32_t w = threadIdx.x; w < mask_words; w += 256) {
+        const uint32_t sl = w / (SLICE / 32);
+        uint32_t acc = 0;
+        for (uint32_t p = 0; p < world; ++p)
+            if ((occ_all[(size_t)p * occ_stride + (size_t)row * ow + (sl >> 5)] >> (sl & 31u)) & 1u)
+                acc |= __ldcs(peer_masks[p] + (size_t)row * mask_words + w);
+        out[(size_t)r * mask_words + w] = acc;
+    }
+}
+
+// In-place form: the rows this rank owns already hold its own shard's bits in its own buffer (which no
+// peer reads: peers pull the rows THEY own), so only the peers' occupied slices are touched -- traffic and
+// time proportional to what the other shards actually found.  One CTA per owned row, one WARP per occupied
+// slice (a slice is 128 words = one uint4 per lane), all peer loads of a warp issued before any is consumed:
+// a row costs about one NVLink load latency however many slices it has.
+__global__ void __launch_bounds__(256)
+k_pull_or_inplace(uint32_t *const *__restrict__ peer_masks, uint32_t world, uint32_t rank, const uint32_t *__restrict__ occ_all,
+                  size_t occ_stride, uint32_t row_lo, uint32_t vocab) {
+    const uint32_t mask_words = (vocab + 31u) >> 5;
+    const uint32_t nslices = (vocab + SLICE - 1) / SLICE, ow = (nslices + 31u) >> 5;
+    const uint32_t row = row_lo + blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t *mine = peer_masks[rank] + (size_t)row * mask_words;
+    for (uint32_t sl = (uint32_t)wid; sl < nslices; sl += 8) {
+        const uint32_t w = sl * (SLICE / 32) + 4u * (uint32_t)lane;
+        if (w >= mask_words) continue;
+        uint4 acc = make_uint4(0, 0, 0, 0);
+        bool any = false;
+        const bool vec = (w + 4u <= mask_words) && ((((size_t)row * mask_words + w) & 3u) == 0);
+        for (uint32_t p = 0; p < world; ++p) {
+            if (p == rank) continue;
+            if (!((occ_all[(size_t)p * occ_stride + (size_t)row * ow + (sl >> 5)] >> (sl & 31u)) & 1u)) continue;
+            const uint32_t *theirs = peer_masks[p] + (size_t)row * mask_words + w;
+            any = true;
+            if (vec) {
+                const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(theirs));
+                acc.x |= v.x; acc.y |= v.y; acc.z |= v.z; acc.w |= v.w;
+            } else {
+                acc.x |= __ldcs(theirs);
+                if (w + 1 < mask_words) acc.y |= __ldcs(theirs + 1);
+                if (w + 2 < mask_words) acc.z |= __ldcs(theirs + 2);
+                if (w + 3 < mask_words) acc.w |= __ldcs(theirs + 3);
+            }
+        }
+        if (any && (acc.x | acc.y | acc.z | acc.w)) {
+            mine[w] |= acc.x;
+            if (w + 1 < mask_words) mine[w + 1] |= acc.y;
+            if (w + 2 < mask_words) mine[w + 2] |= acc.z;
+            if (w + 3 < mask_words) mine[w + 3] |= acc.w;
+        }
+    }
+}
+
+// side data of one shard for one step: [B*ow occupancy words][B counts as int64]
+__global__ void __launch_bounds__(256) k_xchg_counts(const uint64_t *__restrict__ sp, const uint64_t *__restrict__ ep, uint32_t B,
+                                                     uint64_t *__restrict__ out) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) out[b] = ep[b] - sp[b];
+}
+__global__ void __launch_bounds__(256) k_xchg_sum_counts(const uint32_t *__restrict__ inbox, uint32_t world, size_t xwords,
+                                                         size_t count_off, uint32_t B, uint64_t *__restrict__ out) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    uint64_t acc = 0;
+    for (uint32_t p = 0; p < world; ++p)
+        acc += reinterpret_cast<const uint64_t *>(inbox + (size_t)p * xwords + count_off)[b];
+    out[b] = acc;
+}
+
+// ---- NCCL-free signalling for the pull exchange: data + flags written straight into peer memory ---------
+// (one process per GPU; a flag is a monotonically increasing step number, so nothing is ever reset)
+__device__ __forceinline__ uint32_t fm_ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fm_st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// CTA d copies this rank's side data into slot `rank` of shard d's inbox, then raises flags[rank] = seq there
+__global__ void __launch_bounds__(256) k_xchg_publish(uint32_t *const *__restrict__ peer_inbox, uint32_t *const *__restrict__ peer_flags,
+                                                      uint32_t rank, const uint32_t *__restrict__ local, size_t xwords, uint32_t seq) {
+    const uint32_t d = blockIdx.x;
+    uint32_t *dst = peer_inbox[d] + (size_t)rank * xwords;
+    if (((xwords & 3) == 0) && ((((uintptr_t)dst | (uintptr_t)local) & 15) == 0)) {
+        const size_t nv = xwords / 4;
+        for (size_t i = threadIdx.x; i < nv; i += 256) reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(local)[i];
+    } else {
+        for (size_t i = threadIdx.x; i < xwords; i += 256) dst[i] = local[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) fm_st_release_sys(peer_flags[d] + rank, seq);
+}
+
+// one CTA, thread p waits until flags[p] >= seq (bounded: traps after ~10 s instead of hanging the GPU)
+__global__ void k_xchg_wait(const uint32_t *__restrict__ flags, uint32_t world, uint32_t seq) {
+    const uint32_t p = threadIdx.x;
+    if (p >= world) return;
+    const long long t0 = clock64();
+    while ((int32_t)(fm_ld_acquire_sys(flags + p) - seq) < 0) {
+        __nanosleep(200);
+        if (clock64() - t0 > 20000000000ll) __trap();
+    }
+}
+
+__global__ void k_xchg_signal(uint32_t *const *__restrict__ peer_flags, uint32_t world, uint32_t rank, uint32_t seq) {
+    const uint32_t d = threadIdx.x;
+    if (d >= world) return;
+    __threadfence_system();
+    fm_st_release_sys(peer_flags[d] + rank, seq);
+}
+
 __global__ void __launch_bounds__(256) k_popcount(const uint32_t *__restrict__ mask, uint32_t mask_words,
                                                   uint32_t *__restrict__ n_out) {
     __shared__ uint32_t part[8];
@@ -1142,9 +1292,10 @@ int fm_launch_step(fmidx *h, const uint64_t *d_sym, const uint64_t *d_lo, const 
 int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, int64_t shift, uint32_t vocab,
                    const void *d_logits, void *d_out, int dtype, int64_t row_stride, const int32_t *d_override,
                    int32_t always_allow, const uint32_t *d_extra, uint32_t n_extra, uint32_t *d_mask,
-                   uint32_t *d_counts, cudaStream_t s) {
+                   uint32_t *d_counts, cudaStream_t s, uint32_t *d_occ, size_t dense_lo, size_t dense_n) {
     FM_TRY(check_ready(h));
     if (B == 0 || vocab == 0) return FMIDX_OK;
+    if (!d_occ) { dense_lo = 0; dense_n = B; }  // sparse rows are only meaningful together with occupancy words
     const uint32_t nslices = (vocab + SLICE - 1) / SLICE;
     const size_t nblk = (size_t)nslices * B;
     if (nblk > 0x7FFFFFFFull) { fm_set_error("mask batch too large: split the call"); return FMIDX_EINVAL; }
@@ -1171,7 +1322,8 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
         FM_CUDA(cudaMemsetAsync(ctr, 0, 8, s));  // the mask rows themselves are zeroed by k_mask_top
     }
     FM_LAUNCH(k_mask_top, (unsigned)((B * 32 + 127) / 128), 128, 0, s, ix, d_sp, d_ep, (uint32_t)B, LT, lvl, d_override, shift,
-              vocab, items, ctr, has ? nullptr : d_mask, has ? nullptr : d_counts);
+              vocab, items, ctr, has ? nullptr : d_mask, has ? nullptr : d_counts, has ? nullptr : d_occ, (uint32_t)dense_lo,
+              (uint32_t)std::min<size_t>(dense_n, 0xFFFFFFFFu));
     if (!has) {
         const unsigned grid = (unsigned)std::min<size_t>(nblk, (size_t)h->sm_count * 16);
         FM_LAUNCH(k_mask_items, grid, ITEM_THREADS, 0, s, ix, lvl + top_off, P_top, LT, shift, vocab, items, ctr, ctr + 1,
@@ -1256,6 +1408,64 @@ int fm_launch_or(fmidx *h, const uint32_t *d_pieces, uint32_t n_pieces, size_t n
     const size_t cap = (size_t)h->sm_count * 8;
     const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((n_vec + 255) / 256, cap));
     FM_LAUNCH(k_or_pieces, grid, 256, 0, s, (const uint4 *)d_pieces, n_pieces, n_vec, (uint4 *)d_out);
+    FM_CUDA(cudaGetLastError());
+    return FMIDX_OK;
+}
+
+int fm_launch_pull_or(fmidx *h, const uint32_t *const *d_peer_masks, uint32_t world, const uint32_t *d_occ_all,
+                      size_t occ_stride, size_t row_lo, size_t n_rows, uint32_t vocab, uint32_t *d_out, cudaStream_t s) {
+    (void)h;
+    if (n_rows == 0) return FMIDX_OK;
+    FM_LAUNCH(k_pull_or, (unsigned)n_rows, 256, 0, s, d_peer_masks, world, d_occ_all, occ_stride, (uint32_t)row_lo, vocab, d_out);
+    FM_CUDA(cudaGetLastError());
+    return FMIDX_OK;
+}
+
+int fm_launch_pull_or_inplace(fmidx *h, uint32_t *const *d_peer_masks, uint32_t world, uint32_t rank, const uint32_t *d_occ_all,
+                              size_t occ_stride, size_t row_lo, size_t n_rows, uint32_t vocab, cudaStream_t s) {
+    (void)h;
+    if (n_rows == 0) return FMIDX_OK;
+    static_assert(SLICE / 32 == 128, "k_pull_or_inplace maps one lane to four words of a slice");
+    FM_LAUNCH(k_pull_or_inplace, (unsigned)n_rows, 256, 0, s, d_peer_masks, world, rank, d_occ_all, occ_stride, (uint32_t)row_lo, vocab);
+    FM_CUDA(cudaGetLastError());
+    return FMIDX_OK;
+}
+
+int fm_launch_xchg_counts(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, uint64_t *d_out, cudaStream_t s) {
+    (void)h;
+    if (B == 0) return FMIDX_OK;
+    FM_LAUNCH(k_xchg_counts, (unsigned)((B + 255) / 256), 256, 0, s, d_sp, d_ep, (uint32_t)B, d_out);
+    FM_CUDA(cudaGetLastError());
+    return FMIDX_OK;
+}
+
+int fm_launch_xchg_sum_counts(fmidx *h, const uint32_t *d_inbox, uint32_t world, size_t xwords, size_t count_off, size_t B,
+                              uint64_t *d_out, cudaStream_t s) {
+    (void)h;
+    if (B == 0) return FMIDX_OK;
+    FM_LAUNCH(k_xchg_sum_counts, (unsigned)((B + 255) / 256), 256, 0, s, d_inbox, world, xwords, count_off, (uint32_t)B, d_out);
+    FM_CUDA(cudaGetLastError());
+    return FMIDX_OK;
+}
+
+int fm_launch_xchg_publish(fmidx *h, uint32_t *const *d_peer_inbox, uint32_t *const *d_peer_flags, uint32_t world, uint32_t rank,
+                           const uint32_t *d_local, size_t xwords, uint32_t seq, cudaStream_t s) {
+    (void)h;
+    FM_LAUNCH(k_xchg_publish, world, 256, 0, s, d_peer_inbox, d_peer_flags, rank, d_local, xwords, seq);
+    FM_CUDA(cudaGetLastError());
+    return FMIDX_OK;
+}
+
+int fm_launch_xchg_wait(fmidx *h, const uint32_t *d_flags, uint32_t world, uint32_t seq, cudaStream_t s) {
+    (void)h;
+    FM_LAUNCH(k_xchg_wait, 1, 32 * ((world + 31) / 32), 0, s, d_flags, world, seq);
+    FM_CUDA(cudaGetLastError());
+    return FMIDX_OK;
+}
+
+int fm_launch_xchg_signal(fmidx *h, uint32_t *const *d_peer_flags, uint32_t world, uint32_t rank, uint32_t seq, cudaStream_t s) {
+    (void)h;
+    FM_LAUNCH(k_xchg_signal, 1, 32 * ((world + 31) / 32), 0, s, d_peer_flags, world, rank, seq);
     FM_CUDA(cudaGetLastError());
     return FMIDX_OK;
 }

@@ -151,3 +151,136 @@ class ShardedFMIndex:
         valid = rows < ep.unsqueeze(1)
         pos = self.index.locate_batch(torch.where(valid, rows, torch.zeros_like(rows)).contiguous().view(-1)).view(-1, k)
         return gather_hits(pos, valid, self.pos_base, self.group)
+
+
+class _RawCuda:
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can view it."""
+
+    def __init__(self, ptr, n_words):
+        self.__cuda_array_interface__ = {"shape": (n_words,), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
+
+
+class PeerMaskExchange:
+    """OR-reduce-scatter of the per-shard bitmaps by PULLING over NVLink peer memory -- no NCCL in the loop.
+
+    The dense all-to-all moves 16 KB per prefix per shard although a prefix with a few tokens of history has a
+    handful of continuations.  Here every rank keeps its [B, words] bitmaps in a peer-visible buffer (CUDA IPC,
+    fmidx_ipc_*) together with one occupancy word per row (bit s: 4096-token slice s may be non-empty, produced
+    by the mask kernels themselves).  Per step (all kernels of this library, data and flags written straight
+    into peer memory):
+      publish  this shard's occupancy words + occurrence counts -> slot `rank` of every shard's inbox, then
+               flag[rank] = step on every shard                                (fmidx_xchg_publish)
+      wait     a one-CTA kernel spins until every shard's flag reached this step   (fmidx_xchg_wait)
+      pull     for the rows this rank owns, read only the occupied slices out of the peers' bitmaps and OR
+               them                                                              (fmidx_mask_pull_or)
+      ack      ack[rank] = step on every shard                                  (fmidx_xchg_signal)
+    `n_buffers` >= 3 buffer sets let the exchange of step k (on its own stream) overlap the kernels of step k+1;
+    before a set is overwritten, compute_local waits for every shard's ack of the step that last used it.
+    """
+
+    def __init__(self, index, B, vocab, n_buffers=3, group=None):
+        import ctypes as C
+        from . import _native as N
+        self.index, self.group = index, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        assert B % self.world == 0
+        self.B, self.vocab, self.own = B, vocab, B // self.world
+        self.words = (vocab + 31) // 32
+        self.ow = ((vocab + 4095) // 4096 + 31) // 32
+        self.n = n_buffers
+        self.dev = dev = torch.device("cuda", index.device_index)
+        self._local, self._peers = [], []
+        # side data of one shard for one step: occupancy words, then the occurrence counts (ep - sp) as int64
+        self.xwords = B * self.ow + 2 * B
+        self.mask_ptr, self.mask_tables, self.local_views = [], [], []
+        self.inbox_ptr, self.inbox_tables, self.inbox_views = [], [], []
+        for _ in range(n_buffers):
+            ptr, table = self._shared(B * self.words * 4)
+            self.mask_ptr.append(ptr)
+            self.mask_tables.append(table)
+            self.local_views.append(torch.as_tensor(_RawCuda(ptr, B * self.words), device=dev).view(B, self.words))
+            ptr, table = self._shared(self.world * self.xwords * 4)
+            self.inbox_ptr.append(ptr)
+            self.inbox_tables.append(table)
+            self.inbox_views.append(torch.as_tensor(_RawCuda(ptr, self.world * self.xwords), device=dev).view(self.world, self.xwords))
+        fptr, ftable = self._shared(2 * self.world * 4)
+        self.flags = torch.as_tensor(_RawCuda(fptr, 2 * self.world), device=dev)
+        self.flags.zero_()
+        self.data_flag_table = ftable                                  # flags[0:world]  : data of step s published
+        self.ack_flag_table = ftable + 4 * self.world                  # flags[world:2w] : step s pulled
+        self.xlocal = [torch.empty(self.xwords, dtype=torch.int32, device=dev) for _ in range(n_buffers)]
+        self.counts = [torch.empty(B, dtype=torch.int64, device=dev) for _ in range(n_buffers)]
+        self.own_views = [v[self.rank * self.own:(self.rank + 1) * self.own] for v in self.local_views]
+        self.seq = 0
+        self.last_seq = [0] * n_buffers
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+
+    def _shared(self, nbytes):
+        """Allocate a peer-visible buffer; returns (local pointer, device table of every rank's pointer to its copy)."""
+        import ctypes as C
+        from . import _native as N
+        L = N.lib()
+        ptr = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        N.check(L.fmidx_ipc_alloc(self.index._h, nbytes, C.byref(ptr), handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=self.group)
+        ptrs = []
+        for r in range(self.world):
+            if r == self.rank:
+                ptrs.append(ptr.value)
+            else:
+                q = C.c_void_p()
+                hb = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+                N.check(L.fmidx_ipc_open(self.index._h, hb, C.byref(q)))
+                ptrs.append(q.value)
+                self._peers.append(q.value)
+        self._local.append(ptr.value)
+        return ptr.value, torch.tensor(ptrs, dtype=torch.int64, device=self.dev)
+
+    @staticmethod
+    def _s():
+        import ctypes as C
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def compute_local(self, i, sp, ep, shift=10):
+        """K2 of this shard for all B prefixes into buffer set i (bitmaps + occupancy words + counts), current
+        stream; first waits (on the GPU) until every shard has pulled the step that last used set i."""
+        import ctypes as C
+        from . import _native as N
+        N.check(N.lib().fmidx_xchg_local(
+            self.index._h, C.c_void_p(sp.data_ptr()), C.c_void_p(ep.data_ptr()), self.B, shift, self.vocab,
+            C.c_void_p(self.mask_ptr[i]), C.c_void_p(self.xlocal[i].data_ptr()),
+            C.c_void_p(self.flags.data_ptr() + 4 * self.world), self.world, self.rank, self.last_seq[i], self._s()))
+
+    def exchange(self, i):
+        """publish -> wait -> pull + OR (in place) -> total counts -> ack for buffer set i, ONE host call, current
+        stream.  Returns the final [B/world, words] bitmaps of the rows this rank owns (a view of set i)."""
+        import ctypes as C
+        from . import _native as N
+        self.seq += 1
+        N.check(N.lib().fmidx_xchg_round(
+            self.index._h, C.c_void_p(self.mask_tables[i].data_ptr()), C.c_void_p(self.inbox_tables[i].data_ptr()),
+            C.c_void_p(self.data_flag_table.data_ptr()), C.c_void_p(self.ack_flag_table.data_ptr()),
+            C.c_void_p(self.flags.data_ptr()), C.c_void_p(self.inbox_ptr[i]), C.c_void_p(self.xlocal[i].data_ptr()),
+            self.world, self.rank, self.B, self.vocab, self.seq, C.c_void_p(self.counts[i].data_ptr()), self._s()))
+        self.last_seq[i] = self.seq
+        return self.own_views[i]
+
+    def total_counts(self, i):
+        """Sum over shards of the occurrence counts of all B prefixes (they rode in the published side data and
+        were summed by exchange())."""
+        return self.counts[i]
+
+    def close(self):
+        import ctypes as C
+        from . import _native as N
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for q in self._peers:
+            N.lib().fmidx_ipc_close(self.index._h, C.c_void_p(q))
+        dist.barrier(group=self.group)
+        for p in self._local:
+            N.lib().fmidx_ipc_free(self.index._h, C.c_void_p(p))
+        self._peers, self._local = [], []

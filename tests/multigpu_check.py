@@ -51,12 +51,13 @@ def main():
     words = (V + 31) // 32
     exp_mask = np.zeros((B, words), np.uint32)
     exp_cnt = np.zeros(B, np.int64)
-    shard_res = []
+    shard_res, shard_masks = [], []
     for a, b in parts:
         o = OracleFMIndex()
         o.initialize(docs[a:b])
         osp, oep, om, _ = o.query_batch(toks, offs, want_mask=True, vocab=V, nthreads=4)
         exp_mask |= om
+        shard_masks.append(om)
         exp_cnt += (oep - osp).astype(np.int64)
         shard_res.append((osp, oep, o, beg[a]))
     assert (sp.cpu().numpy().astype(np.uint64) == shard_res[rank][0]).all()
@@ -67,6 +68,28 @@ def main():
     m_all = sh.distinct_mask_batch(sp, ep, V, everywhere=True)
     assert (m_all.cpu().numpy().view(np.uint32) == exp_mask).all()
     assert (sh.count_batch(sp, ep).cpu().numpy() == exp_cnt).all()
+    # pull-style exchange over peer memory (CUDA IPC): same result as the all-to-all path, three buffer sets
+    px = sharded.PeerMaskExchange(ix, B, V, n_buffers=3)
+    for it in range(4):
+        i = it % 3
+        px.compute_local(i, sp, ep)
+        got = px.exchange(i)
+        torch.cuda.synchronize()
+        assert (got.cpu().numpy().view(np.uint32) == exp_mask[rank * own:(rank + 1) * own]).all(), "pull exchange mismatch"
+        # rows owned by peers hold this shard's bits in their OCCUPIED slices (the rest is never read)
+        loc = px.local_views[i].cpu().numpy().view(np.uint32)
+        occ = px.xlocal[i][:B].cpu().numpy().view(np.uint32)
+        for r in range(B):
+            if rank * own <= r < (rank + 1) * own:
+                continue
+            for sl in range(32):
+                w0, w1 = sl * 128, min((sl + 1) * 128, words)
+                if (occ[r] >> sl) & 1:
+                    assert (loc[r, w0:w1] == shard_masks[rank][r, w0:w1]).all()
+                else:
+                    assert not shard_masks[rank][r, w0:w1].any()
+        assert (px.total_counts(i).cpu().numpy() == exp_cnt).all()
+    px.close()
     # fused rows
     g = torch.Generator().manual_seed(rank)
     logits = torch.randn(own, V, generator=g)
