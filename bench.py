@@ -227,7 +227,7 @@ def workload_config(args, batch):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--tokens", type=int, default=100_000_000)
@@ -375,7 +375,7 @@ def main():
     barrier()
     total_ms = e_start.elapsed_time(e_end)
     launches = L.fmidx_launch_count() - launches0
-    if sampler and total_ms < 500:  # region too short for NVML's sampling period: keep the same load running
+    if sampler and total_ms < 150:  # region too short for NVML's sampling period: keep the same load running
         t_end = time.time() + 0.6
         k = 0
         scratch_mask = mask if world == 1 else torch.empty((B, words), dtype=torch.int32, device=device)
@@ -390,7 +390,7 @@ def main():
                 torch.cuda.synchronize()
         torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
-    if clocks is not None and total_ms < 500:
+    if clocks is not None and total_ms < 150:
         clocks["note"] = "timed region %.0f ms is shorter than NVML's sampling period; sampled while the same step kept running" % total_ms
     t_search = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
     t_mask = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))

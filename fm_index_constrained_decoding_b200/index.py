@@ -134,6 +134,27 @@ class FMIndex(_FMIndex):
                                           SHIFT, sp.ctypes.data_as(C.c_void_p), ep.ctypes.data_as(C.c_void_p)))
         return int(sp[0]), int(ep[0])
 
+    def get_range_many(self, sequences):
+        """get_range for a list of prefixes in ONE device batch (host lists in, list of (sp, ep) out)."""
+        toks, offs = ragged([list(s) for s in sequences])
+        B = len(sequences)
+        sp = np.empty(max(B, 1), dtype=np.uint64)
+        ep = np.empty(max(B, 1), dtype=np.uint64)
+        if B:
+            N.check(N.lib().fmidx_search_host(self._h, toks.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p), B,
+                                              SHIFT, sp.ctypes.data_as(C.c_void_p), ep.ctypes.data_as(C.c_void_p)))
+        return [(int(sp[i]), int(ep[i])) for i in range(B)]
+
+    def doc_indices_of_rows(self, lo, hi):
+        """get_doc_index_from_row for rows [lo, hi) in one locate batch."""
+        if hi <= lo:
+            return []
+        rows = np.arange(lo, hi, dtype=np.uint64)
+        pos = np.empty(rows.size, dtype=np.uint64)
+        N.check(N.lib().fmidx_locate_host(self._h, rows.ctypes.data_as(C.c_void_p), rows.size, pos.ctypes.data_as(C.c_void_p)))
+        beg = np.asarray(self.beginnings, dtype=np.uint64)
+        return [int(d) for d in np.searchsorted(beg, pos, side="right") - 1]
+
     def get_count(self, sequence):
         lo, hi = self.get_range(sequence)
         return hi - lo
