@@ -309,25 +309,35 @@ __device__ __forceinline__ void fm_eval_byte_node(const FmDev &ix, uint32_t lo, 
     const uint32_t cA = lo >> 9, a = lo & 511u, cB = hi >> 9, b = hi & 511u;
     const uint4 *cellA = ix.bcells + (size_t)cA * FMIDX_BCELL_U4, *cellB = ix.bcells + (size_t)cB * FMIDX_BCELL_U4;
     const bool same = cA == cB;
-    // every load of the node is issued before anything is consumed: the two header slices of this lane's
-    // 8 symbols and the payload words of both scans (a cell has 128 words -> at most 4 per lane per scan)
-    const uint32_t fa = same ? a : 0u, ta = same ? b : a;   // scan 1: cell A, positions [fa,ta), sign +1 / -1
-    const uint32_t fb = 0u, tb = same ? 0u : b;             // scan 2: cell B, positions [0,tb),  sign +1
+    // Each end is counted from its CHEAPER side: #v in A[0,a) is either scanned directly (a <= 256) or taken as
+    // (hdr of cell A+1 - hdr of cell A) - #v in A[a,512); likewise for B when cell B+1 exists (then cell B has no
+    // invalid tail positions).  So
+    //   cnt[v] = hB[v] - hA[v] + sA * #v in A[fa,ta) + sB * #v in B[fb,tb)
+    // with (hA, fa, ta, sA) = (hdrA, 0, a, -1) or (hdrA+1, a, 512, +1) and (hB, fb, tb, sB) = (hdrB, 0, b, +1) or
+    // (hdrB+1, b, 512, -1): at most 256 bytes are scanned per end.  Same cell: one scan of [a,b), no headers.
+    const bool a_hi = !same && a > 256u;
+    const bool b_hi = !same && b > 256u && cB + 1u < ix.nbblocks;
+    const uint32_t fa = same ? a : (a_hi ? a : 0u), ta = same ? b : (a_hi ? 512u : a);
+    const uint32_t fb = b_hi ? b : 0u, tb = same ? 0u : (b_hi ? 512u : b);
+    const int sign_a = same ? 1 : (a_hi ? 1 : -1), sign_b = b_hi ? -1 : 1;
+    const uint4 *hA = a_hi ? cellA + FMIDX_BCELL_U4 : cellA, *hB = b_hi ? cellB + FMIDX_BCELL_U4 : cellB;
     const uint32_t *pwa = reinterpret_cast<const uint32_t *>(cellA + FMIDX_BHDR_U4);
     const uint32_t *pwb = reinterpret_cast<const uint32_t *>(cellB + FMIDX_BHDR_U4);
+    // every load of the node is issued before anything is consumed: the two header slices of this lane's
+    // 8 symbols and the payload words of both scans (a cell has 128 words -> at most 4 per lane per scan)
     uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0, b0 = a0, b1 = a0;
     if (!same) {
-        a0 = fm_ldg(cellA + 2 * lane);
-        a1 = fm_ldg(cellA + 2 * lane + 1);
-        b0 = fm_ldg(cellB + 2 * lane);
-        b1 = fm_ldg(cellB + 2 * lane + 1);
+        a0 = fm_ldg(hA + 2 * lane);
+        a1 = fm_ldg(hA + 2 * lane + 1);
+        b0 = fm_ldg(hB + 2 * lane);
+        b1 = fm_ldg(hB + 2 * lane + 1);
     }
     uint32_t wa[4], wb[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const uint32_t wi = (fa >> 2) + (uint32_t)lane + 32u * k;
         wa[k] = wi < ((ta + 3u) >> 2) ? __ldg(pwa + wi) : 0u;
-        const uint32_t wj = (uint32_t)lane + 32u * k;
+        const uint32_t wj = (fb >> 2) + (uint32_t)lane + 32u * k;
         wb[k] = wj < ((tb + 3u) >> 2) ? __ldg(pwb + wj) : 0u;
     }
     {
@@ -336,7 +346,6 @@ __device__ __forceinline__ void fm_eval_byte_node(const FmDev &ix, uint32_t lo, 
         c[4] = (int)(b1.x - a1.x); c[5] = (int)(b1.y - a1.y); c[6] = (int)(b1.z - a1.z); c[7] = (int)(b1.w - a1.w);
     }
     __syncwarp();
-    const int sign_a = same ? 1 : -1;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const uint32_t wi = (fa >> 2) + (uint32_t)lane + 32u * k;
@@ -347,12 +356,12 @@ __device__ __forceinline__ void fm_eval_byte_node(const FmDev &ix, uint32_t lo, 
                 if (p >= fa && p < ta) atomicAdd(&cnt[(wa[k] >> (8 * e)) & 255u], sign_a);
             }
         }
-        const uint32_t wj = (uint32_t)lane + 32u * k;
+        const uint32_t wj = (fb >> 2) + (uint32_t)lane + 32u * k;
         if (wj < ((tb + 3u) >> 2)) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const uint32_t p = wj * 4u + (uint32_t)e;
-                if (p >= fb && p < tb) atomicAdd(&cnt[(wb[k] >> (8 * e)) & 255u], 1);
+                if (p >= fb && p < tb) atomicAdd(&cnt[(wb[k] >> (8 * e)) & 255u], sign_b);
             }
         }
     }
@@ -376,7 +385,7 @@ __device__ __forceinline__ void fm_eval_byte_node(const FmDev &ix, uint32_t lo, 
 __global__ void __launch_bounds__(128)
 k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict__ ep, uint32_t B, uint32_t LT,
            uint2 *__restrict__ lvl, const int32_t *__restrict__ override_tok, int64_t shift, uint32_t vocab,
-           uint32_t *__restrict__ work_items, uint32_t *__restrict__ work_count, uint32_t *__restrict__ mask_out,
+           uint4 *__restrict__ work_items, uint32_t *__restrict__ work_count, uint32_t *__restrict__ mask_out,
            uint32_t *__restrict__ counts_out, uint32_t *__restrict__ occ_out, uint32_t dense_lo, uint32_t dense_n) {
     __shared__ uint4 stage[8][16];
     const int lane = threadIdx.x & 31, hw = (threadIdx.x >> 4) & 1, hl = threadIdx.x & 15;
@@ -485,6 +494,7 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
         for (uint32_t s0 = 0; s0 < nslices; s0 += 32) {
             const uint32_t s = s0 + lane;
             bool ne = false;
+            uint32_t nseed = 0, sd[2][3] = {{0, 0, 0}, {0, 0, 0}};
             if (s < nslices) {
                 int64_t a64 = (int64_t)s * SLICE + shift, e64 = (int64_t)min((s + 1) * (uint32_t)SLICE, vocab) + shift;
                 if (a64 < 0) a64 = 0;
@@ -492,14 +502,24 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
                 if (a64 < e64)
                     for (uint32_t p = (uint32_t)a64 >> span_bits; p <= ((uint32_t)e64 - 1u) >> span_bits; ++p) {
                         const uint2 nd = cur[p];
-                        ne |= nd.y > nd.x;
+                        if (nd.y > nd.x && nseed < 2) {  // a 4096-token slice overlaps at most two depth-LT nodes
+                            sd[nseed][0] = nd.x;
+                            sd[nseed][1] = nd.y;
+                            sd[nseed][2] = p;
+                            ++nseed;
+                        }
                     }
+                ne = nseed > 0;
             }
             const uint32_t bal = __ballot_sync(FULL, ne);
             uint32_t slot = 0;
             if (lane == 0 && bal) slot = atomicAdd(work_count, (uint32_t)__popc(bal));
             slot = __shfl_sync(FULL, slot, 0);
-            if (ne) work_items[slot + __popc(bal & ((1u << lane) - 1u))] = b * nslices + s;
+            if (ne) {  // the item carries its seeds: the consumer needs no further lookup
+                uint4 *e = work_items + 2 * (size_t)(slot + __popc(bal & ((1u << lane) - 1u)));
+                e[0] = make_uint4(b * nslices + s, nseed, sd[0][0], sd[0][1]);
+                e[1] = make_uint4(sd[0][2], sd[1][0], sd[1][1], sd[1][2]);
+            }
             if (occ_out && lane == 0) occ_out[(size_t)b * ((nslices + 31u) >> 5) + (s0 >> 5)] = bal;
         }
     }
@@ -510,30 +530,31 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
 // symbols; with levels == 0 the single root is itself a byte-level node); [sa,se): the slice's symbol
 // interval; bm (zeroed by the caller) receives bit (symbol - shift - t0); counts_row (nullable) is
 // indexed by token.
-__device__ __forceinline__ void fm_enum_slice(const FmDev &ix, const uint2 *__restrict__ top_b, uint32_t LT, uint32_t sa,
-                                              uint32_t se, int64_t shift, uint32_t t0, EnumSmem &S,
-                                              uint32_t *__restrict__ counts_row) {
+__device__ __forceinline__ void fm_seed_from_table(const FmDev &ix, const uint2 *__restrict__ top_b, uint32_t LT, uint32_t sa,
+                                                   uint32_t se, EnumSmem &S) {  // thread 0 only
+    const uint32_t span_bits = 8u + 4u * (ix.levels - LT);
+    uint32_t n = 0, W = 0;
+    if (sa < se)
+        for (uint32_t p = sa >> span_bits; p <= (se - 1u) >> span_bits && n < 4; ++p) {
+            const uint2 nd = top_b[p];
+            if (nd.y > nd.x) {
+                S.seed[n][0] = nd.x;
+                S.seed[n][1] = nd.y;
+                S.seed[n][2] = p;
+                ++n;
+                W += nd.y - nd.x;
+            }
+        }
+    S.n_seed = n;
+    S.n_bnode = 0;
+    S.width = W;
+}
+
+// walk from the seeds already placed in S (S.seed / n_seed / width / n_bnode = 0, made visible by a barrier)
+__device__ __forceinline__ void fm_enum_seeded(const FmDev &ix, uint32_t LT, uint32_t sa, uint32_t se, int64_t shift,
+                                               uint32_t t0, EnumSmem &S, uint32_t *__restrict__ counts_row) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t L = ix.levels;
-    const uint32_t span_bits = 8u + 4u * (L - LT);
-    if (tid == 0) {
-        uint32_t n = 0, W = 0;
-        if (sa < se)
-            for (uint32_t p = sa >> span_bits; p <= (se - 1u) >> span_bits && n < 4; ++p) {
-                const uint2 nd = top_b[p];
-                if (nd.y > nd.x) {
-                    S.seed[n][0] = nd.x;
-                    S.seed[n][1] = nd.y;
-                    S.seed[n][2] = p;
-                    ++n;
-                    W += nd.y - nd.x;
-                }
-            }
-        S.n_seed = n;
-        S.n_bnode = 0;
-        S.width = W;
-    }
-    __syncthreads();
     const uint32_t n_seed = S.n_seed, W = S.width;
     if (n_seed == 0) return;
     if (W <= 32u) {
@@ -622,6 +643,14 @@ __device__ __forceinline__ void fm_enum_slice(const FmDev &ix, const uint2 *__re
     __syncthreads();
 }
 
+__device__ __forceinline__ void fm_enum_slice(const FmDev &ix, const uint2 *__restrict__ top_b, uint32_t LT, uint32_t sa,
+                                              uint32_t se, int64_t shift, uint32_t t0, EnumSmem &S,
+                                              uint32_t *__restrict__ counts_row) {
+    if (threadIdx.x == 0) fm_seed_from_table(ix, top_b, LT, sa, se, S);
+    __syncthreads();
+    fm_enum_seeded(ix, LT, sa, se, shift, t0, S, counts_row);
+}
+
 __device__ __forceinline__ void fm_slice_interval(const FmDev &ix, uint32_t t0, uint32_t t1, int64_t shift, uint32_t &sa,
                                                   uint32_t &se) {
     int64_t a64 = (int64_t)t0 + shift, e64 = (int64_t)t1 + shift;
@@ -633,28 +662,63 @@ __device__ __forceinline__ void fm_slice_interval(const FmDev &ix, uint32_t t0, 
 
 // ---- phase B, bitmap only: persistent CTAs over the work list ------------------------------------------
 __global__ void __launch_bounds__(ITEM_THREADS, 1024 / ITEM_THREADS)
-k_mask_items(FmDev ix, const uint2 *__restrict__ top, uint32_t P_top, uint32_t LT, int64_t shift, uint32_t vocab,
-             const uint32_t *__restrict__ items, const uint32_t *__restrict__ n_items_ptr, uint32_t *__restrict__ next_ptr,
-             uint32_t *__restrict__ mask_out, uint32_t *__restrict__ counts_out) {
+k_mask_items(FmDev ix, uint32_t LT, int64_t shift, uint32_t vocab, const uint4 *__restrict__ items,
+             const uint32_t *__restrict__ n_items_ptr, uint32_t *__restrict__ next_ptr, uint32_t *__restrict__ mask_out,
+             uint32_t *__restrict__ counts_out) {
     __shared__ EnumSmem S;
-    __shared__ uint32_t cur_item;
+    __shared__ uint4 ent[2][2];      // double-buffered item entries (id, seeds)
+    __shared__ uint32_t ent_idx[2];  // their indices in the work list
     const int tid = threadIdx.x;
     const uint32_t n_items = *n_items_ptr;
     const uint32_t nslices = (vocab + SLICE - 1) / SLICE, mask_words = (vocab + 31u) >> 5;
-    for (;;) {
+    // thread 0 keeps the fetch of the NEXT item (claim by atomicAdd + entry load, two dependent global round trips)
+    // in flight while the CTA walks the current one
+    uint32_t idx_next = 0;
+    if (tid == 0) {
+        const uint32_t i0 = atomicAdd(next_ptr, 1u);
+        ent_idx[0] = i0;
+        if (i0 < n_items) {
+            ent[0][0] = items[2 * (size_t)i0];
+            ent[0][1] = items[2 * (size_t)i0 + 1];
+        }
+        idx_next = atomicAdd(next_ptr, 1u);
+    }
+    for (uint32_t k = 0;; ++k) {
+        const int cur = (int)(k & 1u);
         __syncthreads();
-        if (tid == 0) cur_item = atomicAdd(next_ptr, 1u);
+        if (ent_idx[cur] >= n_items) break;
+        uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+        uint32_t idx_after = 0;
+        if (tid == 0) {  // issue now, consume at the end of the iteration
+            if (idx_next < n_items) {
+                n0 = items[2 * (size_t)idx_next];
+                n1 = items[2 * (size_t)idx_next + 1];
+            }
+            idx_after = atomicAdd(next_ptr, 1u);
+        }
+        const uint4 e0 = ent[cur][0], e1 = ent[cur][1];
+        const uint32_t b = e0.x / nslices, t0 = (e0.x % nslices) * SLICE, t1 = min(t0 + (uint32_t)SLICE, vocab);
         for (int w = tid; w < SLICE / 32; w += ITEM_THREADS) S.bm[w] = 0;
-        __syncthreads();
-        const uint32_t it = cur_item;
-        if (it >= n_items) break;
-        const uint32_t v = items[it], b = v / nslices, t0 = (v % nslices) * SLICE, t1 = min(t0 + (uint32_t)SLICE, vocab);
+        if (tid == 0) {
+            S.seed[0][0] = e0.z; S.seed[0][1] = e0.w; S.seed[0][2] = e1.x;
+            S.seed[1][0] = e1.y; S.seed[1][1] = e1.z; S.seed[1][2] = e1.w;
+            S.n_seed = e0.y;
+            S.n_bnode = 0;
+            S.width = (e0.w - e0.z) + (e0.y > 1 ? e1.z - e1.y : 0u);
+        }
         uint32_t sa, se;
         fm_slice_interval(ix, t0, t1, shift, sa, se);
-        fm_enum_slice(ix, top + (size_t)b * P_top, LT, sa, se, shift, t0, S, counts_out ? counts_out + (size_t)b * vocab : nullptr);
+        __syncthreads();
+        fm_enum_seeded(ix, LT, sa, se, shift, t0, S, counts_out ? counts_out + (size_t)b * vocab : nullptr);
         __syncthreads();
         const uint32_t nw = (t1 - t0 + 31u) >> 5;
         for (uint32_t w = tid; w < nw; w += ITEM_THREADS) mask_out[(size_t)b * mask_words + (t0 >> 5) + w] = S.bm[w];
+        if (tid == 0) {
+            ent[cur ^ 1][0] = n0;
+            ent[cur ^ 1][1] = n1;
+            ent_idx[cur ^ 1] = idx_next;
+            idx_next = idx_after;
+        }
     }
 }
 
@@ -1312,12 +1376,12 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
     }
     const uint32_t P_top = fm_nodes_at(ix.max_sym, L, LT);
     const size_t lvl_bytes = n_nodes * sizeof(uint2);
-    const size_t items_bytes = has ? 0 : nblk * 4;
+    const size_t items_bytes = has ? 0 : nblk * 32;  // two uint4 per (range, slice) item: id + seeds
     FmBuf &ws = h->mask_ws_override ? *h->mask_ws_override : h->mask_ws;
-    FM_TRY(fm_scratch(h, ws, lvl_bytes + items_bytes + 64, false));
+    FM_TRY(fm_scratch(h, ws, lvl_bytes + items_bytes + 128, false));
     uint2 *lvl = (uint2 *)ws.p;
-    uint32_t *items = has ? nullptr : (uint32_t *)((char *)ws.p + lvl_bytes);
-    uint32_t *ctr = (uint32_t *)((char *)ws.p + lvl_bytes + items_bytes);  // [0]=count [1]=next
+    uint4 *items = has ? nullptr : (uint4 *)((char *)ws.p + ((lvl_bytes + 15) & ~(size_t)15));
+    uint32_t *ctr = (uint32_t *)((char *)ws.p + ((lvl_bytes + 15) & ~(size_t)15) + items_bytes);  // [0]=count [1]=next
     if (!has) {
         FM_CUDA(cudaMemsetAsync(ctr, 0, 8, s));  // the mask rows themselves are zeroed by k_mask_top
     }
@@ -1326,7 +1390,7 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
               (uint32_t)std::min<size_t>(dense_n, 0xFFFFFFFFu));
     if (!has) {
         const unsigned grid = (unsigned)std::min<size_t>(nblk, (size_t)h->sm_count * 16);
-        FM_LAUNCH(k_mask_items, grid, ITEM_THREADS, 0, s, ix, lvl + top_off, P_top, LT, shift, vocab, items, ctr, ctr + 1,
+        FM_LAUNCH(k_mask_items, grid, ITEM_THREADS, 0, s, ix, LT, shift, vocab, items, ctr, ctr + 1,
                   d_mask, d_counts);
         FM_CUDA(cudaGetLastError());
         return FMIDX_OK;
