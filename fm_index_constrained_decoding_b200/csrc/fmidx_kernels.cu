@@ -202,7 +202,6 @@ __global__ void __launch_bounds__(128) k_step(FmDev ix, const uint64_t *__restri
 // =================================================================================================
 constexpr int SLICE = 4096;        // tokens per CTA
 constexpr int MASK_THREADS = 256;   // logits kernels (one CTA per slice)
-constexpr int ITEM_THREADS = 128;   // k_mask_items (bitmap-only work items): more, smaller CTAs hide the walks better
 constexpr int MAXF = 288;          // BFS frontier capacity: <= SLICE/16 + 2 nodes at the deepest inner level
 
 template <int DT> struct Elem;
@@ -265,7 +264,7 @@ struct EnumSmem {
     uint32_t seed[4][3];            // depth-LT nodes of this slice (<= 2 when a top node spans one slice)
     uint32_t bnode[48][3];          // byte-level nodes (each covers 256 symbols): <= 16 per seed (+ overlap)
     uint32_t n_seed, n_bnode, width;
-    int cnt[MASK_THREADS / 32][256];  // per-warp signed histogram of one byte-level node
+    alignas(16) int cnt[MASK_THREADS / 32][256];  // per-warp histogram / presence flags of one byte-level node (int4 access)
     uint4 stage[MASK_THREADS / 16][16];
 };
 
@@ -274,7 +273,7 @@ __device__ __host__ __forceinline__ uint32_t fm_nodes_at(uint32_t max_sym, uint3
     return (max_sym >> (8u + 4u * (levels - l))) + 1u;
 }
 
-// OR `bits` (nbits <= 16 consecutive symbols starting at base_sym) into the slice bitmap
+// OR `bits` (<= 32 consecutive symbols starting at base_sym; bits of symbols outside the bitmap are zero) into the bitmap
 __device__ __forceinline__ void fm_or_bits(uint32_t *bm, uint32_t bits, uint32_t base_sym, int64_t shift, uint32_t t0) {
     const int64_t r = (int64_t)base_sym - shift - (int64_t)t0;  // bit position of the first symbol
     if (r >= 0) {
@@ -295,15 +294,72 @@ __device__ __forceinline__ void fm_eval_byte_node(const FmDev &ix, uint32_t lo, 
                                                   uint32_t se, int64_t shift, uint32_t t0, uint32_t *bm, int *cnt,
                                                   uint32_t *__restrict__ counts_row, int lane) {
     const uint32_t base_sym = prefix << 8;
-    const uint32_t w = hi - lo;
-    if (w <= 128u && !counts_row) {
-        for (uint32_t t = (uint32_t)lane; t < w; t += 32) {
-            const uint32_t sy = base_sym | fm_byte_at(ix.bcells, lo + t);
-            if (sy >= sa && sy < se) {
-                const uint32_t rel = (uint32_t)((int64_t)sy - shift) - t0;
-                atomicOr(&bm[rel >> 5], 1u << (rel & 31u));
+    if (!counts_row) {
+        // Presence only (the mask path): symbol v occurs in [lo,hi) iff it occurs in the part of cell A at or after
+        // lo, in the part of cell B before hi, or in a whole cell between them (header difference hdr[B] - hdr[A+1]
+        // > 0, read only when such cells exist).  The partial cells are scanned with PLAIN shared-memory stores of 1
+        // (same-address stores of a warp merge; no atomics), so skewed byte distributions cost nothing extra.
+        const uint32_t cA = lo >> 9, a = lo & 511u, cB = hi >> 9, b = hi & 511u;
+        const bool same = cA == cB, far = cB > cA + 1u;
+        const uint4 *cellA = ix.bcells + (size_t)cA * FMIDX_BCELL_U4, *cellB = ix.bcells + (size_t)cB * FMIDX_BCELL_U4;
+        const uint32_t ta = same ? b : 512u, tb = same ? 0u : b;  // scans A[a,ta) and B[0,tb)
+        const uint32_t *pwa = reinterpret_cast<const uint32_t *>(cellA + FMIDX_BHDR_U4);
+        const uint32_t *pwb = reinterpret_cast<const uint32_t *>(cellB + FMIDX_BHDR_U4);
+        uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0, b0 = a0, b1 = a0;
+        if (far) {
+            a0 = fm_ldg(cellA + FMIDX_BCELL_U4 + 2 * lane);
+            a1 = fm_ldg(cellA + FMIDX_BCELL_U4 + 2 * lane + 1);
+            b0 = fm_ldg(cellB + 2 * lane);
+            b1 = fm_ldg(cellB + 2 * lane + 1);
+        }
+        uint32_t wa[4], wb[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t wi = (a >> 2) + (uint32_t)lane + 32u * k;
+            wa[k] = wi < ((ta + 3u) >> 2) ? __ldg(pwa + wi) : 0u;
+            const uint32_t wj = (uint32_t)lane + 32u * k;
+            wb[k] = wj < ((tb + 3u) >> 2) ? __ldg(pwb + wj) : 0u;
+        }
+        {
+            int4 *c = reinterpret_cast<int4 *>(cnt + lane * 8);
+            c[0] = make_int4((int)(b0.x - a0.x), (int)(b0.y - a0.y), (int)(b0.z - a0.z), (int)(b0.w - a0.w));
+            c[1] = make_int4((int)(b1.x - a1.x), (int)(b1.y - a1.y), (int)(b1.z - a1.z), (int)(b1.w - a1.w));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t wi = (a >> 2) + (uint32_t)lane + 32u * k;
+            if (wi < ((ta + 3u) >> 2)) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t p = wi * 4u + (uint32_t)e;
+                    if (p >= a && p < ta) cnt[(wa[k] >> (8 * e)) & 255u] = 1;
+                }
+            }
+            const uint32_t wj = (uint32_t)lane + 32u * k;
+            if (wj < ((tb + 3u) >> 2)) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t p = wj * 4u + (uint32_t)e;
+                    if (p < tb) cnt[(wb[k] >> (8 * e)) & 255u] = 1;
+                }
             }
         }
+        __syncwarp();
+        const int4 c0 = reinterpret_cast<const int4 *>(cnt + lane * 8)[0], c1 = reinterpret_cast<const int4 *>(cnt + lane * 8)[1];
+        const int cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        uint32_t bits = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t sy = base_sym | (uint32_t)(lane * 8 + k);
+            if (cc[k] > 0 && sy >= sa && sy < se) bits |= 1u << k;
+        }
+        // four lanes assemble one 32-symbol word: at most 2 OR operations per 32 symbols reach the bitmap
+        uint32_t v = bits << (8 * (lane & 3));
+        v |= __shfl_xor_sync(FULL, v, 1);
+        v |= __shfl_xor_sync(FULL, v, 2);
+        if ((lane & 3) == 0 && v) fm_or_bits(bm, v, base_sym + (uint32_t)(lane >> 2) * 32u, shift, t0);
+        __syncwarp();
         return;
     }
     const uint32_t cA = lo >> 9, a = lo & 511u, cB = hi >> 9, b = hi & 511u;
@@ -489,38 +545,56 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
         base += (size_t)B * P_next;
     }
     if (work_items) {
+        // bitmap-only mode: one work item per non-empty depth-LT node (b, node, lo, hi) that intersects the token
+        // window; k_mask_expand / k_mask_bytes finish the walk with warps that never synchronise with each other
         const uint32_t nslices = (vocab + SLICE - 1) / SLICE;
         const uint32_t span_bits = 8u + 4u * (L - LT);
-        for (uint32_t s0 = 0; s0 < nslices; s0 += 32) {
-            const uint32_t s = s0 + lane;
+        const int64_t ga = shift > 0 ? shift : 0;
+        const int64_t ge = min((int64_t)vocab + shift, (int64_t)ix.max_sym + 1);
+        for (uint32_t p0 = 0; p0 < P_cur; p0 += 32) {
+            const uint32_t p = p0 + (uint32_t)lane;
+            uint2 nd = make_uint2(0u, 0u);
             bool ne = false;
-            uint32_t nseed = 0, sd[2][3] = {{0, 0, 0}, {0, 0, 0}};
-            if (s < nslices) {
-                int64_t a64 = (int64_t)s * SLICE + shift, e64 = (int64_t)min((s + 1) * (uint32_t)SLICE, vocab) + shift;
-                if (a64 < 0) a64 = 0;
-                if (e64 > (int64_t)ix.max_sym + 1) e64 = (int64_t)ix.max_sym + 1;
-                if (a64 < e64)
-                    for (uint32_t p = (uint32_t)a64 >> span_bits; p <= ((uint32_t)e64 - 1u) >> span_bits; ++p) {
-                        const uint2 nd = cur[p];
-                        if (nd.y > nd.x && nseed < 2) {  // a 4096-token slice overlaps at most two depth-LT nodes
-                            sd[nseed][0] = nd.x;
-                            sd[nseed][1] = nd.y;
-                            sd[nseed][2] = p;
-                            ++nseed;
-                        }
-                    }
-                ne = nseed > 0;
+            if (p < P_cur) {
+                nd = cur[p];
+                const int64_t na = (int64_t)p << span_bits;
+                ne = nd.y > nd.x && na < ge && na + ((int64_t)1 << span_bits) > ga;
             }
             const uint32_t bal = __ballot_sync(FULL, ne);
             uint32_t slot = 0;
             if (lane == 0 && bal) slot = atomicAdd(work_count, (uint32_t)__popc(bal));
             slot = __shfl_sync(FULL, slot, 0);
-            if (ne) {  // the item carries its seeds: the consumer needs no further lookup
-                uint4 *e = work_items + 2 * (size_t)(slot + __popc(bal & ((1u << lane) - 1u)));
-                e[0] = make_uint4(b * nslices + s, nseed, sd[0][0], sd[0][1]);
-                e[1] = make_uint4(sd[0][2], sd[1][0], sd[1][1], sd[1][2]);
+            if (ne) work_items[slot + __popc(bal & ((1u << lane) - 1u))] = make_uint4(b, p, nd.x, nd.y);
+        }
+        if (occ_out || !(b - dense_lo < dense_n)) {
+            // slice occupancy (bit s: slice s may receive bits) and, for sparse rows, zeroing of exactly those slices
+            const uint32_t mw = (vocab + 31u) >> 5;
+            uint32_t *row = mask_out + (size_t)b * mw;
+            for (uint32_t s0 = 0; s0 < nslices; s0 += 32) {
+                const uint32_t s = s0 + lane;
+                bool ne = false;
+                if (s < nslices) {
+                    int64_t a64 = (int64_t)s * SLICE + shift, e64 = (int64_t)min((s + 1) * (uint32_t)SLICE, vocab) + shift;
+                    if (a64 < 0) a64 = 0;
+                    if (e64 > (int64_t)ix.max_sym + 1) e64 = (int64_t)ix.max_sym + 1;
+                    if (a64 < e64)
+                        for (uint32_t p = (uint32_t)a64 >> span_bits; p <= ((uint32_t)e64 - 1u) >> span_bits; ++p) {
+                            const uint2 nd = cur[p];
+                            ne |= nd.y > nd.x;
+                        }
+                }
+                const uint32_t bal = __ballot_sync(FULL, ne);
+                if (occ_out && lane == 0) occ_out[(size_t)b * ((nslices + 31u) >> 5) + (s0 >> 5)] = bal;
+                if (!(b - dense_lo < dense_n)) {
+                    uint32_t todo = bal;
+                    while (todo) {
+                        const uint32_t s_cur = s0 + (uint32_t)__ffs(todo) - 1u;
+                        const uint32_t w0 = s_cur * (SLICE / 32), w1 = min(w0 + SLICE / 32, mw);
+                        for (uint32_t i = w0 + (uint32_t)lane; i < w1; i += 32) row[i] = 0u;
+                        todo &= todo - 1u;
+                    }
+                }
             }
-            if (occ_out && lane == 0) occ_out[(size_t)b * ((nslices + 31u) >> 5) + (s0 >> 5)] = bal;
         }
     }
 }
@@ -660,65 +734,102 @@ __device__ __forceinline__ void fm_slice_interval(const FmDev &ix, uint32_t t0, 
     se = e64 > a64 ? (uint32_t)e64 : (uint32_t)a64;
 }
 
-// ---- phase B, bitmap only: persistent CTAs over the work list ------------------------------------------
-__global__ void __launch_bounds__(ITEM_THREADS, 1024 / ITEM_THREADS)
-k_mask_items(FmDev ix, uint32_t LT, int64_t shift, uint32_t vocab, const uint4 *__restrict__ items,
-             const uint32_t *__restrict__ n_items_ptr, uint32_t *__restrict__ next_ptr, uint32_t *__restrict__ mask_out,
-             uint32_t *__restrict__ counts_out) {
-    __shared__ EnumSmem S;
-    __shared__ uint4 ent[2][2];      // double-buffered item entries (id, seeds)
-    __shared__ uint32_t ent_idx[2];  // their indices in the work list
-    const int tid = threadIdx.x;
+// ---- phase B, bitmap only ---------------------------------------------------------------------------------
+// k_mask_expand: one half-warp per depth-LT work item (LT = levels-1): a node of <= 16 rows is resolved by direct
+// access (one lane per row); otherwise lane d ranks child d at the last nibble level and the non-empty children
+// -- byte-level nodes (b, prefix, lo, hi) -- are appended to a second list.  If that list is full the warp
+// evaluates the child itself (slow, correct).
+constexpr int EXPAND_THREADS = 128;
+constexpr int BYTES_THREADS = 256;
+
+__global__ void __launch_bounds__(EXPAND_THREADS)
+k_mask_expand(FmDev ix, uint32_t LT, int64_t shift, uint32_t vocab, const uint4 *__restrict__ items,
+              const uint32_t *__restrict__ n_items_ptr, uint4 *__restrict__ bnodes, uint32_t *__restrict__ n_bnodes,
+              uint32_t cap, uint32_t *__restrict__ mask_out, uint32_t *__restrict__ counts_out) {
+    __shared__ uint4 stage[EXPAND_THREADS / 16][16];
+    __shared__ __align__(16) int cnt[EXPAND_THREADS / 32][256];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, hw = (tid >> 4) & 1, hl = tid & 15, hslot = tid >> 4;
     const uint32_t n_items = *n_items_ptr;
-    const uint32_t nslices = (vocab + SLICE - 1) / SLICE, mask_words = (vocab + 31u) >> 5;
-    // thread 0 keeps the fetch of the NEXT item (claim by atomicAdd + entry load, two dependent global round trips)
-    // in flight while the CTA walks the current one
-    uint32_t idx_next = 0;
-    if (tid == 0) {
-        const uint32_t i0 = atomicAdd(next_ptr, 1u);
-        ent_idx[0] = i0;
-        if (i0 < n_items) {
-            ent[0][0] = items[2 * (size_t)i0];
-            ent[0][1] = items[2 * (size_t)i0 + 1];
-        }
-        idx_next = atomicAdd(next_ptr, 1u);
-    }
-    for (uint32_t k = 0;; ++k) {
-        const int cur = (int)(k & 1u);
-        __syncthreads();
-        if (ent_idx[cur] >= n_items) break;
-        uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
-        uint32_t idx_after = 0;
-        if (tid == 0) {  // issue now, consume at the end of the iteration
-            if (idx_next < n_items) {
-                n0 = items[2 * (size_t)idx_next];
-                n1 = items[2 * (size_t)idx_next + 1];
+    const uint32_t mask_words = (vocab + 31u) >> 5;
+    const uint32_t ga = (uint32_t)(shift > 0 ? shift : 0);
+    const int64_t ge64 = min((int64_t)vocab + shift, (int64_t)ix.max_sym + 1);
+    const uint32_t ge = ge64 > (int64_t)ga ? (uint32_t)ge64 : ga;
+    const uint32_t x0 = (hl & 1) ? 0u : ~0u, x1 = (hl & 2) ? 0u : ~0u, x2 = (hl & 4) ? 0u : ~0u, x3 = (hl & 8) ? 0u : ~0u;
+    const uint4 *lc = ix.cells + (size_t)LT * ix.level_stride;
+    const uint32_t gwarp = (blockIdx.x * EXPAND_THREADS + tid) >> 5, nwarps = (gridDim.x * EXPAND_THREADS) >> 5;
+    for (uint32_t base = gwarp * 2u; base < n_items; base += nwarps * 2u) {
+        const uint32_t i = base + (uint32_t)hw;
+        const bool has = i < n_items;
+        const uint4 it = has ? __ldg(items + i) : make_uint4(0u, 0u, 0u, 0u);
+        const uint32_t b = it.x, prefix = it.y, lo = it.z, hi = it.w;
+        const bool narrow = has && hi - lo <= 16u;
+        if (__any_sync(FULL, narrow)) {
+            const bool valid = narrow && (uint32_t)hl < hi - lo;
+            uint32_t c = prefix;
+            if (valid) {
+                uint32_t dig;
+                const uint32_t pos = fm_access1(lc, lo + (uint32_t)hl, dig);
+                c = (((c << 4) | dig) << 8) | fm_byte_at(ix.bcells, pos);
             }
-            idx_after = atomicAdd(next_ptr, 1u);
+            const bool inside = valid && c >= ga && c < ge;
+            const uint32_t tk = (uint32_t)((int64_t)c - shift);
+            if (inside) atomicOr(&mask_out[(size_t)b * mask_words + (tk >> 5)], 1u << (tk & 31u));
+            if (counts_out) {
+                const unsigned long long key = inside ? (((unsigned long long)hw << 32) | c) : ((1ull << 40) | (unsigned)lane);
+                const uint32_t same = __match_any_sync(FULL, key);
+                if (inside) counts_out[(size_t)b * vocab + tk] = (uint32_t)__popc(same);
+            }
         }
-        const uint4 e0 = ent[cur][0], e1 = ent[cur][1];
-        const uint32_t b = e0.x / nslices, t0 = (e0.x % nslices) * SLICE, t1 = min(t0 + (uint32_t)SLICE, vocab);
-        for (int w = tid; w < SLICE / 32; w += ITEM_THREADS) S.bm[w] = 0;
-        if (tid == 0) {
-            S.seed[0][0] = e0.z; S.seed[0][1] = e0.w; S.seed[0][2] = e1.x;
-            S.seed[1][0] = e1.y; S.seed[1][1] = e1.z; S.seed[1][2] = e1.w;
-            S.n_seed = e0.y;
-            S.n_bnode = 0;
-            S.width = (e0.w - e0.z) + (e0.y > 1 ? e1.z - e1.y : 0u);
+        const bool wide = has && !narrow;
+        if (wide) stage[hslot][hl] = fm_ldg(lc + (size_t)((hl < 8 ? lo : hi) >> 7) * FMIDX_CELL_U4 + (hl & 7));
+        __syncwarp();
+        uint32_t r_lo = 0, r_hi = 0;
+        if (wide) {
+            r_lo = fm_rank_fast(&stage[hslot][0], (uint32_t)hl, lo & 127u, x0, x1, x2, x3);
+            r_hi = fm_rank_fast(&stage[hslot][8], (uint32_t)hl, hi & 127u, x0, x1, x2, x3);
         }
-        uint32_t sa, se;
-        fm_slice_interval(ix, t0, t1, shift, sa, se);
-        __syncthreads();
-        fm_enum_seeded(ix, LT, sa, se, shift, t0, S, counts_out ? counts_out + (size_t)b * vocab : nullptr);
-        __syncthreads();
-        const uint32_t nw = (t1 - t0 + 31u) >> 5;
-        for (uint32_t w = tid; w < nw; w += ITEM_THREADS) mask_out[(size_t)b * mask_words + (t0 >> 5) + w] = S.bm[w];
-        if (tid == 0) {
-            ent[cur ^ 1][0] = n0;
-            ent[cur ^ 1][1] = n1;
-            ent_idx[cur ^ 1] = idx_next;
-            idx_next = idx_after;
+        __syncwarp();
+        const uint32_t cp = (prefix << 4) | (uint32_t)hl;
+        const uint64_t c_lo = (uint64_t)cp << 8, c_hi = ((uint64_t)cp + 1) << 8;
+        const bool exists = wide && r_hi > r_lo && c_lo < ge && c_hi > ga;
+        const uint32_t bal = __ballot_sync(FULL, exists);
+        uint32_t slot = 0;
+        if (lane == 0 && bal) slot = atomicAdd(n_bnodes, (uint32_t)__popc(bal));
+        slot = __shfl_sync(FULL, slot, 0);
+        const uint32_t idx = slot + __popc(bal & ((1u << lane) - 1u));
+        if (exists && idx < cap) bnodes[idx] = make_uint4(b, cp, r_lo, r_hi);
+        uint32_t ovf = __ballot_sync(FULL, exists && idx >= cap);
+        while (ovf) {  // list full: evaluate the child here
+            const int src = __ffs(ovf) - 1;
+            const uint32_t ob = __shfl_sync(FULL, b, src), ocp = __shfl_sync(FULL, cp, src);
+            const uint32_t olo = __shfl_sync(FULL, r_lo, src), ohi = __shfl_sync(FULL, r_hi, src);
+            fm_eval_byte_node(ix, olo, ohi, ocp, ga, ge, shift, 0u, mask_out + (size_t)ob * mask_words, cnt[wid],
+                              counts_out ? counts_out + (size_t)ob * vocab : nullptr, lane);
+            ovf &= ovf - 1u;
         }
+    }
+}
+
+// k_mask_bytes: one warp per byte-level node, bits ORed straight into the (pre-zeroed) mask row in global memory.
+// Warps are fully independent: no block-level barrier anywhere, the next node's entry is fetched ahead.
+template <int MINB>
+__global__ void __launch_bounds__(BYTES_THREADS, MINB)
+k_mask_bytes(FmDev ix, int64_t shift, uint32_t vocab, const uint4 *__restrict__ bnodes, const uint32_t *__restrict__ n_ptr,
+             uint32_t cap, uint32_t *__restrict__ mask_out, uint32_t *__restrict__ counts_out) {
+    __shared__ __align__(16) int cnt[BYTES_THREADS / 32][256];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t n = min(*n_ptr, cap);
+    const uint32_t mask_words = (vocab + 31u) >> 5;
+    const uint32_t ga = (uint32_t)(shift > 0 ? shift : 0);
+    const int64_t ge64 = min((int64_t)vocab + shift, (int64_t)ix.max_sym + 1);
+    const uint32_t ge = ge64 > (int64_t)ga ? (uint32_t)ge64 : ga;
+    const uint32_t gwarp = (blockIdx.x * BYTES_THREADS + tid) >> 5, nwarps = (gridDim.x * BYTES_THREADS) >> 5;
+    uint4 it = gwarp < n ? __ldg(bnodes + gwarp) : make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t i = gwarp; i < n; i += nwarps) {
+        const uint4 nx = i + nwarps < n ? __ldg(bnodes + i + nwarps) : make_uint4(0u, 0u, 0u, 0u);
+        fm_eval_byte_node(ix, it.z, it.w, it.y, ga, ge, shift, 0u, mask_out + (size_t)it.x * mask_words, cnt[wid],
+                          counts_out ? counts_out + (size_t)it.x * vocab : nullptr, lane);
+        it = nx;
     }
 }
 
@@ -1376,12 +1487,24 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
     }
     const uint32_t P_top = fm_nodes_at(ix.max_sym, L, LT);
     const size_t lvl_bytes = n_nodes * sizeof(uint2);
-    const size_t items_bytes = has ? 0 : nblk * 32;  // two uint4 per (range, slice) item: id + seeds
+    // work lists (bitmap mode): depth-LT items (<= P_top per range) and byte-level nodes (<= P_leaf per range, capped:
+    // k_mask_expand evaluates the overflow itself); FMIDX_BNODE_CAP overrides the cap (tests)
+    const uint32_t P_leaf = fm_nodes_at(ix.max_sym, L, L);
+    static const size_t cap_max = [] {
+        const char *e = getenv("FMIDX_BNODE_CAP");
+        return e && *e ? (size_t)strtoull(e, nullptr, 10) : ((size_t)1 << 22);
+    }();
+    if ((size_t)B * P_top > 0x7FFFFFFFull) { fm_set_error("mask batch too large: split the call"); return FMIDX_EINVAL; }
+    const size_t cap = std::min<size_t>((size_t)B * P_leaf, cap_max);
+    const size_t items_bytes = has ? 0 : (size_t)B * P_top * 16;
+    const size_t bnode_bytes = has || L == 0 ? 0 : cap * 16;
     FmBuf &ws = h->mask_ws_override ? *h->mask_ws_override : h->mask_ws;
-    FM_TRY(fm_scratch(h, ws, lvl_bytes + items_bytes + 128, false));
+    FM_TRY(fm_scratch(h, ws, lvl_bytes + items_bytes + bnode_bytes + 128, false));
     uint2 *lvl = (uint2 *)ws.p;
-    uint4 *items = has ? nullptr : (uint4 *)((char *)ws.p + ((lvl_bytes + 15) & ~(size_t)15));
-    uint32_t *ctr = (uint32_t *)((char *)ws.p + ((lvl_bytes + 15) & ~(size_t)15) + items_bytes);  // [0]=count [1]=next
+    const size_t items_off = (lvl_bytes + 15) & ~(size_t)15;
+    uint4 *items = has ? nullptr : (uint4 *)((char *)ws.p + items_off);
+    uint4 *bnodes = (uint4 *)((char *)ws.p + items_off + items_bytes);
+    uint32_t *ctr = (uint32_t *)((char *)ws.p + items_off + items_bytes + bnode_bytes);  // [0]=#items [1]=#byte nodes / next
     if (!has) {
         FM_CUDA(cudaMemsetAsync(ctr, 0, 8, s));  // the mask rows themselves are zeroed by k_mask_top
     }
@@ -1389,9 +1512,27 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
               vocab, items, ctr, has ? nullptr : d_mask, has ? nullptr : d_counts, has ? nullptr : d_occ, (uint32_t)dense_lo,
               (uint32_t)std::min<size_t>(dense_n, 0xFFFFFFFFu));
     if (!has) {
-        const unsigned grid = (unsigned)std::min<size_t>(nblk, (size_t)h->sm_count * 16);
-        FM_LAUNCH(k_mask_items, grid, ITEM_THREADS, 0, s, ix, LT, shift, vocab, items, ctr, ctr + 1,
-                  d_mask, d_counts);
+        static const int occ = [] {
+            const char *e = getenv("FMIDX_BYTES_OCC");
+            return e && *e ? atoi(e) : 6;
+        }();
+        const unsigned bgrid = (unsigned)h->sm_count * occ;
+#define FM_BYTES(LIST, CNT, CAP)                                                                                            \
+    do {                                                                                                                    \
+        if (occ == 4) FM_LAUNCH(k_mask_bytes<4>, bgrid, BYTES_THREADS, 0, s, ix, shift, vocab, LIST, CNT, CAP, d_mask, d_counts); \
+        else if (occ == 5) FM_LAUNCH(k_mask_bytes<5>, bgrid, BYTES_THREADS, 0, s, ix, shift, vocab, LIST, CNT, CAP, d_mask, d_counts); \
+        else if (occ == 8) FM_LAUNCH(k_mask_bytes<8>, bgrid, BYTES_THREADS, 0, s, ix, shift, vocab, LIST, CNT, CAP, d_mask, d_counts); \
+        else FM_LAUNCH(k_mask_bytes<6>, bgrid, BYTES_THREADS, 0, s, ix, shift, vocab, LIST, CNT, CAP, d_mask, d_counts); \
+    } while (0)
+        if (L == 0) {  // the root is itself a byte-level node: the item list is the node list
+            FM_BYTES(items, ctr, (uint32_t)(B * P_top));
+        } else {
+            const unsigned egrid = (unsigned)std::min<size_t>(((size_t)B * P_top + 7) / 8, (size_t)h->sm_count * 16);
+            FM_LAUNCH(k_mask_expand, egrid, EXPAND_THREADS, 0, s, ix, LT, shift, vocab, items, ctr, bnodes, ctr + 1, (uint32_t)cap,
+                      d_mask, d_counts);
+            FM_BYTES(bnodes, ctr + 1, (uint32_t)cap);
+        }
+#undef FM_BYTES
         FM_CUDA(cudaGetLastError());
         return FMIDX_OK;
     }

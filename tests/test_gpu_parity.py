@@ -442,3 +442,42 @@ def test_pipelined_host_api(cuda):
         assert (outs[s][0] == osp).all() and (outs[s][1] == oep).all() and (outs[s][2] == ond.astype(np.uint32)).all()
     with pytest.raises(_native.FmidxError):
         _native.check(L.fmidx_query_wait(ix._h, 7))
+
+
+_OVERFLOW_SCRIPT = r"""
+import random, sys
+import numpy as np, torch
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(tests)r)
+from test_gpu_parity import make, oracle, random_docs
+from fm_index_constrained_decoding_b200.index import ragged
+rng = random.Random(77)
+V = 128256
+docs = random_docs(rng, V, 300, 20, 400)
+ix, o = make(docs), oracle(docs)
+seqs = [[]] + [[rng.choice(rng.choice(docs))] for _ in range(40)] + [[]] * 3
+toks, offs = ragged(seqs)
+sp_o, ep_o, m_o, _ = o.query_batch(toks, offs, want_mask=True, vocab=V, nthreads=2)
+sp, ep = ix.get_range_batch(torch.from_numpy(toks).cuda(), torch.from_numpy(offs).cuda())
+mask, counts = ix.distinct_mask_batch(sp, ep, V, want_counts=True)
+assert (mask.cpu().numpy().view(np.uint32) == m_o).all()
+mask2 = ix.distinct_mask_batch(sp, ep, V)
+assert (mask2.cpu().numpy().view(np.uint32) == m_o).all()
+exp = o.get_distinct_count_multi(sp_o[:8].tolist(), ep_o[:8].tolist())
+cn = counts.cpu().numpy()
+for k in range(8):
+    for t, c in zip(*exp[k]):
+        assert cn[k, t] == c
+print("OVERFLOW-OK")
+"""
+
+
+def test_mask_byte_node_list_overflow(cuda):
+    """k_mask_expand evaluates byte-level nodes itself once the node list is full: force that path with a
+    7-entry list (FMIDX_BNODE_CAP is read once per process, hence the subprocess)."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, FMIDX_BNODE_CAP="7")
+    r = subprocess.run([sys.executable, "-c", _OVERFLOW_SCRIPT % {"root": os.path.dirname(here), "tests": here}],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "OVERFLOW-OK" in r.stdout, r.stdout + r.stderr
