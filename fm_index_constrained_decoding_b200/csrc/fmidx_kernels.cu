@@ -286,6 +286,62 @@ __device__ __forceinline__ void fm_or_bits(uint32_t *bm, uint32_t bits, uint32_t
     }
 }
 
+// Presence flags of a byte-level node wider than 512 rows: symbol v occurs in [lo,hi) iff it occurs in the part of
+// cell A at or after lo, in the part of cell B before hi, or in a whole cell between them (header difference
+// hdr[B] - hdr[A+1] > 0, read only when such cells exist).  Returns the lane's 8 flags (symbols 8*lane..8*lane+7).
+__device__ __forceinline__ uint32_t fm_byte_node_presence_wide(const FmDev &ix, uint32_t lo, uint32_t hi, int *cnt, int lane) {
+    const uint32_t cA = lo >> 9, a = lo & 511u, cB = hi >> 9, b = hi & 511u;
+    const bool same = cA == cB, far = cB > cA + 1u;
+    const uint4 *cellA = ix.bcells + (size_t)cA * FMIDX_BCELL_U4, *cellB = ix.bcells + (size_t)cB * FMIDX_BCELL_U4;
+    const uint32_t ta = same ? b : 512u, tb = same ? 0u : b;  // scans A[a,ta) and B[0,tb)
+    const uint32_t *pwa = reinterpret_cast<const uint32_t *>(cellA + FMIDX_BHDR_U4);
+    const uint32_t *pwb = reinterpret_cast<const uint32_t *>(cellB + FMIDX_BHDR_U4);
+    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0, b0 = a0, b1 = a0;
+    if (far) {
+        a0 = fm_ldg(cellA + FMIDX_BCELL_U4 + 2 * lane);
+        a1 = fm_ldg(cellA + FMIDX_BCELL_U4 + 2 * lane + 1);
+        b0 = fm_ldg(cellB + 2 * lane);
+        b1 = fm_ldg(cellB + 2 * lane + 1);
+    }
+    uint32_t wa[4], wb[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t wi = (a >> 2) + (uint32_t)lane + 32u * k;
+        wa[k] = wi < ((ta + 3u) >> 2) ? __ldg(pwa + wi) : 0u;
+        const uint32_t wj = (uint32_t)lane + 32u * k;
+        wb[k] = wj < ((tb + 3u) >> 2) ? __ldg(pwb + wj) : 0u;
+    }
+    {
+        int4 *c = reinterpret_cast<int4 *>(cnt + lane * 8);
+        c[0] = make_int4((int)(b0.x - a0.x), (int)(b0.y - a0.y), (int)(b0.z - a0.z), (int)(b0.w - a0.w));
+        c[1] = make_int4((int)(b1.x - a1.x), (int)(b1.y - a1.y), (int)(b1.z - a1.z), (int)(b1.w - a1.w));
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t wi = (a >> 2) + (uint32_t)lane + 32u * k;
+        if (wi < ((ta + 3u) >> 2)) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t p = wi * 4u + (uint32_t)e;
+                if (p >= a && p < ta) cnt[(wa[k] >> (8 * e)) & 255u] = 1;
+            }
+        }
+        const uint32_t wj = (uint32_t)lane + 32u * k;
+        if (wj < ((tb + 3u) >> 2)) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t p = wj * 4u + (uint32_t)e;
+                if (p < tb) cnt[(wb[k] >> (8 * e)) & 255u] = 1;
+            }
+        }
+    }
+    __syncwarp();
+    const int4 c0 = reinterpret_cast<const int4 *>(cnt + lane * 8)[0], c1 = reinterpret_cast<const int4 *>(cnt + lane * 8)[1];
+    return (c0.x > 0 ? 1u : 0u) | (c0.y > 0 ? 2u : 0u) | (c0.z > 0 ? 4u : 0u) | (c0.w > 0 ? 8u : 0u) | (c1.x > 0 ? 16u : 0u) |
+           (c1.y > 0 ? 32u : 0u) | (c1.z > 0 ? 64u : 0u) | (c1.w > 0 ? 128u : 0u);
+}
+
 // Distinct symbols of one byte-level node (positions [lo,hi) of the last level, all sharing `prefix`),
 // by one warp: narrow nodes read their bytes directly; otherwise a 256-bin signed histogram
 //   cnt[v] = hdrB[v] - hdrA[v] - #v in A[0,a) + #v in B[0,b)        (cells A, B of lo and hi)
@@ -295,65 +351,50 @@ __device__ __forceinline__ void fm_eval_byte_node(const FmDev &ix, uint32_t lo, 
                                                   uint32_t *__restrict__ counts_row, int lane) {
     const uint32_t base_sym = prefix << 8;
     if (!counts_row) {
-        // Presence only (the mask path): symbol v occurs in [lo,hi) iff it occurs in the part of cell A at or after
-        // lo, in the part of cell B before hi, or in a whole cell between them (header difference hdr[B] - hdr[A+1]
-        // > 0, read only when such cells exist).  The partial cells are scanned with PLAIN shared-memory stores of 1
-        // (same-address stores of a warp merge; no atomics), so skewed byte distributions cost nothing extra.
-        const uint32_t cA = lo >> 9, a = lo & 511u, cB = hi >> 9, b = hi & 511u;
-        const bool same = cA == cB, far = cB > cA + 1u;
-        const uint4 *cellA = ix.bcells + (size_t)cA * FMIDX_BCELL_U4, *cellB = ix.bcells + (size_t)cB * FMIDX_BCELL_U4;
-        const uint32_t ta = same ? b : 512u, tb = same ? 0u : b;  // scans A[a,ta) and B[0,tb)
-        const uint32_t *pwa = reinterpret_cast<const uint32_t *>(cellA + FMIDX_BHDR_U4);
-        const uint32_t *pwb = reinterpret_cast<const uint32_t *>(cellB + FMIDX_BHDR_U4);
-        uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0, b0 = a0, b1 = a0;
-        if (far) {
-            a0 = fm_ldg(cellA + FMIDX_BCELL_U4 + 2 * lane);
-            a1 = fm_ldg(cellA + FMIDX_BCELL_U4 + 2 * lane + 1);
-            b0 = fm_ldg(cellB + 2 * lane);
-            b1 = fm_ldg(cellB + 2 * lane + 1);
-        }
-        uint32_t wa[4], wb[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t wi = (a >> 2) + (uint32_t)lane + 32u * k;
-            wa[k] = wi < ((ta + 3u) >> 2) ? __ldg(pwa + wi) : 0u;
-            const uint32_t wj = (uint32_t)lane + 32u * k;
-            wb[k] = wj < ((tb + 3u) >> 2) ? __ldg(pwb + wj) : 0u;
-        }
-        {
-            int4 *c = reinterpret_cast<int4 *>(cnt + lane * 8);
-            c[0] = make_int4((int)(b0.x - a0.x), (int)(b0.y - a0.y), (int)(b0.z - a0.z), (int)(b0.w - a0.w));
-            c[1] = make_int4((int)(b1.x - a1.x), (int)(b1.y - a1.y), (int)(b1.z - a1.z), (int)(b1.w - a1.w));
-        }
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t wi = (a >> 2) + (uint32_t)lane + 32u * k;
-            if (wi < ((ta + 3u) >> 2)) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const uint32_t p = wi * 4u + (uint32_t)e;
-                    if (p >= a && p < ta) cnt[(wa[k] >> (8 * e)) & 255u] = 1;
+        // Presence only (the mask path); three tiers by node width, each with as few issued instructions as possible
+        // (the kernel is issue-bound: ~90 K nodes per step, most of them a handful of rows).
+        const uint32_t w = hi - lo;
+        if (w <= 32u) {  // one lane per row, straight into the bitmap
+            if ((uint32_t)lane < w) {
+                const uint32_t sy = base_sym | fm_byte_at(ix.bcells, lo + (uint32_t)lane);
+                if (sy >= sa && sy < se) {
+                    const uint32_t rel = (uint32_t)((int64_t)sy - shift) - t0;
+                    atomicOr(&bm[rel >> 5], 1u << (rel & 31u));
                 }
             }
-            const uint32_t wj = (uint32_t)lane + 32u * k;
-            if (wj < ((tb + 3u) >> 2)) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const uint32_t p = wj * 4u + (uint32_t)e;
-                    if (p < tb) cnt[(wb[k] >> (8 * e)) & 255u] = 1;
-                }
-            }
+            return;
         }
-        __syncwarp();
-        const int4 c0 = reinterpret_cast<const int4 *>(cnt + lane * 8)[0], c1 = reinterpret_cast<const int4 *>(cnt + lane * 8)[1];
-        const int cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        // lane i owns symbols 8i..8i+7: which of them lie in [sa,se) (the window clips at most the first / last node)
+        const int64_t sb = (int64_t)base_sym + 8 * lane;
+        const int64_t c_lo = (int64_t)sa - sb, c_hi = (int64_t)se - sb;
+        const uint32_t keep = (c_hi <= 0 || c_lo >= 8) ? 0u : ((c_hi >= 8 ? 0xFFu : ((1u << (int)c_hi) - 1u)) & ~(c_lo <= 0 ? 0u : ((1u << (int)c_lo) - 1u)));
         uint32_t bits = 0;
+        if (w <= 512u) {
+            // Flags by PLAIN shared-memory stores of 1 (same-address stores of a warp merge; no atomics, so a skewed
+            // byte distribution costs nothing extra); rows read as single bytes, 4 loads in flight per lane.
+            int4 *c = reinterpret_cast<int4 *>(cnt + lane * 8);
+            c[0] = make_int4(0, 0, 0, 0);
+            c[1] = make_int4(0, 0, 0, 0);
+            __syncwarp();
+            for (uint32_t k0 = 0; k0 < w; k0 += 128u) {
+                uint32_t v[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t sy = base_sym | (uint32_t)(lane * 8 + k);
-            if (cc[k] > 0 && sy >= sa && sy < se) bits |= 1u << k;
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t t = k0 + 32u * j + (uint32_t)lane;
+                    v[j] = t < w ? fm_byte_at(ix.bcells, lo + t) : 0xFFFFFFFFu;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (v[j] != 0xFFFFFFFFu) cnt[v[j]] = 1;
+            }
+            __syncwarp();
+            const int4 c0 = c[0], c1 = c[1];
+            bits = (c0.x ? 1u : 0u) | (c0.y ? 2u : 0u) | (c0.z ? 4u : 0u) | (c0.w ? 8u : 0u) | (c1.x ? 16u : 0u) |
+                   (c1.y ? 32u : 0u) | (c1.z ? 64u : 0u) | (c1.w ? 128u : 0u);
+        } else {
+            bits = fm_byte_node_presence_wide(ix, lo, hi, cnt, lane);
         }
+        bits &= keep;
         // four lanes assemble one 32-symbol word: at most 2 OR operations per 32 symbols reach the bitmap
         uint32_t v = bits << (8 * (lane & 3));
         v |= __shfl_xor_sync(FULL, v, 1);
@@ -1514,7 +1555,7 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
     if (!has) {
         static const int occ = [] {
             const char *e = getenv("FMIDX_BYTES_OCC");
-            return e && *e ? atoi(e) : 6;
+            return e && *e ? atoi(e) : 5;
         }();
         const unsigned bgrid = (unsigned)h->sm_count * occ;
 #define FM_BYTES(LIST, CNT, CAP)                                                                                            \
