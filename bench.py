@@ -38,9 +38,10 @@ BYTES_PER_SEARCH_STEP = 1088      # 2 boundaries x 17 levels x 3
 MASK_BYTES = 16032                # one 128,256-bit vocab mask
 N_QUERY_SETS = 8                  # distinct prefix batches rotated through the timed steps
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of this very
-# command (profiles/r1_v2_ncu_full_summary.csv; 100M tokens, batch 4096).  k_mask = k_mask_top +
-# k_mask_items + the 65.7 MB memset of the mask rows that precedes them.
-NCU_TRAFFIC = {"k_mask": 2.69e6 + 40.87e6 + 0.79e6 + 65.7e6, "k_search": 10.88e6}
+# command (profiles/r1_v3_ncu_full_summary.csv; 100M tokens, batch 4096).  k_mask = k_mask_top + k_mask_expand +
+# k_mask_bytes: 2.32 + 2.45 + 31.82 MB read; the 65.7 MB of mask rows are written once (zeroed in k_mask_top, bits
+# ORed in by L2 atomics) -- ncu sees 10.5 MB of them leave L2 inside the kernels' own windows, the rest drains later.
+NCU_TRAFFIC = {"k_mask": 2.32e6 + 2.45e6 + 31.82e6 + 65.7e6, "k_search": 11.44e6}
 
 
 _JSON_OUT = None
@@ -357,24 +358,69 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # N = 1: consecutive steps are independent batches, so two of them are kept in flight on two streams through
+    # fmidx_query_batch (one call = search + masks of one batch; each stream has its own output buffers and scratch
+    # slot).  The latency-bound search of one batch then overlaps the issue-bound enumeration of the other.  The
+    # per-kernel durations for the roofline come from a SERIAL pass of the same steps below (events on one stream).
+    NPIPE = 2
+    pstreams = [torch.cuda.Stream(device=device) for _ in range(NPIPE)] if world == 1 else []
+    pbufs = [bufs[0]] + [(torch.empty_like(sp), torch.empty_like(ep), torch.empty_like(mask)) for _ in range(NPIPE - 1)] \
+        if world == 1 else []
+
+    def step_pipe(k):
+        q, offs = qsets[k % N_QUERY_SETS]
+        psp, pep, pmask = pbufs[k % NPIPE]
+        _native.check(L.fmidx_query_batch(ix._h, k % NPIPE, C.c_void_p(q.data_ptr()), C.c_void_p(offs.data_ptr()), B, SHIFT, VOCAB,
+                                          C.c_void_p(psp.data_ptr()), C.c_void_p(pep.data_ptr()), C.c_void_p(pmask.data_ptr()),
+                                          C.c_void_p(pstreams[k % NPIPE].cuda_stream)))
+
+    def fork():
+        e = torch.cuda.Event()
+        e.record(stream)
+        for ps in pstreams:
+            ps.wait_event(e)
+
+    def join():
+        for ps in pstreams:
+            e = torch.cuda.Event()
+            e.record(ps)
+            stream.wait_event(e)
+
+    step = step_pipe if world == 1 else step_full
+    fork()
     for w in range(args.warmup):
-        step_full(w)
+        step(w)
+    join()
     barrier()
     launches0 = L.fmidx_launch_count()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     barrier()
     e_start.record(stream)
+    fork()
     for k in range(args.steps):
-        step_full(k, evs[k])
+        step(k)
+    join()
     drain()  # the timed region ends when the last exchange has completed
     e_end.record(stream)
     barrier()
     total_ms = e_start.elapsed_time(e_end)
     launches = L.fmidx_launch_count() - launches0
+    # serial pass with events around each kernel group (N = 1: this is where the roofline's launch durations come
+    # from; N > 1: the timed region itself is serial on the kernel stream, so it is simply repeated)
+    n_ev = min(args.steps, 500)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_ev)]
+    es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    es0.record(stream)
+    for k in range(n_ev):
+        step_full(k, evs[k])
+    drain()
+    es1.record(stream)
+    barrier()
+    serial_ms_per_step = es0.elapsed_time(es1) / n_ev
     if sampler and total_ms < 150:  # region too short for NVML's sampling period: keep the same load running
         t_end = time.time() + 0.6
         k = 0
@@ -442,7 +488,7 @@ def main():
     bytes_mask_ref = 2 * 32 * enum_nodes_bin + MASK_BYTES * B
     peak, peak_src = measured_peaks()
     if t_mask >= t_search:
-        dom = {"kernel": "k_mask (k_mask_top + k_mask_items: distinct-token enumeration -> vocab bitmap)", "bound": "hbm",
+        dom = {"kernel": "k_mask (k_mask_top + k_mask_expand + k_mask_bytes: distinct-token enumeration -> vocab bitmap)", "bound": "hbm",
                "achieved": bytes_mask / (t_mask * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                "traffic": NCU_TRAFFIC["k_mask"] if args.tokens == 100_000_000 and B == 4096 else None,
                "algorithmic_bytes_per_launch": bytes_mask, "avg_launch_ms": t_mask,
@@ -452,7 +498,7 @@ def main():
                "frac_reference_layout": bytes_mask_ref / (t_mask * 1e-3) / 1e9 / peak,
                "per_unit_reference_layout": "64 B per visited node of the 17-level binary tree + 16,032 B mask per prefix",
                "distinct_symbols_per_launch": distinct_total,
-               "note": "latency/issue bound (ncu: 36% issue-active, 7% DRAM): the fraction measures distance from the HBM "
+               "note": "issue bound (ncu: k_mask_bytes 67% issue-active, 9% DRAM): the fraction measures distance from the HBM "
                        "bound, the reference-layout figure shows how much less this layout has to move"}
     else:
         dom = {"kernel": "k_search (batched backward search)", "bound": "hbm",
@@ -479,7 +525,7 @@ def main():
         n32 = torch.empty(own, dtype=torch.int32, device=device)
         hcnt = torch.empty(B, dtype=torch.int64).pin_memory()
 
-        NSLOT = 2  # batches in flight through the pipelined host API
+        NSLOT = int(os.environ.get("BENCH_NSLOT", "4"))  # batches in flight through the pipelined host API
         hres = [(torch.empty(B, dtype=torch.int64).pin_memory(), torch.empty(B, dtype=torch.int64).pin_memory(),
                  torch.empty(B, dtype=torch.int32).pin_memory()) for _ in range(NSLOT)]
 
@@ -528,8 +574,8 @@ def main():
         h2d = int(np.mean([q.numel() * 4 + offs.numel() * 8 for q, offs in hq]))
         e2e = {"value": B * args.steps / dt, "unit": "queries/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": B * (8 + 8 + 4) if world == 1 else B * 24 + own * 4, "ms_per_step": 1e3 * dt / args.steps,
-               "api": "fmidx_query_submit/fmidx_query_wait, 2 batches in flight (pinned host prefixes in; ranges + distinct-token "
-                      "counts out, every step; masks stay in HBM)"
+               "api": "fmidx_query_submit/fmidx_query_wait, %d batches in flight (pinned host prefixes in; ranges + distinct-token "
+                      "counts out, every step; masks stay in HBM)" % NSLOT
                       if world == 1 else "pinned host prefixes -> H2D -> fmidx_search_batch + fmidx_distinct_mask_batch -> all-to-all + "
                       "fmidx_mask_or + all-reduce -> D2H of ranges, total counts and distinct counts of the owned prefixes"}
 
@@ -568,6 +614,10 @@ def main():
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": workload_config(args, B),
             "masks_per_sec": value, "roofline": dom, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "pipeline": {"streams": NPIPE if world == 1 else 1, "serial_ms_per_step": serial_ms_per_step,
+                         "note": "value/ms_per_step: independent batches alternate between the streams (fmidx_query_batch); "
+                                 "roofline launch durations come from the serial pass (one stream, events around each kernel group)"
+                                 if world == 1 else "kernels on one stream, exchange on its own stream"},
             "clocks": clocks, "index": {"build_s": t_build, "device_mb": info["device_bytes"] / 1e6, "levels": info["levels"],
                                         "layout": "wavelet matrix: 3 nibble levels (128-B cells) + byte level (1,536-B cells); %s (sa_dens %d, isa_dens %d, text %s)" % (args.layout, info["sa_dens"], info["isa_dens"], bool(info["keep_text"]))},
         }

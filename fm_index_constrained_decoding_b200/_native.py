@@ -30,6 +30,7 @@ SIGNATURES = {
     "fmidx_search_batch": (C.c_int, [p, p, p, sz, i64, p, p, p]),
     "fmidx_step_batch": (C.c_int, [p, p, p, p, sz, p, p, p]),
     "fmidx_distinct_mask_batch": (C.c_int, [p, p, p, sz, i64, u32, p, p, p]),
+    "fmidx_query_batch": (C.c_int, [p, C.c_int, p, p, sz, i64, u32, p, p, p, p]),
     "fmidx_distinct_mask_batch_occ": (C.c_int, [p, p, p, sz, i64, u32, p, p, p, p]),
     "fmidx_mask_pull_or": (C.c_int, [p, p, u32, p, sz, sz, sz, u32, p, p]),  # (h, peers, world, occ_all, occ_stride, row_lo, n_rows, vocab, out, stream)
     "fmidx_mask_pull_or_inplace": (C.c_int, [p, p, u32, u32, p, sz, sz, sz, u32, p]),

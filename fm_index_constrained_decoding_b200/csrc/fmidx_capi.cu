@@ -489,6 +489,19 @@ int fmidx_distinct_mask_batch(fmidx_t *h, const uint64_t *d_sp, const uint64_t *
                           (cudaStream_t)stream);
 }
 
+int fmidx_query_batch(fmidx_t *h, int ws_slot, const int32_t *d_toks, const int64_t *d_offs, size_t B, int64_t shift,
+                      uint32_t vocab, uint64_t *d_sp, uint64_t *d_ep, uint32_t *d_mask, void *stream) {
+    FM_TRY(enter(h, true));
+    if (ws_slot < 0 || ws_slot >= 4) { fm_set_error("ws_slot must be 0..3"); return FMIDX_EINVAL; }
+    if (!d_sp || !d_ep) { fm_set_error("null argument"); return FMIDX_EINVAL; }
+    FM_TRY(fm_launch_search(h, d_toks, d_offs, B, shift, d_sp, d_ep, 0, (cudaStream_t)stream));
+    if (!d_mask || vocab == 0) return FMIDX_OK;
+    h->mask_ws_override = &h->slots[ws_slot].ws;  // calls on different streams must not share the node lists
+    struct Reset { fmidx_t *h; ~Reset() { h->mask_ws_override = nullptr; } } reset{h};
+    return fm_launch_mask(h, d_sp, d_ep, B, shift, vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, d_mask, nullptr,
+                          (cudaStream_t)stream);
+}
+
 int fmidx_distinct_mask_batch_occ(fmidx_t *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, int64_t shift,
                                   uint32_t vocab, uint32_t *d_mask, uint32_t *d_counts, uint32_t *d_occ, void *stream) {
     FM_TRY(enter(h, true));

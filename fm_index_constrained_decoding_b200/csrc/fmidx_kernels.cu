@@ -286,60 +286,83 @@ __device__ __forceinline__ void fm_or_bits(uint32_t *bm, uint32_t bits, uint32_t
     }
 }
 
-// Presence flags of a byte-level node wider than 512 rows: symbol v occurs in [lo,hi) iff it occurs in the part of
-// cell A at or after lo, in the part of cell B before hi, or in a whole cell between them (header difference
-// hdr[B] - hdr[A+1] > 0, read only when such cells exist).  Returns the lane's 8 flags (symbols 8*lane..8*lane+7).
+// cnt[v] = 1 for the 16 bytes v of q (plain stores: same-address stores of a warp merge)
+__device__ __forceinline__ void fm_flag16(int *cnt, const uint4 &q) {
+    const uint32_t x[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        cnt[x[j] & 255u] = 1;
+        cnt[(x[j] >> 8) & 255u] = 1;
+        cnt[(x[j] >> 16) & 255u] = 1;
+        cnt[x[j] >> 24] = 1;
+    }
+}
+
+// Presence flags of a byte-level node wider than 512 rows (so lo and hi lie in different cells A < B): symbol v
+// occurs in [lo,hi) iff it occurs in A[a,512), in B[0,b), or in a whole cell between them (header difference
+// hdr[B] - hdr[A+1] > 0, read only when such cells exist).  Lane i holds payload bytes 16i..16i+15 of each cell (one
+// 16-byte load per cell); the bytes outside the scan in the single boundary lane are overwritten with a byte from
+// inside it, so every store is unconditional.  Returns the lane's 8 flags (symbols 8*lane..8*lane+7).
 __device__ __forceinline__ uint32_t fm_byte_node_presence_wide(const FmDev &ix, uint32_t lo, uint32_t hi, int *cnt, int lane) {
     const uint32_t cA = lo >> 9, a = lo & 511u, cB = hi >> 9, b = hi & 511u;
-    const bool same = cA == cB, far = cB > cA + 1u;
     const uint4 *cellA = ix.bcells + (size_t)cA * FMIDX_BCELL_U4, *cellB = ix.bcells + (size_t)cB * FMIDX_BCELL_U4;
-    const uint32_t ta = same ? b : 512u, tb = same ? 0u : b;  // scans A[a,ta) and B[0,tb)
-    const uint32_t *pwa = reinterpret_cast<const uint32_t *>(cellA + FMIDX_BHDR_U4);
-    const uint32_t *pwb = reinterpret_cast<const uint32_t *>(cellB + FMIDX_BHDR_U4);
-    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0, b0 = a0, b1 = a0;
+    const bool far = cB > cA + 1u;
+    const int fa = (int)a - 16 * lane;  // scan A: local bytes [max(fa,0), 16)
+    const int tb = (int)b - 16 * lane;  // scan B: local bytes [0, min(tb,16))
+    uint4 qa = make_uint4(0, 0, 0, 0), qb = qa, a0 = qa, a1 = qa, b0 = qa, b1 = qa;
+    if (fa < 16) qa = fm_ldg(cellA + FMIDX_BHDR_U4 + lane);
+    if (tb > 0) qb = fm_ldg(cellB + FMIDX_BHDR_U4 + lane);
     if (far) {
         a0 = fm_ldg(cellA + FMIDX_BCELL_U4 + 2 * lane);
         a1 = fm_ldg(cellA + FMIDX_BCELL_U4 + 2 * lane + 1);
         b0 = fm_ldg(cellB + 2 * lane);
         b1 = fm_ldg(cellB + 2 * lane + 1);
     }
-    uint32_t wa[4], wb[4];
+    const uint32_t hb = (b0.x != a0.x ? 1u : 0u) | (b0.y != a0.y ? 2u : 0u) | (b0.z != a0.z ? 4u : 0u) | (b0.w != a0.w ? 8u : 0u) |
+                        (b1.x != a1.x ? 16u : 0u) | (b1.y != a1.y ? 32u : 0u) | (b1.z != a1.z ? 64u : 0u) | (b1.w != a1.w ? 128u : 0u);
+    if (__all_sync(FULL, hb == 0xFFu)) return 0xFFu;  // every symbol already occurs in the whole cells
+    int4 *c = reinterpret_cast<int4 *>(cnt + lane * 8);
+    c[0] = make_int4(0, 0, 0, 0);
+    c[1] = make_int4(0, 0, 0, 0);
+    __syncwarp();
+    if (fa < 16) {
+        if (fa > 0) {  // the boundary lane: leading fa bytes lie before lo
+            const uint32_t fw = (qa.w >> 24) * 0x01010101u;
+            uint32_t x[4] = {qa.x, qa.y, qa.z, qa.w};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t wi = (a >> 2) + (uint32_t)lane + 32u * k;
-        wa[k] = wi < ((ta + 3u) >> 2) ? __ldg(pwa + wi) : 0u;
-        const uint32_t wj = (uint32_t)lane + 32u * k;
-        wb[k] = wj < ((tb + 3u) >> 2) ? __ldg(pwb + wj) : 0u;
+            for (int j = 0; j < 4; ++j) {
+                const int nj = fa - 4 * j;
+                if (nj >= 4) x[j] = fw;
+                else if (nj > 0) {
+                    const uint32_t m = (1u << (8 * nj)) - 1u;
+                    x[j] = (x[j] & ~m) | (fw & m);
+                }
+            }
+            qa = make_uint4(x[0], x[1], x[2], x[3]);
+        }
+        fm_flag16(cnt, qa);
     }
-    {
-        int4 *c = reinterpret_cast<int4 *>(cnt + lane * 8);
-        c[0] = make_int4((int)(b0.x - a0.x), (int)(b0.y - a0.y), (int)(b0.z - a0.z), (int)(b0.w - a0.w));
-        c[1] = make_int4((int)(b1.x - a1.x), (int)(b1.y - a1.y), (int)(b1.z - a1.z), (int)(b1.w - a1.w));
+    if (tb > 0) {
+        if (tb < 16) {  // the boundary lane: bytes from tb on lie at or after hi
+            const uint32_t fw = (qb.x & 255u) * 0x01010101u;
+            uint32_t x[4] = {qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int vj = tb - 4 * j;
+                if (vj <= 0) x[j] = fw;
+                else if (vj < 4) {
+                    const uint32_t m = (1u << (8 * vj)) - 1u;
+                    x[j] = (x[j] & m) | (fw & ~m);
+                }
+            }
+            qb = make_uint4(x[0], x[1], x[2], x[3]);
+        }
+        fm_flag16(cnt, qb);
     }
     __syncwarp();
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t wi = (a >> 2) + (uint32_t)lane + 32u * k;
-        if (wi < ((ta + 3u) >> 2)) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const uint32_t p = wi * 4u + (uint32_t)e;
-                if (p >= a && p < ta) cnt[(wa[k] >> (8 * e)) & 255u] = 1;
-            }
-        }
-        const uint32_t wj = (uint32_t)lane + 32u * k;
-        if (wj < ((tb + 3u) >> 2)) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const uint32_t p = wj * 4u + (uint32_t)e;
-                if (p < tb) cnt[(wb[k] >> (8 * e)) & 255u] = 1;
-            }
-        }
-    }
-    __syncwarp();
-    const int4 c0 = reinterpret_cast<const int4 *>(cnt + lane * 8)[0], c1 = reinterpret_cast<const int4 *>(cnt + lane * 8)[1];
-    return (c0.x > 0 ? 1u : 0u) | (c0.y > 0 ? 2u : 0u) | (c0.z > 0 ? 4u : 0u) | (c0.w > 0 ? 8u : 0u) | (c1.x > 0 ? 16u : 0u) |
-           (c1.y > 0 ? 32u : 0u) | (c1.z > 0 ? 64u : 0u) | (c1.w > 0 ? 128u : 0u);
+    const int4 c0 = c[0], c1 = c[1];
+    return hb | (c0.x ? 1u : 0u) | (c0.y ? 2u : 0u) | (c0.z ? 4u : 0u) | (c0.w ? 8u : 0u) | (c1.x ? 16u : 0u) |
+           (c1.y ? 32u : 0u) | (c1.z ? 64u : 0u) | (c1.w ? 128u : 0u);
 }
 
 // Distinct symbols of one byte-level node (positions [lo,hi) of the last level, all sharing `prefix`),
@@ -852,7 +875,8 @@ k_mask_expand(FmDev ix, uint32_t LT, int64_t shift, uint32_t vocab, const uint4 
 }
 
 // k_mask_bytes: one warp per byte-level node, bits ORed straight into the (pre-zeroed) mask row in global memory.
-// Warps are fully independent: no block-level barrier anywhere, the next node's entry is fetched ahead.
+// Warps are fully independent: no block-level barrier anywhere; node entries are fetched two ahead.  (Prefetching the
+// next node's cells into L1/L2 one node ahead was measured and lost 3%: the kernel is issue-bound, not latency-bound.)
 template <int MINB>
 __global__ void __launch_bounds__(BYTES_THREADS, MINB)
 k_mask_bytes(FmDev ix, int64_t shift, uint32_t vocab, const uint4 *__restrict__ bnodes, const uint32_t *__restrict__ n_ptr,
@@ -865,12 +889,15 @@ k_mask_bytes(FmDev ix, int64_t shift, uint32_t vocab, const uint4 *__restrict__ 
     const int64_t ge64 = min((int64_t)vocab + shift, (int64_t)ix.max_sym + 1);
     const uint32_t ge = ge64 > (int64_t)ga ? (uint32_t)ge64 : ga;
     const uint32_t gwarp = (blockIdx.x * BYTES_THREADS + tid) >> 5, nwarps = (gridDim.x * BYTES_THREADS) >> 5;
-    uint4 it = gwarp < n ? __ldg(bnodes + gwarp) : make_uint4(0u, 0u, 0u, 0u);
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    uint4 it = gwarp < n ? __ldg(bnodes + gwarp) : zero;
+    uint4 n1 = gwarp + nwarps < n ? __ldg(bnodes + gwarp + nwarps) : zero;
     for (uint32_t i = gwarp; i < n; i += nwarps) {
-        const uint4 nx = i + nwarps < n ? __ldg(bnodes + i + nwarps) : make_uint4(0u, 0u, 0u, 0u);
+        const uint4 n2 = i + 2u * nwarps < n ? __ldg(bnodes + i + 2u * nwarps) : zero;
         fm_eval_byte_node(ix, it.z, it.w, it.y, ga, ge, shift, 0u, mask_out + (size_t)it.x * mask_words, cnt[wid],
                           counts_out ? counts_out + (size_t)it.x * vocab : nullptr, lane);
-        it = nx;
+        it = n1;
+        n1 = n2;
     }
 }
 
@@ -1557,13 +1584,11 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
             const char *e = getenv("FMIDX_BYTES_OCC");
             return e && *e ? atoi(e) : 5;
         }();
-        const unsigned bgrid = (unsigned)h->sm_count * occ;
-#define FM_BYTES(LIST, CNT, CAP)                                                                                            \
-    do {                                                                                                                    \
-        if (occ == 4) FM_LAUNCH(k_mask_bytes<4>, bgrid, BYTES_THREADS, 0, s, ix, shift, vocab, LIST, CNT, CAP, d_mask, d_counts); \
-        else if (occ == 5) FM_LAUNCH(k_mask_bytes<5>, bgrid, BYTES_THREADS, 0, s, ix, shift, vocab, LIST, CNT, CAP, d_mask, d_counts); \
-        else if (occ == 8) FM_LAUNCH(k_mask_bytes<8>, bgrid, BYTES_THREADS, 0, s, ix, shift, vocab, LIST, CNT, CAP, d_mask, d_counts); \
-        else FM_LAUNCH(k_mask_bytes<6>, bgrid, BYTES_THREADS, 0, s, ix, shift, vocab, LIST, CNT, CAP, d_mask, d_counts); \
+        const unsigned bgrid = (unsigned)h->sm_count * (occ == 6 ? 6 : 5);
+#define FM_BYTES(LIST, CNT, CAP)                                                                                             \
+    do {                                                                                                                     \
+        if (occ == 6) FM_LAUNCH(k_mask_bytes<6>, bgrid, BYTES_THREADS, 0, s, ix, shift, vocab, LIST, CNT, CAP, d_mask, d_counts); \
+        else FM_LAUNCH(k_mask_bytes<5>, bgrid, BYTES_THREADS, 0, s, ix, shift, vocab, LIST, CNT, CAP, d_mask, d_counts);          \
     } while (0)
         if (L == 0) {  // the root is itself a byte-level node: the item list is the node list
             FM_BYTES(items, ctr, (uint32_t)(B * P_top));

@@ -267,6 +267,22 @@ class FMIndex(_FMIndex):
             N.check(N.lib().fmidx_distinct_mask_batch(self._h, _ptr(sp), _ptr(ep), B, shift, vocab, _ptr(mask), _ptr(counts), _stream(torch)))
         return (mask, counts) if want_counts else mask
 
+    def query_batch(self, toks, offs, vocab, shift=SHIFT, ws_slot=0, out=None):
+        """Ranges AND allowed-token bitmaps of B ragged prefixes in one call (fmidx_query_batch): returns
+        (sp, ep, mask).  Batches issued on different CUDA streams must use different ws_slot values (0..3)."""
+        torch = _torch()
+        B = offs.numel() - 1
+        words = (vocab + 31) // 32
+        if out is None:
+            out = (torch.empty(B, dtype=torch.int64, device=toks.device), torch.empty(B, dtype=torch.int64, device=toks.device),
+                   torch.empty((B, words), dtype=torch.int32, device=toks.device))
+        sp, ep, mask = out
+        assert mask.is_contiguous() and mask.shape == (B, words) and mask.dtype == torch.int32
+        if B:
+            N.check(N.lib().fmidx_query_batch(self._h, ws_slot, _ptr(toks), _ptr(offs), B, shift, vocab, _ptr(sp), _ptr(ep),
+                                              _ptr(mask), _stream(torch)))
+        return sp, ep, mask
+
     def mask_logits(self, sp, ep, logits, out=None, override_tok=None, always_allow=-1, extra_masks=None,
                     mask_out=None, shift=SHIFT):
         """Fused constrained-decoding step: out = logits + (-inf outside the allowed set).

@@ -97,6 +97,14 @@ int fmidx_step_batch(fmidx_t *h, const uint64_t *d_symbols, const uint64_t *d_lo
  * SET position (other entries are left untouched). */
 int fmidx_distinct_mask_batch(fmidx_t *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, int64_t shift,
                               uint32_t vocab, uint32_t *d_mask, uint32_t *d_counts, void *stream);
+/* One decoding step's lookups for B beams in ONE call: fmidx_search_batch followed by
+ * fmidx_distinct_mask_batch on the same stream (what index.py:93-131 `get_range` + index.py:146-159
+ * `get_distinct_count` do per beam in document_constrained_generation_vllm.py:72-137), d_sp/d_ep and d_mask as
+ * in those two calls (d_mask NULL or vocab 0: ranges only).  ws_slot (0..3) selects the scratch workspace the
+ * enumeration uses: calls that may run concurrently on DIFFERENT streams must use different slots, calls that
+ * share a slot must be stream-ordered. */
+int fmidx_query_batch(fmidx_t *h, int ws_slot, const int32_t *d_toks, const int64_t *d_offs, size_t B, int64_t shift,
+                      uint32_t vocab, uint64_t *d_sp, uint64_t *d_ep, uint32_t *d_mask, void *stream);
 /* same, additionally filling d_occ ([B][ceil(nslices/32)] u32, nslices = ceil(vocab/4096)): bit s of a row is set
  * when the row's 4096-token slice s may hold set bits (conservative).  Feeds fmidx_mask_pull_or. */
 int fmidx_distinct_mask_batch_occ(fmidx_t *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, int64_t shift,

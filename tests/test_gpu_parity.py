@@ -481,3 +481,36 @@ def test_mask_byte_node_list_overflow(cuda):
     r = subprocess.run([sys.executable, "-c", _OVERFLOW_SCRIPT % {"root": os.path.dirname(here), "tests": here}],
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "OVERFLOW-OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_query_batch_two_streams(cuda):
+    """fmidx_query_batch: search + masks in one call; two batches in flight on two streams with their own
+    workspace slots must not disturb each other."""
+    from fm_index_constrained_decoding_b200.index import ragged
+    rng = random.Random(31)
+    V = 128256
+    docs = random_docs(rng, 3000, 400, 20, 400)
+    ix, o = make(docs), oracle(docs)
+    batches = []
+    for k in range(2):
+        seqs = [[]] + [rng.choice(docs)[:rng.randint(1, 3)] for _ in range(300)]
+        for _ in range(300):
+            d = rng.choice(docs)
+            i = rng.randrange(len(d))
+            seqs.append(d[i:i + rng.randint(1, 6)])
+        toks, offs = ragged(seqs)
+        batches.append((toks, offs, o.query_batch(toks, offs, want_mask=True, vocab=V, nthreads=4)))
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    dev = [(torch.from_numpy(t).cuda(), torch.from_numpy(f).cuda()) for t, f, _ in batches]
+    torch.cuda.synchronize()
+    for rep in range(6):
+        outs = []
+        for k in range(2):
+            with torch.cuda.stream(streams[k]):
+                outs.append(ix.query_batch(dev[k][0], dev[k][1], V, ws_slot=k))
+        torch.cuda.synchronize()
+        for k in range(2):
+            sp_o, ep_o, m_o, _ = batches[k][2]
+            sp, ep, mask = outs[k]
+            assert (sp.cpu().numpy().astype(np.uint64) == sp_o).all() and (ep.cpu().numpy().astype(np.uint64) == ep_o).all()
+            assert (mask.cpu().numpy().view(np.uint32) == m_o).all()
