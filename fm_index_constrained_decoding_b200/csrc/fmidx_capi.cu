@@ -48,6 +48,8 @@ int fm_scratch(fmidx *h, FmBuf &b, size_t bytes, bool pinned_host) {
     }
     b.cap = want;
     b.pinned_host = pinned_host;
+    b.epoch = 0;
+    b.ctr_clean = false;
     return FMIDX_OK;
 }
 
@@ -492,7 +494,7 @@ int fmidx_distinct_mask_batch(fmidx_t *h, const uint64_t *d_sp, const uint64_t *
 int fmidx_query_batch(fmidx_t *h, int ws_slot, const int32_t *d_toks, const int64_t *d_offs, size_t B, int64_t shift,
                       uint32_t vocab, uint64_t *d_sp, uint64_t *d_ep, uint32_t *d_mask, void *stream) {
     FM_TRY(enter(h, true));
-    if (ws_slot < 0 || ws_slot >= 4) { fm_set_error("ws_slot must be 0..3"); return FMIDX_EINVAL; }
+    if (ws_slot < 0 || ws_slot >= 8) { fm_set_error("ws_slot must be 0..7"); return FMIDX_EINVAL; }
     if (!d_sp || !d_ep) { fm_set_error("null argument"); return FMIDX_EINVAL; }
     FM_TRY(fm_launch_search(h, d_toks, d_offs, B, shift, d_sp, d_ep, 0, (cudaStream_t)stream));
     if (!d_mask || vocab == 0) return FMIDX_OK;
@@ -707,13 +709,13 @@ static int query_host_impl(fmidx_t *h, const int32_t *toks, const int64_t *offs,
 
 int fmidx_query_submit(fmidx_t *h, int slot, const int32_t *toks, const int64_t *offs, size_t B, int64_t shift,
                        uint32_t vocab, uint64_t *sp, uint64_t *ep, uint32_t *n_distinct) {
-    if (slot < 0 || slot >= 4) { fm_set_error("slot must be 0..3"); return FMIDX_EINVAL; }
+    if (slot < 0 || slot >= 8) { fm_set_error("slot must be 0..7"); return FMIDX_EINVAL; }
     return query_host_impl(h, toks, offs, B, shift, vocab, sp, ep, nullptr, n_distinct, slot);
 }
 
 int fmidx_query_wait(fmidx_t *h, int slot) {
     FM_TRY(enter(h, false));
-    if (slot < 0 || slot >= 4) { fm_set_error("slot must be 0..3"); return FMIDX_EINVAL; }
+    if (slot < 0 || slot >= 8) { fm_set_error("slot must be 0..7"); return FMIDX_EINVAL; }
     if (h->slots[slot].stream) FM_CUDA(cudaStreamSynchronize(h->slots[slot].stream));
     return FMIDX_OK;
 }

@@ -42,6 +42,10 @@ struct FmBuf {  // growable device / pinned-host scratch
     void *p = nullptr;
     size_t cap = 0;
     bool pinned_host = false;
+    // mask workspaces only: the two work-list counter pairs at the start of the buffer alternate between calls and
+    // each call's last kernel zeroes the pair of the next one (no memset node per call)
+    uint32_t epoch = 0;
+    bool ctr_clean = false;
 };
 
 struct fmidx {
@@ -60,7 +64,7 @@ struct fmidx {
     struct Slot {                // fmidx_query_submit / fmidx_query_wait: independent in-flight host batches
         cudaStream_t stream = nullptr;
         FmBuf in, mask, ws;
-    } slots[4];
+    } slots[8];
     FmBuf h_scratch[4];
     int sm_count = 148;
 };

@@ -880,9 +880,13 @@ k_mask_expand(FmDev ix, uint32_t LT, int64_t shift, uint32_t vocab, const uint4 
 template <int MINB>
 __global__ void __launch_bounds__(BYTES_THREADS, MINB)
 k_mask_bytes(FmDev ix, int64_t shift, uint32_t vocab, const uint4 *__restrict__ bnodes, const uint32_t *__restrict__ n_ptr,
-             uint32_t cap, uint32_t *__restrict__ mask_out, uint32_t *__restrict__ counts_out) {
+             uint32_t cap, uint32_t *__restrict__ mask_out, uint32_t *__restrict__ counts_out, uint32_t *__restrict__ reset_ctr) {
     __shared__ __align__(16) int cnt[BYTES_THREADS / 32][256];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (blockIdx.x == 0 && tid == 0) {  // the counter pair of the NEXT call on this workspace (unused by this one)
+        reset_ctr[0] = 0u;
+        reset_ctr[1] = 0u;
+    }
     const uint32_t n = min(*n_ptr, cap);
     const uint32_t mask_words = (vocab + 31u) >> 5;
     const uint32_t ga = (uint32_t)(shift > 0 ? shift : 0);
@@ -1567,15 +1571,20 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
     const size_t items_bytes = has ? 0 : (size_t)B * P_top * 16;
     const size_t bnode_bytes = has || L == 0 ? 0 : cap * 16;
     FmBuf &ws = h->mask_ws_override ? *h->mask_ws_override : h->mask_ws;
-    FM_TRY(fm_scratch(h, ws, lvl_bytes + items_bytes + bnode_bytes + 128, false));
-    uint2 *lvl = (uint2 *)ws.p;
-    const size_t items_off = (lvl_bytes + 15) & ~(size_t)15;
+    FM_TRY(fm_scratch(h, ws, 128 + lvl_bytes + items_bytes + bnode_bytes + 128, false));
+    // first 128 bytes: two pairs of work-list counters ([0]=#items [1]=#byte nodes / next), used alternately: the last
+    // kernel of a call zeroes the pair of the following call, so steady-state calls need no memset
+    if (!ws.ctr_clean) {
+        FM_CUDA(cudaMemsetAsync(ws.p, 0, 128, s));
+        ws.epoch = 0;
+    }
+    ws.ctr_clean = false;  // set again once every launch of this call went through
+    uint32_t *ctr = (uint32_t *)ws.p + 2 * (ws.epoch & 1u), *ctr_next = (uint32_t *)ws.p + 2 * ((ws.epoch & 1u) ^ 1u);
+    ++ws.epoch;
+    uint2 *lvl = (uint2 *)((char *)ws.p + 128);
+    const size_t items_off = 128 + ((lvl_bytes + 15) & ~(size_t)15);
     uint4 *items = has ? nullptr : (uint4 *)((char *)ws.p + items_off);
     uint4 *bnodes = (uint4 *)((char *)ws.p + items_off + items_bytes);
-    uint32_t *ctr = (uint32_t *)((char *)ws.p + items_off + items_bytes + bnode_bytes);  // [0]=#items [1]=#byte nodes / next
-    if (!has) {
-        FM_CUDA(cudaMemsetAsync(ctr, 0, 8, s));  // the mask rows themselves are zeroed by k_mask_top
-    }
     FM_LAUNCH(k_mask_top, (unsigned)((B * 32 + 127) / 128), 128, 0, s, ix, d_sp, d_ep, (uint32_t)B, LT, lvl, d_override, shift,
               vocab, items, ctr, has ? nullptr : d_mask, has ? nullptr : d_counts, has ? nullptr : d_occ, (uint32_t)dense_lo,
               (uint32_t)std::min<size_t>(dense_n, 0xFFFFFFFFu));
@@ -1587,8 +1596,8 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
         const unsigned bgrid = (unsigned)h->sm_count * (occ == 6 ? 6 : 5);
 #define FM_BYTES(LIST, CNT, CAP)                                                                                             \
     do {                                                                                                                     \
-        if (occ == 6) FM_LAUNCH(k_mask_bytes<6>, bgrid, BYTES_THREADS, 0, s, ix, shift, vocab, LIST, CNT, CAP, d_mask, d_counts); \
-        else FM_LAUNCH(k_mask_bytes<5>, bgrid, BYTES_THREADS, 0, s, ix, shift, vocab, LIST, CNT, CAP, d_mask, d_counts);          \
+        if (occ == 6) FM_LAUNCH(k_mask_bytes<6>, bgrid, BYTES_THREADS, 0, s, ix, shift, vocab, LIST, CNT, CAP, d_mask, d_counts, ctr_next); \
+        else FM_LAUNCH(k_mask_bytes<5>, bgrid, BYTES_THREADS, 0, s, ix, shift, vocab, LIST, CNT, CAP, d_mask, d_counts, ctr_next); \
     } while (0)
         if (L == 0) {  // the root is itself a byte-level node: the item list is the node list
             FM_BYTES(items, ctr, (uint32_t)(B * P_top));
@@ -1600,6 +1609,7 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
         }
 #undef FM_BYTES
         FM_CUDA(cudaGetLastError());
+        ws.ctr_clean = true;
         return FMIDX_OK;
     }
     auto aligned = [&](int esz) {

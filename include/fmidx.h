@@ -100,7 +100,7 @@ int fmidx_distinct_mask_batch(fmidx_t *h, const uint64_t *d_sp, const uint64_t *
 /* One decoding step's lookups for B beams in ONE call: fmidx_search_batch followed by
  * fmidx_distinct_mask_batch on the same stream (what index.py:93-131 `get_range` + index.py:146-159
  * `get_distinct_count` do per beam in document_constrained_generation_vllm.py:72-137), d_sp/d_ep and d_mask as
- * in those two calls (d_mask NULL or vocab 0: ranges only).  ws_slot (0..3) selects the scratch workspace the
+ * in those two calls (d_mask NULL or vocab 0: ranges only).  ws_slot (0..7) selects the scratch workspace the
  * enumeration uses: calls that may run concurrently on DIFFERENT streams must use different slots, calls that
  * share a slot must be stream-ordered. */
 int fmidx_query_batch(fmidx_t *h, int ws_slot, const int32_t *d_toks, const int64_t *d_offs, size_t B, int64_t shift,
@@ -188,7 +188,7 @@ int fmidx_query_host(fmidx_t *h, const int32_t *toks, const int64_t *offs, size_
  * receives the ranges and n_distinct[b] = number of distinct next tokens of prefix b */
 int fmidx_query_host_summary(fmidx_t *h, const int32_t *toks, const int64_t *offs, size_t B, int64_t shift,
                              uint32_t vocab, uint64_t *sp, uint64_t *ep, uint32_t *n_distinct);
-/* pipelined form of fmidx_query_host_summary: up to 4 batches in flight, each in its own slot (own stream,
+/* pipelined form of fmidx_query_host_summary: up to 8 batches in flight, each in its own slot (own stream,
  * buffers and workspace).  submit enqueues H2D copies, kernels and D2H copies and returns; wait blocks until the
  * slot's host buffers (which should be pinned) hold the results.  n_distinct may be NULL (ranges only). */
 int fmidx_query_submit(fmidx_t *h, int slot, const int32_t *toks, const int64_t *offs, size_t B, int64_t shift,
