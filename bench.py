@@ -281,10 +281,10 @@ def main():
     words = (VOCAB + 31) // 32
     stream = torch.cuda.current_stream()
     sptr = C.c_void_p(stream.cuda_stream)
-    # N > 1: three buffer sets.  The cross-shard exchange of step k runs on its own stream while the kernels of
+    # N > 1: NBUF (4) buffer sets.  The cross-shard exchange of step k runs on its own stream while the kernels of
     # step k+1 fill the next set; the bitmaps live in peer-visible memory and the exchange PULLS only the occupied
     # 4096-token slices of the rows this rank owns (sharded.PeerMaskExchange), instead of an all-to-all of 16 KB rows.
-    NBUF = 3 if world > 1 else 1
+    NBUF = int(os.environ.get("BENCH_NBUF", "4")) if world > 1 else 1
     bufs = [(torch.empty(B, dtype=torch.int64, device=device), torch.empty(B, dtype=torch.int64, device=device),
              torch.empty((B, words), dtype=torch.int32, device=device) if world == 1 else None) for _ in range(NBUF)]
     sp, ep, mask = bufs[0]
@@ -311,40 +311,50 @@ def main():
         mask = px.local_views[0] if px is not None else bufs[0][2]
     cnt_bufs = [torch.empty(B, dtype=torch.int64, device=device) for _ in bufs]
 
-    def step_full(k, ev=None, q_off=None):
+    # N > 1: every buffer set has its own kernel stream and scratch slot, so the kernels of up to NBUF consecutive steps
+    # overlap each other as well as the exchanges (which stay ordered on the exchange stream)
+    kstreams = [torch.cuda.Stream(device=device) for _ in bufs] if world > 1 else [stream]
+
+    def step_full(k, ev=None, q_off=None, serial=False):
         q, offs = q_off if q_off is not None else qsets[k % N_QUERY_SETS]
         bi = k % NBUF
         bsp, bep, bmask = bufs[bi]
+        ks = stream if serial or world == 1 else kstreams[bi]
+        kptr = C.c_void_p(ks.cuda_stream)
         if world > 1:
-            # set bi was last pulled from by the peers at step k-3; this rank's exchange of step k-2 (whose
-            # all-gather every peer joins only after finishing its pull of step k-3) has to be complete
-            stream.wait_event(ev_comm[(k + 1) % NBUF])
+            # set bi was last used by step k-NBUF: this rank's exchange of that step has to be complete (the peers'
+            # pulls of it are awaited on the GPU through the ack flags inside compute_local)
+            ks.wait_event(ev_comm[bi])
+            if q_off is not None and ks is not stream:  # inputs were copied on the caller's stream
+                e_in = torch.cuda.Event()
+                e_in.record(stream)
+                ks.wait_event(e_in)
         if ev:
-            ev[0].record(stream)
+            ev[0].record(ks)
         _native.check(L.fmidx_search_batch(ix._h, C.c_void_p(q.data_ptr()), C.c_void_p(offs.data_ptr()), B, SHIFT,
-                                           C.c_void_p(bsp.data_ptr()), C.c_void_p(bep.data_ptr()), sptr))
+                                           C.c_void_p(bsp.data_ptr()), C.c_void_p(bep.data_ptr()), kptr))
         if ev:
-            ev[1].record(stream)
+            ev[1].record(ks)
         if px is not None:
-            px.compute_local(bi, bsp, bep, SHIFT)
+            px.compute_local(bi, bsp, bep, SHIFT, ws_slot=bi, stream=ks)
         else:
             _native.check(L.fmidx_distinct_mask_batch(ix._h, C.c_void_p(bsp.data_ptr()), C.c_void_p(bep.data_ptr()), B, SHIFT,
-                                                      VOCAB, C.c_void_p(bmask.data_ptr()), None, sptr))
+                                                      VOCAB, C.c_void_p(bmask.data_ptr()), None, kptr))
         if ev:
-            ev[2].record(stream)
+            ev[2].record(ks)
         if world > 1:
             # rank r ends up owning the final masks of prefixes [r*B/W, (r+1)*B/W); total occurrence counts are
-            # all-reduced (sum).  Runs on the exchange stream, overlapping the next step's kernels.
-            ev_kernels[bi].record(stream)
-            with torch.cuda.stream(comm_stream):
-                comm_stream.wait_event(ev_kernels[bi])
-                if px is not None:
-                    result["mask"] = px.exchange(bi)          # publish / wait / pull+OR / counts / ack: one host call
-                    result["count"] = px.total_counts(bi)
-                else:
+            # all-reduced (sum).  Runs on the exchange stream, overlapping the next steps' kernels.
+            ev_kernels[bi].record(ks)
+            comm_stream.wait_event(ev_kernels[bi])
+            if px is not None:
+                result["mask"] = px.exchange(bi, stream=comm_stream)  # publish / wait / pull+OR / counts / ack: one host call
+                result["count"] = px.total_counts(bi)
+            else:
+                with torch.cuda.stream(comm_stream):
                     result["mask"] = sharded.or_reduce_scatter(bmask, index=ix)[1]
                     result["count"] = sharded.sum_counts(bsp, bep)
-                ev_comm[bi].record(comm_stream)
+            ev_comm[bi].record(comm_stream)
         else:
             result["mask"] = bmask
 
@@ -384,11 +394,11 @@ def main():
     def fork():
         e = torch.cuda.Event()
         e.record(stream)
-        for ps in pstreams:
+        for ps in pstreams + (kstreams if world > 1 else []):
             ps.wait_event(e)
 
     def join():
-        for ps in pstreams:
+        for ps in pstreams + (kstreams if world > 1 else []):
             e = torch.cuda.Event()
             e.record(ps)
             stream.wait_event(e)
@@ -423,7 +433,7 @@ def main():
     barrier()
     es0.record(stream)
     for k in range(n_ev):
-        step_full(k, evs[k])
+        step_full(k, evs[k], serial=True)
     drain()
     es1.record(stream)
     barrier()
@@ -629,7 +639,8 @@ def main():
             "pipeline": {"streams": NPIPE if world == 1 else 1, "serial_ms_per_step": serial_ms_per_step,
                          "note": "value/ms_per_step: independent batches alternate between the streams (fmidx_query_batch); "
                                  "roofline launch durations come from the serial pass (one stream, events around each kernel group)"
-                                 if world == 1 else "kernels on one stream, exchange on its own stream"},
+                                 if world == 1 else "one kernel stream + scratch slot per buffer set (4), exchange on its own stream; roofline "
+                                 "launch durations from a serial pass"},
             "clocks": clocks, "index": {"build_s": t_build, "device_mb": info["device_bytes"] / 1e6, "levels": info["levels"],
                                         "layout": "wavelet matrix: 3 nibble levels (128-B cells) + byte level (1,536-B cells); %s (sa_dens %d, isa_dens %d, text %s)" % (args.layout, info["sa_dens"], info["isa_dens"], bool(info["keep_text"]))},
         }

@@ -37,7 +37,7 @@ SIGNATURES = {
     "fmidx_xchg_publish": (C.c_int, [p, p, p, u32, u32, p, sz, u32, p]),
     "fmidx_xchg_wait": (C.c_int, [p, p, u32, u32, p]),
     "fmidx_xchg_signal": (C.c_int, [p, p, u32, u32, u32, p]),
-    "fmidx_xchg_local": (C.c_int, [p, p, p, sz, i64, u32, p, p, p, u32, u32, u32, p]),
+    "fmidx_xchg_local": (C.c_int, [p, p, p, sz, i64, u32, p, p, p, u32, u32, u32, C.c_int, p]),
     "fmidx_xchg_round": (C.c_int, [p, p, p, p, p, p, p, p, u32, u32, sz, u32, u32, p, p]),
     "fmidx_ipc_alloc": (C.c_int, [p, sz, C.POINTER(p), p]),
     "fmidx_ipc_open": (C.c_int, [p, p, C.POINTER(p)]),

@@ -552,9 +552,12 @@ int fmidx_xchg_signal(fmidx_t *h, const uint64_t *d_peer_flags, uint32_t world, 
 // Side data layout of a shard (xwords u32): [B*ow occupancy words][B occurrence counts as u64], ow = ceil(nslices/32).
 int fmidx_xchg_local(fmidx_t *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, int64_t shift, uint32_t vocab,
                      uint32_t *d_mask, uint32_t *d_xlocal, const uint32_t *d_ack_flags, uint32_t world, uint32_t rank,
-                     uint32_t wait_seq, void *stream) {
+                     uint32_t wait_seq, int ws_slot, void *stream) {
     FM_TRY(enter(h, true));
     if (rank >= world || B % world) { fm_set_error("bad rank/world/B"); return FMIDX_EINVAL; }
+    if (ws_slot >= 8) { fm_set_error("ws_slot must be -1..7"); return FMIDX_EINVAL; }
+    if (ws_slot >= 0) h->mask_ws_override = &h->slots[ws_slot].ws;
+    struct Reset { fmidx_t *h; ~Reset() { h->mask_ws_override = nullptr; } } reset{h};
     if (!d_mask || !d_xlocal || !d_ack_flags) { fm_set_error("null argument"); return FMIDX_EINVAL; }
     cudaStream_t s = (cudaStream_t)stream;
     const size_t ow = (((size_t)vocab + 4095) / 4096 + 31) / 32;

@@ -213,6 +213,17 @@ class PeerMaskExchange:
         self.own_views = [v[self.rank * self.own:(self.rank + 1) * self.own] for v in self.local_views]
         self.seq = 0
         self.last_seq = [0] * n_buffers
+        # ctypes views of the fixed pointers (built once: two host calls per step is all the Python there is)
+        self._c_mask = [C.c_void_p(p) for p in self.mask_ptr]
+        self._c_inbox = [C.c_void_p(p) for p in self.inbox_ptr]
+        self._c_xlocal = [C.c_void_p(t.data_ptr()) for t in self.xlocal]
+        self._c_counts = [C.c_void_p(t.data_ptr()) for t in self.counts]
+        self._c_mask_tables = [C.c_void_p(t.data_ptr()) for t in self.mask_tables]
+        self._c_inbox_tables = [C.c_void_p(t.data_ptr()) for t in self.inbox_tables]
+        self._c_flags = C.c_void_p(self.flags.data_ptr())
+        self._c_ack = C.c_void_p(self.flags.data_ptr() + 4 * self.world)
+        self._c_data_flag_table = C.c_void_p(self.data_flag_table.data_ptr())
+        self._c_ack_flag_table = C.c_void_p(self.ack_flag_table.data_ptr())
         torch.cuda.synchronize()
         dist.barrier(group=group)
 
@@ -244,27 +255,30 @@ class PeerMaskExchange:
         import ctypes as C
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
-    def compute_local(self, i, sp, ep, shift=10):
-        """K2 of this shard for all B prefixes into buffer set i (bitmaps + occupancy words + counts), current
-        stream; first waits (on the GPU) until every shard has pulled the step that last used set i."""
+    def compute_local(self, i, sp, ep, shift=10, ws_slot=-1, stream=None):
+        """K2 of this shard for all B prefixes into buffer set i (bitmaps + occupancy words + counts); first waits
+        (on the GPU) until every shard has pulled the step that last used set i.  ws_slot: the enumeration's scratch
+        workspace (give every stream that may run concurrently its own, 0..7).  stream: a torch stream (default: the
+        current one; passing it avoids a stream context switch per step -- the host is the bottleneck here)."""
         import ctypes as C
         from . import _native as N
+        sptr = self._s() if stream is None else C.c_void_p(stream.cuda_stream)
         N.check(N.lib().fmidx_xchg_local(
             self.index._h, C.c_void_p(sp.data_ptr()), C.c_void_p(ep.data_ptr()), self.B, shift, self.vocab,
-            C.c_void_p(self.mask_ptr[i]), C.c_void_p(self.xlocal[i].data_ptr()),
-            C.c_void_p(self.flags.data_ptr() + 4 * self.world), self.world, self.rank, self.last_seq[i], self._s()))
+            self._c_mask[i], self._c_xlocal[i], self._c_ack, self.world, self.rank, self.last_seq[i], ws_slot, sptr))
 
-    def exchange(self, i):
-        """publish -> wait -> pull + OR (in place) -> total counts -> ack for buffer set i, ONE host call, current
-        stream.  Returns the final [B/world, words] bitmaps of the rows this rank owns (a view of set i)."""
+    def exchange(self, i, stream=None):
+        """publish -> wait -> pull + OR (in place) -> total counts -> ack for buffer set i, ONE host call on `stream`
+        (default: the current one).  Returns the final [B/world, words] bitmaps of the rows this rank owns (a view
+        of set i)."""
         import ctypes as C
         from . import _native as N
+        sptr = self._s() if stream is None else C.c_void_p(stream.cuda_stream)
         self.seq += 1
         N.check(N.lib().fmidx_xchg_round(
-            self.index._h, C.c_void_p(self.mask_tables[i].data_ptr()), C.c_void_p(self.inbox_tables[i].data_ptr()),
-            C.c_void_p(self.data_flag_table.data_ptr()), C.c_void_p(self.ack_flag_table.data_ptr()),
-            C.c_void_p(self.flags.data_ptr()), C.c_void_p(self.inbox_ptr[i]), C.c_void_p(self.xlocal[i].data_ptr()),
-            self.world, self.rank, self.B, self.vocab, self.seq, C.c_void_p(self.counts[i].data_ptr()), self._s()))
+            self.index._h, self._c_mask_tables[i], self._c_inbox_tables[i], self._c_data_flag_table, self._c_ack_flag_table,
+            self._c_flags, self._c_inbox[i], self._c_xlocal[i],
+            self.world, self.rank, self.B, self.vocab, self.seq, self._c_counts[i], sptr))
         self.last_seq[i] = self.seq
         return self.own_views[i]
 

@@ -137,10 +137,11 @@ int fmidx_xchg_signal(fmidx_t *h, const uint64_t *d_peer_flags, uint32_t world, 
  *        the other rows are valid in their OCCUPIED slices only (that is all the peers ever read).
  * round: publish d_xlocal to every inbox + data flag = seq -> wait for all data flags -> pull + OR the peers' occupied
  *        slices into this rank's rows of its own bitmap buffer -> total counts of all B prefixes into d_counts_out
- *        (optional) -> ack flag = seq on every shard. */
+ *        (optional) -> ack flag = seq on every shard.
+ * ws_slot: scratch workspace of the enumeration as in fmidx_query_batch (-1: the handle's default workspace). */
 int fmidx_xchg_local(fmidx_t *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, int64_t shift, uint32_t vocab,
                      uint32_t *d_mask, uint32_t *d_xlocal, const uint32_t *d_ack_flags, uint32_t world, uint32_t rank,
-                     uint32_t wait_seq, void *stream);
+                     uint32_t wait_seq, int ws_slot, void *stream);
 int fmidx_xchg_round(fmidx_t *h, const uint64_t *d_peer_masks, const uint64_t *d_peer_inbox, const uint64_t *d_peer_data_flags,
                      const uint64_t *d_peer_ack_flags, const uint32_t *d_data_flags, const uint32_t *d_inbox,
                      const uint32_t *d_xlocal, uint32_t world, uint32_t rank, size_t B, uint32_t vocab, uint32_t seq,
