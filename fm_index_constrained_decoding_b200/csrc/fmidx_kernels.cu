@@ -388,27 +388,50 @@ __device__ __forceinline__ void fm_eval_byte_node(const FmDev &ix, uint32_t lo, 
             return;
         }
         // lane i owns symbols 8i..8i+7: which of them lie in [sa,se) (the window clips at most the first / last node)
-        const int64_t sb = (int64_t)base_sym + 8 * lane;
-        const int64_t c_lo = (int64_t)sa - sb, c_hi = (int64_t)se - sb;
-        const uint32_t keep = (c_hi <= 0 || c_lo >= 8) ? 0u : ((c_hi >= 8 ? 0xFFu : ((1u << (int)c_hi) - 1u)) & ~(c_lo <= 0 ? 0u : ((1u << (int)c_lo) - 1u)));
+        uint32_t keep = 0xFFu;
+        if (base_sym < sa || base_sym + 256u > se) {  // warp-uniform, rare
+            const int64_t sb = (int64_t)base_sym + 8 * lane;
+            const int64_t c_lo = (int64_t)sa - sb, c_hi = (int64_t)se - sb;
+            keep = (c_hi <= 0 || c_lo >= 8) ? 0u : ((c_hi >= 8 ? 0xFFu : ((1u << (int)c_hi) - 1u)) & ~(c_lo <= 0 ? 0u : ((1u << (int)c_lo) - 1u)));
+        }
         uint32_t bits = 0;
         if (w <= 512u) {
             // Flags by PLAIN shared-memory stores of 1 (same-address stores of a warp merge; no atomics, so a skewed
-            // byte distribution costs nothing extra); rows read as single bytes, 4 loads in flight per lane.
+            // byte distribution costs nothing extra).  The rows are read as aligned 4-byte words (<= 130 of them, all
+            // loads issued first); in the two boundary words the bytes outside [lo,hi) are overwritten with a byte from
+            // inside, so the four stores per word are unconditional.
             int4 *c = reinterpret_cast<int4 *>(cnt + lane * 8);
             c[0] = make_int4(0, 0, 0, 0);
             c[1] = make_int4(0, 0, 0, 0);
-            __syncwarp();
-            for (uint32_t k0 = 0; k0 < w; k0 += 128u) {
-                uint32_t v[4];
+            const uint32_t p0 = lo & ~3u, nwords = (((hi + 3u) & ~3u) - p0) >> 2;
+            const char *pay = reinterpret_cast<const char *>(ix.bcells) + FMIDX_BHDR_U4 * 16;
+            uint32_t wv[5];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t t = k0 + 32u * j + (uint32_t)lane;
-                    v[j] = t < w ? fm_byte_at(ix.bcells, lo + t) : 0xFFFFFFFFu;
+            for (int j = 0; j < 5; ++j) {
+                wv[j] = 0u;
+                if (32u * j < nwords) {  // warp-uniform
+                    const uint32_t p = p0 + 4u * (32u * j + (uint32_t)lane);
+                    if (32u * j + (uint32_t)lane < nwords)
+                        wv[j] = __ldg(reinterpret_cast<const uint32_t *>(pay + (size_t)(p >> 9) * (FMIDX_BCELL_U4 * 16) + (p & 511u)));
                 }
+            }
+            __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (v[j] != 0xFFFFFFFFu) cnt[v[j]] = 1;
+            for (int j = 0; j < 5; ++j) {
+                if (32u * j < nwords && 32u * j + (uint32_t)lane < nwords) {
+                    const uint32_t p = p0 + 4u * (32u * j + (uint32_t)lane);
+                    uint32_t x = wv[j];
+                    if (p < lo || p + 4u > hi) {  // boundary word: valid bytes [e0,e1), never empty
+                        const uint32_t e0 = p < lo ? lo - p : 0u, e1 = min(hi - p, 4u);
+                        const uint32_t vm = (e1 >= 4u ? 0xFFFFFFFFu : ((1u << (8u * e1)) - 1u)) & ~((1u << (8u * e0)) - 1u);
+                        const uint32_t fw = ((x >> (8u * e0)) & 255u) * 0x01010101u;
+                        x = (x & vm) | (fw & ~vm);
+                    }
+                    cnt[x & 255u] = 1;
+                    cnt[(x >> 8) & 255u] = 1;
+                    cnt[(x >> 16) & 255u] = 1;
+                    cnt[x >> 24] = 1;
+                }
             }
             __syncwarp();
             const int4 c0 = c[0], c1 = c[1];
@@ -856,13 +879,46 @@ k_mask_expand(FmDev ix, uint32_t LT, int64_t shift, uint32_t vocab, const uint4 
         const uint32_t cp = (prefix << 4) | (uint32_t)hl;
         const uint64_t c_lo = (uint64_t)cp << 8, c_hi = ((uint64_t)cp + 1) << 8;
         const bool exists = wide && r_hi > r_lo && c_lo < ge && c_hi > ga;
-        const uint32_t bal = __ballot_sync(FULL, exists);
+        // children of <= 32 rows (the majority) are finished right here, all of the warp's children together: their rows
+        // form one flat list (prefix sums over the lanes), 32 rows per pass, owner found by a 5-step search over the
+        // sums; only the wider children become byte-level nodes of the second list
+        const uint32_t cw = r_hi - r_lo;
+        const bool small = exists && !counts_out && cw <= 32u;
+        const bool big = exists && !small;
+        {
+            const uint32_t wsm = small ? cw : 0u;
+            uint32_t inc = wsm;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL, inc, d);
+                if (lane >= d) inc += t;
+            }
+            const uint32_t total = __shfl_sync(FULL, inc, 31), excl = inc - wsm;
+            for (uint32_t f0 = 0; f0 < total; f0 += 32u) {
+                const uint32_t f = f0 + (uint32_t)lane;
+                uint32_t own = 0;  // first lane whose inclusive sum exceeds f
+#pragma unroll
+                for (int step = 16; step >= 1; step >>= 1)
+                    if (__shfl_sync(FULL, inc, (int)own + step - 1) <= f) own += (uint32_t)step;
+                own = min(own, 31u);
+                const uint32_t o_excl = __shfl_sync(FULL, excl, (int)own), o_lo = __shfl_sync(FULL, r_lo, (int)own);
+                const uint32_t o_cp = __shfl_sync(FULL, cp, (int)own), o_b = __shfl_sync(FULL, b, (int)own);
+                if (f < total) {
+                    const uint32_t sy = (o_cp << 8) | fm_byte_at(ix.bcells, o_lo + (f - o_excl));
+                    if (sy >= ga && sy < ge) {
+                        const uint32_t tk = (uint32_t)((int64_t)sy - shift);
+                        atomicOr(&mask_out[(size_t)o_b * mask_words + (tk >> 5)], 1u << (tk & 31u));
+                    }
+                }
+            }
+        }
+        const uint32_t bal = __ballot_sync(FULL, big);
         uint32_t slot = 0;
         if (lane == 0 && bal) slot = atomicAdd(n_bnodes, (uint32_t)__popc(bal));
         slot = __shfl_sync(FULL, slot, 0);
         const uint32_t idx = slot + __popc(bal & ((1u << lane) - 1u));
-        if (exists && idx < cap) bnodes[idx] = make_uint4(b, cp, r_lo, r_hi);
-        uint32_t ovf = __ballot_sync(FULL, exists && idx >= cap);
+        if (big && idx < cap) bnodes[idx] = make_uint4(b, cp, r_lo, r_hi);
+        uint32_t ovf = __ballot_sync(FULL, big && idx >= cap);
         while (ovf) {  // list full: evaluate the child here
             const int src = __ffs(ovf) - 1;
             const uint32_t ob = __shfl_sync(FULL, b, src), ocp = __shfl_sync(FULL, cp, src);
