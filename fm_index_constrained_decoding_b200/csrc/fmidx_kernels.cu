@@ -264,7 +264,7 @@ struct EnumSmem {
     uint32_t seed[4][3];            // depth-LT nodes of this slice (<= 2 when a top node spans one slice)
     uint32_t bnode[48][3];          // byte-level nodes (each covers 256 symbols): <= 16 per seed (+ overlap)
     uint32_t n_seed, n_bnode, width;
-    alignas(16) int cnt[MASK_THREADS / 32][256];  // per-warp histogram / presence flags of one byte-level node (int4 access)
+    alignas(1024) int cnt[MASK_THREADS / 32][256];  // per-warp histogram, or 256 presence-flag BYTES, of one byte-level node
     uint4 stage[MASK_THREADS / 16][16];
 };
 
@@ -286,23 +286,29 @@ __device__ __forceinline__ void fm_or_bits(uint32_t *bm, uint32_t bits, uint32_t
     }
 }
 
-// cnt[v] = 1 for the 16 bytes v of q (plain stores: same-address stores of a warp merge)
-__device__ __forceinline__ void fm_flag16(int *cnt, const uint4 &q) {
-    const uint32_t x[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        cnt[x[j] & 255u] = 1;
-        cnt[(x[j] >> 8) & 255u] = 1;
-        cnt[(x[j] >> 16) & 255u] = 1;
-        cnt[x[j] >> 24] = 1;
-    }
+// ---- presence flags: 256 BYTES per warp (the first 256 bytes of its cnt[] block, 256-aligned) -------------------
+// flag[v] = 1 by a plain one-byte store; same-address stores of a warp merge and different bytes of one word do not
+// conflict, so a skewed byte distribution costs nothing.  The store address is formed by ONE byte permute (byte e of
+// x into the low byte of the 256-aligned shared-space base): two issued instructions per scanned row.
+#define FM_FLAG_ST(x, e) asm volatile("st.shared.u8 [%0], %1;" ::"r"(__byte_perm((x), fbase, 0x7650 + (e))), "r"(1) : "memory")
+__device__ __forceinline__ void fm_flag4(uint32_t fbase, uint32_t x) {
+    FM_FLAG_ST(x, 0);
+    FM_FLAG_ST(x, 1);
+    FM_FLAG_ST(x, 2);
+    FM_FLAG_ST(x, 3);
+}
+__device__ __forceinline__ void fm_flags_zero(int *cnt, int lane) { reinterpret_cast<uint2 *>(cnt)[lane] = make_uint2(0u, 0u); }
+// the lane's 8 flags (symbols 8*lane..8*lane+7) as bits; flag bytes are 0 or 1
+__device__ __forceinline__ uint32_t fm_flags_read(const int *cnt, int lane) {
+    const uint2 f = reinterpret_cast<const uint2 *>(cnt)[lane];
+    return (((f.x * 0x01020408u) >> 24) & 0xFu) | ((((f.y * 0x01020408u) >> 24) & 0xFu) << 4);
 }
 
 // Presence flags of a byte-level node wider than 512 rows (so lo and hi lie in different cells A < B): symbol v
 // occurs in [lo,hi) iff it occurs in A[a,512), in B[0,b), or in a whole cell between them (header difference
 // hdr[B] - hdr[A+1] > 0, read only when such cells exist).  Lane i holds payload bytes 16i..16i+15 of each cell (one
-// 16-byte load per cell); the bytes outside the scan in the single boundary lane are overwritten with a byte from
-// inside it, so every store is unconditional.  Returns the lane's 8 flags (symbols 8*lane..8*lane+7).
+// 16-byte load per cell); bytes outside the scan (in the single boundary lane) are replaced by a byte from inside it
+// with a byte permute, so every store is unconditional.  Returns the lane's 8 flags (symbols 8*lane..8*lane+7).
 __device__ __forceinline__ uint32_t fm_byte_node_presence_wide(const FmDev &ix, uint32_t lo, uint32_t hi, int *cnt, int lane) {
     const uint32_t cA = lo >> 9, a = lo & 511u, cB = hi >> 9, b = hi & 511u;
     const uint4 *cellA = ix.bcells + (size_t)cA * FMIDX_BCELL_U4, *cellB = ix.bcells + (size_t)cB * FMIDX_BCELL_U4;
@@ -321,48 +327,31 @@ __device__ __forceinline__ uint32_t fm_byte_node_presence_wide(const FmDev &ix, 
     const uint32_t hb = (b0.x != a0.x ? 1u : 0u) | (b0.y != a0.y ? 2u : 0u) | (b0.z != a0.z ? 4u : 0u) | (b0.w != a0.w ? 8u : 0u) |
                         (b1.x != a1.x ? 16u : 0u) | (b1.y != a1.y ? 32u : 0u) | (b1.z != a1.z ? 64u : 0u) | (b1.w != a1.w ? 128u : 0u);
     if (__all_sync(FULL, hb == 0xFFu)) return 0xFFu;  // every symbol already occurs in the whole cells
-    int4 *c = reinterpret_cast<int4 *>(cnt + lane * 8);
-    c[0] = make_int4(0, 0, 0, 0);
-    c[1] = make_int4(0, 0, 0, 0);
+    const uint32_t fbase = (uint32_t)__cvta_generic_to_shared(cnt);
+    fm_flags_zero(cnt, lane);
     __syncwarp();
     if (fa < 16) {
-        if (fa > 0) {  // the boundary lane: leading fa bytes lie before lo
-            const uint32_t fw = (qa.w >> 24) * 0x01010101u;
-            uint32_t x[4] = {qa.x, qa.y, qa.z, qa.w};
+        // leading max(fa,0) bytes lie before lo: selector nibble i = i (keep) or 7 (= last byte of the lane's 16)
+        const uint32_t x[4] = {qa.x, qa.y, qa.z, qa.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int nj = fa - 4 * j;
-                if (nj >= 4) x[j] = fw;
-                else if (nj > 0) {
-                    const uint32_t m = (1u << (8 * nj)) - 1u;
-                    x[j] = (x[j] & ~m) | (fw & m);
-                }
-            }
-            qa = make_uint4(x[0], x[1], x[2], x[3]);
+        for (int j = 0; j < 4; ++j) {
+            const int nj = min(max(fa - 4 * j, 0), 4);
+            const uint32_t m = (1u << (4 * nj)) - 1u;  // nj <= 4
+            fm_flag4(fbase, __byte_perm(x[j], qa.w, (0x3210u & ~m) | (0x7777u & m)));
         }
-        fm_flag16(cnt, qa);
     }
     if (tb > 0) {
-        if (tb < 16) {  // the boundary lane: bytes from tb on lie at or after hi
-            const uint32_t fw = (qb.x & 255u) * 0x01010101u;
-            uint32_t x[4] = {qb.x, qb.y, qb.z, qb.w};
+        // bytes from min(tb,16) on lie at or after hi: selector nibble i = i (keep) or 4 (= first byte of the lane's 16)
+        const uint32_t x[4] = {qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int vj = tb - 4 * j;
-                if (vj <= 0) x[j] = fw;
-                else if (vj < 4) {
-                    const uint32_t m = (1u << (8 * vj)) - 1u;
-                    x[j] = (x[j] & m) | (fw & ~m);
-                }
-            }
-            qb = make_uint4(x[0], x[1], x[2], x[3]);
+        for (int j = 0; j < 4; ++j) {
+            const int vj = min(max(tb - 4 * j, 0), 4);
+            const uint32_t m = (1u << (4 * vj)) - 1u;
+            fm_flag4(fbase, __byte_perm(x[j], qb.x, (0x3210u & m) | (0x4444u & ~m)));
         }
-        fm_flag16(cnt, qb);
     }
     __syncwarp();
-    const int4 c0 = c[0], c1 = c[1];
-    return hb | (c0.x ? 1u : 0u) | (c0.y ? 2u : 0u) | (c0.z ? 4u : 0u) | (c0.w ? 8u : 0u) | (c1.x ? 16u : 0u) |
-           (c1.y ? 32u : 0u) | (c1.z ? 64u : 0u) | (c1.w ? 128u : 0u);
+    return hb | fm_flags_read(cnt, lane);
 }
 
 // Distinct symbols of one byte-level node (positions [lo,hi) of the last level, all sharing `prefix`),
@@ -400,9 +389,8 @@ __device__ __forceinline__ void fm_eval_byte_node(const FmDev &ix, uint32_t lo, 
             // byte distribution costs nothing extra).  The rows are read as aligned 4-byte words (<= 130 of them, all
             // loads issued first); in the two boundary words the bytes outside [lo,hi) are overwritten with a byte from
             // inside, so the four stores per word are unconditional.
-            int4 *c = reinterpret_cast<int4 *>(cnt + lane * 8);
-            c[0] = make_int4(0, 0, 0, 0);
-            c[1] = make_int4(0, 0, 0, 0);
+            const uint32_t fbase = (uint32_t)__cvta_generic_to_shared(cnt);
+            fm_flags_zero(cnt, lane);
             const uint32_t p0 = lo & ~3u, nwords = (((hi + 3u) & ~3u) - p0) >> 2;
             const char *pay = reinterpret_cast<const char *>(ix.bcells) + FMIDX_BHDR_U4 * 16;
             uint32_t wv[5];
@@ -421,22 +409,16 @@ __device__ __forceinline__ void fm_eval_byte_node(const FmDev &ix, uint32_t lo, 
                 if (32u * j < nwords && 32u * j + (uint32_t)lane < nwords) {
                     const uint32_t p = p0 + 4u * (32u * j + (uint32_t)lane);
                     uint32_t x = wv[j];
-                    if (p < lo || p + 4u > hi) {  // boundary word: valid bytes [e0,e1), never empty
+                    if (p < lo || p + 4u > hi) {  // boundary word: valid bytes [e0,e1), never empty; others := byte e0
                         const uint32_t e0 = p < lo ? lo - p : 0u, e1 = min(hi - p, 4u);
-                        const uint32_t vm = (e1 >= 4u ? 0xFFFFFFFFu : ((1u << (8u * e1)) - 1u)) & ~((1u << (8u * e0)) - 1u);
-                        const uint32_t fw = ((x >> (8u * e0)) & 255u) * 0x01010101u;
-                        x = (x & vm) | (fw & ~vm);
+                        const uint32_t vm = ((1u << (4u * e1)) - 1u) & ~((1u << (4u * e0)) - 1u);
+                        x = __byte_perm(x, x, (0x3210u & vm) | ((e0 * 0x1111u) & ~vm));
                     }
-                    cnt[x & 255u] = 1;
-                    cnt[(x >> 8) & 255u] = 1;
-                    cnt[(x >> 16) & 255u] = 1;
-                    cnt[x >> 24] = 1;
+                    fm_flag4(fbase, x);
                 }
             }
             __syncwarp();
-            const int4 c0 = c[0], c1 = c[1];
-            bits = (c0.x ? 1u : 0u) | (c0.y ? 2u : 0u) | (c0.z ? 4u : 0u) | (c0.w ? 8u : 0u) | (c1.x ? 16u : 0u) |
-                   (c1.y ? 32u : 0u) | (c1.z ? 64u : 0u) | (c1.w ? 128u : 0u);
+            bits = fm_flags_read(cnt, lane);
         } else {
             bits = fm_byte_node_presence_wide(ix, lo, hi, cnt, lane);
         }
@@ -834,7 +816,7 @@ k_mask_expand(FmDev ix, uint32_t LT, int64_t shift, uint32_t vocab, const uint4 
               const uint32_t *__restrict__ n_items_ptr, uint4 *__restrict__ bnodes, uint32_t *__restrict__ n_bnodes,
               uint32_t cap, uint32_t *__restrict__ mask_out, uint32_t *__restrict__ counts_out) {
     __shared__ uint4 stage[EXPAND_THREADS / 16][16];
-    __shared__ __align__(16) int cnt[EXPAND_THREADS / 32][256];
+    __shared__ __align__(1024) int cnt[EXPAND_THREADS / 32][256];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, hw = (tid >> 4) & 1, hl = tid & 15, hslot = tid >> 4;
     const uint32_t n_items = *n_items_ptr;
     const uint32_t mask_words = (vocab + 31u) >> 5;
@@ -937,7 +919,7 @@ template <int MINB>
 __global__ void __launch_bounds__(BYTES_THREADS, MINB)
 k_mask_bytes(FmDev ix, int64_t shift, uint32_t vocab, const uint4 *__restrict__ bnodes, const uint32_t *__restrict__ n_ptr,
              uint32_t cap, uint32_t *__restrict__ mask_out, uint32_t *__restrict__ counts_out, uint32_t *__restrict__ reset_ctr) {
-    __shared__ __align__(16) int cnt[BYTES_THREADS / 32][256];
+    __shared__ __align__(1024) int cnt[BYTES_THREADS / 32][256];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (blockIdx.x == 0 && tid == 0) {  // the counter pair of the NEXT call on this workspace (unused by this one)
         reset_ctr[0] = 0u;
