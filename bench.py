@@ -39,9 +39,9 @@ MASK_BYTES = 16032                # one 128,256-bit vocab mask
 N_QUERY_SETS = 8                  # distinct prefix batches rotated through the timed steps
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of this very
 # command (profiles/r1_v3_ncu_full_summary.csv; 100M tokens, batch 4096).  k_mask = k_mask_top + k_mask_expand +
-# k_mask_bytes: 2.32 + 2.45 + 31.82 MB read; the 65.7 MB of mask rows are written once (zeroed in k_mask_top, bits
-# ORed in by L2 atomics) -- ncu sees 10.5 MB of them leave L2 inside the kernels' own windows, the rest drains later.
-NCU_TRAFFIC = {"k_mask": 2.32e6 + 2.45e6 + 31.82e6 + 65.7e6, "k_search": 11.44e6}
+# k_mask_bytes: 2.32 + 7.36 + 27.42 MB read; the 65.7 MB of mask rows are written once (zeroed in k_mask_top, bits
+# ORed in by L2 atomics) -- ncu sees 10.1 MB of them leave L2 inside the kernels' own windows, the rest drains later.
+NCU_TRAFFIC = {"k_mask": 2.32e6 + 7.36e6 + 27.42e6 + 65.7e6, "k_search": 11.44e6}
 
 
 _JSON_OUT = None
@@ -228,7 +228,7 @@ def workload_config(args, batch):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=5000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--tokens", type=int, default=100_000_000)
@@ -515,7 +515,7 @@ def main():
                "frac_reference_layout": bytes_mask_ref / (t_mask * 1e-3) / 1e9 / peak,
                "per_unit_reference_layout": "64 B per visited node of the 17-level binary tree + 16,032 B mask per prefix",
                "distinct_symbols_per_launch": distinct_total,
-               "note": "issue bound (ncu: k_mask_bytes 67% issue-active, 9% DRAM): the fraction measures distance from the HBM "
+               "note": "issue/latency bound (ncu: k_mask_bytes 66% issue-active, 13% DRAM; k_mask_top / k_mask_expand latency-bound): the fraction measures distance from the HBM "
                        "bound, the reference-layout figure shows how much less this layout has to move"}
     else:
         dom = {"kernel": "k_search (batched backward search)", "bound": "hbm",
