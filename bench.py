@@ -343,18 +343,20 @@ def main():
         if ev:
             ev[2].record(ks)
         if world > 1:
-            # rank r ends up owning the final masks of prefixes [r*B/W, (r+1)*B/W); total occurrence counts are
-            # all-reduced (sum).  Runs on the exchange stream, overlapping the next steps' kernels.
-            ev_kernels[bi].record(ks)
-            comm_stream.wait_event(ev_kernels[bi])
+            # rank r ends up owning the final masks of prefixes [r*B/W, (r+1)*B/W); total occurrence counts are summed
             if px is not None:
-                result["mask"] = px.exchange(bi, stream=comm_stream)  # publish / wait / pull+OR / counts / ack: one host call
+                # publish / wait / pull+OR / counts / ack: one host call, on the set's own stream right behind its
+                # kernels (every set has its own flags, so the exchanges of the sets in flight overlap each other)
+                result["mask"] = px.exchange(bi, stream=ks)
                 result["count"] = px.total_counts(bi)
+                ev_comm[bi].record(ks)
             else:
+                ev_kernels[bi].record(ks)
+                comm_stream.wait_event(ev_kernels[bi])
                 with torch.cuda.stream(comm_stream):
                     result["mask"] = sharded.or_reduce_scatter(bmask, index=ix)[1]
                     result["count"] = sharded.sum_counts(bsp, bep)
-            ev_comm[bi].record(comm_stream)
+                ev_comm[bi].record(comm_stream)
         else:
             result["mask"] = bmask
 
@@ -639,7 +641,7 @@ def main():
             "pipeline": {"streams": NPIPE if world == 1 else 1, "serial_ms_per_step": serial_ms_per_step,
                          "note": "value/ms_per_step: independent batches alternate between the streams (fmidx_query_batch); "
                                  "roofline launch durations come from the serial pass (one stream, events around each kernel group)"
-                                 if world == 1 else "one kernel stream + scratch slot per buffer set (4), exchange on its own stream; roofline "
+                                 if world == 1 else "one stream + scratch slot + flag set per buffer set (4): kernels and exchange of a set back to back on its stream; roofline "
                                  "launch durations from a serial pass"},
             "clocks": clocks, "index": {"build_s": t_build, "device_mb": info["device_bytes"] / 1e6, "levels": info["levels"],
                                         "layout": "wavelet matrix: 3 nibble levels (128-B cells) + byte level (1,536-B cells); %s (sa_dens %d, isa_dens %d, text %s)" % (args.layout, info["sa_dens"], info["isa_dens"], bool(info["keep_text"]))},

@@ -174,8 +174,10 @@ class PeerMaskExchange:
       pull     for the rows this rank owns, read only the occupied slices out of the peers' bitmaps and OR
                them                                                              (fmidx_mask_pull_or)
       ack      ack[rank] = step on every shard                                  (fmidx_xchg_signal)
-    `n_buffers` >= 3 buffer sets let the exchange of step k (on its own stream) overlap the kernels of step k+1;
-    before a set is overwritten, compute_local waits for every shard's ack of the step that last used it.
+    `n_buffers` buffer sets, each with its own flags and step counter: the sets are independent, so set i's kernels
+    and exchange can run back to back on "its" stream while the other sets' steps overlap them on theirs (bench.py:
+    4 sets, 4 streams).  Before a set is overwritten, compute_local waits for every shard's ack of the step that
+    last used it.
     """
 
     def __init__(self, index, B, vocab, n_buffers=3, group=None):
@@ -203,15 +205,18 @@ class PeerMaskExchange:
             self.inbox_ptr.append(ptr)
             self.inbox_tables.append(table)
             self.inbox_views.append(torch.as_tensor(_RawCuda(ptr, self.world * self.xwords), device=dev).view(self.world, self.xwords))
-        fptr, ftable = self._shared(2 * self.world * 4)
-        self.flags = torch.as_tensor(_RawCuda(fptr, 2 * self.world), device=dev)
+        # every buffer set has its OWN data / ack flags and step counter, so the exchanges of different sets are
+        # independent and may run on different streams (set i: flags[i][0:world] data of step s published by rank r,
+        # flags[i][world:2*world] step s pulled by rank r)
+        fptr, ftable = self._shared(n_buffers * 2 * self.world * 4)
+        self.flags = torch.as_tensor(_RawCuda(fptr, n_buffers * 2 * self.world), device=dev)
         self.flags.zero_()
-        self.data_flag_table = ftable                                  # flags[0:world]  : data of step s published
-        self.ack_flag_table = ftable + 4 * self.world                  # flags[world:2w] : step s pulled
+        self.data_flag_tables = [ftable + 8 * self.world * i for i in range(n_buffers)]
+        self.ack_flag_tables = [ftable + 8 * self.world * i + 4 * self.world for i in range(n_buffers)]
         self.xlocal = [torch.empty(self.xwords, dtype=torch.int32, device=dev) for _ in range(n_buffers)]
         self.counts = [torch.empty(B, dtype=torch.int64, device=dev) for _ in range(n_buffers)]
         self.own_views = [v[self.rank * self.own:(self.rank + 1) * self.own] for v in self.local_views]
-        self.seq = 0
+        self.seq = [0] * n_buffers
         self.last_seq = [0] * n_buffers
         # ctypes views of the fixed pointers (built once: two host calls per step is all the Python there is)
         self._c_mask = [C.c_void_p(p) for p in self.mask_ptr]
@@ -220,10 +225,10 @@ class PeerMaskExchange:
         self._c_counts = [C.c_void_p(t.data_ptr()) for t in self.counts]
         self._c_mask_tables = [C.c_void_p(t.data_ptr()) for t in self.mask_tables]
         self._c_inbox_tables = [C.c_void_p(t.data_ptr()) for t in self.inbox_tables]
-        self._c_flags = C.c_void_p(self.flags.data_ptr())
-        self._c_ack = C.c_void_p(self.flags.data_ptr() + 4 * self.world)
-        self._c_data_flag_table = C.c_void_p(self.data_flag_table.data_ptr())
-        self._c_ack_flag_table = C.c_void_p(self.ack_flag_table.data_ptr())
+        self._c_flags = [C.c_void_p(self.flags.data_ptr() + 8 * self.world * i) for i in range(n_buffers)]
+        self._c_ack = [C.c_void_p(self.flags.data_ptr() + 8 * self.world * i + 4 * self.world) for i in range(n_buffers)]
+        self._c_data_flag_table = [C.c_void_p(t.data_ptr()) for t in self.data_flag_tables]
+        self._c_ack_flag_table = [C.c_void_p(t.data_ptr()) for t in self.ack_flag_tables]
         torch.cuda.synchronize()
         dist.barrier(group=group)
 
@@ -265,7 +270,7 @@ class PeerMaskExchange:
         sptr = self._s() if stream is None else C.c_void_p(stream.cuda_stream)
         N.check(N.lib().fmidx_xchg_local(
             self.index._h, C.c_void_p(sp.data_ptr()), C.c_void_p(ep.data_ptr()), self.B, shift, self.vocab,
-            self._c_mask[i], self._c_xlocal[i], self._c_ack, self.world, self.rank, self.last_seq[i], ws_slot, sptr))
+            self._c_mask[i], self._c_xlocal[i], self._c_ack[i], self.world, self.rank, self.last_seq[i], ws_slot, sptr))
 
     def exchange(self, i, stream=None):
         """publish -> wait -> pull + OR (in place) -> total counts -> ack for buffer set i, ONE host call on `stream`
@@ -274,12 +279,12 @@ class PeerMaskExchange:
         import ctypes as C
         from . import _native as N
         sptr = self._s() if stream is None else C.c_void_p(stream.cuda_stream)
-        self.seq += 1
+        self.seq[i] += 1
         N.check(N.lib().fmidx_xchg_round(
-            self.index._h, self._c_mask_tables[i], self._c_inbox_tables[i], self._c_data_flag_table, self._c_ack_flag_table,
-            self._c_flags, self._c_inbox[i], self._c_xlocal[i],
-            self.world, self.rank, self.B, self.vocab, self.seq, self._c_counts[i], sptr))
-        self.last_seq[i] = self.seq
+            self.index._h, self._c_mask_tables[i], self._c_inbox_tables[i], self._c_data_flag_table[i], self._c_ack_flag_table[i],
+            self._c_flags[i], self._c_inbox[i], self._c_xlocal[i],
+            self.world, self.rank, self.B, self.vocab, self.seq[i], self._c_counts[i], sptr))
+        self.last_seq[i] = self.seq[i]
         return self.own_views[i]
 
     def total_counts(self, i):
