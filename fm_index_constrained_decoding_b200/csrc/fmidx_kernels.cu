@@ -183,22 +183,22 @@ __global__ void __launch_bounds__(128) k_step(FmDev ix, const uint64_t *__restri
 
 // =================================================================================================
 // K2: distinct-symbol enumeration of BWT[sp,ep) -> vocab bitmap (+counts), fused with the -inf
-// masking of the beam's logits row.  Two phases:
+// masking of the beam's logits row.
 //
-//  k_mask_top    one warp per range: descend all nibble levels but the last (LT = levels-1) of the matrix
-//                ONCE per range and leave, per range, the dense table of the <= 256 depth-LT nodes
-//                (each covers 4096 symbols = one vocab slice); for the bitmap-only entry point it
-//                also appends the non-empty (range, slice) pairs to a work list, so ranges with a
-//                handful of continuations cost a handful of CTAs instead of vocab/4096.
-//  k_mask_items  persistent CTAs pull (range, slice) items and finish the walk inside the slice;
-//  k_mask_logits one CTA per (beam, slice): issues the slice's logits loads FIRST (registers), then
-//                finishes the walk (its latency overlaps the streaming traffic), ORs the per-shard
+//  k_mask_top    one warp per range.  Bitmap mode: zeroes the mask row; a range of <= 32 rows is finished here (one
+//                lane per row, `levels` access probes + 1 byte load, bit ORed into the row).  Otherwise: descend all
+//                nibble levels but the last (LT = levels-1) ONCE and leave the dense table of the depth-LT nodes (each
+//                covers 4096 symbols); bitmap mode appends the non-empty nodes (b, node, lo, hi) to a work list.
+//  k_mask_expand (bitmap mode) one half-warp per work item: ranks the 16 children at the last nibble level; children
+//                of <= 32 rows are finished right there (all of the warp's small children as ONE flat row list), the
+//                wider ones become byte-level nodes (b, prefix, lo, hi) of a second list.
+//  k_mask_bytes  (bitmap mode) one warp per byte-level node, presence flags in 256 bytes of shared memory, bits ORed
+//                into the mask row by L2 atomics.  No block barrier anywhere in the bitmap pipeline: every warp runs
+//                on its own, so several batches on different streams interleave freely.
+//  k_mask_logits one CTA per (beam, 4096-token slice): issues the slice's logits loads FIRST (registers), then
+//                finishes the walk from the depth-LT table inside the CTA (half-warp per node at the last nibble
+//                level, warp per byte-level node; its latency overlaps the streaming traffic), ORs the per-shard
 //                masks of the other GPUs, applies override / always-allowed tokens, streams out.
-//
-// Inside a slice: if the seed nodes hold <= 32 BWT positions, one warp resolves them by direct
-// per-position access (no tree bookkeeping at all); otherwise a level-synchronous BFS, one
-// half-warp per node (octet 0 loads the cell of lo, octet 1 the cell of hi, lane d evaluates
-// child d), pruned to the slice's symbol interval.  Slices never communicate.
 // =================================================================================================
 constexpr int SLICE = 4096;        // tokens per CTA
 constexpr int MASK_THREADS = 256;   // logits kernels (one CTA per slice)
@@ -354,10 +354,12 @@ __device__ __forceinline__ uint32_t fm_byte_node_presence_wide(const FmDev &ix, 
     return hb | fm_flags_read(cnt, lane);
 }
 
-// Distinct symbols of one byte-level node (positions [lo,hi) of the last level, all sharing `prefix`),
-// by one warp: narrow nodes read their bytes directly; otherwise a 256-bin signed histogram
-//   cnt[v] = hdrB[v] - hdrA[v] - #v in A[0,a) + #v in B[0,b)        (cells A, B of lo and hi)
-// built with shared-memory atomics; lane i then owns the 8 symbols 8i..8i+7.
+// Distinct symbols of one byte-level node (positions [lo,hi) of the last level, all sharing `prefix`), by one warp;
+// lane i owns the 8 symbols 8i..8i+7.  Without counts: presence only, three tiers by width (<= 32 rows: one lane per
+// row; <= 512 rows: flag bytes from a word-granular scan of the rows; wider: header difference of the whole cells in
+// between + scans of the two partial cells).  With counts: a 256-bin signed histogram
+//   cnt[v] = hdrB[v] - hdrA[v] - #v in A[0,a) + #v in B[0,b)        (cells A, B of lo and hi; cheaper side of each)
+// built with shared-memory atomics.
 __device__ __forceinline__ void fm_eval_byte_node(const FmDev &ix, uint32_t lo, uint32_t hi, uint32_t prefix, uint32_t sa,
                                                   uint32_t se, int64_t shift, uint32_t t0, uint32_t *bm, int *cnt,
                                                   uint32_t *__restrict__ counts_row, int lane) {
