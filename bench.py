@@ -567,6 +567,28 @@ def main():
                     _native.check(-1)
                 return
             # N > 1: pinned host prefixes -> device, search + masks + cross-shard exchange, results -> host
+            if px is not None:
+                # pipelined like the N = 1 path: the step's copies, kernels, exchange and result reads are all queued on
+                # the stream of its buffer set; the host only waits for a set's previous results when it reuses the set
+                bi = k % NBUF
+                ks = kstreams[bi]
+                set_done[bi].synchronize()
+                dtok, doff = set_in[bi]
+                rsp, rep, rcnt, rnd = set_out[bi]
+                n = q.numel()
+                with torch.cuda.stream(ks):
+                    dtok[:n].copy_(q, non_blocking=True)
+                    doff.copy_(offs, non_blocking=True)
+                step_full(k, q_off=(dtok[:n], doff))
+                _native.check(L.fmidx_mask_popcount(ix._h, C.c_void_p(result["mask"].data_ptr()), own, VOCAB,
+                                                    C.c_void_p(set_n32[bi].data_ptr()), C.c_void_p(ks.cuda_stream)))
+                with torch.cuda.stream(ks):
+                    rsp.copy_(bufs[bi][0], non_blocking=True)
+                    rep.copy_(bufs[bi][1], non_blocking=True)
+                    rcnt.copy_(result["count"], non_blocking=True)
+                    rnd[:own].copy_(set_n32[bi], non_blocking=True)
+                    set_done[bi].record(ks)
+                return
             dtok = torch.empty(q.numel(), dtype=torch.int32, device=device)
             dtok.copy_(q, non_blocking=True)
             doff = dq[0][1]
@@ -579,6 +601,17 @@ def main():
             hcnt.copy_(result["count"], non_blocking=True)
             hnd[:own].copy_(n32, non_blocking=True)
             torch.cuda.current_stream().synchronize()
+
+        if world > 1 and px is not None:
+            max_tok = max(q.numel() for q, _ in hq)
+            set_in = [(torch.empty(max_tok, dtype=torch.int32, device=device), torch.empty(B + 1, dtype=torch.int64, device=device))
+                      for _ in range(NBUF)]
+            set_out = [(torch.empty(B, dtype=torch.int64).pin_memory(), torch.empty(B, dtype=torch.int64).pin_memory(),
+                        torch.empty(B, dtype=torch.int64).pin_memory(), torch.empty(B, dtype=torch.int32).pin_memory())
+                       for _ in range(NBUF)]
+            set_n32 = [torch.empty(own, dtype=torch.int32, device=device) for _ in range(NBUF)]
+            set_done = [torch.cuda.Event() for _ in range(NBUF)]
+            torch.cuda.synchronize()
 
         for w in range(args.warmup):
             e2e_step(w)
@@ -600,8 +633,9 @@ def main():
                "d2h_bytes_per_step": B * (8 + 8 + 4) if world == 1 else B * 24 + own * 4, "ms_per_step": 1e3 * dt / args.steps,
                "api": "fmidx_query_submit/fmidx_query_wait, %d batches in flight (pinned host prefixes in; ranges + distinct-token "
                       "counts out, every step; masks stay in HBM)" % NSLOT
-                      if world == 1 else "pinned host prefixes -> H2D -> fmidx_search_batch + fmidx_distinct_mask_batch -> all-to-all + "
-                      "fmidx_mask_or + all-reduce -> D2H of ranges, total counts and distinct counts of the owned prefixes"}
+                      if world == 1 else "pinned host prefixes -> H2D -> fmidx_search_batch + fmidx_xchg_local + fmidx_xchg_round (peer-memory "
+                      "exchange) -> D2H of ranges, total counts and distinct counts of the owned prefixes, every step; %d steps in "
+                      "flight, one per buffer set" % NBUF}
 
     # ---- CPU baseline beside the GPU numbers (rank 0, N=1) ---------------------------------------------------
     cpu = None
