@@ -529,6 +529,21 @@ def main():
                "achieved_reference_layout": bytes_search_ref / (t_search * 1e-3) / 1e9,
                "frac_reference_layout": bytes_search_ref / (t_search * 1e-3) / 1e9 / peak}
     dom["frac"] = dom["achieved"] / peak
+    # the rank probes are random accesses, so also measure what this GPU sustains for INDEPENDENT random
+    # 32-B units / aligned 128-B lines over the index's own byte-level cells (fmidx_gather_peak) and relate both
+    # kernels' algorithmic bytes (own layout) to the 128-B figure
+    try:
+        gp = {}
+        for unit in (32, 128):
+            v = C.c_double()
+            _native.check(L.fmidx_gather_peak(ix._h, unit, 1 << 25, C.byref(v)))
+            gp["%dB_GBps" % unit] = v.value
+        dom["random_gather_peak"] = gp
+        dom["frac_of_random_gather_128B"] = dom["achieved"] / gp["128B_GBps"]
+        dom["k_search_achieved_GBps"] = bytes_search / (t_search * 1e-3) / 1e9
+        dom["k_search_frac_of_random_gather_128B"] = dom["k_search_achieved_GBps"] / gp["128B_GBps"]
+    except Exception as e:  # noqa: BLE001 -- a measurement aid must not take the line down
+        dom["random_gather_peak"] = {"error": repr(e)}
     dom["peak_source"] = peak_src
     dom["other_kernel_ms"] = {"k_search": t_search, "k_mask": t_mask}
 

@@ -57,6 +57,7 @@ SIGNATURES = {
     "fmidx_locate_host": (C.c_int, [p, p, sz, p]),
     "fmidx_info": (C.c_int, [p, C.POINTER(u64)]),
     "fmidx_debug_copy_sa": (C.c_int, [p, p, sz]),
+    "fmidx_gather_peak": (C.c_int, [p, C.c_int, sz, C.POINTER(C.c_double)]),
     "fmidx_launch_count": (u64, []),
 }
 

@@ -310,6 +310,11 @@ int fmidx_info(fmidx_t *h, uint64_t info[8]) {
     return FMIDX_OK;
 }
 
+int fmidx_gather_peak(fmidx_t *h, int unit_bytes, size_t n_loads, double *out_gbps) {
+    FM_TRY(enter(h, true));
+    return fm_launch_gather_probe(h, unit_bytes, n_loads, out_gbps, h->stream);
+}
+
 int fmidx_debug_copy_sa(fmidx_t *h, uint32_t *out, size_t cap) {
     FM_TRY(enter(h, true));
     if (h->dev.sa_dens != 1) { fm_set_error("debug_copy_sa needs sa_dens == 1"); return FMIDX_ESTATE; }

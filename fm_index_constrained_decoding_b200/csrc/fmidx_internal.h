@@ -98,6 +98,7 @@ int fm_launch_xchg_publish(fmidx *h, uint32_t *const *d_peer_inbox, uint32_t *co
 int fm_launch_xchg_wait(fmidx *h, const uint32_t *d_flags, uint32_t world, uint32_t seq, cudaStream_t s);
 int fm_launch_xchg_signal(fmidx *h, uint32_t *const *d_peer_flags, uint32_t world, uint32_t rank, uint32_t seq, cudaStream_t s);
 int fm_launch_popcount(fmidx *h, const uint32_t *d_mask, size_t B, uint32_t vocab, uint32_t *d_n, cudaStream_t s);
+int fm_launch_gather_probe(fmidx *h, int unit_bytes, size_t n_loads, double *out_gbps, cudaStream_t s);
 int fm_launch_compact(fmidx *h, const uint32_t *d_mask, const uint32_t *d_counts, size_t B, uint32_t vocab,
                       const uint64_t *d_offs, int64_t *d_tokens, uint64_t *d_cnts, cudaStream_t s);
 int fm_launch_locate(fmidx *h, const uint64_t *d_rows, size_t n, uint64_t *d_pos, cudaStream_t s);

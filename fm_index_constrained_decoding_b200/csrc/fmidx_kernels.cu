@@ -1791,6 +1791,59 @@ int fm_launch_xchg_signal(fmidx *h, uint32_t *const *d_peer_flags, uint32_t worl
     return FMIDX_OK;
 }
 
+// ---- random-gather probe (the roofline the rank probes live under) ---------------------------------
+// Independent pseudo-random loads over the byte-level cells (>= 3 bytes per token, far larger than L2): each lane
+// reads 32 B of its own random 32-B unit (UNIT = 32), or the 8 lanes of an octet read one random aligned 128-B line
+// (UNIT = 128, the shape of a nibble-cell probe).  Addresses never depend on loaded data, so this is the memory
+// system's random-access throughput, not its latency.
+template <int UNIT>
+__global__ void __launch_bounds__(256) k_gather_probe(const uint4 *__restrict__ base, unsigned long long n_units,
+                                                      uint32_t loads_per_thread, uint32_t *__restrict__ sink) {
+    const uint32_t tid = blockIdx.x * 256u + threadIdx.x;
+    unsigned long long x = (unsigned long long)(UNIT == 128 ? (tid >> 3) : tid) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    uint32_t acc = 0;
+#pragma unroll 8
+    for (uint32_t i = 0; i < loads_per_thread; ++i) {
+        x = x * 6364136223846793005ull + 1442695040888963407ull;
+        const unsigned long long u = __umul64hi(x, n_units);
+        if (UNIT == 128) {
+            acc ^= fm_ldg(base + u * 8ull + (tid & 7u)).x;
+        } else {
+            const uint4 a = fm_ldg(base + u * 2ull), b = fm_ldg(base + u * 2ull + 1ull);
+            acc ^= a.x ^ b.w;
+        }
+    }
+    if (acc == 0x5EED5EEDu) *sink = acc;  // keeps the loads alive
+}
+
+int fm_launch_gather_probe(fmidx *h, int unit_bytes, size_t n_loads, double *out_gbps, cudaStream_t s) {
+    FM_TRY(check_ready(h));
+    if ((unit_bytes != 32 && unit_bytes != 128) || !out_gbps || n_loads == 0) { fm_set_error("gather_peak: unit must be 32 or 128"); return FMIDX_EINVAL; }
+    const unsigned long long n_units = (unsigned long long)h->dev.nbblocks * (FMIDX_BCELL_U4 * 16) / (unsigned)unit_bytes;
+    if (n_units == 0) { fm_set_error("index too small"); return FMIDX_ESTATE; }
+    const unsigned grid = (unsigned)h->sm_count * 16u;
+    const size_t lanes_per_load = unit_bytes == 128 ? 8 : 1, threads = (size_t)grid * 256;
+    const uint32_t per_thread = (uint32_t)std::max<size_t>(1, n_loads * lanes_per_load / threads);
+    FM_TRY(fm_scratch(h, h->d_scratch[0], 64, false));
+    cudaEvent_t e0, e1;
+    FM_CUDA(cudaEventCreate(&e0));
+    FM_CUDA(cudaEventCreate(&e1));
+    for (int rep = 0; rep < 2; ++rep) {  // first launch warms up
+        FM_CUDA(cudaEventRecord(e0, s));
+        if (unit_bytes == 128) FM_LAUNCH(k_gather_probe<128>, grid, 256, 0, s, h->dev.bcells, n_units, per_thread, (uint32_t *)h->d_scratch[0].p);
+        else FM_LAUNCH(k_gather_probe<32>, grid, 256, 0, s, h->dev.bcells, n_units, per_thread, (uint32_t *)h->d_scratch[0].p);
+        FM_CUDA(cudaEventRecord(e1, s));
+    }
+    FM_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    FM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double loads = (double)per_thread * (double)threads / (double)lanes_per_load;
+    *out_gbps = loads * unit_bytes / (ms * 1e-3) / 1e9;
+    return FMIDX_OK;
+}
+
 int fm_launch_popcount(fmidx *h, const uint32_t *d_mask, size_t B, uint32_t vocab, uint32_t *d_n, cudaStream_t s) {
     (void)h;
     if (B == 0) return FMIDX_OK;

@@ -102,7 +102,8 @@ int fmidx_distinct_mask_batch(fmidx_t *h, const uint64_t *d_sp, const uint64_t *
  * `get_distinct_count` do per beam in document_constrained_generation_vllm.py:72-137), d_sp/d_ep and d_mask as
  * in those two calls (d_mask NULL or vocab 0: ranges only).  ws_slot (0..7) selects the scratch workspace the
  * enumeration uses: calls that may run concurrently on DIFFERENT streams must use different slots, calls that
- * share a slot must be stream-ordered. */
+ * share a slot must be stream-ordered.  The slots are the ones fmidx_query_submit uses: do not mix the two on one
+ * slot number. */
 int fmidx_query_batch(fmidx_t *h, int ws_slot, const int32_t *d_toks, const int64_t *d_offs, size_t B, int64_t shift,
                       uint32_t vocab, uint64_t *d_sp, uint64_t *d_ep, uint32_t *d_mask, void *stream);
 /* same, additionally filling d_occ ([B][ceil(nslices/32)] u32, nslices = ceil(vocab/4096)): bit s of a row is set
@@ -204,6 +205,10 @@ int fmidx_info(fmidx_t *h, uint64_t info[8]);
 /* copy the suffix array / BWT of the last build to the host (testing the builder); the SA is
  * only available when sa_dens == 1 */
 int fmidx_debug_copy_sa(fmidx_t *h, uint32_t *out, size_t cap);
+/* Measurement aid (SURVEY.md 8(d) "random-gather peak"): n_loads independent random loads of unit_bytes (32: one
+ * lane per 32-B unit; 128: one octet per aligned 128-B line) over this index's byte-level cells; *out_gbps receives
+ * n_loads * unit_bytes / time.  Synchronous, on the handle's private stream.  No reference counterpart. */
+int fmidx_gather_peak(fmidx_t *h, int unit_bytes, size_t n_loads, double *out_gbps);
 /* number of kernels this library has launched in this process (bench.py gpu_launches) */
 uint64_t fmidx_launch_count(void);
 

@@ -514,3 +514,16 @@ def test_query_batch_two_streams(cuda):
             sp, ep, mask = outs[k]
             assert (sp.cpu().numpy().astype(np.uint64) == sp_o).all() and (ep.cpu().numpy().astype(np.uint64) == ep_o).all()
             assert (mask.cpu().numpy().view(np.uint32) == m_o).all()
+
+
+def test_gather_peak_probe(cuda):
+    """fmidx_gather_peak (measurement aid): runs on a small index and returns a positive rate."""
+    from fm_index_constrained_decoding_b200 import _native
+    rng = random.Random(5)
+    ix = make(random_docs(rng, 5000, 200, 50, 400))
+    for unit in (32, 128):
+        v = C.c_double()
+        _native.check(_native.lib().fmidx_gather_peak(ix._h, unit, 1 << 20, C.byref(v)))
+        assert v.value > 0.0
+    with pytest.raises(_native.FmidxError):
+        _native.check(_native.lib().fmidx_gather_peak(ix._h, 64, 1 << 20, C.byref(C.c_double())))
