@@ -1792,25 +1792,38 @@ int fm_launch_xchg_signal(fmidx *h, uint32_t *const *d_peer_flags, uint32_t worl
 }
 
 // ---- random-gather probe (the roofline the rank probes live under) ---------------------------------
-// Independent pseudo-random loads over the byte-level cells (>= 3 bytes per token, far larger than L2): each lane
-// reads 32 B of its own random 32-B unit (UNIT = 32), or the 8 lanes of an octet read one random aligned 128-B line
-// (UNIT = 128, the shape of a nibble-cell probe).  Addresses never depend on loaded data, so this is the memory
-// system's random-access throughput, not its latency.
+// Independent pseudo-random loads over ALL of the index's large arrays taken as one address space (nibble cells,
+// byte cells and -- resident layout -- SA, ISA, text: 18 B per token, >= 14 x L2 at 100 M tokens): each lane reads its
+// own random 32-B unit (UNIT = 32), or the 8 lanes of an octet read one random aligned 128-B line (UNIT = 128, the
+// shape of a nibble-cell probe).  Addresses never depend on loaded data, so this is the memory system's random-access
+// throughput, not its latency.
+struct GatherBufs {
+    const uint4 *base[5];
+    unsigned long long cum[5];  // inclusive prefix sums of the buffers' unit counts
+    int n;
+};
+
 template <int UNIT>
-__global__ void __launch_bounds__(256) k_gather_probe(const uint4 *__restrict__ base, unsigned long long n_units,
-                                                      uint32_t loads_per_thread, uint32_t *__restrict__ sink) {
+__global__ void __launch_bounds__(256) k_gather_probe(GatherBufs g, uint32_t loads_per_thread, uint32_t *__restrict__ sink) {
     const uint32_t tid = blockIdx.x * 256u + threadIdx.x;
     unsigned long long x = (unsigned long long)(UNIT == 128 ? (tid >> 3) : tid) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    const unsigned long long total = g.cum[g.n - 1];
     uint32_t acc = 0;
-#pragma unroll 8
+#pragma unroll 4
     for (uint32_t i = 0; i < loads_per_thread; ++i) {
         x = x * 6364136223846793005ull + 1442695040888963407ull;
-        const unsigned long long u = __umul64hi(x, n_units);
+        unsigned long long u = __umul64hi(x, total);
+        int j = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (k + 1 < g.n && u >= g.cum[k]) j = k + 1;
+        if (j) u -= g.cum[j - 1];
+        const uint4 *b = g.base[j];
         if (UNIT == 128) {
-            acc ^= fm_ldg(base + u * 8ull + (tid & 7u)).x;
+            acc ^= fm_ldg(b + u * 8ull + (tid & 7u)).x;
         } else {
-            const uint4 a = fm_ldg(base + u * 2ull), b = fm_ldg(base + u * 2ull + 1ull);
-            acc ^= a.x ^ b.w;
+            const uint4 v0 = fm_ldg(b + u * 2ull), v1 = fm_ldg(b + u * 2ull + 1ull);
+            acc ^= v0.x ^ v1.w;
         }
     }
     if (acc == 0x5EED5EEDu) *sink = acc;  // keeps the loads alive
@@ -1819,8 +1832,20 @@ __global__ void __launch_bounds__(256) k_gather_probe(const uint4 *__restrict__ 
 int fm_launch_gather_probe(fmidx *h, int unit_bytes, size_t n_loads, double *out_gbps, cudaStream_t s) {
     FM_TRY(check_ready(h));
     if ((unit_bytes != 32 && unit_bytes != 128) || !out_gbps || n_loads == 0) { fm_set_error("gather_peak: unit must be 32 or 128"); return FMIDX_EINVAL; }
-    const unsigned long long n_units = (unsigned long long)h->dev.nbblocks * (FMIDX_BCELL_U4 * 16) / (unsigned)unit_bytes;
-    if (n_units == 0) { fm_set_error("index too small"); return FMIDX_ESTATE; }
+    const FmDev &ix = h->dev;
+    GatherBufs g{};
+    auto add = [&](const void *p, unsigned long long bytes) {
+        if (!p || ((uintptr_t)p & 127u) || bytes < 128 || g.n >= 5) return;
+        g.base[g.n] = (const uint4 *)p;
+        g.cum[g.n] = (g.n ? g.cum[g.n - 1] : 0ull) + bytes / (unsigned)unit_bytes;
+        ++g.n;
+    };
+    add(ix.cells, (unsigned long long)ix.levels * ix.level_stride * 16ull);
+    add(ix.bcells, (unsigned long long)ix.nbblocks * (FMIDX_BCELL_U4 * 16));
+    if (ix.sa_dens == 1) add(ix.sa_samples, (unsigned long long)ix.n * 4ull);
+    if (ix.isa_dens == 1) add(ix.isa_samples, (unsigned long long)ix.n * 4ull);
+    add(ix.text, (unsigned long long)ix.n * 4ull);
+    if (g.n == 0) { fm_set_error("index too small"); return FMIDX_ESTATE; }
     const unsigned grid = (unsigned)h->sm_count * 16u;
     const size_t lanes_per_load = unit_bytes == 128 ? 8 : 1, threads = (size_t)grid * 256;
     const uint32_t per_thread = (uint32_t)std::max<size_t>(1, n_loads * lanes_per_load / threads);
@@ -1830,8 +1855,8 @@ int fm_launch_gather_probe(fmidx *h, int unit_bytes, size_t n_loads, double *out
     FM_CUDA(cudaEventCreate(&e1));
     for (int rep = 0; rep < 2; ++rep) {  // first launch warms up
         FM_CUDA(cudaEventRecord(e0, s));
-        if (unit_bytes == 128) FM_LAUNCH(k_gather_probe<128>, grid, 256, 0, s, h->dev.bcells, n_units, per_thread, (uint32_t *)h->d_scratch[0].p);
-        else FM_LAUNCH(k_gather_probe<32>, grid, 256, 0, s, h->dev.bcells, n_units, per_thread, (uint32_t *)h->d_scratch[0].p);
+        if (unit_bytes == 128) FM_LAUNCH(k_gather_probe<128>, grid, 256, 0, s, g, per_thread, (uint32_t *)h->d_scratch[0].p);
+        else FM_LAUNCH(k_gather_probe<32>, grid, 256, 0, s, g, per_thread, (uint32_t *)h->d_scratch[0].p);
         FM_CUDA(cudaEventRecord(e1, s));
     }
     FM_CUDA(cudaEventSynchronize(e1));

@@ -206,7 +206,8 @@ int fmidx_info(fmidx_t *h, uint64_t info[8]);
  * only available when sa_dens == 1 */
 int fmidx_debug_copy_sa(fmidx_t *h, uint32_t *out, size_t cap);
 /* Measurement aid (SURVEY.md 8(d) "random-gather peak"): n_loads independent random loads of unit_bytes (32: one
- * lane per 32-B unit; 128: one octet per aligned 128-B line) over this index's byte-level cells; *out_gbps receives
+ * lane per 32-B unit; 128: one octet per aligned 128-B line) over this index's large arrays (cells, and SA / ISA /
+ * text when resident) taken as one address space; *out_gbps receives
  * n_loads * unit_bytes / time.  Synchronous, on the handle's private stream.  No reference counterpart. */
 int fmidx_gather_peak(fmidx_t *h, int unit_bytes, size_t n_loads, double *out_gbps);
 /* number of kernels this library has launched in this process (bench.py gpu_launches) */
