@@ -90,3 +90,173 @@ class IndexBasedLogitsProcessor:
             count = torch.where(finished, zero, pep - psp)
             override[count <= self.stop_at_count] = eos  # checked first in the reference, vllm.py:105-108
         return ix.mask_logits(sp, ep, scores, out=torch.empty_like(scores), override_tok=override, always_allow=allow)
+
+
+class SoftBoostLogitsProcessor:
+    """The reference's soft-boost ("causal") processors over the batched GPU path:
+
+      variant "causal": document_constrained_generation_causal.py:7-180
+      variant "qwen"  : document_constrained_generation_causal_qwen.py:7-214 (thinking prefix, min_new_tokens)
+
+    out = scores + mask, mask = 0 everywhere except, per row whose trailing corpus n-gram `s` is non-empty,
+    BOOST * factor**len(s) on the tokens that continue `s` in the corpus and BOOST/2 on the other corpus unigrams
+    (qwen: BOOST when nothing continues `s`); rows without a trailing n-gram get BOOST on every corpus unigram; EOS is
+    boosted by BOOST * factor**generated_length (qwen: only after min_new_tokens and only for rows that finished
+    thinking).  Reference behaviours kept as written: the trailing-n-gram search only ever looks up the LAST token
+    (causal.py:68-73 returns inside the first loop iteration), override rows ({eos} under stop_at_count, {pad} after
+    eos/pad), `count` is the count of the n-gram itself.
+
+    One step = host bookkeeping on the token lists, ONE batched search (2 queries per row: the last token and the
+    whole n-gram), ONE enumeration launch group for all rows, and elementwise tensor ops in the dtype of `scores`
+    (so the additions round exactly like the reference's `scores + mask`).  Every row must contain the chat-template
+    end marker exactly once (the only case in which the reference's own row bookkeeping is well defined).
+    """
+    END_MARKERS = {"qwen": [151645, 198, 151644, 77091, 198], "llama": [78191, 128007, 271]}
+    THINK_PREFIX = [151667, 271, 151668, 271]
+    THINK_DONE = (151668, 271)
+
+    def __init__(self, index, num_beams, variant="causal", model_name="llama", min_new_tokens=5, pad_token_id=0,
+                 eos_token_id=2, force_decoding_from=None, stop_at_count=0, always_allow_eos=False,
+                 forced_bos_token_id=None, length_reward_factor=2.0, end_marker=None):
+        assert variant in ("causal", "qwen")
+        self.index = index
+        self._num_beams = num_beams
+        self.variant = variant
+        self.min_new_tokens = min_new_tokens
+        self.pad_token_id = pad_token_id
+        self.eos_token_id = eos_token_id
+        self.force_decoding_from = force_decoding_from
+        self.stop_at_count = stop_at_count
+        self.always_allow_eos = always_allow_eos
+        self.forced_bos_token_id = forced_bos_token_id
+        self.length_reward_factor = length_reward_factor
+        self.BOOST = 10.0
+        if end_marker is not None:
+            self.end_marker = list(end_marker)
+        elif variant == "qwen" or str(model_name).lower().startswith("qwen"):
+            self.end_marker = self.END_MARKERS["qwen"]
+        else:
+            self.end_marker = self.END_MARKERS["llama"]
+        self._unigrams = {}  # (device, V) -> bool [V]
+
+    def __call__(self, input_ids, scores):
+        return self._process(input_ids, scores)
+
+    # ---- host bookkeeping (token lists) ----------------------------------------------------------------------------
+    def _after_end_marker(self, rows):
+        m, marker, out = len(self.end_marker), self.end_marker, []
+        for row in rows:
+            hits = [i for i in range(len(row) - m + 1) if row[i:i + m] == marker]
+            if len(hits) != 1:
+                raise ValueError("every row of input_ids must contain the end marker exactly once")
+            out.append(row[hits[0] + m:])
+        return out
+
+    def _candidate(self, row):
+        """None: row is skipped (qwen: still thinking); otherwise the sequence whose last token decides between
+        'no trailing n-gram' and 'the whole sequence is the n-gram'."""
+        if self.variant == "causal":
+            return row
+        if not (len(row) >= 2 and any((row[i], row[i + 1]) == self.THINK_DONE for i in range(len(row) - 1))):
+            return None
+        k = len(self.THINK_PREFIX)
+        if len(row) < k:
+            return [] if row == self.THINK_PREFIX[:len(row)] else row
+        return row[k:] if row[:k] == self.THINK_PREFIX else row
+
+    def _unigram_mask(self, device, V):
+        key = (str(device), V)
+        if key not in self._unigrams:
+            u = torch.zeros(V, dtype=torch.bool)
+            toks = [t for t in self.index.occurring_distinct if 0 <= t < V]
+            u[torch.tensor(toks, dtype=torch.long)] = True
+            self._unigrams[key] = u.to(device)
+        return self._unigrams[key]
+
+    # ---- the step ----------------------------------------------------------------------------------------------------
+    def _process(self, input_ids, scores):
+        rows = self._after_end_marker(input_ids.tolist() if torch.is_tensor(input_ids) else [list(r) for r in input_ids])
+        R, V = scores.shape
+        dev, dt = scores.device, scores.dtype
+        eos, pad, BOOST = self.eos_token_id, self.pad_token_id, self.BOOST
+        mask = torch.zeros_like(scores)
+        if self.variant == "causal" and self.forced_bos_token_id is not None:
+            if len(rows[0]) == 0:
+                mask[:, self.forced_bos_token_id] = BOOST
+                return scores + mask
+            rows = [r[1:] for r in rows]
+        width = len(rows[0])
+        unig = self._unigram_mask(dev, V)
+        col = torch.arange(V, device=dev)
+        if width == 0:
+            if self.variant == "causal":
+                mask = torch.where(unig.unsqueeze(0), torch.tensor(BOOST, dtype=dt, device=dev), mask)
+                if self.always_allow_eos:
+                    mask[:, eos] = BOOST
+            return scores + mask
+        cands = [self._candidate(r) for r in rows]
+        force = list(self.force_decoding_from) if self.force_decoding_from is not None else []
+        # two queries per row: [last token] and force + candidate (dummy empty queries where there is no candidate)
+        queries = [[c[-1]] if c else [] for c in cands] + [force + c if c else [] for c in cands]
+        toks, offs = ragged(queries)
+        sp2, ep2 = self.index.get_range_batch(torch.from_numpy(toks).to(dev), torch.from_numpy(offs).to(dev))
+        skip = torch.tensor([c is None for c in cands], device=dev)
+        has = torch.tensor([bool(c) for c in cands], device=dev)
+        fin_last = torch.tensor([bool(c) and c[-1] in (eos, pad) for c in cands], device=dev)
+        length = torch.tensor([len(c) if c else 0 for c in cands], device=dev)
+        ngram = has & ((ep2[:R] - sp2[:R]) > 0)   # the last token occurs in the corpus -> the n-gram is the whole candidate
+        zero = torch.zeros_like(sp2[:R])
+        live = ngram & ~fin_last
+        sp, ep = torch.where(live, sp2[R:], zero), torch.where(live, ep2[R:], zero)
+        words = self.index.distinct_mask_batch(sp, ep, V)
+        sh = torch.arange(32, device=dev, dtype=words.dtype)
+        D = ((words.unsqueeze(-1) >> sh) & 1).bool().view(R, -1)[:, :V]
+        if self.stop_at_count > 0:
+            ov_eos = ngram & ((ep - sp) <= self.stop_at_count)
+        else:
+            ov_eos = torch.zeros_like(ngram)
+        ov_pad = ngram & ~ov_eos & fin_last
+        D = torch.where(ov_eos.unsqueeze(1), (col == eos).unsqueeze(0), D)
+        D = torch.where(ov_pad.unsqueeze(1), (col == pad).unsqueeze(0), D)
+        # boosts are computed as Python floats (like the reference) and only then cast to the dtype of `scores`
+        f = self.length_reward_factor
+        table = torch.tensor([BOOST * (f ** n) for n in range(width + len(self.THINK_PREFIX) + 1)], dtype=torch.float64).to(dt).to(dev)
+        b_len = table[length]
+        full, half = torch.tensor(BOOST, dtype=dt, device=dev), torch.tensor(BOOST / 2, dtype=dt, device=dev)
+        if self.variant == "qwen":
+            add = torch.where(D.any(1), half, full)
+        else:
+            add = half.expand(R)
+        z = torch.zeros((), dtype=dt, device=dev)
+        m_ngram = torch.where(D, b_len.unsqueeze(1), torch.where(unig.unsqueeze(0), add.unsqueeze(1), z))
+        m_uni = torch.where(unig, full, z).unsqueeze(0)
+        mask = torch.where(ngram.unsqueeze(1), m_ngram, torch.where(skip.unsqueeze(1), z, m_uni))
+        if self.always_allow_eos:
+            e = torch.tensor(BOOST * (f ** width), dtype=torch.float64).to(dt).to(dev)
+            if self.variant == "causal":
+                mask[:, eos] = e
+            elif width >= self.min_new_tokens:
+                mask[:, eos] = torch.where(skip, mask[:, eos], e)
+        return scores + mask
+
+
+class CausalIndexBasedLogitsProcessor(SoftBoostLogitsProcessor):
+    """Constructor of document_constrained_generation_causal.py:8-20."""
+
+    def __init__(self, index, num_beams, model_name, pad_token_id=0, eos_token_id=2, force_decoding_from=None,
+                 stop_at_count=0, always_allow_eos=False, forced_bos_token_id=None, length_reward_factor=2.0):
+        super().__init__(index, num_beams, variant="causal", model_name=model_name, pad_token_id=pad_token_id,
+                         eos_token_id=eos_token_id, force_decoding_from=force_decoding_from, stop_at_count=stop_at_count,
+                         always_allow_eos=always_allow_eos, forced_bos_token_id=forced_bos_token_id,
+                         length_reward_factor=length_reward_factor)
+
+
+class QwenIndexBasedLogitsProcessor(SoftBoostLogitsProcessor):
+    """Constructor of document_constrained_generation_causal_qwen.py:8-20."""
+
+    def __init__(self, index, num_beams, min_new_tokens=5, pad_token_id=0, eos_token_id=2, force_decoding_from=None,
+                 stop_at_count=0, always_allow_eos=False, forced_bos_token_id=None, length_reward_factor=2.0):
+        super().__init__(index, num_beams, variant="qwen", min_new_tokens=min_new_tokens, pad_token_id=pad_token_id,
+                         eos_token_id=eos_token_id, force_decoding_from=force_decoding_from, stop_at_count=stop_at_count,
+                         always_allow_eos=always_allow_eos, forced_bos_token_id=forced_bos_token_id,
+                         length_reward_factor=length_reward_factor)

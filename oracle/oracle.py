@@ -282,3 +282,115 @@ def hard_mask_reference(index, input_ids_rows, scores, num_beams, eos_token_id, 
     if always_allow_eos:
         mask[:, eos_token_id] = BOOST
     return scores + mask
+
+
+# ---- soft-boost ("causal") processors -------------------------------------------------------------------------
+END_MARKERS = {"qwen": [151645, 198, 151644, 77091, 198], "llama": [78191, 128007, 271]}   # causal.py:40-41
+THINK_PREFIX = [151667, 271, 151668, 271]                                                   # causal_qwen.py:60
+THINK_DONE = (151668, 271)                                                                  # causal_qwen.py:76
+
+
+def _strip_end_marker(rows, marker):
+    """causal.py:48-60 / causal_qwen.py:45-57: everything after the chat-template end marker; the reference appends one
+    result per OCCURRENCE and stacks them, which only lines up with the score rows when each row holds the marker
+    exactly once -- that is the supported case here."""
+    out = []
+    m = len(marker)
+    for row in rows:
+        hits = [i for i in range(len(row) - m + 1) if list(row[i:i + m]) == list(marker)]
+        if len(hits) != 1:
+            raise ValueError("every row must contain the end marker exactly once")
+        out.append(list(row[hits[0] + m:]))
+    return out
+
+
+def _trailing_ngram(index, sent):
+    """causal.py:62-73 as written: the loop returns on its first iteration, so only the LAST token is looked up --
+    absent from the corpus -> [], otherwise the whole sequence.  Empty input falls off the loop -> None."""
+    for ind in range(len(sent) - 1, -1, -1):
+        if index.get_count(sent[ind:]) == 0:
+            return sent[ind + 1:]
+        return sent
+    return None
+
+
+def soft_boost_reference(index, input_ids_rows, scores, num_beams, variant, eos_token_id, pad_token_id,
+                         end_marker, stop_at_count=0, always_allow_eos=False, force_decoding_from=None,
+                         forced_bos_token_id=None, length_reward_factor=2.0, min_new_tokens=5, boost=10.0):
+    """document_constrained_generation_causal.py:75-180 (variant "causal") and
+    document_constrained_generation_causal_qwen.py:100-214 (variant "qwen") restated row by row.
+    input_ids_rows: B*beams equal-length token lists INCLUDING the prompt and its end marker."""
+    import torch
+
+    rows = _strip_end_marker(input_ids_rows, end_marker)
+    mask = torch.full_like(scores, 0.0)
+    if variant == "causal" and forced_bos_token_id is not None:          # causal.py:80-85
+        if len(rows[0]) == 0:
+            mask[:, forced_bos_token_id] = boost
+            return scores + mask
+        rows = [r[1:] for r in rows]
+    width = len(rows[0])
+    unig = list(index.occurring_distinct)
+    if width == 0:
+        if variant == "causal":                                          # causal.py:87-91
+            mask[:, torch.LongTensor(unig)] = boost
+        # causal_qwen.py:105: nothing happens for an empty continuation (not even the eos rule)
+    else:
+        if variant == "qwen":                                            # causal_qwen.py:107-112
+            def think_done(s):
+                return len(s) >= 2 and any((s[i], s[i + 1]) == THINK_DONE for i in range(len(s) - 1))
+
+            def strip_prefix(s):
+                k = len(THINK_PREFIX)
+                if len(s) < k:
+                    return [] if s == THINK_PREFIX[:len(s)] else s
+                return s[k:] if s[:k] == THINK_PREFIX else s
+
+            sents = []
+            for r in rows:
+                if not think_done(r):
+                    sents.append(None)
+                    continue
+                s = strip_prefix(r)
+                sents.append([] if s == [] else _trailing_ngram(index, s))
+        else:
+            sents = [_trailing_ngram(index, r) for r in rows]            # causal.py:100
+        lows, highs, counts, which = [], [], [], []
+        for i, s in enumerate(sents):
+            if s:                                                        # causal.py:104-123
+                if s[-1] in (eos_token_id, pad_token_id):
+                    lo, hi, cnt = 0, 0, 0
+                else:
+                    q = (force_decoding_from or []) + s if force_decoding_from is not None else s
+                    lo, hi = index.get_range(q)
+                    cnt = index.get_count(q)
+                lows.append(lo)
+                highs.append(hi)
+                counts.append(cnt)
+                which.append(i)
+        res = dict(zip(which, index.get_distinct_count_multi(lows, highs)))
+        cnt_of = dict(zip(which, counts))
+        for i, s in enumerate(sents):
+            if variant == "qwen" and s is None:
+                continue
+            if not s:                                                    # causal.py:137-140
+                mask[i, torch.LongTensor(unig)] = boost
+            else:
+                if stop_at_count > 0 and cnt_of[i] <= stop_at_count:     # causal.py:144-160
+                    distinct = [eos_token_id]
+                elif s[-1] == eos_token_id or s[-1] == pad_token_id:
+                    distinct = [pad_token_id]
+                else:
+                    distinct = list(res[i][0])
+                dset = set(distinct)
+                extra = [u for u in unig if u not in dset]
+                mask[i, torch.LongTensor(distinct)] = boost * (length_reward_factor ** len(s))
+                if variant == "qwen":                                    # causal_qwen.py:200-205
+                    mask[i, torch.LongTensor(extra)] = boost if len(distinct) == 0 else boost / 2
+                else:                                                    # causal.py:171
+                    mask[i, torch.LongTensor(extra)] = boost / 2
+            if variant == "qwen" and always_allow_eos and width >= min_new_tokens:   # causal_qwen.py:207-212
+                mask[i, eos_token_id] = boost * (length_reward_factor ** width)
+    if variant == "causal" and always_allow_eos:                         # causal.py:173-178
+        mask[:, eos_token_id] = boost * (length_reward_factor ** width)
+    return scores + mask

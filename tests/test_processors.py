@@ -92,3 +92,39 @@ def test_forced_bos(cuda):
     got = proc.process_batch(h, s.cuda())
     exp = hard_mask_reference(o, [x[1:] for x in h], s, 1, EOS, PAD, 0, True)
     assert same(got, exp)
+
+
+@pytest.mark.parametrize("variant", ["causal", "qwen"])
+def test_soft_boost_on_gpu(cuda, variant):
+    """Soft-boost processors (causal.py / causal_qwen.py semantics) over the real index: search + enumeration on
+    the GPU, boosts added in the dtype of the scores; bit-exact against the row-by-row restatement."""
+    from fm_index_constrained_decoding_b200.processors import CausalIndexBasedLogitsProcessor, QwenIndexBasedLogitsProcessor
+    from oracle.oracle import soft_boost_reference
+    rng, docs, ix, o = setup(33)
+    think = [151667, 271, 151668, 271]
+    marker = [151645, 198, 151644, 77091, 198] if variant == "qwen" else [78191, 128007, 271]
+    width, n = 6, 24
+    rows = []
+    for k in range(n):
+        d = rng.choice(docs)
+        i = rng.randrange(0, len(d) - width)
+        c = d[i:i + width]
+        if k % 6 == 1:
+            c = c[:-1] + [EOS]
+        if k % 6 == 2:
+            c = c[:-1] + [PAD]
+        if k % 6 == 3:
+            c = c[:-1] + [4500]  # not in the corpus
+        if variant == "qwen":
+            c = (think[:2] + c + [5, 6]) if k % 6 == 4 else (think + c)
+        rows.append([rng.randrange(4000) for _ in range(5)] + marker + c)
+    g = torch.Generator().manual_seed(9)
+    for dtype in (torch.float32, torch.bfloat16):
+        scores = torch.randn(n, V, generator=g).to(dtype)
+        if variant == "causal":
+            proc = CausalIndexBasedLogitsProcessor(ix, 4, "llama", pad_token_id=PAD, eos_token_id=EOS, stop_at_count=2, always_allow_eos=True)
+        else:
+            proc = QwenIndexBasedLogitsProcessor(ix, 4, min_new_tokens=3, pad_token_id=PAD, eos_token_id=EOS, stop_at_count=2, always_allow_eos=True)
+        got = proc(torch.tensor(rows), scores.cuda())
+        exp = soft_boost_reference(o, rows, scores, 4, variant, EOS, PAD, marker, 2, True, None, None, 2.0, 3)
+        assert got.dtype == dtype and torch.equal(got.cpu(), exp)
