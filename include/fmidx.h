@@ -14,6 +14,9 @@
  *   - rows / positions are uint64_t at the ABI like the reference's `unsigned long`
  *     (fm_index.hpp:16-18); one index holds fewer than 2^32 symbols (shard larger corpora).
  *   - there is NO CPU fallback: without a CUDA device every call fails with FMIDX_ECUDA.
+ *   - a handle is used by ONE host thread at a time (like the reference object under the GIL); work is
+ *     made concurrent on the DEVICE: device entry points that take a ws_slot / slot may be in flight on different
+ *     streams at once, the ones without share one scratch workspace and must be stream-ordered with each other.
  */
 #ifndef FMIDX_H
 #define FMIDX_H
