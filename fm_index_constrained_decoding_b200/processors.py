@@ -54,7 +54,7 @@ class IndexBasedLogitsProcessor:
     def process_batch(self, histories, scores):
         """histories: B token lists (all of the same length in the reference's use); scores [B, V]."""
         ix = self.index
-        assert scores.is_cuda, "scores must live on the GPU that holds the index"
+        assert scores.is_cuda or not isinstance(ix, FMIndex), "scores must live on the GPU that holds the index"
         B, V = scores.shape
         dev = scores.device
         scores = scores.contiguous()
