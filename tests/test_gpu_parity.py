@@ -527,3 +527,20 @@ def test_gather_peak_probe(cuda):
         assert v.value > 0.0
     with pytest.raises(_native.FmidxError):
         _native.check(_native.lib().fmidx_gather_peak(ix._h, 64, 1 << 20, C.byref(C.c_double())))
+
+
+def test_build_index_cli_roundtrip(cuda, tmp_path):
+    """build_index (reference build_fm_index.py command line): TSV -> index files -> load -> same answers as an index
+    initialised from the same token lists."""
+    from fm_index_constrained_decoding_b200 import FMIndex, build_index as bi
+    tsv = tmp_path / "c.tsv"
+    tsv.write_text("".join("%d\tT%d\tdoc %d says hello world number %d again hello\n" % (i, i, i % 3, i % 5) for i in range(12)),
+                   encoding="utf-8")
+    bi.main([str(tsv), str(tmp_path / "idx"), "--standin_tokenizer", "--include_title"])
+    ix = FMIndex.load(str(tmp_path / "idx"))
+    docs = [bi.standin_encode(t) for _, t in bi.iter_documents(str(tsv), include_title=True)]
+    ref = make(docs)
+    assert ix.labels == [str(i) for i in range(12)] and len(ix) == len(ref) and ix.beginnings == ref.beginnings
+    for q in (docs[0][:1], docs[0][1:3], docs[5][2:6], [123]):
+        assert ix.get_range(q) == ref.get_range(q)
+        assert ix.get_distinct_count(*ix.get_range(q)) == ref.get_distinct_count(*ref.get_range(q))
