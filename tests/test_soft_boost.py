@@ -129,3 +129,49 @@ def test_end_marker_must_be_unique():
     proc = CausalIndexBasedLogitsProcessor(OracleBackedIndex(o), 1, "llama")
     with pytest.raises(ValueError):
         proc(torch.tensor([[1, 2, 3, 4, 5, 6]]), torch.zeros(1, V))
+
+
+def test_random_histories_property():
+    """Randomised comparison (hypothesis): any mix of corpus n-grams, unknown tokens, EOS / PAD endings, thinking
+    prefixes and parameters gives exactly the reference's scores."""
+    from hypothesis import given, settings, strategies as st
+    from fm_index_constrained_decoding_b200.processors import SoftBoostLogitsProcessor
+    from oracle.oracle import soft_boost_reference
+    rng0, docs, o = corpus(8)
+    ix = OracleBackedIndex(o)
+    tok = st.one_of(st.integers(0, 1999), st.sampled_from([EOS, PAD, ABSENT, 271, 151668, 151667]))
+
+    @st.composite
+    def case(draw):
+        variant = draw(st.sampled_from(["causal", "qwen"]))
+        width = draw(st.integers(0, 8))
+        n = draw(st.integers(1, 5))
+        rows = []
+        for _ in range(n):
+            kind = draw(st.integers(0, 3))
+            if kind == 0 and width:
+                d = docs[draw(st.integers(0, len(docs) - 1))]
+                i = draw(st.integers(0, max(0, len(d) - width)))
+                c = (d[i:i + width] + [EOS] * width)[:width]
+            else:
+                c = [draw(tok) for _ in range(width)]
+            if variant == "qwen" and width >= 4 and draw(st.booleans()):
+                c = (THINK + c)[:width]
+            rows.append(c)
+        return (variant, rows, draw(st.integers(0, 3)), draw(st.booleans()), draw(st.integers(0, 6)),
+                draw(st.sampled_from([1.5, 2.0])), draw(st.integers(0, 2 ** 31)))
+
+    @settings(max_examples=60, deadline=None)
+    @given(case())
+    def run(c):
+        variant, conts, stop, allow_eos, min_new, factor, seed = c
+        marker = QWEN_MARK if variant == "qwen" else LLAMA_MARK
+        rows = [[3, 4] + marker + r for r in conts]
+        scores = torch.randn(len(rows), V, generator=torch.Generator().manual_seed(seed))
+        proc = SoftBoostLogitsProcessor(ix, 1, variant=variant, model_name="llama", min_new_tokens=min_new, pad_token_id=PAD,
+                                        eos_token_id=EOS, stop_at_count=stop, always_allow_eos=allow_eos,
+                                        length_reward_factor=factor)
+        exp = soft_boost_reference(o, rows, scores, 1, variant, EOS, PAD, marker, stop, allow_eos, None, None, factor, min_new)
+        assert torch.equal(proc(torch.tensor(rows), scores), exp)
+
+    run()
