@@ -73,3 +73,39 @@ def test_service_on_gpu_index(cuda):
     assert ix.get_range_many([d[:3] for d in docs[:10]] + [[]]) == [o.get_range(d[:3]) for d in docs[:10]] + [o.get_range([])]
     with TestClient(create_app(ix, window_ms=2.0)) as client:
         check_endpoints(client, o, rng, docs)
+
+
+def test_remote_index_drives_the_soft_boost_processor():
+    """causal_qwen_api.py as a composition: the soft-boost processor over RemoteFMIndex over the HTTP service gives the
+    scores of the restated reference over the local index."""
+    import torch
+    from fm_index_constrained_decoding_b200.client import RemoteFMIndex
+    from fm_index_constrained_decoding_b200.processors import SoftBoostLogitsProcessor
+    from oracle.oracle import soft_boost_reference
+    rng, docs = corpus()
+    o = OracleFMIndex()
+    o.initialize(docs)
+    with TestClient(create_app(o)) as client:
+        remote = RemoteFMIndex(session=client)
+        assert len(remote) == len(o) and remote.occurring_distinct == o.occurring_distinct
+        q = docs[4][2:5]
+        assert remote.get_range(q) == o.get_range(q) and remote.get_count(q) == o.get_count(q)
+        assert remote.get_continuations(q) == o.get_continuations(q)
+        V, EOS, PAD = 600, 590, 591
+        marker = [151645, 198, 151644, 77091, 198]
+        think = [151667, 271, 151668, 271]
+        rows = []
+        for k in range(6):
+            d = rng.choice(docs)
+            i = rng.randrange(len(d) - 4)
+            c = d[i:i + 4]
+            if k == 1:
+                c = c[:-1] + [EOS]
+            if k == 2:
+                c = c[:-1] + [555]  # not in the corpus
+            rows.append([1, 2] + marker + (think[:2] + c + [7, 8] if k == 3 else think + c))
+        scores = torch.randn(len(rows), V, generator=torch.Generator().manual_seed(4))
+        proc = SoftBoostLogitsProcessor(remote, 2, variant="qwen", min_new_tokens=2, pad_token_id=PAD, eos_token_id=EOS,
+                                        stop_at_count=1, always_allow_eos=True)
+        exp = soft_boost_reference(o, rows, scores, 2, "qwen", EOS, PAD, marker, 1, True, None, None, 2.0, 2)
+        assert torch.equal(proc(torch.tensor(rows), scores), exp)
