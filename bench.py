@@ -8,12 +8,14 @@
 One STEP = one batch of `--batch` ragged prefixes (length 1..32, substrings of corpus documents)
 pushed through the hot path on a device-resident index of a synthetic `--tokens`-token corpus
 (vocab 128,256): K1 batched backward search -> [sp,ep), then K2 distinct-next-token enumeration
--> one 128,256-bit vocab mask per prefix.  `value` = prefixes/s with inputs resident in HBM;
-`e2e` = the same through the host-buffer C-ABI call (H2D of the prefixes, D2H of ranges and the
+-> one 128,256-bit vocab mask per prefix.  `value` = prefixes/s with inputs resident in HBM,
+consecutive (independent) steps kept in flight on 4 streams through fmidx_query_batch; the roofline's
+per-kernel durations come from a serial pass of the same steps.  `e2e` = the same through the
+host-buffer C-ABI call (fmidx_query_submit / fmidx_query_wait: H2D of the prefixes, D2H of ranges and the
 per-prefix distinct counts inside the timed region).  Multi-GPU (N>1): the corpus is sharded by
 document, one 100M-token shard per GPU (weak scaling), prefixes are replicated, per-shard masks
-are OR-reduced with an all-to-all over NCCL so that rank r ends up owning the final masks of
-its 1/N of the prefixes.
+are OR-reduced by the peer-memory pull exchange (own kernels over CUDA-IPC buffers; NCCL all-to-all
+only as fallback) so that rank r ends up owning the final masks of its 1/N of the prefixes.
 
 --impl reference times the CPU oracle (oracle/fm_oracle.c: sdsl-semantics restatement; the real
 reference needs sdsl-lite and cannot be built here) on all host threads on the same workload.
