@@ -32,13 +32,15 @@ SIGNATURES = {
     "fmidx_distinct_mask_batch": (C.c_int, [p, p, p, sz, i64, u32, p, p, p]),
     "fmidx_query_batch": (C.c_int, [p, C.c_int, p, p, sz, i64, u32, p, p, p, p]),
     "fmidx_distinct_mask_batch_occ": (C.c_int, [p, p, p, sz, i64, u32, p, p, p, p]),
-    "fmidx_mask_pull_or": (C.c_int, [p, p, u32, p, sz, sz, sz, u32, p, p]),  # (h, peers, world, occ_all, occ_stride, row_lo, n_rows, vocab, out, stream)
-    "fmidx_mask_pull_or_inplace": (C.c_int, [p, p, u32, u32, p, sz, sz, sz, u32, p]),
-    "fmidx_xchg_publish": (C.c_int, [p, p, p, u32, u32, p, sz, u32, p]),
-    "fmidx_xchg_wait": (C.c_int, [p, p, u32, u32, p]),
-    "fmidx_xchg_signal": (C.c_int, [p, p, u32, u32, u32, p]),
-    "fmidx_xchg_local": (C.c_int, [p, p, p, sz, i64, u32, p, p, p, u32, u32, u32, C.c_int, p]),
-    "fmidx_xchg_round": (C.c_int, [p, p, p, p, p, p, p, p, u32, u32, sz, u32, u32, p, p]),
+    "fmidx_shard_create": (C.c_int, [p, u32, u32, sz, u32, u32, C.POINTER(p)]),
+    "fmidx_shard_export": (C.c_int, [p, u32, C.c_int, p]),
+    "fmidx_shard_import": (C.c_int, [p, u32, C.c_int, u32, p]),
+    "fmidx_shard_ready": (C.c_int, [p]),
+    "fmidx_shard_step": (C.c_int, [p, u32, p, p, i64, p, p, p]),
+    "fmidx_shard_result": (C.c_int, [p, u32, C.POINTER(p), C.POINTER(p), C.POINTER(p)]),
+    "fmidx_shard_submit": (C.c_int, [p, u32, p, p, i64, p, p, p, p]),
+    "fmidx_shard_wait": (C.c_int, [p, u32]),
+    "fmidx_shard_destroy": (None, [p]),
     "fmidx_ipc_alloc": (C.c_int, [p, sz, C.POINTER(p), p]),
     "fmidx_ipc_open": (C.c_int, [p, p, C.POINTER(p)]),
     "fmidx_ipc_close": (C.c_int, [p, p]),

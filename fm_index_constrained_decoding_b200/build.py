@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libfmidx.so")
-SOURCES = ["fmidx_build.cu", "fmidx_kernels.cu", "fmidx_capi.cu"]
+SOURCES = ["fmidx_build.cu", "fmidx_kernels.cu", "fmidx_capi.cu", "fmidx_shard.cu"]
 HEADERS = ["fmidx_layout.cuh", "fmidx_internal.h", os.path.join("..", "..", "include", "fmidx.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

@@ -454,6 +454,11 @@ int fm_build_from_device_text(fmidx *h, const uint32_t *d_symbols, size_t n_data
         FM_TRY(fm_dev_alloc(h, (void **)&tk, N * 4, true));
         FM_CUDA(cudaMemcpyAsync(tk, T, N * 4, cudaMemcpyDeviceToDevice, s));
         dv.text = tk;
+        // resident layout: the BWT itself as plain symbols (the level permutation consumed the first copy)
+        uint32_t *bw = nullptr;
+        FM_TRY(fm_dev_alloc(h, (void **)&bw, N * 4, true));
+        FM_LAUNCH(k_bwt, grid_for(N, 256, sms), 256, 0, s, T, SA, N, bw);
+        dv.bwt = bw;
     }
     FM_CUDA(cudaStreamSynchronize(s));
     FM_CUDA(cudaGetLastError());

@@ -19,7 +19,7 @@ void fm_set_error(const char *fmt, ...) {
 }
 
 int fm_dev_alloc(fmidx *h, void **out, size_t bytes, bool owned) {
-    cudaError_t e = cudaMalloc(out, bytes ? bytes : 16);
+    cudaError_t e = cudaMalloc(out, bytes + 16);  // vector loads may read up to 12 bytes past the last element
     if (e != cudaSuccess) {
         fm_set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
         return FMIDX_ECUDA;
@@ -107,7 +107,10 @@ void fmidx_free(fmidx_t *h) {
     cudaSetDevice(h->device);
     fm_release_index(h);
     for (auto &b : h->d_scratch) if (b.p) cudaFree(b.p);
-    if (h->mask_ws.p) cudaFree(h->mask_ws.p);
+    for (FmBuf *b : {&h->mask_ws, &h->mask_ws_host}) {
+        if (b->last_use) { cudaEventSynchronize(b->last_use); cudaEventDestroy(b->last_use); }
+        if (b->p) cudaFree(b->p);
+    }
     for (auto &sl : h->slots) {
         if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
         if (sl.in.p) cudaFree(sl.in.p);
@@ -200,10 +203,11 @@ struct FmFileHeader {
     char magic[8];
     uint32_t version, levels, max_sym, sa_dens, isa_dens, keep_text, nblocks, nbblocks;
     uint64_t n;
-    uint64_t bytes[8];  // nibble cells, C, D, sa_marks, sa_samples, isa_samples, text, byte-level cells
+    uint64_t bytes[9];  // nibble cells, C, D, sa_marks, sa_samples, isa_samples, text, byte-level cells, bwt
 };
+constexpr int FM_SECTIONS = 9;
 
-static void section_sizes(const FmDev &d, uint64_t b[8]) {
+static void section_sizes(const FmDev &d, uint64_t b[FM_SECTIONS]) {
     const uint64_t N = d.n;
     b[0] = (uint64_t)d.levels * d.nblocks * 128;
     b[1] = ((uint64_t)d.max_sym + 2) * 4;
@@ -213,6 +217,7 @@ static void section_sizes(const FmDev &d, uint64_t b[8]) {
     b[5] = ((N - 1) / d.isa_dens + 1) * 4;
     b[6] = d.text ? N * 4 : 0;
     b[7] = (uint64_t)d.nbblocks * FMIDX_BCELL_U4 * 16;
+    b[8] = d.bwt ? N * 4 : 0;
 }
 
 int fmidx_save(fmidx_t *h, const char *path) {
@@ -223,15 +228,15 @@ int fmidx_save(fmidx_t *h, const char *path) {
     FmFileHeader hd{};
     memcpy(hd.magic, FM_MAGIC, 8);
     const FmDev &d = h->dev;
-    hd.version = 2; hd.nbblocks = d.nbblocks; hd.levels = d.levels; hd.max_sym = d.max_sym; hd.sa_dens = d.sa_dens; hd.isa_dens = d.isa_dens;
+    hd.version = 3; hd.nbblocks = d.nbblocks; hd.levels = d.levels; hd.max_sym = d.max_sym; hd.sa_dens = d.sa_dens; hd.isa_dens = d.isa_dens;
     hd.keep_text = d.text ? 1 : 0; hd.nblocks = d.nblocks; hd.n = d.n;
     section_sizes(d, hd.bytes);
-    const void *src[8] = {d.cells, d.C, d.D, d.sa_marks, d.sa_samples, d.isa_samples, d.text, d.bcells};
+    const void *src[FM_SECTIONS] = {d.cells, d.C, d.D, d.sa_marks, d.sa_samples, d.isa_samples, d.text, d.bcells, d.bwt};
     int rc = FMIDX_OK;
     if (fwrite(&hd, sizeof(hd), 1, f) != 1) rc = FMIDX_EIO;
     const size_t CH = 64u << 20;
     std::vector<unsigned char> buf(CH);
-    for (int sct = 0; sct < 8 && rc == FMIDX_OK; ++sct) {
+    for (int sct = 0; sct < FM_SECTIONS && rc == FMIDX_OK; ++sct) {
         for (uint64_t off = 0; off < hd.bytes[sct] && rc == FMIDX_OK; off += CH) {
             size_t len = (size_t)std::min<uint64_t>(CH, hd.bytes[sct] - off);
             cudaError_t e = cudaMemcpy(buf.data(), (const char *)src[sct] + off, len, cudaMemcpyDeviceToHost);
@@ -253,7 +258,7 @@ int fmidx_load(const char *path, int device, fmidx_t **out) {
     if (!f) { fm_set_error("cannot open %s: %s", path, strerror(errno)); fmidx_free(h); return FMIDX_EIO; }
     FmFileHeader hd{};
     int rc = FMIDX_OK;
-    if (fread(&hd, sizeof(hd), 1, f) != 1 || memcmp(hd.magic, FM_MAGIC, 8) != 0 || hd.version != 2) {
+    if (fread(&hd, sizeof(hd), 1, f) != 1 || memcmp(hd.magic, FM_MAGIC, 8) != 0 || hd.version != 3) {
         fm_set_error("%s is not an fmidx-b200 index file (bad magic/version)", path);
         rc = FMIDX_EIO;
     }
@@ -261,15 +266,16 @@ int fmidx_load(const char *path, int device, fmidx_t **out) {
         FmDev d{};
         d.levels = hd.levels; d.max_sym = hd.max_sym; d.sa_dens = hd.sa_dens; d.isa_dens = hd.isa_dens;
         d.nblocks = hd.nblocks; d.nbblocks = hd.nbblocks; d.n = (uint32_t)hd.n; d.level_stride = (uint64_t)hd.nblocks * FMIDX_CELL_U4;
-        uint64_t expect[8];
+        uint64_t expect[FM_SECTIONS];
         FmDev probe = d;
         probe.text = hd.keep_text ? (const uint32_t *)1 : nullptr;
+        probe.bwt = hd.bytes[8] ? (const uint32_t *)1 : nullptr;
         section_sizes(probe, expect);
-        for (int i = 0; i < 8; ++i) if (expect[i] != hd.bytes[i]) { fm_set_error("%s: corrupt section table", path); rc = FMIDX_EIO; }
-        void *dst[8] = {nullptr};
+        for (int i = 0; i < FM_SECTIONS; ++i) if (expect[i] != hd.bytes[i]) { fm_set_error("%s: corrupt section table", path); rc = FMIDX_EIO; }
+        void *dst[FM_SECTIONS] = {nullptr};
         const size_t CH = 64u << 20;
         std::vector<unsigned char> buf(CH);
-        for (int sct = 0; sct < 8 && rc == FMIDX_OK; ++sct) {
+        for (int sct = 0; sct < FM_SECTIONS && rc == FMIDX_OK; ++sct) {
             if (!hd.bytes[sct]) continue;
             rc = fm_dev_alloc(h, &dst[sct], hd.bytes[sct], true);
             for (uint64_t off = 0; off < hd.bytes[sct] && rc == FMIDX_OK; off += CH) {
@@ -282,7 +288,7 @@ int fmidx_load(const char *path, int device, fmidx_t **out) {
         if (rc == FMIDX_OK) {
             d.cells = (const uint4 *)dst[0]; d.C = (const uint32_t *)dst[1]; d.D = (const uint32_t *)dst[2];
             d.sa_marks = (const uint2 *)dst[3]; d.sa_samples = (const uint32_t *)dst[4];
-            d.isa_samples = (const uint32_t *)dst[5]; d.text = (const uint32_t *)dst[6]; d.bcells = (const uint4 *)dst[7];
+            d.isa_samples = (const uint32_t *)dst[5]; d.text = (const uint32_t *)dst[6]; d.bcells = (const uint4 *)dst[7]; d.bwt = (const uint32_t *)dst[8];
             h->dev = d;
             h->opt_sa_dens = d.sa_dens; h->opt_isa_dens = d.isa_dens; h->opt_keep_text = hd.keep_text;
             h->ready = true;
@@ -501,12 +507,14 @@ int fmidx_query_batch(fmidx_t *h, int ws_slot, const int32_t *d_toks, const int6
     FM_TRY(enter(h, true));
     if (ws_slot < 0 || ws_slot >= 8) { fm_set_error("ws_slot must be 0..7"); return FMIDX_EINVAL; }
     if (!d_sp || !d_ep) { fm_set_error("null argument"); return FMIDX_EINVAL; }
-    FM_TRY(fm_launch_search(h, d_toks, d_offs, B, shift, d_sp, d_ep, 0, (cudaStream_t)stream));
+    // the search kernel also zeroes the mask rows (its stores are free: it is bound by its dependent-load chain)
+    const bool kz = vocab != 0 && fm_search_can_zero(d_mask, vocab);
+    FM_TRY(fm_launch_search(h, d_toks, d_offs, B, shift, d_sp, d_ep, 0, (cudaStream_t)stream, kz ? d_mask : nullptr, (vocab + 31u) >> 5));
     if (!d_mask || vocab == 0) return FMIDX_OK;
     h->mask_ws_override = &h->slots[ws_slot].ws;  // calls on different streams must not share the node lists
     struct Reset { fmidx_t *h; ~Reset() { h->mask_ws_override = nullptr; } } reset{h};
     return fm_launch_mask(h, d_sp, d_ep, B, shift, vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, d_mask, nullptr,
-                          (cudaStream_t)stream);
+                          (cudaStream_t)stream, nullptr, 0, ~(size_t)0, kz);
 }
 
 int fmidx_distinct_mask_batch_occ(fmidx_t *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, int64_t shift,
@@ -515,78 +523,6 @@ int fmidx_distinct_mask_batch_occ(fmidx_t *h, const uint64_t *d_sp, const uint64
     if (!d_mask || !d_occ) { fm_set_error("null argument"); return FMIDX_EINVAL; }
     return fm_launch_mask(h, d_sp, d_ep, B, shift, vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, d_mask, d_counts,
                           (cudaStream_t)stream, d_occ);
-}
-
-int fmidx_mask_pull_or(fmidx_t *h, const uint64_t *d_peer_masks, uint32_t world, const uint32_t *d_occ_all,
-                       size_t occ_stride, size_t row_lo, size_t n_rows, uint32_t vocab, uint32_t *d_out, void *stream) {
-    FM_TRY(enter(h, false));
-    if (!d_peer_masks || !d_occ_all || !d_out) { fm_set_error("null argument"); return FMIDX_EINVAL; }
-    return fm_launch_pull_or(h, (const uint32_t *const *)d_peer_masks, world, d_occ_all, occ_stride, row_lo, n_rows, vocab, d_out,
-                             (cudaStream_t)stream);
-}
-
-int fmidx_mask_pull_or_inplace(fmidx_t *h, const uint64_t *d_peer_masks, uint32_t world, uint32_t rank, const uint32_t *d_occ_all,
-                               size_t occ_stride, size_t row_lo, size_t n_rows, uint32_t vocab, void *stream) {
-    FM_TRY(enter(h, false));
-    if (!d_peer_masks || !d_occ_all || rank >= world) { fm_set_error("bad argument"); return FMIDX_EINVAL; }
-    return fm_launch_pull_or_inplace(h, (uint32_t *const *)d_peer_masks, world, rank, d_occ_all, occ_stride, row_lo, n_rows, vocab,
-                                     (cudaStream_t)stream);
-}
-
-int fmidx_xchg_publish(fmidx_t *h, const uint64_t *d_peer_inbox, const uint64_t *d_peer_flags, uint32_t world, uint32_t rank,
-                       const uint32_t *d_local, size_t xwords, uint32_t seq, void *stream) {
-    FM_TRY(enter(h, false));
-    if (!d_peer_inbox || !d_peer_flags || !d_local || rank >= world) { fm_set_error("bad argument"); return FMIDX_EINVAL; }
-    return fm_launch_xchg_publish(h, (uint32_t *const *)d_peer_inbox, (uint32_t *const *)d_peer_flags, world, rank, d_local, xwords,
-                                  seq, (cudaStream_t)stream);
-}
-
-int fmidx_xchg_wait(fmidx_t *h, const uint32_t *d_flags, uint32_t world, uint32_t seq, void *stream) {
-    FM_TRY(enter(h, false));
-    if (!d_flags || world == 0 || world > 1024) { fm_set_error("bad argument"); return FMIDX_EINVAL; }
-    return fm_launch_xchg_wait(h, d_flags, world, seq, (cudaStream_t)stream);
-}
-
-int fmidx_xchg_signal(fmidx_t *h, const uint64_t *d_peer_flags, uint32_t world, uint32_t rank, uint32_t seq, void *stream) {
-    FM_TRY(enter(h, false));
-    if (!d_peer_flags || rank >= world || world > 1024) { fm_set_error("bad argument"); return FMIDX_EINVAL; }
-    return fm_launch_xchg_signal(h, (uint32_t *const *)d_peer_flags, world, rank, seq, (cudaStream_t)stream);
-}
-
-// One host call per half of a sharded step (the Python loop was launch-bound with one call per kernel).
-// Side data layout of a shard (xwords u32): [B*ow occupancy words][B occurrence counts as u64], ow = ceil(nslices/32).
-int fmidx_xchg_local(fmidx_t *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, int64_t shift, uint32_t vocab,
-                     uint32_t *d_mask, uint32_t *d_xlocal, const uint32_t *d_ack_flags, uint32_t world, uint32_t rank,
-                     uint32_t wait_seq, int ws_slot, void *stream) {
-    FM_TRY(enter(h, true));
-    if (rank >= world || B % world) { fm_set_error("bad rank/world/B"); return FMIDX_EINVAL; }
-    if (ws_slot >= 8) { fm_set_error("ws_slot must be -1..7"); return FMIDX_EINVAL; }
-    if (ws_slot >= 0) h->mask_ws_override = &h->slots[ws_slot].ws;
-    struct Reset { fmidx_t *h; ~Reset() { h->mask_ws_override = nullptr; } } reset{h};
-    if (!d_mask || !d_xlocal || !d_ack_flags) { fm_set_error("null argument"); return FMIDX_EINVAL; }
-    cudaStream_t s = (cudaStream_t)stream;
-    const size_t ow = (((size_t)vocab + 4095) / 4096 + 31) / 32;
-    if (wait_seq) FM_TRY(fm_launch_xchg_wait(h, d_ack_flags, world, wait_seq, s));  // every shard has pulled the step that last used d_mask
-    // only the rows this rank owns come out as complete bitmaps; the others are written slice-wise (occupied slices)
-    FM_TRY(fm_launch_mask(h, d_sp, d_ep, B, shift, vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, d_mask, nullptr, s, d_xlocal,
-                          rank * (B / world), B / world));
-    return fm_launch_xchg_counts(h, d_sp, d_ep, B, (uint64_t *)(d_xlocal + B * ow), s);
-}
-
-int fmidx_xchg_round(fmidx_t *h, const uint64_t *d_peer_masks, const uint64_t *d_peer_inbox, const uint64_t *d_peer_data_flags,
-                     const uint64_t *d_peer_ack_flags, const uint32_t *d_data_flags, const uint32_t *d_inbox,
-                     const uint32_t *d_xlocal, uint32_t world, uint32_t rank, size_t B, uint32_t vocab, uint32_t seq,
-                     uint64_t *d_counts_out, void *stream) {
-    FM_TRY(enter(h, false));
-    if (!d_peer_masks || !d_peer_inbox || !d_peer_data_flags || !d_peer_ack_flags || !d_data_flags || !d_inbox || !d_xlocal ||
-        rank >= world || B % world) { fm_set_error("bad argument"); return FMIDX_EINVAL; }
-    cudaStream_t s = (cudaStream_t)stream;
-    const size_t ow = (((size_t)vocab + 4095) / 4096 + 31) / 32, xwords = B * ow + 2 * B, own = B / world;
-    FM_TRY(fm_launch_xchg_publish(h, (uint32_t *const *)d_peer_inbox, (uint32_t *const *)d_peer_data_flags, world, rank, d_xlocal, xwords, seq, s));
-    FM_TRY(fm_launch_xchg_wait(h, d_data_flags, world, seq, s));
-    FM_TRY(fm_launch_pull_or_inplace(h, (uint32_t *const *)d_peer_masks, world, rank, d_inbox, xwords, rank * own, own, vocab, s));
-    if (d_counts_out) FM_TRY(fm_launch_xchg_sum_counts(h, d_inbox, world, xwords, B * ow, B, d_counts_out, s));
-    return fm_launch_xchg_signal(h, (uint32_t *const *)d_peer_ack_flags, world, rank, seq, s);
 }
 
 // ---- peer-visible buffers (CUDA IPC) for the pull-style cross-shard exchange ------------------------------
@@ -699,12 +635,16 @@ static int query_host_impl(fmidx_t *h, const int32_t *toks, const int64_t *offs,
     int32_t *d_toks = (int32_t *)(d_n + B);
     FM_CUDA(cudaMemcpyAsync(d_offs, offs, (B + 1) * 8, cudaMemcpyHostToDevice, s));
     if (ntok) FM_CUDA(cudaMemcpyAsync(d_toks, toks, ntok * 4, cudaMemcpyHostToDevice, s));
-    FM_TRY(fm_launch_search(h, d_toks, d_offs, B, shift, d_sp, d_ep, 0, s));
     uint32_t *d_mask = nullptr;
     if (want_mask) {
         FM_TRY(fm_scratch(h, *mb, B * (size_t)words * 4, false));
         d_mask = (uint32_t *)mb->p;
-        FM_TRY(fm_launch_mask(h, d_sp, d_ep, B, shift, vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, d_mask, nullptr, s));
+    }
+    const bool kz = want_mask && fm_search_can_zero(d_mask, vocab);
+    FM_TRY(fm_launch_search(h, d_toks, d_offs, B, shift, d_sp, d_ep, 0, s, kz ? d_mask : nullptr, words));
+    if (want_mask) {
+        FM_TRY(fm_launch_mask(h, d_sp, d_ep, B, shift, vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, d_mask, nullptr, s,
+                              nullptr, 0, ~(size_t)0, kz));
         if (n_distinct) FM_TRY(fm_launch_popcount(h, d_mask, B, vocab, d_n, s));
     }
     FM_CUDA(cudaMemcpyAsync(sp, d_sp, B * 8, cudaMemcpyDeviceToHost, s));

@@ -46,6 +46,23 @@ struct FmBuf {  // growable device / pinned-host scratch
     // each call's last kernel zeroes the pair of the next one (no memset node per call)
     uint32_t epoch = 0;
     bool ctr_clean = false;
+    // shared (non-slot) mask workspaces: last use, so that a call on another stream orders itself behind it
+    cudaEvent_t last_use = nullptr;
+    cudaStream_t last_stream = nullptr;
+};
+
+// sharded step: the parts of the cross-shard exchange that are folded into the enumeration kernels
+struct FmXchgArgs {
+    uint64_t *xcounts = nullptr;            // [B] occurrence counts (ep - sp) of this shard, part of its side data
+    const uint32_t *ack_flags = nullptr;    // k_mask_top first waits until ack_flags[p] >= ack_seq for p < ack_world
+    uint32_t ack_world = 0, ack_seq = 0;
+    // publication at the tail of the last enumeration kernel (world == 0: none)
+    uint32_t *const *peer_inbox = nullptr;
+    uint32_t *const *peer_data_flags = nullptr;
+    const uint32_t *xlocal = nullptr;
+    uint32_t *done_ctr = nullptr;
+    size_t xwords = 0;
+    uint32_t world = 0, rank = 0, seq = 0;
 };
 
 struct fmidx {
@@ -59,7 +76,8 @@ struct fmidx {
     size_t dev_bytes = 0;
     cudaStream_t stream = nullptr;  // private stream of the synchronous host-style calls
     FmBuf d_scratch[8];
-    FmBuf mask_ws;               // node tables + work list of the mask kernels
+    FmBuf mask_ws;               // node tables + work list of the mask kernels: device-style calls (caller's stream)
+    FmBuf mask_ws_host;          // same for the host-style calls on the private stream
     FmBuf *mask_ws_override = nullptr;  // set while a pipelined slot launches (its own workspace)
     struct Slot {                // fmidx_query_submit / fmidx_query_wait: independent in-flight host batches
         cudaStream_t stream = nullptr;
@@ -78,25 +96,20 @@ int fm_build_from_device_text(fmidx *h, const uint32_t *d_symbols, size_t n_data
 
 // kernel launchers (fmidx_kernels.cu); all enqueue on `s`
 int fm_launch_search(fmidx *h, const int32_t *d_toks, const int64_t *d_offs, size_t B, int64_t shift, uint64_t *d_sp,
-                     uint64_t *d_ep, int raw, cudaStream_t s);
+                     uint64_t *d_ep, int raw, cudaStream_t s, uint32_t *d_zero_rows = nullptr, uint32_t zero_words = 0,
+                     size_t zero_lo = 0, size_t zero_n = ~(size_t)0);
+bool fm_search_can_zero(const uint32_t *d_mask, uint32_t vocab);
 int fm_launch_step(fmidx *h, const uint64_t *d_sym, const uint64_t *d_lo, const uint64_t *d_hi, size_t B,
                    uint64_t *d_sp, uint64_t *d_ep, cudaStream_t s);
 int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, int64_t shift, uint32_t vocab,
                    const void *d_logits, void *d_out, int dtype, int64_t row_stride, const int32_t *d_override,
                    int32_t always_allow, const uint32_t *d_extra, uint32_t n_extra, uint32_t *d_mask,
-                   uint32_t *d_counts, cudaStream_t s, uint32_t *d_occ = nullptr, size_t dense_lo = 0, size_t dense_n = ~(size_t)0);
-int fm_launch_pull_or(fmidx *h, const uint32_t *const *d_peer_masks, uint32_t world, const uint32_t *d_occ_all,
-                      size_t occ_stride, size_t row_lo, size_t n_rows, uint32_t vocab, uint32_t *d_out, cudaStream_t s);
+                   uint32_t *d_counts, cudaStream_t s, uint32_t *d_occ = nullptr, size_t dense_lo = 0, size_t dense_n = ~(size_t)0,
+                   bool prezeroed = false, const FmXchgArgs *xa = nullptr);
+int fm_launch_xchg_pull(fmidx *h, uint32_t *const *d_peer_masks, uint32_t *const *d_peer_ack_flags, const uint32_t *d_data_flags,
+                        const uint32_t *d_inbox, size_t xwords, size_t count_off, uint32_t world, uint32_t rank, size_t B, uint32_t vocab,
+                        uint32_t seq, uint64_t *d_counts_out, uint32_t *d_done_ctr, cudaStream_t s);
 int fm_launch_or(fmidx *h, const uint32_t *d_pieces, uint32_t n_pieces, size_t n_words, uint32_t *d_out, cudaStream_t s);
-int fm_launch_pull_or_inplace(fmidx *h, uint32_t *const *d_peer_masks, uint32_t world, uint32_t rank, const uint32_t *d_occ_all,
-                              size_t occ_stride, size_t row_lo, size_t n_rows, uint32_t vocab, cudaStream_t s);
-int fm_launch_xchg_counts(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, uint64_t *d_out, cudaStream_t s);
-int fm_launch_xchg_sum_counts(fmidx *h, const uint32_t *d_inbox, uint32_t world, size_t xwords, size_t count_off, size_t B,
-                              uint64_t *d_out, cudaStream_t s);
-int fm_launch_xchg_publish(fmidx *h, uint32_t *const *d_peer_inbox, uint32_t *const *d_peer_flags, uint32_t world, uint32_t rank,
-                           const uint32_t *d_local, size_t xwords, uint32_t seq, cudaStream_t s);
-int fm_launch_xchg_wait(fmidx *h, const uint32_t *d_flags, uint32_t world, uint32_t seq, cudaStream_t s);
-int fm_launch_xchg_signal(fmidx *h, uint32_t *const *d_peer_flags, uint32_t world, uint32_t rank, uint32_t seq, cudaStream_t s);
 int fm_launch_popcount(fmidx *h, const uint32_t *d_mask, size_t B, uint32_t vocab, uint32_t *d_n, cudaStream_t s);
 int fm_launch_gather_probe(fmidx *h, int unit_bytes, size_t n_loads, double *out_gbps, cudaStream_t s);
 int fm_launch_compact(fmidx *h, const uint32_t *d_mask, const uint32_t *d_counts, size_t B, uint32_t vocab,

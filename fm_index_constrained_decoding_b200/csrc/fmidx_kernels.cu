@@ -26,6 +26,16 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 
+// system-scope flag accesses of the peer-memory exchange (one process per GPU; flags are monotonically increasing step numbers)
+__device__ __forceinline__ uint32_t fm_ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fm_st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // =================================================================================================
 // K1: backward search.  16 lanes per prefix: octet 0 chases sp, octet 1 chases ep, both through
 // the same `levels` cells per token; D[c] and the next token are fetched ahead of the descent.
@@ -36,7 +46,9 @@ constexpr unsigned FULL = 0xffffffffu;
 template <bool RAW>
 __global__ void __launch_bounds__(128) k_search(FmDev ix, const int32_t *__restrict__ toks,
                                                 const int64_t *__restrict__ offs, uint32_t B, int64_t shift,
-                                                uint64_t *__restrict__ sp, uint64_t *__restrict__ ep) {
+                                                uint64_t *__restrict__ sp, uint64_t *__restrict__ ep,
+                                                uint32_t *__restrict__ zero_rows, uint32_t zero_words, uint32_t zero_lo,
+                                                uint32_t zero_n) {
     const int lane = threadIdx.x & 31, sub = lane & 7, half = (lane >> 3) & 1;
     const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
     const bool valid = q < B;
@@ -45,6 +57,15 @@ __global__ void __launch_bounds__(128) k_search(FmDev ix, const int32_t *__restr
     if (valid) {
         o0 = offs[q];
         len = (int)(offs[q + 1] - o0);
+    }
+    // fmidx_query_batch: the mask row of this prefix is zeroed HERE (16 lanes, 16-byte stores, issued before the
+    // dependent-load chain starts and never waited for), so the enumeration kernels find pre-zeroed rows and the
+    // latency-bound search hides the 16 KB of store traffic per prefix.  zero_words % 4 == 0 and a 16-byte aligned
+    // base are checked by the launcher.
+    if (zero_rows && valid && q - zero_lo < zero_n) {
+        uint4 *row = reinterpret_cast<uint4 *>(zero_rows + (size_t)q * zero_words);
+        const uint32_t nv = zero_words >> 2;
+        for (uint32_t i = (uint32_t)(lane & 15); i < nv; i += 16) row[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     const int other_len = __shfl_xor_sync(FULL, len, 16);
     const int maxlen = len > other_len ? len : other_len;
@@ -101,34 +122,63 @@ __global__ void __launch_bounds__(128) k_search(FmDev ix, const int32_t *__restr
         }
     }
     if (accel) {
+        // Three dependent round trips for the whole tail, however many tokens remain: (1) lane i < w loads p_i = SA[lo+i]
+        // while every lane loads "its" remaining tokens (hl, hl+16); (2) for every candidate row the half-warp compares
+        // the remaining tokens with T[p_i-1], T[p_i-2], ... (lane hl: positions hl and hl+16, i.e. two coalesced 64-byte
+        // reads per row; the loads of four rows are issued before any is consumed); (3) the surviving rows' final rows
+        // ISA[p_i - rem].  Tails longer than 32 tokens and texts shorter than 64 symbols (the cyclic index could wrap more
+        // than once) take the serial loop below.
         const bool pend = t_stop >= 0;  // uniform inside the query's 16 lanes
-        const int hl = lane & 15;
+        const int hl = lane & 15, hbase = lane & 16;
         const int rem = pend ? len - t_stop : 0;
         const uint32_t n = ix.n;
-        bool ok = pend && (uint32_t)hl < hi - lo;
+        const uint32_t w = pend ? hi - lo : 0u;  // 1..16
+        const bool fast = n >= 64u && rem <= 32;
+        bool ok = pend && (uint32_t)hl < w;
         uint32_t p = 0;
         if (ok) p = ix.sa_samples[lo + (uint32_t)hl];
-        const bool live = ok;
-        if (n >= 64u) {
-            // rem <= 31 < n: (p-1-j) mod n wraps at most once; the loads do not depend on `ok`, so they pipeline
-#pragma unroll 4
-            for (int j = 0; j < rem; ++j) {
-                const int64_t sym = (int64_t)toks[o0 + t_stop + j] + shift;
-                const uint32_t at = p > (uint32_t)j ? p - 1u - (uint32_t)j : p + n - 1u - (uint32_t)j;  // the text is cyclic under LF
-                const uint32_t tv = live ? ix.text[at] : 0u;
-                ok = ok && sym >= 0 && sym <= 0xFFFFFFFFll && (uint32_t)sym == tv;
+        if (__any_sync(FULL, pend && fast)) {
+            int64_t s0 = -1, s1 = -1;
+            if (pend && fast && hl < rem) s0 = (int64_t)toks[o0 + t_stop + hl] + shift;
+            if (pend && fast && hl + 16 < rem) s1 = (int64_t)toks[o0 + t_stop + hl + 16] + shift;
+            const bool use0 = pend && fast && hl < rem, use1 = pend && fast && hl + 16 < rem;
+            // a symbol outside u32 can never equal a text symbol
+            const bool inv0 = use0 && (s0 < 0 || s0 > 0xFFFFFFFFll), inv1 = use1 && (s1 < 0 || s1 > 0xFFFFFFFFll);
+            const uint32_t wo = __shfl_xor_sync(FULL, fast ? w : 0u, 16);
+            const uint32_t wmax = max(fast ? w : 0u, wo);
+            uint32_t okmask = 0;
+            for (uint32_t i0 = 0; i0 < wmax; i0 += 4) {
+                uint32_t t0v[4], t1v[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const uint32_t pi = __shfl_sync(FULL, p, hbase + (int)((i0 + r) & 15u));
+                    const bool row = i0 + r < w;
+                    t0v[r] = 0u;
+                    t1v[r] = 0u;
+                    if (row && use0) t0v[r] = ix.text[pi > (uint32_t)hl ? pi - 1u - (uint32_t)hl : pi + n - 1u - (uint32_t)hl];
+                    if (row && use1) t1v[r] = ix.text[pi > (uint32_t)hl + 16u ? pi - 17u - (uint32_t)hl : pi + n - 17u - (uint32_t)hl];
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const bool row = i0 + r < w;
+                    const bool bad = row && (inv0 || inv1 || (use0 && t0v[r] != (uint32_t)s0) || (use1 && t1v[r] != (uint32_t)s1));
+                    const uint32_t anybad = (__ballot_sync(FULL, bad) >> hbase) & 0xFFFFu;
+                    if (row && !anybad) okmask |= 1u << (i0 + r);
+                }
             }
-        } else {
+            if (fast) ok = ok && ((okmask >> hl) & 1u);
+        }
+        if (pend && !fast) {
             for (int j = 0; j < rem && ok; ++j) {
                 const int64_t sym = (int64_t)toks[o0 + t_stop + j] + shift;
-                const uint32_t at = (uint32_t)(((uint64_t)p + n - 1u - ((uint32_t)j % n)) % n);
+                const uint32_t at = (uint32_t)(((uint64_t)p + n - 1u - ((uint32_t)j % n)) % n);  // the text is cyclic under LF
                 ok = sym >= 0 && sym <= 0xFFFFFFFFll && (uint32_t)sym == ix.text[at];
             }
         }
         uint32_t mn = 0xFFFFFFFFu, mx = 0u;
         if (ok) {
-            const uint32_t back = n >= 64u ? (p >= (uint32_t)rem ? p - (uint32_t)rem : p + n - (uint32_t)rem)
-                                           : (uint32_t)(((uint64_t)p + n - ((uint32_t)rem % n)) % n);
+            const uint32_t back = fast ? (p >= (uint32_t)rem ? p - (uint32_t)rem : p + n - (uint32_t)rem)
+                                       : (uint32_t)(((uint64_t)p + n - ((uint32_t)rem % n)) % n);
             mn = mx = ix.isa_samples[back];
         }
 #pragma unroll
@@ -507,14 +557,45 @@ __device__ __forceinline__ void fm_eval_byte_node(const FmDev &ix, uint32_t lo, 
     __syncwarp();
 }
 
+// ---- resident BWT: the rows of a range are contiguous plain symbols ---------------------------------------------
+// Calls f(symbol) for every row of [lo,hi), the work split over `nl` cooperating lanes (this one is lane l): 16-byte
+// loads of four consecutive rows per lane, i.e. fully coalesced 512-byte (warp) / 256-byte (half-warp) requests.
+// The array is padded so that the last vector may be read past row n-1.
+constexpr uint32_t SCAN_INLINE = 1024;  // ranges up to this many rows are scanned by the warp / CTA that owns the prefix
+template <typename F>
+__device__ __forceinline__ void fm_scan_rows(const uint32_t *__restrict__ bwt, uint32_t lo, uint32_t hi, uint32_t l, uint32_t nl, F &&f) {
+#pragma unroll 2
+    for (uint32_t p = (lo & ~3u) + 4u * l; p < hi; p += 4u * nl) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(bwt + p));
+        if (p >= lo) f(v.x);
+        if (p + 1u >= lo && p + 1u < hi) f(v.y);
+        if (p + 2u >= lo && p + 2u < hi) f(v.z);
+        if (p + 3u >= lo && p + 3u < hi) f(v.w);
+    }
+}
+
 // ---- phase A --------------------------------------------------------------------------------------
 // lvl = concatenated dense node tables, level l at offset B * sum_{j<l} P_j, row b = P_l entries.
 __global__ void __launch_bounds__(128)
 k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict__ ep, uint32_t B, uint32_t LT,
            uint2 *__restrict__ lvl, const int32_t *__restrict__ override_tok, int64_t shift, uint32_t vocab,
            uint4 *__restrict__ work_items, uint32_t *__restrict__ work_count, uint32_t *__restrict__ mask_out,
-           uint32_t *__restrict__ counts_out, uint32_t *__restrict__ occ_out, uint32_t dense_lo, uint32_t dense_n) {
+           uint32_t *__restrict__ counts_out, uint32_t *__restrict__ occ_out, uint32_t dense_lo, uint32_t dense_n,
+           uint32_t zflags, uint64_t *__restrict__ xcounts, const uint32_t *__restrict__ ack_flags, uint32_t ack_world,
+           uint32_t ack_seq, uint32_t scan_max) {
     __shared__ uint4 stage[8][16];
+    // sharded step: the bitmap buffer may only be overwritten once every shard has pulled the step that last used it
+    // (ack flags live in THIS GPU's memory, the peers raise them by remote stores; normally long since satisfied)
+    if (ack_seq) {
+        if (threadIdx.x < ack_world) {
+            const long long t0 = clock64();
+            while ((int32_t)(fm_ld_acquire_sys(ack_flags + threadIdx.x) - ack_seq) < 0) {
+                __nanosleep(100);
+                if (clock64() - t0 > 20000000000ll) __trap();
+            }
+        }
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31, hw = (threadIdx.x >> 4) & 1, hl = threadIdx.x & 15;
     const int wslot = threadIdx.x >> 4;  // half-warp slot in the CTA
     const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -533,14 +614,80 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
         const uint32_t mw = (vocab + 31u) >> 5;
         uint32_t *row = mask_out + (size_t)b * mw;
         const bool dense = b - dense_lo < dense_n;
-        if (dense)
-            for (uint32_t i = (uint32_t)lane; i < mw; i += 32) row[i] = 0u;
+        if (xcounts && lane == 0) xcounts[b] = e > s ? e - s : 0ull;  // occurrence count of the prefix on this shard
+        if (dense && !(zflags & 1u)) {  // bit 0: the rows were zeroed by k_search (fmidx_query_batch)
+            if (zflags & 2u) {           // bit 1: 16-byte stores are legal
+                uint4 *row4 = reinterpret_cast<uint4 *>(row);
+                for (uint32_t i = (uint32_t)lane; i < (mw >> 2); i += 32) row4[i] = make_uint4(0u, 0u, 0u, 0u);
+            } else {
+                for (uint32_t i = (uint32_t)lane; i < mw; i += 32) row[i] = 0u;
+            }
+        }
         if (occ_out) {  // slice-occupancy words of this row (bit s: slice s may hold set bits)
             const uint32_t ow = ((vocab + SLICE - 1) / SLICE + 31u) >> 5;
             for (uint32_t i = (uint32_t)lane; i < ow; i += 32) occ_out[(size_t)b * ow + i] = 0u;
         }
         __syncwarp();
         if (s >= e) return;
+        if (ix.bwt && !counts_out && e - s <= (uint64_t)scan_max) {
+            // Resident BWT: the distinct symbols of a range of up to scan_max rows are READ, not searched for -- one
+            // coalesced pass over BWT[s,e) instead of a descent per visited node.
+            const uint32_t lo = (uint32_t)s, hi = (uint32_t)e, w = hi - lo;
+            const uint32_t nslices = (vocab + SLICE - 1) / SLICE, ow = (nslices + 31u) >> 5;
+            const int64_t ga64 = shift > 0 ? shift : 0, ge64 = min((int64_t)vocab + shift, (int64_t)ix.max_sym + 1);
+            const uint32_t ga = (uint32_t)ga64, ge = ge64 > ga64 ? (uint32_t)ge64 : ga;
+            if (w <= SCAN_INLINE) {
+                if (!dense || occ_out) {
+                    // slice occupancy first (sparse rows: exactly the occupied slices are zeroed before any bit is set)
+                    for (uint32_t ws = 0; ws < ow; ++ws) {
+                        uint32_t occw = 0;
+                        fm_scan_rows(ix.bwt, lo, hi, (uint32_t)lane, 32u, [&](uint32_t c) {
+                            if (c >= ga && c < ge) {
+                                const uint32_t sl = (uint32_t)((int64_t)c - shift) / SLICE;
+                                if ((sl >> 5) == ws) occw |= 1u << (sl & 31u);
+                            }
+                        });
+                        occw = __reduce_or_sync(FULL, occw);
+                        if (occ_out && lane == 0) occ_out[(size_t)b * ow + ws] = occw;
+                        if (!dense) {
+                            uint32_t todo = occw;
+                            while (todo) {
+                                const uint32_t s_cur = ws * 32u + (uint32_t)__ffs(todo) - 1u;
+                                const uint32_t w0 = s_cur * (SLICE / 32), w1 = min(w0 + SLICE / 32, mw);
+                                for (uint32_t i = w0 + (uint32_t)lane; i < w1; i += 32) row[i] = 0u;
+                                todo &= todo - 1u;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+                fm_scan_rows(ix.bwt, lo, hi, (uint32_t)lane, 32u, [&](uint32_t c) {
+                    if (c >= ga && c < ge) {
+                        const uint32_t tk = (uint32_t)((int64_t)c - shift);
+                        atomicOr(&row[tk >> 5], 1u << (tk & 31u));
+                    }
+                });
+                return;
+            }
+            // wider: at most P_top (<= 32) chunks of the range go to the work list, one half-warp of k_mask_expand each.
+            // The occupancy is not known without reading the rows: every slice is reported as possibly occupied (the
+            // words are conservative by contract) and sparse rows are zeroed whole.
+            const uint32_t P_top = fm_nodes_at(ix.max_sym, L, LT);
+            uint32_t chunk = (w + P_top - 1u) / P_top;
+            chunk = max(256u, (chunk + 63u) & ~63u);
+            const uint32_t nchunks = (w + chunk - 1u) / chunk;
+            uint32_t slot = 0;
+            if (lane == 0) slot = atomicAdd(work_count, nchunks);
+            slot = __shfl_sync(FULL, slot, 0);
+            if ((uint32_t)lane < nchunks)
+                work_items[slot + (uint32_t)lane] = make_uint4(b, 0xFFFFFFFFu, lo + (uint32_t)lane * chunk, min(hi, lo + ((uint32_t)lane + 1u) * chunk));
+            if (occ_out)
+                for (uint32_t i = (uint32_t)lane; i < ow; i += 32)
+                    occ_out[(size_t)b * ow + i] = (i + 1u) * 32u <= nslices ? ~0u : ((1u << (nslices & 31u)) - 1u);
+            if (!dense)
+                for (uint32_t i = (uint32_t)lane; i < mw; i += 32) row[i] = 0u;
+            return;
+        }
         if (e - s <= 32u) {
             const bool valid = (uint64_t)lane < e - s;
             uint32_t pos = (uint32_t)s + (uint32_t)lane, c = 0;
@@ -580,6 +727,11 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
         }
     }
     uint2 *cur = lvl + b;
+    if (!work_items && ix.bwt) {  // logits mode: k_mask_logits reads narrow ranges off the resident BWT itself
+        uint64_t s = sp[b], e = ep[b];
+        if (e > ix.n) e = ix.n;
+        if (s >= e || e - s <= (uint64_t)SCAN_INLINE) return;
+    }
     if (lane == 0) {
         uint64_t s = sp[b], e = ep[b];
         if (e > ix.n) e = ix.n;                                          // fm_index.cpp:130-132
@@ -790,7 +942,23 @@ __device__ __forceinline__ void fm_enum_seeded(const FmDev &ix, uint32_t LT, uin
 
 __device__ __forceinline__ void fm_enum_slice(const FmDev &ix, const uint2 *__restrict__ top_b, uint32_t LT, uint32_t sa,
                                               uint32_t se, int64_t shift, uint32_t t0, EnumSmem &S,
-                                              uint32_t *__restrict__ counts_row) {
+                                              uint32_t *__restrict__ counts_row, uint64_t s64, uint64_t e64) {
+    if (ix.bwt && !counts_row) {
+        // resident BWT: a range of up to SCAN_INLINE rows is read by the CTA itself (every slice-CTA of the beam reads the
+        // same few hundred bytes, L2 hits after the first) and filtered to the slice -- no table, no dependent probes
+        if (e64 > ix.n) e64 = ix.n;
+        if (s64 >= e64) return;
+        if (e64 - s64 <= (uint64_t)SCAN_INLINE) {
+            __syncthreads();  // S.bm was zeroed by all threads
+            fm_scan_rows(ix.bwt, (uint32_t)s64, (uint32_t)e64, threadIdx.x, blockDim.x, [&](uint32_t c) {
+                if (c >= sa && c < se) {
+                    const uint32_t rel = (uint32_t)((int64_t)c - shift) - t0;
+                    atomicOr(&S.bm[rel >> 5], 1u << (rel & 31u));
+                }
+            });
+            return;
+        }
+    }
     if (threadIdx.x == 0) fm_seed_from_table(ix, top_b, LT, sa, se, S);
     __syncthreads();
     fm_enum_seeded(ix, LT, sa, se, shift, t0, S, counts_row);
@@ -830,9 +998,21 @@ k_mask_expand(FmDev ix, uint32_t LT, int64_t shift, uint32_t vocab, const uint4 
     const uint32_t gwarp = (blockIdx.x * EXPAND_THREADS + tid) >> 5, nwarps = (gridDim.x * EXPAND_THREADS) >> 5;
     for (uint32_t base = gwarp * 2u; base < n_items; base += nwarps * 2u) {
         const uint32_t i = base + (uint32_t)hw;
-        const bool has = i < n_items;
+        bool has = i < n_items;
         const uint4 it = has ? __ldg(items + i) : make_uint4(0u, 0u, 0u, 0u);
         const uint32_t b = it.x, prefix = it.y, lo = it.z, hi = it.w;
+        const bool scan_item = has && prefix == 0xFFFFFFFFu;  // a chunk of a mid-sized range: read its rows off the resident BWT
+        if (__any_sync(FULL, scan_item)) {
+            if (scan_item)
+                fm_scan_rows(ix.bwt, lo, hi, (uint32_t)hl, 16u, [&](uint32_t c) {
+                    if (c >= ga && c < ge) {
+                        const uint32_t tk = (uint32_t)((int64_t)c - shift);
+                        atomicOr(&mask_out[(size_t)b * mask_words + (tk >> 5)], 1u << (tk & 31u));
+                    }
+                });
+            __syncwarp();
+        }
+        has = has && !scan_item;
         const bool narrow = has && hi - lo <= 16u;
         if (__any_sync(FULL, narrow)) {
             const bool valid = narrow && (uint32_t)hl < hi - lo;
@@ -914,13 +1094,55 @@ k_mask_expand(FmDev ix, uint32_t LT, int64_t shift, uint32_t vocab, const uint4 
     }
 }
 
+// Publication of a shard's side data at the TAIL of its last enumeration kernel (sharded step): the CTA that finishes
+// last copies the occupancy words + occurrence counts into slot `rank` of every shard's inbox by peer stores and then
+// raises data flag[rank] = seq on every shard (st.release.sys) -- no separate publish launch, and the flag can only be
+// seen after every bit of this step's bitmaps has been written (each CTA fences before it takes its ticket).
+struct FmPublish {
+    uint32_t *const *peer_inbox;   // device array [world]: every shard's inbox base (peer-mapped)
+    uint32_t *const *peer_flags;   // device array [world]: every shard's data-flag array
+    const uint32_t *xlocal;        // this shard's side data (xwords u32)
+    uint32_t *done_ctr;            // ticket counter (zero between launches)
+    uint32_t xwords, world, rank, seq;  // world == 0: nothing to publish
+};
+
+__device__ __forceinline__ void fm_publish_tail(const FmPublish &pub) {
+    __shared__ uint32_t s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(pub.done_ctr, 1u) == gridDim.x - 1u ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const bool vec = (pub.xwords & 3u) == 0 && (((uintptr_t)pub.xlocal) & 15) == 0;
+    for (uint32_t d = 0; d < pub.world; ++d) {
+        uint32_t *dst = pub.peer_inbox[d] + (size_t)pub.rank * pub.xwords;
+        if (vec && (((uintptr_t)dst) & 15) == 0) {
+            for (uint32_t i = threadIdx.x; i < (pub.xwords >> 2); i += blockDim.x)
+                reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(pub.xlocal)[i];
+        } else {
+            for (uint32_t i = threadIdx.x; i < pub.xwords; i += blockDim.x) dst[i] = pub.xlocal[i];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < pub.world) fm_st_release_sys(pub.peer_flags[threadIdx.x] + pub.rank, pub.seq);
+    if (threadIdx.x == 0) *pub.done_ctr = 0u;  // the next launch on this buffer set is stream-ordered after this one
+}
+
 // k_mask_bytes: one warp per byte-level node, bits ORed straight into the (pre-zeroed) mask row in global memory.
-// Warps are fully independent: no block-level barrier anywhere; node entries are fetched two ahead.  (Prefetching the
-// next node's cells into L1/L2 one node ahead was measured and lost 3%: the kernel is issue-bound, not latency-bound.)
+// Warps are fully independent: no block-level barrier in the node loop; node entries are fetched two ahead.  (Prefetching
+// the next node's cells into L1/L2 one node ahead was measured and lost 3%: the kernel is issue-bound, not latency-bound.)
+// The grid is persistent with `occ` CTAs per SM chosen by the launcher: the kernel is the only issue-bound one of the
+// step, so it must NOT own every register of every SM -- the latency-bound kernels of the other batches in flight
+// (k_search, k_mask_top, k_mask_expand) need resident warps next to it to overlap.
 template <int MINB>
 __global__ void __launch_bounds__(BYTES_THREADS, MINB)
 k_mask_bytes(FmDev ix, int64_t shift, uint32_t vocab, const uint4 *__restrict__ bnodes, const uint32_t *__restrict__ n_ptr,
-             uint32_t cap, uint32_t *__restrict__ mask_out, uint32_t *__restrict__ counts_out, uint32_t *__restrict__ reset_ctr) {
+             uint32_t cap, uint32_t *__restrict__ mask_out, uint32_t *__restrict__ counts_out, uint32_t *__restrict__ reset_ctr,
+             FmPublish pub) {
     __shared__ __align__(1024) int cnt[BYTES_THREADS / 32][256];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (blockIdx.x == 0 && tid == 0) {  // the counter pair of the NEXT call on this workspace (unused by this one)
@@ -943,6 +1165,7 @@ k_mask_bytes(FmDev ix, int64_t shift, uint32_t vocab, const uint4 *__restrict__ 
         it = n1;
         n1 = n2;
     }
+    if (pub.world) fm_publish_tail(pub);
 }
 
 // ---- phase B, fused with the logits row: TMA-staged variant ---------------------------------------------
@@ -957,7 +1180,7 @@ __global__ void __launch_bounds__(MASK_THREADS)
 k_mask_logits_tma(FmDev ix, const uint2 *__restrict__ top, uint32_t P_top, uint32_t LT, int64_t shift, uint32_t vocab,
                   const void *logits_v, void *out_v, int64_t row_stride, const int32_t *__restrict__ override_tok,
                   int32_t always_allow, const uint32_t *__restrict__ extra, uint32_t n_extra, uint32_t B,
-                  uint32_t *__restrict__ mask_out) {
+                  uint32_t *__restrict__ mask_out, const uint64_t *__restrict__ sp, const uint64_t *__restrict__ ep) {
     using ET = typename Elem<DT>::T;
     constexpr int VEC = Elem<DT>::VEC;
     __shared__ __align__(128) uint4 buf[SLICE / VEC];
@@ -987,7 +1210,7 @@ k_mask_logits_tma(FmDev ix, const uint2 *__restrict__ top, uint32_t P_top, uint3
     const int32_t ovr = override_tok ? override_tok[b] : -1;
     uint32_t sa, se;
     fm_slice_interval(ix, t0, t1, shift, sa, se);
-    if (ovr < 0) fm_enum_slice(ix, top + (size_t)b * P_top, LT, sa, se, shift, t0, S, nullptr);
+    if (ovr < 0) fm_enum_slice(ix, top + (size_t)b * P_top, LT, sa, se, shift, t0, S, nullptr, sp[b], ep[b]);
     __syncthreads();
     if (ovr >= 0) {
         if (tid == 0 && (uint32_t)ovr >= t0 && (uint32_t)ovr < t1) S.bm[((uint32_t)ovr - t0) >> 5] = 1u << (((uint32_t)ovr - t0) & 31u);
@@ -1052,7 +1275,8 @@ __global__ void __launch_bounds__(MASK_THREADS)
 k_mask_logits_pipe(FmDev ix, const uint2 *__restrict__ top, uint32_t P_top, uint32_t LT, int64_t shift, uint32_t vocab,
                    const void *logits_v, void *out_v, int64_t row_stride, const int32_t *__restrict__ override_tok,
                    int32_t always_allow, const uint32_t *__restrict__ extra, uint32_t n_extra, uint32_t B,
-                   uint32_t *__restrict__ mask_out, uint32_t n_items, uint32_t *__restrict__ next_ptr) {
+                   uint32_t *__restrict__ mask_out, uint32_t n_items, uint32_t *__restrict__ next_ptr,
+                   const uint64_t *__restrict__ sp, const uint64_t *__restrict__ ep) {
     using ET = typename Elem<DT>::T;
     constexpr int VEC = Elem<DT>::VEC;
     constexpr uint32_t STAGE_BYTES = SLICE * sizeof(ET);
@@ -1097,7 +1321,7 @@ k_mask_logits_pipe(FmDev ix, const uint2 *__restrict__ top, uint32_t P_top, uint
         const int32_t ovr = override_tok ? override_tok[b] : -1;
         uint32_t sa, se;
         fm_slice_interval(ix, t0, t1, shift, sa, se);
-        if (ovr < 0) fm_enum_slice(ix, top + (size_t)b * P_top, LT, sa, se, shift, t0, S, nullptr);
+        if (ovr < 0) fm_enum_slice(ix, top + (size_t)b * P_top, LT, sa, se, shift, t0, S, nullptr, sp[b], ep[b]);
         __syncthreads();
         if (ovr >= 0) {
             if (tid == 0 && (uint32_t)ovr >= t0 && (uint32_t)ovr < t1) S.bm[((uint32_t)ovr - t0) >> 5] = 1u << (((uint32_t)ovr - t0) & 31u);
@@ -1167,7 +1391,7 @@ __global__ void __launch_bounds__(MASK_THREADS)
 k_mask_logits(FmDev ix, const uint2 *__restrict__ top, uint32_t P_top, uint32_t LT, int64_t shift, uint32_t vocab,
               const void *logits_v, void *out_v, int64_t row_stride, const int32_t *__restrict__ override_tok,
               int32_t always_allow, const uint32_t *__restrict__ extra, uint32_t n_extra, uint32_t B,
-              uint32_t *__restrict__ mask_out) {
+              uint32_t *__restrict__ mask_out, const uint64_t *__restrict__ sp, const uint64_t *__restrict__ ep) {
     __shared__ EnumSmem S;
     const int tid = threadIdx.x;
     const uint32_t nslices = (vocab + SLICE - 1) / SLICE;
@@ -1195,7 +1419,7 @@ k_mask_logits(FmDev ix, const uint2 *__restrict__ top, uint32_t P_top, uint32_t 
     const int32_t ovr = override_tok ? override_tok[b] : -1;
     uint32_t sa, se;
     fm_slice_interval(ix, t0, t1, shift, sa, se);
-    if (ovr < 0) fm_enum_slice(ix, top + (size_t)b * P_top, LT, sa, se, shift, t0, S, nullptr);  // (k_mask_top left override rows empty)
+    if (ovr < 0) fm_enum_slice(ix, top + (size_t)b * P_top, LT, sa, se, shift, t0, S, nullptr, sp[b], ep[b]);  // (k_mask_top left override rows empty)
     __syncthreads();
     // 3. per-shard masks of the other GPUs, override rows, always-allowed token
     if (ovr >= 0) {
@@ -1254,128 +1478,107 @@ __global__ void __launch_bounds__(256) k_or_pieces(const uint4 *__restrict__ pie
     }
 }
 
-// Cross-shard OR by PULLING over NVLink: the masks of the other shards live in peer memory (CUDA IPC);
-// this rank owns rows [row_lo, row_lo+n_rows) and ORs, for each of them, only the 4096-token slices that a
-// shard marked occupied -- a prefix with a handful of continuations moves a few hundred bytes per shard
-// instead of a 16 KB bitmap.  One CTA per owned row; loads from peers are coalesced 512-B segments.
+// ---- fused second half of a sharded step: wait + pull + OR + total counts + ack in ONE launch ------------------------
+// Persistent grid (at most 2 CTAs per SM, so that CTAs spinning on a flag can never crowd the kernels that the other
+// buffer sets in flight -- or the peers' progress -- depend on).  A warp owns rows gw, gw + nwarps, ... of the rows
+// this rank owns.  Peers are visited in ring order starting after this rank; a warp polls ONLY the data flag of the
+// peer it is about to read (ld.acquire.sys on this GPU's own memory; the peer raised it by a remote store at the tail
+// of its last enumeration kernel), then reads that peer's occupancy word(s) from the local inbox and pulls just the
+// occupied 4096-token slices (512 B each, one LDG.128 per lane, four slices in flight) straight out of the peer's
+// bitmap buffer over NVLink, OR-ing them into this rank's own rows in place.  When every peer has been read the warps
+// sum the occurrence counts of all B prefixes, and the CTA that finishes last raises ack flag[rank] = seq on every
+// shard ("rank has finished reading your buffers of step seq").
 __global__ void __launch_bounds__(256)
-k_pull_or(const uint32_t *const *__restrict__ peer_masks, uint32_t world, const uint32_t *__restrict__ occ_all,
-          size_t occ_stride, uint32_t row_lo, uint32_t vocab, uint32_t *__restrict__ out) {
+k_xchg_pull(uint32_t *const *__restrict__ peer_masks, uint32_t *const *__restrict__ peer_ack_flags,
+            const uint32_t *__restrict__ data_flags, const uint32_t *__restrict__ inbox, uint32_t xwords, uint32_t count_off,
+            uint32_t world, uint32_t rank, uint32_t B, uint32_t vocab, uint32_t seq, uint64_t *__restrict__ counts_out,
+            uint32_t *__restrict__ done_ctr) {
+    __shared__ uint32_t s_last;
     const uint32_t mask_words = (vocab + 31u) >> 5;
     const uint32_t nslices = (vocab + SLICE - 1) / SLICE, ow = (nslices + 31u) >> 5;
-    const uint32_t r = blockIdx.x, row = row_lo + r;
-    for (uint32_t w = threadIdx.x; w < mask_words; w += 256) {
-        const uint32_t sl = w / (SLICE / 32);
-        uint32_t acc = 0;
-        for (uint32_t p = 0; p < world; ++p)
-            if ((occ_all[(size_t)p * occ_stride + (size_t)row * ow + (sl >> 5)] >> (sl & 31u)) & 1u)
-                acc |= __ldcs(peer_masks[p] + (size_t)row * mask_words + w);
-        out[(size_t)r * mask_words + w] = acc;
-    }
-}
-
-// In-place form: the rows this rank owns already hold its own shard's bits in its own buffer (which no
-// peer reads: peers pull the rows THEY own), so only the peers' occupied slices are touched -- traffic and
-// time proportional to what the other shards actually found.  One CTA per owned row, one WARP per occupied
-// slice (a slice is 128 words = one uint4 per lane), all peer loads of a warp issued before any is consumed:
-// a row costs about one NVLink load latency however many slices it has.
-__global__ void __launch_bounds__(256)
-k_pull_or_inplace(uint32_t *const *__restrict__ peer_masks, uint32_t world, uint32_t rank, const uint32_t *__restrict__ occ_all,
-                  size_t occ_stride, uint32_t row_lo, uint32_t vocab) {
-    const uint32_t mask_words = (vocab + 31u) >> 5;
-    const uint32_t nslices = (vocab + SLICE - 1) / SLICE, ow = (nslices + 31u) >> 5;
-    const uint32_t row = row_lo + blockIdx.x;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t *mine = peer_masks[rank] + (size_t)row * mask_words;
-    for (uint32_t sl = (uint32_t)wid; sl < nslices; sl += 8) {
-        const uint32_t w = sl * (SLICE / 32) + 4u * (uint32_t)lane;
-        if (w >= mask_words) continue;
-        uint4 acc = make_uint4(0, 0, 0, 0);
-        bool any = false;
-        const bool vec = (w + 4u <= mask_words) && ((((size_t)row * mask_words + w) & 3u) == 0);
-        for (uint32_t p = 0; p < world; ++p) {
-            if (p == rank) continue;
-            if (!((occ_all[(size_t)p * occ_stride + (size_t)row * ow + (sl >> 5)] >> (sl & 31u)) & 1u)) continue;
-            const uint32_t *theirs = peer_masks[p] + (size_t)row * mask_words + w;
-            any = true;
-            if (vec) {
-                const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(theirs));
-                acc.x |= v.x; acc.y |= v.y; acc.z |= v.z; acc.w |= v.w;
-            } else {
-                acc.x |= __ldcs(theirs);
-                if (w + 1 < mask_words) acc.y |= __ldcs(theirs + 1);
-                if (w + 2 < mask_words) acc.z |= __ldcs(theirs + 2);
-                if (w + 3 < mask_words) acc.w |= __ldcs(theirs + 3);
+    const uint32_t own = B / world, row_lo = rank * own;
+    const int lane = threadIdx.x & 31;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t *mine = peer_masks[rank];
+    const bool vec_ok = (mask_words & 3u) == 0;  // rows are 16-byte aligned (checked by the launcher for the bases)
+    for (uint32_t k = 1; k < world; ++k) {
+        const uint32_t p = rank + k < world ? rank + k : rank + k - world;
+        if (lane == 0) {
+            const long long t0 = clock64();
+            while ((int32_t)(fm_ld_acquire_sys(data_flags + p) - seq) < 0) {
+                __nanosleep(64);
+                if (clock64() - t0 > 20000000000ll) __trap();
             }
         }
-        if (any && (acc.x | acc.y | acc.z | acc.w)) {
-            mine[w] |= acc.x;
-            if (w + 1 < mask_words) mine[w + 1] |= acc.y;
-            if (w + 2 < mask_words) mine[w + 2] |= acc.z;
-            if (w + 3 < mask_words) mine[w + 3] |= acc.w;
+        __syncwarp();
+        const uint32_t *occ_p = inbox + (size_t)p * xwords;
+        const uint32_t *theirs = peer_masks[p];
+        for (uint32_t r = gw; r < own; r += nwarps) {
+            const uint32_t row = row_lo + r;
+            for (uint32_t ws = 0; ws < ow; ++ws) {
+                uint32_t occ = __ldcg(occ_p + (size_t)row * ow + ws);
+                while (occ) {
+                    uint32_t sl[4];
+                    uint4 v[4];
+                    int cnt = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        sl[j] = 0xFFFFFFFFu;
+                        if (occ) {
+                            sl[j] = ws * 32u + (uint32_t)__ffs(occ) - 1u;
+                            occ &= occ - 1u;
+                            ++cnt;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        v[j] = make_uint4(0u, 0u, 0u, 0u);
+                        if (j < cnt) {
+                            const uint32_t w = sl[j] * (SLICE / 32) + 4u * (uint32_t)lane;
+                            const uint32_t *src = theirs + (size_t)row * mask_words + w;
+                            if (vec_ok && w + 4u <= mask_words) {
+                                v[j] = __ldcs(reinterpret_cast<const uint4 *>(src));
+                            } else {
+                                if (w < mask_words) v[j].x = __ldcs(src);
+                                if (w + 1 < mask_words) v[j].y = __ldcs(src + 1);
+                                if (w + 2 < mask_words) v[j].z = __ldcs(src + 2);
+                                if (w + 3 < mask_words) v[j].w = __ldcs(src + 3);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (j < cnt && (v[j].x | v[j].y | v[j].z | v[j].w)) {
+                            const uint32_t w = sl[j] * (SLICE / 32) + 4u * (uint32_t)lane;
+                            uint32_t *dst = mine + (size_t)row * mask_words + w;
+                            if (w < mask_words) dst[0] |= v[j].x;
+                            if (w + 1 < mask_words) dst[1] |= v[j].y;
+                            if (w + 2 < mask_words) dst[2] |= v[j].z;
+                            if (w + 3 < mask_words) dst[3] |= v[j].w;
+                        }
+                    }
+                }
+            }
         }
     }
-}
-
-// side data of one shard for one step: [B*ow occupancy words][B counts as int64]
-__global__ void __launch_bounds__(256) k_xchg_counts(const uint64_t *__restrict__ sp, const uint64_t *__restrict__ ep, uint32_t B,
-                                                     uint64_t *__restrict__ out) {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < B) out[b] = ep[b] - sp[b];
-}
-__global__ void __launch_bounds__(256) k_xchg_sum_counts(const uint32_t *__restrict__ inbox, uint32_t world, size_t xwords,
-                                                         size_t count_off, uint32_t B, uint64_t *__restrict__ out) {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    uint64_t acc = 0;
-    for (uint32_t p = 0; p < world; ++p)
-        acc += reinterpret_cast<const uint64_t *>(inbox + (size_t)p * xwords + count_off)[b];
-    out[b] = acc;
-}
-
-// ---- NCCL-free signalling for the pull exchange: data + flags written straight into peer memory ---------
-// (one process per GPU; a flag is a monotonically increasing step number, so nothing is ever reset)
-__device__ __forceinline__ uint32_t fm_ld_acquire_sys(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void fm_st_release_sys(uint32_t *p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// CTA d copies this rank's side data into slot `rank` of shard d's inbox, then raises flags[rank] = seq there
-__global__ void __launch_bounds__(256) k_xchg_publish(uint32_t *const *__restrict__ peer_inbox, uint32_t *const *__restrict__ peer_flags,
-                                                      uint32_t rank, const uint32_t *__restrict__ local, size_t xwords, uint32_t seq) {
-    const uint32_t d = blockIdx.x;
-    uint32_t *dst = peer_inbox[d] + (size_t)rank * xwords;
-    if (((xwords & 3) == 0) && ((((uintptr_t)dst | (uintptr_t)local) & 15) == 0)) {
-        const size_t nv = xwords / 4;
-        for (size_t i = threadIdx.x; i < nv; i += 256) reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(local)[i];
-    } else {
-        for (size_t i = threadIdx.x; i < xwords; i += 256) dst[i] = local[i];
+    if (counts_out) {  // every peer's side data has arrived by now (each warp waited for all of them)
+        for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+            uint64_t acc = 0;
+            for (uint32_t p = 0; p < world; ++p)
+                acc += __ldcg(reinterpret_cast<const uint64_t *>(inbox + (size_t)p * xwords + count_off) + b);
+            counts_out[b] = acc;
+        }
     }
-    __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) fm_st_release_sys(peer_flags[d] + rank, seq);
-}
-
-// one CTA, thread p waits until flags[p] >= seq (bounded: traps after ~10 s instead of hanging the GPU)
-__global__ void k_xchg_wait(const uint32_t *__restrict__ flags, uint32_t world, uint32_t seq) {
-    const uint32_t p = threadIdx.x;
-    if (p >= world) return;
-    const long long t0 = clock64();
-    while ((int32_t)(fm_ld_acquire_sys(flags + p) - seq) < 0) {
-        __nanosleep(200);
-        if (clock64() - t0 > 20000000000ll) __trap();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(done_ctr, 1u) == gridDim.x - 1u ? 1u : 0u;
     }
-}
-
-__global__ void k_xchg_signal(uint32_t *const *__restrict__ peer_flags, uint32_t world, uint32_t rank, uint32_t seq) {
-    const uint32_t d = threadIdx.x;
-    if (d >= world) return;
+    __syncthreads();
+    if (!s_last) return;
     __threadfence_system();
-    fm_st_release_sys(peer_flags[d] + rank, seq);
+    if (threadIdx.x < world) fm_st_release_sys(peer_ack_flags[threadIdx.x] + rank, seq);
+    if (threadIdx.x == 0) *done_ctr = 0u;
 }
 
 __global__ void __launch_bounds__(256) k_popcount(const uint32_t *__restrict__ mask, uint32_t mask_words,
@@ -1555,15 +1758,23 @@ static int check_ready(fmidx *h) {
 }
 
 int fm_launch_search(fmidx *h, const int32_t *d_toks, const int64_t *d_offs, size_t B, int64_t shift, uint64_t *d_sp,
-                     uint64_t *d_ep, int raw, cudaStream_t s) {
+                     uint64_t *d_ep, int raw, cudaStream_t s, uint32_t *d_zero_rows, uint32_t zero_words, size_t zero_lo,
+                     size_t zero_n) {
     FM_TRY(check_ready(h));
     if (B == 0) return FMIDX_OK;
     if (B > 0x0FFFFFFFull) { fm_set_error("batch too large"); return FMIDX_EINVAL; }
     const unsigned grid = (unsigned)((B * 16 + 127) / 128);
-    if (raw) FM_LAUNCH(k_search<true>, grid, 128, 0, s, h->dev, d_toks, d_offs, (uint32_t)B, shift, d_sp, d_ep);
-    else FM_LAUNCH(k_search<false>, grid, 128, 0, s, h->dev, d_toks, d_offs, (uint32_t)B, shift, d_sp, d_ep);
+    if (d_zero_rows && ((zero_words & 3u) || ((uintptr_t)d_zero_rows & 15))) d_zero_rows = nullptr;  // caller falls back to k_mask_top
+    const uint32_t zlo = (uint32_t)zero_lo, zn = (uint32_t)std::min<size_t>(zero_n, 0xFFFFFFFFu);
+    if (raw) FM_LAUNCH(k_search<true>, grid, 128, 0, s, h->dev, d_toks, d_offs, (uint32_t)B, shift, d_sp, d_ep, d_zero_rows, zero_words, zlo, zn);
+    else FM_LAUNCH(k_search<false>, grid, 128, 0, s, h->dev, d_toks, d_offs, (uint32_t)B, shift, d_sp, d_ep, d_zero_rows, zero_words, zlo, zn);
     FM_CUDA(cudaGetLastError());
     return FMIDX_OK;
+}
+
+// true when fm_launch_search can zero [B][words] mask rows at d_mask on behalf of fm_launch_mask
+bool fm_search_can_zero(const uint32_t *d_mask, uint32_t vocab) {
+    return d_mask && ((((vocab + 31u) >> 5) & 3u) == 0) && (((uintptr_t)d_mask & 15) == 0);
 }
 
 int fm_launch_step(fmidx *h, const uint64_t *d_sym, const uint64_t *d_lo, const uint64_t *d_hi, size_t B,
@@ -1579,7 +1790,8 @@ int fm_launch_step(fmidx *h, const uint64_t *d_sym, const uint64_t *d_lo, const 
 int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, int64_t shift, uint32_t vocab,
                    const void *d_logits, void *d_out, int dtype, int64_t row_stride, const int32_t *d_override,
                    int32_t always_allow, const uint32_t *d_extra, uint32_t n_extra, uint32_t *d_mask,
-                   uint32_t *d_counts, cudaStream_t s, uint32_t *d_occ, size_t dense_lo, size_t dense_n) {
+                   uint32_t *d_counts, cudaStream_t s, uint32_t *d_occ, size_t dense_lo, size_t dense_n, bool prezeroed,
+                   const FmXchgArgs *xa) {
     FM_TRY(check_ready(h));
     if (B == 0 || vocab == 0) return FMIDX_OK;
     if (!d_occ) { dense_lo = 0; dense_n = B; }  // sparse rows are only meaningful together with occupancy words
@@ -1610,8 +1822,28 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
     const size_t cap = std::min<size_t>((size_t)B * P_leaf, cap_max);
     const size_t items_bytes = has ? 0 : (size_t)B * P_top * 16;
     const size_t bnode_bytes = has || L == 0 ? 0 : cap * 16;
-    FmBuf &ws = h->mask_ws_override ? *h->mask_ws_override : h->mask_ws;
+    // Workspace: a pipelined slot's own (the caller guarantees stream order per slot), else the host-style calls'
+    // (private stream h->stream) and the device-style calls (caller's stream) each have their own, and a workspace
+    // that is used from a different stream than last time first waits for its previous user (event), so neither the
+    // node tables nor the alternating counter pairs are ever shared by two calls in flight.
+    FmBuf &ws = h->mask_ws_override ? *h->mask_ws_override : (s == h->stream ? h->mask_ws_host : h->mask_ws);
+    const bool guarded = !h->mask_ws_override;
+    if (guarded && ws.last_use && ws.last_stream != s) FM_CUDA(cudaStreamWaitEvent(s, ws.last_use, 0));
+    if (ws.p && 128 + lvl_bytes + items_bytes + bnode_bytes + 128 > ws.cap) {
+        // growing frees the old buffer: wait for whoever still runs on it
+        if (ws.last_use) FM_CUDA(cudaEventSynchronize(ws.last_use));
+        else FM_CUDA(cudaStreamSynchronize(s));
+    }
     FM_TRY(fm_scratch(h, ws, 128 + lvl_bytes + items_bytes + bnode_bytes + 128, false));
+    struct Stamp {  // records the workspace's last use on every exit path
+        FmBuf &ws; cudaStream_t s; bool on;
+        ~Stamp() {
+            if (!on) return;
+            if (!ws.last_use && cudaEventCreateWithFlags(&ws.last_use, cudaEventDisableTiming) != cudaSuccess) { ws.last_use = nullptr; return; }
+            cudaEventRecord(ws.last_use, s);
+            ws.last_stream = s;
+        }
+    } stamp{ws, s, guarded};
     // first 128 bytes: two pairs of work-list counters ([0]=#items [1]=#byte nodes / next), used alternately: the last
     // kernel of a call zeroes the pair of the following call, so steady-state calls need no memset
     if (!ws.ctr_clean) {
@@ -1625,19 +1857,38 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
     const size_t items_off = 128 + ((lvl_bytes + 15) & ~(size_t)15);
     uint4 *items = has ? nullptr : (uint4 *)((char *)ws.p + items_off);
     uint4 *bnodes = (uint4 *)((char *)ws.p + items_off + items_bytes);
+    // ranges of up to $FMIDX_SCAN_MAX rows (default 16384) are read off the resident BWT instead of walking the matrix
+    static const uint32_t scan_max = [] {
+        const char *e = getenv("FMIDX_SCAN_MAX");
+        const long v = e && *e ? atol(e) : 16384;
+        return (uint32_t)(v < (long)SCAN_INLINE ? (long)SCAN_INLINE : (v > (1l << 24) ? (1l << 24) : v));
+    }();
+    const uint32_t mwords = (vocab + 31u) >> 5;
+    const uint32_t zflags = (prezeroed ? 1u : 0u) | ((!has && (mwords & 3u) == 0 && ((uintptr_t)d_mask & 15) == 0) ? 2u : 0u);
     FM_LAUNCH(k_mask_top, (unsigned)((B * 32 + 127) / 128), 128, 0, s, ix, d_sp, d_ep, (uint32_t)B, LT, lvl, d_override, shift,
               vocab, items, ctr, has ? nullptr : d_mask, has ? nullptr : d_counts, has ? nullptr : d_occ, (uint32_t)dense_lo,
-              (uint32_t)std::min<size_t>(dense_n, 0xFFFFFFFFu));
+              (uint32_t)std::min<size_t>(dense_n, 0xFFFFFFFFu), zflags, xa && !has ? xa->xcounts : nullptr,
+              xa ? xa->ack_flags : nullptr, xa ? xa->ack_world : 0u, xa ? xa->ack_seq : 0u, L == 0 ? SCAN_INLINE : scan_max);
     if (!has) {
+        // CTAs per SM of the persistent k_mask_bytes grid ($FMIDX_BYTES_OCC, 1..6).  Default 3: the kernel is
+        // issue-bound, and at 5-6 CTAs per SM it owns every register of the GPU for its whole run, which serialises it
+        // against the latency-bound kernels of the other batches in flight.
         static const int occ = [] {
             const char *e = getenv("FMIDX_BYTES_OCC");
-            return e && *e ? atoi(e) : 5;
+            const int v = e && *e ? atoi(e) : 3;
+            return v < 1 ? 1 : (v > 6 ? 6 : v);
         }();
-        const unsigned bgrid = (unsigned)h->sm_count * (occ == 6 ? 6 : 5);
+        const unsigned bgrid = (unsigned)h->sm_count * (unsigned)occ;
+        FmPublish pub{};
+        if (xa && xa->world) {
+            pub.peer_inbox = xa->peer_inbox; pub.peer_flags = xa->peer_data_flags; pub.xlocal = xa->xlocal; pub.done_ctr = xa->done_ctr;
+            pub.xwords = (uint32_t)xa->xwords; pub.world = xa->world; pub.rank = xa->rank; pub.seq = xa->seq;
+        }
 #define FM_BYTES(LIST, CNT, CAP)                                                                                             \
     do {                                                                                                                     \
-        if (occ == 6) FM_LAUNCH(k_mask_bytes<6>, bgrid, BYTES_THREADS, 0, s, ix, shift, vocab, LIST, CNT, CAP, d_mask, d_counts, ctr_next); \
-        else FM_LAUNCH(k_mask_bytes<5>, bgrid, BYTES_THREADS, 0, s, ix, shift, vocab, LIST, CNT, CAP, d_mask, d_counts, ctr_next); \
+        if (occ >= 6) FM_LAUNCH(k_mask_bytes<6>, bgrid, BYTES_THREADS, 0, s, ix, shift, vocab, LIST, CNT, CAP, d_mask, d_counts, ctr_next, pub); \
+        else if (occ >= 4) FM_LAUNCH(k_mask_bytes<5>, bgrid, BYTES_THREADS, 0, s, ix, shift, vocab, LIST, CNT, CAP, d_mask, d_counts, ctr_next, pub); \
+        else FM_LAUNCH(k_mask_bytes<3>, bgrid, BYTES_THREADS, 0, s, ix, shift, vocab, LIST, CNT, CAP, d_mask, d_counts, ctr_next, pub); \
     } while (0)
         if (L == 0) {  // the root is itself a byte-level node: the item list is the node list
             FM_BYTES(items, ctr, (uint32_t)(B * P_top));
@@ -1660,10 +1911,10 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
     const unsigned grid = (unsigned)nblk;
 #define FM_MASK_CASE(DT, VECT)                                                                                     \
     FM_LAUNCH((k_mask_logits<DT, VECT>), grid, MASK_THREADS, 0, s, ix, lvl + top_off, P_top, LT, shift, vocab, d_logits, \
-              d_out, row_stride, d_override, always_allow, d_extra, n_extra, (uint32_t)B, d_mask)
+              d_out, row_stride, d_override, always_allow, d_extra, n_extra, (uint32_t)B, d_mask, d_sp, d_ep)
 #define FM_MASK_TMA(DT)                                                                                            \
     FM_LAUNCH((k_mask_logits_tma<DT>), grid, MASK_THREADS, 0, s, ix, lvl + top_off, P_top, LT, shift, vocab, d_logits,   \
-              d_out, row_stride, d_override, always_allow, d_extra, n_extra, (uint32_t)B, d_mask)
+              d_out, row_stride, d_override, always_allow, d_extra, n_extra, (uint32_t)B, d_mask, d_sp, d_ep)
     // FMIDX_LOGITS_PATH = regs (default: one-shot CTAs, logits staged in registers -- the fastest measured,
     // 0.83 of HBM bandwidth on narrow beams) | tma (one-shot CTAs, one bulk async copy each way) | pipe
     // (persistent CTAs, multi-stage bulk-copy ring).  The TMA variants are kept selectable: they match the
@@ -1686,7 +1937,7 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
         }                                                                                                           \
         FM_LAUNCH((k_mask_logits_pipe<DT>), pgrid, MASK_THREADS, dyn, s, ix, lvl + top_off, P_top, LT, shift, vocab,    \
                   d_logits, d_out, row_stride, d_override, always_allow, d_extra, n_extra, (uint32_t)B, d_mask,     \
-                  (uint32_t)nblk, ctr + 1);                                                                                \
+                  (uint32_t)nblk, ctr + 1, d_sp, d_ep);                                                                    \
     } while (0)
         if (dtype == FMIDX_F32) FM_MASK_PIPE(FMIDX_F32);
         else if (dtype == FMIDX_BF16) FM_MASK_PIPE(FMIDX_BF16);
@@ -1733,60 +1984,15 @@ int fm_launch_or(fmidx *h, const uint32_t *d_pieces, uint32_t n_pieces, size_t n
     return FMIDX_OK;
 }
 
-int fm_launch_pull_or(fmidx *h, const uint32_t *const *d_peer_masks, uint32_t world, const uint32_t *d_occ_all,
-                      size_t occ_stride, size_t row_lo, size_t n_rows, uint32_t vocab, uint32_t *d_out, cudaStream_t s) {
-    (void)h;
-    if (n_rows == 0) return FMIDX_OK;
-    FM_LAUNCH(k_pull_or, (unsigned)n_rows, 256, 0, s, d_peer_masks, world, d_occ_all, occ_stride, (uint32_t)row_lo, vocab, d_out);
-    FM_CUDA(cudaGetLastError());
-    return FMIDX_OK;
-}
-
-int fm_launch_pull_or_inplace(fmidx *h, uint32_t *const *d_peer_masks, uint32_t world, uint32_t rank, const uint32_t *d_occ_all,
-                              size_t occ_stride, size_t row_lo, size_t n_rows, uint32_t vocab, cudaStream_t s) {
-    (void)h;
-    if (n_rows == 0) return FMIDX_OK;
-    static_assert(SLICE / 32 == 128, "k_pull_or_inplace maps one lane to four words of a slice");
-    FM_LAUNCH(k_pull_or_inplace, (unsigned)n_rows, 256, 0, s, d_peer_masks, world, rank, d_occ_all, occ_stride, (uint32_t)row_lo, vocab);
-    FM_CUDA(cudaGetLastError());
-    return FMIDX_OK;
-}
-
-int fm_launch_xchg_counts(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, uint64_t *d_out, cudaStream_t s) {
-    (void)h;
-    if (B == 0) return FMIDX_OK;
-    FM_LAUNCH(k_xchg_counts, (unsigned)((B + 255) / 256), 256, 0, s, d_sp, d_ep, (uint32_t)B, d_out);
-    FM_CUDA(cudaGetLastError());
-    return FMIDX_OK;
-}
-
-int fm_launch_xchg_sum_counts(fmidx *h, const uint32_t *d_inbox, uint32_t world, size_t xwords, size_t count_off, size_t B,
-                              uint64_t *d_out, cudaStream_t s) {
-    (void)h;
-    if (B == 0) return FMIDX_OK;
-    FM_LAUNCH(k_xchg_sum_counts, (unsigned)((B + 255) / 256), 256, 0, s, d_inbox, world, xwords, count_off, (uint32_t)B, d_out);
-    FM_CUDA(cudaGetLastError());
-    return FMIDX_OK;
-}
-
-int fm_launch_xchg_publish(fmidx *h, uint32_t *const *d_peer_inbox, uint32_t *const *d_peer_flags, uint32_t world, uint32_t rank,
-                           const uint32_t *d_local, size_t xwords, uint32_t seq, cudaStream_t s) {
-    (void)h;
-    FM_LAUNCH(k_xchg_publish, world, 256, 0, s, d_peer_inbox, d_peer_flags, rank, d_local, xwords, seq);
-    FM_CUDA(cudaGetLastError());
-    return FMIDX_OK;
-}
-
-int fm_launch_xchg_wait(fmidx *h, const uint32_t *d_flags, uint32_t world, uint32_t seq, cudaStream_t s) {
-    (void)h;
-    FM_LAUNCH(k_xchg_wait, 1, 32 * ((world + 31) / 32), 0, s, d_flags, world, seq);
-    FM_CUDA(cudaGetLastError());
-    return FMIDX_OK;
-}
-
-int fm_launch_xchg_signal(fmidx *h, uint32_t *const *d_peer_flags, uint32_t world, uint32_t rank, uint32_t seq, cudaStream_t s) {
-    (void)h;
-    FM_LAUNCH(k_xchg_signal, 1, 32 * ((world + 31) / 32), 0, s, d_peer_flags, world, rank, seq);
+int fm_launch_xchg_pull(fmidx *h, uint32_t *const *d_peer_masks, uint32_t *const *d_peer_ack_flags, const uint32_t *d_data_flags,
+                        const uint32_t *d_inbox, size_t xwords, size_t count_off, uint32_t world, uint32_t rank, size_t B, uint32_t vocab,
+                        uint32_t seq, uint64_t *d_counts_out, uint32_t *d_done_ctr, cudaStream_t s) {
+    if (B == 0 || world == 0) return FMIDX_OK;
+    const size_t own = B / world;
+    const size_t warps = std::max<size_t>(own, (B + 31) / 32);
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((warps + 7) / 8, (size_t)h->sm_count * 2));
+    FM_LAUNCH(k_xchg_pull, grid, 256, 0, s, d_peer_masks, d_peer_ack_flags, d_data_flags, d_inbox, (uint32_t)xwords, (uint32_t)count_off,
+              world, rank, (uint32_t)B, vocab, seq, d_counts_out, d_done_ctr);
     FM_CUDA(cudaGetLastError());
     return FMIDX_OK;
 }

@@ -48,6 +48,8 @@ struct FmDev {
     const uint32_t *sa_samples;  // sa_dens==1: SA[row] ; else SA value of the k-th marked row
     const uint32_t *isa_samples; // ISA[k*isa_dens]
     const uint32_t *text;        // optional resident text T (n entries) or nullptr
+    const uint32_t *bwt;         // optional resident BWT as plain u32 symbols (n entries) or nullptr: the rows of a range are
+                                 // CONTIGUOUS here, so the distinct symbols of a narrow / mid-sized range are one coalesced read
     uint64_t level_stride;       // uint4 per level = nblocks*8
     uint32_t n;                  // csa.size(): text length incl. the 0 sentinel
     uint32_t max_sym;

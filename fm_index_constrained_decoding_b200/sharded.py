@@ -107,6 +107,8 @@ class ShardedFMIndex:
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        self._send = None
+        self._rng = None
 
     # ranges are shard-local and never reduced
     def get_range_batch(self, toks, offs):
@@ -123,17 +125,19 @@ class ShardedFMIndex:
         return or_reduce_scatter(local, self.group, self.index)[1]
 
     def mask_logits_rows(self, sp, ep, logits_rows, override_tok=None, always_allow=-1):
-        """Fused step for the rows this rank owns: logits_rows [B/world, V] are the logits of beams
-        [rank*B/world, (rank+1)*B/world).  sp/ep are this shard's ranges of ALL B beams.
-        The rows owned by OTHER ranks are enumerated into bitmaps and exchanged (all-to-all); the
-        rows owned by this rank are enumerated inside the fused kernel, which ORs the pieces
-        received from the other shards while it streams the logits."""
+        """Fused step for the rows this rank owns, from ranges (NCCL all-to-all form; CPU-testable plumbing):
+        logits_rows [B/world, V] are the logits of beams [rank*B/world, (rank+1)*B/world), sp/ep this shard's ranges
+        of ALL B beams.  The rows owned by OTHER ranks are enumerated into bitmaps and exchanged; the rows owned by
+        this rank are enumerated inside the fused kernel, which ORs the pieces received from the other shards while
+        it streams the logits.  On GPUs prefer decode_step(): same result through the peer-memory exchange."""
         B = sp.numel()
         own = B // self.world
         V = logits_rows.shape[1]
         words = (V + 31) // 32
         lo, hi = self.rank * own, (self.rank + 1) * own
-        send = torch.zeros((B, words), dtype=torch.int32, device=sp.device)
+        if self._send is None or self._send.shape != (B, words) or self._send.device != sp.device:
+            self._send = torch.zeros((B, words), dtype=torch.int32, device=sp.device)  # own rows stay zero for good
+        send = self._send
         if lo > 0:
             self.index.distinct_mask_batch(sp[:lo].contiguous(), ep[:lo].contiguous(), V, out=send[:lo])
         if hi < B:
@@ -144,6 +148,26 @@ class ShardedFMIndex:
         ovr = override_tok[lo:hi].contiguous() if override_tok is not None else None
         return self.index.mask_logits(sp[lo:hi].contiguous(), ep[lo:hi].contiguous(), logits_rows,
                                       override_tok=ovr, always_allow=always_allow, extra_masks=others)
+
+    def decode_step(self, step, set_index, toks, offs, logits_rows, override_tok=None, always_allow=-1, stream=None):
+        """The fused constrained-decoding step of a document-sharded index over the peer-memory exchange (no NCCL, no
+        per-step allocation): `step` is a ShardStep for B beams; toks/offs the B replicated beam histories;
+        logits_rows [B/world, V] the logits of the beams this rank owns.  One sharded step (search + enumeration +
+        exchange -> final bitmaps of the owned rows), then the logits kernel applies them (x + 0.0 / x + -inf,
+        override rows, always-allowed token) while it streams the rows.  Returns (masked rows, total counts [B])."""
+        own, lo = step.own, step.rank * step.own
+        if self._rng is None or self._rng[0].numel() != step.B or self._rng[0].device != logits_rows.device:
+            self._rng = (torch.empty(step.B, dtype=torch.int64, device=logits_rows.device),
+                         torch.empty(step.B, dtype=torch.int64, device=logits_rows.device),
+                         torch.zeros(own, dtype=torch.int64, device=logits_rows.device))
+        sp, ep, zero = self._rng
+        s = stream if stream is not None else step.streams[set_index]
+        masks, counts = step.step(set_index, toks, offs, sp, ep, stream=s)
+        ovr = override_tok[lo:lo + own].contiguous() if override_tok is not None else None
+        with torch.cuda.stream(s):
+            out = self.index.mask_logits(zero, zero, logits_rows, override_tok=ovr, always_allow=always_allow,
+                                         extra_masks=masks.unsqueeze(0))
+        return out, counts
 
     def locate_topk(self, sp, ep, k):
         """First k rows of every range located on this shard, all-gathered as global positions."""
@@ -156,150 +180,88 @@ class ShardedFMIndex:
 class _RawCuda:
     """Exposes a raw device pointer through __cuda_array_interface__ so torch can view it."""
 
-    def __init__(self, ptr, n_words):
-        self.__cuda_array_interface__ = {"shape": (n_words,), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
+    def __init__(self, ptr, n, typestr="<i4"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
-class PeerMaskExchange:
-    """OR-reduce-scatter of the per-shard bitmaps by PULLING over NVLink peer memory -- no NCCL in the loop.
+class ShardStep:
+    """One shard's side of the document-sharded step, over the C context `fmidx_shard_*` (include/fmidx.h).
 
-    The dense all-to-all moves 16 KB per prefix per shard although a prefix with a few tokens of history has a
-    handful of continuations.  Here every rank keeps its [B, words] bitmaps in a peer-visible buffer (CUDA IPC,
-    fmidx_ipc_*) together with one occupancy word per row (bit s: 4096-token slice s may be non-empty, produced
-    by the mask kernels themselves).  Per step (all kernels of this library, data and flags written straight
-    into peer memory):
-      publish  this shard's occupancy words + occurrence counts -> slot `rank` of every shard's inbox, then
-               flag[rank] = step on every shard                                (fmidx_xchg_publish)
-      wait     a one-CTA kernel spins until every shard's flag reached this step   (fmidx_xchg_wait)
-      pull     for the rows this rank owns, read only the occupied slices out of the peers' bitmaps and OR
-               them                                                              (fmidx_mask_pull_or)
-      ack      ack[rank] = step on every shard                                  (fmidx_xchg_signal)
-    `n_buffers` buffer sets, each with its own flags and step counter: the sets are independent, so set i's kernels
-    and exchange can run back to back on "its" stream while the other sets' steps overlap them on theirs (bench.py:
-    4 sets, 4 streams).  Before a set is overwritten, compute_local waits for every shard's ack of the step that
-    last used it.
+    step(set, toks, offs) enqueues ONE whole step -- search of all B replicated prefixes on this shard, enumeration
+    into peer-visible bitmaps (+ slice-occupancy words and occurrence counts), publication into every shard's inbox
+    at the tail of the last enumeration kernel, and the fused wait + pull + OR + total-counts + ack kernel -- with one
+    host call and five launches, no NCCL.  Afterwards rank r owns the final bitmaps of prefixes
+    [r*B/world, (r+1)*B/world) and the total occurrence counts of all B prefixes.  `n_sets` independent buffer sets:
+    steps on different sets may be in flight on different streams; every rank must issue the same steps on the same
+    sets in the same order.  `group`: the process group whose ranks hold the shards (hybrid: one group per replica).
     """
 
-    def __init__(self, index, B, vocab, n_buffers=3, group=None):
+    def __init__(self, index, B, vocab, n_sets=4, group=None):
         import ctypes as C
         from . import _native as N
         self.index, self.group = index, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        assert B % self.world == 0
-        self.B, self.vocab, self.own = B, vocab, B // self.world
+        assert B % self.world == 0, "pad the batch to a multiple of the number of shards"
+        self.B, self.vocab, self.own, self.n = B, vocab, B // self.world, n_sets
         self.words = (vocab + 31) // 32
-        self.ow = ((vocab + 4095) // 4096 + 31) // 32
-        self.n = n_buffers
         self.dev = dev = torch.device("cuda", index.device_index)
-        self._local, self._peers = [], []
-        # side data of one shard for one step: occupancy words, then the occurrence counts (ep - sp) as int64
-        self.xwords = B * self.ow + 2 * B
-        self.mask_ptr, self.mask_tables, self.local_views = [], [], []
-        self.inbox_ptr, self.inbox_tables, self.inbox_views = [], [], []
-        for _ in range(n_buffers):
-            ptr, table = self._shared(B * self.words * 4)
-            self.mask_ptr.append(ptr)
-            self.mask_tables.append(table)
-            self.local_views.append(torch.as_tensor(_RawCuda(ptr, B * self.words), device=dev).view(B, self.words))
-            ptr, table = self._shared(self.world * self.xwords * 4)
-            self.inbox_ptr.append(ptr)
-            self.inbox_tables.append(table)
-            self.inbox_views.append(torch.as_tensor(_RawCuda(ptr, self.world * self.xwords), device=dev).view(self.world, self.xwords))
-        # every buffer set has its OWN data / ack flags and step counter, so the exchanges of different sets are
-        # independent and may run on different streams (set i: flags[i][0:world] data of step s published by rank r,
-        # flags[i][world:2*world] step s pulled by rank r)
-        fptr, ftable = self._shared(n_buffers * 2 * self.world * 4)
-        self.flags = torch.as_tensor(_RawCuda(fptr, n_buffers * 2 * self.world), device=dev)
-        self.flags.zero_()
-        self.data_flag_tables = [ftable + 8 * self.world * i for i in range(n_buffers)]
-        self.ack_flag_tables = [ftable + 8 * self.world * i + 4 * self.world for i in range(n_buffers)]
-        self.xlocal = [torch.empty(self.xwords, dtype=torch.int32, device=dev) for _ in range(n_buffers)]
-        self.counts = [torch.empty(B, dtype=torch.int64, device=dev) for _ in range(n_buffers)]
-        self.own_views = [v[self.rank * self.own:(self.rank + 1) * self.own] for v in self.local_views]
-        self.seq = [0] * n_buffers
-        self.last_seq = [0] * n_buffers
-        # ctypes views of the fixed pointers (built once: two host calls per step is all the Python there is)
-        self._c_mask = [C.c_void_p(p) for p in self.mask_ptr]
-        self._c_inbox = [C.c_void_p(p) for p in self.inbox_ptr]
-        self._c_xlocal = [C.c_void_p(t.data_ptr()) for t in self.xlocal]
-        self._c_counts = [C.c_void_p(t.data_ptr()) for t in self.counts]
-        self._c_mask_tables = [C.c_void_p(t.data_ptr()) for t in self.mask_tables]
-        self._c_inbox_tables = [C.c_void_p(t.data_ptr()) for t in self.inbox_tables]
-        self._c_flags = [C.c_void_p(self.flags.data_ptr() + 8 * self.world * i) for i in range(n_buffers)]
-        self._c_ack = [C.c_void_p(self.flags.data_ptr() + 8 * self.world * i + 4 * self.world) for i in range(n_buffers)]
-        self._c_data_flag_table = [C.c_void_p(t.data_ptr()) for t in self.data_flag_tables]
-        self._c_ack_flag_table = [C.c_void_p(t.data_ptr()) for t in self.ack_flag_tables]
+        L = self._L = N.lib()
+        x = C.c_void_p()
+        N.check(L.fmidx_shard_create(index._h, self.world, self.rank, B, vocab, n_sets, C.byref(x)))
+        self._x = x
+        # handle exchange (plumbing): kind 0 = bitmaps of a set, 1 = inbox of a set, 2 = the flag block
+        mine = []
+        for kind, sets in ((0, range(n_sets)), (1, range(n_sets)), (2, (0,))):
+            for i in sets:
+                hd = (C.c_ubyte * 64)()
+                N.check(L.fmidx_shard_export(x, i, kind, hd))
+                mine.append((kind, i, bytes(hd)))
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=group)
+        for r, items in enumerate(everyone):
+            if r == self.rank:
+                continue
+            for kind, i, hb in items:
+                N.check(L.fmidx_shard_import(x, i, kind, r, (C.c_ubyte * 64).from_buffer_copy(hb)))
+        N.check(L.fmidx_shard_ready(x))
+        self.own_masks, self.counts, self.streams = [], [], []
+        for i in range(n_sets):
+            pm, pc, ps = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            N.check(L.fmidx_shard_result(x, i, C.byref(pm), C.byref(pc), C.byref(ps)))
+            self.own_masks.append(torch.as_tensor(_RawCuda(pm.value, self.own * self.words), device=dev).view(self.own, self.words))
+            self.counts.append(torch.as_tensor(_RawCuda(pc.value, B, "<i8"), device=dev))
+            self.streams.append(torch.cuda.ExternalStream(ps.value, device=dev))
         torch.cuda.synchronize()
         dist.barrier(group=group)
 
-    def _shared(self, nbytes):
-        """Allocate a peer-visible buffer; returns (local pointer, device table of every rank's pointer to its copy)."""
+    def step(self, i, toks, offs, sp, ep, shift=10, stream=None):
+        """Enqueue the step of buffer set i (stream: a torch stream, default the set's own).  sp/ep (int64 [B], CUDA)
+        receive this shard's ranges.  Returns (final bitmaps of the owned rows [B/world, words], total counts [B])."""
         import ctypes as C
         from . import _native as N
-        L = N.lib()
-        ptr = C.c_void_p()
-        handle = (C.c_ubyte * 64)()
-        N.check(L.fmidx_ipc_alloc(self.index._h, nbytes, C.byref(ptr), handle))
-        handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(handle), group=self.group)
-        ptrs = []
-        for r in range(self.world):
-            if r == self.rank:
-                ptrs.append(ptr.value)
-            else:
-                q = C.c_void_p()
-                hb = (C.c_ubyte * 64).from_buffer_copy(handles[r])
-                N.check(L.fmidx_ipc_open(self.index._h, hb, C.byref(q)))
-                ptrs.append(q.value)
-                self._peers.append(q.value)
-        self._local.append(ptr.value)
-        return ptr.value, torch.tensor(ptrs, dtype=torch.int64, device=self.dev)
+        sptr = C.c_void_p(stream.cuda_stream) if stream is not None else None
+        N.check(self._L.fmidx_shard_step(self._x, i, C.c_void_p(toks.data_ptr()), C.c_void_p(offs.data_ptr()), shift,
+                                         C.c_void_p(sp.data_ptr()), C.c_void_p(ep.data_ptr()), sptr))
+        return self.own_masks[i], self.counts[i]
 
-    @staticmethod
-    def _s():
-        import ctypes as C
-        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
-
-    def compute_local(self, i, sp, ep, shift=10, ws_slot=-1, stream=None):
-        """K2 of this shard for all B prefixes into buffer set i (bitmaps + occupancy words + counts); first waits
-        (on the GPU) until every shard has pulled the step that last used set i.  ws_slot: the enumeration's scratch
-        workspace (give every stream that may run concurrently its own, 0..7).  stream: a torch stream (default: the
-        current one; passing it avoids a stream context switch per step -- the host is the bottleneck here)."""
+    def submit(self, i, toks, offs, sp, ep, counts=None, n_distinct_own=None, shift=10):
+        """Host-buffer form on the set's own stream (pinned CPU tensors in and out); wait(i) blocks until they hold the
+        results."""
         import ctypes as C
         from . import _native as N
-        sptr = self._s() if stream is None else C.c_void_p(stream.cuda_stream)
-        N.check(N.lib().fmidx_xchg_local(
-            self.index._h, C.c_void_p(sp.data_ptr()), C.c_void_p(ep.data_ptr()), self.B, shift, self.vocab,
-            self._c_mask[i], self._c_xlocal[i], self._c_ack[i], self.world, self.rank, self.last_seq[i], ws_slot, sptr))
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+        N.check(self._L.fmidx_shard_submit(self._x, i, p(toks), p(offs), shift, p(sp), p(ep), p(counts), p(n_distinct_own)))
 
-    def exchange(self, i, stream=None):
-        """publish -> wait -> pull + OR (in place) -> total counts -> ack for buffer set i, ONE host call on `stream`
-        (default: the current one).  Returns the final [B/world, words] bitmaps of the rows this rank owns (a view
-        of set i)."""
-        import ctypes as C
+    def wait(self, i):
         from . import _native as N
-        sptr = self._s() if stream is None else C.c_void_p(stream.cuda_stream)
-        self.seq[i] += 1
-        N.check(N.lib().fmidx_xchg_round(
-            self.index._h, self._c_mask_tables[i], self._c_inbox_tables[i], self._c_data_flag_table[i], self._c_ack_flag_table[i],
-            self._c_flags[i], self._c_inbox[i], self._c_xlocal[i],
-            self.world, self.rank, self.B, self.vocab, self.seq[i], self._c_counts[i], sptr))
-        self.last_seq[i] = self.seq[i]
-        return self.own_views[i]
-
-    def total_counts(self, i):
-        """Sum over shards of the occurrence counts of all B prefixes (they rode in the published side data and
-        were summed by exchange())."""
-        return self.counts[i]
+        N.check(self._L.fmidx_shard_wait(self._x, i))
 
     def close(self):
-        import ctypes as C
-        from . import _native as N
+        if self._x is None:
+            return
         torch.cuda.synchronize()
+        dist.barrier(group=self.group)  # nobody is still pulling from anybody
+        self.own_masks, self.counts = [], []
+        self._L.fmidx_shard_destroy(self._x)
+        self._x = None
         dist.barrier(group=self.group)
-        for q in self._peers:
-            N.lib().fmidx_ipc_close(self.index._h, C.c_void_p(q))
-        dist.barrier(group=self.group)
-        for p in self._local:
-            N.lib().fmidx_ipc_free(self.index._h, C.c_void_p(p))
-        self._peers, self._local = [], []

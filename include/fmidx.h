@@ -110,46 +110,41 @@ int fmidx_distinct_mask_batch(fmidx_t *h, const uint64_t *d_sp, const uint64_t *
 int fmidx_query_batch(fmidx_t *h, int ws_slot, const int32_t *d_toks, const int64_t *d_offs, size_t B, int64_t shift,
                       uint32_t vocab, uint64_t *d_sp, uint64_t *d_ep, uint32_t *d_mask, void *stream);
 /* same, additionally filling d_occ ([B][ceil(nslices/32)] u32, nslices = ceil(vocab/4096)): bit s of a row is set
- * when the row's 4096-token slice s may hold set bits (conservative).  Feeds fmidx_mask_pull_or. */
+ * when the row's 4096-token slice s may hold set bits (conservative).  The sharded step publishes these words to the peers. */
 int fmidx_distinct_mask_batch_occ(fmidx_t *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, int64_t shift,
                                   uint32_t vocab, uint32_t *d_mask, uint32_t *d_counts, uint32_t *d_occ, void *stream);
-/* Cross-shard OR by pulling over NVLink: d_peer_masks is a DEVICE array of `world` pointers to the shards'
- * [B][ceil(vocab/32)] bitmaps (the local one and the peers' buffers opened with fmidx_ipc_open), d_occ_all the
- * all-gathered occupancy words, shard p's row r at d_occ_all[p*occ_stride + r*ow ...] (occ_stride in u32 words, so
- * other per-shard data can ride in the same all-gather).  Rows [row_lo, row_lo+n_rows) are OR-ed into d_out [n_rows][words];
- * only occupied slices are read.  The caller orders this call after the peers' mask kernels (e.g. with the
- * all-gather of the occupancy words on the same stream). */
-int fmidx_mask_pull_or(fmidx_t *h, const uint64_t *d_peer_masks, uint32_t world, const uint32_t *d_occ_all,
-                       size_t occ_stride, size_t row_lo, size_t n_rows, uint32_t vocab, uint32_t *d_out, void *stream);
-/* in-place form: rows [row_lo, row_lo+n_rows) of THIS rank's bitmap buffer (d_peer_masks[rank], which already holds
- * this shard's bits and which no peer reads for those rows) receive the OR of the peers' occupied slices */
-int fmidx_mask_pull_or_inplace(fmidx_t *h, const uint64_t *d_peer_masks, uint32_t world, uint32_t rank, const uint32_t *d_occ_all,
-                               size_t occ_stride, size_t row_lo, size_t n_rows, uint32_t vocab, void *stream);
-/* NCCL-free signalling for that exchange, all over peer memory (one process per GPU).  Flags hold monotonically
- * increasing step numbers.  publish: copy d_local (xwords u32: occupancy words + anything else per shard) into slot
- * `rank` of every shard's inbox (d_peer_inbox[d] + rank*xwords), fence, then set d_peer_flags[d][rank] = seq.
- * wait: one tiny kernel that spins (bounded, traps after ~10 s) until d_flags[p] >= seq for all p < world.
- * signal: set d_peer_flags[d][rank] = seq on every shard (acknowledgements). */
-int fmidx_xchg_publish(fmidx_t *h, const uint64_t *d_peer_inbox, const uint64_t *d_peer_flags, uint32_t world, uint32_t rank,
-                       const uint32_t *d_local, size_t xwords, uint32_t seq, void *stream);
-int fmidx_xchg_wait(fmidx_t *h, const uint32_t *d_flags, uint32_t world, uint32_t seq, void *stream);
-int fmidx_xchg_signal(fmidx_t *h, const uint64_t *d_peer_flags, uint32_t world, uint32_t rank, uint32_t seq, void *stream);
-/* The two halves of a sharded step, one host call each.  Side data of a shard (xwords = B*ow + 2*B u32): the
- * occupancy words, then the B occurrence counts (ep - sp) as u64.
- * local: [wait until every shard acknowledged step wait_seq, if non-zero] -> K2 with occupancy into d_mask / d_xlocal
- *        -> counts into d_xlocal.  Only rows [rank*B/world, (rank+1)*B/world) of d_mask come out as complete bitmaps;
- *        the other rows are valid in their OCCUPIED slices only (that is all the peers ever read).
- * round: publish d_xlocal to every inbox + data flag = seq -> wait for all data flags -> pull + OR the peers' occupied
- *        slices into this rank's rows of its own bitmap buffer -> total counts of all B prefixes into d_counts_out
- *        (optional) -> ack flag = seq on every shard.
- * ws_slot: scratch workspace of the enumeration as in fmidx_query_batch (-1: the handle's default workspace). */
-int fmidx_xchg_local(fmidx_t *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, int64_t shift, uint32_t vocab,
-                     uint32_t *d_mask, uint32_t *d_xlocal, const uint32_t *d_ack_flags, uint32_t world, uint32_t rank,
-                     uint32_t wait_seq, int ws_slot, void *stream);
-int fmidx_xchg_round(fmidx_t *h, const uint64_t *d_peer_masks, const uint64_t *d_peer_inbox, const uint64_t *d_peer_data_flags,
-                     const uint64_t *d_peer_ack_flags, const uint32_t *d_data_flags, const uint32_t *d_inbox,
-                     const uint32_t *d_xlocal, uint32_t world, uint32_t rank, size_t B, uint32_t vocab, uint32_t seq,
-                     uint64_t *d_counts_out, void *stream);
+/* ---- document-sharded step; no reference counterpart: the reference's only parallelism is one
+ * std::async per range (fm_index.cpp:146-166) --------------------------------------------------------------------
+ * One process per GPU, each holding the index of its own document shard; the B prefixes of a step are replicated.
+ * A shard context owns n_sets (<= 8) independent buffer sets in peer-visible memory (CUDA IPC): [B][ceil(vocab/32)]
+ * bitmaps, an inbox with one slot per shard (slice-occupancy words + occurrence counts), data / ack flags.  Set-up: every
+ * rank creates its context, exports the 64-byte handles of its buffers (kind 0 = bitmaps of a set, 1 = inbox of a set,
+ * 2 = the flag block of all sets), the host language exchanges them (torch.distributed all_gather_object), every rank
+ * imports every peer's, then fmidx_shard_ready.
+ * fmidx_shard_step enqueues ONE whole step of set `set` on `stream` (NULL: the set's own stream) with five launches and
+ * no NCCL: search (also zeroes the owned rows) -> enumeration into bitmaps + occupancy + counts (first waits on the GPU
+ * for every shard's ack of the step that last used the set; the CTA that finishes last publishes the side data into
+ * every shard's inbox and raises the data flags) -> per peer: wait for its data flag, pull its occupied 4096-token slices
+ * over NVLink, OR them into the rows this rank owns; total counts; ack.  Afterwards (stream-ordered) rank r owns the final
+ * bitmaps of prefixes [r*B/world, (r+1)*B/world) and the total occurrence counts of all B prefixes (fmidx_shard_result).
+ * d_sp/d_ep receive THIS shard's ranges (ranges are shard-local and never reduced).  Steps on different sets may be in
+ * flight on different streams; every rank must issue the same steps on the same sets in the same order.
+ * fmidx_shard_submit / fmidx_shard_wait: host-buffer form on the set's own stream (H2D of the prefixes and D2H of the
+ * ranges, total counts and distinct-token counts of the owned prefixes inside the call). */
+typedef struct fmidx_shard fmidx_shard_t;
+int fmidx_shard_create(fmidx_t *h, uint32_t world, uint32_t rank, size_t B, uint32_t vocab, uint32_t n_sets,
+                       fmidx_shard_t **out);
+int fmidx_shard_export(fmidx_shard_t *x, uint32_t set, int kind, unsigned char handle[64]);
+int fmidx_shard_import(fmidx_shard_t *x, uint32_t set, int kind, uint32_t peer, const unsigned char handle[64]);
+int fmidx_shard_ready(fmidx_shard_t *x);
+int fmidx_shard_step(fmidx_shard_t *x, uint32_t set, const int32_t *d_toks, const int64_t *d_offs, int64_t shift, uint64_t *d_sp,
+                     uint64_t *d_ep, void *stream);
+int fmidx_shard_result(fmidx_shard_t *x, uint32_t set, uint32_t **d_own_masks, uint64_t **d_counts, void **stream);
+int fmidx_shard_submit(fmidx_shard_t *x, uint32_t set, const int32_t *toks, const int64_t *offs, int64_t shift, uint64_t *sp,
+                       uint64_t *ep, uint64_t *counts, uint32_t *n_distinct_own);
+int fmidx_shard_wait(fmidx_shard_t *x, uint32_t set);
+/* every rank: after a barrier that follows its last step (peers may still be pulling otherwise) */
+void fmidx_shard_destroy(fmidx_shard_t *x);
 /* peer-visible device buffers (CUDA IPC): alloc on the owner, ship the 64-byte handle, open on the peers */
 int fmidx_ipc_alloc(fmidx_t *h, size_t bytes, void **d_ptr, unsigned char handle[64]);
 int fmidx_ipc_open(fmidx_t *h, const unsigned char handle[64], void **d_ptr);
