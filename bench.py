@@ -1,30 +1,35 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the FM-index query path (BASELINE.json configs[1]).
+"""bench.py -- benchmark of the FM-index query path (BASELINE.json).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
-                    [--tokens 100000000] [--batch 4096]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
-One STEP = one batch of `--batch` ragged prefixes (length 1..32, substrings of corpus documents)
-pushed through the hot path on a device-resident index of a synthetic `--tokens`-token corpus
-(vocab 128,256): K1 batched backward search -> [sp,ep), then K2 distinct-next-token enumeration
--> one 128,256-bit vocab mask per prefix.  `value` = prefixes/s with inputs resident in HBM,
-consecutive (independent) steps kept in flight on 4 streams through fmidx_query_batch; the roofline's
-per-kernel durations come from a serial pass of the same steps.  `e2e` = the same through the
-host-buffer C-ABI call (fmidx_query_submit / fmidx_query_wait: H2D of the prefixes, D2H of ranges and the
-per-prefix distinct counts inside the timed region).  Multi-GPU (N>1): the corpus is sharded by
-document, one 100M-token shard per GPU (weak scaling), prefixes are replicated, per-shard masks
-are OR-reduced by the peer-memory pull exchange (own kernels over CUDA-IPC buffers; NCCL all-to-all
-only as fallback) so that rank r ends up owning the final masks of its 1/N of the prefixes.
+One STEP = one batch of 4,096 ragged prefixes (length 1..32, substrings of corpus documents) pushed through the hot
+path on a device-resident index: K1 batched backward search -> [sp,ep), then K2 distinct-next-token enumeration -> one
+128,256-bit vocab mask per prefix.  The K-step block the driver asks for is REPEATED until >= 250 ms of steps have
+been timed; the reported time is the median block (CUDA events, max over ranks).
 
---impl reference times the CPU oracle (oracle/fm_oracle.c: sdsl-semantics restatement; the real
-reference needs sdsl-lite and cannot be built here) on all host threads on the same workload.
+N = 1 (configs[1], 100M-token corpus): `value` = prefixes/s with inputs resident in HBM, four independent batches in
+flight on four streams through fmidx_query_batch; `e2e` = the same through fmidx_query_submit / fmidx_query_wait with
+pinned HOST buffers (H2D of the prefixes and D2H of the ranges + distinct-token counts inside the timed region).  The
+same line carries `other_configs`: configs[0] batch-1 latency, the 1B-token single-GPU figure (north star), the fused
+decode step (configs[3]), locate + extract (configs[4]), each with a parity flag.
+
+N > 1, three modes measured in the same run (`modes`):
+  replicas     index replicated (100M tokens each), prefixes split N ways, zero collectives  -> `value` (weak scaling)
+  doc_sharded  configs[2]: a fixed 1B-token corpus split N ways by document, prefixes replicated, per-shard masks
+               OR-reduced and counts summed over NVLink peer memory (fmidx_shard_step: five launches, no NCCL)
+  hybrid       2 document shards x N/2 replica groups of the same 1B-token corpus (N >= 4)
+
+--impl reference: the CPU implementation of the path (oracle/fm_oracle.c, a restatement of fm_index.cpp + sdsl-lite's
+algorithms: the real reference needs sdsl-lite, which is neither in /root/reference nor in this image) on all host
+threads, over a corpus generated and suffix-sorted on the CPU: that arm never loads libfmidx.so.
 """
 import argparse
 import ctypes as C
 import json
+import math
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -34,17 +39,16 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# The step keeps up to 8 independent batches in flight on 8 streams.  With the default 8 hardware work queues streams alias
+# and falsely serialise (round 1: "eight streams collapse to 36 M q/s"); 32 queues remove that.  Must be set before CUDA starts.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 VOCAB, EOS, SHIFT = 128256, 128009, 10
-BYTES_PER_SEARCH_STEP = 1088      # 2 boundaries x 17 levels x 32-B rank cell
-MASK_BYTES = 16032                # one 128,256-bit vocab mask
+WORDS = (VOCAB + 31) // 32
+MASK_BYTES = WORDS * 4            # 16,032 B: one 128,256-bit vocab mask
 N_QUERY_SETS = 8                  # distinct prefix batches rotated through the timed steps
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of this very
-# command (profiles/r1_v3_ncu_full_summary.csv; 100M tokens, batch 4096).  k_mask = k_mask_top + k_mask_expand +
-# k_mask_bytes: 2.32 + 7.36 + 27.42 MB read; the 65.7 MB of mask rows are written once (zeroed in k_mask_top, bits
-# ORed in by L2 atomics) -- ncu sees 10.1 MB of them leave L2 inside the kernels' own windows, the rest drains later.
-NCU_TRAFFIC = {"k_mask": 2.32e6 + 7.36e6 + 27.42e6 + 65.7e6, "k_search": 11.44e6}
-
+MIN_TIMED_S = 0.25                # every timed quantity covers at least this much device time
+SCAN_MAX = int(os.environ.get("FMIDX_SCAN_MAX", "16384"))
 
 _JSON_OUT = None
 
@@ -114,48 +118,154 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def build_workload(args, rank, device):
-    """Synthetic corpus shard + query batches for this rank."""
-    from fm_index_constrained_decoding_b200 import synth
-    # every rank owns a different 100M-token shard (seed differs); queries come from shard 0's
-    # generator on every rank (replicated prefixes) so rank 0's positives are real matches there
-    toks, beg = synth.zipf_corpus(args.tokens, seed=1000 * rank, device=device)
-    q_src, q_beg = (toks, beg) if rank == 0 else synth.zipf_corpus(args.tokens, seed=0, device=device)
-    qsets = [synth.sample_queries(q_src, args.batch, seed=100 + i, beginnings=q_beg) for i in range(N_QUERY_SETS)]
-    del q_src
-    return toks, beg, qsets
-
-
+# =====================================================================================================================
+# workload
+# =====================================================================================================================
 def reversed_symbols(toks, beg):
     """The text handed to FMIndex::initialize: per-document reversal + SHIFT (index.py:52,62)."""
     n = toks.numel()
-    pos = torch.arange(n, device=toks.device, dtype=torch.int64)
-    doc = torch.searchsorted(beg, pos, right=True) - 1
-    src = beg[doc] + beg[doc + 1] - 1 - pos
-    return (toks.long()[src] + SHIFT).to(torch.int32)
+    out = torch.empty(n, dtype=torch.int32, device=toks.device)
+    CH = 1 << 27
+    for a in range(0, n, CH):
+        pos = torch.arange(a, min(n, a + CH), device=toks.device, dtype=torch.int64)
+        doc = torch.searchsorted(beg, pos, right=True) - 1
+        out[a:a + pos.numel()] = (toks[beg[doc] + beg[doc + 1] - 1 - pos] + SHIFT).to(torch.int32)
+    return out
 
 
-def oracle_from_gpu_sa(toks, beg, device_index, ix=None):
-    """CPU oracle over the SAME corpus.  Suffix-sorting 100M tokens on one host core would take
-    longer than the whole bench, so the oracle's structures are built from the suffix array the
-    GPU builder produced (the oracle's own SA-IS is cross-checked against it in tests/)."""
-    from fm_index_constrained_decoding_b200 import _native, fm_index
-    from oracle.oracle import NativeOracle
-    sym = reversed_symbols(toks, beg)
-    tmp = ix if (ix is not None and ix.info()["sa_dens"] == 1) else None
-    if tmp is None:
-        tmp = fm_index.FMIndex(device=device_index, sa_dens=1, isa_dens=1 << 20, keep_text=False)
-        _native.check(_native.lib().fmidx_initialize_device(tmp._h, C.c_void_p(sym.data_ptr()), sym.numel(),
-                                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-    sa = np.empty(sym.numel() + 1, dtype=np.uint32)
-    _native.check(_native.lib().fmidx_debug_copy_sa(tmp._h, sa.ctypes.data_as(C.c_void_p), sa.size))
-    del tmp
-    text = np.concatenate([sym.cpu().numpy().astype(np.uint32), np.zeros(1, np.uint32)])
-    o = NativeOracle()
-    o.initialize_from_sa(text, sa)
-    return o
+def workload_config(tokens, batch, mode="single"):
+    return {"workload": "configs[1]: synthetic %dM-token corpus per GPU, vocab 128256, batch %d prefixes of length 1-32: "
+                        "backward search + distinct next-token mask" % (tokens // 1_000_000, batch),
+            "tokens_per_gpu": tokens, "batch": batch, "prefix_len": "U{1..32} clipped at document end",
+            "corpus": "Zipf(1.1) token ids, docs U[64,1024] ending in EOS 128009, 1% planted repeats",
+            "l2": "index (>= 14x L2) larger than L2; %d distinct prefix batches rotated" % N_QUERY_SETS,
+            "mode": mode}
 
 
+def build_index(toks, beg, local, layout="resident"):
+    from fm_index_constrained_decoding_b200 import FMIndex
+    t0 = time.time()
+    ix = FMIndex(device=local, layout=layout)
+    ix.initialize_from_device_tokens(toks, beg)
+    torch.cuda.synchronize()
+    return ix, time.time() - t0
+
+
+# =====================================================================================================================
+# timing helpers: every quantity = median over repeated K-step blocks covering >= MIN_TIMED_S
+# =====================================================================================================================
+class BlockTimer:
+    def __init__(self, device, dist=None):
+        self.device, self.dist = device, dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(self, block, steps, warmup_steps):
+        """block(k0, n): enqueue steps k0..k0+n-1 including fork/join so that the CURRENT torch stream covers them.
+        The K-step block the caller asks for is repeated back to back, WITHOUT draining the pipeline in between, in
+        super-blocks of m x K steps (each >= MIN_TIMED_S / 5 of device time); at least 5 super-blocks are timed (CUDA
+        events on the launching stream, per super-block the slowest rank) and the MEDIAN is reported per K steps.
+        Returns (median ms per `steps` steps, number of K-step blocks timed, super-block times)."""
+        stream = torch.cuda.current_stream()
+        block(0, warmup_steps)
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        block(0, 4 * steps)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        probe_ms = max(e0.elapsed_time(e1) / 4, 1e-3)  # per K steps
+        m = int(min(2000, max(1, math.ceil(MIN_TIMED_S * 1e3 / 5 / probe_ms))))
+        if self.dist is not None:
+            t = torch.tensor([m], device=self.device)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            m = int(t[0])
+        n_super = 7
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_super)]
+        self.barrier()
+        for r, (a, b) in enumerate(evs):
+            a.record(stream)
+            block(r * m * steps, m * steps)
+            b.record(stream)
+        self.barrier()
+        times = torch.tensor([a.elapsed_time(b) for a, b in evs], device=self.device, dtype=torch.float64)
+        if self.dist is not None:  # per super-block: the slowest rank
+            self.dist.all_reduce(times, op=self.dist.ReduceOp.MAX)
+        return float(times.median()) / m, n_super * m, (times / m).tolist()
+
+
+def host_blocks(fn_step, drain, steps, warmup, dist=None, device=None):
+    """Host-timed variant for the e2e loops: wall clock around super-blocks of m x K steps that end with every result on
+    the host (drain); median of 7 super-blocks, per K steps."""
+    for w in range(warmup):
+        fn_step(w)
+    drain()
+    t0 = time.perf_counter()
+    for k in range(4 * steps):
+        fn_step(k)
+    drain()
+    probe = max((time.perf_counter() - t0) / 4, 1e-6)
+    m = int(min(2000, max(1, math.ceil(MIN_TIMED_S / 5 / probe))))
+    if dist is not None:
+        t = torch.tensor([m], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        m = int(t[0])
+        dist.barrier()
+    times = []
+    for r in range(7):
+        t0 = time.perf_counter()
+        for k in range(m * steps):
+            fn_step(r * m * steps + k)
+        drain()
+        times.append((time.perf_counter() - t0) / m)
+    tt = torch.tensor(times, dtype=torch.float64, device=device if dist is not None else "cpu")
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    return float(tt.median()), 7 * m
+
+
+# =====================================================================================================================
+# checkers that live on the bench side
+# =====================================================================================================================
+def bruteforce_sample(sym, queries, vocab=VOCAB):
+    """Independent of the FM-index: occurrence counts and next-token bitmaps of `queries` (token lists) by scanning the
+    text itself with torch.  sym: int32 CUDA tensor, the reversed-document concatenation T WITHOUT its sentinel (T[n] = 0).
+    A prefix q occurs where T[j..j+L) == reversed(q) + SHIFT; its continuations are T[j-1] (row j = 0 contributes the
+    sentinel, which index.py drops).  Returns (counts int64 [Q], masks int32 [Q, words])."""
+    n = sym.numel()
+    dev = sym.device
+    counts = torch.zeros(len(queries), dtype=torch.int64, device=dev)
+    masks = torch.zeros((len(queries), WORDS * 32), dtype=torch.bool, device=dev)
+    for qi, q in enumerate(queries):
+        pat = [t + SHIFT for t in reversed(q)]
+        cand = torch.nonzero(sym == pat[0]).flatten()
+        for k in range(1, len(pat)):
+            if cand.numel() == 0:
+                break
+            nxt = cand + k
+            ok = nxt < n
+            ok &= sym[nxt.clamp(max=n - 1)] == pat[k]
+            cand = cand[ok]
+        counts[qi] = cand.numel()
+        prev = sym[cand[cand > 0] - 1].long() - SHIFT
+        prev = prev[(prev >= 0) & (prev < vocab)]
+        masks[qi, prev] = True
+    sh = torch.arange(32, device=dev, dtype=torch.int64)
+    packed = (masks.view(len(queries), WORDS, 32).long() << sh).sum(-1)
+    return counts, packed.to(torch.int32)  # wraps bit 31 into the sign, like the product's int32 view
+
+
+def queries_as_lists(q, offs, n):
+    qn, on = q[:int(offs[n])].cpu().tolist(), offs[:n + 1].cpu().tolist()
+    return [qn[on[i]:on[i + 1]] for i in range(n)]
+
+
+# =====================================================================================================================
+# --impl reference: CPU only, never touches libfmidx.so
+# =====================================================================================================================
 def cpu_step(o, toks_np, offs_np, nthreads):
     t0 = time.perf_counter()
     o.query_batch(toks_np, offs_np, shift=SHIFT, want_mask=True, vocab=VOCAB, nthreads=nthreads)
@@ -163,39 +273,38 @@ def cpu_step(o, toks_np, offs_np, nthreads):
 
 
 def run_reference(args):
-    """--impl reference: the CPU implementation of the path on all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     nthreads = os.cpu_count() or 1
-    from fm_index_constrained_decoding_b200 import synth
-    note = ""
-    if torch.cuda.is_available():
-        device = torch.device("cuda", 0)
-        torch.cuda.set_device(device)
-        os.environ.setdefault("FMIDX_DEVICE", "0")
-        toks, beg, qsets = build_workload(args, 0, device)
-        t0 = time.time()
-        o = oracle_from_gpu_sa(toks, beg, 0)
-        log("oracle built in %.1fs" % (time.time() - t0))
-    else:
-        # no GPU: the oracle suffix-sorts itself (SA-IS, one core), on a corpus cut to 10M tokens
-        from oracle.oracle import NativeOracle
-        args.tokens = min(args.tokens, 10_000_000)
-        note = " [no GPU: corpus cut to %d tokens, oracle's own SA-IS]" % args.tokens
-        toks, beg = synth.zipf_corpus(args.tokens, seed=0, device="cpu")
-        qsets = [synth.sample_queries(toks, args.batch, seed=100 + i, beginnings=beg) for i in range(N_QUERY_SETS)]
-        o = NativeOracle()
-        o.initialize(reversed_symbols(toks, beg).numpy().astype(np.uint64))
-    # bounded sample: each step = the first `cpu_batch` prefixes of the step's batch, sized from a probe so
-    # that warm-up + steps stay within ~2 minutes of host time
-    qn, on = qsets[0][0].cpu().numpy(), qsets[0][1].cpu().numpy()
+    torch.set_num_threads(nthreads)
+    # synth is pure torch; importing the package itself would load libfmidx.so
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fm_synth", os.path.join(ROOT, "fm_index_constrained_decoding_b200", "synth.py"))
+    synth = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(synth)
+    from oracle.oracle import NativeOracle
+    t0 = time.time()
+    toks, beg = synth.zipf_corpus(args.tokens, seed=0, device="cpu")
+    qsets = [synth.sample_queries(toks, args.batch, seed=100 + i, beginnings=beg) for i in range(N_QUERY_SETS)]
+    sym = reversed_symbols(toks, beg).numpy().astype(np.uint64)
+    del toks
+    log("reference arm: corpus of %d tokens generated on the CPU in %.1fs" % (args.tokens, time.time() - t0))
+    t0 = time.time()
+    o = NativeOracle()
+    o.initialize(sym)  # the oracle's own SA-IS + structures
+    del sym
+    t_build = time.time() - t0
+    log("reference arm: oracle (own SA-IS) built in %.1fs" % t_build)
+    # bounded sample: each step = the first `cpu_batch` prefixes of the step's batch, sized from a probe so that
+    # warm-up + steps stay within ~60 s of host time
+    qn, on = qsets[0][0].numpy(), qsets[0][1].numpy()
     t_probe = cpu_step(o, qn[:on[256]], on[:257], nthreads) / 256
-    budget = 120.0 / max(1, args.steps + args.warmup)
+    budget = 60.0 / max(1, args.steps + args.warmup)
     cpu_batch = int(max(64, min(args.batch, args.cpu_batch, budget / max(t_probe, 1e-9))))
     host = []
     for q, offs in qsets:
-        qn, on = q.cpu().numpy(), offs.cpu().numpy()
+        qn, on = q.numpy(), offs.numpy()
         host.append((qn[:on[cpu_batch]].copy(), on[:cpu_batch + 1].copy()))
     for w in range(args.warmup):
         cpu_step(o, *host[w % len(host)], nthreads)
@@ -207,42 +316,717 @@ def run_reference(args):
         "impl": "reference", "metric": "prefix_queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": workload_config(args, cpu_batch),
+        "config": workload_config(args.tokens, cpu_batch, "cpu"),
         "cpu_baseline": {"value": value, "unit": "queries/s", "cores": nthreads, "kind": "port",
-                         "sample": "%d of the %d prefixes of each step (search + distinct-token mask), oracle/fm_oracle.c "
-                                   "(sdsl-semantics restatement, not sdsl-lite), pthread pool%s" % (cpu_batch, args.batch, note)},
+                         "sample": "%d of the %d prefixes of each step (search + distinct-token mask written to a 16 KB host bitmap per "
+                                   "prefix), oracle/fm_oracle.c (sdsl-semantics restatement, not sdsl-lite) on a pthread pool; corpus "
+                                   "generated and suffix-sorted (SA-IS, %.0f s) on the CPU, libfmidx.so is not loaded" % (cpu_batch, args.batch, t_build)},
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "repo_native_libs_mapped": sorted({l.split()[-1].replace(ROOT + "/", "") for l in open("/proc/self/maps") if ROOT in l and ".so" in l}),
     }
     emit(line)
 
 
-def workload_config(args, batch):
-    return {"workload": "configs[1]: synthetic %dM-token corpus per GPU, vocab 128256, batch %d prefixes of length 1-32: "
-                        "backward search + distinct next-token mask" % (args.tokens // 1_000_000, batch),
-            "tokens_per_gpu": args.tokens, "batch": batch, "prefix_len": "U{1..32} clipped at document end",
-            "corpus": "Zipf(1.1) token ids, docs U[64,1024] ending in EOS 128009, 1% planted repeats",
-            "l2": "index (>=5x L2) larger than L2; %d distinct prefix batches rotated" % N_QUERY_SETS,
-            "sharding": "by document, one shard per GPU, prefixes replicated; per step every rank publishes its occupancy words "
-                        "+ counts into the peers' inboxes and pulls + ORs the occupied 4096-token slices of the rows it owns "
-                        "straight from peer memory over NVLink (own kernels, no NCCL in the loop)"}
+# =====================================================================================================================
+# single-GPU engine of a step (used by N = 1 and by the replicas mode)
+# =====================================================================================================================
+class LocalEngine:
+    """NPIPE (8) independent batches in flight on as many streams through fmidx_query_batch, and the host-buffer pipeline."""
+
+    def __init__(self, ix, qsets, device, B):
+        from fm_index_constrained_decoding_b200 import _native
+        self.N, self.L = _native, _native.lib()
+        self.ix, self.qsets, self.device, self.B = ix, qsets, device, B
+        self.NPIPE = int(os.environ.get("BENCH_NPIPE", "8"))
+        self.pstreams = [torch.cuda.Stream(device=device) for _ in range(self.NPIPE)]
+        self.pbufs = [(torch.empty(B, dtype=torch.int64, device=device), torch.empty(B, dtype=torch.int64, device=device),
+                       torch.empty((B, WORDS), dtype=torch.int32, device=device)) for _ in range(self.NPIPE)]
+        self.pipe_args = {}
+        for qi, (q, offs) in enumerate(qsets):
+            for pi in range(self.NPIPE):
+                psp, pep, pmask = self.pbufs[pi]
+                self.pipe_args[(qi, pi)] = (ix._h, pi, C.c_void_p(q.data_ptr()), C.c_void_p(offs.data_ptr()), B, SHIFT, VOCAB,
+                                            C.c_void_p(psp.data_ptr()), C.c_void_p(pep.data_ptr()), C.c_void_p(pmask.data_ptr()),
+                                            C.c_void_p(self.pstreams[pi].cuda_stream))
+        self._qb = self.L.fmidx_query_batch
+
+    def block(self, k0, n):
+        stream = torch.cuda.current_stream()
+        e = torch.cuda.Event()
+        e.record(stream)
+        for ps in self.pstreams:
+            ps.wait_event(e)
+        nq, npipe, qb, args = len(self.qsets), self.NPIPE, self._qb, self.pipe_args
+        for k in range(k0, k0 + n):
+            if qb(*args[(k % nq, k % npipe)]) != 0:
+                self.N.check(-1)
+        for ps in self.pstreams:
+            e = torch.cuda.Event()
+            e.record(ps)
+            stream.wait_event(e)
+
+    def serial_kernel_times(self, n_steps):
+        """One stream, events around K1 and the K2 group: the per-kernel durations behind the overlapped step."""
+        L, ix, B = self.L, self.ix, self.B
+        sp, ep, mask = self.pbufs[0]
+        stream = torch.cuda.current_stream()
+        sptr = C.c_void_p(stream.cuda_stream)
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_steps)]
+        for k in range(n_steps):
+            q, offs = self.qsets[k % len(self.qsets)]
+            evs[k][0].record(stream)
+            L.fmidx_search_batch(ix._h, C.c_void_p(q.data_ptr()), C.c_void_p(offs.data_ptr()), B, SHIFT,
+                                 C.c_void_p(sp.data_ptr()), C.c_void_p(ep.data_ptr()), sptr)
+            evs[k][1].record(stream)
+            L.fmidx_distinct_mask_batch(ix._h, C.c_void_p(sp.data_ptr()), C.c_void_p(ep.data_ptr()), B, SHIFT, VOCAB,
+                                        C.c_void_p(mask.data_ptr()), None, sptr)
+            evs[k][2].record(stream)
+        torch.cuda.synchronize()
+        t1 = float(np.median([e[0].elapsed_time(e[1]) for e in evs]))
+        t2 = float(np.median([e[1].elapsed_time(e[2]) for e in evs]))
+        return t1, t2
+
+    def setup_e2e(self):
+        B = self.B
+        self.NSLOT = int(os.environ.get("BENCH_NSLOT", "8"))
+        self.hq = [(q.cpu().pin_memory(), offs.cpu().pin_memory()) for q, offs in self.qsets]
+        self.hres = [(torch.empty(B, dtype=torch.int64).pin_memory(), torch.empty(B, dtype=torch.int64).pin_memory(),
+                      torch.empty(B, dtype=torch.int32).pin_memory()) for _ in range(self.NSLOT)]
+        self.submit_args = {}
+        for qi, (q, offs) in enumerate(self.hq):
+            for slot in range(self.NSLOT):
+                rsp, rep, rnd = self.hres[slot]
+                self.submit_args[(qi, slot)] = (self.ix._h, slot, C.c_void_p(q.data_ptr()), C.c_void_p(offs.data_ptr()), B, SHIFT,
+                                                VOCAB, C.c_void_p(rsp.data_ptr()), C.c_void_p(rep.data_ptr()), C.c_void_p(rnd.data_ptr()))
+        self.h2d = int(np.mean([q.numel() * 4 + offs.numel() * 8 for q, offs in self.hq]))
+        self.d2h = B * (8 + 8 + 4)
+
+    def e2e_step(self, k):
+        slot = k % self.NSLOT
+        if self.L.fmidx_query_wait(self.ix._h, slot) != 0 or self.L.fmidx_query_submit(*self.submit_args[(k % len(self.hq), slot)]) != 0:
+            self.N.check(-1)
+
+    def e2e_drain(self):
+        for slot in range(self.NSLOT):
+            self.N.check(self.L.fmidx_query_wait(self.ix._h, slot))
+
+
+# =====================================================================================================================
+# algorithmic bytes of one step (SURVEY 8(d)), counted as the 32-byte SECTORS the algorithm has to touch
+# =====================================================================================================================
+NIB_PROBE_B = 32 + 32 * 1.49     # header sector + E[plane sectors below pos] (two 32-B plane sectors per 128-B cell)
+BYTE_PROBE_B = 32 + 32 * 8.5     # header-word sector + E[payload sectors below pos] (512 payload bytes per cell)
+STEP_B = 2 * (3 * NIB_PROBE_B + BYTE_PROBE_B)  # two boundaries; = 1,086 B (SURVEY 8(d) quotes 1,088 B for the reference layout)
+
+
+def algorithmic_bytes(ix, qsets, device, B, info):
+    """Per step, from the actual results: what K1 and K2 must read and write at the granularity of DRAM sectors.
+    K1  probe steps (range still > 16 rows; resident layout) x STEP_B; the first token costs two C[] sectors; the tail
+        of a prefix costs ceil(4w/32) SA sectors, w x ceil(4 rem/32) text sectors and one ISA sector per survivor; plus
+        the tokens and the result.
+    K2  the mask row once (16,032 B); ranges of <= SCAN_MAX rows: their 4 B/row of the resident BWT; wider ranges (tree
+        walk): 2 x 128 B per visited nibble node, and per visited byte-level node its rows' payload bytes when it is
+        <= 512 rows wide, else two 1,024-B header slices + 512 B of partial cells."""
+    from fm_index_constrained_decoding_b200 import _native
+    L = _native.lib()
+    resident = bool(info["keep_text"]) and info["sa_dens"] == 1
+    sptr = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    tot = {"k1": 0.0, "k2": 0.0, "search_steps": 0.0, "probe_steps": 0.0, "distinct": 0.0, "scan_rows": 0.0, "tree_prefixes": 0.0,
+           "byte_nodes": 0.0}
+    sp = torch.empty(B, dtype=torch.int64, device=device)
+    ep = torch.empty(B, dtype=torch.int64, device=device)
+    for q, offs in qsets:
+        lens = (offs[1:] - offs[:-1])
+        maxlen = int(lens.max())
+        # widths after every token: search the truncated prefixes (the search kernel is cheap)
+        alive = torch.ones(B, dtype=torch.bool, device=device)
+        probe_steps = torch.zeros(B, dtype=torch.int64, device=device)
+        tail_w = torch.zeros(B, dtype=torch.int64, device=device)
+        tail_rem = torch.zeros(B, dtype=torch.int64, device=device)
+        for t in range(1, maxlen + 1):
+            tl = torch.minimum(lens, torch.full_like(lens, t))
+            toffs = torch.zeros(B + 1, dtype=torch.int64, device=device)
+            toffs[1:] = torch.cumsum(tl, 0)
+            idx = torch.arange(int(toffs[-1]), device=device) - torch.repeat_interleave(toffs[:-1], tl) + torch.repeat_interleave(offs[:-1], tl)
+            tq = q[idx].contiguous()
+            L.fmidx_search_batch(ix._h, C.c_void_p(tq.data_ptr()), C.c_void_p(toffs.data_ptr()), B, SHIFT,
+                                 C.c_void_p(sp.data_ptr()), C.c_void_p(ep.data_ptr()), sptr)
+            w = ep - sp
+            act = alive & (lens >= t)
+            if t > 1:
+                probe_steps += act.long()
+            stop = act & (w <= 16) & (lens > t) & resident
+            tail_w = torch.where(stop, w, tail_w)
+            tail_rem = torch.where(stop, lens - t, tail_rem)
+            alive = alive & ~stop & (w > 0)
+        k1 = (probe_steps.sum() * STEP_B + B * 64 + (torch.ceil(tail_w * 4 / 32) * 32).sum()
+              + (tail_w * torch.ceil(tail_rem * 4 / 32) * 32).sum() + (tail_w > 0).sum() * 32 + lens.sum() * 4 + B * 16)
+        tot["k1"] += float(k1)
+        tot["search_steps"] += float(lens.sum())
+        tot["probe_steps"] += float(probe_steps.sum())
+        # K2 from the final ranges
+        L.fmidx_search_batch(ix._h, C.c_void_p(q.data_ptr()), C.c_void_p(offs.data_ptr()), B, SHIFT,
+                             C.c_void_p(sp.data_ptr()), C.c_void_p(ep.data_ptr()), sptr)
+        w = ep - sp
+        scan = (w <= SCAN_MAX) if resident else torch.zeros_like(w, dtype=torch.bool)
+        k2 = B * MASK_BYTES + float((torch.ceil(w[scan] * 4 / 32) * 32).sum())
+        tot["scan_rows"] += float(w[scan].sum())
+        heavy = torch.nonzero(~scan & (w > 0)).flatten()
+        tot["tree_prefixes"] += heavy.numel()
+        for a in range(0, heavy.numel(), 128):
+            hb = heavy[a:a + 128]
+            m, cnt = ix.distinct_mask_batch(sp[hb].contiguous(), ep[hb].contiguous(), VOCAB, want_counts=True)
+            sh = torch.arange(32, device=device, dtype=torch.int32)
+            bits = ((m.unsqueeze(-1) >> sh) & 1).bool().view(hb.numel(), -1)[:, :VOCAB]
+            cnt = torch.where(bits, cnt, torch.zeros_like(cnt)).long()
+            symc = torch.zeros((hb.numel(), 1 << 17), dtype=torch.int64, device=device)
+            symc[:, SHIFT:SHIFT + VOCAB] = cnt
+            bw = symc.view(hb.numel(), -1, 256).sum(-1)                 # rows per byte-level node
+            narrow = (bw > 0) & (bw <= 512)
+            wide = bw > 512
+            nib = (bw.view(hb.numel(), -1, 16).sum(-1) > 0).sum() + (bw.view(hb.numel(), -1, 256).sum(-1) > 0).sum() + hb.numel()
+            k2 += float((torch.ceil(bw[narrow] / 32) * 32 + 32).sum()) + float(wide.sum()) * (2048 + 512) + float(nib) * 256
+            tot["byte_nodes"] += float((bw > 0).sum())
+        tot["k2"] += k2
+    torch.cuda.synchronize()
+    return {k: v / len(qsets) for k, v in tot.items()}
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` summary of THIS command
+    (profiles/r2_ncu_full_summary.csv, written by profiles/summarize.py); None when the file is absent."""
+    p = os.path.join(ROOT, "profiles", "r2_ncu_full_summary.csv")
+    if not os.path.exists(p):
+        return None, None
+    import csv
+    per = {}
+    with open(p) as f:
+        rows = list(csv.reader(f))
+    hdr = rows[0]
+    try:
+        iname = 0
+        ir = next(i for i, h in enumerate(hdr) if h.startswith("dram__bytes_read.sum"))
+        iw = next(i for i, h in enumerate(hdr) if h.startswith("dram__bytes_write.sum"))
+    except StopIteration:
+        return None, None
+    scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+    ur = next((v for k, v in scale.items() if k in hdr[ir]), 1.0)
+    uw = next((v for k, v in scale.items() if k in hdr[iw]), 1.0)
+    for r in rows[1:]:
+        if len(r) <= max(ir, iw):
+            continue
+        name = r[iname]
+        key = next((k for k in ("k_search", "k_mask_top", "k_mask_expand", "k_mask_bytes") if k in name), None)
+        if key:
+            per.setdefault(key, []).append(float(r[ir]) * ur + float(r[iw]) * uw)
+    if not per:
+        return None, None
+    per = {k: float(np.mean(v)) for k, v in per.items()}
+    return sum(per.values()), per
+
+
+# =====================================================================================================================
+# N = 1
+# =====================================================================================================================
+def oracle_verified(toks, beg, ix, nthreads):
+    """CPU oracle over the SAME corpus as the GPU index.  Suffix-sorting 100M tokens on one host core takes ~30 s, so the
+    oracle's structures are built from the suffix array the GPU builder produced -- after oracle-side code has PROVED
+    that array correct (fmo_verify_sa: permutation + adjacent-suffix order via ISA, O(n)), so the parity check below does
+    not rest on the product's builder.  (--impl reference uses the oracle's own SA-IS throughout.)"""
+    from fm_index_constrained_decoding_b200 import _native
+    from oracle.oracle import NativeOracle
+    sym = reversed_symbols(toks, beg)
+    sa = np.empty(sym.numel() + 1, dtype=np.uint32)
+    _native.check(_native.lib().fmidx_debug_copy_sa(ix._h, sa.ctypes.data_as(C.c_void_p), sa.size))
+    text = np.concatenate([sym.cpu().numpy().astype(np.uint32), np.zeros(1, np.uint32)])
+    o = NativeOracle()
+    o.initialize_from_sa(text, sa, verify=True, nthreads=nthreads)
+    return o
+
+
+def run_single(args, device, local):
+    from fm_index_constrained_decoding_b200 import _native, synth
+    L = _native.lib()
+    B = args.batch
+    t0 = time.time()
+    toks, beg = synth.zipf_corpus(args.tokens, seed=0, device=device)
+    qsets = [synth.sample_queries(toks, B, seed=100 + i, beginnings=beg) for i in range(N_QUERY_SETS)]
+    torch.cuda.synchronize()
+    t_gen = time.time() - t0
+    ix, t_build = build_index(toks, beg, local, args.layout)
+    info = ix.info()
+    log("corpus %.1fs, index build %.1fs, %d levels, %.0f MB on device" % (t_gen, t_build, info["levels"], info["device_bytes"] / 1e6))
+    eng = LocalEngine(ix, qsets, device, B)
+    timer = BlockTimer(device)
+    sampler = ClockSampler(local)
+    launches0 = L.fmidx_launch_count()
+    sampler.start()
+    block_ms, reps, _ = timer.run(eng.block, args.steps, args.warmup)
+    clocks = sampler.stop()
+    launches_per_block = (L.fmidx_launch_count() - launches0) / (reps + 4 + args.warmup / args.steps)
+    ms_per_step = block_ms / args.steps
+    value = B * args.steps / (block_ms * 1e-3)
+    log("value %.1f M q/s (%.4f ms/step, %d blocks of %d steps)" % (value / 1e6, ms_per_step, reps, args.steps))
+    t_search, t_mask = eng.serial_kernel_times(max(args.steps, int(MIN_TIMED_S * 1e3 / max(3 * ms_per_step, 1e-3))))
+    # ablation: the same steps with the unigram continuation table ignored (every wide range is walked)
+    ix.tune(unigram_table=0)
+    abl_ms, _, _ = timer.run(eng.block, args.steps, args.warmup)
+    t_search_off, t_mask_off = eng.serial_kernel_times(200)
+    ix.tune(unigram_table=1)
+    ablation = {"unigram_table_off": {"value": B * args.steps / (abl_ms * 1e-3), "ms_per_step": abl_ms / args.steps,
+                                      "serial_kernel_ms": {"k_search": t_search_off, "k_mask": t_mask_off}},
+                "note": "the table holds, for the <= 1024 most frequent symbols, the distinct symbols of the symbol's BWT block (built by the "
+                        "library's own enumeration at index build; the reference precomputes the same for the empty prefix, index.py:206)"}
+
+    # ---- roofline of the step, live ------------------------------------------------------------------------------------
+    peak, peak_src = measured_peaks()
+    ab = algorithmic_bytes(ix, qsets, device, B, info)
+    step_bytes = ab["k1"] + ab["k2"]
+    traffic, traffic_per = ncu_traffic()
+    roof = {"kernel": "one step = k_search + k_mask_top + k_mask_expand + k_mask_bytes (%d independent batches in flight on as many streams)" % eng.NPIPE + "",
+            "bound": "hbm", "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+            "traffic": traffic, "algorithmic_bytes_per_launch": step_bytes, "avg_launch_ms": ms_per_step,
+            "time_source": "the timed (overlapped) region: median K-step block / K",
+            "per_unit": "K1: %.0f B per probe step (2 boundaries x (3 nibble probes of 32-B header sector + 1.49 plane sectors, 1 byte-level "
+                        "probe of 32-B header sector + 8.5 payload sectors)); tail of a prefix: SA/text/ISA sectors; K2: 16,032 B mask row + "
+                        "4 B per row of ranges <= %d rows (resident BWT) + tree walk of wider ranges (2 x 128 B per nibble node, payload bytes "
+                        "or 2,560 B per byte-level node)" % (STEP_B, SCAN_MAX),
+            "per_kernel": {"k_search": {"algorithmic_bytes": ab["k1"], "serial_ms": t_search, "GBps_serial": ab["k1"] / (t_search * 1e-3) / 1e9,
+                                        "traffic": traffic_per.get("k_search") if traffic_per else None},
+                           "k_mask": {"algorithmic_bytes": ab["k2"], "serial_ms": t_mask, "GBps_serial": ab["k2"] / (t_mask * 1e-3) / 1e9,
+                                      "traffic": sum(v for k, v in traffic_per.items() if k != "k_search") if traffic_per else None}},
+            "other_kernel_ms": {"k_search": t_search, "k_mask": t_mask},
+            "counts_per_step": {k: ab[k] for k in ("search_steps", "probe_steps", "scan_rows", "tree_prefixes", "byte_nodes")},
+            "reference_layout_bytes_per_step": 1088 * ab["search_steps"] + B * MASK_BYTES,
+            "note": "mask rows (65.7 MB per step, written once) dominate the bytes; the enumeration of the ~2% widest ranges dominates "
+                    "the time (issue-bound tree walk), which is why the fraction of the HBM roofline is what it is"}
+    roof["frac"] = roof["achieved"] / peak
+    roof["frac_of_traffic"] = (traffic / (ms_per_step * 1e-3) / 1e9 / peak) if traffic else None
+    try:
+        gp = {}
+        for unit in (32, 128):
+            v = C.c_double()
+            _native.check(L.fmidx_gather_peak(ix._h, unit, 1 << 25, C.byref(v)))
+            gp["%dB_GBps" % unit] = v.value
+        roof["random_gather_peak"] = gp
+    except Exception as e:  # noqa: BLE001
+        roof["random_gather_peak"] = {"error": repr(e)}
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region ------------------------------------------------
+    eng.setup_e2e()
+    e2e_s, e2e_reps = host_blocks(eng.e2e_step, eng.e2e_drain, args.steps, args.warmup)
+    e2e = {"value": B * args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": eng.h2d, "d2h_bytes_per_step": eng.d2h,
+           "ms_per_step": 1e3 * e2e_s / args.steps, "blocks": e2e_reps,
+           "api": "fmidx_query_submit/fmidx_query_wait, %d batches in flight (pinned host prefixes in; ranges + distinct-token counts "
+                  "out, every step; the 16 KB masks stay in HBM where the logits kernel consumes them -- the CPU arm writes them to host "
+                  "memory)" % eng.NSLOT}
+
+    # ---- CPU baseline + parity on the same corpus (the only place the oracle is used) ---------------------------------------
+    cpu, o = None, None
+    nthreads = os.cpu_count() or 1
+    if not args.no_cpu_baseline:
+        try:
+            t0 = time.time()
+            o = oracle_verified(toks, beg, ix, nthreads)
+            log("oracle: GPU suffix array verified by fmo_verify_sa, structures built in %.1fs" % (time.time() - t0))
+            q, offs = qsets[0]
+            qn, on = q.cpu().numpy(), offs.cpu().numpy()
+            cb = min(B, args.cpu_batch)
+            qn, on = qn[:on[cb]], on[:cb + 1]
+            osp, oep, omask, _ = o.query_batch(qn, on, shift=SHIFT, want_mask=True, vocab=VOCAB, nthreads=nthreads)
+            sp, ep, mask = ix.query_batch(q, offs, VOCAB)
+            torch.cuda.synchronize()
+            ok = bool((sp[:cb].cpu().numpy().astype(np.uint64) == osp).all() and (ep[:cb].cpu().numpy().astype(np.uint64) == oep).all()
+                      and (mask[:cb].cpu().numpy().view(np.uint32) == omask).all())
+            tt = min(cpu_step(o, qn, on, nthreads) for _ in range(2))
+            t1 = cpu_step(o, qn[:on[256]], on[:257], 1)
+            cpu = {"value": cb / tt, "unit": "queries/s", "cores": nthreads, "kind": "port",
+                   "sample": "one batch of %d prefixes (search + distinct-token mask), best of 2, oracle/fm_oracle.c (sdsl-semantics "
+                             "restatement, not sdsl-lite) on a pthread pool" % cb,
+                   "single_thread_queries_per_sec": 256 / t1, "parity_vs_gpu_on_sample": ok,
+                   "oracle_suffix_array": "GPU builder's array, proved correct by oracle-side fmo_verify_sa before use"}
+        except Exception as e:  # the baseline must never take the bench line down
+            cpu = {"value": None, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
+
+    other = {}
+    if not args.no_other_configs:
+        for name, fn in (("configs0_sample_corpus_batch1", lambda: other_config0(local)),
+                         ("configs3_fused_decode_step", lambda: other_decode(ix, toks, beg, device, o)),
+                         ("configs4_locate_extract", lambda: other_locate(ix, toks, beg, device, o))):
+            try:
+                other[name] = fn()
+            except Exception as e:  # noqa: BLE001
+                other[name] = {"error": repr(e)}
+            log(name, json.dumps(other[name])[:400])
+    del o, eng
+    del ix, toks, beg, qsets
+    torch.cuda.empty_cache()
+    if not args.no_other_configs:
+        try:
+            other["configs2_1B_tokens_one_gpu"] = other_one_billion(args, device, local)
+        except Exception as e:  # noqa: BLE001
+            other["configs2_1B_tokens_one_gpu"] = {"error": repr(e)}
+        log("configs2_1B_tokens_one_gpu", json.dumps(other["configs2_1B_tokens_one_gpu"])[:400])
+
+    emit({
+        "metric": "prefix_queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": workload_config(args.tokens, B),
+        "masks_per_sec": value, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(round(launches_per_block)),
+        "timing": {"blocks": reps, "block_steps": args.steps, "min_timed_s": MIN_TIMED_S, "streams": eng_streams(),
+                   "statistic": "the K-step block repeated back to back (no pipeline drain in between) in 7 super-blocks; median "
+                                "super-block, reported per K steps"},
+        "clocks": clocks, "ablation": ablation, "other_configs": other,
+        "index": {"build_s": t_build, "device_mb": info["device_bytes"] / 1e6, "levels": info["levels"],
+                  "layout": "wavelet matrix: 3 nibble levels (128-B cells) + byte level (1,536-B cells); %s (sa_dens %d, isa_dens %d, text+BWT %s)"
+                            % (args.layout, info["sa_dens"], info["isa_dens"], bool(info["keep_text"]))},
+    })
+
+
+def eng_streams():
+    return int(os.environ.get("BENCH_NPIPE", "8"))
+
+
+# ---- other configs (N = 1) -----------------------------------------------------------------------------------------------
+def other_config0(local):
+    """configs[0]: test_data/sample_corpus.tsv (token ids of the documented stand-in tokenizer, tests/golden/sample_corpus.json),
+    batch 1 through the reference-shaped scalar API: get_range + get_distinct_count per prefix."""
+    from fm_index_constrained_decoding_b200 import FMIndex
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "sample_corpus.json")))
+    ix = FMIndex(device=local)
+    ix.initialize(g["docs"], in_memory=True)
+    qs = [q for q in g["queries"]]
+    ok = True
+    for q in qs[:20]:
+        lo, hi = ix.get_range(q["q"])
+        d, c = ix.get_distinct_count(lo, hi)
+        ok = ok and [lo, hi] == q["range"] and d == q["distinct"] and c == q["counts"]
+    for q in qs[:10]:
+        ix.get_distinct_count(*ix.get_range(q["q"]))
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(5):
+        for q in qs:
+            ix.get_distinct_count(*ix.get_range(q["q"]))
+            n += 1
+    us = (time.perf_counter() - t0) / n * 1e6
+    return {"us_per_query_pair": us, "queries": len(qs), "parity_vs_golden": ok,
+            "note": "latency of get_range + get_distinct_count through the SWIG-shaped scalar API (one prefix at a time); stand-in "
+                    "tokenizer (FNV-1a word hash), expectations from tests/golden/sample_corpus.json"}
+
+
+def other_decode(ix, toks, beg, device, o):
+    """configs[3]: 256 beams x 128,256 logits, search + fused enumerate/-inf mask; fp32 and bf16."""
+    from fm_index_constrained_decoding_b200 import synth
+    peak, _ = measured_peaks()
+    R = 256
+    out = {}
+    q, offs = synth.sample_queries(toks, R, seed=7, beginnings=beg)
+    g = torch.Generator(device=device).manual_seed(3)
+    for name, dt, esz in (("fp32", torch.float32, 4), ("bf16", torch.bfloat16, 2)):
+        # 8 logits buffers rotated: 8 x 131 MB (fp32) > L2
+        bufs = [torch.randn(R, VOCAB, device=device, generator=g, dtype=torch.float32).to(dt) for _ in range(8)]
+        outb = torch.empty_like(bufs[0])
+        st = torch.cuda.current_stream()
+
+        def step(k):
+            sp, ep = ix.get_range_batch(q, offs)
+            ix.mask_logits(sp, ep, bufs[k % 8], out=outb, always_allow=EOS)
+            return sp, ep
+        for k in range(5):
+            sp, ep = step(k)
+        torch.cuda.synchronize()
+        n = 200
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for k in range(n):
+            step(k)
+        e1.record(st)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        # the fused kernel alone
+        e0.record(st)
+        for k in range(n):
+            ix.mask_logits(sp, ep, bufs[k % 8], out=outb, always_allow=EOS)
+        e1.record(st)
+        torch.cuda.synchronize()
+        ms_k = e0.elapsed_time(e1) / n
+        bytes_ = R * VOCAB * esz * 2
+        res = {"ms_per_step": ms, "steps_per_s": 1e3 / ms, "fused_kernel_ms": ms_k, "fused_kernel_GBps": bytes_ / (ms_k * 1e-3) / 1e9,
+               "fused_kernel_frac_of_hbm": bytes_ / (ms_k * 1e-3) / 1e9 / peak, "algorithmic_bytes": bytes_}
+        if o is not None:
+            from oracle.oracle import SHIFT as _S  # noqa: F401
+            qn, on = q.cpu().numpy(), offs.cpu().numpy()
+            osp, oep, om, _ = o.query_batch(qn, on, shift=SHIFT, want_mask=True, vocab=VOCAB, nthreads=os.cpu_count() or 1)
+            ix.mask_logits(sp, ep, bufs[0], out=outb, always_allow=EOS)
+            bits = np.unpackbits(om.view(np.uint8), axis=1, bitorder="little")[:, :VOCAB].astype(bool)
+            bits[:, EOS] = True
+            want = torch.where(torch.from_numpy(bits).to(device), bufs[0] + 0.0, torch.full_like(bufs[0], float("-inf")))
+            res["parity_vs_oracle"] = bool(torch.equal(outb, want) and (sp.cpu().numpy().astype(np.uint64) == osp).all())
+        out[name] = res
+        del bufs, outb
+    out["workload"] = "256 beam histories of length 1-32 (corpus substrings), always_allow_eos, logits randn(seed 3), 8 logits buffers rotated"
+    return out
+
+
+def other_locate(ix, toks, beg, device, o):
+    """configs[4] on one shard: 65,536 prefixes, locate the first K = 8 rows of every range + extract 32 tokens per hit."""
+    from fm_index_constrained_decoding_b200 import synth
+    Q, K, M = 65536, 8, 32
+    q, offs = synth.sample_queries(toks, Q, seed=11, beginnings=beg)
+    st = torch.cuda.current_stream()
+    ar = torch.arange(K, device=device, dtype=torch.int64).unsqueeze(0)
+
+    def step():
+        sp, ep = ix.get_range_batch(q, offs)
+        rows = sp.unsqueeze(1) + ar
+        valid = rows < ep.unsqueeze(1)
+        pos = ix.locate_batch(torch.where(valid, rows, torch.zeros_like(rows)).contiguous().view(-1))
+        begins = torch.where(valid.view(-1), pos, torch.zeros_like(pos))
+        ext, lens = ix.extract_batch(begins, begins + M, M)
+        return sp, ep, valid, pos, ext
+    for _ in range(3):
+        sp, ep, valid, pos, ext = step()
+    torch.cuda.synchronize()
+    n = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(n):
+        step()
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    hits = int(valid.sum())
+    res = {"ms_per_step": ms, "prefixes_per_s": Q / (ms * 1e-3), "locates_per_s": hits / (ms * 1e-3),
+           "tokens_extracted_per_s": Q * K * M / (ms * 1e-3), "hits_per_step": hits,
+           "workload": "65,536 prefixes: search + locate of the first 8 rows of every range + extract_text of 32 symbols per hit slot"}
+    if o is not None:
+        rows = (sp[:64].unsqueeze(1) + ar)[valid[:64]].cpu().numpy().astype(np.uint64)
+        want = o.locate_batch(rows, nthreads=4)
+        got = pos.view(Q, K)[:64][valid[:64]].cpu().numpy().astype(np.uint64)
+        ok = bool((want == got).all())
+        for r in range(8):  # extract parity on a few hit slots
+            b = int(got[r])
+            ok = ok and list(o.extract_text(b, b + M)) == ext.view(Q, K, M)[:64][valid[:64]][r].tolist()[:len(o.extract_text(b, b + M))]
+        res["parity_vs_oracle_on_sample"] = ok
+    return res
+
+
+def other_one_billion(args, device, local):
+    """The north-star sentence: one B200, 1B-token corpus, the same step."""
+    from fm_index_constrained_decoding_b200 import synth
+    n_tok = args.big_tokens
+    B = args.batch
+    t0 = time.time()
+    toks, beg = synth.zipf_corpus(n_tok, seed=2, device=device)
+    qsets = [synth.sample_queries(toks, B, seed=200 + i, beginnings=beg) for i in range(N_QUERY_SETS)]
+    torch.cuda.synchronize()
+    t_gen = time.time() - t0
+    ix, t_build = build_index(toks, beg, local)
+    info = ix.info()
+    eng = LocalEngine(ix, qsets, device, B)
+    timer = BlockTimer(device)
+    block_ms, reps, _ = timer.run(eng.block, args.steps, args.warmup)
+    eng.setup_e2e()
+    e2e_s, _ = host_blocks(eng.e2e_step, eng.e2e_drain, args.steps, args.warmup)
+    # parity: brute force over the text itself on a sample
+    nq = 24
+    sp, ep, mask = ix.query_batch(qsets[0][0], qsets[0][1], VOCAB)
+    sym = reversed_symbols(toks, beg)
+    cnt, bm = bruteforce_sample(sym, queries_as_lists(qsets[0][0], qsets[0][1], nq))
+    ok = bool(((ep - sp)[:nq] == cnt).all() and torch.equal(mask[:nq], bm))
+    return {"tokens": n_tok, "value": B * args.steps / (block_ms * 1e-3), "unit": "queries/s", "ms_per_step": block_ms / args.steps,
+            "blocks": reps, "e2e_value": B * args.steps / e2e_s, "index_device_gb": info["device_bytes"] / 1e9, "build_s": t_build,
+            "corpus_gen_s": t_gen, "parity_vs_bruteforce_on_sample": ok,
+            "parity_note": "%d prefixes: occurrence counts and next-token bitmaps recomputed by scanning the 1B-token text with torch "
+                           "(no FM-index involved)" % nq}
+
+
+# =====================================================================================================================
+# N > 1
+# =====================================================================================================================
+def run_multi(args, device, local, rank, world, dist):
+    from fm_index_constrained_decoding_b200 import _native, sharded, synth
+    L = _native.lib()
+    B = args.batch
+    timer = BlockTimer(device, dist)
+    modes = {}
+    want = args.mode
+
+    # ---- replicas: index replicated, prefixes split N ways, zero collectives ------------------------------------------------
+    toks, beg = synth.zipf_corpus(args.tokens, seed=0, device=device)
+    qsets = [synth.sample_queries(toks, B, seed=100 + 1000 * rank + i, beginnings=beg) for i in range(N_QUERY_SETS)]
+    ix, t_build = build_index(toks, beg, local, args.layout)
+    info = ix.info()
+    eng = LocalEngine(ix, qsets, device, B)
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = L.fmidx_launch_count()
+    if sampler:
+        sampler.start()
+    block_ms, reps, _ = timer.run(eng.block, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    launches_per_block = (L.fmidx_launch_count() - launches0) / (reps + 4 + args.warmup / args.steps)
+    value = world * B * args.steps / (block_ms * 1e-3)
+    eng.setup_e2e()
+    e2e_s, e2e_reps = host_blocks(eng.e2e_step, eng.e2e_drain, args.steps, args.warmup, dist, device)
+    # parity of this rank's replica on a sample: brute force over the text
+    nq = 16
+    sp, ep, mask = ix.query_batch(qsets[0][0], qsets[0][1], VOCAB)
+    cnt, bm = bruteforce_sample(reversed_symbols(toks, beg), queries_as_lists(qsets[0][0], qsets[0][1], nq))
+    okt = torch.tensor([int(bool(((ep - sp)[:nq] == cnt).all() and torch.equal(mask[:nq], bm)))], device=device)
+    dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    modes["replicas"] = {"value": value, "unit": "queries/s", "ms_per_step": block_ms / args.steps, "blocks": reps,
+                         "e2e_value": world * B * args.steps / e2e_s, "tokens_per_gpu": args.tokens, "prefixes_per_step": world * B,
+                         "collectives_per_step": 0, "parity_vs_bruteforce_on_sample": bool(int(okt[0])),
+                         "what": "every GPU holds the whole index (a 1B-token index is 22 GB of 180 GB) and serves its own 1/N of the prefixes"}
+    e2e = {"value": world * B * args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": eng.h2d * world, "d2h_bytes_per_step": eng.d2h * world,
+           "ms_per_step": 1e3 * e2e_s / args.steps, "blocks": e2e_reps,
+           "api": "per GPU: fmidx_query_submit/fmidx_query_wait, %d batches in flight (pinned host prefixes in; ranges + distinct-token counts out)" % eng.NSLOT}
+    log("rank %d replicas: %.1f M q/s total" % (rank, value / 1e6))
+    del eng, ix, toks, beg, qsets
+    torch.cuda.empty_cache()
+
+    # ---- document-sharded modes over the fixed big corpus -------------------------------------------------------------------
+    def sharded_mode(g_size, tag):
+        """g_size shards per group, world / g_size replica groups; every group sees its own prefix batches."""
+        n_groups = world // g_size
+        grp_id, grank = rank // g_size, rank % g_size
+        groups = [dist.new_group(list(range(a * g_size, (a + 1) * g_size))) for a in range(n_groups)]
+        group = groups[grp_id] if n_groups > 1 else None
+        toks, beg = synth.zipf_corpus(args.big_tokens, seed=2, device=device)
+        parts = sharded.shard_documents(beg.tolist(), g_size)
+        lo, hi = parts[grank]
+        qs = [synth.sample_queries(toks, B, seed=300 + 50 * grp_id + i, beginnings=beg) for i in range(N_QUERY_SETS)]
+        a, b = int(beg[lo]), int(beg[hi])
+        stoks, sbeg = toks[a:b].clone(), (beg[lo:hi + 1] - beg[lo]).clone()
+        del toks
+        torch.cuda.empty_cache()
+        six, tb = build_index(stoks, sbeg, local, args.layout)
+        NSET = int(os.environ.get("BENCH_NBUF", "8"))
+        st = sharded.ShardStep(six, B, VOCAB, n_sets=NSET, group=group)
+        rb = [(torch.empty(B, dtype=torch.int64, device=device), torch.empty(B, dtype=torch.int64, device=device)) for _ in range(NSET)]
+        step_args = {}
+        for qi, (q, offs) in enumerate(qs):
+            for i in range(NSET):
+                step_args[(qi, i)] = (st._x, i, C.c_void_p(q.data_ptr()), C.c_void_p(offs.data_ptr()), SHIFT,
+                                      C.c_void_p(rb[i][0].data_ptr()), C.c_void_p(rb[i][1].data_ptr()), None)
+        shard_step = L.fmidx_shard_step
+
+        def block(k0, n):
+            stream = torch.cuda.current_stream()
+            e = torch.cuda.Event()
+            e.record(stream)
+            for s in st.streams:
+                s.wait_event(e)
+            for k in range(k0, k0 + n):
+                if shard_step(*step_args[(k % N_QUERY_SETS, k % NSET)]) != 0:
+                    _native.check(-1)
+            for s in st.streams:
+                e = torch.cuda.Event()
+                e.record(s)
+                stream.wait_event(e)
+        l0 = L.fmidx_launch_count()
+        bms, rps, _ = timer.run(block, args.steps, args.warmup)
+        lpb = (L.fmidx_launch_count() - l0) / (rps + 4 + args.warmup / args.steps)
+        # e2e: host-buffer form
+        hq = [(q.cpu().pin_memory(), offs.cpu().pin_memory()) for q, offs in qs]
+        own = B // g_size
+        hout = [(torch.empty(B, dtype=torch.int64).pin_memory(), torch.empty(B, dtype=torch.int64).pin_memory(),
+                 torch.empty(B, dtype=torch.int64).pin_memory(), torch.empty(own, dtype=torch.int32).pin_memory()) for _ in range(NSET)]
+        sub_args = {}
+        for qi, (q, offs) in enumerate(hq):
+            for i in range(NSET):
+                sub_args[(qi, i)] = (st._x, i, C.c_void_p(q.data_ptr()), C.c_void_p(offs.data_ptr()), SHIFT) + tuple(C.c_void_p(t.data_ptr()) for t in hout[i])
+
+        def e2e_step(k):
+            i = k % NSET
+            if L.fmidx_shard_wait(st._x, i) != 0 or L.fmidx_shard_submit(*sub_args[(k % N_QUERY_SETS, i)]) != 0:
+                _native.check(-1)
+
+        def e2e_drain():
+            for i in range(NSET):
+                _native.check(L.fmidx_shard_wait(st._x, i))
+        es, erps = host_blocks(e2e_step, e2e_drain, args.steps, args.warmup, dist, device)
+        # parity on a sample: per-shard brute force over the text, OR / sum reduced over the group on the host side
+        nq = 16 * g_size
+        q0, o0 = qs[0]
+        masks, counts = st.step(0, q0, o0, rb[0][0], rb[0][1])
+        torch.cuda.synchronize()
+        ssym = reversed_symbols(stoks, sbeg)
+        cnt, bm = bruteforce_sample(ssym, queries_as_lists(q0, o0, nq))
+        local_ok = bool(((rb[0][1] - rb[0][0])[:nq] == cnt).all())  # shard-local ranges
+        allc = [torch.empty_like(cnt) for _ in range(g_size)]
+        allm = [torch.empty_like(bm) for _ in range(g_size)]
+        dist.all_gather(allc, cnt, group=group)
+        dist.all_gather(allm, bm, group=group)
+        tot_c = torch.stack(allc).sum(0)
+        tot_m = allm[0].clone()
+        for m in allm[1:]:
+            tot_m |= m
+        ok = local_ok and bool((counts[:nq] == tot_c).all())
+        lo_r, hi_r = grank * own, min((grank + 1) * own, nq)
+        if hi_r > lo_r:  # the rows of the sample this rank owns
+            ok = ok and bool(torch.equal(masks[:hi_r - lo_r], tot_m[lo_r:hi_r]))
+        okt = torch.tensor([int(ok)], device=device)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        res = {"value": n_groups * B * args.steps / (bms * 1e-3), "unit": "queries/s", "ms_per_step": bms / args.steps, "blocks": rps,
+               "e2e_value": n_groups * B * args.steps / es, "shards": g_size, "replica_groups": n_groups, "corpus_tokens": args.big_tokens,
+               "tokens_per_gpu": int(b - a), "prefixes_per_step": n_groups * B, "buffer_sets": NSET, "launches_per_step": lpb / args.steps,
+               "shard_index_device_gb": six.info()["device_bytes"] / 1e9, "build_s": tb,
+               "parity_vs_bruteforce_on_sample": bool(int(okt[0])),
+               "parity_note": "%d prefixes: per-shard counts / next-token bitmaps recomputed by scanning each shard's text with torch, "
+                              "OR / sum reduced over the shards, against the exchanged results" % nq,
+               "exchange": "fmidx_shard_step: publish at the tail of the last enumeration kernel + fused wait/pull/OR/counts/ack kernel over "
+                           "CUDA-IPC peer memory (5 launches per step, no NCCL)"}
+        st.close()
+        del six, stoks, sbeg, qs
+        torch.cuda.empty_cache()
+        return res
+
+    if want in ("all", "sharded"):
+        modes["doc_sharded"] = sharded_mode(world, "doc_sharded")
+        log("rank %d doc_sharded: %.1f M q/s" % (rank, modes["doc_sharded"]["value"] / 1e6))
+    if want in ("all", "hybrid") and world >= 4 and world % 2 == 0:
+        modes["hybrid"] = sharded_mode(2, "hybrid")
+        log("rank %d hybrid: %.1f M q/s" % (rank, modes["hybrid"]["value"] / 1e6))
+
+    if rank == 0:
+        cfg = workload_config(args.tokens, B, "replicas")
+        cfg["sharding"] = ("value = replicas mode (index replicated on every GPU, each GPU serves its own batch of %d prefixes per step, no "
+                           "collective on the data path); modes.doc_sharded = BASELINE configs[2] (a fixed %dM-token corpus split N ways by "
+                           "document, prefixes replicated, masks OR-reduced + counts summed over NVLink peer memory); modes.hybrid = 2 shards x "
+                           "N/2 replica groups" % (B, args.big_tokens // 1_000_000))
+        emit({
+            "metric": "prefix_queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": block_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": cfg, "masks_per_sec": value,
+            "modes": modes, "e2e": e2e, "gpu_launches": int(round(launches_per_block)), "cpu_baseline": None,
+            "roofline": None, "timing": {"blocks": reps, "block_steps": args.steps, "min_timed_s": MIN_TIMED_S,
+                                         "statistic": "the K-step block repeated back to back in 7 super-blocks; per super-block the "
+                                                      "slowest rank; median super-block, reported per K steps"},
+            "clocks": clocks,
+            "index": {"build_s": t_build, "device_mb": info["device_bytes"] / 1e6, "levels": info["levels"]},
+        })
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5000)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--tokens", type=int, default=100_000_000)
+    ap.add_argument("--big-tokens", type=int, default=1_000_000_000)
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--cpu-batch", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--mode", default="all", choices=["all", "replicas", "sharded", "hybrid"])
     ap.add_argument("--layout", default="resident", choices=["resident", "sampled"])
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    # the one JSON line must be the only thing on stdout: NCCL / library banners that print to fd 1
-    # are sent to stderr, the line itself goes to the saved descriptor
+    # the one JSON line must be the only thing on stdout: NCCL / library banners that print to fd 1 are sent to stderr
     global _JSON_OUT
     sys.stdout.flush()
     _JSON_OUT = os.fdopen(os.dup(1), "w")
@@ -258,453 +1042,16 @@ def main():
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
     os.environ["FMIDX_DEVICE"] = str(local)
-    dist = None
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
-
-    from fm_index_constrained_decoding_b200 import FMIndex, _native
-    L = _native.lib()
-    t0 = time.time()
-    toks, beg, qsets = build_workload(args, rank, device)
-    torch.cuda.synchronize()
-    t_gen = time.time() - t0
-    t0 = time.time()
-    ix = FMIndex(device=local, layout=args.layout)
-    ix.initialize_from_device_tokens(toks, beg)
-    torch.cuda.synchronize()
-    t_build = time.time() - t0
-    info = ix.info()
-    log("rank %d: corpus %.1fs, index build %.1fs, %d levels, %.0f MB on device" %
-        (rank, t_gen, t_build, info["levels"], info["device_bytes"] / 1e6))
-
-    B = args.batch
-    words = (VOCAB + 31) // 32
-    stream = torch.cuda.current_stream()
-    sptr = C.c_void_p(stream.cuda_stream)
-    # N > 1: NBUF (4) buffer sets.  The cross-shard exchange of step k runs on its own stream while the kernels of
-    # step k+1 fill the next set; the bitmaps live in peer-visible memory and the exchange PULLS only the occupied
-    # 4096-token slices of the rows this rank owns (sharded.PeerMaskExchange), instead of an all-to-all of 16 KB rows.
-    NBUF = int(os.environ.get("BENCH_NBUF", "4")) if world > 1 else 1
-    bufs = [(torch.empty(B, dtype=torch.int64, device=device), torch.empty(B, dtype=torch.int64, device=device),
-             torch.empty((B, words), dtype=torch.int32, device=device) if world == 1 else None) for _ in range(NBUF)]
-    sp, ep, mask = bufs[0]
-    own = B // world  # prefixes whose final mask this rank owns
-    from fm_index_constrained_decoding_b200 import sharded
-    result = {}
-    comm_stream = torch.cuda.Stream(device=device) if world > 1 else None
-    ev_kernels = [torch.cuda.Event() for _ in bufs]
-    ev_comm = [torch.cuda.Event() for _ in bufs]
-    px = None
-    if world > 1:
-        # peer-memory exchange (CUDA IPC); if any rank cannot set it up, every rank falls back to the NCCL
-        # all-to-all + fmidx_mask_or path
         try:
-            px = sharded.PeerMaskExchange(ix, B, VOCAB, n_buffers=NBUF)
-            ok = torch.ones(1, device=device)
-        except Exception as e:  # noqa: BLE001
-            log("rank %d: peer-memory exchange unavailable (%r), using the NCCL all-to-all path" % (rank, e))
-            ok = torch.zeros(1, device=device)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if float(ok[0]) == 0.0:
-            px = None
-            bufs = [(b0, b1, torch.empty((B, words), dtype=torch.int32, device=device)) for b0, b1, _ in bufs]
-        mask = px.local_views[0] if px is not None else bufs[0][2]
-    cnt_bufs = [torch.empty(B, dtype=torch.int64, device=device) for _ in bufs]
-
-    # N > 1: every buffer set has its own kernel stream and scratch slot, so the kernels of up to NBUF consecutive steps
-    # overlap each other as well as the exchanges (which stay ordered on the exchange stream)
-    kstreams = [torch.cuda.Stream(device=device) for _ in bufs] if world > 1 else [stream]
-
-    def step_full(k, ev=None, q_off=None, serial=False):
-        q, offs = q_off if q_off is not None else qsets[k % N_QUERY_SETS]
-        bi = k % NBUF
-        bsp, bep, bmask = bufs[bi]
-        ks = stream if serial or world == 1 else kstreams[bi]
-        kptr = C.c_void_p(ks.cuda_stream)
-        if world > 1:
-            # set bi was last used by step k-NBUF: this rank's exchange of that step has to be complete (the peers'
-            # pulls of it are awaited on the GPU through the ack flags inside compute_local)
-            ks.wait_event(ev_comm[bi])
-            if q_off is not None and ks is not stream:  # inputs were copied on the caller's stream
-                e_in = torch.cuda.Event()
-                e_in.record(stream)
-                ks.wait_event(e_in)
-        if ev:
-            ev[0].record(ks)
-        _native.check(L.fmidx_search_batch(ix._h, C.c_void_p(q.data_ptr()), C.c_void_p(offs.data_ptr()), B, SHIFT,
-                                           C.c_void_p(bsp.data_ptr()), C.c_void_p(bep.data_ptr()), kptr))
-        if ev:
-            ev[1].record(ks)
-        if px is not None:
-            px.compute_local(bi, bsp, bep, SHIFT, ws_slot=bi, stream=ks)
-        else:
-            _native.check(L.fmidx_distinct_mask_batch(ix._h, C.c_void_p(bsp.data_ptr()), C.c_void_p(bep.data_ptr()), B, SHIFT,
-                                                      VOCAB, C.c_void_p(bmask.data_ptr()), None, kptr))
-        if ev:
-            ev[2].record(ks)
-        if world > 1:
-            # rank r ends up owning the final masks of prefixes [r*B/W, (r+1)*B/W); total occurrence counts are summed
-            if px is not None:
-                # publish / wait / pull+OR / counts / ack: one host call, on the set's own stream right behind its
-                # kernels (every set has its own flags, so the exchanges of the sets in flight overlap each other)
-                result["mask"] = px.exchange(bi, stream=ks)
-                result["count"] = px.total_counts(bi)
-                ev_comm[bi].record(ks)
-            else:
-                ev_kernels[bi].record(ks)
-                comm_stream.wait_event(ev_kernels[bi])
-                with torch.cuda.stream(comm_stream):
-                    result["mask"] = sharded.or_reduce_scatter(bmask, index=ix)[1]
-                    result["count"] = sharded.sum_counts(bsp, bep)
-                ev_comm[bi].record(comm_stream)
-        else:
-            result["mask"] = bmask
-
-    def drain():
-        if world > 1:
-            for e in ev_comm:
-                stream.wait_event(e)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # N = 1: consecutive steps are independent batches, so NPIPE (4) of them are kept in flight on as many streams through
-    # fmidx_query_batch (one call = search + masks of one batch; each stream has its own output buffers and scratch
-    # slot).  The latency-bound search of one batch then overlaps the issue-bound enumeration of the other.  The
-    # per-kernel durations for the roofline come from a SERIAL pass of the same steps below (events on one stream).
-    NPIPE = int(os.environ.get("BENCH_NPIPE", "4"))
-    pstreams = [torch.cuda.Stream(device=device) for _ in range(NPIPE)] if world == 1 else []
-    pbufs = [bufs[0]] + [(torch.empty_like(sp), torch.empty_like(ep), torch.empty_like(mask)) for _ in range(NPIPE - 1)] \
-        if world == 1 else []
-
-    # ctypes argument tuples are built once: the host has ~45 us per step at four batches in flight
-    pipe_args = {}
-    for qi, (q, offs) in enumerate(qsets):
-        for pi in range(len(pstreams)):
-            psp, pep, pmask = pbufs[pi]
-            pipe_args[(qi, pi)] = (ix._h, pi, C.c_void_p(q.data_ptr()), C.c_void_p(offs.data_ptr()), B, SHIFT, VOCAB,
-                                   C.c_void_p(psp.data_ptr()), C.c_void_p(pep.data_ptr()), C.c_void_p(pmask.data_ptr()),
-                                   C.c_void_p(pstreams[pi].cuda_stream))
-    query_batch = L.fmidx_query_batch
-
-    def step_pipe(k):
-        if query_batch(*pipe_args[(k % N_QUERY_SETS, k % NPIPE)]) != 0:
-            _native.check(-1)
-
-    def fork():
-        e = torch.cuda.Event()
-        e.record(stream)
-        for ps in pstreams + (kstreams if world > 1 else []):
-            ps.wait_event(e)
-
-    def join():
-        for ps in pstreams + (kstreams if world > 1 else []):
-            e = torch.cuda.Event()
-            e.record(ps)
-            stream.wait_event(e)
-
-    step = step_pipe if world == 1 else step_full
-    fork()
-    for w in range(args.warmup):
-        step(w)
-    join()
-    barrier()
-    launches0 = L.fmidx_launch_count()
-    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    barrier()
-    e_start.record(stream)
-    fork()
-    for k in range(args.steps):
-        step(k)
-    join()
-    drain()  # the timed region ends when the last exchange has completed
-    e_end.record(stream)
-    barrier()
-    total_ms = e_start.elapsed_time(e_end)
-    launches = L.fmidx_launch_count() - launches0
-    # serial pass with events around each kernel group (N = 1: this is where the roofline's launch durations come
-    # from; N > 1: the timed region itself is serial on the kernel stream, so it is simply repeated)
-    n_ev = min(args.steps, 500)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_ev)]
-    es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    es0.record(stream)
-    for k in range(n_ev):
-        step_full(k, evs[k], serial=True)
-    drain()
-    es1.record(stream)
-    barrier()
-    serial_ms_per_step = es0.elapsed_time(es1) / n_ev
-    if sampler and total_ms < 150:  # region too short for NVML's sampling period: keep the same load running
-        t_end = time.time() + 0.6
-        k = 0
-        scratch_mask = mask if world == 1 else torch.empty((B, words), dtype=torch.int32, device=device)
-        while time.time() < t_end:  # local kernels only: the other ranks are not in this loop
-            q, offs = qsets[k % N_QUERY_SETS]
-            L.fmidx_search_batch(ix._h, C.c_void_p(q.data_ptr()), C.c_void_p(offs.data_ptr()), B, SHIFT,
-                                 C.c_void_p(sp.data_ptr()), C.c_void_p(ep.data_ptr()), sptr)
-            L.fmidx_distinct_mask_batch(ix._h, C.c_void_p(sp.data_ptr()), C.c_void_p(ep.data_ptr()), B, SHIFT, VOCAB,
-                                        C.c_void_p(scratch_mask.data_ptr()), None, sptr)
-            k += 1
-            if k % 50 == 0:
-                torch.cuda.synchronize()
-        torch.cuda.synchronize()
-    clocks = sampler.stop() if sampler else None
-    if clocks is not None and total_ms < 150:
-        clocks["note"] = "timed region %.0f ms is shorter than NVML's sampling period; sampled while the same step kept running" % total_ms
-    t_search = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
-    t_mask = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
-    if world > 1:
-        tt = torch.tensor([total_ms, t_search, t_mask], device=device, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        total_ms, t_search, t_mask = tt.tolist()
-
-    # ---- algorithmic bytes of one step, from the actual results ------------------------
-    # "visited nodes per level, 2 cells each" for the enumeration and "2 boundaries x levels x
-    # 1 rank cell" for a search step, with the cell size of the layout in use ("state which").  Ours
-    # (DESIGN.md section 3): 3 nibble levels of 128-B cells + 1 byte level of 1,536-B cells, so
-    #   K2: 2 x 128 B per visited nibble node + 2 x 1,536 B per visited byte-level node + the 16,032-B mask row,
-    #       visited nodes counted exactly from the result masks (distinct symbol prefixes per level);
-    #   K1: 2 x (3 x 128 + 1,536) = 3,840 B per executed step.
-    # The same sums on the REFERENCE's layout (17 binary levels, 32-B cells: 64 B per visited node, 1,088 B
-    # per search step) are reported beside them as *_reference_layout.
-    search_steps, enum_nodes_bin, nib_nodes, byte_nodes, distinct_total = 0, 0, 0, 0, 0
-    for q, offs in qsets:
-        L.fmidx_search_batch(ix._h, C.c_void_p(q.data_ptr()), C.c_void_p(offs.data_ptr()), B, SHIFT,
-                             C.c_void_p(sp.data_ptr()), C.c_void_p(ep.data_ptr()), sptr)
-        L.fmidx_distinct_mask_batch(ix._h, C.c_void_p(sp.data_ptr()), C.c_void_p(ep.data_ptr()), B, SHIFT, VOCAB,
-                                    C.c_void_p(mask.data_ptr()), None, sptr)
-        torch.cuda.synchronize()
-        search_steps += int((offs[1:] - offs[:-1]).sum())  # positive prefixes: every step executes
-        sh = torch.arange(32, device=device, dtype=torch.int32)
-        for r0 in range(0, B, 256):
-            bits = ((mask[r0:r0 + 256].unsqueeze(-1) >> sh) & 1).bool().view(-1, words * 32)[:, :VOCAB]
-            symb = torch.zeros((bits.shape[0], 1 << 17), dtype=torch.bool, device=device)
-            symb[:, SHIFT:SHIFT + VOCAB] = bits  # symbol axis = token + SHIFT
-            distinct_total += int(bits.sum())
-            lvl = symb
-            for l in range(17, 0, -1):          # nodes at binary depth l-1 = distinct (l-1)-bit prefixes
-                lvl = lvl.view(lvl.shape[0], -1, 2).any(-1)
-                cnt_l = int(lvl.sum())
-                enum_nodes_bin += cnt_l
-                if l - 1 == 9:                  # byte-level nodes: symbol >> 8
-                    byte_nodes += cnt_l
-                elif l - 1 in (5, 1, 0):        # nibble-level nodes: symbol >> 12, >> 16, root
-                    nib_nodes += cnt_l
-    search_steps /= N_QUERY_SETS
-    enum_nodes_bin /= N_QUERY_SETS
-    nib_nodes /= N_QUERY_SETS
-    byte_nodes /= N_QUERY_SETS
-    distinct_total /= N_QUERY_SETS
-    bytes_search = 3840 * search_steps
-    bytes_search_ref = BYTES_PER_SEARCH_STEP * search_steps
-    bytes_mask = 2 * 128 * nib_nodes + 2 * 1536 * byte_nodes + MASK_BYTES * B
-    bytes_mask_ref = 2 * 32 * enum_nodes_bin + MASK_BYTES * B
-    peak, peak_src = measured_peaks()
-    if t_mask >= t_search:
-        dom = {"kernel": "k_mask (k_mask_top + k_mask_expand + k_mask_bytes: distinct-token enumeration -> vocab bitmap)", "bound": "hbm",
-               "achieved": bytes_mask / (t_mask * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-               "traffic": NCU_TRAFFIC["k_mask"] if args.tokens == 100_000_000 and B == 4096 else None,
-               "algorithmic_bytes_per_launch": bytes_mask, "avg_launch_ms": t_mask,
-               "per_unit": "2 x 128 B per visited nibble node + 2 x 1,536 B per visited byte-level node + 16,032 B mask per prefix",
-               "algorithmic_bytes_reference_layout": bytes_mask_ref,
-               "achieved_reference_layout": bytes_mask_ref / (t_mask * 1e-3) / 1e9,
-               "frac_reference_layout": bytes_mask_ref / (t_mask * 1e-3) / 1e9 / peak,
-               "per_unit_reference_layout": "64 B per visited node of the 17-level binary tree + 16,032 B mask per prefix",
-               "distinct_symbols_per_launch": distinct_total,
-               "note": "issue/latency bound (ncu: k_mask_bytes 66% issue-active, 13% DRAM; k_mask_top / k_mask_expand latency-bound): the fraction measures distance from the HBM "
-                       "bound, the reference-layout figure shows how much less this layout has to move"}
+            run_multi(args, device, local, rank, world, dist)
+        finally:
+            dist.destroy_process_group()
     else:
-        dom = {"kernel": "k_search (batched backward search)", "bound": "hbm",
-               "achieved": bytes_search / (t_search * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-               "traffic": NCU_TRAFFIC["k_search"] if args.tokens == 100_000_000 and B == 4096 else None,
-               "algorithmic_bytes_per_launch": bytes_search, "avg_launch_ms": t_search,
-               "per_unit": "3,840 B per backward-search step of the prefix (2 x (3 x 128 + 1,536) B)",
-               "algorithmic_bytes_reference_layout": bytes_search_ref,
-               "achieved_reference_layout": bytes_search_ref / (t_search * 1e-3) / 1e9,
-               "frac_reference_layout": bytes_search_ref / (t_search * 1e-3) / 1e9 / peak}
-    dom["frac"] = dom["achieved"] / peak
-    # the rank probes are random accesses, so also measure what this GPU sustains for INDEPENDENT random
-    # 32-B units / aligned 128-B lines over the index's own arrays (fmidx_gather_peak) and relate both
-    # kernels' algorithmic bytes (own layout) to the 128-B figure
-    try:
-        gp = {}
-        for unit in (32, 128):
-            v = C.c_double()
-            _native.check(L.fmidx_gather_peak(ix._h, unit, 1 << 25, C.byref(v)))
-            gp["%dB_GBps" % unit] = v.value
-        gp["note"] = ("independent random loads over the index's own arrays (18 B/token); fractions above 1 mean the kernel "
-                      "touches less than its full-cell algorithmic figure (<=16-row search shortcut, partially read byte "
-                      "cells, L2 hits on the top levels)")
-        dom["random_gather_peak"] = gp
-        dom["frac_of_random_gather_128B"] = dom["achieved"] / gp["128B_GBps"]
-        dom["k_search_achieved_GBps"] = bytes_search / (t_search * 1e-3) / 1e9
-        dom["k_search_frac_of_random_gather_128B"] = dom["k_search_achieved_GBps"] / gp["128B_GBps"]
-    except Exception as e:  # noqa: BLE001 -- a measurement aid must not take the line down
-        dom["random_gather_peak"] = {"error": repr(e)}
-    dom["peak_source"] = peak_src
-    dom["other_kernel_ms"] = {"k_search": t_search, "k_mask": t_mask}
-
-    # ---- e2e: host buffers through the C ABI, copies inside the timed region -----------------------------
-    e2e = None
-    if rank == 0 or world > 1:
-        hq = [(q.cpu().pin_memory(), offs.cpu().pin_memory()) for q, offs in qsets]
-        hsp = torch.empty(B, dtype=torch.int64).pin_memory()
-        hep = torch.empty(B, dtype=torch.int64).pin_memory()
-        hnd = torch.empty(B, dtype=torch.int32).pin_memory()
-
-        dq = [(torch.empty_like(q, device=device), torch.empty_like(offs, device=device)) for q, offs in hq[:1]]
-        n32 = torch.empty(own, dtype=torch.int32, device=device)
-        hcnt = torch.empty(B, dtype=torch.int64).pin_memory()
-
-        NSLOT = int(os.environ.get("BENCH_NSLOT", "6"))  # batches in flight through the pipelined host API
-        hres = [(torch.empty(B, dtype=torch.int64).pin_memory(), torch.empty(B, dtype=torch.int64).pin_memory(),
-                 torch.empty(B, dtype=torch.int32).pin_memory()) for _ in range(NSLOT)]
-
-        submit_args = {}
-        for qi, (q, offs) in enumerate(hq):
-            for slot in range(NSLOT):
-                rsp, rep, rnd = hres[slot]
-                submit_args[(qi, slot)] = (ix._h, slot, C.c_void_p(q.data_ptr()), C.c_void_p(offs.data_ptr()), B, SHIFT, VOCAB,
-                                           C.c_void_p(rsp.data_ptr()), C.c_void_p(rep.data_ptr()), C.c_void_p(rnd.data_ptr()))
-        query_wait, query_submit = L.fmidx_query_wait, L.fmidx_query_submit
-
-        def e2e_step(k):
-            q, offs = hq[k % N_QUERY_SETS]
-            if world == 1:
-                # fmidx_query_submit/wait: the H2D copy of this step's prefixes, its kernels and the D2H read of its
-                # results are all inside the timed region; the wait for a slot happens when the slot is reused, so
-                # the copies of one step overlap the kernels of the others
-                slot = k % NSLOT
-                if query_wait(ix._h, slot) != 0 or query_submit(*submit_args[(k % N_QUERY_SETS, slot)]) != 0:
-                    _native.check(-1)
-                return
-            # N > 1: pinned host prefixes -> device, search + masks + cross-shard exchange, results -> host
-            if px is not None:
-                # pipelined like the N = 1 path: the step's copies, kernels, exchange and result reads are all queued on
-                # the stream of its buffer set; the host only waits for a set's previous results when it reuses the set
-                bi = k % NBUF
-                ks = kstreams[bi]
-                set_done[bi].synchronize()
-                dtok, doff = set_in[bi]
-                rsp, rep, rcnt, rnd = set_out[bi]
-                n = q.numel()
-                with torch.cuda.stream(ks):
-                    dtok[:n].copy_(q, non_blocking=True)
-                    doff.copy_(offs, non_blocking=True)
-                step_full(k, q_off=(dtok[:n], doff))
-                _native.check(L.fmidx_mask_popcount(ix._h, C.c_void_p(result["mask"].data_ptr()), own, VOCAB,
-                                                    C.c_void_p(set_n32[bi].data_ptr()), C.c_void_p(ks.cuda_stream)))
-                with torch.cuda.stream(ks):
-                    rsp.copy_(bufs[bi][0], non_blocking=True)
-                    rep.copy_(bufs[bi][1], non_blocking=True)
-                    rcnt.copy_(result["count"], non_blocking=True)
-                    rnd[:own].copy_(set_n32[bi], non_blocking=True)
-                    set_done[bi].record(ks)
-                return
-            dtok = torch.empty(q.numel(), dtype=torch.int32, device=device)
-            dtok.copy_(q, non_blocking=True)
-            doff = dq[0][1]
-            doff.copy_(offs, non_blocking=True)
-            step_full(k, q_off=(dtok, doff))
-            drain()
-            _native.check(L.fmidx_mask_popcount(ix._h, C.c_void_p(result["mask"].data_ptr()), own, VOCAB, C.c_void_p(n32.data_ptr()), sptr))
-            hsp.copy_(bufs[k % len(bufs)][0], non_blocking=True)
-            hep.copy_(bufs[k % len(bufs)][1], non_blocking=True)
-            hcnt.copy_(result["count"], non_blocking=True)
-            hnd[:own].copy_(n32, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-
-        if world > 1 and px is not None:
-            max_tok = max(q.numel() for q, _ in hq)
-            set_in = [(torch.empty(max_tok, dtype=torch.int32, device=device), torch.empty(B + 1, dtype=torch.int64, device=device))
-                      for _ in range(NBUF)]
-            set_out = [(torch.empty(B, dtype=torch.int64).pin_memory(), torch.empty(B, dtype=torch.int64).pin_memory(),
-                        torch.empty(B, dtype=torch.int64).pin_memory(), torch.empty(B, dtype=torch.int32).pin_memory())
-                       for _ in range(NBUF)]
-            set_n32 = [torch.empty(own, dtype=torch.int32, device=device) for _ in range(NBUF)]
-            set_done = [torch.cuda.Event() for _ in range(NBUF)]
-            torch.cuda.synchronize()
-
-        for w in range(args.warmup):
-            e2e_step(w)
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(args.steps):
-            e2e_step(k)
-        if world == 1:
-            for slot in range(NSLOT):
-                _native.check(L.fmidx_query_wait(ix._h, slot))  # every step's results are on the host
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            tt = torch.tensor([dt], device=device, dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt[0])
-        h2d = int(np.mean([q.numel() * 4 + offs.numel() * 8 for q, offs in hq]))
-        e2e = {"value": B * args.steps / dt, "unit": "queries/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": B * (8 + 8 + 4) if world == 1 else B * 24 + own * 4, "ms_per_step": 1e3 * dt / args.steps,
-               "api": "fmidx_query_submit/fmidx_query_wait, %d batches in flight (pinned host prefixes in; ranges + distinct-token "
-                      "counts out, every step; masks stay in HBM)" % NSLOT
-                      if world == 1 else "pinned host prefixes -> H2D -> fmidx_search_batch + fmidx_xchg_local + fmidx_xchg_round (peer-memory "
-                      "exchange) -> D2H of ranges, total counts and distinct counts of the owned prefixes, every step; %d steps in "
-                      "flight, one per buffer set" % NBUF}
-
-    # ---- CPU baseline beside the GPU numbers (rank 0, N=1) ---------------------------------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        try:
-            nthreads = os.cpu_count() or 1
-            t0 = time.time()
-            o = oracle_from_gpu_sa(toks, beg, local, ix)
-            log("oracle built in %.1fs" % (time.time() - t0))
-            q, offs = qsets[0]
-            qn, on = q.cpu().numpy(), offs.cpu().numpy()
-            cb = min(B, args.cpu_batch)
-            qn, on = qn[:on[cb]], on[:cb + 1]
-            # parity spot check of the product against the oracle on this very batch
-            osp, oep, omask, _ = o.query_batch(qn, on, shift=SHIFT, want_mask=True, vocab=VOCAB, nthreads=nthreads)
-            step_full(0)
-            torch.cuda.synchronize()
-            ok = bool((sp[:cb].cpu().numpy().astype(np.uint64) == osp).all() and (ep[:cb].cpu().numpy().astype(np.uint64) == oep).all()
-                      and (mask[:cb].cpu().numpy().view(np.uint32) == omask).all())
-            tt = min(cpu_step(o, qn, on, nthreads) for _ in range(2))
-            t1 = cpu_step(o, qn[:on[256]], on[:257], 1)
-            cpu = {"value": cb / tt, "unit": "queries/s", "cores": nthreads, "kind": "port",
-                   "sample": "one batch of %d prefixes (search + distinct-token mask), best of 2, oracle/fm_oracle.c "
-                             "(sdsl-semantics restatement, not sdsl-lite) on a pthread pool" % cb,
-                   "single_thread_queries_per_sec": 256 / t1, "parity_vs_gpu_on_sample": ok}
-            del o
-        except Exception as e:  # the baseline must never take the bench line down
-            cpu = {"value": None, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
-
-    if rank == 0:
-        value = B * args.steps / (total_ms * 1e-3)
-        line = {
-            "metric": "prefix_queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": workload_config(args, B),
-            "masks_per_sec": value, "roofline": dom, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "pipeline": {"streams": NPIPE if world == 1 else 1, "serial_ms_per_step": serial_ms_per_step,
-                         "note": "value/ms_per_step: independent batches alternate between the streams (fmidx_query_batch); "
-                                 "roofline launch durations come from the serial pass (one stream, events around each kernel group)"
-                                 if world == 1 else "one stream + scratch slot + flag set per buffer set (4): kernels and exchange of a set back to back on its stream; roofline "
-                                 "launch durations from a serial pass"},
-            "clocks": clocks, "index": {"build_s": t_build, "device_mb": info["device_bytes"] / 1e6, "levels": info["levels"],
-                                        "layout": "wavelet matrix: 3 nibble levels (128-B cells) + byte level (1,536-B cells); %s (sa_dens %d, isa_dens %d, text %s)" % (args.layout, info["sa_dens"], info["isa_dens"], bool(info["keep_text"]))},
-        }
-        emit(line)
-    if world > 1:
-        if px is not None:
-            px.close()
-        dist.destroy_process_group()
+        run_single(args, device, local)
 
 
 if __name__ == "__main__":

@@ -14,6 +14,7 @@ SIGNATURES = {
     "fmidx_new": (C.c_int, [C.c_int, C.POINTER(p)]),
     "fmidx_free": (None, [p]),
     "fmidx_set_options": (C.c_int, [p, u32, u32, C.c_int]),
+    "fmidx_tune": (C.c_int, [p, C.c_char_p, i64]),
     "fmidx_initialize": (C.c_int, [p, p, sz]),
     "fmidx_initialize_from_file": (C.c_int, [p, C.c_char_p, C.c_int]),
     "fmidx_initialize_device": (C.c_int, [p, p, sz, p]),
@@ -29,6 +30,7 @@ SIGNATURES = {
     "fmidx_extract_text": (C.c_int, [p, u64, u64, p, sz, C.POINTER(sz)]),
     "fmidx_search_batch": (C.c_int, [p, p, p, sz, i64, p, p, p]),
     "fmidx_step_batch": (C.c_int, [p, p, p, p, sz, p, p, p]),
+    "fmidx_decode_step": (C.c_int, [p, p, i64, p, p, p, p, p, sz, i64, i64, i64, i64, p, p, p, p]),
     "fmidx_distinct_mask_batch": (C.c_int, [p, p, p, sz, i64, u32, p, p, p]),
     "fmidx_query_batch": (C.c_int, [p, C.c_int, p, p, sz, i64, u32, p, p, p, p]),
     "fmidx_distinct_mask_batch_occ": (C.c_int, [p, p, p, sz, i64, u32, p, p, p, p]),

@@ -58,7 +58,9 @@ class RemoteFMIndex:
     def get_range_batch(self, toks, offs):
         t, f = toks.tolist(), offs.tolist()
         r = [self.get_range(t[f[i]:f[i + 1]]) for i in range(len(f) - 1)]
-        return torch.tensor([x[0] for x in r], dtype=torch.int64), torch.tensor([x[1] for x in r], dtype=torch.int64)
+        dev = toks.device  # results live where the inputs live (the processors combine them with tensors on scores.device)
+        return (torch.tensor([x[0] for x in r], dtype=torch.int64, device=dev),
+                torch.tensor([x[1] for x in r], dtype=torch.int64, device=dev))
 
     def distinct_mask_batch(self, sp, ep, vocab):
         words = (vocab + 31) // 32
@@ -67,4 +69,4 @@ class RemoteFMIndex:
         for i, (dist, _) in enumerate(res):
             t = np.asarray([x for x in dist if 0 <= x < vocab], dtype=np.int64)
             np.bitwise_or.at(m[i], t >> 5, (np.uint32(1) << (t & 31).astype(np.uint32)))
-        return torch.from_numpy(m.view(np.int32))
+        return torch.from_numpy(m.view(np.int32)).to(sp.device)

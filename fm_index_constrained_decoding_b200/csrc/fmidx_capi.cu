@@ -1,5 +1,6 @@
 // fmidx_capi.cu -- the extern "C" boundary declared in include/fmidx.h.
 // Replaces the SWIG wrapper generated from cpp_modules_linux/fm_index.i:7-21 of the reference.
+#include <algorithm>
 #include <cerrno>
 #include <cstdlib>
 #include <cstring>
@@ -74,6 +75,55 @@ static int enter(fmidx *h, bool need_ready) {
     return FMIDX_OK;
 }
 
+// Unigram continuation table (fmidx_layout.cuh): built with the library's own enumeration kernels, once per index.
+int fm_build_unigram_table(fmidx *h, cudaStream_t s) {
+    FmDev &d = h->dev;
+    d.uni_n = 0;
+    d.uni_sp = d.uni_ep = d.uni_masks = nullptr;
+    if (!d.bwt || h->tune_unigram_max == 0 || d.n < 2) return FMIDX_OK;  // resident layout only
+    const uint32_t nsym = d.max_sym + 1;
+    std::vector<uint32_t> C(nsym + 1);
+    FM_CUDA(cudaMemcpyAsync(C.data(), d.C, (size_t)(nsym + 1) * 4, cudaMemcpyDeviceToHost, s));
+    FM_CUDA(cudaStreamSynchronize(s));
+    // the symbols whose block is too wide to be read row by row, most frequent first, at most tune_unigram_max
+    const uint32_t min_rows = std::max<uint32_t>(h->tune_scan_max, 1024u);
+    std::vector<uint32_t> cand;
+    for (uint32_t c = 1; c < nsym; ++c)
+        if (C[c + 1] - C[c] > min_rows) cand.push_back(c);
+    if (cand.size() > h->tune_unigram_max) {
+        std::nth_element(cand.begin(), cand.begin() + h->tune_unigram_max, cand.end(),
+                         [&](uint32_t a, uint32_t b) { return C[a + 1] - C[a] > C[b + 1] - C[b]; });
+        cand.resize(h->tune_unigram_max);
+    }
+    std::sort(cand.begin(), cand.end());
+    const size_t n = cand.size();
+    if (n == 0) return FMIDX_OK;
+    const uint32_t words = (nsym + 31u) >> 5;
+    std::vector<uint32_t> sp(n), ep(n);
+    std::vector<uint64_t> sp64(n), ep64(n);
+    for (size_t i = 0; i < n; ++i) {
+        sp[i] = C[cand[i]]; ep[i] = C[cand[i] + 1];
+        sp64[i] = sp[i]; ep64[i] = ep[i];
+    }
+    uint32_t *d_sp = nullptr, *d_ep = nullptr, *d_masks = nullptr;
+    uint64_t *d_r = nullptr;
+    FM_TRY(fm_dev_alloc(h, (void **)&d_sp, n * 4, true));
+    FM_TRY(fm_dev_alloc(h, (void **)&d_ep, n * 4, true));
+    FM_TRY(fm_dev_alloc(h, (void **)&d_masks, n * (size_t)words * 4, true));
+    FM_CUDA(cudaMalloc((void **)&d_r, n * 16));
+    FM_CUDA(cudaMemcpyAsync(d_sp, sp.data(), n * 4, cudaMemcpyHostToDevice, s));
+    FM_CUDA(cudaMemcpyAsync(d_ep, ep.data(), n * 4, cudaMemcpyHostToDevice, s));
+    FM_CUDA(cudaMemcpyAsync(d_r, sp64.data(), n * 8, cudaMemcpyHostToDevice, s));
+    FM_CUDA(cudaMemcpyAsync(d_r + n, ep64.data(), n * 8, cudaMemcpyHostToDevice, s));
+    // symbol axis: shift 0, "vocab" = every symbol; the table is not in use yet (uni_n == 0), so this is the plain walk
+    int rc = fm_launch_mask(h, d_r, d_r + n, n, 0, nsym, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, d_masks, nullptr, s);
+    cudaStreamSynchronize(s);
+    cudaFree(d_r);
+    FM_TRY(rc);
+    d.uni_sp = d_sp; d.uni_ep = d_ep; d.uni_masks = d_masks; d.uni_n = (uint32_t)n; d.uni_words = words;
+    return FMIDX_OK;
+}
+
 extern "C" {
 
 const char *fmidx_last_error(void) { return g_err; }
@@ -98,6 +148,14 @@ int fmidx_new(int device, fmidx_t **out) {
     int sms = 0;
     FM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     h->sm_count = sms > 0 ? sms : 148;
+    auto env_long = [](const char *name, long dflt) {
+        const char *e = getenv(name);
+        return e && *e ? atol(e) : dflt;
+    };
+    h->tune_scan_max = (uint32_t)std::min<long>(std::max<long>(env_long("FMIDX_SCAN_MAX", 16384), 0), 1l << 24);
+    h->tune_bytes_occ = (int)env_long("FMIDX_BYTES_OCC", 5);
+    h->tune_unigram = env_long("FMIDX_UNIGRAM_TABLE", 1) ? 1 : 0;
+    h->tune_unigram_max = (uint32_t)std::min<long>(std::max<long>(env_long("FMIDX_UNIGRAM_MAX", 1024), 0), 65536);
     *out = h.release();
     return FMIDX_OK;
 }
@@ -131,6 +189,16 @@ int fmidx_set_options(fmidx_t *h, uint32_t sa_dens, uint32_t isa_dens, int keep_
     return FMIDX_OK;
 }
 
+// ---- tunables ---------------------------------------------------------------------------------------
+int fmidx_tune(fmidx_t *h, const char *key, int64_t value) {
+    if (!h || !key) { fm_set_error("null argument"); return FMIDX_EINVAL; }
+    if (!strcmp(key, "scan_max")) h->tune_scan_max = (uint32_t)std::min<int64_t>(std::max<int64_t>(value, 0), 1ll << 24);
+    else if (!strcmp(key, "bytes_occ")) h->tune_bytes_occ = (int)value;
+    else if (!strcmp(key, "unigram_table")) h->tune_unigram = value ? 1 : 0;
+    else { fm_set_error("fmidx_tune: unknown key '%s'", key); return FMIDX_EINVAL; }
+    return FMIDX_OK;
+}
+
 // ---- build ------------------------------------------------------------------------------------------
 static int build_from_host_u32(fmidx *h, const std::vector<uint32_t> &sym) {
     uint32_t *d = nullptr;
@@ -142,6 +210,7 @@ static int build_from_host_u32(fmidx *h, const std::vector<uint32_t> &sym) {
         rc = FMIDX_ECUDA;
     } else {
         rc = fm_build_from_device_text(h, d, sym.size(), h->stream);
+        if (rc == FMIDX_OK) rc = fm_build_unigram_table(h, h->stream);
     }
     cudaStreamSynchronize(h->stream);
     cudaFree(d);
@@ -194,7 +263,8 @@ int fmidx_initialize_from_file(fmidx_t *h, const char *path, int width) {
 int fmidx_initialize_device(fmidx_t *h, const uint32_t *d_symbols, size_t n, void *stream) {
     FM_TRY(enter(h, false));
     if (n && !d_symbols) { fm_set_error("d_symbols is NULL"); return FMIDX_EINVAL; }
-    return fm_build_from_device_text(h, d_symbols, n, (cudaStream_t)stream);
+    FM_TRY(fm_build_from_device_text(h, d_symbols, n, (cudaStream_t)stream));
+    return fm_build_unigram_table(h, (cudaStream_t)stream);
 }
 
 // ---- persistence ------------------------------------------------------------------------------------
@@ -292,6 +362,7 @@ int fmidx_load(const char *path, int device, fmidx_t **out) {
             h->dev = d;
             h->opt_sa_dens = d.sa_dens; h->opt_isa_dens = d.isa_dens; h->opt_keep_text = hd.keep_text;
             h->ready = true;
+            rc = fm_build_unigram_table(h, h->stream);  // derived data: rebuilt rather than stored
         }
     }
     fclose(f);
@@ -494,6 +565,20 @@ int fmidx_step_batch(fmidx_t *h, const uint64_t *d_symbols, const uint64_t *d_lo
     return fm_launch_step(h, d_symbols, d_lows, d_highs, B, d_sp, d_ep, (cudaStream_t)stream);
 }
 
+int fmidx_decode_step(fmidx_t *h, const int64_t *d_last_tok, int64_t tok_stride, const int32_t *d_parent, const uint64_t *d_state_sp_in,
+                      const uint64_t *d_state_ep_in, uint64_t *d_state_sp_out, uint64_t *d_state_ep_out, size_t B, int64_t shift,
+                      int64_t eos, int64_t pad, int64_t stop_at_count, uint64_t *d_query_sp, uint64_t *d_query_ep,
+                      int32_t *d_override_tok, void *stream) {
+    FM_TRY(enter(h, true));
+    if (!d_last_tok || !d_state_sp_in || !d_state_ep_in || !d_state_sp_out || !d_state_ep_out || !d_query_sp || !d_query_ep || !d_override_tok) {
+        fm_set_error("null argument");
+        return FMIDX_EINVAL;
+    }
+    if (d_state_sp_in == d_state_sp_out || d_state_ep_in == d_state_ep_out) { fm_set_error("decode_step: the state is double-buffered (rows are gathered by parent)"); return FMIDX_EINVAL; }
+    return fm_launch_decode_step(h, d_last_tok, tok_stride, d_parent, d_state_sp_in, d_state_ep_in, d_state_sp_out, d_state_ep_out, B,
+                                 shift, eos, pad, stop_at_count, d_query_sp, d_query_ep, d_override_tok, (cudaStream_t)stream);
+}
+
 int fmidx_distinct_mask_batch(fmidx_t *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, int64_t shift,
                               uint32_t vocab, uint32_t *d_mask, uint32_t *d_counts, void *stream) {
     FM_TRY(enter(h, true));
@@ -505,7 +590,7 @@ int fmidx_distinct_mask_batch(fmidx_t *h, const uint64_t *d_sp, const uint64_t *
 int fmidx_query_batch(fmidx_t *h, int ws_slot, const int32_t *d_toks, const int64_t *d_offs, size_t B, int64_t shift,
                       uint32_t vocab, uint64_t *d_sp, uint64_t *d_ep, uint32_t *d_mask, void *stream) {
     FM_TRY(enter(h, true));
-    if (ws_slot < 0 || ws_slot >= 8) { fm_set_error("ws_slot must be 0..7"); return FMIDX_EINVAL; }
+    if (ws_slot < 0 || ws_slot >= FMIDX_SLOTS) { fm_set_error("ws_slot must be 0..%d", FMIDX_SLOTS - 1); return FMIDX_EINVAL; }
     if (!d_sp || !d_ep) { fm_set_error("null argument"); return FMIDX_EINVAL; }
     // the search kernel also zeroes the mask rows (its stores are free: it is bound by its dependent-load chain)
     const bool kz = vocab != 0 && fm_search_can_zero(d_mask, vocab);
@@ -657,13 +742,13 @@ static int query_host_impl(fmidx_t *h, const int32_t *toks, const int64_t *offs,
 
 int fmidx_query_submit(fmidx_t *h, int slot, const int32_t *toks, const int64_t *offs, size_t B, int64_t shift,
                        uint32_t vocab, uint64_t *sp, uint64_t *ep, uint32_t *n_distinct) {
-    if (slot < 0 || slot >= 8) { fm_set_error("slot must be 0..7"); return FMIDX_EINVAL; }
+    if (slot < 0 || slot >= FMIDX_SLOTS) { fm_set_error("slot must be 0..%d", FMIDX_SLOTS - 1); return FMIDX_EINVAL; }
     return query_host_impl(h, toks, offs, B, shift, vocab, sp, ep, nullptr, n_distinct, slot);
 }
 
 int fmidx_query_wait(fmidx_t *h, int slot) {
     FM_TRY(enter(h, false));
-    if (slot < 0 || slot >= 8) { fm_set_error("slot must be 0..7"); return FMIDX_EINVAL; }
+    if (slot < 0 || slot >= FMIDX_SLOTS) { fm_set_error("slot must be 0..%d", FMIDX_SLOTS - 1); return FMIDX_EINVAL; }
     if (h->slots[slot].stream) FM_CUDA(cudaStreamSynchronize(h->slots[slot].stream));
     return FMIDX_OK;
 }

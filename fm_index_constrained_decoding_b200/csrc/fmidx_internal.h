@@ -13,6 +13,8 @@
 #include "../../include/fmidx.h"
 #include "fmidx_layout.cuh"
 
+#define FMIDX_SLOTS 16  // pipelined slots / scratch workspaces / buffer sets per handle
+
 void fm_set_error(const char *fmt, ...);
 extern std::atomic<uint64_t> g_fm_launches;
 
@@ -82,10 +84,17 @@ struct fmidx {
     struct Slot {                // fmidx_query_submit / fmidx_query_wait: independent in-flight host batches
         cudaStream_t stream = nullptr;
         FmBuf in, mask, ws;
-    } slots[8];
+    } slots[FMIDX_SLOTS];
     FmBuf h_scratch[4];
     int sm_count = 148;
+    // tunables (fmidx_tune; initialised from the environment by fmidx_new)
+    uint32_t tune_scan_max = 16384;  // ranges of up to this many rows are read off the resident BWT ($FMIDX_SCAN_MAX)
+    int tune_bytes_occ = 5;          // CTAs per SM of the persistent k_mask_bytes grid ($FMIDX_BYTES_OCC)
+    int tune_unigram = 1;            // use the unigram continuation table at query time ($FMIDX_UNIGRAM_TABLE)
+    uint32_t tune_unigram_max = 1024;  // table entries built at most ($FMIDX_UNIGRAM_MAX; 0: none)
 };
+
+int fm_build_unigram_table(fmidx *h, cudaStream_t s);
 
 int fm_dev_alloc(fmidx *h, void **out, size_t bytes, bool owned);
 int fm_scratch(fmidx *h, FmBuf &b, size_t bytes, bool pinned_host);
@@ -101,6 +110,9 @@ int fm_launch_search(fmidx *h, const int32_t *d_toks, const int64_t *d_offs, siz
 bool fm_search_can_zero(const uint32_t *d_mask, uint32_t vocab);
 int fm_launch_step(fmidx *h, const uint64_t *d_sym, const uint64_t *d_lo, const uint64_t *d_hi, size_t B,
                    uint64_t *d_sp, uint64_t *d_ep, cudaStream_t s);
+int fm_launch_decode_step(fmidx *h, const int64_t *d_last_tok, int64_t tok_stride, const int32_t *d_parent, const uint64_t *d_sp_in,
+                          const uint64_t *d_ep_in, uint64_t *d_sp_out, uint64_t *d_ep_out, size_t B, int64_t shift, int64_t eos,
+                          int64_t pad, int64_t stop_at_count, uint64_t *d_qsp, uint64_t *d_qep, int32_t *d_override, cudaStream_t s);
 int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, int64_t shift, uint32_t vocab,
                    const void *d_logits, void *d_out, int dtype, int64_t row_stride, const int32_t *d_override,
                    int32_t always_allow, const uint32_t *d_extra, uint32_t n_extra, uint32_t *d_mask,

@@ -231,6 +231,56 @@ __global__ void __launch_bounds__(128) k_step(FmDev ix, const uint64_t *__restri
     }
 }
 
+// Incremental decoding: one backward-search step per beam per generated token, state kept on the device.
+// state (sp, ep) of beam r = get_range(force + history_r) as index.py:103-114 computes it ((0,0) once empty, and then for
+// good); the new row r continues the state of row parent[r] (beam reordering) with its newest token, read on the device
+// out of input_ids (last column, row stride given).  The kernel also prepares what the fused mask kernel needs,
+// exactly as document_constrained_generation_vllm.py:78-118 decides it row by row:
+//   last token eos / pad             -> query range (0,0), override {pad}
+//   stop_at_count > 0 and count(history[:-1]) = width of the PARENT state <= stop_at_count (checked first) -> override {eos}
+//   otherwise                        -> query range = new state, no override
+__global__ void __launch_bounds__(128)
+k_decode_step(FmDev ix, const int64_t *__restrict__ last_tok, int64_t tok_stride, const int32_t *__restrict__ parent,
+              const uint64_t *__restrict__ st_sp_in, const uint64_t *__restrict__ st_ep_in, uint64_t *__restrict__ st_sp_out,
+              uint64_t *__restrict__ st_ep_out, uint32_t B, int64_t shift, int64_t eos, int64_t pad, int64_t stop_at_count,
+              uint64_t *__restrict__ q_sp, uint64_t *__restrict__ q_ep, int32_t *__restrict__ override_tok) {
+    const int lane = threadIdx.x & 31, sub = lane & 7, half = (lane >> 3) & 1;
+    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const bool valid = q < B;
+    int64_t tok = 0;
+    uint64_t psp = 0, pep = 0;
+    if (valid) {
+        tok = last_tok[(int64_t)q * tok_stride];
+        const uint32_t pr = parent ? (uint32_t)parent[q] : q;
+        psp = st_sp_in[pr];
+        pep = st_ep_in[pr];
+    }
+    const int64_t sym = tok + shift;
+    const bool alive = valid && pep > psp;                                  // (0,0): the history left the corpus earlier
+    const bool ok = alive && sym >= 0 && sym <= (int64_t)ix.max_sym;        // absent symbol -> empty
+    const uint32_t c = ok ? (uint32_t)sym : 0u;
+    const uint32_t Dc = ok ? ix.D[c] : 0u;
+    uint32_t pos = ok ? (half ? (uint32_t)pep : (uint32_t)psp) : 0u;        // step(sym, low, high = ep - 1): rank at low and at high + 1
+    pos = fm_descend8(ix, pos, c, sub, ok);
+    const uint32_t res = Dc + pos;
+    const uint32_t oth = __shfl_xor_sync(FULL, res, 8);
+    const uint32_t nlo = half ? oth : res, nhi = half ? res : oth;
+    if (valid && (lane & 15) == 0) {
+        const bool hit = ok && nlo < nhi;
+        const uint64_t nsp = hit ? nlo : 0, nep = hit ? nhi : 0;
+        st_sp_out[q] = nsp;
+        st_ep_out[q] = nep;
+        const bool finished = tok == eos || tok == pad;
+        const uint64_t count_prev = finished ? 0 : pep - psp;               // vllm.py:81-92
+        int32_t ovr = -1;
+        if (stop_at_count > 0 && (int64_t)count_prev <= stop_at_count) ovr = (int32_t)eos;   // vllm.py:105-108
+        else if (finished) ovr = (int32_t)pad;                                               // vllm.py:110-118
+        q_sp[q] = finished ? 0 : nsp;
+        q_ep[q] = finished ? 0 : nep;
+        override_tok[q] = ovr;
+    }
+}
+
 // =================================================================================================
 // K2: distinct-symbol enumeration of BWT[sp,ep) -> vocab bitmap (+counts), fused with the -inf
 // masking of the beam's logits row.
@@ -574,6 +624,36 @@ __device__ __forceinline__ void fm_scan_rows(const uint32_t *__restrict__ bwt, u
     }
 }
 
+// ---- unigram continuation table ---------------------------------------------------------------------------------
+// index of the table entry whose block is exactly [s,e), or -1 (binary search over <= 1024 sorted block starts)
+__device__ __forceinline__ int fm_uni_find(const FmDev &ix, uint32_t s, uint32_t e) {
+    int lo = 0, hi = (int)ix.uni_n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(ix.uni_sp + mid) < s) lo = mid + 1;
+        else hi = mid;
+    }
+    return (lo < (int)ix.uni_n && __ldg(ix.uni_sp + lo) == s && __ldg(ix.uni_ep + lo) == e) ? lo : -1;
+}
+// word i of the TOKEN-axis bitmap (token = symbol - shift, 0 <= token < vocab) cut out of a symbol-axis table row
+__device__ __forceinline__ uint32_t fm_uni_word(const uint32_t *__restrict__ srow, uint32_t src_words, uint32_t i, int64_t shift,
+                                                uint32_t vocab) {
+    const int64_t b0 = (int64_t)32 * i + shift;  // symbol index of the word's bit 0
+    uint32_t v = 0;
+    if (b0 >= 0) {
+        const uint64_t w = (uint64_t)b0 >> 5;
+        const uint32_t r = (uint32_t)b0 & 31u;
+        const uint32_t lo = w < src_words ? __ldg(srow + w) : 0u, hi = (r && w + 1 < src_words) ? __ldg(srow + w + 1) : 0u;
+        v = r ? (lo >> r) | (hi << (32u - r)) : lo;
+    } else if (b0 > -32) {
+        v = (src_words ? __ldg(srow) : 0u) << (uint32_t)(-b0);
+    }
+    const uint32_t t0 = 32u * i;
+    if (t0 >= vocab) return 0u;
+    if (vocab - t0 < 32u) v &= (1u << (vocab - t0)) - 1u;
+    return v;
+}
+
 // ---- phase A --------------------------------------------------------------------------------------
 // lvl = concatenated dense node tables, level l at offset B * sum_{j<l} P_j, row b = P_l entries.
 __global__ void __launch_bounds__(128)
@@ -615,6 +695,24 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
         uint32_t *row = mask_out + (size_t)b * mw;
         const bool dense = b - dense_lo < dense_n;
         if (xcounts && lane == 0) xcounts[b] = e > s ? e - s : 0ull;  // occurrence count of the prefix on this shard
+        if (ix.uni_n && !counts_out && e > s && e - s > (uint64_t)SCAN_INLINE) {
+            const int ui = fm_uni_find(ix, (uint32_t)s, (uint32_t)e);
+            const uint32_t nslices = (vocab + SLICE - 1) / SLICE;
+            if (ui >= 0 && L > 0 && nslices <= fm_nodes_at(ix.max_sym, L, LT)) {  // the work list has P_top slots per prefix
+                // the range is one frequent symbol's whole block: its continuation set is in the table.  One work item per
+                // 4096-token slice (a half-warp of k_mask_expand copies 512 B); the row is written once, complete -- no
+                // zeroing, no walk.  Every slice is reported as possibly occupied (the words are conservative by contract).
+                const uint32_t ow = (nslices + 31u) >> 5;
+                uint32_t slot = 0;
+                if (lane == 0) slot = atomicAdd(work_count, nslices);
+                slot = __shfl_sync(FULL, slot, 0);
+                for (uint32_t i = (uint32_t)lane; i < nslices; i += 32) work_items[slot + i] = make_uint4(b, 0xFFFFFFFEu, (uint32_t)ui, i);
+                if (occ_out)
+                    for (uint32_t i = (uint32_t)lane; i < ow; i += 32)
+                        occ_out[(size_t)b * ow + i] = (i + 1u) * 32u <= nslices ? ~0u : ((1u << (nslices & 31u)) - 1u);
+                return;
+            }
+        }
         if (dense && !(zflags & 1u)) {  // bit 0: the rows were zeroed by k_search (fmidx_query_batch)
             if (zflags & 2u) {           // bit 1: 16-byte stores are legal
                 uint4 *row4 = reinterpret_cast<uint4 *>(row);
@@ -727,10 +825,11 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
         }
     }
     uint2 *cur = lvl + b;
-    if (!work_items && ix.bwt) {  // logits mode: k_mask_logits reads narrow ranges off the resident BWT itself
+    if (!work_items && ix.bwt && !(override_tok && override_tok[b] >= 0)) {  // logits mode: k_mask_logits reads narrow ranges off the resident BWT itself
         uint64_t s = sp[b], e = ep[b];
         if (e > ix.n) e = ix.n;
         if (s >= e || e - s <= (uint64_t)SCAN_INLINE) return;
+        if (ix.uni_n && fm_uni_find(ix, (uint32_t)s, (uint32_t)e) >= 0) return;  // k_mask_logits takes the slice from the table
     }
     if (lane == 0) {
         uint64_t s = sp[b], e = ep[b];
@@ -958,6 +1057,15 @@ __device__ __forceinline__ void fm_enum_slice(const FmDev &ix, const uint2 *__re
             });
             return;
         }
+        if (ix.uni_n) {
+            const int ui = fm_uni_find(ix, (uint32_t)s64, (uint32_t)e64);
+            if (ui >= 0) {  // one frequent symbol's whole block: the slice comes straight out of the unigram table
+                const uint32_t *srow = ix.uni_masks + (size_t)ui * ix.uni_words;
+                const uint32_t t1 = (uint32_t)min((int64_t)se - shift, (int64_t)t0 + SLICE);  // tokens of this slice: [t0, t1)
+                for (uint32_t w = threadIdx.x; w < SLICE / 32; w += blockDim.x) S.bm[w] = fm_uni_word(srow, ix.uni_words, (t0 >> 5) + w, shift, t1);
+                return;
+            }
+        }
     }
     if (threadIdx.x == 0) fm_seed_from_table(ix, top_b, LT, sa, se, S);
     __syncthreads();
@@ -1001,6 +1109,26 @@ k_mask_expand(FmDev ix, uint32_t LT, int64_t shift, uint32_t vocab, const uint4 
         bool has = i < n_items;
         const uint4 it = has ? __ldg(items + i) : make_uint4(0u, 0u, 0u, 0u);
         const uint32_t b = it.x, prefix = it.y, lo = it.z, hi = it.w;
+        const bool tab_item = has && prefix == 0xFFFFFFFEu;   // one 4096-token slice of a unigram-table row: lo = entry, hi = slice
+        if (__any_sync(FULL, tab_item)) {
+            if (tab_item) {
+                const uint32_t *srow = ix.uni_masks + (size_t)lo * ix.uni_words;
+                uint32_t *drow = mask_out + (size_t)b * mask_words;
+                uint32_t v[SLICE / 32 / 16];
+#pragma unroll
+                for (int k = 0; k < SLICE / 32 / 16; ++k) {
+                    const uint32_t i = hi * (SLICE / 32) + 16u * (uint32_t)k + (uint32_t)hl;
+                    v[k] = i < mask_words ? fm_uni_word(srow, ix.uni_words, i, shift, vocab) : 0u;
+                }
+#pragma unroll
+                for (int k = 0; k < SLICE / 32 / 16; ++k) {
+                    const uint32_t i = hi * (SLICE / 32) + 16u * (uint32_t)k + (uint32_t)hl;
+                    if (i < mask_words) drow[i] = v[k];
+                }
+            }
+            __syncwarp();
+        }
+        has = has && !tab_item;
         const bool scan_item = has && prefix == 0xFFFFFFFFu;  // a chunk of a mid-sized range: read its rows off the resident BWT
         if (__any_sync(FULL, scan_item)) {
             if (scan_item)
@@ -1058,20 +1186,35 @@ k_mask_expand(FmDev ix, uint32_t LT, int64_t shift, uint32_t vocab, const uint4 
                 if (lane >= d) inc += t;
             }
             const uint32_t total = __shfl_sync(FULL, inc, 31), excl = inc - wsm;
-            for (uint32_t f0 = 0; f0 < total; f0 += 32u) {
-                const uint32_t f = f0 + (uint32_t)lane;
-                uint32_t own = 0;  // first lane whose inclusive sum exceeds f
+            // four passes (128 rows) per iteration: the owners of all four are found first, then the four byte loads are
+            // issued, then the bits are set -- the passes are independent, and a serial load -> atomic chain per pass made this
+            // kernel latency-bound (20 us for 1.3 M instructions)
+            for (uint32_t f0 = 0; f0 < total; f0 += 128u) {
+                uint32_t o_cp[4], o_b[4], addr[4];
+                bool live[4];
 #pragma unroll
-                for (int step = 16; step >= 1; step >>= 1)
-                    if (__shfl_sync(FULL, inc, (int)own + step - 1) <= f) own += (uint32_t)step;
-                own = min(own, 31u);
-                const uint32_t o_excl = __shfl_sync(FULL, excl, (int)own), o_lo = __shfl_sync(FULL, r_lo, (int)own);
-                const uint32_t o_cp = __shfl_sync(FULL, cp, (int)own), o_b = __shfl_sync(FULL, b, (int)own);
-                if (f < total) {
-                    const uint32_t sy = (o_cp << 8) | fm_byte_at(ix.bcells, o_lo + (f - o_excl));
-                    if (sy >= ga && sy < ge) {
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t f = f0 + 32u * (uint32_t)u + (uint32_t)lane;
+                    uint32_t own = 0;  // first lane whose inclusive sum exceeds f
+#pragma unroll
+                    for (int step = 16; step >= 1; step >>= 1)
+                        if (__shfl_sync(FULL, inc, (int)own + step - 1) <= f) own += (uint32_t)step;
+                    own = min(own, 31u);
+                    const uint32_t o_excl = __shfl_sync(FULL, excl, (int)own), o_lo = __shfl_sync(FULL, r_lo, (int)own);
+                    o_cp[u] = __shfl_sync(FULL, cp, (int)own);
+                    o_b[u] = __shfl_sync(FULL, b, (int)own);
+                    live[u] = f < total;
+                    addr[u] = o_lo + (f - o_excl);
+                }
+                uint32_t by[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) by[u] = live[u] ? fm_byte_at(ix.bcells, addr[u]) : 0u;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t sy = (o_cp[u] << 8) | by[u];
+                    if (live[u] && sy >= ga && sy < ge) {
                         const uint32_t tk = (uint32_t)((int64_t)sy - shift);
-                        atomicOr(&mask_out[(size_t)o_b * mask_words + (tk >> 5)], 1u << (tk & 31u));
+                        atomicOr(&mask_out[(size_t)o_b[u] * mask_words + (tk >> 5)], 1u << (tk & 31u));
                     }
                 }
             }
@@ -1479,8 +1622,10 @@ __global__ void __launch_bounds__(256) k_or_pieces(const uint4 *__restrict__ pie
 }
 
 // ---- fused second half of a sharded step: wait + pull + OR + total counts + ack in ONE launch ------------------------
-// Persistent grid (at most 2 CTAs per SM, so that CTAs spinning on a flag can never crowd the kernels that the other
-// buffer sets in flight -- or the peers' progress -- depend on).  A warp owns rows gw, gw + nwarps, ... of the rows
+// Persistent grid of at most sm_count / 2 CTAs of 128 threads: even with all 16 buffer sets of a context waiting at once,
+// CTAs spinning on a flag can hold at most half of the GPU's thread slots, so the enumeration kernels whose tails raise
+// those very flags (on this GPU for its peers, on the peers for this GPU) always find room to run -- no launch order or
+// scheduling policy is relied upon for progress.  A warp owns rows gw, gw + nwarps, ... of the rows
 // this rank owns.  Peers are visited in ring order starting after this rank; a warp polls ONLY the data flag of the
 // peer it is about to read (ld.acquire.sys on this GPU's own memory; the peer raised it by a remote store at the tail
 // of its last enumeration kernel), then reads that peer's occupancy word(s) from the local inbox and pulls just the
@@ -1488,7 +1633,7 @@ __global__ void __launch_bounds__(256) k_or_pieces(const uint4 *__restrict__ pie
 // bitmap buffer over NVLink, OR-ing them into this rank's own rows in place.  When every peer has been read the warps
 // sum the occurrence counts of all B prefixes, and the CTA that finishes last raises ack flag[rank] = seq on every
 // shard ("rank has finished reading your buffers of step seq").
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 k_xchg_pull(uint32_t *const *__restrict__ peer_masks, uint32_t *const *__restrict__ peer_ack_flags,
             const uint32_t *__restrict__ data_flags, const uint32_t *__restrict__ inbox, uint32_t xwords, uint32_t count_off,
             uint32_t world, uint32_t rank, uint32_t B, uint32_t vocab, uint32_t seq, uint64_t *__restrict__ counts_out,
@@ -1774,7 +1919,14 @@ int fm_launch_search(fmidx *h, const int32_t *d_toks, const int64_t *d_offs, siz
 
 // true when fm_launch_search can zero [B][words] mask rows at d_mask on behalf of fm_launch_mask
 bool fm_search_can_zero(const uint32_t *d_mask, uint32_t vocab) {
-    return d_mask && ((((vocab + 31u) >> 5) & 3u) == 0) && (((uintptr_t)d_mask & 15) == 0);
+    // Off unless $FMIDX_K1_ZERO=1.  Measured on B200 (profiles/README.md, round 2): the 65 MB of row stores queue up in front
+    // of the search's dependent-load chain (lg_throttle) and the kernel cannot retire before they have drained: k_search
+    // 30 -> 38 us, while k_mask_top only saves 3 us -- the rows are zeroed by k_mask_top with 16-byte stores instead.
+    static const bool on = [] {
+        const char *e = getenv("FMIDX_K1_ZERO");
+        return e && *e == '1';
+    }();
+    return on && d_mask && ((((vocab + 31u) >> 5) & 3u) == 0) && (((uintptr_t)d_mask & 15) == 0);
 }
 
 int fm_launch_step(fmidx *h, const uint64_t *d_sym, const uint64_t *d_lo, const uint64_t *d_hi, size_t B,
@@ -1783,6 +1935,18 @@ int fm_launch_step(fmidx *h, const uint64_t *d_sym, const uint64_t *d_lo, const 
     if (B == 0) return FMIDX_OK;
     if (B > 0x0FFFFFFFull) { fm_set_error("batch too large"); return FMIDX_EINVAL; }
     FM_LAUNCH(k_step, (unsigned)((B * 16 + 127) / 128), 128, 0, s, h->dev, d_sym, d_lo, d_hi, (uint32_t)B, d_sp, d_ep);
+    FM_CUDA(cudaGetLastError());
+    return FMIDX_OK;
+}
+
+int fm_launch_decode_step(fmidx *h, const int64_t *d_last_tok, int64_t tok_stride, const int32_t *d_parent, const uint64_t *d_sp_in,
+                          const uint64_t *d_ep_in, uint64_t *d_sp_out, uint64_t *d_ep_out, size_t B, int64_t shift, int64_t eos,
+                          int64_t pad, int64_t stop_at_count, uint64_t *d_qsp, uint64_t *d_qep, int32_t *d_override, cudaStream_t s) {
+    FM_TRY(check_ready(h));
+    if (B == 0) return FMIDX_OK;
+    if (B > 0x0FFFFFFFull) { fm_set_error("batch too large"); return FMIDX_EINVAL; }
+    FM_LAUNCH(k_decode_step, (unsigned)((B * 16 + 127) / 128), 128, 0, s, h->dev, d_last_tok, tok_stride, d_parent, d_sp_in, d_ep_in,
+              d_sp_out, d_ep_out, (uint32_t)B, shift, eos, pad, stop_at_count, d_qsp, d_qep, d_override);
     FM_CUDA(cudaGetLastError());
     return FMIDX_OK;
 }
@@ -1802,7 +1966,8 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
     if (has && !d_out) { fm_set_error("d_out is NULL"); return FMIDX_EINVAL; }
     if (!has && !d_mask) { fm_set_error("d_mask is NULL"); return FMIDX_EINVAL; }
     // workspace: dense node tables of levels 0..LT, then the work list and its two counters
-    const FmDev &ix = h->dev;
+    FmDev ix = h->dev;
+    if (!h->tune_unigram) ix.uni_n = 0;
     const uint32_t L = ix.levels, LT = L > 0 ? L - 1 : 0;  // nibble levels consumed by k_mask_top
     size_t n_nodes = 0, top_off = 0;
     for (uint32_t l = 0; l <= LT; ++l) {
@@ -1857,12 +2022,7 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
     const size_t items_off = 128 + ((lvl_bytes + 15) & ~(size_t)15);
     uint4 *items = has ? nullptr : (uint4 *)((char *)ws.p + items_off);
     uint4 *bnodes = (uint4 *)((char *)ws.p + items_off + items_bytes);
-    // ranges of up to $FMIDX_SCAN_MAX rows (default 16384) are read off the resident BWT instead of walking the matrix
-    static const uint32_t scan_max = [] {
-        const char *e = getenv("FMIDX_SCAN_MAX");
-        const long v = e && *e ? atol(e) : 16384;
-        return (uint32_t)(v < (long)SCAN_INLINE ? (long)SCAN_INLINE : (v > (1l << 24) ? (1l << 24) : v));
-    }();
+    const uint32_t scan_max = std::max<uint32_t>(h->tune_scan_max, SCAN_INLINE);  // rows read off the resident BWT instead of walking the matrix
     const uint32_t mwords = (vocab + 31u) >> 5;
     const uint32_t zflags = (prezeroed ? 1u : 0u) | ((!has && (mwords & 3u) == 0 && ((uintptr_t)d_mask & 15) == 0) ? 2u : 0u);
     FM_LAUNCH(k_mask_top, (unsigned)((B * 32 + 127) / 128), 128, 0, s, ix, d_sp, d_ep, (uint32_t)B, LT, lvl, d_override, shift,
@@ -1870,14 +2030,8 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
               (uint32_t)std::min<size_t>(dense_n, 0xFFFFFFFFu), zflags, xa && !has ? xa->xcounts : nullptr,
               xa ? xa->ack_flags : nullptr, xa ? xa->ack_world : 0u, xa ? xa->ack_seq : 0u, L == 0 ? SCAN_INLINE : scan_max);
     if (!has) {
-        // CTAs per SM of the persistent k_mask_bytes grid ($FMIDX_BYTES_OCC, 1..6).  Default 3: the kernel is
-        // issue-bound, and at 5-6 CTAs per SM it owns every register of the GPU for its whole run, which serialises it
-        // against the latency-bound kernels of the other batches in flight.
-        static const int occ = [] {
-            const char *e = getenv("FMIDX_BYTES_OCC");
-            const int v = e && *e ? atoi(e) : 3;
-            return v < 1 ? 1 : (v > 6 ? 6 : v);
-        }();
+        // CTAs per SM of the persistent k_mask_bytes grid (fmidx_tune "bytes_occ", 1..6)
+        const int occ = h->tune_bytes_occ < 1 ? 1 : (h->tune_bytes_occ > 6 ? 6 : h->tune_bytes_occ);
         const unsigned bgrid = (unsigned)h->sm_count * (unsigned)occ;
         FmPublish pub{};
         if (xa && xa->world) {
@@ -1990,8 +2144,8 @@ int fm_launch_xchg_pull(fmidx *h, uint32_t *const *d_peer_masks, uint32_t *const
     if (B == 0 || world == 0) return FMIDX_OK;
     const size_t own = B / world;
     const size_t warps = std::max<size_t>(own, (B + 31) / 32);
-    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((warps + 7) / 8, (size_t)h->sm_count * 2));
-    FM_LAUNCH(k_xchg_pull, grid, 256, 0, s, d_peer_masks, d_peer_ack_flags, d_data_flags, d_inbox, (uint32_t)xwords, (uint32_t)count_off,
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((warps + 3) / 4, (size_t)std::max(1, h->sm_count / 2)));
+    FM_LAUNCH(k_xchg_pull, grid, 128, 0, s, d_peer_masks, d_peer_ack_flags, d_data_flags, d_inbox, (uint32_t)xwords, (uint32_t)count_off,
               world, rank, (uint32_t)B, vocab, seq, d_counts_out, d_done_ctr);
     FM_CUDA(cudaGetLastError());
     return FMIDX_OK;

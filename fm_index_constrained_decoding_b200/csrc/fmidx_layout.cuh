@@ -50,6 +50,14 @@ struct FmDev {
     const uint32_t *text;        // optional resident text T (n entries) or nullptr
     const uint32_t *bwt;         // optional resident BWT as plain u32 symbols (n entries) or nullptr: the rows of a range are
                                  // CONTIGUOUS here, so the distinct symbols of a narrow / mid-sized range are one coalesced read
+    // unigram continuation table (resident layout): for the symbols c with the most occurrences, the distinct symbols of
+    // BWT[C[c], C[c+1]) as a bitmap over the SYMBOL axis -- the continuations of a one-token prefix are a property of the
+    // index (the reference precomputes the same thing for the EMPTY prefix: occurring_distinct, index.py:206), and the
+    // one-token prefixes of frequent tokens are exactly the ranges whose enumeration costs the most
+    const uint32_t *uni_sp;      // [uni_n] C[c], ascending
+    const uint32_t *uni_ep;      // [uni_n] C[c+1]
+    const uint32_t *uni_masks;   // [uni_n][uni_words] bit s of a row: symbol s occurs in the block
+    uint32_t uni_n, uni_words;
     uint64_t level_stride;       // uint4 per level = nblocks*8
     uint32_t n;                  // csa.size(): text length incl. the 0 sentinel
     uint32_t max_sym;

@@ -51,8 +51,8 @@ int fmidx_shard_create(fmidx_t *h, uint32_t world, uint32_t rank, size_t B, uint
                        fmidx_shard_t **out) {
     if (!h || !out) { fm_set_error("null argument"); return FMIDX_EINVAL; }
     *out = nullptr;
-    if (world == 0 || world > 64 || rank >= world || B == 0 || B % world || vocab == 0 || n_sets == 0 || n_sets > 8) {
-        fm_set_error("shard_create: need 1 <= world <= 64, rank < world, B a positive multiple of world, 1 <= n_sets <= 8");
+    if (world == 0 || world > 64 || rank >= world || B == 0 || B % world || vocab == 0 || n_sets == 0 || n_sets > FMIDX_SLOTS) {
+        fm_set_error("shard_create: need 1 <= world <= 64, rank < world, B a positive multiple of world, 1 <= n_sets <= 16");
         return FMIDX_EINVAL;
     }
     FM_CUDA(cudaSetDevice(h->device));

@@ -172,6 +172,11 @@ class FMIndex:
         return tuple(int(x) for x in buf[:k.value])
 
     # ---- extras (not in the SWIG surface) ------------------------------------------------------------
+    def tune(self, **kw):
+        """Run-time tunables (fmidx_tune): scan_max, bytes_occ, unigram_table.  Results never depend on them."""
+        for k, v in kw.items():
+            N.check(N.lib().fmidx_tune(self._h, k.encode(), int(v)))
+
     def info(self):
         out = (C.c_uint64 * 8)()
         N.check(N.lib().fmidx_info(self._h, out))

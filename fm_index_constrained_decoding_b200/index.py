@@ -269,7 +269,7 @@ class FMIndex(_FMIndex):
 
     def query_batch(self, toks, offs, vocab, shift=SHIFT, ws_slot=0, out=None):
         """Ranges AND allowed-token bitmaps of B ragged prefixes in one call (fmidx_query_batch): returns
-        (sp, ep, mask).  Batches issued on different CUDA streams must use different ws_slot values (0..7)."""
+        (sp, ep, mask).  Batches issued on different CUDA streams must use different ws_slot values (0..15)."""
         torch = _torch()
         B = offs.numel() - 1
         words = (vocab + 31) // 32

@@ -19,9 +19,19 @@ from .index import FMIndex, SHIFT, ragged
 
 
 class IndexBasedLogitsProcessor:
+    """Hard-mask processor (document_constrained_generation_vllm.py:7-137 / _seq.py:6-123).
+
+    CUDA `input_ids` tensors take the DEVICE path: no `.tolist()`, no ragged host lists, no host synchronisation.  The
+    per-beam state (sp, ep) = get_range(force + history) is kept on the GPU between calls; a call whose histories are one
+    token longer than the previous call's continues it with ONE backward-search step per beam (`fmidx_decode_step`: rows
+    gathered by `beam_idx`, or by parents matched on the device when it is not given), where the reference re-searches
+    every history twice (vllm.py:91-92).  Otherwise the parent states come from one batched search of the histories minus
+    their last token, and the same step kernel finishes -- so both ways share every decision rule.  `reset()` forgets
+    the state."""
+
     def __init__(self, index: FMIndex, num_beams: int, pad_token_id: int = 0, eos_token_id: int = 2,
                  force_decoding_from=None, stop_at_count: int = 0, always_allow_eos: bool = False,
-                 forced_bos_token_id=None, skip_first_token: bool = False):
+                 forced_bos_token_id=None, skip_first_token: bool = False, incremental: bool = True):
         self.index = index
         self._num_beams = num_beams
         self.pad_token_id = pad_token_id
@@ -31,26 +41,94 @@ class IndexBasedLogitsProcessor:
         self.always_allow_eos = always_allow_eos
         self.forced_bos_token_id = forced_bos_token_id
         self.skip_first_token = skip_first_token
+        self.incremental = incremental
         self.BOOST = 0.0
+        self._state = None       # (sp, ep, history tensor [R, L]) of the previous device-path call
+        self.steps_incremental = 0
+        self.steps_searched = 0
 
     def clone(self):
         return IndexBasedLogitsProcessor(
             index=self.index, num_beams=self._num_beams, pad_token_id=self.pad_token_id, eos_token_id=self.eos_token_id,
             force_decoding_from=self.force_decoding_from, stop_at_count=self.stop_at_count,
             always_allow_eos=self.always_allow_eos, forced_bos_token_id=self.forced_bos_token_id,
-            skip_first_token=self.skip_first_token)
+            skip_first_token=self.skip_first_token, incremental=self.incremental)
+
+    def reset(self):
+        self._state = None
 
     # ---- call styles ------------------------------------------------------------------------------
-    def __call__(self, input_ids, scores):
+    def __call__(self, input_ids, scores, beam_idx=None):
         if torch.is_tensor(input_ids) and input_ids.dim() == 2:
             hist = input_ids[:, 1:] if self.skip_first_token else input_ids
+            if hist.is_cuda and scores.is_cuda and isinstance(self.index, FMIndex):
+                return self.process_device(hist, scores, beam_idx)
             return self.process_batch(hist.tolist(), scores)
         single = scores.dim() == 1
         hist = list(input_ids)
         out = self.process_batch([hist], scores.unsqueeze(0) if single else scores)
         return out.squeeze(0) if single else out
 
-    # ---- the step ----------------------------------------------------------------------------------
+    # ---- the step, device-resident -------------------------------------------------------------------------------------
+    def process_device(self, hist, scores, beam_idx=None):
+        """hist: int64 CUDA tensor [R, L] (equal-length histories); scores [R, V] CUDA; beam_idx: optional int tensor [R],
+        row r of this call continues row beam_idx[r] of the previous call."""
+        import ctypes as C
+        from . import _native as N
+        ix = self.index
+        R, V = scores.shape
+        dev = scores.device
+        scores = scores.contiguous()
+        eos, pad = self.eos_token_id, self.pad_token_id
+        allow = eos if self.always_allow_eos else -1
+        L = hist.shape[1]
+        if self.forced_bos_token_id is not None:
+            if L == 0:  # only the forced BOS token (vllm.py:55-58); always_allow_eos is NOT applied on this early return
+                z = torch.zeros(R, dtype=torch.int64, device=dev)
+                ovr = torch.full((R,), int(self.forced_bos_token_id), dtype=torch.int32, device=dev)
+                self._state = None
+                return ix.mask_logits(z, z, scores, out=torch.empty_like(scores), override_tok=ovr, always_allow=-1)
+            hist = hist[:, 1:]
+            L -= 1
+        hist = hist.to(torch.int64)
+        force = list(self.force_decoding_from) if self.force_decoding_from is not None else []
+        if L == 0:
+            # S = occurring_distinct = distinct symbols of rows [0, len(index)) (vllm.py:62-66, index.py:206)
+            sp = torch.zeros(R, dtype=torch.int64, device=dev)
+            ep = torch.full((R,), len(ix), dtype=torch.int64, device=dev)
+            self._state = None
+            return ix.mask_logits(sp, ep, scores, out=torch.empty_like(scores), always_allow=allow)
+        st = self._state
+        parent = None
+        if self.incremental and st is not None and st[2].shape == (R, L - 1) and st[2].device == dev:
+            psp, pep = st[0], st[1]
+            if beam_idx is not None:
+                parent = beam_idx.to(device=dev, dtype=torch.int32).contiguous()
+            elif L > 1:  # match every row's history[:-1] against the previous call's rows, on the device
+                eq = (hist[:, None, :-1] == st[2][None, :, :]).all(-1)
+                parent = eq.to(torch.int8).argmax(1).to(torch.int32).contiguous()
+            self.steps_incremental += 1
+        else:
+            # parent states by ONE batched search of force + history[:-1] (device-side ragged layout, no host lists)
+            head = hist[:, :-1]
+            if force:
+                head = torch.cat([torch.tensor(force, dtype=torch.int64, device=dev).expand(R, -1), head], 1)
+            Lh = head.shape[1]
+            offs = torch.arange(R + 1, dtype=torch.int64, device=dev) * Lh
+            psp, pep = ix.get_range_batch(head.to(torch.int32).contiguous().view(-1), offs)
+            self.steps_searched += 1
+        buf = torch.empty((4, R), dtype=torch.int64, device=dev)
+        override = torch.empty(R, dtype=torch.int32, device=dev)
+        last = hist[:, -1]
+        N.check(N.lib().fmidx_decode_step(
+            ix._h, C.c_void_p(last.data_ptr()), last.stride(0), C.c_void_p(parent.data_ptr()) if parent is not None else None,
+            C.c_void_p(psp.data_ptr()), C.c_void_p(pep.data_ptr()), C.c_void_p(buf[0].data_ptr()), C.c_void_p(buf[1].data_ptr()), R,
+            SHIFT, eos, pad, int(self.stop_at_count), C.c_void_p(buf[2].data_ptr()), C.c_void_p(buf[3].data_ptr()),
+            C.c_void_p(override.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        self._state = (buf[0], buf[1], hist.clone()) if self.incremental else None
+        return ix.mask_logits(buf[2], buf[3], scores, out=torch.empty_like(scores), override_tok=override, always_allow=allow)
+
+    # ---- the step, from host token lists ---------------------------------------------------------------------------------
     def process_batch(self, histories, scores):
         """histories: B token lists (all of the same length in the reference's use); scores [B, V]."""
         ix = self.index

@@ -106,7 +106,9 @@ def read_csa_wt_int(path):
     size, sigma = r.u64(), r.u64()
     tree_bits, tree = r.bit_vector()
     rank_blocks = r.int_vector64()
-    if rank_blocks.size != ((tree_bits >> 9) + 1) * 2:
+    # sdsl sizes the block array from the bit vector's CAPACITY (bits rounded up to whole 64-bit words) [sdsl, recalled]
+    cap_bits = ((tree_bits + 63) >> 6) << 6
+    if rank_blocks.size != ((cap_bits >> 9) + 1) * 2:
         raise SdslFormatError("rank_support_v has %d words for %d bits" % (rank_blocks.size, tree_bits))
     ones = int(np.unpackbits(tree.view(np.uint8)).sum()) if tree_bits < (1 << 33) else None
     r.select_mcl(ones)

@@ -14,6 +14,7 @@ requests) becomes ONE batched device call (`get_range_many` -> fmidx_search_host
 `create_app` accepts any engine with the index.py method surface.
 """
 import asyncio
+import concurrent.futures
 import time
 from typing import List, Optional, Tuple
 
@@ -72,8 +73,12 @@ class DistinctResponse(BaseModel):
 class RangeCoalescer:
     """Collects concurrent prefix lookups and resolves them with one batched engine call."""
 
-    def __init__(self, engine, max_batch=4096, window_ms=1.0):
+    def __init__(self, engine, max_batch=4096, window_ms=1.0, executor=None):
         self.engine = engine
+        # include/fmidx.h: a handle is used by ONE host thread at a time.  Every engine call of the service -- coalesced
+        # batches, locate, extract, distinct lists -- runs on this single worker thread, so two batches can never be
+        # inside the library at once (ctypes releases the GIL) and share its stream and scratch buffers.
+        self.executor = executor or concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix="fmidx")
         self.max_batch = max_batch
         self.window = window_ms / 1000.0
         self.pending = []  # (sequence, want_continuations, future)
@@ -103,7 +108,7 @@ class RangeCoalescer:
 
     async def _run(self, loop, batch):
         try:
-            results = await loop.run_in_executor(None, self._resolve, batch)
+            results = await loop.run_in_executor(self.executor, self._resolve, batch)
             for (_, _, fut), res in zip(batch, results):
                 if not fut.done():
                     fut.set_result(res)
@@ -146,8 +151,12 @@ def create_app(index, max_batch=4096, window_ms=1.0):
         try:
             (lo, hi), _ = await co.lookup(request.sequence)
             rows = range(lo, hi if not request.limit else min(hi, lo + request.limit))
-            docs = [index.get_doc_index_from_row(r) for r in rows] if not hasattr(index, "doc_indices_of_rows") \
-                else index.doc_indices_of_rows(lo, rows.stop)
+
+            def locate():
+                if hasattr(index, "doc_indices_of_rows"):
+                    return index.doc_indices_of_rows(lo, rows.stop)
+                return [index.get_doc_index_from_row(r) for r in rows]
+            docs = await asyncio.get_running_loop().run_in_executor(co.executor, locate)
             return SearchResponse(count=hi - lo, doc_indices=docs, took_ms=ms(t0))
         except Exception as e:  # noqa: BLE001
             raise HTTPException(status_code=500, detail=str(e))
@@ -179,7 +188,7 @@ def create_app(index, max_batch=4096, window_ms=1.0):
         t0 = time.time()
         try:
             loop = asyncio.get_running_loop()
-            out = await loop.run_in_executor(None, index.get_distinct_count_multi, request.lows, request.highs)
+            out = await loop.run_in_executor(co.executor, index.get_distinct_count_multi, request.lows, request.highs)
             return DistinctResponse(distinct_list=out, took_ms=ms(t0))
         except Exception as e:  # noqa: BLE001
             raise HTTPException(status_code=500, detail=str(e))
@@ -198,7 +207,7 @@ def create_app(index, max_batch=4096, window_ms=1.0):
         if doc_index < 0 or doc_index >= index.n_docs:
             raise HTTPException(status_code=404, detail="Document not found")
         try:
-            doc = index.get_doc(doc_index)
+            doc = await asyncio.get_running_loop().run_in_executor(co.executor, index.get_doc, doc_index)
             return {"doc_index": doc_index, "tokens": doc, "length": len(doc)}
         except Exception as e:  # noqa: BLE001
             raise HTTPException(status_code=500, detail=str(e))

@@ -52,6 +52,12 @@ void fmidx_free(fmidx_t *h);
  * (reference default 64); keep_text keeps the symbol text resident so extract is a gather. */
 int fmidx_set_options(fmidx_t *h, uint32_t sa_dens, uint32_t isa_dens, int keep_text);
 
+/* run-time tunables of a handle (defaults come from the environment when the handle is created): "scan_max" -- ranges of up
+ * to this many rows are read off the resident BWT instead of walking the matrix ($FMIDX_SCAN_MAX, 16384); "bytes_occ" -- CTAs
+ * per SM of the byte-level enumeration kernel ($FMIDX_BYTES_OCC, 5); "unigram_table" -- 1/0: use / ignore the unigram
+ * continuation table at query time ($FMIDX_UNIGRAM_TABLE, 1).  Results never depend on them. */
+int fmidx_tune(fmidx_t *h, const char *key, int64_t value);
+
 /* ---- build: FMIndex::initialize (fm_index.cpp:33-41), initialize_from_file (:43-48) ------- */
 int fmidx_initialize(fmidx_t *h, const uint64_t *data, size_t n);
 int fmidx_initialize_from_file(fmidx_t *h, const char *path, int width);
@@ -93,6 +99,18 @@ int fmidx_search_batch(fmidx_t *h, const int32_t *d_toks, const int64_t *d_offs,
  * beam per generated token instead of re-searching the history). Inclusive highs in. */
 int fmidx_step_batch(fmidx_t *h, const uint64_t *d_symbols, const uint64_t *d_lows, const uint64_t *d_highs,
                      size_t B, uint64_t *d_sp, uint64_t *d_ep, void *stream);
+/* Incremental constrained decoding: the reference re-searches the whole history twice per beam per step
+ * (document_constrained_generation_vllm.py:91-92); here the per-beam state (sp, ep) = get_range(force + history) stays on
+ * the device and one step costs ONE backward_search_step per beam.  Row r continues the state of row d_parent[r] (NULL:
+ * r itself) with the token d_last_tok[r * tok_stride] (the last column of input_ids, read on the device); the new state goes
+ * to d_state_*_out (double-buffered).  The kernel also emits what fmidx_mask_logits needs for this step, decided row by row
+ * like vllm.py:78-118: d_query_sp/ep ((0,0) for rows whose last token is eos / pad) and d_override_tok ({eos} when
+ * stop_at_count > 0 and the PARENT state is at most stop_at_count wide -- that width is count(history[:-1]) -- else {pad}
+ * for finished rows, else -1).  No host synchronisation, no host-side token lists. */
+int fmidx_decode_step(fmidx_t *h, const int64_t *d_last_tok, int64_t tok_stride, const int32_t *d_parent, const uint64_t *d_state_sp_in,
+                      const uint64_t *d_state_ep_in, uint64_t *d_state_sp_out, uint64_t *d_state_ep_out, size_t B, int64_t shift,
+                      int64_t eos, int64_t pad, int64_t stop_at_count, uint64_t *d_query_sp, uint64_t *d_query_ep,
+                      int32_t *d_override_tok, void *stream);
 /* index.FMIndex.get_distinct_count_multi (index.py:161-174) as bitmaps: for each half-open
  * range, bit v of row b of d_mask ([B, ceil(vocab/32)] u32) is set iff symbol v+shift occurs in
  * BWT[sp,ep) and 0 <= v < vocab (the sentinel and symbols < shift are dropped like index.py's
@@ -103,7 +121,7 @@ int fmidx_distinct_mask_batch(fmidx_t *h, const uint64_t *d_sp, const uint64_t *
 /* One decoding step's lookups for B beams in ONE call: fmidx_search_batch followed by
  * fmidx_distinct_mask_batch on the same stream (what index.py:93-131 `get_range` + index.py:146-159
  * `get_distinct_count` do per beam in document_constrained_generation_vllm.py:72-137), d_sp/d_ep and d_mask as
- * in those two calls (d_mask NULL or vocab 0: ranges only).  ws_slot (0..7) selects the scratch workspace the
+ * in those two calls (d_mask NULL or vocab 0: ranges only).  ws_slot (0..15) selects the scratch workspace the
  * enumeration uses: calls that may run concurrently on DIFFERENT streams must use different slots, calls that
  * share a slot must be stream-ordered.  The slots are the ones fmidx_query_submit uses: do not mix the two on one
  * slot number. */
@@ -116,7 +134,7 @@ int fmidx_distinct_mask_batch_occ(fmidx_t *h, const uint64_t *d_sp, const uint64
 /* ---- document-sharded step; no reference counterpart: the reference's only parallelism is one
  * std::async per range (fm_index.cpp:146-166) --------------------------------------------------------------------
  * One process per GPU, each holding the index of its own document shard; the B prefixes of a step are replicated.
- * A shard context owns n_sets (<= 8) independent buffer sets in peer-visible memory (CUDA IPC): [B][ceil(vocab/32)]
+ * A shard context owns n_sets (<= 16) independent buffer sets in peer-visible memory (CUDA IPC): [B][ceil(vocab/32)]
  * bitmaps, an inbox with one slot per shard (slice-occupancy words + occurrence counts), data / ack flags.  Set-up: every
  * rank creates its context, exports the 64-byte handles of its buffers (kind 0 = bitmaps of a set, 1 = inbox of a set,
  * 2 = the flag block of all sets), the host language exchanges them (torch.distributed all_gather_object), every rank
@@ -188,7 +206,7 @@ int fmidx_query_host(fmidx_t *h, const int32_t *toks, const int64_t *offs, size_
  * receives the ranges and n_distinct[b] = number of distinct next tokens of prefix b */
 int fmidx_query_host_summary(fmidx_t *h, const int32_t *toks, const int64_t *offs, size_t B, int64_t shift,
                              uint32_t vocab, uint64_t *sp, uint64_t *ep, uint32_t *n_distinct);
-/* pipelined form of fmidx_query_host_summary: up to 8 batches in flight, each in its own slot (own stream,
+/* pipelined form of fmidx_query_host_summary: up to 16 batches in flight, each in its own slot (own stream,
  * buffers and workspace).  submit enqueues H2D copies, kernels and D2H copies and returns; wait blocks until the
  * slot's host buffers (which should be pinned) hold the results.  n_distinct may be NULL (ranges only). */
 int fmidx_query_submit(fmidx_t *h, int slot, const int32_t *toks, const int64_t *offs, size_t B, int64_t shift,

@@ -363,6 +363,52 @@ void *fmo_build_from_sa(const u32 *text_with_sentinel, const u32 *sa, u64 n) {
     return f;
 }
 
+/* Independent O(n) proof that `sa` is THE suffix array of `text` (n symbols, unique smallest sentinel 0 at n-1), after
+ * Burkhardt & Karkkainen's checker: (1) sa is a permutation of 0..n-1; (2) adjacent suffixes are in order, i.e.
+ * T[sa[i]] < T[sa[i+1]], or the first symbols are equal and ISA[sa[i]+1] < ISA[sa[i+1]+1].  Used by bench.py before it
+ * hands a suffix array computed elsewhere (the GPU builder) to fmo_build_from_sa, so that the big-corpus parity check
+ * does not rest on the product.  Returns 0 when sa is correct, a positive code otherwise. */
+typedef struct { const u32 *t; const u32 *sa; const u32 *isa; u64 lo, hi, n; int bad; } verify_job_t;
+static void *verify_worker(void *arg) {
+    verify_job_t *j = (verify_job_t *)arg;
+    const u32 *t = j->t, *sa = j->sa, *isa = j->isa;
+    for (u64 i = j->lo; i < j->hi; i++) {
+        u32 a = sa[i], b = sa[i + 1];
+        if (t[a] > t[b]) { j->bad = 3; return NULL; }
+        if (t[a] == t[b]) {
+            /* equal first symbols: neither is the (unique) sentinel, so a+1 and b+1 exist */
+            if ((u64)a + 1 >= j->n || (u64)b + 1 >= j->n || isa[a + 1] >= isa[b + 1]) { j->bad = 4; return NULL; }
+        }
+    }
+    return NULL;
+}
+int fmo_verify_sa(const u32 *text, const u32 *sa, u64 n, int nthreads) {
+    if (n == 0 || text[n - 1] != 0 || sa[0] != (u32)(n - 1)) return 1;
+    u32 *isa = (u32 *)malloc((size_t)n * sizeof(u32));
+    memset(isa, 0xFF, (size_t)n * sizeof(u32));
+    for (u64 i = 0; i < n; i++) {
+        if (sa[i] >= n || isa[sa[i]] != 0xFFFFFFFFu) { free(isa); return 2; }  /* not a permutation */
+        isa[sa[i]] = (u32)i;
+    }
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 64) nthreads = 64;
+    pthread_t th[64];
+    verify_job_t jobs[64];
+    const u64 pairs = n - 1;
+    for (int k = 0; k < nthreads; k++) {
+        verify_job_t jb = {text, sa, isa, pairs * (u64)k / (u64)nthreads, pairs * (u64)(k + 1) / (u64)nthreads, n, 0};
+        jobs[k] = jb;
+        pthread_create(&th[k], NULL, verify_worker, &jobs[k]);
+    }
+    int bad = 0;
+    for (int k = 0; k < nthreads; k++) {
+        pthread_join(th[k], NULL);
+        if (jobs[k].bad && !bad) bad = jobs[k].bad;
+    }
+    free(isa);
+    return bad;
+}
+
 /* Suffix array of data||0 (for cross-checking the device builder). out has n_data+1 slots. */
 int fmo_suffix_array(const u64 *data, u64 n_data, u32 *out) {
     u64 n = n_data + 1;
@@ -590,7 +636,8 @@ static void w_bit_vector(FILE *f, const u64 *words, u64 nbits) {
     fwrite(words, 8, (size_t)((nbits + 63) >> 6), f);
 }
 static void w_rank_v(FILE *f, const u64 *bv, u64 nbits) { /* rank_support_v::m_basic_block : int_vector<64> */
-    u64 nsb = (nbits >> 9) + 1, nwords = (nbits + 63) >> 6, abs = 0;
+    /* sized from the bit vector's capacity (whole 64-bit words) [sdsl, recalled]: ((capacity >> 9) + 1) << 1 words */
+    u64 nwords = (nbits + 63) >> 6, nsb = ((nwords << 6) >> 9) + 1, abs = 0;
     w_u64(f, nsb * 2 * 64);
     for (u64 sb = 0; sb < nsb; sb++) {
         u64 rel = 0, second = 0;

@@ -38,6 +38,8 @@ def lib():
         L.fmo_build_from_sa.argtypes = [p, p, u64]
         L.fmo_suffix_array.restype = C.c_int
         L.fmo_suffix_array.argtypes = [p, u64, p]
+        L.fmo_verify_sa.restype = C.c_int
+        L.fmo_verify_sa.argtypes = [p, p, u64, C.c_int]
         L.fmo_free.argtypes = [p]
         L.fmo_size.restype = u64
         L.fmo_size.argtypes = [p]
@@ -82,9 +84,16 @@ class NativeOracle:
             raise ValueError("oracle: text contains a zero symbol / symbol too large")
         self._h = h
 
-    def initialize_from_sa(self, text_with_sentinel_u32, sa_u32):
+    def initialize_from_sa(self, text_with_sentinel_u32, sa_u32, verify=True, nthreads=8):
+        """Build from a suffix array computed elsewhere (bench.py: the GPU builder's).  verify=True first PROVES, with
+        oracle-side code only, that it is the suffix array of the text (fmo_verify_sa), so nothing downstream rests on
+        the producer of the array."""
         t = np.ascontiguousarray(text_with_sentinel_u32, dtype=np.uint32)
         s = np.ascontiguousarray(sa_u32, dtype=np.uint32)
+        if verify:
+            rc = lib().fmo_verify_sa(_ptr(t), _ptr(s), t.size, nthreads)
+            if rc != 0:
+                raise ValueError("the supplied suffix array is wrong (fmo_verify_sa code %d)" % rc)
         self._h = lib().fmo_build_from_sa(_ptr(t), _ptr(s), t.size)
 
     def size(self):

@@ -219,6 +219,47 @@ def processor_vectors(mods, ix, docs):
     return out
 
 
+def beam_search_vectors(mods, ix, docs):
+    """A 32-step beam search (2 prompts x 4 beams) driven through the reference's seq processor, with beam reordering:
+    every new row continues a pseudo-randomly chosen parent row of its prompt with a token taken from that parent's
+    allowed set (so beams are duplicated and dropped like in a real search; rows that drew EOS continue with PAD).
+    Stored per step: parents, the new tokens and the digest of the reference's output rows."""
+    seq_cls = mods["document_constrained_generation_seq"].IndexBasedLogitsProcessor
+    force = docs[3][10:11]
+    out = []
+    for ci, cfg in enumerate([dict(always_allow_eos=True), dict(always_allow_eos=True, stop_at_count=1),
+                              dict(always_allow_eos=True, force_decoding_from=force), dict()]):
+        nb, nprompt = 4, 2
+        R = nb * nprompt
+        proc = seq_cls(index=ix, num_beams=nb, pad_token_id=G.PAD, eos_token_id=G.EOS, **cfg)
+        r = G.lcg(6000 + ci)
+        ids = [[2] for _ in range(R)]
+        steps = []
+        for step in range(32):
+            s = G.make_scores(R, torch.float32, 6000 + 100 * ci + step)
+            res = proc(torch.tensor(ids, dtype=torch.long), s)
+            allowed = [torch.nonzero(~torch.isneginf(res[i]) & ~torch.isnan(res[i])).flatten().tolist() for i in range(R)]
+            parents, toks = [], []
+            for row in range(R):
+                base = (row // nb) * nb
+                p = base + r(nb)
+                last = ids[p][-1]
+                if last in (G.EOS, G.PAD) and len(ids[p]) > 1:
+                    t = G.PAD
+                elif allowed[p]:
+                    live = [a for a in allowed[p] if a != G.EOS]
+                    cand = live if live and r(16) else allowed[p]   # mostly keep the beam alive
+                    t = cand[r(len(cand))]
+                else:
+                    t = G.PAD
+                parents.append(p)
+                toks.append(t)
+            steps.append({"digest": G.row_digest(res), "n_allowed": [len(a) for a in allowed], "parents": parents, "tokens": toks})
+            ids = [ids[p] + [t] for p, t in zip(parents, toks)]
+        out.append({"cfg": cfg, "num_beams": nb, "rows": R, "steps": steps})
+    return out
+
+
 def generate():
     mods = import_reference()
     cs = corpora()
@@ -232,6 +273,7 @@ def generate():
             res["indexes"].append(v)
             keep[name] = ix
     res["processors"] = processor_vectors(mods, keep["random_4000"], cs["random_4000"])
+    res["beam_search"] = beam_search_vectors(mods, keep["random_4000"], cs["random_4000"])
     res["corpora"] = {"unicorn_paragraph": cs["unicorn_paragraph"]}  # token ids of the stand-in tokenizer (no text)
     return res
 

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 sys.path.insert(0, os.path.join(HERE, "golden"))
 import refgolden_common as G  # noqa: E402
-from test_reference_python import GOLD, DT, check_index_vectors, corpus_docs, hard_mask_rows  # noqa: E402
+from test_reference_python import GOLD, DT, check_index_vectors, corpus_docs, hard_mask_rows, replay_beam_search  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -103,3 +103,25 @@ def test_reference_index_py_unmodified_over_the_gpu_shim(cuda):
         sys.path.remove("/root/reference")
         for m in ("cpp_modules", "cpp_modules.fm_index", "index"):
             sys.modules.pop(m, None)
+
+
+@pytest.mark.parametrize("mode", ["beam_idx", "matched_parents", "searched"])
+def test_incremental_decode_replays_the_reference_beam_search(cuda, index4000, mode):
+    """32 steps x 8 rows with beam reordering, device-resident state: one backward-search step per beam per token
+    (`fmidx_decode_step`), parents given (beam_idx), matched on the device, or no state at all (every step searched) --
+    every step's rows equal the reference seq processor's, bit for bit."""
+    from fm_index_constrained_decoding_b200.processors import IndexBasedLogitsProcessor
+    for case in GOLD["beam_search"]:
+        cfg = dict(case["cfg"])
+        proc = IndexBasedLogitsProcessor(index4000, num_beams=case["num_beams"], pad_token_id=G.PAD, eos_token_id=G.EOS,
+                                         skip_first_token=True, incremental=(mode != "searched"), **cfg)
+        prev_parents = None
+        for step, ids, scores, st in replay_beam_search(case):
+            bi = torch.tensor(prev_parents, dtype=torch.int32).cuda() if (mode == "beam_idx" and prev_parents is not None) else None
+            got = proc(torch.tensor(ids, dtype=torch.long).cuda(), scores.cuda(), beam_idx=bi)
+            assert G.row_digest(got) == st["digest"], (mode, case["cfg"], step)
+            prev_parents = st["parents"]
+        if mode == "searched":
+            assert proc.steps_incremental == 0
+        else:
+            assert proc.steps_incremental == 30 and proc.steps_searched == 1  # step 0 has no history, step 1 searches, 2..31 step

@@ -138,3 +138,24 @@ def test_oracle_soft_boost_restatement_matches_reference_python(variant):
                                    cfg.get("always_allow_eos", False), cfg.get("force_decoding_from"), cfg.get("forced_bos_token_id"),
                                    2.0, cfg.get("min_new_tokens", 5))
         assert G.row_digest(got) == v["digest"], (variant, cfg, v["dtype"])
+
+
+def replay_beam_search(case):
+    """Yields (step, input_ids rows incl. the decoder-start column, scores, parents, expected digest) of a stored search."""
+    ci = GOLD["beam_search"].index(case)
+    R = case["rows"]
+    ids = [[2] for _ in range(R)]
+    for step, st in enumerate(case["steps"]):
+        yield step, ids, G.make_scores(R, torch.float32, 6000 + 100 * ci + step), st
+        ids = [ids[p] + [t] for p, t in zip(st["parents"], st["tokens"])]
+
+
+def test_oracle_hard_mask_restatement_replays_the_reference_beam_search():
+    from oracle.oracle import hard_mask_reference
+    o = _oracle_index()
+    for case in GOLD["beam_search"]:
+        cfg = case["cfg"]
+        for step, ids, scores, st in replay_beam_search(case):
+            got = hard_mask_reference(o, [r[1:] for r in ids], scores, case["num_beams"], G.EOS, G.PAD, cfg.get("stop_at_count", 0),
+                                      cfg.get("always_allow_eos", False), cfg.get("force_decoding_from"))
+            assert G.row_digest(got) == st["digest"], (cfg, step)
