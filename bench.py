@@ -171,6 +171,7 @@ class BlockTimer:
         Returns (median ms per `steps` steps, number of K-step blocks timed, super-block times)."""
         stream = torch.cuda.current_stream()
         block(0, warmup_steps)
+        block(0, 2 * steps)  # untimed: first use of every buffer set / stream / peer mapping
         self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -401,6 +402,29 @@ class LocalEngine:
         self.h2d = int(np.mean([q.numel() * 4 + offs.numel() * 8 for q, offs in self.hq]))
         self.d2h = B * (8 + 8 + 4)
 
+    def setup_e2e_graph(self):
+        """The captured form: slot i's pinned staging buffer holds prefix batch i (NSLOT == number of batches), exactly like
+        the eager form rotates the same pinned batches; one cudaGraphLaunch per step does H2D + kernels + D2H."""
+        from fm_index_constrained_decoding_b200.index import GraphQuerySlots
+        assert len(self.qsets) <= 8
+        hq = [(q.cpu().numpy(), offs.cpu().numpy()) for q, offs in self.qsets]
+        self.g_maxtok = max(q.size for q, _ in hq)
+        self.gs = GraphQuerySlots(self.ix, len(hq), self.B, self.g_maxtok, VOCAB, first_slot=8)
+        for i, (q, offs) in enumerate(hq):
+            self.gs.offs[i][:] = offs
+            self.gs.toks[i][:q.size] = q
+        self.g_h2d = (self.B + 1) * 8 + self.g_maxtok * 4
+        self._gl, self._gw, self._gh = self.gs._launch, self.gs._wait, self.ix._h
+
+    def e2e_graph_step(self, k):
+        slot = 8 + k % self.gs.n
+        if self._gw(self._gh, slot) != 0 or self._gl(self._gh, slot) != 0:
+            self.N.check(-1)
+
+    def e2e_graph_drain(self):
+        for i in range(self.gs.n):
+            self.gs.wait(i)
+
     def e2e_step(self, k):
         slot = k % self.NSLOT
         if self.L.fmidx_query_wait(self.ix._h, slot) != 0 or self.L.fmidx_query_submit(*self.submit_args[(k % len(self.hq), slot)]) != 0:
@@ -419,20 +443,21 @@ BYTE_PROBE_B = 32 + 32 * 8.5     # header-word sector + E[payload sectors below 
 STEP_B = 2 * (3 * NIB_PROBE_B + BYTE_PROBE_B)  # two boundaries; = 1,086 B (SURVEY 8(d) quotes 1,088 B for the reference layout)
 
 
-def algorithmic_bytes(ix, qsets, device, B, info):
+def algorithmic_bytes(ix, qsets, device, B, info, table=True):
     """Per step, from the actual results: what K1 and K2 must read and write at the granularity of DRAM sectors.
     K1  probe steps (range still > 16 rows; resident layout) x STEP_B; the first token costs two C[] sectors; the tail
         of a prefix costs ceil(4w/32) SA sectors, w x ceil(4 rem/32) text sectors and one ISA sector per survivor; plus
         the tokens and the result.
     K2  the mask row once (16,032 B); ranges of <= SCAN_MAX rows: their 4 B/row of the resident BWT; wider ranges (tree
         walk): 2 x 128 B per visited nibble node, and per visited byte-level node its rows' payload bytes when it is
-        <= 512 rows wide, else two 1,024-B header slices + 512 B of partial cells."""
+        <= 512 rows wide, else two 1,024-B header slices + 512 B of partial cells; a one-token prefix of a frequent token
+        (its range is the token's whole block): one 16,032-B row of the unigram continuation table instead of a walk."""
     from fm_index_constrained_decoding_b200 import _native
     L = _native.lib()
     resident = bool(info["keep_text"]) and info["sa_dens"] == 1
     sptr = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     tot = {"k1": 0.0, "k2": 0.0, "search_steps": 0.0, "probe_steps": 0.0, "distinct": 0.0, "scan_rows": 0.0, "tree_prefixes": 0.0,
-           "byte_nodes": 0.0}
+           "byte_nodes": 0.0, "table_rows": 0.0}
     sp = torch.empty(B, dtype=torch.int64, device=device)
     ep = torch.empty(B, dtype=torch.int64, device=device)
     for q, offs in qsets:
@@ -471,7 +496,14 @@ def algorithmic_bytes(ix, qsets, device, B, info):
         scan = (w <= SCAN_MAX) if resident else torch.zeros_like(w, dtype=torch.bool)
         k2 = B * MASK_BYTES + float((torch.ceil(w[scan] * 4 / 32) * 32).sum())
         tot["scan_rows"] += float(w[scan].sum())
-        heavy = torch.nonzero(~scan & (w > 0)).flatten()
+        heavy_m = ~scan & (w > 0)
+        if resident and table:
+            # one-token prefixes of frequent tokens: the range is the token's whole block -> one row of the unigram table
+            hit = heavy_m & (lens == 1)
+            k2 += float(hit.sum()) * MASK_BYTES
+            tot["table_rows"] += float(hit.sum())
+            heavy_m = heavy_m & ~hit
+        heavy = torch.nonzero(heavy_m).flatten()
         tot["tree_prefixes"] += heavy.numel()
         for a in range(0, heavy.numel(), 128):
             hb = heavy[a:a + 128]
@@ -563,7 +595,7 @@ def run_single(args, device, local):
     sampler.start()
     block_ms, reps, _ = timer.run(eng.block, args.steps, args.warmup)
     clocks = sampler.stop()
-    launches_per_block = (L.fmidx_launch_count() - launches0) / (reps + 4 + args.warmup / args.steps)
+    launches_per_block = (L.fmidx_launch_count() - launches0) / (reps + 6 + args.warmup / args.steps)
     ms_per_step = block_ms / args.steps
     value = B * args.steps / (block_ms * 1e-3)
     log("value %.1f M q/s (%.4f ms/step, %d blocks of %d steps)" % (value / 1e6, ms_per_step, reps, args.steps))
@@ -589,17 +621,18 @@ def run_single(args, device, local):
             "time_source": "the timed (overlapped) region: median K-step block / K",
             "per_unit": "K1: %.0f B per probe step (2 boundaries x (3 nibble probes of 32-B header sector + 1.49 plane sectors, 1 byte-level "
                         "probe of 32-B header sector + 8.5 payload sectors)); tail of a prefix: SA/text/ISA sectors; K2: 16,032 B mask row + "
-                        "4 B per row of ranges <= %d rows (resident BWT) + tree walk of wider ranges (2 x 128 B per nibble node, payload bytes "
-                        "or 2,560 B per byte-level node)" % (STEP_B, SCAN_MAX),
+                        "4 B per row of ranges <= %d rows (resident BWT) + 16,032 B table row per frequent one-token prefix + tree walk of the other "
+                        "wide ranges (2 x 128 B per nibble node, payload bytes or 2,560 B per byte-level node)" % (STEP_B, SCAN_MAX),
             "per_kernel": {"k_search": {"algorithmic_bytes": ab["k1"], "serial_ms": t_search, "GBps_serial": ab["k1"] / (t_search * 1e-3) / 1e9,
                                         "traffic": traffic_per.get("k_search") if traffic_per else None},
                            "k_mask": {"algorithmic_bytes": ab["k2"], "serial_ms": t_mask, "GBps_serial": ab["k2"] / (t_mask * 1e-3) / 1e9,
                                       "traffic": sum(v for k, v in traffic_per.items() if k != "k_search") if traffic_per else None}},
             "other_kernel_ms": {"k_search": t_search, "k_mask": t_mask},
-            "counts_per_step": {k: ab[k] for k in ("search_steps", "probe_steps", "scan_rows", "tree_prefixes", "byte_nodes")},
+            "counts_per_step": {k: ab[k] for k in ("search_steps", "probe_steps", "scan_rows", "table_rows", "tree_prefixes", "byte_nodes")},
             "reference_layout_bytes_per_step": 1088 * ab["search_steps"] + B * MASK_BYTES,
-            "note": "mask rows (65.7 MB per step, written once) dominate the bytes; the enumeration of the ~2% widest ranges dominates "
-                    "the time (issue-bound tree walk), which is why the fraction of the HBM roofline is what it is"}
+            "note": "the mask rows (65.7 MB per step, written once) dominate the bytes; the search's dependent-load chains (latency) and "
+                    "the walk of the few wide multi-token ranges (instruction issue) dominate the time, so the step sits at about half of "
+                    "the HBM roofline with 8 batches in flight"}
     roof["frac"] = roof["achieved"] / peak
     roof["frac_of_traffic"] = (traffic / (ms_per_step * 1e-3) / 1e9 / peak) if traffic else None
     try:
@@ -615,11 +648,19 @@ def run_single(args, device, local):
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ------------------------------------------------
     eng.setup_e2e()
     e2e_s, e2e_reps = host_blocks(eng.e2e_step, eng.e2e_drain, args.steps, args.warmup)
-    e2e = {"value": B * args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": eng.h2d, "d2h_bytes_per_step": eng.d2h,
-           "ms_per_step": 1e3 * e2e_s / args.steps, "blocks": e2e_reps,
-           "api": "fmidx_query_submit/fmidx_query_wait, %d batches in flight (pinned host prefixes in; ranges + distinct-token counts "
-                  "out, every step; the 16 KB masks stay in HBM where the logits kernel consumes them -- the CPU arm writes them to host "
-                  "memory)" % eng.NSLOT}
+    eng.setup_e2e_graph()
+    g_s, g_reps = host_blocks(eng.e2e_graph_step, eng.e2e_graph_drain, args.steps, args.warmup)
+    # parity of the captured path on the spot: slot 0 holds batch 0
+    gsp, gep, _ = ix.query_batch(qsets[0][0], qsets[0][1], VOCAB)
+    torch.cuda.synchronize()
+    g_ok = bool((torch.from_numpy(eng.gs.sp[0].astype(np.int64)) == gsp.cpu()).all() and (torch.from_numpy(eng.gs.ep[0].astype(np.int64)) == gep.cpu()).all())
+    e2e = {"value": B * args.steps / g_s, "unit": "queries/s", "h2d_bytes_per_step": eng.g_h2d, "d2h_bytes_per_step": eng.d2h,
+           "ms_per_step": 1e3 * g_s / args.steps, "blocks": g_reps, "matches_device_path": g_ok,
+           "api": "fmidx_query_graph_launch/fmidx_query_wait: one CUDA-graph launch per step = H2D of the step's prefixes from pinned host "
+                  "memory -> search -> enumeration -> popcount -> D2H of ranges + distinct-token counts into pinned host memory; %d steps in "
+                  "flight (the 16 KB masks stay in HBM where the logits kernel consumes them -- the CPU arm writes them to host memory)" % eng.gs.n,
+           "eager_api": {"value": B * args.steps / e2e_s, "ms_per_step": 1e3 * e2e_s / args.steps, "h2d_bytes_per_step": eng.h2d,
+                         "api": "fmidx_query_submit/fmidx_query_wait (ten driver calls per step), %d batches in flight" % eng.NSLOT}}
 
     # ---- CPU baseline + parity on the same corpus (the only place the oracle is used) ---------------------------------------
     cpu, o = None, None
@@ -865,7 +906,7 @@ def run_multi(args, device, local, rank, world, dist):
         sampler.start()
     block_ms, reps, _ = timer.run(eng.block, args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
-    launches_per_block = (L.fmidx_launch_count() - launches0) / (reps + 4 + args.warmup / args.steps)
+    launches_per_block = (L.fmidx_launch_count() - launches0) / (reps + 6 + args.warmup / args.steps)
     value = world * B * args.steps / (block_ms * 1e-3)
     eng.setup_e2e()
     e2e_s, e2e_reps = host_blocks(eng.e2e_step, eng.e2e_drain, args.steps, args.warmup, dist, device)
@@ -927,7 +968,7 @@ def run_multi(args, device, local, rank, world, dist):
                 stream.wait_event(e)
         l0 = L.fmidx_launch_count()
         bms, rps, _ = timer.run(block, args.steps, args.warmup)
-        lpb = (L.fmidx_launch_count() - l0) / (rps + 4 + args.warmup / args.steps)
+        lpb = (L.fmidx_launch_count() - l0) / (rps + 6 + args.warmup / args.steps)
         # e2e: host-buffer form
         hq = [(q.cpu().pin_memory(), offs.cpu().pin_memory()) for q, offs in qs]
         own = B // g_size

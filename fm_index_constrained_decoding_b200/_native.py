@@ -39,7 +39,7 @@ SIGNATURES = {
     "fmidx_shard_import": (C.c_int, [p, u32, C.c_int, u32, p]),
     "fmidx_shard_ready": (C.c_int, [p]),
     "fmidx_shard_step": (C.c_int, [p, u32, p, p, i64, p, p, p]),
-    "fmidx_shard_result": (C.c_int, [p, u32, C.POINTER(p), C.POINTER(p), C.POINTER(p)]),
+    "fmidx_shard_result": (C.c_int, [p, u32, C.c_int, C.POINTER(p), C.POINTER(p), C.POINTER(p)]),
     "fmidx_shard_submit": (C.c_int, [p, u32, p, p, i64, p, p, p, p]),
     "fmidx_shard_wait": (C.c_int, [p, u32]),
     "fmidx_shard_destroy": (None, [p]),
@@ -48,6 +48,7 @@ SIGNATURES = {
     "fmidx_ipc_close": (C.c_int, [p, p]),
     "fmidx_ipc_free": (C.c_int, [p, p]),
     "fmidx_mask_logits": (C.c_int, [p, p, p, sz, i64, u32, p, p, C.c_int, i64, p, i32, p, u32, p, p]),
+    "fmidx_boost_logits": (C.c_int, [p, p, p, C.c_int, i64, sz, u32, p, p, p, p, p, p, p, p, i32, p]),
     "fmidx_mask_or": (C.c_int, [p, p, u32, sz, p, p]),
     "fmidx_mask_popcount": (C.c_int, [p, p, sz, u32, p, p]),
     "fmidx_mask_compact": (C.c_int, [p, p, p, sz, u32, p, p, p, p]),
@@ -58,6 +59,8 @@ SIGNATURES = {
     "fmidx_query_host_summary": (C.c_int, [p, p, p, sz, i64, u32, p, p, p]),
     "fmidx_query_submit": (C.c_int, [p, C.c_int, p, p, sz, i64, u32, p, p, p]),
     "fmidx_query_wait": (C.c_int, [p, C.c_int]),
+    "fmidx_query_graph_prepare": (C.c_int, [p, C.c_int, sz, sz, i64, u32, C.POINTER(p), C.POINTER(p)]),
+    "fmidx_query_graph_launch": (C.c_int, [p, C.c_int]),
     "fmidx_locate_host": (C.c_int, [p, p, sz, p]),
     "fmidx_info": (C.c_int, [p, C.POINTER(u64)]),
     "fmidx_debug_copy_sa": (C.c_int, [p, p, sz]),

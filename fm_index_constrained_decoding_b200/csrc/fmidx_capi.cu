@@ -171,6 +171,11 @@ void fmidx_free(fmidx_t *h) {
     }
     for (auto &sl : h->slots) {
         if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
+        for (auto &g : sl.gexec) if (g) cudaGraphExecDestroy(g);
+        if (sl.g_hin) cudaFreeHost(sl.g_hin);
+        if (sl.g_hout) cudaFreeHost(sl.g_hout);
+        if (sl.g_din) cudaFree(sl.g_din);
+        if (sl.g_dout) cudaFree(sl.g_dout);
         if (sl.in.p) cudaFree(sl.in.p);
         if (sl.mask.p) cudaFree(sl.mask.p);
         if (sl.ws.p) cudaFree(sl.ws.p);
@@ -660,6 +665,19 @@ int fmidx_mask_logits(fmidx_t *h, const uint64_t *d_sp, const uint64_t *d_ep, si
                           d_extra_masks, n_extra, d_mask_out, nullptr, (cudaStream_t)stream);
 }
 
+int fmidx_boost_logits(fmidx_t *h, const void *d_logits, void *d_out, int dtype, int64_t row_stride, size_t B, uint32_t vocab,
+                       const uint32_t *d_dmask, const uint32_t *d_n_distinct, const uint32_t *d_unigram, const int32_t *d_kind,
+                       const float *d_vd, const float *d_vu_nonempty, const float *d_vu_empty, const float *d_ve, int32_t eos,
+                       void *stream) {
+    FM_TRY(enter(h, false));
+    if (!d_logits || !d_out || !d_dmask || !d_n_distinct || !d_unigram || !d_kind || !d_vd || !d_vu_nonempty || !d_vu_empty || !d_ve) {
+        fm_set_error("null argument");
+        return FMIDX_EINVAL;
+    }
+    return fm_launch_boost_apply(h, d_logits, d_out, dtype, row_stride, B, vocab, d_dmask, d_n_distinct, d_unigram, d_kind, d_vd,
+                                 d_vu_nonempty, d_vu_empty, d_ve, eos, (cudaStream_t)stream);
+}
+
 int fmidx_mask_or(fmidx_t *h, const uint32_t *d_pieces, uint32_t n_pieces, size_t n_words, uint32_t *d_out, void *stream) {
     FM_TRY(enter(h, false));
     if (!d_pieces || !d_out) { fm_set_error("null argument"); return FMIDX_EINVAL; }
@@ -740,9 +758,80 @@ static int query_host_impl(fmidx_t *h, const int32_t *toks, const int64_t *offs,
     return FMIDX_OK;
 }
 
+// ---- graph-captured pipelined form -------------------------------------------------------------------------------------
+static int graph_sequence(fmidx_t *h, fmidx::Slot &sl, int64_t shift, uint32_t vocab) {
+    const size_t B = sl.g_B;
+    cudaStream_t s = sl.stream;
+    const uint32_t words = (vocab + 31) / 32;
+    int64_t *d_offs = (int64_t *)sl.g_din;
+    int32_t *d_toks = (int32_t *)((char *)sl.g_din + (B + 1) * 8);
+    uint64_t *d_sp = (uint64_t *)sl.g_dout, *d_ep = d_sp + B;
+    uint32_t *d_n = (uint32_t *)(d_ep + B);
+    uint32_t *d_mask = (uint32_t *)sl.mask.p;
+    FM_CUDA(cudaMemcpyAsync(sl.g_din, sl.g_hin, (B + 1) * 8 + sl.g_maxtok * 4, cudaMemcpyHostToDevice, s));
+    FM_TRY(fm_launch_search(h, d_toks, d_offs, B, shift, d_sp, d_ep, 0, s, nullptr, words));
+    h->mask_ws_override = &sl.ws;
+    struct Reset { fmidx_t *h; ~Reset() { h->mask_ws_override = nullptr; } } reset{h};
+    FM_TRY(fm_launch_mask(h, d_sp, d_ep, B, shift, vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, d_mask, nullptr, s));
+    FM_TRY(fm_launch_popcount(h, d_mask, B, vocab, d_n, s));
+    FM_CUDA(cudaMemcpyAsync(sl.g_hout, sl.g_dout, B * 20, cudaMemcpyDeviceToHost, s));
+    return FMIDX_OK;
+}
+
+int fmidx_query_graph_prepare(fmidx_t *h, int slot, size_t B, size_t max_tokens, int64_t shift, uint32_t vocab, void **h_in,
+                              void **h_out) {
+    FM_TRY(enter(h, true));
+    if (slot < 0 || slot >= FMIDX_SLOTS) { fm_set_error("slot must be 0..%d", FMIDX_SLOTS - 1); return FMIDX_EINVAL; }
+    if (!B || !vocab || !h_in || !h_out) { fm_set_error("bad argument"); return FMIDX_EINVAL; }
+    fmidx::Slot &sl = h->slots[slot];
+    if (sl.gexec[0]) { fm_set_error("slot %d already holds a captured step", slot); return FMIDX_ESTATE; }
+    if (!sl.stream) FM_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    FM_CUDA(cudaStreamSynchronize(sl.stream));
+    sl.g_B = B;
+    sl.g_maxtok = max_tokens;
+    const size_t in_bytes = (B + 1) * 8 + max_tokens * 4;
+    FM_CUDA(cudaMallocHost(&sl.g_hin, in_bytes));
+    FM_CUDA(cudaMallocHost(&sl.g_hout, B * 20));
+    FM_CUDA(cudaMalloc(&sl.g_din, in_bytes + 16));
+    FM_CUDA(cudaMalloc(&sl.g_dout, B * 20 + 16));
+    memset(sl.g_hin, 0, in_bytes);  // B empty prefixes: a valid input
+    FM_TRY(fm_scratch(h, sl.mask, B * (size_t)((vocab + 31) / 32) * 4, false));
+    // one eager pass sizes every workspace (nothing may be allocated while a stream is being captured)
+    FM_TRY(graph_sequence(h, sl, shift, vocab));
+    FM_CUDA(cudaStreamSynchronize(sl.stream));
+    for (int e = 0; e < 2; ++e) {
+        const uint64_t l0 = g_fm_launches.load();
+        FM_CUDA(cudaStreamBeginCapture(sl.stream, cudaStreamCaptureModeThreadLocal));
+        int rc = graph_sequence(h, sl, shift, vocab);
+        cudaGraph_t g = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(sl.stream, &g);
+        if (rc != FMIDX_OK) { if (g) cudaGraphDestroy(g); return rc; }
+        if (ce != cudaSuccess) { fm_set_error("stream capture failed: %s", cudaGetErrorString(ce)); return FMIDX_ECUDA; }
+        ce = cudaGraphInstantiate(&sl.gexec[e], g, 0);
+        cudaGraphDestroy(g);
+        if (ce != cudaSuccess) { fm_set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); return FMIDX_ECUDA; }
+        sl.g_launches = g_fm_launches.load() - l0;
+        g_fm_launches.store(l0);  // captured, not launched
+    }
+    sl.g_step = 0;
+    *h_in = sl.g_hin;
+    *h_out = sl.g_hout;
+    return FMIDX_OK;
+}
+
+int fmidx_query_graph_launch(fmidx_t *h, int slot) {
+    if (!h) { fm_set_error("null handle"); return FMIDX_EINVAL; }
+    if (slot < 0 || slot >= FMIDX_SLOTS || !h->slots[slot].gexec[0]) { fm_set_error("slot %d holds no captured step", slot); return FMIDX_ESTATE; }
+    fmidx::Slot &sl = h->slots[slot];
+    FM_CUDA(cudaGraphLaunch(sl.gexec[sl.g_step++ & 1u], sl.stream));
+    g_fm_launches.fetch_add(sl.g_launches, std::memory_order_relaxed);
+    return FMIDX_OK;
+}
+
 int fmidx_query_submit(fmidx_t *h, int slot, const int32_t *toks, const int64_t *offs, size_t B, int64_t shift,
                        uint32_t vocab, uint64_t *sp, uint64_t *ep, uint32_t *n_distinct) {
     if (slot < 0 || slot >= FMIDX_SLOTS) { fm_set_error("slot must be 0..%d", FMIDX_SLOTS - 1); return FMIDX_EINVAL; }
+    if (h && h->slots[slot].gexec[0]) { fm_set_error("slot %d is driven by a captured step (fmidx_query_graph_launch)", slot); return FMIDX_ESTATE; }
     return query_host_impl(h, toks, offs, B, shift, vocab, sp, ep, nullptr, n_distinct, slot);
 }
 

@@ -56,8 +56,6 @@ struct FmBuf {  // growable device / pinned-host scratch
 // sharded step: the parts of the cross-shard exchange that are folded into the enumeration kernels
 struct FmXchgArgs {
     uint64_t *xcounts = nullptr;            // [B] occurrence counts (ep - sp) of this shard, part of its side data
-    const uint32_t *ack_flags = nullptr;    // k_mask_top first waits until ack_flags[p] >= ack_seq for p < ack_world
-    uint32_t ack_world = 0, ack_seq = 0;
     // publication at the tail of the last enumeration kernel (world == 0: none)
     uint32_t *const *peer_inbox = nullptr;
     uint32_t *const *peer_data_flags = nullptr;
@@ -84,6 +82,14 @@ struct fmidx {
     struct Slot {                // fmidx_query_submit / fmidx_query_wait: independent in-flight host batches
         cudaStream_t stream = nullptr;
         FmBuf in, mask, ws;
+        // graph-captured form (fmidx_query_graph_*): the whole step of the slot as two executable graphs (the mask kernels
+        // alternate between two work-list counter pairs, so consecutive steps alternate between the two captures)
+        cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+        void *g_hin = nullptr, *g_hout = nullptr;   // pinned host staging: [offs | toks] in, [sp | ep | n_distinct] out
+        void *g_din = nullptr, *g_dout = nullptr;
+        size_t g_B = 0, g_maxtok = 0;
+        uint64_t g_launches = 0;
+        uint32_t g_step = 0;
     } slots[FMIDX_SLOTS];
     FmBuf h_scratch[4];
     int sm_count = 148;
@@ -118,9 +124,13 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
                    int32_t always_allow, const uint32_t *d_extra, uint32_t n_extra, uint32_t *d_mask,
                    uint32_t *d_counts, cudaStream_t s, uint32_t *d_occ = nullptr, size_t dense_lo = 0, size_t dense_n = ~(size_t)0,
                    bool prezeroed = false, const FmXchgArgs *xa = nullptr);
-int fm_launch_xchg_pull(fmidx *h, uint32_t *const *d_peer_masks, uint32_t *const *d_peer_ack_flags, const uint32_t *d_data_flags,
-                        const uint32_t *d_inbox, size_t xwords, size_t count_off, uint32_t world, uint32_t rank, size_t B, uint32_t vocab,
-                        uint32_t seq, uint64_t *d_counts_out, uint32_t *d_done_ctr, cudaStream_t s);
+int fm_launch_xchg_pull(fmidx *h, uint32_t *const *d_peer_masks, const uint32_t *d_data_flags, const uint32_t *d_inbox, size_t xwords,
+                        size_t count_off, uint32_t world, uint32_t rank, size_t B, uint32_t vocab, uint32_t seq, uint64_t *d_counts_out,
+                        cudaStream_t s);
+int fm_launch_boost_apply(fmidx *h, const void *d_logits, void *d_out, int dtype, int64_t row_stride, size_t B, uint32_t vocab,
+                          const uint32_t *d_dmask, const uint32_t *d_n_distinct, const uint32_t *d_unigram, const int32_t *d_kind,
+                          const float *d_vd, const float *d_vu_nonempty, const float *d_vu_empty, const float *d_ve, int32_t eos,
+                          cudaStream_t s);
 int fm_launch_or(fmidx *h, const uint32_t *d_pieces, uint32_t n_pieces, size_t n_words, uint32_t *d_out, cudaStream_t s);
 int fm_launch_popcount(fmidx *h, const uint32_t *d_mask, size_t B, uint32_t vocab, uint32_t *d_n, cudaStream_t s);
 int fm_launch_gather_probe(fmidx *h, int unit_bytes, size_t n_loads, double *out_gbps, cudaStream_t s);

@@ -360,7 +360,7 @@ __device__ __forceinline__ uint32_t fm_access1(const uint4 *__restrict__ level_c
 }
 
 struct EnumSmem {
-    uint32_t bm[SLICE / 32];
+    uint32_t bm[2 * SLICE / 32];       // 2-byte logits use 8192-token slices
     uint32_t seed[4][3];            // depth-LT nodes of this slice (<= 2 when a top node spans one slice)
     uint32_t bnode[48][3];          // byte-level nodes (each covers 256 symbols): <= 16 per seed (+ overlap)
     uint32_t n_seed, n_bnode, width;
@@ -635,6 +635,19 @@ __device__ __forceinline__ int fm_uni_find(const FmDev &ix, uint32_t s, uint32_t
     }
     return (lo < (int)ix.uni_n && __ldg(ix.uni_sp + lo) == s && __ldg(ix.uni_ep + lo) == e) ? lo : -1;
 }
+// the same by `nl` cooperating lanes (this one is lane l) in ONE round trip: every lane loads whole 16-byte vectors of the
+// block starts and compares; returns the lane's own finding (or -1) -- reduce with max over the group
+__device__ __forceinline__ int fm_uni_find_part(const FmDev &ix, uint32_t s, uint32_t l, uint32_t nl) {
+    int found = -1;
+    for (uint32_t i = 4u * l; i < ix.uni_n; i += 4u * nl) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(ix.uni_sp + i));  // the array is padded past uni_n
+        if (v.x == s) found = (int)i;
+        if (v.y == s && i + 1u < ix.uni_n) found = (int)i + 1;
+        if (v.z == s && i + 2u < ix.uni_n) found = (int)i + 2;
+        if (v.w == s && i + 3u < ix.uni_n) found = (int)i + 3;
+    }
+    return found;
+}
 // word i of the TOKEN-axis bitmap (token = symbol - shift, 0 <= token < vocab) cut out of a symbol-axis table row
 __device__ __forceinline__ uint32_t fm_uni_word(const uint32_t *__restrict__ srow, uint32_t src_words, uint32_t i, int64_t shift,
                                                 uint32_t vocab) {
@@ -661,21 +674,8 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
            uint2 *__restrict__ lvl, const int32_t *__restrict__ override_tok, int64_t shift, uint32_t vocab,
            uint4 *__restrict__ work_items, uint32_t *__restrict__ work_count, uint32_t *__restrict__ mask_out,
            uint32_t *__restrict__ counts_out, uint32_t *__restrict__ occ_out, uint32_t dense_lo, uint32_t dense_n,
-           uint32_t zflags, uint64_t *__restrict__ xcounts, const uint32_t *__restrict__ ack_flags, uint32_t ack_world,
-           uint32_t ack_seq, uint32_t scan_max) {
+           uint32_t zflags, uint64_t *__restrict__ xcounts, uint32_t scan_max) {
     __shared__ uint4 stage[8][16];
-    // sharded step: the bitmap buffer may only be overwritten once every shard has pulled the step that last used it
-    // (ack flags live in THIS GPU's memory, the peers raise them by remote stores; normally long since satisfied)
-    if (ack_seq) {
-        if (threadIdx.x < ack_world) {
-            const long long t0 = clock64();
-            while ((int32_t)(fm_ld_acquire_sys(ack_flags + threadIdx.x) - ack_seq) < 0) {
-                __nanosleep(100);
-                if (clock64() - t0 > 20000000000ll) __trap();
-            }
-        }
-        __syncthreads();
-    }
     const int lane = threadIdx.x & 31, hw = (threadIdx.x >> 4) & 1, hl = threadIdx.x & 15;
     const int wslot = threadIdx.x >> 4;  // half-warp slot in the CTA
     const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -696,7 +696,8 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
         const bool dense = b - dense_lo < dense_n;
         if (xcounts && lane == 0) xcounts[b] = e > s ? e - s : 0ull;  // occurrence count of the prefix on this shard
         if (ix.uni_n && !counts_out && e > s && e - s > (uint64_t)SCAN_INLINE) {
-            const int ui = fm_uni_find(ix, (uint32_t)s, (uint32_t)e);
+            int ui = __reduce_max_sync(FULL, fm_uni_find_part(ix, (uint32_t)s, (uint32_t)lane, 32u));
+            if (ui >= 0 && __ldg(ix.uni_ep + ui) != (uint32_t)e) ui = -1;
             const uint32_t nslices = (vocab + SLICE - 1) / SLICE;
             if (ui >= 0 && L > 0 && nslices <= fm_nodes_at(ix.max_sym, L, LT)) {  // the work list has P_top slots per prefix
                 // the range is one frequent symbol's whole block: its continuation set is in the table.  One work item per
@@ -1041,7 +1042,8 @@ __device__ __forceinline__ void fm_enum_seeded(const FmDev &ix, uint32_t LT, uin
 
 __device__ __forceinline__ void fm_enum_slice(const FmDev &ix, const uint2 *__restrict__ top_b, uint32_t LT, uint32_t sa,
                                               uint32_t se, int64_t shift, uint32_t t0, EnumSmem &S,
-                                              uint32_t *__restrict__ counts_row, uint64_t s64, uint64_t e64) {
+                                              uint32_t *__restrict__ counts_row, uint64_t s64, uint64_t e64,
+                                              uint32_t slice_tokens = SLICE) {
     if (ix.bwt && !counts_row) {
         // resident BWT: a range of up to SCAN_INLINE rows is read by the CTA itself (every slice-CTA of the beam reads the
         // same few hundred bytes, L2 hits after the first) and filtered to the slice -- no table, no dependent probes
@@ -1058,16 +1060,66 @@ __device__ __forceinline__ void fm_enum_slice(const FmDev &ix, const uint2 *__re
             return;
         }
         if (ix.uni_n) {
-            const int ui = fm_uni_find(ix, (uint32_t)s64, (uint32_t)e64);
+            __syncthreads();  // S.bm was zeroed by all threads; S.n_seed is free until the seeds are made
+            if (threadIdx.x == 0) S.n_seed = 0xFFFFFFFFu;
+            __syncthreads();
+            const int mine = fm_uni_find_part(ix, (uint32_t)s64, threadIdx.x, blockDim.x);
+            if (mine >= 0) S.n_seed = (uint32_t)mine;  // block starts are distinct: at most one thread writes
+            __syncthreads();
+            int ui = (int)S.n_seed;
+            if (ui >= 0 && __ldg(ix.uni_ep + ui) != (uint32_t)e64) ui = -1;
+            __syncthreads();  // everybody has read S.n_seed before the seed code may overwrite it
             if (ui >= 0) {  // one frequent symbol's whole block: the slice comes straight out of the unigram table
                 const uint32_t *srow = ix.uni_masks + (size_t)ui * ix.uni_words;
-                const uint32_t t1 = (uint32_t)min((int64_t)se - shift, (int64_t)t0 + SLICE);  // tokens of this slice: [t0, t1)
-                for (uint32_t w = threadIdx.x; w < SLICE / 32; w += blockDim.x) S.bm[w] = fm_uni_word(srow, ix.uni_words, (t0 >> 5) + w, shift, t1);
+                const uint32_t t1 = (uint32_t)min((int64_t)se - shift, (int64_t)t0 + slice_tokens);  // tokens of this slice: [t0, t1)
+                for (uint32_t w = threadIdx.x; w < slice_tokens / 32; w += blockDim.x) S.bm[w] = fm_uni_word(srow, ix.uni_words, (t0 >> 5) + w, shift, t1);
                 return;
             }
         }
     }
-    if (threadIdx.x == 0) fm_seed_from_table(ix, top_b, LT, sa, se, S);
+    if (top_b) {
+        if (threadIdx.x == 0) fm_seed_from_table(ix, top_b, LT, sa, se, S);
+    } else {
+        // No table from k_mask_top (logits mode launches nothing before this kernel): the CTA descends by itself to the
+        // depth-LT nodes that intersect its slice -- at most four, one half-warp each (sp octet + ep octet, LT dependent probes;
+        // the cells of the first levels are shared by every slice-CTA of the beam, i.e. L2 hits).  Only beams whose range is
+        // wider than SCAN_INLINE rows and not a unigram-table entry come here.
+        const int tid = threadIdx.x, lane = tid & 31, hw = tid >> 4, hl = tid & 15, sub = tid & 7;
+        const uint32_t span_bits = 8u + 4u * (ix.levels - LT);
+        if (tid < 64) {
+            const uint32_t p = (sa >> span_bits) + (uint32_t)hw;
+            const bool need = sa < se && p <= ((se - 1u) >> span_bits);
+            uint32_t lo = (uint32_t)s64, hi = (uint32_t)min(e64, (uint64_t)ix.n);
+            for (uint32_t l = 0; l < LT; ++l) {
+                const uint32_t d = (p >> (4u * (LT - 1u - l))) & 15u;
+                const uint32_t r = fm_step8(ix.cells + l * ix.level_stride, hl < 8 ? lo : hi, d, sub, need && hi > lo);
+                const uint32_t o = __shfl_xor_sync(FULL, r, 8);
+                lo = hl < 8 ? r : o;
+                hi = hl < 8 ? o : r;
+            }
+            if (hl == 0) {
+                S.bnode[hw][0] = lo;  // staging (the byte-level node list is not in use yet)
+                S.bnode[hw][1] = (need && hi > lo) ? hi : lo;
+                S.bnode[hw][2] = p;
+            }
+            (void)lane;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t n = 0, W = 0;
+            for (int k = 0; k < 4; ++k)
+                if (S.bnode[k][1] > S.bnode[k][0]) {
+                    S.seed[n][0] = S.bnode[k][0];
+                    S.seed[n][1] = S.bnode[k][1];
+                    S.seed[n][2] = S.bnode[k][2];
+                    ++n;
+                    W += S.bnode[k][1] - S.bnode[k][0];
+                }
+            S.n_seed = n;
+            S.n_bnode = 0;
+            S.width = W;
+        }
+    }
     __syncthreads();
     fm_enum_seeded(ix, LT, sa, se, shift, t0, S, counts_row);
 }
@@ -1353,7 +1405,7 @@ k_mask_logits_tma(FmDev ix, const uint2 *__restrict__ top, uint32_t P_top, uint3
     const int32_t ovr = override_tok ? override_tok[b] : -1;
     uint32_t sa, se;
     fm_slice_interval(ix, t0, t1, shift, sa, se);
-    if (ovr < 0) fm_enum_slice(ix, top + (size_t)b * P_top, LT, sa, se, shift, t0, S, nullptr, sp[b], ep[b]);
+    if (ovr < 0) fm_enum_slice(ix, top ? top + (size_t)b * P_top : nullptr, LT, sa, se, shift, t0, S, nullptr, sp[b], ep[b]);
     __syncthreads();
     if (ovr >= 0) {
         if (tid == 0 && (uint32_t)ovr >= t0 && (uint32_t)ovr < t1) S.bm[((uint32_t)ovr - t0) >> 5] = 1u << (((uint32_t)ovr - t0) & 31u);
@@ -1464,7 +1516,7 @@ k_mask_logits_pipe(FmDev ix, const uint2 *__restrict__ top, uint32_t P_top, uint
         const int32_t ovr = override_tok ? override_tok[b] : -1;
         uint32_t sa, se;
         fm_slice_interval(ix, t0, t1, shift, sa, se);
-        if (ovr < 0) fm_enum_slice(ix, top + (size_t)b * P_top, LT, sa, se, shift, t0, S, nullptr, sp[b], ep[b]);
+        if (ovr < 0) fm_enum_slice(ix, top ? top + (size_t)b * P_top : nullptr, LT, sa, se, shift, t0, S, nullptr, sp[b], ep[b]);
         __syncthreads();
         if (ovr >= 0) {
             if (tid == 0 && (uint32_t)ovr >= t0 && (uint32_t)ovr < t1) S.bm[((uint32_t)ovr - t0) >> 5] = 1u << (((uint32_t)ovr - t0) & 31u);
@@ -1528,25 +1580,28 @@ k_mask_logits_pipe(FmDev ix, const uint2 *__restrict__ top, uint32_t P_top, uint
 }
 
 // ---- phase B, fused with the logits row -------------------------------------------------------------------
-// DT: FMIDX_F32/BF16/F16.   VECTOR: 16-byte accesses are legal.   grid = ceil(vocab/4096) * B, slice-fastest.
-template <int DT, bool VECTOR>
-__global__ void __launch_bounds__(MASK_THREADS)
+// DT: FMIDX_F32/BF16/F16.   VECTOR: 16-byte accesses are legal.   SL: tokens per CTA -- 4096 for fp32, 8192 for the 2-byte
+// dtypes, so that a CTA moves 16 KB each way whatever the dtype (with 4096-token slices the bf16 step reached 0.54 of the HBM
+// roofline against 0.78 for fp32: same fixed latency per CTA, half the bytes).  Registers are capped for 4 resident CTAs per
+// SM = 64 KB of loads in flight per SM.  grid = ceil(vocab/SL) * B, slice-fastest.
+template <int DT, bool VECTOR, int SL>
+__global__ void __launch_bounds__(MASK_THREADS, 4)
 k_mask_logits(FmDev ix, const uint2 *__restrict__ top, uint32_t P_top, uint32_t LT, int64_t shift, uint32_t vocab,
               const void *logits_v, void *out_v, int64_t row_stride, const int32_t *__restrict__ override_tok,
               int32_t always_allow, const uint32_t *__restrict__ extra, uint32_t n_extra, uint32_t B,
               uint32_t *__restrict__ mask_out, const uint64_t *__restrict__ sp, const uint64_t *__restrict__ ep) {
     __shared__ EnumSmem S;
     const int tid = threadIdx.x;
-    const uint32_t nslices = (vocab + SLICE - 1) / SLICE;
+    const uint32_t nslices = (vocab + SL - 1) / SL;
     const uint32_t b = blockIdx.x / nslices;
-    const uint32_t t0 = (blockIdx.x % nslices) * SLICE;
-    const uint32_t t1 = min(t0 + (uint32_t)SLICE, vocab);
+    const uint32_t t0 = (blockIdx.x % nslices) * SL;
+    const uint32_t t1 = min(t0 + (uint32_t)SL, vocab);
     const uint32_t mask_words = (vocab + 31u) >> 5;
 
     // 1. issue the logits loads for this slice
     using ET = typename Elem<DT>::T;
     constexpr int VEC = Elem<DT>::VEC;
-    constexpr int NV = SLICE / (MASK_THREADS * VEC);  // vectors per thread
+    constexpr int NV = SL / (MASK_THREADS * VEC);  // vectors per thread
     uint4 regs[VECTOR ? NV : 1];
     const ET *row_in = reinterpret_cast<const ET *>(logits_v) + (size_t)b * row_stride;
     ET *row_out = reinterpret_cast<ET *>(out_v) + (size_t)b * row_stride;
@@ -1558,11 +1613,11 @@ k_mask_logits(FmDev ix, const uint2 *__restrict__ top, uint32_t P_top, uint32_t 
         }
     }
     // 2. bitmap of the slice
-    for (int w = tid; w < SLICE / 32; w += MASK_THREADS) S.bm[w] = 0;
+    for (int w = tid; w < SL / 32; w += MASK_THREADS) S.bm[w] = 0;
     const int32_t ovr = override_tok ? override_tok[b] : -1;
     uint32_t sa, se;
     fm_slice_interval(ix, t0, t1, shift, sa, se);
-    if (ovr < 0) fm_enum_slice(ix, top + (size_t)b * P_top, LT, sa, se, shift, t0, S, nullptr, sp[b], ep[b]);  // (k_mask_top left override rows empty)
+    if (ovr < 0) fm_enum_slice(ix, top ? top + (size_t)b * P_top : nullptr, LT, sa, se, shift, t0, S, nullptr, sp[b], ep[b], SL);  // (k_mask_top left override rows empty)
     __syncthreads();
     // 3. per-shard masks of the other GPUs, override rows, always-allowed token
     if (ovr >= 0) {
@@ -1605,6 +1660,52 @@ k_mask_logits(FmDev ix, const uint2 *__restrict__ top, uint32_t P_top, uint32_t 
     }
 }
 
+// ---- soft boost as a streaming epilogue over bitmaps -------------------------------------------------------------
+// document_constrained_generation_causal.py:137-178 / _causal_qwen.py:159-212:  out = scores + mask with, per row,
+//   kind 0 (qwen: still thinking)        mask = 0
+//   kind 1 (no trailing corpus n-gram)    mask = vu_empty on the corpus unigrams
+//   kind 2 (trailing n-gram)              mask = vd on the continuations D of the n-gram, and on the other corpus unigrams
+//                                         vu_nonempty, or vu_empty when D is empty (qwen boosts a fresh start more)
+//   and, last, mask[eos] = ve unless ve is NaN (the eos rule).
+// D is the row's bitmap from the enumeration kernels (override rows: a single bit), n_distinct its popcount, U the
+// resident unigram bitmap.  The values arrive already rounded to the dtype of the scores (the reference assigns Python
+// floats into a tensor of that dtype); the addition is done in fp32 and rounded once, like torch's.  One CTA per
+// (row, 4096-token slice): pure streaming, 2 x V x sizeof(dtype) + 16 KB per row.
+template <int DT>
+__global__ void __launch_bounds__(MASK_THREADS)
+k_boost_apply(const void *logits_v, void *out_v, int64_t row_stride, uint32_t vocab, const uint32_t *__restrict__ dmask,
+              const uint32_t *__restrict__ n_distinct, const uint32_t *__restrict__ unigram, const int32_t *__restrict__ kind,
+              const float *__restrict__ vd, const float *__restrict__ vu_nonempty, const float *__restrict__ vu_empty,
+              const float *__restrict__ ve, int32_t eos) {
+    using ET = typename Elem<DT>::T;
+    const uint32_t nslices = (vocab + SLICE - 1) / SLICE;
+    const uint32_t b = blockIdx.x / nslices;
+    const uint32_t t0 = (blockIdx.x % nslices) * SLICE, t1 = min(t0 + (uint32_t)SLICE, vocab);
+    const uint32_t mask_words = (vocab + 31u) >> 5;
+    const ET *row_in = reinterpret_cast<const ET *>(logits_v) + (size_t)b * row_stride;
+    ET *row_out = reinterpret_cast<ET *>(out_v) + (size_t)b * row_stride;
+    const int k = kind[b];
+    const float fd = vd[b], fu = (k == 2 && n_distinct[b] != 0u) ? vu_nonempty[b] : vu_empty[b], fe = ve[b];
+    const bool has_e = !(fe != fe) && k != 0;
+    for (uint32_t v = t0 + threadIdx.x; v < t1; v += MASK_THREADS) {
+        float m = 0.0f;
+        if (k != 0) {
+            const bool ub = (__ldg(unigram + (v >> 5)) >> (v & 31u)) & 1u;
+            const bool db = k == 2 && ((__ldg(dmask + (size_t)b * mask_words + (v >> 5)) >> (v & 31u)) & 1u);
+            m = db ? fd : (ub ? fu : 0.0f);
+            if (has_e && (int32_t)v == eos) m = fe;
+        }
+        float x;
+        if (DT == FMIDX_F32) x = reinterpret_cast<const float *>(row_in)[v];
+        else if (DT == FMIDX_BF16) x = __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(row_in)[v]);
+        else x = __half2float(reinterpret_cast<const __half *>(row_in)[v]);
+        const float y = x + m;
+        if (DT == FMIDX_F32) reinterpret_cast<float *>(row_out)[v] = y;
+        else if (DT == FMIDX_BF16) reinterpret_cast<__nv_bfloat16 *>(row_out)[v] = __float2bfloat16_rn(y);
+        else reinterpret_cast<__half *>(row_out)[v] = __float2half_rn(y);
+    }
+}
+
 // ---- bitmap -> sparse lists --------------------------------------------------------------------------
 // OR of the per-shard bitmap pieces gathered from the other GPUs (NCCL has no bitwise-OR reduction)
 __global__ void __launch_bounds__(256) k_or_pieces(const uint4 *__restrict__ pieces, uint32_t n_pieces, size_t n_vec,
@@ -1631,14 +1732,11 @@ __global__ void __launch_bounds__(256) k_or_pieces(const uint4 *__restrict__ pie
 // of its last enumeration kernel), then reads that peer's occupancy word(s) from the local inbox and pulls just the
 // occupied 4096-token slices (512 B each, one LDG.128 per lane, four slices in flight) straight out of the peer's
 // bitmap buffer over NVLink, OR-ing them into this rank's own rows in place.  When every peer has been read the warps
-// sum the occurrence counts of all B prefixes, and the CTA that finishes last raises ack flag[rank] = seq on every
-// shard ("rank has finished reading your buffers of step seq").
+// sum the occurrence counts of all B prefixes.  No acknowledgement: the buffer sets ping-pong (fmidx_shard.cu).
 __global__ void __launch_bounds__(128)
-k_xchg_pull(uint32_t *const *__restrict__ peer_masks, uint32_t *const *__restrict__ peer_ack_flags,
-            const uint32_t *__restrict__ data_flags, const uint32_t *__restrict__ inbox, uint32_t xwords, uint32_t count_off,
-            uint32_t world, uint32_t rank, uint32_t B, uint32_t vocab, uint32_t seq, uint64_t *__restrict__ counts_out,
-            uint32_t *__restrict__ done_ctr) {
-    __shared__ uint32_t s_last;
+k_xchg_pull(uint32_t *const *__restrict__ peer_masks, const uint32_t *__restrict__ data_flags, const uint32_t *__restrict__ inbox,
+            uint32_t xwords, uint32_t count_off, uint32_t world, uint32_t rank, uint32_t B, uint32_t vocab, uint32_t seq,
+            uint64_t *__restrict__ counts_out) {
     const uint32_t mask_words = (vocab + 31u) >> 5;
     const uint32_t nslices = (vocab + SLICE - 1) / SLICE, ow = (nslices + 31u) >> 5;
     const uint32_t own = B / world, row_lo = rank * own;
@@ -1714,16 +1812,6 @@ k_xchg_pull(uint32_t *const *__restrict__ peer_masks, uint32_t *const *__restric
             counts_out[b] = acc;
         }
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        s_last = atomicAdd(done_ctr, 1u) == gridDim.x - 1u ? 1u : 0u;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence_system();
-    if (threadIdx.x < world) fm_st_release_sys(peer_ack_flags[threadIdx.x] + rank, seq);
-    if (threadIdx.x == 0) *done_ctr = 0u;
 }
 
 __global__ void __launch_bounds__(256) k_popcount(const uint32_t *__restrict__ mask, uint32_t mask_words,
@@ -2025,10 +2113,13 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
     const uint32_t scan_max = std::max<uint32_t>(h->tune_scan_max, SCAN_INLINE);  // rows read off the resident BWT instead of walking the matrix
     const uint32_t mwords = (vocab + 31u) >> 5;
     const uint32_t zflags = (prezeroed ? 1u : 0u) | ((!has && (mwords & 3u) == 0 && ((uintptr_t)d_mask & 15) == 0) ? 2u : 0u);
+    // logits mode launches no k_mask_top: the slice-CTAs of k_mask_logits read narrow ranges off the resident BWT, take frequent
+    // one-token prefixes from the unigram table and descend to their own depth-LT nodes otherwise (fm_enum_slice)
+    if (!has)
     FM_LAUNCH(k_mask_top, (unsigned)((B * 32 + 127) / 128), 128, 0, s, ix, d_sp, d_ep, (uint32_t)B, LT, lvl, d_override, shift,
               vocab, items, ctr, has ? nullptr : d_mask, has ? nullptr : d_counts, has ? nullptr : d_occ, (uint32_t)dense_lo,
               (uint32_t)std::min<size_t>(dense_n, 0xFFFFFFFFu), zflags, xa && !has ? xa->xcounts : nullptr,
-              xa ? xa->ack_flags : nullptr, xa ? xa->ack_world : 0u, xa ? xa->ack_seq : 0u, L == 0 ? SCAN_INLINE : scan_max);
+              L == 0 ? SCAN_INLINE : scan_max);
     if (!has) {
         // CTAs per SM of the persistent k_mask_bytes grid (fmidx_tune "bytes_occ", 1..6)
         const int occ = h->tune_bytes_occ < 1 ? 1 : (h->tune_bytes_occ > 6 ? 6 : h->tune_bytes_occ);
@@ -2063,11 +2154,18 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
                (vocab % vec == 0);
     };
     const unsigned grid = (unsigned)nblk;
+    const unsigned grid2 = (unsigned)((size_t)((vocab + 2 * SLICE - 1) / (2 * SLICE)) * B);  // 8192-token slices (2-byte dtypes)
 #define FM_MASK_CASE(DT, VECT)                                                                                     \
-    FM_LAUNCH((k_mask_logits<DT, VECT>), grid, MASK_THREADS, 0, s, ix, lvl + top_off, P_top, LT, shift, vocab, d_logits, \
-              d_out, row_stride, d_override, always_allow, d_extra, n_extra, (uint32_t)B, d_mask, d_sp, d_ep)
+    do {                                                                                                           \
+        if (VECT && DT != FMIDX_F32)                                                                               \
+            FM_LAUNCH((k_mask_logits<DT, VECT, 2 * SLICE>), grid2, MASK_THREADS, 0, s, ix, (const uint2 *)nullptr, P_top, LT, shift, vocab, \
+                      d_logits, d_out, row_stride, d_override, always_allow, d_extra, n_extra, (uint32_t)B, d_mask, d_sp, d_ep);  \
+        else                                                                                                       \
+            FM_LAUNCH((k_mask_logits<DT, VECT, SLICE>), grid, MASK_THREADS, 0, s, ix, (const uint2 *)nullptr, P_top, LT, shift, vocab, \
+                      d_logits, d_out, row_stride, d_override, always_allow, d_extra, n_extra, (uint32_t)B, d_mask, d_sp, d_ep);  \
+    } while (0)
 #define FM_MASK_TMA(DT)                                                                                            \
-    FM_LAUNCH((k_mask_logits_tma<DT>), grid, MASK_THREADS, 0, s, ix, lvl + top_off, P_top, LT, shift, vocab, d_logits,   \
+    FM_LAUNCH((k_mask_logits_tma<DT>), grid, MASK_THREADS, 0, s, ix, (const uint2 *)nullptr, P_top, LT, shift, vocab, d_logits,   \
               d_out, row_stride, d_override, always_allow, d_extra, n_extra, (uint32_t)B, d_mask, d_sp, d_ep)
     // FMIDX_LOGITS_PATH = regs (default: one-shot CTAs, logits staged in registers -- the fastest measured,
     // 0.83 of HBM bandwidth on narrow beams) | tma (one-shot CTAs, one bulk async copy each way) | pipe
@@ -2089,7 +2187,7 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
             FM_CUDA(cudaFuncSetAttribute(k_mask_logits_pipe<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)); \
             attr_set = true;                                                                                        \
         }                                                                                                           \
-        FM_LAUNCH((k_mask_logits_pipe<DT>), pgrid, MASK_THREADS, dyn, s, ix, lvl + top_off, P_top, LT, shift, vocab,    \
+        FM_LAUNCH((k_mask_logits_pipe<DT>), pgrid, MASK_THREADS, dyn, s, ix, (const uint2 *)nullptr, P_top, LT, shift, vocab,    \
                   d_logits, d_out, row_stride, d_override, always_allow, d_extra, n_extra, (uint32_t)B, d_mask,     \
                   (uint32_t)nblk, ctr + 1, d_sp, d_ep);                                                                    \
     } while (0)
@@ -2124,6 +2222,25 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
     return FMIDX_OK;
 }
 
+int fm_launch_boost_apply(fmidx *h, const void *d_logits, void *d_out, int dtype, int64_t row_stride, size_t B, uint32_t vocab,
+                          const uint32_t *d_dmask, const uint32_t *d_n_distinct, const uint32_t *d_unigram, const int32_t *d_kind,
+                          const float *d_vd, const float *d_vu_nonempty, const float *d_vu_empty, const float *d_ve, int32_t eos,
+                          cudaStream_t s) {
+    (void)h;
+    if (B == 0 || vocab == 0) return FMIDX_OK;
+    const size_t nblk = (size_t)((vocab + SLICE - 1) / SLICE) * B;
+    if (nblk > 0x7FFFFFFFull) { fm_set_error("boost batch too large: split the call"); return FMIDX_EINVAL; }
+#define FM_BOOST(DT) FM_LAUNCH((k_boost_apply<DT>), (unsigned)nblk, MASK_THREADS, 0, s, d_logits, d_out, row_stride, vocab, d_dmask, d_n_distinct, \
+                               d_unigram, d_kind, d_vd, d_vu_nonempty, d_vu_empty, d_ve, eos)
+    if (dtype == FMIDX_F32) FM_BOOST(FMIDX_F32);
+    else if (dtype == FMIDX_BF16) FM_BOOST(FMIDX_BF16);
+    else if (dtype == FMIDX_F16) FM_BOOST(FMIDX_F16);
+    else { fm_set_error("unknown logits dtype %d", dtype); return FMIDX_EINVAL; }
+#undef FM_BOOST
+    FM_CUDA(cudaGetLastError());
+    return FMIDX_OK;
+}
+
 int fm_launch_or(fmidx *h, const uint32_t *d_pieces, uint32_t n_pieces, size_t n_words, uint32_t *d_out, cudaStream_t s) {
     if (n_words == 0 || n_pieces == 0) return FMIDX_OK;
     if ((n_words & 3) || ((uintptr_t)d_pieces & 15) || ((uintptr_t)d_out & 15)) {
@@ -2138,15 +2255,15 @@ int fm_launch_or(fmidx *h, const uint32_t *d_pieces, uint32_t n_pieces, size_t n
     return FMIDX_OK;
 }
 
-int fm_launch_xchg_pull(fmidx *h, uint32_t *const *d_peer_masks, uint32_t *const *d_peer_ack_flags, const uint32_t *d_data_flags,
-                        const uint32_t *d_inbox, size_t xwords, size_t count_off, uint32_t world, uint32_t rank, size_t B, uint32_t vocab,
-                        uint32_t seq, uint64_t *d_counts_out, uint32_t *d_done_ctr, cudaStream_t s) {
+int fm_launch_xchg_pull(fmidx *h, uint32_t *const *d_peer_masks, const uint32_t *d_data_flags, const uint32_t *d_inbox, size_t xwords,
+                        size_t count_off, uint32_t world, uint32_t rank, size_t B, uint32_t vocab, uint32_t seq, uint64_t *d_counts_out,
+                        cudaStream_t s) {
     if (B == 0 || world == 0) return FMIDX_OK;
     const size_t own = B / world;
     const size_t warps = std::max<size_t>(own, (B + 31) / 32);
     const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((warps + 3) / 4, (size_t)std::max(1, h->sm_count / 2)));
-    FM_LAUNCH(k_xchg_pull, grid, 128, 0, s, d_peer_masks, d_peer_ack_flags, d_data_flags, d_inbox, (uint32_t)xwords, (uint32_t)count_off,
-              world, rank, (uint32_t)B, vocab, seq, d_counts_out, d_done_ctr);
+    FM_LAUNCH(k_xchg_pull, grid, 128, 0, s, d_peer_masks, d_data_flags, d_inbox, (uint32_t)xwords, (uint32_t)count_off, world, rank,
+              (uint32_t)B, vocab, seq, d_counts_out);
     FM_CUDA(cudaGetLastError());
     return FMIDX_OK;
 }

@@ -1,12 +1,17 @@
 // fmidx_shard.cu -- one document shard's side of a sharded step: ONE host call enqueues
 //   k_search  (ranges of all B replicated prefixes on this shard; also zeroes the bitmap rows this rank owns)
 //   k_mask_top / k_mask_expand / k_mask_bytes  (bitmaps + slice-occupancy words + occurrence counts into peer-visible
-//              buffers; k_mask_top first waits for the acks of the step that last used the buffer set; the CTA of
-//              k_mask_bytes that finishes last PUBLISHES the side data into every shard's inbox and raises the data flags)
+//              buffers; the CTA of k_mask_bytes that finishes last PUBLISHES the side data into every shard's inbox and
+//              raises the data flags)
 //   k_xchg_pull (per peer: wait for its data flag -> pull its occupied 4096-token slices over NVLink -> OR into the rows this
-//              rank owns; total counts; ack)
+//              rank owns; total counts)
 // on one stream: five launches, no NCCL, no host synchronisation.  Buffer sets are independent (own buffers, flags, step
-// counters, scratch slot), so several steps overlap on several streams.  The reference has no distributed path
+// counters, scratch slot), so several steps overlap on several streams.
+// No acknowledgements are needed: every set PING-PONGS between two bitmap buffers and two inboxes (step parity).  When this
+// rank's pull of step s-1 has returned, every peer has published step s-1, hence (stream order on the peer) finished its
+// pull of step s-2 -- the last reader of the buffers that step s is about to overwrite.  (Round 1 and the first version of
+// this file waited for ack flags at the head of the 1024-CTA k_mask_top; spinning CTAs then held every thread slot of the GPU
+// whenever a peer was a little late, and the ranks slowed each other down: 59 M q/s on 4 GPUs against 131 M on one.)  The reference has no distributed path
 // (its only parallelism is one std::async per range, fm_index.cpp:146-166); parity for the sharded configuration is
 // "one reference index per shard, results OR/sum-reduced on the host".
 #include <cstring>
@@ -20,27 +25,27 @@ struct fmidx_shard {
     size_t B = 0, words = 0, ow = 0, count_off = 0, xwords = 0;
     bool ready = false;
     struct Set {
-        uint32_t *mask = nullptr;    // [B][words]    peer-visible (CUDA IPC)
-        uint32_t *inbox = nullptr;   // [world][xwords] peer-visible
+        uint32_t *mask[2] = {nullptr, nullptr};    // [B][words]    peer-visible (CUDA IPC), by step parity
+        uint32_t *inbox[2] = {nullptr, nullptr};   // [world][xwords] peer-visible, by step parity
         uint32_t *xlocal = nullptr;  // [xwords] occupancy words | occurrence counts (u64)
         uint64_t *counts = nullptr;  // [B] totals over all shards
         uint32_t *n_own = nullptr;   // [B/world] distinct-token counts of the owned rows (host-buffer form)
-        uint32_t *ctr = nullptr;     // [2] ticket counters: publish, pull
-        uint64_t *tables = nullptr;  // device: [4][world] peer pointers (masks, inbox, data flags, ack flags)
-        uint32_t *data_flags = nullptr, *ack_flags = nullptr;  // into `flags`
+        uint32_t *ctr = nullptr;     // ticket counter of the publish
+        uint64_t *tables = nullptr;  // device: [2 parities][3][world] peer pointers (masks, inbox, data flags)
+        uint32_t *data_flags = nullptr;  // into `flags`
         uint32_t seq = 0;
         cudaStream_t stream = nullptr;
         FmBuf in;                    // host-buffer form: prefixes + ranges on the device
     };
     std::vector<Set> sets;
-    uint32_t *flags = nullptr;       // [n_sets][2][world] peer-visible
-    std::vector<std::vector<void *>> peer;  // [3 kinds][n_sets * world] imported pointers (kind 2: one block, set 0 only)
+    uint32_t *flags = nullptr;       // [n_sets][world] peer-visible
+    std::vector<std::vector<void *>> peer;  // [3 kinds][2 * n_sets * world] imported pointers (kind 2: one block, buffer 0 only)
     std::vector<void *> opened;
 };
 
-static int shard_check(fmidx_shard *x, uint32_t set) {
+static int shard_check(fmidx_shard *x, uint32_t set, uint32_t mult = 1) {
     if (!x || !x->h) { fm_set_error("null shard context"); return FMIDX_EINVAL; }
-    if (set >= x->n_sets) { fm_set_error("buffer set %u out of range [0,%u)", set, x->n_sets); return FMIDX_EINVAL; }
+    if (set >= x->n_sets * mult) { fm_set_error("buffer set %u out of range [0,%u)", set, x->n_sets); return FMIDX_EINVAL; }
     FM_CUDA(cudaSetDevice(x->h->device));
     return FMIDX_OK;
 }
@@ -63,28 +68,29 @@ int fmidx_shard_create(fmidx_t *h, uint32_t world, uint32_t rank, size_t B, uint
     x->count_off = (B * x->ow + 1) & ~(size_t)1;              // the counts are u64
     x->xwords = (x->count_off + 2 * B + 3) & ~(size_t)3;      // whole 16-byte vectors
     x->sets.resize(n_sets);
-    x->peer.assign(3, std::vector<void *>((size_t)n_sets * world, nullptr));
-    const size_t flag_words = (size_t)n_sets * 2 * world;
+    x->peer.assign(3, std::vector<void *>((size_t)2 * n_sets * world, nullptr));
+    const size_t flag_words = (size_t)n_sets * world;
     FM_CUDA(cudaMalloc((void **)&x->flags, flag_words * 4));
     FM_CUDA(cudaMemset(x->flags, 0, flag_words * 4));
     for (uint32_t i = 0; i < n_sets; ++i) {
         fmidx_shard::Set &st = x->sets[i];
-        FM_CUDA(cudaMalloc((void **)&st.mask, B * x->words * 4));
-        FM_CUDA(cudaMalloc((void **)&st.inbox, (size_t)world * x->xwords * 4));
+        for (int par = 0; par < 2; ++par) {
+            FM_CUDA(cudaMalloc((void **)&st.mask[par], B * x->words * 4));
+            FM_CUDA(cudaMalloc((void **)&st.inbox[par], (size_t)world * x->xwords * 4));
+            FM_CUDA(cudaMemset(st.mask[par], 0, B * x->words * 4));
+            FM_CUDA(cudaMemset(st.inbox[par], 0, (size_t)world * x->xwords * 4));
+            x->peer[0][((size_t)i * 2 + par) * world + rank] = st.mask[par];
+            x->peer[1][((size_t)i * 2 + par) * world + rank] = st.inbox[par];
+        }
         FM_CUDA(cudaMalloc((void **)&st.xlocal, x->xwords * 4));
         FM_CUDA(cudaMalloc((void **)&st.counts, B * 8));
         FM_CUDA(cudaMalloc((void **)&st.n_own, (B / world) * 4 + 16));
         FM_CUDA(cudaMalloc((void **)&st.ctr, 16));
-        FM_CUDA(cudaMalloc((void **)&st.tables, (size_t)4 * world * 8));
-        FM_CUDA(cudaMemset(st.mask, 0, B * x->words * 4));
-        FM_CUDA(cudaMemset(st.inbox, 0, (size_t)world * x->xwords * 4));
+        FM_CUDA(cudaMalloc((void **)&st.tables, (size_t)2 * 3 * world * 8));
         FM_CUDA(cudaMemset(st.xlocal, 0, x->xwords * 4));
         FM_CUDA(cudaMemset(st.ctr, 0, 16));
         FM_CUDA(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
-        st.data_flags = x->flags + (size_t)i * 2 * world;
-        st.ack_flags = st.data_flags + world;
-        x->peer[0][(size_t)i * world + rank] = st.mask;
-        x->peer[1][(size_t)i * world + rank] = st.inbox;
+        st.data_flags = x->flags + (size_t)i * world;
     }
     x->peer[2][rank] = x->flags;
     FM_CUDA(cudaDeviceSynchronize());
@@ -92,19 +98,20 @@ int fmidx_shard_create(fmidx_t *h, uint32_t world, uint32_t rank, size_t B, uint
     return FMIDX_OK;
 }
 
-// kind 0: bitmaps of `set`, 1: inbox of `set`, 2: the flag block (all sets; `set` ignored)
-int fmidx_shard_export(fmidx_shard_t *x, uint32_t set, int kind, unsigned char handle[64]) {
-    FM_TRY(shard_check(x, kind == 2 ? 0 : set));
+// kind 0: bitmap buffer `buf`, 1: inbox `buf` (buf = 2 * set + parity, 0 <= buf < 2 * n_sets), 2: the flag block (`buf` ignored)
+int fmidx_shard_export(fmidx_shard_t *x, uint32_t buf, int kind, unsigned char handle[64]) {
+    FM_TRY(shard_check(x, kind == 2 ? 0 : buf, 2));
     if (!handle || kind < 0 || kind > 2) { fm_set_error("bad argument"); return FMIDX_EINVAL; }
-    void *p = kind == 0 ? (void *)x->sets[set].mask : kind == 1 ? (void *)x->sets[set].inbox : (void *)x->flags;
+    void *p = kind == 0 ? (void *)x->sets[buf >> 1].mask[buf & 1] : kind == 1 ? (void *)x->sets[buf >> 1].inbox[buf & 1] : (void *)x->flags;
     cudaIpcMemHandle_t hd;
     FM_CUDA(cudaIpcGetMemHandle(&hd, p));
     memcpy(handle, &hd, 64);
     return FMIDX_OK;
 }
 
-int fmidx_shard_import(fmidx_shard_t *x, uint32_t set, int kind, uint32_t peer, const unsigned char handle[64]) {
-    FM_TRY(shard_check(x, kind == 2 ? 0 : set));
+int fmidx_shard_import(fmidx_shard_t *x, uint32_t buf, int kind, uint32_t peer, const unsigned char handle[64]) {
+    const uint32_t set = buf;
+    FM_TRY(shard_check(x, kind == 2 ? 0 : buf, 2));
     if (!handle || kind < 0 || kind > 2 || peer >= x->world || peer == x->rank) { fm_set_error("bad argument"); return FMIDX_EINVAL; }
     cudaIpcMemHandle_t hd;
     memcpy(&hd, handle, 64);
@@ -120,15 +127,15 @@ int fmidx_shard_ready(fmidx_shard_t *x) {
     FM_TRY(shard_check(x, 0));
     const uint32_t W = x->world;
     for (uint32_t i = 0; i < x->n_sets; ++i) {
-        std::vector<uint64_t> t((size_t)4 * W);
-        for (uint32_t p = 0; p < W; ++p) {
-            void *m = x->peer[0][(size_t)i * W + p], *ib = x->peer[1][(size_t)i * W + p], *fl = x->peer[2][p];
-            if (!m || !ib || !fl) { fm_set_error("shard_ready: buffers of peer %u (set %u) were not imported", p, i); return FMIDX_ESTATE; }
-            t[p] = (uint64_t)(uintptr_t)m;
-            t[W + p] = (uint64_t)(uintptr_t)ib;
-            t[2 * W + p] = (uint64_t)(uintptr_t)((uint32_t *)fl + (size_t)i * 2 * W);
-            t[3 * W + p] = (uint64_t)(uintptr_t)((uint32_t *)fl + (size_t)i * 2 * W + W);
-        }
+        std::vector<uint64_t> t((size_t)2 * 3 * W);
+        for (uint32_t par = 0; par < 2; ++par)
+            for (uint32_t p = 0; p < W; ++p) {
+                void *m = x->peer[0][((size_t)i * 2 + par) * W + p], *ib = x->peer[1][((size_t)i * 2 + par) * W + p], *fl = x->peer[2][p];
+                if (!m || !ib || !fl) { fm_set_error("shard_ready: buffers of peer %u (set %u) were not imported", p, i); return FMIDX_ESTATE; }
+                t[(size_t)par * 3 * W + p] = (uint64_t)(uintptr_t)m;
+                t[(size_t)par * 3 * W + W + p] = (uint64_t)(uintptr_t)ib;
+                t[(size_t)par * 3 * W + 2 * W + p] = (uint64_t)(uintptr_t)((uint32_t *)fl + (size_t)i * W);
+            }
         FM_CUDA(cudaMemcpy(x->sets[i].tables, t.data(), t.size() * 8, cudaMemcpyHostToDevice));
     }
     x->ready = true;
@@ -143,22 +150,24 @@ static int shard_step(fmidx_shard *x, uint32_t set, const int32_t *d_toks, const
     const uint32_t W = x->world;
     const size_t own = x->B / W;
     const uint32_t seq = ++st.seq;
-    const bool kz = fm_search_can_zero(st.mask, x->vocab);
-    FM_TRY(fm_launch_search(h, d_toks, d_offs, x->B, shift, d_sp, d_ep, 0, s, kz ? st.mask : nullptr, (uint32_t)x->words,
+    const uint32_t par = seq & 1u;
+    uint32_t *mask = st.mask[par];
+    const uint64_t *tab = st.tables + (size_t)par * 3 * W;
+    const bool kz = fm_search_can_zero(mask, x->vocab);
+    FM_TRY(fm_launch_search(h, d_toks, d_offs, x->B, shift, d_sp, d_ep, 0, s, kz ? mask : nullptr, (uint32_t)x->words,
                             (size_t)x->rank * own, own));
     FmXchgArgs xa;
     xa.xcounts = (uint64_t *)(st.xlocal + x->count_off);
-    xa.ack_flags = st.ack_flags; xa.ack_world = W; xa.ack_seq = seq - 1;  // every shard has pulled the step that last used this set
-    xa.peer_inbox = (uint32_t *const *)(st.tables + W);
-    xa.peer_data_flags = (uint32_t *const *)(st.tables + 2 * W);
+    xa.peer_inbox = (uint32_t *const *)(tab + W);
+    xa.peer_data_flags = (uint32_t *const *)(tab + 2 * W);
     xa.xlocal = st.xlocal; xa.done_ctr = st.ctr; xa.xwords = x->xwords; xa.world = W; xa.rank = x->rank; xa.seq = seq;
     h->mask_ws_override = &h->slots[set].ws;
     struct Reset { fmidx *h; ~Reset() { h->mask_ws_override = nullptr; } } reset{h};
     // only the rows this rank owns come out as complete bitmaps; the others are written slice-wise (occupied slices)
-    FM_TRY(fm_launch_mask(h, d_sp, d_ep, x->B, shift, x->vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, st.mask, nullptr, s,
+    FM_TRY(fm_launch_mask(h, d_sp, d_ep, x->B, shift, x->vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, mask, nullptr, s,
                           st.xlocal, (size_t)x->rank * own, own, kz, &xa));
-    return fm_launch_xchg_pull(h, (uint32_t *const *)st.tables, (uint32_t *const *)(st.tables + 3 * W), st.data_flags, st.inbox,
-                               x->xwords, x->count_off, W, x->rank, x->B, x->vocab, seq, st.counts, st.ctr + 1, s);
+    return fm_launch_xchg_pull(h, (uint32_t *const *)tab, st.data_flags, st.inbox[par], x->xwords, x->count_off, W, x->rank, x->B,
+                               x->vocab, seq, st.counts, s);
 }
 
 int fmidx_shard_step(fmidx_shard_t *x, uint32_t set, const int32_t *d_toks, const int64_t *d_offs, int64_t shift, uint64_t *d_sp,
@@ -169,9 +178,12 @@ int fmidx_shard_step(fmidx_shard_t *x, uint32_t set, const int32_t *d_toks, cons
     return shard_step(x, set, d_toks, d_offs, shift, d_sp, d_ep, stream ? (cudaStream_t)stream : x->sets[set].stream);
 }
 
-int fmidx_shard_result(fmidx_shard_t *x, uint32_t set, uint32_t **d_own_masks, uint64_t **d_counts, void **stream) {
+int fmidx_shard_result(fmidx_shard_t *x, uint32_t set, int parity, uint32_t **d_own_masks, uint64_t **d_counts, void **stream) {
     FM_TRY(shard_check(x, set));
-    if (d_own_masks) *d_own_masks = x->sets[set].mask + (size_t)x->rank * (x->B / x->world) * x->words;
+    // the sets ping-pong between two bitmap buffers: step number k (1, 2, ...) of a set writes buffer k & 1.
+    // parity 0 / 1: that buffer; -1: the buffer of the step issued last
+    const uint32_t par = parity < 0 ? (x->sets[set].seq & 1u) : ((uint32_t)parity & 1u);
+    if (d_own_masks) *d_own_masks = x->sets[set].mask[par] + (size_t)x->rank * (x->B / x->world) * x->words;
     if (d_counts) *d_counts = x->sets[set].counts;
     if (stream) *stream = x->sets[set].stream;
     return FMIDX_OK;
@@ -199,7 +211,7 @@ int fmidx_shard_submit(fmidx_shard_t *x, uint32_t set, const int32_t *toks, cons
     FM_CUDA(cudaMemcpyAsync(ep, d_ep, B * 8, cudaMemcpyDeviceToHost, s));
     if (counts) FM_CUDA(cudaMemcpyAsync(counts, st.counts, B * 8, cudaMemcpyDeviceToHost, s));
     if (n_distinct_own) {
-        FM_TRY(fm_launch_popcount(x->h, st.mask + (size_t)x->rank * own * x->words, own, x->vocab, st.n_own, s));
+        FM_TRY(fm_launch_popcount(x->h, st.mask[st.seq & 1u] + (size_t)x->rank * own * x->words, own, x->vocab, st.n_own, s));
         FM_CUDA(cudaMemcpyAsync(n_distinct_own, st.n_own, own * 4, cudaMemcpyDeviceToHost, s));
     }
     return FMIDX_OK;
@@ -219,7 +231,7 @@ void fmidx_shard_destroy(fmidx_shard_t *x) {
     for (void *p : x->opened) cudaIpcCloseMemHandle(p);
     for (auto &st : x->sets) {
         if (st.stream) cudaStreamDestroy(st.stream);
-        for (void *p : {(void *)st.mask, (void *)st.inbox, (void *)st.xlocal, (void *)st.counts, (void *)st.n_own, (void *)st.ctr, (void *)st.tables})
+        for (void *p : {(void *)st.mask[0], (void *)st.mask[1], (void *)st.inbox[0], (void *)st.inbox[1], (void *)st.xlocal, (void *)st.counts, (void *)st.n_own, (void *)st.ctr, (void *)st.tables})
             if (p) cudaFree(p);
         if (st.in.p) cudaFree(st.in.p);
     }

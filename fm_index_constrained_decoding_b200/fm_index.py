@@ -122,12 +122,18 @@ class FMIndex:
 
     def _distinct(self, fn, low, high, per):
         low, high = _u64(low, "low"), _u64(high, "high")
-        info = self.info()
-        cap = per * (info["max_sym"] + 1)
-        buf = np.empty(cap, dtype=np.uint64)
+        # one reusable output buffer per object (grown on demand: the C call reports the size it needs), instead of a
+        # 2 * (max_sym + 1) u64 allocation and an fmidx_info call per scalar query
+        buf = getattr(self, "_dbuf", None)
+        if buf is None:
+            buf = self._dbuf = np.empty(4096, dtype=np.uint64)
         k = C.c_size_t()
-        N.check(fn(self._h, low, high, buf.ctypes.data_as(C.c_void_p), cap, C.byref(k)))
-        return tuple(int(x) for x in buf[:k.value])
+        rc = fn(self._h, low, high, buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(k))
+        if rc == N.FMIDX_ERANGE and k.value > buf.size:
+            buf = self._dbuf = np.empty(int(k.value) + 1024, dtype=np.uint64)
+            rc = fn(self._h, low, high, buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(k))
+        N.check(rc)
+        return tuple(buf[:k.value].tolist())
 
     def distinct(self, low, high):
         """fm_index.cpp:99-117."""

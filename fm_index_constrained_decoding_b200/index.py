@@ -320,3 +320,35 @@ class FMIndex(_FMIndex):
         if self._beg_dev is None or self._beg_dev.device != positions.device:
             self._beg_dev = torch.tensor(self.beginnings, dtype=torch.int64, device=positions.device)
         return torch.searchsorted(self._beg_dev, positions, right=True) - 1
+
+
+class GraphQuerySlots:
+    """The host-buffer query pipeline as ONE CUDA-graph launch per batch (fmidx_query_graph_*): `n_slots` slots, each with
+    pinned staging buffers that the caller fills / reads in place:
+        slots.offs[i] int64 [B+1], slots.toks[i] int32 [max_tokens]      (inputs; offs[0] = 0)
+        slots.sp[i], slots.ep[i] uint64 [B], slots.n_distinct[i] uint32 [B]   (results, valid after wait(i))
+    launch(i) enqueues H2D -> search -> enumeration -> popcount -> D2H on the slot's stream and returns."""
+
+    def __init__(self, index, n_slots, B, max_tokens, vocab, shift=SHIFT, first_slot=0):
+        """first_slot: the handle's slots first_slot .. first_slot + n_slots - 1 are taken (16 per handle; a slot is either
+        captured or used by fmidx_query_submit / as the ws_slot of fmidx_query_batch, never both)."""
+        self.index, self.n, self.B, self.first = index, n_slots, B, first_slot
+        self.offs, self.toks, self.sp, self.ep, self.n_distinct = [], [], [], [], []
+        L = N.lib()
+        for i in range(n_slots):
+            hin, hout = C.c_void_p(), C.c_void_p()
+            N.check(L.fmidx_query_graph_prepare(index._h, first_slot + i, B, max_tokens, shift, vocab, C.byref(hin), C.byref(hout)))
+            self.offs.append(np.ctypeslib.as_array((C.c_int64 * (B + 1)).from_address(hin.value)))
+            self.toks.append(np.ctypeslib.as_array((C.c_int32 * max_tokens).from_address(hin.value + (B + 1) * 8)))
+            self.sp.append(np.ctypeslib.as_array((C.c_uint64 * B).from_address(hout.value)))
+            self.ep.append(np.ctypeslib.as_array((C.c_uint64 * B).from_address(hout.value + B * 8)))
+            self.n_distinct.append(np.ctypeslib.as_array((C.c_uint32 * B).from_address(hout.value + B * 16)))
+        self._launch, self._wait = L.fmidx_query_graph_launch, L.fmidx_query_wait
+
+    def launch(self, i):
+        if self._launch(self.index._h, self.first + i) != 0:
+            N.check(-1)
+
+    def wait(self, i):
+        if self._wait(self.index._h, self.first + i) != 0:
+            N.check(-1)

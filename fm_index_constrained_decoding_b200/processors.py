@@ -287,20 +287,24 @@ class SoftBoostLogitsProcessor:
         live = ngram & ~fin_last
         sp, ep = torch.where(live, sp2[R:], zero), torch.where(live, ep2[R:], zero)
         words = self.index.distinct_mask_batch(sp, ep, V)
-        sh = torch.arange(32, device=dev, dtype=words.dtype)
-        D = ((words.unsqueeze(-1) >> sh) & 1).bool().view(R, -1)[:, :V]
         if self.stop_at_count > 0:
             ov_eos = ngram & ((ep - sp) <= self.stop_at_count)
         else:
             ov_eos = torch.zeros_like(ngram)
         ov_pad = ngram & ~ov_eos & fin_last
-        D = torch.where(ov_eos.unsqueeze(1), (col == eos).unsqueeze(0), D)
-        D = torch.where(ov_pad.unsqueeze(1), (col == pad).unsqueeze(0), D)
         # boosts are computed as Python floats (like the reference) and only then cast to the dtype of `scores`
         f = self.length_reward_factor
         table = torch.tensor([BOOST * (f ** n) for n in range(width + len(self.THINK_PREFIX) + 1)], dtype=torch.float64).to(dt).to(dev)
         b_len = table[length]
         full, half = torch.tensor(BOOST, dtype=dt, device=dev), torch.tensor(BOOST / 2, dtype=dt, device=dev)
+        eos_rule = self.always_allow_eos and (self.variant == "causal" or width >= self.min_new_tokens)
+        e = torch.tensor(BOOST * (f ** width), dtype=torch.float64).to(dt).to(dev) if eos_rule else None
+        if scores.is_cuda and hasattr(self.index, "_h"):
+            return self._apply_on_device(scores, words, ngram, skip, ov_eos, ov_pad, b_len, full, half, e)
+        sh = torch.arange(32, device=dev, dtype=words.dtype)
+        D = ((words.unsqueeze(-1) >> sh) & 1).bool().view(R, -1)[:, :V]
+        D = torch.where(ov_eos.unsqueeze(1), (col == eos).unsqueeze(0), D)
+        D = torch.where(ov_pad.unsqueeze(1), (col == pad).unsqueeze(0), D)
         if self.variant == "qwen":
             add = torch.where(D.any(1), half, full)
         else:
@@ -309,13 +313,64 @@ class SoftBoostLogitsProcessor:
         m_ngram = torch.where(D, b_len.unsqueeze(1), torch.where(unig.unsqueeze(0), add.unsqueeze(1), z))
         m_uni = torch.where(unig, full, z).unsqueeze(0)
         mask = torch.where(ngram.unsqueeze(1), m_ngram, torch.where(skip.unsqueeze(1), z, m_uni))
-        if self.always_allow_eos:
-            e = torch.tensor(BOOST * (f ** width), dtype=torch.float64).to(dt).to(dev)
+        if e is not None:
             if self.variant == "causal":
                 mask[:, eos] = e
-            elif width >= self.min_new_tokens:
+            else:
                 mask[:, eos] = torch.where(skip, mask[:, eos], e)
         return scores + mask
+
+    def _apply_on_device(self, scores, words, ngram, skip, ov_eos, ov_pad, b_len, full, half, e):
+        """The arithmetic as ONE streaming kernel over bitmaps (fmidx_boost_logits): no [R, V] intermediate tensors.  Override
+        rows ({eos} under stop_at_count, {pad} after eos / pad) are patched into the [R, V/32] continuation bitmaps."""
+        import ctypes as C
+        from . import _native as N
+        R, V = scores.shape
+        dev = scores.device
+        eos, pad = self.eos_token_id, self.pad_token_id
+        ov = ov_eos | ov_pad
+        tok = torch.where(ov_eos, torch.full_like(ov_eos, eos, dtype=torch.int64), torch.full_like(ov_eos, pad, dtype=torch.int64))
+        one = torch.ones((), dtype=torch.int64, device=dev)
+        bit = torch.bitwise_left_shift(one, tok & 31)
+        bit = torch.where(bit >= 2 ** 31, bit - 2 ** 32, bit).to(torch.int32)  # bit 31 lives in the sign of the int32 word
+        words = torch.where(ov.unsqueeze(1), torch.zeros_like(words), words)
+        rows = torch.arange(R, device=dev)
+        in_vocab = ov & (tok >= 0) & (tok < V)
+        patched = torch.where(in_vocab, bit, words[rows, (tok >> 5).clamp(0, words.shape[1] - 1)])
+        words[rows, (tok >> 5).clamp(0, words.shape[1] - 1)] = patched
+        words = words.contiguous()
+        nd = torch.empty(R, dtype=torch.int32, device=dev)
+        sptr = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        L = N.lib()
+        N.check(L.fmidx_mask_popcount(self.index._h, C.c_void_p(words.data_ptr()), R, V, C.c_void_p(nd.data_ptr()), sptr))
+        kind = torch.where(ngram, 2, torch.where(skip, 0, 1)).to(torch.int32)
+        vd = b_len.to(torch.float32).contiguous()
+        vu_ne = half.to(torch.float32).expand(R).contiguous()
+        if self.variant == "qwen":
+            vu_e = full.to(torch.float32).expand(R).contiguous()
+        else:
+            vu_e = torch.where(ngram, half.to(torch.float32), full.to(torch.float32)).contiguous()
+        ve = (e.to(torch.float32) if e is not None else torch.tensor(float("nan"), device=dev)).expand(R).contiguous()
+        ub = self._unigram_words(dev, V)
+        scores = scores.contiguous()
+        out = torch.empty_like(scores)
+        code = N.DTYPE_CODES[str(scores.dtype).replace("torch.", "")]
+        N.check(L.fmidx_boost_logits(self.index._h, C.c_void_p(scores.data_ptr()), C.c_void_p(out.data_ptr()), code, scores.stride(0), R, V,
+                                     C.c_void_p(words.data_ptr()), C.c_void_p(nd.data_ptr()), C.c_void_p(ub.data_ptr()),
+                                     C.c_void_p(kind.data_ptr()), C.c_void_p(vd.data_ptr()), C.c_void_p(vu_ne.data_ptr()),
+                                     C.c_void_p(vu_e.data_ptr()), C.c_void_p(ve.data_ptr()), eos, sptr))
+        return out
+
+    def _unigram_words(self, device, V):
+        """The corpus unigrams (index.occurring_distinct) as a resident [ceil(V/32)] int32 bitmap."""
+        key = ("words", str(device), V)
+        if key not in self._unigrams:
+            import numpy as np
+            w = np.zeros((V + 31) // 32, dtype=np.uint32)
+            t = np.asarray([t for t in self.index.occurring_distinct if 0 <= t < V], dtype=np.int64)
+            np.bitwise_or.at(w, t >> 5, (np.uint32(1) << (t & 31).astype(np.uint32)))
+            self._unigrams[key] = torch.from_numpy(w.view(np.int32)).to(device)
+        return self._unigrams[key]
 
 
 class CausalIndexBasedLogitsProcessor(SoftBoostLogitsProcessor):

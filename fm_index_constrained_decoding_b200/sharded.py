@@ -209,9 +209,9 @@ class ShardStep:
         x = C.c_void_p()
         N.check(L.fmidx_shard_create(index._h, self.world, self.rank, B, vocab, n_sets, C.byref(x)))
         self._x = x
-        # handle exchange (plumbing): kind 0 = bitmaps of a set, 1 = inbox of a set, 2 = the flag block
+        # handle exchange (plumbing): kind 0 = bitmap buffer, 1 = inbox (two of each per set: steps ping-pong), 2 = the flag block
         mine = []
-        for kind, sets in ((0, range(n_sets)), (1, range(n_sets)), (2, (0,))):
+        for kind, sets in ((0, range(2 * n_sets)), (1, range(2 * n_sets)), (2, (0,))):
             for i in sets:
                 hd = (C.c_ubyte * 64)()
                 N.check(L.fmidx_shard_export(x, i, kind, hd))
@@ -224,11 +224,16 @@ class ShardStep:
             for kind, i, hb in items:
                 N.check(L.fmidx_shard_import(x, i, kind, r, (C.c_ubyte * 64).from_buffer_copy(hb)))
         N.check(L.fmidx_shard_ready(x))
-        self.own_masks, self.counts, self.streams = [], [], []
+        self.own_masks, self.counts, self.streams, self._ptrs = [], [], [], []
         for i in range(n_sets):
-            pm, pc, ps = C.c_void_p(), C.c_void_p(), C.c_void_p()
-            N.check(L.fmidx_shard_result(x, i, C.byref(pm), C.byref(pc), C.byref(ps)))
-            self.own_masks.append(torch.as_tensor(_RawCuda(pm.value, self.own * self.words), device=dev).view(self.own, self.words))
+            views = []
+            self._ptrs.append([])
+            for par in (0, 1):  # step k of a set writes bitmap buffer k & 1
+                pm, pc, ps = C.c_void_p(), C.c_void_p(), C.c_void_p()
+                N.check(L.fmidx_shard_result(x, i, par, C.byref(pm), C.byref(pc), C.byref(ps)))
+                views.append(torch.as_tensor(_RawCuda(pm.value, self.own * self.words), device=dev).view(self.own, self.words))
+                self._ptrs[i].append(pm.value)
+            self.own_masks.append(views)
             self.counts.append(torch.as_tensor(_RawCuda(pc.value, B, "<i8"), device=dev))
             self.streams.append(torch.cuda.ExternalStream(ps.value, device=dev))
         torch.cuda.synchronize()
@@ -236,13 +241,23 @@ class ShardStep:
 
     def step(self, i, toks, offs, sp, ep, shift=10, stream=None):
         """Enqueue the step of buffer set i (stream: a torch stream, default the set's own).  sp/ep (int64 [B], CUDA)
-        receive this shard's ranges.  Returns (final bitmaps of the owned rows [B/world, words], total counts [B])."""
+        receive this shard's ranges.  Returns (final bitmaps of the owned rows [B/world, words], total counts [B]); the
+        bitmaps stay valid until the set's second-next step (the sets ping-pong between two buffers), the counts until
+        its next step."""
         import ctypes as C
         from . import _native as N
         sptr = C.c_void_p(stream.cuda_stream) if stream is not None else None
         N.check(self._L.fmidx_shard_step(self._x, i, C.c_void_p(toks.data_ptr()), C.c_void_p(offs.data_ptr()), shift,
                                          C.c_void_p(sp.data_ptr()), C.c_void_p(ep.data_ptr()), sptr))
-        return self.own_masks[i], self.counts[i]
+        return self.result(i)
+
+    def result(self, i):
+        """(owned bitmaps, total counts) of the step issued last on set i (also after a direct fmidx_shard_step call)."""
+        import ctypes as C
+        from . import _native as N
+        pm = C.c_void_p()
+        N.check(self._L.fmidx_shard_result(self._x, i, -1, C.byref(pm), None, None))
+        return self.own_masks[i][self._ptrs[i].index(pm.value)], self.counts[i]
 
     def submit(self, i, toks, offs, sp, ep, counts=None, n_distinct_own=None, shift=10):
         """Host-buffer form on the set's own stream (pinned CPU tensors in and out); wait(i) blocks until they hold the

@@ -134,30 +134,34 @@ int fmidx_distinct_mask_batch_occ(fmidx_t *h, const uint64_t *d_sp, const uint64
 /* ---- document-sharded step; no reference counterpart: the reference's only parallelism is one
  * std::async per range (fm_index.cpp:146-166) --------------------------------------------------------------------
  * One process per GPU, each holding the index of its own document shard; the B prefixes of a step are replicated.
- * A shard context owns n_sets (<= 16) independent buffer sets in peer-visible memory (CUDA IPC): [B][ceil(vocab/32)]
- * bitmaps, an inbox with one slot per shard (slice-occupancy words + occurrence counts), data / ack flags.  Set-up: every
- * rank creates its context, exports the 64-byte handles of its buffers (kind 0 = bitmaps of a set, 1 = inbox of a set,
- * 2 = the flag block of all sets), the host language exchanges them (torch.distributed all_gather_object), every rank
- * imports every peer's, then fmidx_shard_ready.
+ * A shard context owns n_sets (<= 16) independent buffer sets in peer-visible memory (CUDA IPC); a set holds TWO
+ * [B][ceil(vocab/32)] bitmap buffers and TWO inboxes (one slot per shard: slice-occupancy words + occurrence counts), used
+ * alternately by consecutive steps, and one data flag per shard.  Set-up: every rank creates its context, exports the
+ * 64-byte handles of its buffers (kind 0 = bitmap buffer buf, 1 = inbox buf, buf = 2 * set + parity; 2 = the flag block),
+ * the host language exchanges them (torch.distributed all_gather_object), every rank imports every peer's, then
+ * fmidx_shard_ready.
  * fmidx_shard_step enqueues ONE whole step of set `set` on `stream` (NULL: the set's own stream) with five launches and
- * no NCCL: search (also zeroes the owned rows) -> enumeration into bitmaps + occupancy + counts (first waits on the GPU
- * for every shard's ack of the step that last used the set; the CTA that finishes last publishes the side data into
- * every shard's inbox and raises the data flags) -> per peer: wait for its data flag, pull its occupied 4096-token slices
- * over NVLink, OR them into the rows this rank owns; total counts; ack.  Afterwards (stream-ordered) rank r owns the final
- * bitmaps of prefixes [r*B/world, (r+1)*B/world) and the total occurrence counts of all B prefixes (fmidx_shard_result).
- * d_sp/d_ep receive THIS shard's ranges (ranges are shard-local and never reduced).  Steps on different sets may be in
- * flight on different streams; every rank must issue the same steps on the same sets in the same order.
+ * no NCCL: search -> enumeration into bitmaps + occupancy + counts (the CTA that finishes last publishes the side data
+ * into every shard's inbox and raises the data flags) -> per peer: wait for its data flag, pull its occupied 4096-token
+ * slices over NVLink, OR them into the rows this rank owns; total counts.  No acknowledgements: when this rank's pull of
+ * step k-1 has returned, every peer has published step k-1 and therefore finished its pull of step k-2, the last reader of
+ * the buffers step k overwrites.  Afterwards (stream-ordered) rank r owns the final bitmaps of prefixes
+ * [r*B/world, (r+1)*B/world) in the buffer of that step's parity and the total occurrence counts of all B prefixes
+ * (fmidx_shard_result; consume them before the set's second-next step).  d_sp/d_ep receive THIS shard's ranges (ranges are
+ * shard-local and never reduced).  Steps on different sets may be in flight on different streams; every rank must issue the
+ * same steps on the same sets in the same order.
  * fmidx_shard_submit / fmidx_shard_wait: host-buffer form on the set's own stream (H2D of the prefixes and D2H of the
  * ranges, total counts and distinct-token counts of the owned prefixes inside the call). */
 typedef struct fmidx_shard fmidx_shard_t;
 int fmidx_shard_create(fmidx_t *h, uint32_t world, uint32_t rank, size_t B, uint32_t vocab, uint32_t n_sets,
                        fmidx_shard_t **out);
-int fmidx_shard_export(fmidx_shard_t *x, uint32_t set, int kind, unsigned char handle[64]);
-int fmidx_shard_import(fmidx_shard_t *x, uint32_t set, int kind, uint32_t peer, const unsigned char handle[64]);
+int fmidx_shard_export(fmidx_shard_t *x, uint32_t buf, int kind, unsigned char handle[64]);
+int fmidx_shard_import(fmidx_shard_t *x, uint32_t buf, int kind, uint32_t peer, const unsigned char handle[64]);
 int fmidx_shard_ready(fmidx_shard_t *x);
 int fmidx_shard_step(fmidx_shard_t *x, uint32_t set, const int32_t *d_toks, const int64_t *d_offs, int64_t shift, uint64_t *d_sp,
                      uint64_t *d_ep, void *stream);
-int fmidx_shard_result(fmidx_shard_t *x, uint32_t set, uint32_t **d_own_masks, uint64_t **d_counts, void **stream);
+/* step number k (1, 2, ...) of a set writes bitmap buffer k & 1; parity 0 / 1 selects that buffer, -1 the one of the step issued last */
+int fmidx_shard_result(fmidx_shard_t *x, uint32_t set, int parity, uint32_t **d_own_masks, uint64_t **d_counts, void **stream);
 int fmidx_shard_submit(fmidx_shard_t *x, uint32_t set, const int32_t *toks, const int64_t *offs, int64_t shift, uint64_t *sp,
                        uint64_t *ep, uint64_t *counts, uint32_t *n_distinct_own);
 int fmidx_shard_wait(fmidx_shard_t *x, uint32_t set);
@@ -180,6 +184,19 @@ int fmidx_mask_logits(fmidx_t *h, const uint64_t *d_sp, const uint64_t *d_ep, si
                       uint32_t vocab, const void *d_logits, void *d_out, int dtype, int64_t row_stride,
                       const int32_t *d_override_tok, int32_t always_allow, const uint32_t *d_extra_masks,
                       uint32_t n_extra, uint32_t *d_mask_out, void *stream);
+/* Soft-boost arithmetic of the causal processors as ONE streaming kernel over bitmaps
+ * (document_constrained_generation_causal.py:137-178, _causal_qwen.py:159-212):  out[b,v] = logits[b,v] + m[b,v],
+ *   d_kind[b] == 0: m = 0;   == 1: m = d_vu_empty[b] on the corpus unigrams (bitmap d_unigram, [ceil(vocab/32)]);
+ *   == 2: m = d_vd[b] on the row's continuation bitmap d_dmask[b] ([B][ceil(vocab/32)], from fmidx_distinct_mask_batch /
+ *         fmidx_query_batch), and on the OTHER unigrams d_vu_nonempty[b], or d_vu_empty[b] when the row's bitmap is empty
+ *         (d_n_distinct[b] == 0, from fmidx_mask_popcount);
+ *   finally m[eos] = d_ve[b] unless d_ve[b] is NaN (kind 0 rows are never touched).
+ * The values are float32 holding numbers already rounded to the dtype of the logits; the sum is formed in fp32 and rounded
+ * once.  d_out may alias d_logits. */
+int fmidx_boost_logits(fmidx_t *h, const void *d_logits, void *d_out, int dtype, int64_t row_stride, size_t B, uint32_t vocab,
+                       const uint32_t *d_dmask, const uint32_t *d_n_distinct, const uint32_t *d_unigram, const int32_t *d_kind,
+                       const float *d_vd, const float *d_vu_nonempty, const float *d_vu_empty, const float *d_ve, int32_t eos,
+                       void *stream);
 /* bitmap + counts -> sparse ascending (token,count) lists (index.py:161-174 return shape).
  * d_list_offsets [B+1] must hold the exclusive prefix sums of the per-row popcounts, which
  * fmidx_mask_popcount computes into d_n ([B] u32). */
@@ -212,6 +229,14 @@ int fmidx_query_host_summary(fmidx_t *h, const int32_t *toks, const int64_t *off
 int fmidx_query_submit(fmidx_t *h, int slot, const int32_t *toks, const int64_t *offs, size_t B, int64_t shift,
                        uint32_t vocab, uint64_t *sp, uint64_t *ep, uint32_t *n_distinct);
 int fmidx_query_wait(fmidx_t *h, int slot);
+/* The same step as ONE CUDA-graph launch per batch: a slot prepared here owns pinned host staging buffers -- the caller
+ * writes a batch into *h_in ([offs: (B+1) int64][toks: up to max_tokens int32], offs[0] = 0, B fixed) and, after
+ * fmidx_query_graph_launch + fmidx_query_wait, reads *h_out ([sp: B u64][ep: B u64][n_distinct: B u32]).  The captured
+ * sequence is H2D of the input block -> search -> enumeration -> popcount -> D2H of the result block on the slot's
+ * stream; ten driver calls of fmidx_query_submit become one.  A prepared slot cannot be used with fmidx_query_submit. */
+int fmidx_query_graph_prepare(fmidx_t *h, int slot, size_t B, size_t max_tokens, int64_t shift, uint32_t vocab, void **h_in,
+                              void **h_out);
+int fmidx_query_graph_launch(fmidx_t *h, int slot);
 int fmidx_locate_host(fmidx_t *h, const uint64_t *rows, size_t n, uint64_t *pos);
 
 /* ---- introspection -------------------------------------------------------------------------- */

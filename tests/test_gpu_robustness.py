@@ -197,3 +197,49 @@ def test_wide_range_paths_agree_with_the_oracle(cuda, setting):
         assert torch.equal(got, torch.where(bits, lg + 0.0, torch.full_like(lg, float("-inf")))), (setting, dtp)
     for i in (0, 5, 100, vocab + 3):
         assert tuple(map(list, ix.get_distinct_count(int(osp[i]), int(oep[i])))) == tuple(map(list, o.get_distinct_count(int(osp[i]), int(oep[i]))))
+
+
+def test_graph_captured_host_pipeline(cuda):
+    """fmidx_query_graph_*: the captured step gives the oracle's ranges and distinct-token counts, over many replays (the two
+    captures alternate between the work-list counter pairs), with different batches per slot, and wide ranges in the mix."""
+    from fm_index_constrained_decoding_b200 import FMIndex
+    from fm_index_constrained_decoding_b200.index import GraphQuerySlots, ragged
+    from oracle.oracle import OracleFMIndex
+    rng = random.Random(41)
+    vocab = 400
+    weights = [1.0 / (r + 1) for r in range(vocab)]
+    docs = [rng.choices(range(vocab), weights=weights, k=rng.randint(100, 600)) + [EOS] for _ in range(200)]
+    o = OracleFMIndex()
+    o.initialize(docs)
+    ix = FMIndex()
+    ix.tune(scan_max=1024)
+    ix.initialize(docs, in_memory=True)
+    B, MAXTOK, NS = 256, 256 * 8, 3
+    gs = GraphQuerySlots(ix, NS, B, MAXTOK, V)
+    batches = []
+    for k in range(5):
+        seqs = [[rng.randrange(vocab)] if j % 7 == 0 else (lambda d, i: d[i:i + rng.randint(1, 8)])(rng.choice(docs), rng.randrange(50)) for j in range(B)]
+        toks, offs = ragged(seqs)
+        osp, oep, _, ond = o.query_batch(toks, offs, want_mask=True, vocab=V, nthreads=4)
+        batches.append((toks, offs, osp, oep, ond.astype(np.uint32)))
+    pending = [None] * NS
+    for step in range(4 * NS + 2):
+        i = step % NS
+        gs.wait(i)
+        if pending[i] is not None:
+            _, _, osp, oep, ond = batches[pending[i]]
+            assert (gs.sp[i] == osp).all() and (gs.ep[i] == oep).all() and (gs.n_distinct[i] == ond).all(), step
+        toks, offs = batches[step % len(batches)][:2]
+        gs.offs[i][:] = offs
+        gs.toks[i][:toks.size] = toks
+        gs.launch(i)
+        pending[i] = step % len(batches)
+    for i in range(NS):
+        gs.wait(i)
+        _, _, osp, oep, ond = batches[pending[i]]
+        assert (gs.sp[i] == osp).all() and (gs.ep[i] == oep).all() and (gs.n_distinct[i] == ond).all()
+    with pytest.raises(Exception):  # a captured slot refuses the eager submit
+        toks, offs = batches[0][:2]
+        sp = np.empty(B, np.uint64)
+        from fm_index_constrained_decoding_b200 import _native
+        _native.check(_native.lib().fmidx_query_submit(ix._h, 0, toks.ctypes.data, offs.ctypes.data, B, 10, V, sp.ctypes.data, sp.ctypes.data, None))
