@@ -403,21 +403,22 @@ class LocalEngine:
         self.d2h = B * (8 + 8 + 4)
 
     def setup_e2e_graph(self):
-        """The captured form: slot i's pinned staging buffer holds prefix batch i (NSLOT == number of batches), exactly like
-        the eager form rotates the same pinned batches; one cudaGraphLaunch per step does H2D + kernels + D2H."""
+        """The captured form: slot i's pinned staging buffer holds prefix batch i % 8, exactly like the eager form rotates the
+        same pinned batches; one cudaGraphLaunch per step does H2D + kernels + D2H.  BENCH_GSLOTS (16) steps in flight."""
         from fm_index_constrained_decoding_b200.index import GraphQuerySlots
-        assert len(self.qsets) <= 8
         hq = [(q.cpu().numpy(), offs.cpu().numpy()) for q, offs in self.qsets]
         self.g_maxtok = max(q.size for q, _ in hq)
-        self.gs = GraphQuerySlots(self.ix, len(hq), self.B, self.g_maxtok, VOCAB, first_slot=8)
-        for i, (q, offs) in enumerate(hq):
+        self.GSLOTS = int(os.environ.get("BENCH_GSLOTS", "16"))
+        self.gs = GraphQuerySlots(self.ix, self.GSLOTS, self.B, self.g_maxtok, VOCAB, first_slot=16)
+        for i in range(self.GSLOTS):
+            q, offs = hq[i % len(hq)]
             self.gs.offs[i][:] = offs
             self.gs.toks[i][:q.size] = q
         self.g_h2d = (self.B + 1) * 8 + self.g_maxtok * 4
         self._gl, self._gw, self._gh = self.gs._launch, self.gs._wait, self.ix._h
 
     def e2e_graph_step(self, k):
-        slot = 8 + k % self.gs.n
+        slot = 16 + k % self.GSLOTS
         if self._gw(self._gh, slot) != 0 or self._gl(self._gh, slot) != 0:
             self.N.check(-1)
 

@@ -61,6 +61,8 @@ SIGNATURES = {
     "fmidx_query_wait": (C.c_int, [p, C.c_int]),
     "fmidx_query_graph_prepare": (C.c_int, [p, C.c_int, sz, sz, i64, u32, C.POINTER(p), C.POINTER(p)]),
     "fmidx_query_graph_launch": (C.c_int, [p, C.c_int]),
+    "fmidx_query_graph_prepare_device": (C.c_int, [p, C.c_int, p, p, sz, i64, u32, p, p, p]),
+    "fmidx_query_graph_launch_on": (C.c_int, [p, C.c_int, p]),
     "fmidx_locate_host": (C.c_int, [p, p, sz, p]),
     "fmidx_info": (C.c_int, [p, C.POINTER(u64)]),
     "fmidx_debug_copy_sa": (C.c_int, [p, p, sz]),

@@ -200,6 +200,7 @@ int fmidx_tune(fmidx_t *h, const char *key, int64_t value) {
     if (!strcmp(key, "scan_max")) h->tune_scan_max = (uint32_t)std::min<int64_t>(std::max<int64_t>(value, 0), 1ll << 24);
     else if (!strcmp(key, "bytes_occ")) h->tune_bytes_occ = (int)value;
     else if (!strcmp(key, "unigram_table")) h->tune_unigram = value ? 1 : 0;
+    else if (!strcmp(key, "probe_phase")) h->tune_probe_phase = (int)value;
     else { fm_set_error("fmidx_tune: unknown key '%s'", key); return FMIDX_EINVAL; }
     return FMIDX_OK;
 }
@@ -599,8 +600,11 @@ int fmidx_query_batch(fmidx_t *h, int ws_slot, const int32_t *d_toks, const int6
     if (!d_sp || !d_ep) { fm_set_error("null argument"); return FMIDX_EINVAL; }
     // the search kernel also zeroes the mask rows (its stores are free: it is bound by its dependent-load chain)
     const bool kz = vocab != 0 && fm_search_can_zero(d_mask, vocab);
+    // probe_phase (measurement only, benchmarks/overlap_probe.py): 1 = search (+ row zeroing) alone, 2 = enumeration alone on the
+    // ranges already in d_sp / d_ep
+    if (h->tune_probe_phase != 2)
     FM_TRY(fm_launch_search(h, d_toks, d_offs, B, shift, d_sp, d_ep, 0, (cudaStream_t)stream, kz ? d_mask : nullptr, (vocab + 31u) >> 5));
-    if (!d_mask || vocab == 0) return FMIDX_OK;
+    if (!d_mask || vocab == 0 || h->tune_probe_phase == 1) return FMIDX_OK;
     h->mask_ws_override = &h->slots[ws_slot].ws;  // calls on different streams must not share the node lists
     struct Reset { fmidx_t *h; ~Reset() { h->mask_ws_override = nullptr; } } reset{h};
     return fm_launch_mask(h, d_sp, d_ep, B, shift, vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, d_mask, nullptr,
@@ -763,18 +767,50 @@ static int graph_sequence(fmidx_t *h, fmidx::Slot &sl, int64_t shift, uint32_t v
     const size_t B = sl.g_B;
     cudaStream_t s = sl.stream;
     const uint32_t words = (vocab + 31) / 32;
+    h->mask_ws_override = &sl.ws;
+    struct Reset { fmidx_t *h; ~Reset() { h->mask_ws_override = nullptr; } } reset{h};
+    if (sl.g_dev_mask) {  // device-resident form: the caller's buffers, no copies
+        const bool kz = fm_search_can_zero(sl.g_dev_mask, vocab);
+        FM_TRY(fm_launch_search(h, sl.g_dev_toks, sl.g_dev_offs, B, shift, sl.g_dev_sp, sl.g_dev_ep, 0, s, kz ? sl.g_dev_mask : nullptr, words));
+        return fm_launch_mask(h, sl.g_dev_sp, sl.g_dev_ep, B, shift, vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, sl.g_dev_mask,
+                              nullptr, s, nullptr, 0, ~(size_t)0, kz);
+    }
     int64_t *d_offs = (int64_t *)sl.g_din;
     int32_t *d_toks = (int32_t *)((char *)sl.g_din + (B + 1) * 8);
     uint64_t *d_sp = (uint64_t *)sl.g_dout, *d_ep = d_sp + B;
     uint32_t *d_n = (uint32_t *)(d_ep + B);
     uint32_t *d_mask = (uint32_t *)sl.mask.p;
     FM_CUDA(cudaMemcpyAsync(sl.g_din, sl.g_hin, (B + 1) * 8 + sl.g_maxtok * 4, cudaMemcpyHostToDevice, s));
-    FM_TRY(fm_launch_search(h, d_toks, d_offs, B, shift, d_sp, d_ep, 0, s, nullptr, words));
-    h->mask_ws_override = &sl.ws;
-    struct Reset { fmidx_t *h; ~Reset() { h->mask_ws_override = nullptr; } } reset{h};
-    FM_TRY(fm_launch_mask(h, d_sp, d_ep, B, shift, vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, d_mask, nullptr, s));
+    // the search kernel also zeroes the mask rows (as in fmidx_query_batch)
+    const bool kz = fm_search_can_zero(d_mask, vocab);
+    FM_TRY(fm_launch_search(h, d_toks, d_offs, B, shift, d_sp, d_ep, 0, s, kz ? d_mask : nullptr, words));
+    FM_TRY(fm_launch_mask(h, d_sp, d_ep, B, shift, vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, d_mask, nullptr, s, nullptr, 0,
+                          ~(size_t)0, kz));
     FM_TRY(fm_launch_popcount(h, d_mask, B, vocab, d_n, s));
     FM_CUDA(cudaMemcpyAsync(sl.g_hout, sl.g_dout, B * 20, cudaMemcpyDeviceToHost, s));
+    return FMIDX_OK;
+}
+
+// eager sizing pass + the two captures (the mask kernels alternate between two work-list counter pairs)
+static int graph_capture(fmidx_t *h, fmidx::Slot &sl, int64_t shift, uint32_t vocab) {
+    // one eager pass sizes every workspace (nothing may be allocated while a stream is being captured)
+    FM_TRY(graph_sequence(h, sl, shift, vocab));
+    FM_CUDA(cudaStreamSynchronize(sl.stream));
+    for (int e = 0; e < 2; ++e) {
+        const uint64_t l0 = g_fm_launches.load();
+        FM_CUDA(cudaStreamBeginCapture(sl.stream, cudaStreamCaptureModeThreadLocal));
+        int rc = graph_sequence(h, sl, shift, vocab);
+        cudaGraph_t g = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(sl.stream, &g);
+        if (rc != FMIDX_OK) { if (g) cudaGraphDestroy(g); return rc; }
+        if (ce != cudaSuccess) { fm_set_error("stream capture failed: %s", cudaGetErrorString(ce)); return FMIDX_ECUDA; }
+        ce = cudaGraphInstantiate(&sl.gexec[e], g, 0);
+        cudaGraphDestroy(g);
+        if (ce != cudaSuccess) { fm_set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); return FMIDX_ECUDA; }
+        sl.g_launches = g_fm_launches.load() - l0;
+        g_fm_launches.store(l0);  // captured, not launched
+    }
+    sl.g_step = 0;
     return FMIDX_OK;
 }
 
@@ -796,26 +832,34 @@ int fmidx_query_graph_prepare(fmidx_t *h, int slot, size_t B, size_t max_tokens,
     FM_CUDA(cudaMalloc(&sl.g_dout, B * 20 + 16));
     memset(sl.g_hin, 0, in_bytes);  // B empty prefixes: a valid input
     FM_TRY(fm_scratch(h, sl.mask, B * (size_t)((vocab + 31) / 32) * 4, false));
-    // one eager pass sizes every workspace (nothing may be allocated while a stream is being captured)
-    FM_TRY(graph_sequence(h, sl, shift, vocab));
-    FM_CUDA(cudaStreamSynchronize(sl.stream));
-    for (int e = 0; e < 2; ++e) {
-        const uint64_t l0 = g_fm_launches.load();
-        FM_CUDA(cudaStreamBeginCapture(sl.stream, cudaStreamCaptureModeThreadLocal));
-        int rc = graph_sequence(h, sl, shift, vocab);
-        cudaGraph_t g = nullptr;
-        cudaError_t ce = cudaStreamEndCapture(sl.stream, &g);
-        if (rc != FMIDX_OK) { if (g) cudaGraphDestroy(g); return rc; }
-        if (ce != cudaSuccess) { fm_set_error("stream capture failed: %s", cudaGetErrorString(ce)); return FMIDX_ECUDA; }
-        ce = cudaGraphInstantiate(&sl.gexec[e], g, 0);
-        cudaGraphDestroy(g);
-        if (ce != cudaSuccess) { fm_set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); return FMIDX_ECUDA; }
-        sl.g_launches = g_fm_launches.load() - l0;
-        g_fm_launches.store(l0);  // captured, not launched
-    }
-    sl.g_step = 0;
+    FM_TRY(graph_capture(h, sl, shift, vocab));
     *h_in = sl.g_hin;
     *h_out = sl.g_hout;
+    return FMIDX_OK;
+}
+
+int fmidx_query_graph_prepare_device(fmidx_t *h, int slot, const int32_t *d_toks, const int64_t *d_offs, size_t B, int64_t shift,
+                                     uint32_t vocab, uint64_t *d_sp, uint64_t *d_ep, uint32_t *d_mask) {
+    FM_TRY(enter(h, true));
+    if (slot < 0 || slot >= FMIDX_SLOTS) { fm_set_error("slot must be 0..%d", FMIDX_SLOTS - 1); return FMIDX_EINVAL; }
+    if (!B || !vocab || !d_toks || !d_offs || !d_sp || !d_ep || !d_mask) { fm_set_error("bad argument"); return FMIDX_EINVAL; }
+    fmidx::Slot &sl = h->slots[slot];
+    if (sl.gexec[0]) { fm_set_error("slot %d already holds a captured step", slot); return FMIDX_ESTATE; }
+    if (!sl.stream) FM_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    FM_CUDA(cudaStreamSynchronize(sl.stream));
+    sl.g_B = B;
+    sl.g_dev_toks = d_toks; sl.g_dev_offs = d_offs; sl.g_dev_sp = d_sp; sl.g_dev_ep = d_ep; sl.g_dev_mask = d_mask;
+    int rc = graph_capture(h, sl, shift, vocab);
+    if (rc != FMIDX_OK) sl.g_dev_mask = nullptr;
+    return rc;
+}
+
+int fmidx_query_graph_launch_on(fmidx_t *h, int slot, void *stream) {
+    if (!h) { fm_set_error("null handle"); return FMIDX_EINVAL; }
+    if (slot < 0 || slot >= FMIDX_SLOTS || !h->slots[slot].gexec[0]) { fm_set_error("slot %d holds no captured step", slot); return FMIDX_ESTATE; }
+    fmidx::Slot &sl = h->slots[slot];
+    FM_CUDA(cudaGraphLaunch(sl.gexec[sl.g_step++ & 1u], stream ? (cudaStream_t)stream : sl.stream));
+    g_fm_launches.fetch_add(sl.g_launches, std::memory_order_relaxed);
     return FMIDX_OK;
 }
 

@@ -13,7 +13,7 @@
 #include "../../include/fmidx.h"
 #include "fmidx_layout.cuh"
 
-#define FMIDX_SLOTS 16  // pipelined slots / scratch workspaces / buffer sets per handle
+#define FMIDX_SLOTS 32  // pipelined slots / scratch workspaces / buffer sets per handle
 
 void fm_set_error(const char *fmt, ...);
 extern std::atomic<uint64_t> g_fm_launches;
@@ -87,6 +87,9 @@ struct fmidx {
         cudaGraphExec_t gexec[2] = {nullptr, nullptr};
         void *g_hin = nullptr, *g_hout = nullptr;   // pinned host staging: [offs | toks] in, [sp | ep | n_distinct] out
         void *g_din = nullptr, *g_dout = nullptr;
+        // device-resident captured form (fmidx_query_graph_prepare_device): the caller's buffers, no copies
+        const int32_t *g_dev_toks = nullptr; const int64_t *g_dev_offs = nullptr;
+        uint64_t *g_dev_sp = nullptr, *g_dev_ep = nullptr; uint32_t *g_dev_mask = nullptr;
         size_t g_B = 0, g_maxtok = 0;
         uint64_t g_launches = 0;
         uint32_t g_step = 0;
@@ -97,6 +100,7 @@ struct fmidx {
     uint32_t tune_scan_max = 16384;  // ranges of up to this many rows are read off the resident BWT ($FMIDX_SCAN_MAX)
     int tune_bytes_occ = 5;          // CTAs per SM of the persistent k_mask_bytes grid ($FMIDX_BYTES_OCC)
     int tune_unigram = 1;            // use the unigram continuation table at query time ($FMIDX_UNIGRAM_TABLE)
+    int tune_probe_phase = 0;        // measurement only: fmidx_query_batch runs one phase alone (1 search, 2 enumeration)
     uint32_t tune_unigram_max = 1024;  // table entries built at most ($FMIDX_UNIGRAM_MAX; 0: none)
 };
 

@@ -269,7 +269,7 @@ class FMIndex(_FMIndex):
 
     def query_batch(self, toks, offs, vocab, shift=SHIFT, ws_slot=0, out=None):
         """Ranges AND allowed-token bitmaps of B ragged prefixes in one call (fmidx_query_batch): returns
-        (sp, ep, mask).  Batches issued on different CUDA streams must use different ws_slot values (0..15)."""
+        (sp, ep, mask).  Batches issued on different CUDA streams must use different ws_slot values (0..31)."""
         torch = _torch()
         B = offs.numel() - 1
         words = (vocab + 31) // 32
@@ -330,7 +330,7 @@ class GraphQuerySlots:
     launch(i) enqueues H2D -> search -> enumeration -> popcount -> D2H on the slot's stream and returns."""
 
     def __init__(self, index, n_slots, B, max_tokens, vocab, shift=SHIFT, first_slot=0):
-        """first_slot: the handle's slots first_slot .. first_slot + n_slots - 1 are taken (16 per handle; a slot is either
+        """first_slot: the handle's slots first_slot .. first_slot + n_slots - 1 are taken (32 per handle; a slot is either
         captured or used by fmidx_query_submit / as the ws_slot of fmidx_query_batch, never both)."""
         self.index, self.n, self.B, self.first = index, n_slots, B, first_slot
         self.offs, self.toks, self.sp, self.ep, self.n_distinct = [], [], [], [], []
@@ -347,6 +347,43 @@ class GraphQuerySlots:
 
     def launch(self, i):
         if self._launch(self.index._h, self.first + i) != 0:
+            N.check(-1)
+
+    def wait(self, i):
+        if self._wait(self.index._h, self.first + i) != 0:
+            N.check(-1)
+
+
+class DeviceGraphSteps:
+    """The device-resident query step (search + enumeration into a mask buffer) captured once per slot for FIXED device
+    buffers and replayed with one CUDA-graph launch (fmidx_query_graph_prepare_device / fmidx_query_graph_launch_on): the
+    serving-loop form of FMIndex.query_batch.  Slot i owns toks[i] (int32 [max_tokens]), offs[i] (int64 [B+1], offs[0] = 0),
+    sp[i], ep[i] (int64 [B]) and mask[i] (int32 [B, words]); the caller rewrites toks / offs in place between replays."""
+
+    def __init__(self, index, n_slots, B, max_tokens, vocab, shift=SHIFT, first_slot=0, buffers=None):
+        import torch
+        dev = torch.device("cuda", index.device_index)
+        words = (vocab + 31) // 32
+        self.index, self.n, self.B, self.first = index, n_slots, B, first_slot
+        if buffers is None:
+            buffers = [(torch.zeros(max_tokens, dtype=torch.int32, device=dev), torch.zeros(B + 1, dtype=torch.int64, device=dev))
+                       for _ in range(n_slots)]
+        self.toks = [b[0] for b in buffers]
+        self.offs = [b[1] for b in buffers]
+        self.sp = [torch.empty(B, dtype=torch.int64, device=dev) for _ in range(n_slots)]
+        self.ep = [torch.empty(B, dtype=torch.int64, device=dev) for _ in range(n_slots)]
+        self.mask = [torch.empty((B, words), dtype=torch.int32, device=dev) for _ in range(n_slots)]
+        L = N.lib()
+        for i in range(n_slots):
+            N.check(L.fmidx_query_graph_prepare_device(index._h, first_slot + i, C.c_void_p(self.toks[i].data_ptr()),
+                                                       C.c_void_p(self.offs[i].data_ptr()), B, shift, vocab,
+                                                       C.c_void_p(self.sp[i].data_ptr()), C.c_void_p(self.ep[i].data_ptr()),
+                                                       C.c_void_p(self.mask[i].data_ptr())))
+        self._launch, self._wait = L.fmidx_query_graph_launch_on, L.fmidx_query_wait
+
+    def launch(self, i, stream=None):
+        """Replay slot i's step on `stream` (a torch stream; None: the slot's own stream, see wait)."""
+        if self._launch(self.index._h, self.first + i, C.c_void_p(stream.cuda_stream) if stream is not None else None) != 0:
             N.check(-1)
 
     def wait(self, i):

@@ -121,7 +121,7 @@ int fmidx_distinct_mask_batch(fmidx_t *h, const uint64_t *d_sp, const uint64_t *
 /* One decoding step's lookups for B beams in ONE call: fmidx_search_batch followed by
  * fmidx_distinct_mask_batch on the same stream (what index.py:93-131 `get_range` + index.py:146-159
  * `get_distinct_count` do per beam in document_constrained_generation_vllm.py:72-137), d_sp/d_ep and d_mask as
- * in those two calls (d_mask NULL or vocab 0: ranges only).  ws_slot (0..15) selects the scratch workspace the
+ * in those two calls (d_mask NULL or vocab 0: ranges only).  ws_slot (0..31) selects the scratch workspace the
  * enumeration uses: calls that may run concurrently on DIFFERENT streams must use different slots, calls that
  * share a slot must be stream-ordered.  The slots are the ones fmidx_query_submit uses: do not mix the two on one
  * slot number. */
@@ -134,7 +134,7 @@ int fmidx_distinct_mask_batch_occ(fmidx_t *h, const uint64_t *d_sp, const uint64
 /* ---- document-sharded step; no reference counterpart: the reference's only parallelism is one
  * std::async per range (fm_index.cpp:146-166) --------------------------------------------------------------------
  * One process per GPU, each holding the index of its own document shard; the B prefixes of a step are replicated.
- * A shard context owns n_sets (<= 16) independent buffer sets in peer-visible memory (CUDA IPC); a set holds TWO
+ * A shard context owns n_sets (<= 32) independent buffer sets in peer-visible memory (CUDA IPC); a set holds TWO
  * [B][ceil(vocab/32)] bitmap buffers and TWO inboxes (one slot per shard: slice-occupancy words + occurrence counts), used
  * alternately by consecutive steps, and one data flag per shard.  Set-up: every rank creates its context, exports the
  * 64-byte handles of its buffers (kind 0 = bitmap buffer buf, 1 = inbox buf, buf = 2 * set + parity; 2 = the flag block),
@@ -223,7 +223,7 @@ int fmidx_query_host(fmidx_t *h, const int32_t *toks, const int64_t *offs, size_
  * receives the ranges and n_distinct[b] = number of distinct next tokens of prefix b */
 int fmidx_query_host_summary(fmidx_t *h, const int32_t *toks, const int64_t *offs, size_t B, int64_t shift,
                              uint32_t vocab, uint64_t *sp, uint64_t *ep, uint32_t *n_distinct);
-/* pipelined form of fmidx_query_host_summary: up to 16 batches in flight, each in its own slot (own stream,
+/* pipelined form of fmidx_query_host_summary: up to 32 batches in flight, each in its own slot (own stream,
  * buffers and workspace).  submit enqueues H2D copies, kernels and D2H copies and returns; wait blocks until the
  * slot's host buffers (which should be pinned) hold the results.  n_distinct may be NULL (ranges only). */
 int fmidx_query_submit(fmidx_t *h, int slot, const int32_t *toks, const int64_t *offs, size_t B, int64_t shift,
@@ -237,6 +237,15 @@ int fmidx_query_wait(fmidx_t *h, int slot);
 int fmidx_query_graph_prepare(fmidx_t *h, int slot, size_t B, size_t max_tokens, int64_t shift, uint32_t vocab, void **h_in,
                               void **h_out);
 int fmidx_query_graph_launch(fmidx_t *h, int slot);
+/* The device-resident step (what fmidx_query_batch enqueues: search + row zeroing -> enumeration into d_mask) captured
+ * once for FIXED device buffers -- the serving-loop pattern: the caller rewrites d_toks / d_offs in place (B fixed,
+ * offs[0] = 0) and replays.  fmidx_query_graph_launch_on replays the slot's captured step on `stream` (NULL: the slot's
+ * own stream, which fmidx_query_wait synchronises); replays of ONE slot must be stream-ordered, different slots are
+ * independent.  Replaces four kernel launches per step by one graph launch (the step is otherwise bound by the host's
+ * launch rate).  No reference counterpart (the reference issues one SWIG call per token, index.py:103-114). */
+int fmidx_query_graph_prepare_device(fmidx_t *h, int slot, const int32_t *d_toks, const int64_t *d_offs, size_t B, int64_t shift,
+                                     uint32_t vocab, uint64_t *d_sp, uint64_t *d_ep, uint32_t *d_mask);
+int fmidx_query_graph_launch_on(fmidx_t *h, int slot, void *stream);
 int fmidx_locate_host(fmidx_t *h, const uint64_t *rows, size_t n, uint64_t *pos);
 
 /* ---- introspection -------------------------------------------------------------------------- */

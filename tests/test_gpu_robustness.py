@@ -243,3 +243,46 @@ def test_graph_captured_host_pipeline(cuda):
         sp = np.empty(B, np.uint64)
         from fm_index_constrained_decoding_b200 import _native
         _native.check(_native.lib().fmidx_query_submit(ix._h, 0, toks.ctypes.data, offs.ctypes.data, B, 10, V, sp.ctypes.data, sp.ctypes.data, None))
+
+
+def test_graph_captured_device_step(cuda):
+    """fmidx_query_graph_prepare_device / _launch_on: the device-resident step captured for fixed buffers gives the oracle's
+    ranges and bitmaps over many replays, with the inputs rewritten in place between replays, on the slot's own stream and on
+    a caller's stream."""
+    from fm_index_constrained_decoding_b200 import FMIndex
+    from fm_index_constrained_decoding_b200.index import DeviceGraphSteps, ragged
+    from oracle.oracle import OracleFMIndex
+    rng = random.Random(43)
+    vocab = 400
+    weights = [1.0 / (r + 1) for r in range(vocab)]
+    docs = [rng.choices(range(vocab), weights=weights, k=rng.randint(100, 600)) + [EOS] for _ in range(200)]
+    o = OracleFMIndex()
+    o.initialize(docs)
+    ix = FMIndex()
+    ix.tune(scan_max=1024)
+    ix.initialize(docs, in_memory=True)
+    B, MAXTOK, NS = 256, 256 * 8, 2
+    gs = DeviceGraphSteps(ix, NS, B, MAXTOK, V, first_slot=20)
+    batches = []
+    for k in range(4):
+        seqs = [[rng.randrange(vocab)] if j % 5 == 0 else (lambda d, i: d[i:i + rng.randint(1, 8)])(rng.choice(docs), rng.randrange(50)) for j in range(B)]
+        toks, offs = ragged(seqs)
+        osp, oep, om, _ = o.query_batch(toks, offs, want_mask=True, vocab=V, nthreads=4)
+        batches.append((torch.from_numpy(toks), torch.from_numpy(offs), osp.astype(np.int64), oep.astype(np.int64), om.view(np.int32)))
+    side = torch.cuda.Stream()
+    for step in range(9):
+        i = step % NS
+        toks, offs, osp, oep, om = batches[step % len(batches)]
+        st = side if step % 3 == 2 else None
+        if st is None:
+            gs.wait(i)
+        else:
+            torch.cuda.synchronize()
+        with torch.cuda.stream(st if st is not None else torch.cuda.current_stream()):
+            gs.toks[i][:toks.numel()].copy_(toks)
+            gs.offs[i].copy_(offs)
+        torch.cuda.synchronize()
+        gs.launch(i, st)
+        torch.cuda.synchronize()
+        assert (gs.sp[i].cpu().numpy() == osp).all() and (gs.ep[i].cpu().numpy() == oep).all(), step
+        assert (gs.mask[i].cpu().numpy() == om.reshape(B, -1)).all(), step
