@@ -155,6 +155,7 @@ int fmidx_new(int device, fmidx_t **out) {
     h->tune_scan_max = (uint32_t)std::min<long>(std::max<long>(env_long("FMIDX_SCAN_MAX", 16384), 0), 1l << 24);
     h->tune_bytes_occ = (int)env_long("FMIDX_BYTES_OCC", 5);
     h->tune_unigram = env_long("FMIDX_UNIGRAM_TABLE", 1) ? 1 : 0;
+    h->tune_scalar_fast = env_long("FMIDX_SCALAR_FAST", 1) ? 1 : 0;
     h->tune_unigram_max = (uint32_t)std::min<long>(std::max<long>(env_long("FMIDX_UNIGRAM_MAX", 1024), 0), 65536);
     *out = h.release();
     return FMIDX_OK;
@@ -164,6 +165,8 @@ void fmidx_free(fmidx_t *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     fm_release_index(h);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->scalar_out) cudaFreeHost(h->scalar_out);
     for (auto &b : h->d_scratch) if (b.p) cudaFree(b.p);
     for (FmBuf *b : {&h->mask_ws, &h->mask_ws_host}) {
         if (b->last_use) { cudaEventSynchronize(b->last_use); cudaEventDestroy(b->last_use); }
@@ -201,6 +204,7 @@ int fmidx_tune(fmidx_t *h, const char *key, int64_t value) {
     else if (!strcmp(key, "bytes_occ")) h->tune_bytes_occ = (int)value;
     else if (!strcmp(key, "unigram_table")) h->tune_unigram = value ? 1 : 0;
     else if (!strcmp(key, "probe_phase")) h->tune_probe_phase = (int)value;
+    else if (!strcmp(key, "scalar_fast")) h->tune_scalar_fast = value ? 1 : 0;
     else { fm_set_error("fmidx_tune: unknown key '%s'", key); return FMIDX_EINVAL; }
     return FMIDX_OK;
 }
@@ -408,6 +412,7 @@ int fmidx_debug_copy_sa(fmidx_t *h, uint32_t *out, size_t cap) {
 
 int fmidx_backward_search_step(fmidx_t *h, uint64_t symbol, uint64_t low, uint64_t high, uint64_t out[2]) {
     FM_TRY(enter(h, true));
+    if (h->tune_scalar_fast) return fm_scalar_step(h, symbol, low, high, out);
     FM_TRY(fm_scratch(h, h->d_scratch[0], 64, false));
     FM_TRY(fm_scratch(h, h->h_scratch[0], 64, true));
     uint64_t *hp = (uint64_t *)h->h_scratch[0].p, *dp = (uint64_t *)h->d_scratch[0].p;
@@ -422,6 +427,11 @@ int fmidx_backward_search_step(fmidx_t *h, uint64_t symbol, uint64_t low, uint64
 
 int fmidx_backward_search_multi(fmidx_t *h, const uint64_t *query, size_t n, uint64_t out[2]) {
     FM_TRY(enter(h, true));
+    if (h->tune_scalar_fast && n <= (size_t)fm_scalar_max_tokens()) {
+        int64_t t[128];
+        for (size_t i = 0; i < n; ++i) t[i] = query[i] > 0x7FFFFFFFull ? -1 : (int64_t)query[i];  // -1: absent
+        return fm_scalar_search(h, t, (int)n, 0, 1, out);
+    }
     const size_t tb = (n + 4) * 4;
     FM_TRY(fm_scratch(h, h->d_scratch[0], tb + 64, false));
     FM_TRY(fm_scratch(h, h->h_scratch[0], tb + 64, true));
@@ -498,6 +508,11 @@ static int distinct_lists(fmidx *h, const uint64_t *lows, const uint64_t *highs,
 static int distinct_one(fmidx_t *h, uint64_t low, uint64_t high, bool with_counts, uint64_t *out, size_t cap, size_t *k) {
     FM_TRY(enter(h, true));
     if (!k) { fm_set_error("k is NULL"); return FMIDX_EINVAL; }
+    if (h->tune_scalar_fast) {
+        bool fallback = false;
+        int rc = fm_scalar_distinct(h, low, high, with_counts ? 1 : 0, out, cap, k, &fallback);
+        if (rc != FMIDX_OK || !fallback) return rc;
+    }
     std::vector<uint64_t> flat, offs;
     FM_TRY(distinct_lists(h, &low, &high, 1, with_counts, flat, offs));
     *k = flat.size();
@@ -527,6 +542,8 @@ int fmidx_distinct_count_multi(fmidx_t *h, const uint64_t *lows, const uint64_t 
 
 int fmidx_locate(fmidx_t *h, uint64_t row, uint64_t *out) {
     FM_TRY(enter(h, true));
+    if (!out) { fm_set_error("null argument"); return FMIDX_EINVAL; }
+    if (h->tune_scalar_fast) return fm_scalar_locate(h, row, out);
     FM_TRY(fm_scratch(h, h->d_scratch[0], 64, false));
     FM_TRY(fm_scratch(h, h->h_scratch[0], 64, true));
     uint64_t *hp = (uint64_t *)h->h_scratch[0].p, *dp = (uint64_t *)h->d_scratch[0].p;
@@ -771,7 +788,9 @@ static int graph_sequence(fmidx_t *h, fmidx::Slot &sl, int64_t shift, uint32_t v
     struct Reset { fmidx_t *h; ~Reset() { h->mask_ws_override = nullptr; } } reset{h};
     if (sl.g_dev_mask) {  // device-resident form: the caller's buffers, no copies
         const bool kz = fm_search_can_zero(sl.g_dev_mask, vocab);
+        if (h->tune_probe_phase != 2)  // probe_phase: measurement only (see fmidx_query_batch)
         FM_TRY(fm_launch_search(h, sl.g_dev_toks, sl.g_dev_offs, B, shift, sl.g_dev_sp, sl.g_dev_ep, 0, s, kz ? sl.g_dev_mask : nullptr, words));
+        if (h->tune_probe_phase == 1) return FMIDX_OK;
         return fm_launch_mask(h, sl.g_dev_sp, sl.g_dev_ep, B, shift, vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, sl.g_dev_mask,
                               nullptr, s, nullptr, 0, ~(size_t)0, kz);
     }
@@ -899,6 +918,16 @@ int fmidx_query_host_summary(fmidx_t *h, const int32_t *toks, const int64_t *off
 
 int fmidx_search_host(fmidx_t *h, const int32_t *toks, const int64_t *offs, size_t B, int64_t shift, uint64_t *sp,
                       uint64_t *ep) {
+    if (h && B == 1 && h->tune_scalar_fast && toks && offs && sp && ep && offs[0] == 0 && offs[1] >= 0 && offs[1] <= fm_scalar_max_tokens()) {
+        FM_TRY(enter(h, true));
+        int64_t t[128];
+        for (int64_t i = 0; i < offs[1]; ++i) t[i] = toks[i];
+        uint64_t r[2];
+        FM_TRY(fm_scalar_search(h, t, (int)offs[1], shift, 0, r));
+        sp[0] = r[0];
+        ep[0] = r[1];
+        return FMIDX_OK;
+    }
     return fmidx_query_host(h, toks, offs, B, shift, 0, sp, ep, nullptr);
 }
 

@@ -100,6 +100,11 @@ struct fmidx {
     uint32_t tune_scan_max = 16384;  // ranges of up to this many rows are read off the resident BWT ($FMIDX_SCAN_MAX)
     int tune_bytes_occ = 5;          // CTAs per SM of the persistent k_mask_bytes grid ($FMIDX_BYTES_OCC)
     int tune_unigram = 1;            // use the unigram continuation table at query time ($FMIDX_UNIGRAM_TABLE)
+    // scalar calls: result block in mapped pinned host memory + the sequence number of the last call
+    void *scalar_out = nullptr;
+    uint32_t scalar_seq = 0;
+    size_t scalar_cap_u64 = 0;
+    int tune_scalar_fast = 1;        // scalar calls take the zero-copy single-launch kernels ($FMIDX_SCALAR_FAST)
     int tune_probe_phase = 0;        // measurement only: fmidx_query_batch runs one phase alone (1 search, 2 enumeration)
     uint32_t tune_unigram_max = 1024;  // table entries built at most ($FMIDX_UNIGRAM_MAX; 0: none)
 };
@@ -141,5 +146,11 @@ int fm_launch_gather_probe(fmidx *h, int unit_bytes, size_t n_loads, double *out
 int fm_launch_compact(fmidx *h, const uint32_t *d_mask, const uint32_t *d_counts, size_t B, uint32_t vocab,
                       const uint64_t *d_offs, int64_t *d_tokens, uint64_t *d_cnts, cudaStream_t s);
 int fm_launch_locate(fmidx *h, const uint64_t *d_rows, size_t n, uint64_t *d_pos, cudaStream_t s);
+// scalar (batch 1) calls on h->stream: arguments as kernel parameters, results polled from mapped pinned host memory
+int fm_scalar_max_tokens();
+int fm_scalar_search(fmidx *h, const int64_t *toks, int n, int64_t shift, int raw, uint64_t res[2]);
+int fm_scalar_step(fmidx *h, uint64_t sym, uint64_t low, uint64_t high, uint64_t res[2]);
+int fm_scalar_locate(fmidx *h, uint64_t row, uint64_t *pos);
+int fm_scalar_distinct(fmidx *h, uint64_t low, uint64_t high, int with_counts, uint64_t *dst, size_t cap, size_t *k, bool *fallback);
 int fm_launch_extract(fmidx *h, const uint64_t *d_begin, const uint64_t *d_end, size_t n, uint64_t max_len,
                       uint64_t *d_out, uint64_t *d_len, cudaStream_t s);

@@ -43,21 +43,28 @@ __device__ __forceinline__ void fm_st_release_sys(uint32_t *p, uint32_t v) {
 // RAW=true  : FMIndex::backward_search_multi semantics (fm_index.cpp:55-65; no guards, an absent
 //             symbol gives l=1,r=0 and the arithmetic just continues)
 // =================================================================================================
-template <bool RAW>
-__global__ void __launch_bounds__(128) k_search(FmDev ix, const int32_t *__restrict__ toks,
-                                                const int64_t *__restrict__ offs, uint32_t B, int64_t shift,
-                                                uint64_t *__restrict__ sp, uint64_t *__restrict__ ep,
-                                                uint32_t *__restrict__ zero_rows, uint32_t zero_words, uint32_t zero_lo,
-                                                uint32_t zero_n) {
+// token sources of the search: the batch's token array in global memory / the tokens of ONE prefix handed over as kernel
+// parameters (scalar calls: no H2D copy in front of the launch)
+struct FmToksGlobal {
+    const int32_t *__restrict__ p;
+    __device__ __forceinline__ int32_t at(int64_t i) const { return p[i]; }
+};
+#define FM_SCALAR_MAX_TOKENS 96
+struct FmToksParam {
+    int32_t t[FM_SCALAR_MAX_TOKENS];
+};
+struct FmToksShared {
+    const int32_t *p;  // shared memory
+    __device__ __forceinline__ int32_t at(int64_t i) const { return p[i]; }
+};
+
+// the search of prefix q by its 16 lanes (whole warps call this; q >= B: idle lanes)
+template <bool RAW, class Toks>
+__device__ __forceinline__ void fm_search_one(const FmDev &ix, const Toks toks, int64_t o0, int len, bool valid, uint32_t q, int64_t shift,
+                                              uint64_t *__restrict__ sp, uint64_t *__restrict__ ep,
+                                              uint32_t *__restrict__ zero_rows, uint32_t zero_words, uint32_t zero_lo,
+                                              uint32_t zero_n) {
     const int lane = threadIdx.x & 31, sub = lane & 7, half = (lane >> 3) & 1;
-    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
-    const bool valid = q < B;
-    int64_t o0 = 0;
-    int len = 0;
-    if (valid) {
-        o0 = offs[q];
-        len = (int)(offs[q + 1] - o0);
-    }
     // fmidx_query_batch: the mask row of this prefix is zeroed HERE (16 lanes, 16-byte stores, issued before the
     // dependent-load chain starts and never waited for), so the enumeration kernels find pre-zeroed rows and the
     // latency-bound search hides the 16 KB of store traffic per prefix.  zero_words % 4 == 0 and a 16-byte aligned
@@ -79,12 +86,12 @@ __global__ void __launch_bounds__(128) k_search(FmDev ix, const int32_t *__restr
     // 5 per remaining token.
     const bool accel = !RAW && ix.text != nullptr && ix.sa_dens == 1 && ix.isa_dens == 1;
     int t_stop = -1;  // >= 0: range fell to <= 16 rows after token t_stop-1; tokens t_stop.. are pending
-    int32_t tok_next = (valid && len > 0) ? toks[o0] : 0;
+    int32_t tok_next = (valid && len > 0) ? toks.at(o0) : 0;
     for (int t = 0; t < maxlen; ++t) {
         const bool act = alive && t < len;
         if (!__any_sync(FULL, act)) break;
         const int64_t sym = (int64_t)tok_next + shift;
-        if (act && t + 1 < len) tok_next = toks[o0 + t + 1];
+        if (act && t + 1 < len) tok_next = toks.at(o0 + t + 1);
         const bool symok = act && sym >= 0 && sym <= (int64_t)ix.max_sym;
         const uint32_t c = symok ? (uint32_t)sym : 0u;
         // RAW: sdsl::backward_search answers l=1,r=0 for a symbol that is not in the text
@@ -139,8 +146,8 @@ __global__ void __launch_bounds__(128) k_search(FmDev ix, const int32_t *__restr
         if (ok) p = ix.sa_samples[lo + (uint32_t)hl];
         if (__any_sync(FULL, pend && fast)) {
             int64_t s0 = -1, s1 = -1;
-            if (pend && fast && hl < rem) s0 = (int64_t)toks[o0 + t_stop + hl] + shift;
-            if (pend && fast && hl + 16 < rem) s1 = (int64_t)toks[o0 + t_stop + hl + 16] + shift;
+            if (pend && fast && hl < rem) s0 = (int64_t)toks.at(o0 + t_stop + hl) + shift;
+            if (pend && fast && hl + 16 < rem) s1 = (int64_t)toks.at(o0 + t_stop + hl + 16) + shift;
             const bool use0 = pend && fast && hl < rem, use1 = pend && fast && hl + 16 < rem;
             // a symbol outside u32 can never equal a text symbol
             const bool inv0 = use0 && (s0 < 0 || s0 > 0xFFFFFFFFll), inv1 = use1 && (s1 < 0 || s1 > 0xFFFFFFFFll);
@@ -170,7 +177,7 @@ __global__ void __launch_bounds__(128) k_search(FmDev ix, const int32_t *__restr
         }
         if (pend && !fast) {
             for (int j = 0; j < rem && ok; ++j) {
-                const int64_t sym = (int64_t)toks[o0 + t_stop + j] + shift;
+                const int64_t sym = (int64_t)toks.at(o0 + t_stop + j) + shift;
                 const uint32_t at = (uint32_t)(((uint64_t)p + n - 1u - ((uint32_t)j % n)) % n);  // the text is cyclic under LF
                 ok = sym >= 0 && sym <= 0xFFFFFFFFll && (uint32_t)sym == ix.text[at];
             }
@@ -202,20 +209,54 @@ __global__ void __launch_bounds__(128) k_search(FmDev ix, const int32_t *__restr
     }
 }
 
-// B independent FMIndex::backward_search_step calls (inclusive [low,high] in, half-open out).
-__global__ void __launch_bounds__(128) k_step(FmDev ix, const uint64_t *__restrict__ syms,
-                                              const uint64_t *__restrict__ lows, const uint64_t *__restrict__ highs,
-                                              uint32_t B, uint64_t *__restrict__ sp, uint64_t *__restrict__ ep) {
-    const int lane = threadIdx.x & 31, sub = lane & 7, half = (lane >> 3) & 1;
+template <bool RAW>
+__global__ void __launch_bounds__(128) k_search(FmDev ix, const int32_t *__restrict__ toks,
+                                                const int64_t *__restrict__ offs, uint32_t B, int64_t shift,
+                                                uint64_t *__restrict__ sp, uint64_t *__restrict__ ep,
+                                                uint32_t *__restrict__ zero_rows, uint32_t zero_words, uint32_t zero_lo,
+                                                uint32_t zero_n) {
     const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
     const bool valid = q < B;
-    uint64_t sym = 0, low = 1, high = 0;
+    int64_t o0 = 0;
+    int len = 0;
     if (valid) {
-        sym = syms[q];
-        low = lows[q];
-        high = highs[q];
-        if (high >= ix.n) high = (uint64_t)ix.n - 1;  // fm_index.cpp:74-76
+        o0 = offs[q];
+        len = (int)(offs[q + 1] - o0);
     }
+    fm_search_one<RAW>(ix, FmToksGlobal{toks}, o0, len, valid, q, shift, sp, ep, zero_rows, zero_words, zero_lo, zero_n);
+}
+
+// ---- scalar calls (batch 1): arguments travel as kernel parameters, results go straight into MAPPED PINNED host memory and
+// the host polls a sequence flag -- no H2D copy, no D2H copy, no stream synchronisation around a one-prefix query.
+struct FmScalarOut {            // lives in pinned host memory (device-visible under UVA)
+    uint64_t v[4];              // search / step: sp, ep ; locate: position
+    uint32_t k;                 // distinct: number of u64 written to data
+    uint32_t status;            // distinct: 0 ok, 1 = range too wide for the scalar kernel (caller falls back)
+    uint32_t flag;              // sequence number of the call whose results are complete (written last, system scope)
+    uint32_t pad;
+    uint64_t data[1];           // distinct: (sym[, count]) ascending, up to the capacity given to the kernel
+};
+
+__device__ __forceinline__ void fm_scalar_done(FmScalarOut *out, uint32_t seq) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&out->flag), "r"(seq) : "memory");
+}
+
+template <bool RAW>
+__global__ void __launch_bounds__(32) k_search1(FmDev ix, FmToksParam tp, int len, int64_t shift, FmScalarOut *out, uint32_t seq) {
+    __shared__ int32_t st[FM_SCALAR_MAX_TOKENS];
+    for (int i = threadIdx.x; i < len; i += 32) st[i] = tp.t[i];
+    __syncwarp();
+    fm_search_one<RAW>(ix, FmToksShared{st}, 0, len, threadIdx.x < 16, 0u, shift, &out->v[0], &out->v[1], nullptr, 0u, 0u, 0u);
+    __syncwarp();
+    if (threadIdx.x == 0) fm_scalar_done(out, seq);
+}
+
+// B independent FMIndex::backward_search_step calls (inclusive [low,high] in, half-open out).
+__device__ __forceinline__ void fm_step_one(const FmDev &ix, uint64_t sym, uint64_t low, uint64_t high, bool valid, uint64_t *sp_out,
+                                            uint64_t *ep_out) {
+    const int lane = threadIdx.x & 31, sub = lane & 7, half = (lane >> 3) & 1;
+    if (valid && high >= ix.n) high = (uint64_t)ix.n - 1;  // fm_index.cpp:74-76
     const bool ok = valid && low <= high && sym <= ix.max_sym;  // fm_index.cpp:77-82 ; absent symbol
     const uint32_t c = ok ? (uint32_t)sym : 0u;
     const uint32_t Dc = ok ? ix.D[c] : 0u;
@@ -226,9 +267,30 @@ __global__ void __launch_bounds__(128) k_step(FmDev ix, const uint64_t *__restri
     const uint32_t nlo = half ? oth : res, nhi = half ? res : oth;
     if (valid && (lane & 15) == 0) {
         const bool hit = ok && nlo < nhi;  // fm_index.cpp:87-92
-        sp[q] = hit ? nlo : 0;
-        ep[q] = hit ? nhi : 0;
+        *sp_out = hit ? nlo : 0;
+        *ep_out = hit ? nhi : 0;
     }
+}
+
+__global__ void __launch_bounds__(128) k_step(FmDev ix, const uint64_t *__restrict__ syms,
+                                              const uint64_t *__restrict__ lows, const uint64_t *__restrict__ highs,
+                                              uint32_t B, uint64_t *__restrict__ sp, uint64_t *__restrict__ ep) {
+    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const bool valid = q < B;
+    uint64_t sym = 0, low = 1, high = 0;
+    if (valid) {
+        sym = syms[q];
+        low = lows[q];
+        high = highs[q];
+    }
+    fm_step_one(ix, sym, low, high, valid, sp + (valid ? q : 0), ep + (valid ? q : 0));
+}
+
+// scalar FMIndex::backward_search_step: arguments by value, result into mapped pinned host memory (see k_search1)
+__global__ void __launch_bounds__(32) k_step1(FmDev ix, uint64_t sym, uint64_t low, uint64_t high, FmScalarOut *out, uint32_t seq) {
+    fm_step_one(ix, sym, low, high, threadIdx.x < 16, &out->v[0], &out->v[1]);
+    __syncwarp();
+    if (threadIdx.x == 0) fm_scalar_done(out, seq);
 }
 
 // Incremental decoding: one backward-search step per beam per generated token, state kept on the device.
@@ -1893,12 +1955,7 @@ __global__ void __launch_bounds__(256) k_locate_full(FmDev ix, const uint64_t *_
     pos[i] = r >= ix.n ? ~0ull : (uint64_t)ix.sa_samples[r];  // fm_index.cpp:170
 }
 
-__global__ void __launch_bounds__(128) k_locate(FmDev ix, const uint64_t *__restrict__ rows, size_t n,
-                                                uint64_t *__restrict__ out) {
-    const int sub = threadIdx.x & 7;
-    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    const bool valid = i < n;
-    uint64_t r64 = valid ? rows[i] : 0;
+__device__ __forceinline__ uint64_t fm_locate_one(const FmDev &ix, uint64_t r64, bool valid, int sub) {
     bool act = valid && r64 < ix.n;
     uint32_t row = act ? (uint32_t)r64 : 0u, steps = 0;
     uint64_t result = ~0ull;  // fm_index.cpp:170 : (size_type)-1
@@ -1917,7 +1974,139 @@ __global__ void __launch_bounds__(128) k_locate(FmDev ix, const uint64_t *__rest
             ++steps;
         }
     }
+    return result;
+}
+
+__global__ void __launch_bounds__(128) k_locate(FmDev ix, const uint64_t *__restrict__ rows, size_t n,
+                                                uint64_t *__restrict__ out) {
+    const int sub = threadIdx.x & 7;
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const bool valid = i < n;
+    const uint64_t result = fm_locate_one(ix, valid ? rows[i] : 0, valid, sub);
     if (valid && sub == 0) out[i] = result;
+}
+
+// scalar FMIndex::locate (fm_index.cpp:168-172)
+__global__ void __launch_bounds__(32) k_locate1(FmDev ix, uint64_t row, FmScalarOut *out, uint32_t seq) {
+    uint64_t result;
+    if (ix.sa_dens == 1) result = row >= ix.n ? ~0ull : (uint64_t)ix.sa_samples[row];
+    else result = fm_locate_one(ix, row, threadIdx.x < 8, threadIdx.x & 7);
+    if (threadIdx.x == 0) {
+        out->v[0] = result;
+        fm_scalar_done(out, seq);
+    }
+}
+
+// scalar FMIndex::distinct / distinct_count (fm_index.cpp:99-144) for ranges of up to DISTINCT1_MAX rows: ONE CTA reads the
+// rows' symbols (resident BWT: one coalesced read; otherwise `levels` access probes + a byte load per row), sorts them in
+// shared memory (bitonic), run-length encodes and writes the ascending (symbol[, count]) list straight into mapped pinned
+// host memory.  Wider ranges report status 1 and the caller takes the bitmap path.
+constexpr int DISTINCT1_MAX = 4096, DISTINCT1_THREADS = 512;
+__global__ void __launch_bounds__(DISTINCT1_THREADS) k_distinct1(FmDev ix, uint64_t low, uint64_t high, int with_counts, uint32_t cap_u64,
+                                                                FmScalarOut *out, uint32_t seq) {
+    __shared__ uint32_t key[DISTINCT1_MAX];
+    __shared__ uint32_t head[DISTINCT1_MAX];  // sorted index of the k-th run head
+    __shared__ uint32_t wsum[DISTINCT1_THREADS / 32];
+    __shared__ uint32_t total_s;
+    const int tid = threadIdx.x;
+    uint64_t e = high > ix.n ? ix.n : high;  // fm_index.cpp:104-106 / 130-132
+    const uint32_t w = e > low ? (uint32_t)min(e - low, (uint64_t)DISTINCT1_MAX + 1) : 0u;
+    if (w > DISTINCT1_MAX) {
+        if (tid == 0) {
+            out->status = 1u;
+            out->k = 0u;
+            fm_scalar_done(out, seq);
+        }
+        return;
+    }
+    uint32_t N = 32;
+    while (N < w) N <<= 1;
+    for (uint32_t i = tid; i < N; i += DISTINCT1_THREADS) {
+        uint32_t c = 0xFFFFFFFFu;  // padding sorts last (symbols are <= max_sym < 2^24)
+        if (i < w) {
+            uint32_t pos = (uint32_t)low + i;
+            if (ix.bwt) c = __ldg(ix.bwt + pos);
+            else {
+                c = 0;
+                for (uint32_t l = 0; l < ix.levels; ++l) {
+                    uint32_t dig;
+                    pos = fm_access1(ix.cells + l * ix.level_stride, pos, dig);
+                    c = (c << 4) | dig;
+                }
+                c = (c << 8) | fm_byte_at(ix.bcells, pos);
+            }
+        }
+        key[i] = c;
+    }
+    __syncthreads();
+    for (uint32_t k2 = 2; k2 <= N; k2 <<= 1)
+        for (uint32_t j = k2 >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = tid; i < N; i += DISTINCT1_THREADS) {
+                const uint32_t ixj = i ^ j;
+                if (ixj > i) {
+                    const uint32_t a = key[i], b = key[ixj];
+                    const bool up = (i & k2) == 0;
+                    if ((a > b) == up) { key[i] = b; key[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    // run heads -> compact positions (block-wide exclusive scan over N flags, DISTINCT1_MAX / DISTINCT1_THREADS per thread)
+    constexpr int PER = DISTINCT1_MAX / DISTINCT1_THREADS;
+    uint32_t flags = 0, cnt = 0;
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {
+        const uint32_t i = (uint32_t)tid * PER + r;
+        const bool hd = i < w && (i == 0 || key[i] != key[i - 1]);
+        flags |= (hd ? 1u : 0u) << r;
+        cnt += hd;
+    }
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(FULL, incl, o);
+        if ((tid & 31) >= o) incl += v;
+    }
+    if ((tid & 31) == 31) wsum[tid >> 5] = incl;
+    __syncthreads();
+    if (tid < 32) {
+        uint32_t v = tid < DISTINCT1_THREADS / 32 ? wsum[tid] : 0u, in2 = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(FULL, in2, o);
+            if (tid >= o) in2 += u;
+        }
+        if (tid < DISTINCT1_THREADS / 32) wsum[tid] = in2 - v;
+        if (tid == 31) total_s = in2;
+    }
+    __syncthreads();
+    uint32_t posn = wsum[tid >> 5] + incl - cnt;
+#pragma unroll
+    for (int r = 0; r < PER; ++r)
+        if ((flags >> r) & 1u) head[posn++] = (uint32_t)tid * PER + r;
+    __syncthreads();
+    const uint32_t nd = total_s;
+    const uint32_t per = with_counts ? 2u : 1u;
+    if (nd * per > cap_u64) {
+        if (tid == 0) {
+            out->status = 1u;
+            out->k = nd * per;
+            fm_scalar_done(out, seq);
+        }
+        return;
+    }
+    for (uint32_t k = tid; k < nd; k += DISTINCT1_THREADS) {
+        const uint32_t a = head[k], b = k + 1 < nd ? head[k + 1] : w;
+        out->data[k * per] = key[a];
+        if (with_counts) out->data[k * per + 1] = b - a;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        out->status = 0u;
+        out->k = nd * per;
+        fm_scalar_done(out, seq);
+    }
 }
 
 // isa[p] from text-order samples, then emit BWT[row], row = LF(row), ...
@@ -2360,6 +2549,94 @@ int fm_launch_compact(fmidx *h, const uint32_t *d_mask, const uint32_t *d_counts
     if (B == 0) return FMIDX_OK;
     FM_LAUNCH(k_compact, (unsigned)B, 256, 0, s, d_mask, d_counts, (vocab + 31u) >> 5, vocab, d_offs, d_tokens, d_cnts);
     FM_CUDA(cudaGetLastError());
+    return FMIDX_OK;
+}
+
+// ---- scalar calls: by-value arguments, results in mapped pinned host memory, host polls the sequence flag ------------------
+static int fm_scalar_prepare(fmidx *h, FmScalarOut **out, uint32_t *seq) {
+    FM_TRY(check_ready(h));
+    if (!h->scalar_out) {
+        const size_t bytes = sizeof(FmScalarOut) + (size_t)2 * DISTINCT1_MAX * 8;
+        FM_CUDA(cudaHostAlloc(&h->scalar_out, bytes, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(h->scalar_out, 0, bytes);
+        h->scalar_cap_u64 = (size_t)2 * DISTINCT1_MAX;
+    }
+    *out = (FmScalarOut *)h->scalar_out;
+    *seq = ++h->scalar_seq;
+    if (*seq == 0) *seq = ++h->scalar_seq;  // 0 is the initial flag value
+    return FMIDX_OK;
+}
+
+static int fm_scalar_wait(fmidx *h, FmScalarOut *out, uint32_t seq) {
+    FM_CUDA(cudaGetLastError());
+    volatile uint32_t *flag = &out->flag;
+    for (uint32_t spin = 1;; ++spin) {
+        if (*flag == seq) break;
+        if ((spin & 0xFFFu) == 0) {  // a kernel that died never raises the flag
+            const cudaError_t e = cudaStreamQuery(h->stream);
+            if (e == cudaSuccess) {
+                if (*flag == seq) break;
+                fm_set_error("scalar kernel finished without a result");
+                return FMIDX_ECUDA;
+            }
+            if (e != cudaErrorNotReady) { fm_set_error("scalar kernel failed: %s", cudaGetErrorString(e)); return FMIDX_ECUDA; }
+        }
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    return FMIDX_OK;
+}
+
+int fm_scalar_max_tokens() { return FM_SCALAR_MAX_TOKENS; }
+
+int fm_scalar_search(fmidx *h, const int64_t *toks, int n, int64_t shift, int raw, uint64_t res[2]) {
+    FmScalarOut *out;
+    uint32_t seq;
+    FM_TRY(fm_scalar_prepare(h, &out, &seq));
+    FmToksParam tp;
+    for (int i = 0; i < n; ++i) tp.t[i] = (toks[i] < -0x7FFFFFFFll || toks[i] > 0x7FFFFFFFll) ? -0x7FFFFFFF - 1 : (int32_t)toks[i];
+    if (raw) FM_LAUNCH(k_search1<true>, 1, 32, 0, h->stream, h->dev, tp, n, shift, out, seq);
+    else FM_LAUNCH(k_search1<false>, 1, 32, 0, h->stream, h->dev, tp, n, shift, out, seq);
+    FM_TRY(fm_scalar_wait(h, out, seq));
+    res[0] = out->v[0];
+    res[1] = out->v[1];
+    return FMIDX_OK;
+}
+
+int fm_scalar_step(fmidx *h, uint64_t sym, uint64_t low, uint64_t high, uint64_t res[2]) {
+    FmScalarOut *out;
+    uint32_t seq;
+    FM_TRY(fm_scalar_prepare(h, &out, &seq));
+    FM_LAUNCH(k_step1, 1, 32, 0, h->stream, h->dev, sym, low, high, out, seq);
+    FM_TRY(fm_scalar_wait(h, out, seq));
+    res[0] = out->v[0];
+    res[1] = out->v[1];
+    return FMIDX_OK;
+}
+
+int fm_scalar_locate(fmidx *h, uint64_t row, uint64_t *pos) {
+    FmScalarOut *out;
+    uint32_t seq;
+    FM_TRY(fm_scalar_prepare(h, &out, &seq));
+    FM_LAUNCH(k_locate1, 1, 32, 0, h->stream, h->dev, row, out, seq);
+    FM_TRY(fm_scalar_wait(h, out, seq));
+    *pos = out->v[0];
+    return FMIDX_OK;
+}
+
+// *fallback = true: the range is wider than the scalar kernel handles (nothing written)
+int fm_scalar_distinct(fmidx *h, uint64_t low, uint64_t high, int with_counts, uint64_t *dst, size_t cap, size_t *k, bool *fallback) {
+    FmScalarOut *out;
+    uint32_t seq;
+    *fallback = false;
+    FM_TRY(fm_scalar_prepare(h, &out, &seq));
+    const uint64_t e = high > h->dev.n ? h->dev.n : high;
+    if (e > low && e - low > (uint64_t)DISTINCT1_MAX) { *fallback = true; return FMIDX_OK; }
+    FM_LAUNCH(k_distinct1, 1, DISTINCT1_THREADS, 0, h->stream, h->dev, low, high, with_counts, (uint32_t)h->scalar_cap_u64, out, seq);
+    FM_TRY(fm_scalar_wait(h, out, seq));
+    if (out->status != 0) { *fallback = true; return FMIDX_OK; }
+    *k = out->k;
+    if (out->k > cap) { fm_set_error("output buffer too small: need %u", out->k); return FMIDX_ERANGE; }
+    if (out->k) memcpy(dst, (const void *)out->data, (size_t)out->k * 8);
     return FMIDX_OK;
 }
 

@@ -14,6 +14,7 @@
 // whenever a peer was a little late, and the ranks slowed each other down: 59 M q/s on 4 GPUs against 131 M on one.)  The reference has no distributed path
 // (its only parallelism is one std::async per range, fm_index.cpp:146-166); parity for the sharded configuration is
 // "one reference index per shard, results OR/sum-reduced on the host".
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -161,11 +162,15 @@ static int shard_step(fmidx_shard *x, uint32_t set, const int32_t *d_toks, const
     xa.peer_inbox = (uint32_t *const *)(tab + W);
     xa.peer_data_flags = (uint32_t *const *)(tab + 2 * W);
     xa.xlocal = st.xlocal; xa.done_ctr = st.ctr; xa.xwords = x->xwords; xa.world = W; xa.rank = x->rank; xa.seq = seq;
+    // measurement only ($FMIDX_SHARD_PROBE): 1 = no pull kernel (results incomplete), 2 = neither publish nor pull
+    static const int probe = [] { const char *e = getenv("FMIDX_SHARD_PROBE"); return e ? atoi(e) : 0; }();
+    if (probe >= 2) xa.world = 0;
     h->mask_ws_override = &h->slots[set].ws;
     struct Reset { fmidx *h; ~Reset() { h->mask_ws_override = nullptr; } } reset{h};
     // only the rows this rank owns come out as complete bitmaps; the others are written slice-wise (occupied slices)
     FM_TRY(fm_launch_mask(h, d_sp, d_ep, x->B, shift, x->vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, mask, nullptr, s,
                           st.xlocal, (size_t)x->rank * own, own, kz, &xa));
+    if (probe >= 1) return FMIDX_OK;
     return fm_launch_xchg_pull(h, (uint32_t *const *)tab, st.data_flags, st.inbox[par], x->xwords, x->count_off, W, x->rank, x->B,
                                x->vocab, seq, st.counts, s);
 }

@@ -286,3 +286,47 @@ def test_graph_captured_device_step(cuda):
         torch.cuda.synchronize()
         assert (gs.sp[i].cpu().numpy() == osp).all() and (gs.ep[i].cpu().numpy() == oep).all(), step
         assert (gs.mask[i].cpu().numpy() == om.reshape(B, -1)).all(), step
+
+
+@pytest.mark.parametrize("layout", ["resident", "sampled"])
+def test_scalar_fast_paths_match_batched_paths_and_oracle(cuda, layout):
+    """The scalar (batch 1) calls -- arguments as kernel parameters, results polled from mapped pinned memory -- against
+    the batched code paths (scalar_fast=0) and the oracle: get_range, backward_search_multi, backward_search_step, locate,
+    distinct, distinct_count; ranges around the 4096-row limit of the scalar distinct kernel and prefixes around its
+    96-token limit take the fallback."""
+    from fm_index_constrained_decoding_b200 import FMIndex
+    from oracle.oracle import OracleFMIndex
+    rng = random.Random(47)
+    vocab = 600
+    weights = [1.0 / (r + 1) for r in range(vocab)]
+    docs = [rng.choices(range(vocab), weights=weights, k=rng.randint(50, 400)) + [EOS] for _ in range(120)]
+    o = OracleFMIndex()
+    o.initialize(docs)
+    ix = FMIndex(layout=layout)
+    ix.initialize(docs, in_memory=True)
+    n = ix.size()
+    cases = []
+    for _ in range(60):
+        d = rng.choice(docs)
+        i = rng.randrange(len(d) - 1)
+        cases.append(d[i:i + rng.randint(1, 12)])
+    cases += [[0], [vocab + 5], [], docs[3][:95], docs[3][:96], docs[3][:97], docs[3][:140], [docs[0][0], 10 ** 12]]
+    for fast in (1, 0):
+        ix.tune(scalar_fast=fast)
+        for q in cases:
+            lo, hi = ix.get_range(q)
+            assert (lo, hi) == o.get_range(q), (fast, q[:5])
+            sym = [t + 10 for t in q][::-1]
+            assert ix.backward_search_multi(sym) == o.backward_search_multi(sym), (fast, q[:5])
+            assert ix.distinct(lo, hi) == o.distinct(lo, hi)
+            assert ix.distinct_count(lo, hi) == o.distinct_count(lo, hi)
+        for lo, hi in [(0, n), (0, n + 7), (5, 5), (9, 3), (0, 4096), (0, 4097), (1, 4097), (n - 3, n), (n - 1, n + 100), (n, n + 1),
+                       (17, 18), (100, 4000)]:
+            assert ix.distinct(lo, hi) == o.distinct(lo, hi), (fast, lo, hi)
+            assert ix.distinct_count(lo, hi) == o.distinct_count(lo, hi), (fast, lo, hi)
+        for _ in range(40):
+            s, lo = rng.randrange(vocab + 20), rng.randrange(n)
+            hi = rng.choice([lo, lo + rng.randrange(50), n - 1, n + 5, max(0, lo - 1)])
+            assert ix.backward_search_step(s, lo, hi) == o.backward_search_step(s, lo, hi), (fast, s, lo, hi)
+        for r in [0, 1, n - 1, n, n + 9, 2 ** 40] + [rng.randrange(n) for _ in range(30)]:
+            assert ix.locate(r) == o.locate(r), (fast, r)
