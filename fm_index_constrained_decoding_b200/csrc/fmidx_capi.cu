@@ -51,6 +51,7 @@ int fm_scratch(fmidx *h, FmBuf &b, size_t bytes, bool pinned_host) {
     b.pinned_host = pinned_host;
     b.epoch = 0;
     b.ctr_clean = false;
+    b.row_clean = false;
     return FMIDX_OK;
 }
 

@@ -48,6 +48,7 @@ struct FmBuf {  // growable device / pinned-host scratch
     // each call's last kernel zeroes the pair of the next one (no memset node per call)
     uint32_t epoch = 0;
     bool ctr_clean = false;
+    bool row_clean = false;  // words 8, 9 (claim / exit counters of k_mask_logits_row) are zero
     // shared (non-slot) mask workspaces: last use, so that a call on another stream orders itself behind it
     cudaEvent_t last_use = nullptr;
     cudaStream_t last_stream = nullptr;

@@ -1641,6 +1641,203 @@ k_mask_logits_pipe(FmDev ix, const uint2 *__restrict__ top, uint32_t P_top, uint
     if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the last store's read
 }
 
+// ---- phase B, fused with the logits row: persistent CTAs streaming GROUPS of a row through a bulk-copy ring -----------------
+// The one-shot kernels below pay the enumeration's dependent-load chain once per 16 KB of logits and keep only 64 KB of loads in
+// flight per SM (4 CTAs x 16 KB, registers), i.e. 0.85 (fp32) / 0.70 (bf16) of the HBM roofline.  Here a work item is a beam and a
+// GROUP of 32,768 tokens (128 KB fp32 / 64 KB bf16): the group's bitmap (4 KB of shared memory) is enumerated ONCE, and the
+// group's logits stream through a ROW_STAGES-deep ring of 16 KB stages by bulk async copies (cp.async.bulk + mbarrier in,
+// cp.async.bulk out): the loads of the next stages -- across item boundaries -- are in flight while a stage is masked in shared
+// memory and while the next item's range is enumerated.  Two persistent CTAs per SM, items claimed from a global counter.
+constexpr int ROW_STAGES = 5;
+constexpr int ROW_CTAS_PER_SM = 2;
+constexpr uint32_t ROW_GROUP = 32768;        // tokens per work item
+constexpr uint32_t ROW_STAGE_BYTES = 16384;
+
+template <int DT>
+__global__ void __launch_bounds__(MASK_THREADS)
+k_mask_logits_row(FmDev ix, uint32_t LT, int64_t shift, uint32_t vocab, const void *logits_v, void *out_v, int64_t row_stride,
+                  const int32_t *__restrict__ override_tok, int32_t always_allow, const uint32_t *__restrict__ extra, uint32_t n_extra,
+                  uint32_t B, uint32_t *__restrict__ mask_out, uint32_t n_items, uint32_t *__restrict__ claim_ctr,
+                  const uint64_t *__restrict__ sp, const uint64_t *__restrict__ ep) {
+    using ET = typename Elem<DT>::T;
+    constexpr int VEC = Elem<DT>::VEC;
+    constexpr uint32_t CT = ROW_STAGE_BYTES / sizeof(ET);  // tokens per stage
+    extern __shared__ __align__(128) unsigned char ring[];  // ROW_STAGES x ROW_STAGE_BYTES
+    __shared__ __align__(8) uint64_t mbar[ROW_STAGES];
+    __shared__ uint32_t q_item[ROW_STAGES], q_chunk[ROW_STAGES];
+    __shared__ uint32_t gbm[ROW_GROUP / 32];
+    __shared__ EnumSmem S;
+    const int tid = threadIdx.x;
+    const uint32_t ngroups = (vocab + ROW_GROUP - 1) / ROW_GROUP;
+    const uint32_t mask_words = (vocab + 31u) >> 5;
+    const ET *in_base = reinterpret_cast<const ET *>(logits_v);
+    ET *out_base = reinterpret_cast<ET *>(out_v);
+    // producer state (thread 0): the item being issued and its next chunk
+    uint32_t p_item = 0xFFFFFFFFu, p_chunk = 0, p_nchunks = 0;
+
+    auto item_tokens = [&](uint32_t item, uint32_t &b, uint32_t &t0, uint32_t &t1) {
+        b = item / ngroups;
+        t0 = (item % ngroups) * ROW_GROUP;
+        t1 = min(t0 + ROW_GROUP, vocab);
+    };
+    auto claim = [&]() {  // thread 0
+        p_item = atomicAdd(claim_ctr, 1u);
+        p_chunk = 0;
+        if (p_item < n_items) {
+            uint32_t b, t0, t1;
+            item_tokens(p_item, b, t0, t1);
+            p_nchunks = (t1 - t0 + CT - 1) / CT;
+        } else {
+            p_item = 0xFFFFFFFFu;
+        }
+    };
+    auto produce = [&](int stage) {  // thread 0: next chunk of the stream into `stage`
+        q_item[stage] = p_item;
+        q_chunk[stage] = p_chunk;
+        if (p_item == 0xFFFFFFFFu) return;
+        uint32_t b, t0, t1;
+        item_tokens(p_item, b, t0, t1);
+        const uint32_t c0 = t0 + p_chunk * CT, c1 = min(c0 + CT, t1);
+        const uint32_t bytes = (c1 - c0) * (uint32_t)sizeof(ET);
+        const uint32_t mb = fm_smem_u32(&mbar[stage]), sb = fm_smem_u32(ring + (size_t)stage * ROW_STAGE_BYTES);
+        const ET *src = in_base + (size_t)b * row_stride + c0;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(sb), "l"(src), "r"(bytes), "r"(mb) : "memory");
+        if (++p_chunk == p_nchunks) claim();
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < ROW_STAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fm_smem_u32(&mbar[s])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        claim();
+        for (int s = 0; s < ROW_STAGES; ++s) produce(s);
+    }
+    for (uint32_t k = 0;; ++k) {
+        const int stage = (int)(k % ROW_STAGES);
+        __syncthreads();
+        const uint32_t item = q_item[stage], chunk = q_chunk[stage];
+        if (item == 0xFFFFFFFFu) break;  // the stream of this CTA has ended (claims are handed out in order)
+        uint32_t b, t0, t1;
+        item_tokens(item, b, t0, t1);
+        if (chunk == 0) {
+            // ---- the group's bitmap, once per item (the ring's loads stay in flight meanwhile) ----
+            const uint32_t nw = (t1 - t0 + 31u) >> 5;
+            for (uint32_t w = tid; w < ROW_GROUP / 32; w += MASK_THREADS) gbm[w] = 0u;
+            const int32_t ovr = override_tok ? override_tok[b] : -1;
+            uint64_t s64 = sp[b], e64 = ep[b];
+            if (e64 > ix.n) e64 = ix.n;
+            uint32_t sa, se;
+            fm_slice_interval(ix, t0, t1, shift, sa, se);
+            __syncthreads();
+            if (ovr >= 0) {
+                if (tid == 0 && (uint32_t)ovr >= t0 && (uint32_t)ovr < t1) gbm[((uint32_t)ovr - t0) >> 5] = 1u << (((uint32_t)ovr - t0) & 31u);
+            } else if (s64 < e64) {
+                bool done = false;
+                if (ix.bwt && e64 - s64 <= (uint64_t)SCAN_INLINE) {
+                    // narrow range: read the rows' symbols off the resident BWT, keep the group's tokens
+                    fm_scan_rows(ix.bwt, (uint32_t)s64, (uint32_t)e64, (uint32_t)tid, (uint32_t)MASK_THREADS, [&](uint32_t c) {
+                        if (c >= sa && c < se) {
+                            const uint32_t rel = (uint32_t)((int64_t)c - shift) - t0;
+                            atomicOr(&gbm[rel >> 5], 1u << (rel & 31u));
+                        }
+                    });
+                    done = true;
+                } else if (ix.bwt && ix.uni_n) {
+                    // one frequent symbol's whole block: the group comes straight out of the unigram table
+                    if (tid == 0) S.n_seed = 0xFFFFFFFFu;
+                    __syncthreads();
+                    const int mine = fm_uni_find_part(ix, (uint32_t)s64, (uint32_t)tid, (uint32_t)MASK_THREADS);
+                    if (mine >= 0) S.n_seed = (uint32_t)mine;
+                    __syncthreads();
+                    int ui = (int)S.n_seed;
+                    if (ui >= 0 && __ldg(ix.uni_ep + ui) != (uint32_t)e64) ui = -1;
+                    __syncthreads();
+                    if (ui >= 0) {
+                        const uint32_t *srow = ix.uni_masks + (size_t)ui * ix.uni_words;
+                        const uint32_t tl = (uint32_t)min((int64_t)se - shift, (int64_t)t1);
+                        for (uint32_t w = tid; w < nw; w += MASK_THREADS) gbm[w] = fm_uni_word(srow, ix.uni_words, (t0 >> 5) + w, shift, tl);
+                        done = true;
+                    }
+                }
+                if (!done) {
+                    // any other range (wide and not a table entry; sampled layout): the slice walk of the one-shot kernels,
+                    // 4096 tokens at a time
+                    for (uint32_t st0 = t0; st0 < t1; st0 += SLICE) {
+                        const uint32_t st1 = min(st0 + (uint32_t)SLICE, t1);
+                        for (int w = tid; w < 2 * SLICE / 32; w += MASK_THREADS) S.bm[w] = 0u;
+                        uint32_t ssa, sse;
+                        fm_slice_interval(ix, st0, st1, shift, ssa, sse);
+                        fm_enum_slice(ix, nullptr, LT, ssa, sse, shift, st0, S, nullptr, s64, e64);
+                        __syncthreads();
+                        for (uint32_t w = tid; w < ((st1 - st0 + 31u) >> 5); w += MASK_THREADS) gbm[((st0 - t0) >> 5) + w] = S.bm[w];
+                        __syncthreads();
+                    }
+                }
+            }
+            __syncthreads();
+            if (ovr < 0 && n_extra) {
+                for (uint32_t w = tid; w < nw; w += MASK_THREADS) {
+                    uint32_t acc = gbm[w];
+                    for (uint32_t x = 0; x < n_extra; ++x) acc |= extra[((size_t)x * B + b) * mask_words + (t0 >> 5) + w];
+                    gbm[w] = acc;
+                }
+                __syncthreads();
+            }
+            if (tid == 0 && always_allow >= 0 && (uint32_t)always_allow >= t0 && (uint32_t)always_allow < t1)
+                gbm[((uint32_t)always_allow - t0) >> 5] |= 1u << (((uint32_t)always_allow - t0) & 31u);
+            __syncthreads();
+            if (mask_out)
+                for (uint32_t w = tid; w < nw; w += MASK_THREADS) mask_out[(size_t)b * mask_words + (t0 >> 5) + w] = gbm[w];
+        }
+        // ---- wait for the stage, mask it in shared memory, bulk-store it ----
+        const uint32_t parity = (k / ROW_STAGES) & 1u;
+        const uint32_t mb = fm_smem_u32(&mbar[stage]);
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "FM_RWAIT:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra FM_RDONE;\n"
+            "bra FM_RWAIT;\n"
+            "FM_RDONE:\n"
+            "}\n" ::"r"(mb), "r"(parity) : "memory");
+        const uint32_t c0 = t0 + chunk * CT, c1 = min(c0 + CT, t1);
+        uint4 *buf = reinterpret_cast<uint4 *>(ring + (size_t)stage * ROW_STAGE_BYTES);
+        const uint32_t nvec = (c1 - c0) / VEC, wbase = (c0 - t0) >> 5;
+        for (uint32_t v = tid; v < nvec; v += MASK_THREADS) {
+            const uint32_t rel = v * VEC;
+            const uint32_t bits = (gbm[wbase + (rel >> 5)] >> (rel & 31u)) & ((1u << VEC) - 1u);
+            uint4 r = buf[v];
+            ET *x = reinterpret_cast<ET *>(&r);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) x[e] = fm_add_mask(x[e], (bits >> e) & 1u);
+            buf[v] = r;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t bytes = (c1 - c0) * (uint32_t)sizeof(ET);
+            ET *dst = out_base + (size_t)b * row_stride + c0;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(fm_smem_u32(buf)), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            // a stage may be refilled once its store has READ it: this chunk's store stays outstanding, the previous chunk's
+            // stage is refilled
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            if (k > 0) produce((int)((k - 1) % ROW_STAGES));
+        }
+    }
+    if (tid == 0) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the last store's read
+        // the CTA that leaves last resets the claim counter for the next launch on this workspace (stream / event ordered)
+        __threadfence();
+        if (atomicAdd(claim_ctr + 1, 1u) == gridDim.x - 1u) {
+            claim_ctr[0] = 0u;
+            claim_ctr[1] = 0u;
+        }
+    }
+}
+
 // ---- phase B, fused with the logits row -------------------------------------------------------------------
 // DT: FMIDX_F32/BF16/F16.   VECTOR: 16-byte accesses are legal.   SL: tokens per CTA -- 4096 for fp32, 8192 for the 2-byte
 // dtypes, so that a CTA moves 16 KB each way whatever the dtype (with 4096-token slices the bf16 step reached 0.54 of the HBM
@@ -2288,13 +2485,14 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
     } stamp{ws, s, guarded};
     // first 128 bytes: two pairs of work-list counters ([0]=#items [1]=#byte nodes / next), used alternately: the last
     // kernel of a call zeroes the pair of the following call, so steady-state calls need no memset
-    if (!ws.ctr_clean) {
-        FM_CUDA(cudaMemsetAsync(ws.p, 0, 128, s));
+    // (logits mode uses neither pair: it leaves them and their epoch alone)
+    if (!has && !ws.ctr_clean) {
+        FM_CUDA(cudaMemsetAsync(ws.p, 0, 32, s));
         ws.epoch = 0;
     }
-    ws.ctr_clean = false;  // set again once every launch of this call went through
+    if (!has) ws.ctr_clean = false;  // set again once every launch of this call went through
     uint32_t *ctr = (uint32_t *)ws.p + 2 * (ws.epoch & 1u), *ctr_next = (uint32_t *)ws.p + 2 * ((ws.epoch & 1u) ^ 1u);
-    ++ws.epoch;
+    if (!has) ++ws.epoch;
     uint2 *lvl = (uint2 *)((char *)ws.p + 128);
     const size_t items_off = 128 + ((lvl_bytes + 15) & ~(size_t)15);
     uint4 *items = has ? nullptr : (uint4 *)((char *)ws.p + items_off);
@@ -2364,11 +2562,40 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
     const char *path = getenv("FMIDX_LOGITS_PATH");
     const bool tma = path && strcmp(path, "tma") == 0;
     const bool pipe = path && strcmp(path, "pipe") == 0;
+    const bool regs = path && strcmp(path, "regs") == 0;
     const int esz = dtype == FMIDX_F32 ? 4 : 2;
+    if (!tma && !pipe && !regs && (dtype == FMIDX_F32 || dtype == FMIDX_BF16 || dtype == FMIDX_F16) && aligned(esz)) {
+        // default: persistent CTAs, one work item = a beam's group of 32,768 tokens (k_mask_logits_row)
+        const size_t n_items = (size_t)((vocab + ROW_GROUP - 1) / ROW_GROUP) * B;
+        const unsigned rgrid = (unsigned)std::min<size_t>(n_items, (size_t)h->sm_count * ROW_CTAS_PER_SM);
+        const int dyn = ROW_STAGES * (int)ROW_STAGE_BYTES;
+        uint32_t *claim = (uint32_t *)ws.p + 8;  // words 8, 9 of the workspace header: claim counter, exit counter (self-resetting)
+        if (!ws.row_clean) {
+            FM_CUDA(cudaMemsetAsync(claim, 0, 8, s));
+            ws.row_clean = true;
+        }
+#define FM_MASK_ROW(DT)                                                                                             \
+    do {                                                                                                            \
+        static bool attr_set = false;                                                                               \
+        if (!attr_set) {                                                                                            \
+            FM_CUDA(cudaFuncSetAttribute(k_mask_logits_row<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)); \
+            attr_set = true;                                                                                        \
+        }                                                                                                           \
+        FM_LAUNCH((k_mask_logits_row<DT>), rgrid, MASK_THREADS, dyn, s, ix, LT, shift, vocab, d_logits, d_out, row_stride, d_override, \
+                  always_allow, d_extra, n_extra, (uint32_t)B, d_mask, (uint32_t)n_items, claim, d_sp, d_ep);        \
+    } while (0)
+        if (dtype == FMIDX_F32) FM_MASK_ROW(FMIDX_F32);
+        else if (dtype == FMIDX_BF16) FM_MASK_ROW(FMIDX_BF16);
+        else FM_MASK_ROW(FMIDX_F16);
+#undef FM_MASK_ROW
+        FM_CUDA(cudaGetLastError());
+        return FMIDX_OK;
+    }
     if (pipe && (dtype == FMIDX_F32 || dtype == FMIDX_BF16 || dtype == FMIDX_F16) && aligned(esz)) {
         const int dyn = PIPE_STAGES * SLICE * esz;
         const unsigned pgrid = (unsigned)std::min<size_t>(nblk, (size_t)h->sm_count * PIPE_CTAS_PER_SM);
         FM_CUDA(cudaMemsetAsync(ctr, 0, 8, s));
+        ws.ctr_clean = false;  // the pipe variant borrows (and dirties) a work-list counter pair
 #define FM_MASK_PIPE(DT)                                                                                            \
     do {                                                                                                            \
         static bool attr_set = false;                                                                               \
