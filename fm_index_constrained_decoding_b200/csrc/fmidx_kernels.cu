@@ -2003,6 +2003,8 @@ k_xchg_pull(uint32_t *const *__restrict__ peer_masks, const uint32_t *__restrict
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     uint32_t *mine = peer_masks[rank];
     const bool vec_ok = (mask_words & 3u) == 0;  // rows are 16-byte aligned (checked by the launcher for the bases)
+    const int oct = lane >> 3, l8 = lane & 7;
+    constexpr int RB = 8;  // rows per batch: their occupancy words are fetched together, their slices pulled 8 at a time
     for (uint32_t k = 1; k < world; ++k) {
         const uint32_t p = rank + k < world ? rank + k : rank + k - world;
         if (lane == 0) {
@@ -2015,50 +2017,74 @@ k_xchg_pull(uint32_t *const *__restrict__ peer_masks, const uint32_t *__restrict
         __syncwarp();
         const uint32_t *occ_p = inbox + (size_t)p * xwords;
         const uint32_t *theirs = peer_masks[p];
-        for (uint32_t r = gw; r < own; r += nwarps) {
-            const uint32_t row = row_lo + r;
+        for (uint32_t r0 = gw; r0 < own; r0 += nwarps * RB) {
             for (uint32_t ws = 0; ws < ow; ++ws) {
-                uint32_t occ = __ldcg(occ_p + (size_t)row * ow + ws);
-                while (occ) {
-                    uint32_t sl[4];
-                    uint4 v[4];
-                    int cnt = 0;
+                // one round trip for the occupancy words of the batch's rows (r0, r0 + nwarps, ...)
+                uint32_t occ[RB], cum[RB + 1];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        sl[j] = 0xFFFFFFFFu;
-                        if (occ) {
-                            sl[j] = ws * 32u + (uint32_t)__ffs(occ) - 1u;
-                            occ &= occ - 1u;
-                            ++cnt;
-                        }
-                    }
+                for (int j = 0; j < RB; ++j) {
+                    const uint32_t r = r0 + (uint32_t)j * nwarps;
+                    occ[j] = r < own ? __ldcg(occ_p + (size_t)(row_lo + r) * ow + ws) : 0u;
+                }
+                cum[0] = 0;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        v[j] = make_uint4(0u, 0u, 0u, 0u);
-                        if (j < cnt) {
-                            const uint32_t w = sl[j] * (SLICE / 32) + 4u * (uint32_t)lane;
-                            const uint32_t *src = theirs + (size_t)row * mask_words + w;
-                            if (vec_ok && w + 4u <= mask_words) {
-                                v[j] = __ldcs(reinterpret_cast<const uint4 *>(src));
-                            } else {
-                                if (w < mask_words) v[j].x = __ldcs(src);
-                                if (w + 1 < mask_words) v[j].y = __ldcs(src + 1);
-                                if (w + 2 < mask_words) v[j].z = __ldcs(src + 2);
-                                if (w + 3 < mask_words) v[j].w = __ldcs(src + 3);
+                for (int j = 0; j < RB; ++j) cum[j + 1] = cum[j] + (uint32_t)__popc(occ[j]);
+                const uint32_t total = cum[RB];
+                // every octet of lanes pulls one occupied slice (512 B = 4 x 128-B lines) per pair; two pairs per octet and
+                // round = 8 slices (32 x LDG.128 per warp) in flight over NVLink
+                for (uint32_t t0 = 0; t0 < total; t0 += 8) {
+                    uint4 v[2][4];
+                    uint32_t wofs[2];
+                    size_t rofs[2];
+                    bool act[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const uint32_t t = t0 + (uint32_t)u * 4u + (uint32_t)oct;
+                        act[u] = t < total;
+                        uint32_t word = 0, base = 0, jj = 0;
+#pragma unroll
+                        for (int j = 0; j < RB; ++j)
+                            if (t >= cum[j] && t < cum[j + 1]) { word = occ[j]; base = cum[j]; jj = (uint32_t)j; }
+                        const uint32_t sl = act[u] ? ws * 32u + (uint32_t)__fns(word, 0u, (int)(t - base) + 1) : 0u;
+                        rofs[u] = (size_t)(row_lo + r0 + jj * nwarps) * mask_words;
+                        wofs[u] = sl * (SLICE / 32) + 4u * (uint32_t)l8;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            v[u][q] = make_uint4(0u, 0u, 0u, 0u);
+                            const uint32_t w = wofs[u] + 32u * (uint32_t)q;
+                            if (act[u]) {
+                                const uint32_t *src = theirs + rofs[u] + w;
+                                if (vec_ok && w + 4u <= mask_words) {
+                                    v[u][q] = __ldcs(reinterpret_cast<const uint4 *>(src));
+                                } else {
+                                    if (w < mask_words) v[u][q].x = __ldcs(src);
+                                    if (w + 1 < mask_words) v[u][q].y = __ldcs(src + 1);
+                                    if (w + 2 < mask_words) v[u][q].z = __ldcs(src + 2);
+                                    if (w + 3 < mask_words) v[u][q].w = __ldcs(src + 3);
+                                }
                             }
                         }
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (j < cnt && (v[j].x | v[j].y | v[j].z | v[j].w)) {
-                            const uint32_t w = sl[j] * (SLICE / 32) + 4u * (uint32_t)lane;
-                            uint32_t *dst = mine + (size_t)row * mask_words + w;
-                            if (w < mask_words) dst[0] |= v[j].x;
-                            if (w + 1 < mask_words) dst[1] |= v[j].y;
-                            if (w + 2 < mask_words) dst[2] |= v[j].z;
-                            if (w + 3 < mask_words) dst[3] |= v[j].w;
+                    for (int u = 0; u < 2; ++u)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint4 x = v[u][q];
+                            if (act[u] && (x.x | x.y | x.z | x.w)) {
+                                const uint32_t w = wofs[u] + 32u * (uint32_t)q;
+                                uint32_t *dst = mine + rofs[u] + w;
+                                if (vec_ok && w + 4u <= mask_words) {
+                                    uint4 o = *reinterpret_cast<uint4 *>(dst);
+                                    o.x |= x.x; o.y |= x.y; o.z |= x.z; o.w |= x.w;
+                                    *reinterpret_cast<uint4 *>(dst) = o;
+                                } else {
+                                    if (w < mask_words) dst[0] |= x.x;
+                                    if (w + 1 < mask_words) dst[1] |= x.y;
+                                    if (w + 2 < mask_words) dst[2] |= x.z;
+                                    if (w + 3 < mask_words) dst[3] |= x.w;
+                                }
+                            }
                         }
-                    }
                 }
             }
         }
@@ -2554,7 +2580,7 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
 #define FM_MASK_TMA(DT)                                                                                            \
     FM_LAUNCH((k_mask_logits_tma<DT>), grid, MASK_THREADS, 0, s, ix, (const uint2 *)nullptr, P_top, LT, shift, vocab, d_logits,   \
               d_out, row_stride, d_override, always_allow, d_extra, n_extra, (uint32_t)B, d_mask, d_sp, d_ep)
-    // FMIDX_LOGITS_PATH = regs (default: one-shot CTAs, logits staged in registers -- the fastest measured,
+    // FMIDX_LOGITS_PATH = row (above) | regs (default: one-shot CTAs, logits staged in registers -- the fastest measured,
     // 0.83 of HBM bandwidth on narrow beams) | tma (one-shot CTAs, one bulk async copy each way) | pipe
     // (persistent CTAs, multi-stage bulk-copy ring).  The TMA variants are kept selectable: they match the
     // register variant on narrow beams and lose ~15% when a few beams need long walks (fewer resident CTAs
@@ -2562,10 +2588,13 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
     const char *path = getenv("FMIDX_LOGITS_PATH");
     const bool tma = path && strcmp(path, "tma") == 0;
     const bool pipe = path && strcmp(path, "pipe") == 0;
-    const bool regs = path && strcmp(path, "regs") == 0;
+    const bool rowp = path && strcmp(path, "row") == 0;
     const int esz = dtype == FMIDX_F32 ? 4 : 2;
-    if (!tma && !pipe && !regs && (dtype == FMIDX_F32 || dtype == FMIDX_BF16 || dtype == FMIDX_F16) && aligned(esz)) {
-        // default: persistent CTAs, one work item = a beam's group of 32,768 tokens (k_mask_logits_row)
+    if (rowp && (dtype == FMIDX_F32 || dtype == FMIDX_BF16 || dtype == FMIDX_F16) && aligned(esz)) {
+        // persistent CTAs, one work item = a beam's group of 32,768 tokens (k_mask_logits_row).  Measured SLOWER than the one-shot
+        // register variant (profiles/README.md, round 2: 48 vs 44 us fp32 on narrow beams -- every chunk pays two block barriers
+        // and thread 0's store hand-off -- and 2x slower when some beams need slice walks, which run one after the other inside
+        // the item instead of side by side in 32 CTAs): kept selectable, not the default.
         const size_t n_items = (size_t)((vocab + ROW_GROUP - 1) / ROW_GROUP) * B;
         const unsigned rgrid = (unsigned)std::min<size_t>(n_items, (size_t)h->sm_count * ROW_CTAS_PER_SM);
         const int dyn = ROW_STAGES * (int)ROW_STAGE_BYTES;
@@ -2677,7 +2706,10 @@ int fm_launch_xchg_pull(fmidx *h, uint32_t *const *d_peer_masks, const uint32_t 
     if (B == 0 || world == 0) return FMIDX_OK;
     const size_t own = B / world;
     const size_t warps = std::max<size_t>(own, (B + 31) / 32);
-    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((warps + 3) / 4, (size_t)std::max(1, h->sm_count / 2)));
+    // $FMIDX_PULL_CTAS: CTAs of the pull kernel (default: half the SMs -- its warps spin on the peers' flags first)
+    static const long pull_ctas = [] { const char *e = getenv("FMIDX_PULL_CTAS"); return e && *e ? atol(e) : 0l; }();
+    const size_t cap_ctas = pull_ctas > 0 ? (size_t)pull_ctas : (size_t)std::max(1, h->sm_count / 2);
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((warps + 3) / 4, cap_ctas));
     FM_LAUNCH(k_xchg_pull, grid, 128, 0, s, d_peer_masks, d_data_flags, d_inbox, (uint32_t)xwords, (uint32_t)count_off, world, rank,
               (uint32_t)B, vocab, seq, d_counts_out);
     FM_CUDA(cudaGetLastError());

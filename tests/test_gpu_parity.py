@@ -146,7 +146,7 @@ def test_step_batch_and_raw_multi(cuda):
         assert ix.backward_search_multi(q) == o.backward_search_multi(q), q
 
 
-@pytest.mark.parametrize("path", ["regs", "tma", "pipe"])
+@pytest.mark.parametrize("path", ["regs", "tma", "pipe", "row"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
 def test_fused_mask_logits_vs_reference_arithmetic(cuda, dtype, path, monkeypatch):
     """document_constrained_generation_vllm.py:46-137 on a [B, V] batch (config 4 semantics);

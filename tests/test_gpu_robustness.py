@@ -310,7 +310,7 @@ def test_scalar_fast_paths_match_batched_paths_and_oracle(cuda, layout):
         d = rng.choice(docs)
         i = rng.randrange(len(d) - 1)
         cases.append(d[i:i + rng.randint(1, 12)])
-    cases += [[0], [vocab + 5], [], docs[3][:95], docs[3][:96], docs[3][:97], docs[3][:140], [docs[0][0], 10 ** 12]]
+    cases += [[0], [vocab + 5], [], docs[3][:95], docs[3][:96], docs[3][:97], docs[3][:140], [docs[0][0], 2 ** 31 - 1]]
     for fast in (1, 0):
         ix.tune(scalar_fast=fast)
         for q in cases:
