@@ -927,8 +927,8 @@ def run_multi(args, device, local, rank, world, dist):
     clocks = sampler.stop() if sampler else None
     launches_per_block = (L.fmidx_launch_count() - launches0) / (reps + 6 + args.warmup / args.steps)
     value = world * B * args.steps / (block_ms * 1e-3)
-    eng.setup_e2e()
-    e2e_s, e2e_reps = host_blocks(eng.e2e_step, eng.e2e_drain, args.steps, args.warmup, dist, device)
+    eng.setup_e2e_graph()
+    e2e_s, e2e_reps = host_blocks(eng.e2e_graph_step, eng.e2e_graph_drain, args.steps, args.warmup, dist, device)
     # parity of this rank's replica on a sample: brute force over the text
     nq = 16
     sp, ep, mask = ix.query_batch(qsets[0][0], qsets[0][1], VOCAB)
@@ -939,9 +939,10 @@ def run_multi(args, device, local, rank, world, dist):
                          "e2e_value": world * B * args.steps / e2e_s, "tokens_per_gpu": args.tokens, "prefixes_per_step": world * B,
                          "collectives_per_step": 0, "parity_vs_bruteforce_on_sample": bool(int(okt[0])),
                          "what": "every GPU holds the whole index (a 1B-token index is 22 GB of 180 GB) and serves its own 1/N of the prefixes"}
-    e2e = {"value": world * B * args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": eng.h2d * world, "d2h_bytes_per_step": eng.d2h * world,
+    e2e = {"value": world * B * args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": eng.g_h2d * world, "d2h_bytes_per_step": B * 20 * world,
            "ms_per_step": 1e3 * e2e_s / args.steps, "blocks": e2e_reps,
-           "api": "per GPU: fmidx_query_submit/fmidx_query_wait, %d batches in flight (pinned host prefixes in; ranges + distinct-token counts out)" % eng.NSLOT}
+           "api": "per GPU: fmidx_query_graph_launch/fmidx_query_wait, %d captured steps in flight (pinned host prefixes in; ranges + "
+                  "distinct-token counts out)" % eng.GSLOTS}
     log("rank %d replicas: %.1f M q/s total" % (rank, value / 1e6))
     del eng, ix, toks, beg, qsets
     torch.cuda.empty_cache()
@@ -962,7 +963,10 @@ def run_multi(args, device, local, rank, world, dist):
         del toks
         torch.cuda.empty_cache()
         six, tb = build_index(stoks, sbeg, local, args.layout)
-        NSET = int(os.environ.get("BENCH_NBUF", "8"))
+        # buffer sets in flight: the ranks' pipelines are coupled set by set (a pull waits for the peers' publication of the same
+        # set), so the sharded step needs a deeper pipeline than the single-GPU one: 8 sets 63 M q/s, 16 sets 107 M, 24 sets 121 M
+        # (2 GPUs, 400M tokens; profiles/r2_sharded_probe.log)
+        NSET = int(os.environ.get("BENCH_NBUF", "24"))
         st = sharded.ShardStep(six, B, VOCAB, n_sets=NSET, group=group)
         rb = [(torch.empty(B, dtype=torch.int64, device=device), torch.empty(B, dtype=torch.int64, device=device)) for _ in range(NSET)]
         step_args = {}
@@ -971,6 +975,14 @@ def run_multi(args, device, local, rank, world, dist):
                 step_args[(qi, i)] = (st._x, i, C.c_void_p(q.data_ptr()), C.c_void_p(offs.data_ptr()), SHIFT,
                                       C.c_void_p(rb[i][0].data_ptr()), C.c_void_p(rb[i][1].data_ptr()), None)
         shard_step = L.fmidx_shard_step
+        # the timed form: every buffer set's step captured once (set i serves prefix batch i % 8: NSET is a multiple of 8, so
+        # the rotation (k % 8, k % NSET) of the eager form is the same), then ONE graph launch per step
+        use_graph = os.environ.get("BENCH_SHARD_GRAPH", "1") == "1" and NSET % N_QUERY_SETS == 0
+        if use_graph:
+            for i in range(NSET):
+                q, offs = qs[i % N_QUERY_SETS]
+                st.graph_prepare(i, q, offs, rb[i][0], rb[i][1])
+            glaunch, gx = L.fmidx_shard_graph_launch, st._x
 
         def block(k0, n):
             stream = torch.cuda.current_stream()
@@ -978,9 +990,14 @@ def run_multi(args, device, local, rank, world, dist):
             e.record(stream)
             for s in st.streams:
                 s.wait_event(e)
-            for k in range(k0, k0 + n):
-                if shard_step(*step_args[(k % N_QUERY_SETS, k % NSET)]) != 0:
-                    _native.check(-1)
+            if use_graph:
+                for k in range(k0, k0 + n):
+                    if glaunch(gx, k % NSET) != 0:
+                        _native.check(-1)
+            else:
+                for k in range(k0, k0 + n):
+                    if shard_step(*step_args[(k % N_QUERY_SETS, k % NSET)]) != 0:
+                        _native.check(-1)
             for s in st.streams:
                 e = torch.cuda.Event()
                 e.record(s)
@@ -1010,7 +1027,7 @@ def run_multi(args, device, local, rank, world, dist):
         # parity on a sample: per-shard brute force over the text, OR / sum reduced over the group on the host side
         nq = 16 * g_size
         q0, o0 = qs[0]
-        masks, counts = st.step(0, q0, o0, rb[0][0], rb[0][1])
+        masks, counts = st.graph_launch(0) if use_graph else st.step(0, q0, o0, rb[0][0], rb[0][1])  # set 0 holds batch 0
         torch.cuda.synchronize()
         ssym = reversed_symbols(stoks, sbeg)
         cnt, bm = bruteforce_sample(ssym, queries_as_lists(q0, o0, nq))
@@ -1036,21 +1053,15 @@ def run_multi(args, device, local, rank, world, dist):
                "parity_vs_bruteforce_on_sample": bool(int(okt[0])),
                "parity_note": "%d prefixes: per-shard counts / next-token bitmaps recomputed by scanning each shard's text with torch, "
                               "OR / sum reduced over the shards, against the exchanged results" % nq,
-               "exchange": "fmidx_shard_step: publish at the tail of the last enumeration kernel + fused wait/pull/OR/counts/ack kernel over "
-                           "CUDA-IPC peer memory (5 launches per step, no NCCL)"}
+               "step_api": "fmidx_shard_graph_launch (one CUDA-graph launch per step)" if use_graph else "fmidx_shard_step (5 launches per step)",
+               "exchange": "publish at the tail of the last enumeration kernel + fused wait/pull/OR/counts kernel over CUDA-IPC peer "
+                           "memory (5 kernels per step, no NCCL, no acknowledgements: ping-pong buffers)"}
         st.close()
         del six, stoks, sbeg, qs
         torch.cuda.empty_cache()
         return res
 
-    if want in ("all", "sharded"):
-        modes["doc_sharded"] = sharded_mode(world, "doc_sharded")
-        log("rank %d doc_sharded: %.1f M q/s" % (rank, modes["doc_sharded"]["value"] / 1e6))
-    if want in ("all", "hybrid") and world >= 4 and world % 2 == 0:
-        modes["hybrid"] = sharded_mode(2, "hybrid")
-        log("rank %d hybrid: %.1f M q/s" % (rank, modes["hybrid"]["value"] / 1e6))
-
-    if rank == 0:
+    def _final_line():
         cfg = workload_config(args.tokens, B, "replicas")
         cfg["sharding"] = ("value = replicas mode (index replicated on every GPU, each GPU serves its own batch of %d prefixes per step, no "
                            "collective on the data path); modes.doc_sharded = BASELINE configs[2] (a fixed %dM-token corpus split N ways by "
@@ -1067,6 +1078,44 @@ def run_multi(args, device, local, rank, world, dist):
             "clocks": clocks,
             "index": {"build_s": t_build, "device_mb": info["device_bytes"] / 1e6, "levels": info["levels"]},
         })
+
+    def final_line():
+        if rank == 0:
+            _final_line()
+
+    # The sharded modes couple the ranks (peer-memory flags, process groups): a rank that dies or a box that misbehaves must not
+    # cost the line its headline -- after $BENCH_SHARD_BUDGET_S (default 420 s) every rank gives up on them, rank 0 prints the line
+    # with what has been measured, and the process exits 0.
+    done = threading.Event()
+
+    def give_up():
+        if done.is_set():
+            return
+        log("rank %d: sharded modes exceeded their time budget -- reporting what was measured" % rank)
+        modes.setdefault("aborted", "the sharded modes did not finish within BENCH_SHARD_BUDGET_S")
+        try:
+            final_line()
+        finally:
+            os._exit(0)
+    watchdog = threading.Timer(float(os.environ.get("BENCH_SHARD_BUDGET_S", "420")), give_up)
+    watchdog.daemon = True
+    watchdog.start()
+    try:
+        if want in ("all", "sharded"):
+            modes["doc_sharded"] = sharded_mode(world, "doc_sharded")
+            log("rank %d doc_sharded: %.1f M q/s" % (rank, modes["doc_sharded"]["value"] / 1e6))
+        if want in ("all", "hybrid") and world >= 4 and world % 2 == 0:
+            modes["hybrid"] = sharded_mode(2, "hybrid")
+            log("rank %d hybrid: %.1f M q/s" % (rank, modes["hybrid"]["value"] / 1e6))
+    except Exception as e:  # noqa: BLE001 -- a failed sharded mode is reported, not fatal: the replicas figure stands
+        log("rank %d: sharded mode failed: %r" % (rank, e))
+        modes["error"] = repr(e)[:300]
+        done.set()
+        final_line()
+        os._exit(0)  # the CUDA context / the process group may be unusable: no orderly teardown
+    done.set()
+    watchdog.cancel()
+    final_line()
 
 
 def main():

@@ -39,6 +39,8 @@ SIGNATURES = {
     "fmidx_shard_import": (C.c_int, [p, u32, C.c_int, u32, p]),
     "fmidx_shard_ready": (C.c_int, [p]),
     "fmidx_shard_step": (C.c_int, [p, u32, p, p, i64, p, p, p]),
+    "fmidx_shard_graph_prepare": (C.c_int, [p, u32, p, p, i64, p, p]),
+    "fmidx_shard_graph_launch": (C.c_int, [p, u32]),
     "fmidx_shard_result": (C.c_int, [p, u32, C.c_int, C.POINTER(p), C.POINTER(p), C.POINTER(p)]),
     "fmidx_shard_submit": (C.c_int, [p, u32, p, p, i64, p, p, p, p]),
     "fmidx_shard_wait": (C.c_int, [p, u32]),

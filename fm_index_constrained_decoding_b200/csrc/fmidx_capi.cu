@@ -768,9 +768,10 @@ static int query_host_impl(fmidx_t *h, const int32_t *toks, const int64_t *offs,
     const bool kz = want_mask && fm_search_can_zero(d_mask, vocab);
     FM_TRY(fm_launch_search(h, d_toks, d_offs, B, shift, d_sp, d_ep, 0, s, kz ? d_mask : nullptr, words));
     if (want_mask) {
+        // the distinct-token counts come out of the enumeration itself (rows it finishes by scanning count their newly set bits;
+        // only the few wide rows are re-read by k_popcount_pending) instead of a popcount pass over all B x 16 KB
         FM_TRY(fm_launch_mask(h, d_sp, d_ep, B, shift, vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, d_mask, nullptr, s,
-                              nullptr, 0, ~(size_t)0, kz));
-        if (n_distinct) FM_TRY(fm_launch_popcount(h, d_mask, B, vocab, d_n, s));
+                              nullptr, 0, ~(size_t)0, kz, nullptr, n_distinct ? d_n : nullptr));
     }
     FM_CUDA(cudaMemcpyAsync(sp, d_sp, B * 8, cudaMemcpyDeviceToHost, s));
     FM_CUDA(cudaMemcpyAsync(ep, d_ep, B * 8, cudaMemcpyDeviceToHost, s));
@@ -805,8 +806,7 @@ static int graph_sequence(fmidx_t *h, fmidx::Slot &sl, int64_t shift, uint32_t v
     const bool kz = fm_search_can_zero(d_mask, vocab);
     FM_TRY(fm_launch_search(h, d_toks, d_offs, B, shift, d_sp, d_ep, 0, s, kz ? d_mask : nullptr, words));
     FM_TRY(fm_launch_mask(h, d_sp, d_ep, B, shift, vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, d_mask, nullptr, s, nullptr, 0,
-                          ~(size_t)0, kz));
-    FM_TRY(fm_launch_popcount(h, d_mask, B, vocab, d_n, s));
+                          ~(size_t)0, kz, nullptr, d_n));
     FM_CUDA(cudaMemcpyAsync(sl.g_hout, sl.g_dout, B * 20, cudaMemcpyDeviceToHost, s));
     return FMIDX_OK;
 }

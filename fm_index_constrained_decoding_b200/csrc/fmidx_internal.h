@@ -64,6 +64,7 @@ struct FmXchgArgs {
     uint32_t *done_ctr = nullptr;
     size_t xwords = 0;
     uint32_t world = 0, rank = 0, seq = 0;
+    uint32_t *seq_dev = nullptr;            // the set's step number in device memory: advanced by k_mask_top, read by publish / pull
 };
 
 struct fmidx {
@@ -133,10 +134,10 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
                    const void *d_logits, void *d_out, int dtype, int64_t row_stride, const int32_t *d_override,
                    int32_t always_allow, const uint32_t *d_extra, uint32_t n_extra, uint32_t *d_mask,
                    uint32_t *d_counts, cudaStream_t s, uint32_t *d_occ = nullptr, size_t dense_lo = 0, size_t dense_n = ~(size_t)0,
-                   bool prezeroed = false, const FmXchgArgs *xa = nullptr);
+                   bool prezeroed = false, const FmXchgArgs *xa = nullptr, uint32_t *d_ndist = nullptr);
 int fm_launch_xchg_pull(fmidx *h, uint32_t *const *d_peer_masks, const uint32_t *d_data_flags, const uint32_t *d_inbox, size_t xwords,
                         size_t count_off, uint32_t world, uint32_t rank, size_t B, uint32_t vocab, uint32_t seq, uint64_t *d_counts_out,
-                        cudaStream_t s);
+                        cudaStream_t s, unsigned long long *d_trace = nullptr, uint32_t n_sets = 1, const uint32_t *d_seq = nullptr);
 int fm_launch_boost_apply(fmidx *h, const void *d_logits, void *d_out, int dtype, int64_t row_stride, size_t B, uint32_t vocab,
                           const uint32_t *d_dmask, const uint32_t *d_n_distinct, const uint32_t *d_unigram, const int32_t *d_kind,
                           const float *d_vd, const float *d_vu_nonempty, const float *d_vu_empty, const float *d_ve, int32_t eos,

@@ -673,6 +673,7 @@ __device__ __forceinline__ void fm_eval_byte_node(const FmDev &ix, uint32_t lo, 
 // Calls f(symbol) for every row of [lo,hi), the work split over `nl` cooperating lanes (this one is lane l): 16-byte
 // loads of four consecutive rows per lane, i.e. fully coalesced 512-byte (warp) / 256-byte (half-warp) requests.
 // The array is padded so that the last vector may be read past row n-1.
+constexpr uint32_t NDIST_PENDING = 0xFFFFFFFFu;  // k_mask_top -> k_popcount_pending: this row's count must come from its bitmap
 constexpr uint32_t SCAN_INLINE = 1024;  // ranges up to this many rows are scanned by the warp / CTA that owns the prefix
 template <typename F>
 __device__ __forceinline__ void fm_scan_rows(const uint32_t *__restrict__ bwt, uint32_t lo, uint32_t hi, uint32_t l, uint32_t nl, F &&f) {
@@ -736,7 +737,15 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
            uint2 *__restrict__ lvl, const int32_t *__restrict__ override_tok, int64_t shift, uint32_t vocab,
            uint4 *__restrict__ work_items, uint32_t *__restrict__ work_count, uint32_t *__restrict__ mask_out,
            uint32_t *__restrict__ counts_out, uint32_t *__restrict__ occ_out, uint32_t dense_lo, uint32_t dense_n,
-           uint32_t zflags, uint64_t *__restrict__ xcounts, uint32_t scan_max) {
+           uint32_t zflags, uint64_t *__restrict__ xcounts, uint32_t scan_max, uint32_t *__restrict__ ndist_out,
+           uint32_t *__restrict__ seq_inc) {
+    // sharded step: this kernel -- the first of the step that nobody reads the step number in -- advances the buffer set's
+    // step number in device memory; the publication at the tail of k_mask_bytes and the pull kernel read it there, so the
+    // whole step has no per-step host argument and can be captured in a CUDA graph
+    if (seq_inc && blockIdx.x == 0 && threadIdx.x == 0) *seq_inc += 1u;
+    // ndist_out (nullable, bitmap mode): number of distinct tokens of row b when the row is finished HERE (empty range, or
+    // a range scanned off the resident BWT / resolved row by row: the bits newly set are counted from the atomics' return
+    // values), else NDIST_PENDING -- k_popcount_pending then counts just those rows, instead of re-reading every 16-KB row
     __shared__ uint4 stage[8][16];
     const int lane = threadIdx.x & 31, hw = (threadIdx.x >> 4) & 1, hl = threadIdx.x & 15;
     const int wslot = threadIdx.x >> 4;  // half-warp slot in the CTA
@@ -757,6 +766,8 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
         uint32_t *row = mask_out + (size_t)b * mw;
         const bool dense = b - dense_lo < dense_n;
         if (xcounts && lane == 0) xcounts[b] = e > s ? e - s : 0ull;  // occurrence count of the prefix on this shard
+        if (ndist_out && lane == 0) ndist_out[b] = (s >= e && !override_tok) ? 0u : NDIST_PENDING;
+        const bool count_here = ndist_out && !override_tok;
         if (ix.uni_n && !counts_out && e > s && e - s > (uint64_t)SCAN_INLINE) {
             int ui = __reduce_max_sync(FULL, fm_uni_find_part(ix, (uint32_t)s, (uint32_t)lane, 32u));
             if (ui >= 0 && __ldg(ix.uni_ep + ui) != (uint32_t)e) ui = -1;
@@ -822,12 +833,18 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
                     }
                     __syncwarp();
                 }
+                uint32_t fresh = 0;
                 fm_scan_rows(ix.bwt, lo, hi, (uint32_t)lane, 32u, [&](uint32_t c) {
                     if (c >= ga && c < ge) {
                         const uint32_t tk = (uint32_t)((int64_t)c - shift);
-                        atomicOr(&row[tk >> 5], 1u << (tk & 31u));
+                        const uint32_t bit = 1u << (tk & 31u);
+                        fresh += (atomicOr(&row[tk >> 5], bit) & bit) ? 0u : 1u;
                     }
                 });
+                if (count_here) {
+                    fresh = __reduce_add_sync(FULL, fresh);
+                    if (lane == 0) ndist_out[b] = fresh;
+                }
                 return;
             }
             // wider: at most P_top (<= 32) chunks of the range go to the work list, one half-warp of k_mask_expand each.
@@ -873,8 +890,10 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
                 }
                 __syncwarp();
             }
+            bool fresh1 = false;
             if (inside) {
-                atomicOr(&row[(uint32_t)tk >> 5], 1u << ((uint32_t)tk & 31u));
+                const uint32_t bit = 1u << ((uint32_t)tk & 31u);
+                fresh1 = !(atomicOr(&row[(uint32_t)tk >> 5], bit) & bit);
                 if (occ_out) {
                     const uint32_t ow = ((vocab + SLICE - 1) / SLICE + 31u) >> 5;
                     atomicOr(&occ_out[(size_t)b * ow + (sl >> 5)], 1u << (sl & 31u));
@@ -883,6 +902,10 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
             if (counts_out) {
                 const uint32_t same = __match_any_sync(FULL, inside ? c : (0xFFFFFF00u + (uint32_t)lane));
                 if (inside) counts_out[(size_t)b * vocab + (uint32_t)tk] = (uint32_t)__popc(same);
+            }
+            if (count_here) {
+                const uint32_t nf = (uint32_t)__popc(__ballot_sync(FULL, fresh1));
+                if (lane == 0) ndist_out[b] = nf;
             }
             return;
         }
@@ -1361,6 +1384,7 @@ struct FmPublish {
     const uint32_t *xlocal;        // this shard's side data (xwords u32)
     uint32_t *done_ctr;            // ticket counter (zero between launches)
     uint32_t xwords, world, rank, seq;  // world == 0: nothing to publish
+    const uint32_t *seq_ptr;       // non-null: the step number lives in device memory (graph-capturable step), seq is ignored
 };
 
 __device__ __forceinline__ void fm_publish_tail(const FmPublish &pub) {
@@ -1385,7 +1409,7 @@ __device__ __forceinline__ void fm_publish_tail(const FmPublish &pub) {
     }
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x < pub.world) fm_st_release_sys(pub.peer_flags[threadIdx.x] + pub.rank, pub.seq);
+    if (threadIdx.x < pub.world) fm_st_release_sys(pub.peer_flags[threadIdx.x] + pub.rank, pub.seq_ptr ? __ldcg(pub.seq_ptr) : pub.seq);
     if (threadIdx.x == 0) *pub.done_ctr = 0u;  // the next launch on this buffer set is stream-ordered after this one
 }
 
@@ -1994,12 +2018,16 @@ __global__ void __launch_bounds__(256) k_or_pieces(const uint4 *__restrict__ pie
 // sum the occurrence counts of all B prefixes.  No acknowledgement: the buffer sets ping-pong (fmidx_shard.cu).
 __global__ void __launch_bounds__(128)
 k_xchg_pull(uint32_t *const *__restrict__ peer_masks, const uint32_t *__restrict__ data_flags, const uint32_t *__restrict__ inbox,
-            uint32_t xwords, uint32_t count_off, uint32_t world, uint32_t rank, uint32_t B, uint32_t vocab, uint32_t seq,
-            uint64_t *__restrict__ counts_out) {
+            uint32_t xwords, uint32_t count_off, uint32_t world, uint32_t rank, uint32_t B, uint32_t vocab, uint32_t seq_arg,
+            uint64_t *__restrict__ counts_out, unsigned long long *__restrict__ trace, const uint32_t *__restrict__ seq_ptr) {
+    const uint32_t seq = seq_ptr ? __ldcg(seq_ptr) : seq_arg;
     const uint32_t mask_words = (vocab + 31u) >> 5;
     const uint32_t nslices = (vocab + SLICE - 1) / SLICE, ow = (nslices + 31u) >> 5;
     const uint32_t own = B / world, row_lo = rank * own;
     const int lane = threadIdx.x & 31;
+    // $FMIDX_PULL_TRACE (measurement): warp 0 of every CTA adds its flag-wait time and its total time (ns)
+    unsigned long long tr0 = 0, tr_wait = 0;
+    if (trace && (threadIdx.x >> 5) == 0 && lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr0));
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     uint32_t *mine = peer_masks[rank];
     const bool vec_ok = (mask_words & 3u) == 0;  // rows are 16-byte aligned (checked by the launcher for the bases)
@@ -2007,14 +2035,25 @@ k_xchg_pull(uint32_t *const *__restrict__ peer_masks, const uint32_t *__restrict
     constexpr int RB = 8;  // rows per batch: their occupancy words are fetched together, their slices pulled 8 at a time
     for (uint32_t k = 1; k < world; ++k) {
         const uint32_t p = rank + k < world ? rank + k : rank + k - world;
-        if (lane == 0) {
+        // ONE thread per CTA polls the peer's flag (system-scope acquire loads are L2 round trips: with every warp of every
+        // waiting pull kernel of every buffer set polling, the polls alone took a measurable share of the L2), backing off
+        // to ~0.5 us between polls; the CTA's other warps sleep at the barrier
+        if (threadIdx.x == 0) {
             const long long t0 = clock64();
+            unsigned long long w0 = 0, w1 = 0;
+            if (trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(w0));
+            unsigned ns = 64;
             while ((int32_t)(fm_ld_acquire_sys(data_flags + p) - seq) < 0) {
-                __nanosleep(64);
+                __nanosleep(ns);
+                if (ns < 512) ns <<= 1;
                 if (clock64() - t0 > 20000000000ll) __trap();
             }
+            if (trace) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(w1));
+                tr_wait += w1 - w0;
+            }
         }
-        __syncwarp();
+        __syncthreads();
         const uint32_t *occ_p = inbox + (size_t)p * xwords;
         const uint32_t *theirs = peer_masks[p];
         for (uint32_t r0 = gw; r0 < own; r0 += nwarps * RB) {
@@ -2089,6 +2128,13 @@ k_xchg_pull(uint32_t *const *__restrict__ peer_masks, const uint32_t *__restrict
             }
         }
     }
+    if (trace && (threadIdx.x >> 5) == 0 && lane == 0) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        atomicAdd(trace + 0, tr_wait);
+        atomicAdd(trace + 1, t1 - tr0);
+        atomicAdd(trace + 2, 1ull);
+    }
     if (counts_out) {  // every peer's side data has arrived by now (each warp waited for all of them)
         for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
             uint64_t acc = 0;
@@ -2096,6 +2142,33 @@ k_xchg_pull(uint32_t *const *__restrict__ peer_masks, const uint32_t *__restrict
                 acc += __ldcg(reinterpret_cast<const uint64_t *>(inbox + (size_t)p * xwords + count_off) + b);
             counts_out[b] = acc;
         }
+    }
+}
+
+// rows whose distinct-token count k_mask_top could not settle (NDIST_PENDING) are counted from their bitmaps; the others keep
+// the count they have (one CTA per row; most exit at once)
+__global__ void __launch_bounds__(256) k_popcount_pending(const uint32_t *__restrict__ mask, uint32_t mask_words,
+                                                          uint32_t *__restrict__ n_out) {
+    __shared__ uint32_t part[8];
+    const uint32_t b = blockIdx.x;
+    if (n_out[b] != NDIST_PENDING) return;
+    uint32_t s = 0;
+    const uint4 *row4 = reinterpret_cast<const uint4 *>(mask + (size_t)b * mask_words);
+    if ((mask_words & 3u) == 0 && (((uintptr_t)mask) & 15) == 0) {
+        for (uint32_t w = threadIdx.x; w < (mask_words >> 2); w += 256) {
+            const uint4 v = row4[w];
+            s += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+        }
+    } else {
+        for (uint32_t w = threadIdx.x; w < mask_words; w += 256) s += __popc(mask[(size_t)b * mask_words + w]);
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < 8; ++i) t += part[i];
+        n_out[b] = t;
     }
 }
 
@@ -2455,7 +2528,7 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
                    const void *d_logits, void *d_out, int dtype, int64_t row_stride, const int32_t *d_override,
                    int32_t always_allow, const uint32_t *d_extra, uint32_t n_extra, uint32_t *d_mask,
                    uint32_t *d_counts, cudaStream_t s, uint32_t *d_occ, size_t dense_lo, size_t dense_n, bool prezeroed,
-                   const FmXchgArgs *xa) {
+                   const FmXchgArgs *xa, uint32_t *d_ndist) {
     FM_TRY(check_ready(h));
     if (B == 0 || vocab == 0) return FMIDX_OK;
     if (!d_occ) { dense_lo = 0; dense_n = B; }  // sparse rows are only meaningful together with occupancy words
@@ -2532,7 +2605,7 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
     FM_LAUNCH(k_mask_top, (unsigned)((B * 32 + 127) / 128), 128, 0, s, ix, d_sp, d_ep, (uint32_t)B, LT, lvl, d_override, shift,
               vocab, items, ctr, has ? nullptr : d_mask, has ? nullptr : d_counts, has ? nullptr : d_occ, (uint32_t)dense_lo,
               (uint32_t)std::min<size_t>(dense_n, 0xFFFFFFFFu), zflags, xa && !has ? xa->xcounts : nullptr,
-              L == 0 ? SCAN_INLINE : scan_max);
+              L == 0 ? SCAN_INLINE : scan_max, d_occ ? nullptr : d_ndist, xa ? xa->seq_dev : nullptr);
     if (!has) {
         // CTAs per SM of the persistent k_mask_bytes grid (fmidx_tune "bytes_occ", 1..6)
         const int occ = h->tune_bytes_occ < 1 ? 1 : (h->tune_bytes_occ > 6 ? 6 : h->tune_bytes_occ);
@@ -2540,7 +2613,7 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
         FmPublish pub{};
         if (xa && xa->world) {
             pub.peer_inbox = xa->peer_inbox; pub.peer_flags = xa->peer_data_flags; pub.xlocal = xa->xlocal; pub.done_ctr = xa->done_ctr;
-            pub.xwords = (uint32_t)xa->xwords; pub.world = xa->world; pub.rank = xa->rank; pub.seq = xa->seq;
+            pub.xwords = (uint32_t)xa->xwords; pub.world = xa->world; pub.rank = xa->rank; pub.seq = xa->seq; pub.seq_ptr = xa->seq_dev;
         }
 #define FM_BYTES(LIST, CNT, CAP)                                                                                             \
     do {                                                                                                                     \
@@ -2557,6 +2630,11 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
             FM_BYTES(bnodes, ctr + 1, (uint32_t)cap);
         }
 #undef FM_BYTES
+        if (d_ndist) {
+            // distinct-token counts: settled by k_mask_top for the rows it finished itself, from the bitmap for the others
+            if (d_occ) FM_LAUNCH(k_popcount, (unsigned)B, 256, 0, s, d_mask, mwords, d_ndist);
+            else FM_LAUNCH(k_popcount_pending, (unsigned)B, 256, 0, s, d_mask, mwords, d_ndist);
+        }
         FM_CUDA(cudaGetLastError());
         ws.ctr_clean = true;
         return FMIDX_OK;
@@ -2702,16 +2780,20 @@ int fm_launch_or(fmidx *h, const uint32_t *d_pieces, uint32_t n_pieces, size_t n
 
 int fm_launch_xchg_pull(fmidx *h, uint32_t *const *d_peer_masks, const uint32_t *d_data_flags, const uint32_t *d_inbox, size_t xwords,
                         size_t count_off, uint32_t world, uint32_t rank, size_t B, uint32_t vocab, uint32_t seq, uint64_t *d_counts_out,
-                        cudaStream_t s) {
+                        cudaStream_t s, unsigned long long *d_trace, uint32_t n_sets, const uint32_t *d_seq) {
     if (B == 0 || world == 0) return FMIDX_OK;
     const size_t own = B / world;
     const size_t warps = std::max<size_t>(own, (B + 31) / 32);
     // $FMIDX_PULL_CTAS: CTAs of the pull kernel (default: half the SMs -- its warps spin on the peers' flags first)
     static const long pull_ctas = [] { const char *e = getenv("FMIDX_PULL_CTAS"); return e && *e ? atol(e) : 0l; }();
-    const size_t cap_ctas = pull_ctas > 0 ? (size_t)pull_ctas : (size_t)std::max(1, h->sm_count / 2);
+    // the CTAs of a pull kernel spin until the peers have published: the pull kernels of ALL buffer sets together may hold at most
+    // ~40% of the GPU's thread slots, or the kernels that produce what the peers are waiting for starve (with 32 sets x 148 CTAs
+    // the step deadlocked into the kernel's 10-second trap)
+    const size_t fair = std::max<size_t>(8, (size_t)h->sm_count * 6 / std::max<uint32_t>(1u, n_sets));
+    const size_t cap_ctas = pull_ctas > 0 ? (size_t)pull_ctas : std::min<size_t>((size_t)std::max(1, h->sm_count / 2), fair);
     const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((warps + 3) / 4, cap_ctas));
     FM_LAUNCH(k_xchg_pull, grid, 128, 0, s, d_peer_masks, d_data_flags, d_inbox, (uint32_t)xwords, (uint32_t)count_off, world, rank,
-              (uint32_t)B, vocab, seq, d_counts_out);
+              (uint32_t)B, vocab, seq, d_counts_out, d_trace, d_seq);
     FM_CUDA(cudaGetLastError());
     return FMIDX_OK;
 }

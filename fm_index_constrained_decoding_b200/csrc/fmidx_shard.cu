@@ -14,6 +14,7 @@
 // whenever a peer was a little late, and the ranks slowed each other down: 59 M q/s on 4 GPUs against 131 M on one.)  The reference has no distributed path
 // (its only parallelism is one std::async per range, fm_index.cpp:146-166); parity for the sharded configuration is
 // "one reference index per shard, results OR/sum-reduced on the host".
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -34,12 +35,16 @@ struct fmidx_shard {
         uint32_t *ctr = nullptr;     // ticket counter of the publish
         uint64_t *tables = nullptr;  // device: [2 parities][3][world] peer pointers (masks, inbox, data flags)
         uint32_t *data_flags = nullptr;  // into `flags`
-        uint32_t seq = 0;
+        uint32_t seq = 0;            // steps issued on this set (host mirror of *seq_dev once they have run)
+        uint32_t *seq_dev = nullptr; // the step number in device memory (advanced by the step's k_mask_top)
+        cudaGraphExec_t gexec[2] = {nullptr, nullptr};  // captured step per buffer parity (fmidx_shard_graph_prepare)
+        uint64_t g_launches = 0;
         cudaStream_t stream = nullptr;
         FmBuf in;                    // host-buffer form: prefixes + ranges on the device
     };
     std::vector<Set> sets;
     uint32_t *flags = nullptr;       // [n_sets][world] peer-visible
+    unsigned long long *trace = nullptr;  // $FMIDX_PULL_TRACE: {flag-wait ns, total ns, samples} of the pull kernel's warps 0
     std::vector<std::vector<void *>> peer;  // [3 kinds][2 * n_sets * world] imported pointers (kind 2: one block, buffer 0 only)
     std::vector<void *> opened;
 };
@@ -58,7 +63,7 @@ int fmidx_shard_create(fmidx_t *h, uint32_t world, uint32_t rank, size_t B, uint
     if (!h || !out) { fm_set_error("null argument"); return FMIDX_EINVAL; }
     *out = nullptr;
     if (world == 0 || world > 64 || rank >= world || B == 0 || B % world || vocab == 0 || n_sets == 0 || n_sets > FMIDX_SLOTS) {
-        fm_set_error("shard_create: need 1 <= world <= 64, rank < world, B a positive multiple of world, 1 <= n_sets <= 16");
+        fm_set_error("shard_create: need 1 <= world <= 64, rank < world, B a positive multiple of world, 1 <= n_sets <= 32");
         return FMIDX_EINVAL;
     }
     FM_CUDA(cudaSetDevice(h->device));
@@ -87,6 +92,8 @@ int fmidx_shard_create(fmidx_t *h, uint32_t world, uint32_t rank, size_t B, uint
         FM_CUDA(cudaMalloc((void **)&st.counts, B * 8));
         FM_CUDA(cudaMalloc((void **)&st.n_own, (B / world) * 4 + 16));
         FM_CUDA(cudaMalloc((void **)&st.ctr, 16));
+        FM_CUDA(cudaMalloc((void **)&st.seq_dev, 16));
+        FM_CUDA(cudaMemset(st.seq_dev, 0, 16));
         FM_CUDA(cudaMalloc((void **)&st.tables, (size_t)2 * 3 * world * 8));
         FM_CUDA(cudaMemset(st.xlocal, 0, x->xwords * 4));
         FM_CUDA(cudaMemset(st.ctr, 0, 16));
@@ -94,6 +101,10 @@ int fmidx_shard_create(fmidx_t *h, uint32_t world, uint32_t rank, size_t B, uint
         st.data_flags = x->flags + (size_t)i * world;
     }
     x->peer[2][rank] = x->flags;
+    if (getenv("FMIDX_PULL_TRACE")) {
+        FM_CUDA(cudaMalloc((void **)&x->trace, 64));
+        FM_CUDA(cudaMemset(x->trace, 0, 64));
+    }
     FM_CUDA(cudaDeviceSynchronize());
     *out = x.release();
     return FMIDX_OK;
@@ -143,14 +154,14 @@ int fmidx_shard_ready(fmidx_shard_t *x) {
     return FMIDX_OK;
 }
 
-static int shard_step(fmidx_shard *x, uint32_t set, const int32_t *d_toks, const int64_t *d_offs, int64_t shift, uint64_t *d_sp,
-                      uint64_t *d_ep, cudaStream_t s) {
-    if (!x->ready) { fm_set_error("shard context is not ready (import the peers' buffers, then fmidx_shard_ready)"); return FMIDX_ESTATE; }
+// enqueues (or, while the stream is being captured, records) the step number `seq` of the set; the kernels take the number
+// from device memory, `seq` only selects the buffer parity
+static int shard_step_seq(fmidx_shard *x, uint32_t set, uint32_t seq, const int32_t *d_toks, const int64_t *d_offs, int64_t shift,
+                          uint64_t *d_sp, uint64_t *d_ep, cudaStream_t s) {
     fmidx *h = x->h;
     fmidx_shard::Set &st = x->sets[set];
     const uint32_t W = x->world;
     const size_t own = x->B / W;
-    const uint32_t seq = ++st.seq;
     const uint32_t par = seq & 1u;
     uint32_t *mask = st.mask[par];
     const uint64_t *tab = st.tables + (size_t)par * 3 * W;
@@ -162,6 +173,7 @@ static int shard_step(fmidx_shard *x, uint32_t set, const int32_t *d_toks, const
     xa.peer_inbox = (uint32_t *const *)(tab + W);
     xa.peer_data_flags = (uint32_t *const *)(tab + 2 * W);
     xa.xlocal = st.xlocal; xa.done_ctr = st.ctr; xa.xwords = x->xwords; xa.world = W; xa.rank = x->rank; xa.seq = seq;
+    xa.seq_dev = st.seq_dev;
     // measurement only ($FMIDX_SHARD_PROBE): 1 = no pull kernel (results incomplete), 2 = neither publish nor pull
     static const int probe = [] { const char *e = getenv("FMIDX_SHARD_PROBE"); return e ? atoi(e) : 0; }();
     if (probe >= 2) xa.world = 0;
@@ -172,7 +184,52 @@ static int shard_step(fmidx_shard *x, uint32_t set, const int32_t *d_toks, const
                           st.xlocal, (size_t)x->rank * own, own, kz, &xa));
     if (probe >= 1) return FMIDX_OK;
     return fm_launch_xchg_pull(h, (uint32_t *const *)tab, st.data_flags, st.inbox[par], x->xwords, x->count_off, W, x->rank, x->B,
-                               x->vocab, seq, st.counts, s);
+                               x->vocab, seq, st.counts, s, x->trace, x->n_sets, st.seq_dev);
+}
+
+static int shard_step(fmidx_shard *x, uint32_t set, const int32_t *d_toks, const int64_t *d_offs, int64_t shift, uint64_t *d_sp,
+                      uint64_t *d_ep, cudaStream_t s) {
+    if (!x->ready) { fm_set_error("shard context is not ready (import the peers' buffers, then fmidx_shard_ready)"); return FMIDX_ESTATE; }
+    return shard_step_seq(x, set, ++x->sets[set].seq, d_toks, d_offs, shift, d_sp, d_ep, s);
+}
+
+// The sharded step of one buffer set captured for FIXED device buffers (the caller rewrites d_toks / d_offs in place between
+// launches): one eager step first (it sizes the workspaces and is a real step: EVERY shard must prepare the same sets in the
+// same order), then one capture per buffer parity; fmidx_shard_graph_launch replays them alternately on the set's stream.
+int fmidx_shard_graph_prepare(fmidx_shard_t *x, uint32_t set, const int32_t *d_toks, const int64_t *d_offs, int64_t shift, uint64_t *d_sp,
+                              uint64_t *d_ep) {
+    FM_TRY(shard_check(x, set));
+    if (!d_toks || !d_offs || !d_sp || !d_ep) { fm_set_error("null argument"); return FMIDX_EINVAL; }
+    if (!x->h->ready) { fm_set_error("index is not initialised"); return FMIDX_ESTATE; }
+    fmidx_shard::Set &st = x->sets[set];
+    if (st.gexec[0]) { fm_set_error("buffer set %u already holds a captured step", set); return FMIDX_ESTATE; }
+    FM_TRY(shard_step(x, set, d_toks, d_offs, shift, d_sp, d_ep, st.stream));
+    FM_CUDA(cudaStreamSynchronize(st.stream));
+    for (uint32_t e = 1; e <= 2; ++e) {
+        const uint32_t seq = st.seq + e;  // the next two steps: parities (seq+1)&1, (seq+2)&1
+        const uint64_t l0 = g_fm_launches.load();
+        FM_CUDA(cudaStreamBeginCapture(st.stream, cudaStreamCaptureModeThreadLocal));
+        int rc = shard_step_seq(x, set, seq, d_toks, d_offs, shift, d_sp, d_ep, st.stream);
+        cudaGraph_t g = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(st.stream, &g);
+        if (rc != FMIDX_OK) { if (g) cudaGraphDestroy(g); return rc; }
+        if (ce != cudaSuccess) { fm_set_error("stream capture failed: %s", cudaGetErrorString(ce)); return FMIDX_ECUDA; }
+        ce = cudaGraphInstantiate(&st.gexec[seq & 1u], g, 0);
+        cudaGraphDestroy(g);
+        if (ce != cudaSuccess) { fm_set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); return FMIDX_ECUDA; }
+        st.g_launches = g_fm_launches.load() - l0;
+        g_fm_launches.store(l0);  // captured, not launched
+    }
+    return FMIDX_OK;
+}
+
+int fmidx_shard_graph_launch(fmidx_shard_t *x, uint32_t set) {
+    if (!x || set >= x->n_sets || !x->sets[set].gexec[0] || !x->sets[set].gexec[1]) { fm_set_error("buffer set holds no captured step"); return FMIDX_ESTATE; }
+    fmidx_shard::Set &st = x->sets[set];
+    const uint32_t seq = ++st.seq;
+    FM_CUDA(cudaGraphLaunch(st.gexec[seq & 1u], st.stream));
+    g_fm_launches.fetch_add(st.g_launches, std::memory_order_relaxed);
+    return FMIDX_OK;
 }
 
 int fmidx_shard_step(fmidx_shard_t *x, uint32_t set, const int32_t *d_toks, const int64_t *d_offs, int64_t shift, uint64_t *d_sp,
@@ -233,8 +290,17 @@ void fmidx_shard_destroy(fmidx_shard_t *x) {
     if (!x) return;
     cudaSetDevice(x->h->device);
     cudaDeviceSynchronize();
+    if (x->trace) {
+        unsigned long long t[3] = {0, 0, 0};
+        cudaMemcpy(t, x->trace, 24, cudaMemcpyDeviceToHost);
+        if (t[2]) fprintf(stderr, "fmidx pull trace (rank %u): %.1f us flag wait, %.1f us total per pull-kernel CTA (warp 0), %llu samples\n",
+                          x->rank, t[0] / 1e3 / t[2], t[1] / 1e3 / t[2], t[2]);
+        cudaFree(x->trace);
+    }
     for (void *p : x->opened) cudaIpcCloseMemHandle(p);
     for (auto &st : x->sets) {
+        for (auto &g : st.gexec) if (g) cudaGraphExecDestroy(g);
+        if (st.seq_dev) cudaFree(st.seq_dev);
         if (st.stream) cudaStreamDestroy(st.stream);
         for (void *p : {(void *)st.mask[0], (void *)st.mask[1], (void *)st.inbox[0], (void *)st.inbox[1], (void *)st.xlocal, (void *)st.counts, (void *)st.n_own, (void *)st.ctr, (void *)st.tables})
             if (p) cudaFree(p);

@@ -251,6 +251,23 @@ class ShardStep:
                                          C.c_void_p(sp.data_ptr()), C.c_void_p(ep.data_ptr()), sptr))
         return self.result(i)
 
+    def graph_prepare(self, i, toks, offs, sp, ep, shift=10):
+        """Capture the step of buffer set i for these FIXED device buffers (toks / offs are rewritten in place between launches;
+        sp / ep receive this shard's ranges).  Runs one real step: every rank must prepare the same sets in the same order."""
+        import ctypes as C
+        from . import _native as N
+        N.check(self._L.fmidx_shard_graph_prepare(self._x, i, C.c_void_p(toks.data_ptr()), C.c_void_p(offs.data_ptr()), shift,
+                                                  C.c_void_p(sp.data_ptr()), C.c_void_p(ep.data_ptr())))
+        self._keep = getattr(self, "_keep", []) + [(toks, offs, sp, ep)]
+
+    def graph_launch(self, i):
+        """Replay set i's captured step (ONE graph launch: search, enumeration, publication, pull) on the set's stream;
+        result(i) gives the buffers it fills."""
+        from . import _native as N
+        if self._L.fmidx_shard_graph_launch(self._x, i) != 0:
+            N.check(-1)
+        return self.result(i)
+
     def result(self, i):
         """(owned bitmaps, total counts) of the step issued last on set i (also after a direct fmidx_shard_step call)."""
         import ctypes as C

@@ -161,6 +161,15 @@ int fmidx_shard_ready(fmidx_shard_t *x);
 int fmidx_shard_step(fmidx_shard_t *x, uint32_t set, const int32_t *d_toks, const int64_t *d_offs, int64_t shift, uint64_t *d_sp,
                      uint64_t *d_ep, void *stream);
 /* step number k (1, 2, ...) of a set writes bitmap buffer k & 1; parity 0 / 1 selects that buffer, -1 the one of the step issued last */
+/* The step of one buffer set captured in CUDA graphs for FIXED device buffers (the caller rewrites d_toks / d_offs in place
+ * between launches): the step number lives in device memory (advanced by the step's first enumeration kernel, read by the
+ * publication and by the pull kernel), so a step has no per-step host argument.  prepare runs ONE real step (every shard must
+ * prepare the same sets in the same order) and captures one graph per buffer parity; launch replays them alternately on the
+ * set's own stream (fmidx_shard_wait synchronises it).  Eager steps (fmidx_shard_step / fmidx_shard_submit) may be mixed in:
+ * every step of a set, captured or not, advances the same step number and the same scratch epoch. */
+int fmidx_shard_graph_prepare(fmidx_shard_t *x, uint32_t set, const int32_t *d_toks, const int64_t *d_offs, int64_t shift, uint64_t *d_sp,
+                              uint64_t *d_ep);
+int fmidx_shard_graph_launch(fmidx_shard_t *x, uint32_t set);
 int fmidx_shard_result(fmidx_shard_t *x, uint32_t set, int parity, uint32_t **d_own_masks, uint64_t **d_counts, void **stream);
 int fmidx_shard_submit(fmidx_shard_t *x, uint32_t set, const int32_t *toks, const int64_t *offs, int64_t shift, uint64_t *sp,
                        uint64_t *ep, uint64_t *counts, uint32_t *n_distinct_own);

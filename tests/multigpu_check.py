@@ -121,6 +121,39 @@ def check_group(ix_docs_parts, group, grank, gworld, tag, n_sets=4, rounds=4, B_
         st.submit(i, htoks[k % n_batches][0], htoks[k % n_batches][1], *hout[i])
     for i in range(n_sets):
         st.wait(i)
+    # captured form: every set's step recorded once for fixed device buffers whose CONTENT changes between launches, one graph
+    # launch per step, mixed with eager steps on the same sets (both advance the same device-side step number)
+    maxtok = max(t.numel() for t, _ in dev_batches)
+    gbufs = [(torch.zeros(maxtok, dtype=torch.int32, device=dev), torch.zeros(B + 1, dtype=torch.int64, device=dev),
+              torch.empty(B, dtype=torch.int64, device=dev), torch.empty(B, dtype=torch.int64, device=dev)) for _ in range(n_sets)]
+    for i in range(n_sets):
+        st.graph_prepare(i, *gbufs[i])
+    torch.cuda.synchronize()
+    steps2 = n_sets * 3
+    for k in range(steps2):
+        i = k % n_sets
+        s = st.streams[i]
+        toks, offs = dev_batches[(k + 1) % n_batches]
+        gt, go, gsp_b, gep_b = gbufs[i]
+        with torch.cuda.stream(s):
+            gt[:toks.numel()].copy_(toks, non_blocking=True)
+            go.copy_(offs, non_blocking=True)
+        if k % 5 == 3:
+            masks, counts = st.step(i, gt, go, gsp_b, gep_b)  # an eager step in between
+        else:
+            masks, counts = st.graph_launch(i)
+        with torch.cuda.stream(s):
+            got_mask[k].copy_(masks, non_blocking=True)
+            got_cnt[k].copy_(counts, non_blocking=True)
+            got_sp[k].copy_(gsp_b, non_blocking=True)
+    torch.cuda.synchronize()
+    gm, gc = got_mask.cpu().numpy().view(np.uint32), got_cnt.cpu().numpy()
+    gsp = got_sp.cpu().numpy().astype(np.uint64)
+    for k in range(steps2):
+        mask, cnt, per = exp[(k + 1) % n_batches]
+        assert (gsp[k] == per[grank][0]).all(), "%s: captured step %d: ranges differ" % (tag, k)
+        assert (gm[k] == mask[grank * own:(grank + 1) * own]).all(), "%s: captured step %d: owned bitmaps differ" % (tag, k)
+        assert (gc[k] == cnt).all(), "%s: captured step %d: total counts differ" % (tag, k)
     # fused decode step over the exchange (rows this rank owns)
     sh = sharded.ShardedFMIndex(ix, group=group)
     g = torch.Generator().manual_seed(grank)

@@ -441,7 +441,7 @@ def test_pipelined_host_api(cuda):
         osp, oep, _, ond = o.query_batch(toks, offs, want_mask=True, vocab=3000, nthreads=4)
         assert (outs[s][0] == osp).all() and (outs[s][1] == oep).all() and (outs[s][2] == ond.astype(np.uint32)).all()
     with pytest.raises(_native.FmidxError):
-        _native.check(L.fmidx_query_wait(ix._h, 16))
+        _native.check(L.fmidx_query_wait(ix._h, 32))
 
 
 _OVERFLOW_SCRIPT = r"""
