@@ -833,17 +833,25 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
                     }
                     __syncwarp();
                 }
-                uint32_t fresh = 0;
-                fm_scan_rows(ix.bwt, lo, hi, (uint32_t)lane, 32u, [&](uint32_t c) {
-                    if (c >= ga && c < ge) {
-                        const uint32_t tk = (uint32_t)((int64_t)c - shift);
-                        const uint32_t bit = 1u << (tk & 31u);
-                        fresh += (atomicOr(&row[tk >> 5], bit) & bit) ? 0u : 1u;
-                    }
-                });
                 if (count_here) {
+                    // the atomics' return values tell which bits were new (ATOM: a round trip per row -- only when asked for)
+                    uint32_t fresh = 0;
+                    fm_scan_rows(ix.bwt, lo, hi, (uint32_t)lane, 32u, [&](uint32_t c) {
+                        if (c >= ga && c < ge) {
+                            const uint32_t tk = (uint32_t)((int64_t)c - shift);
+                            const uint32_t bit = 1u << (tk & 31u);
+                            fresh += (atomicOr(&row[tk >> 5], bit) & bit) ? 0u : 1u;
+                        }
+                    });
                     fresh = __reduce_add_sync(FULL, fresh);
                     if (lane == 0) ndist_out[b] = fresh;
+                } else {
+                    fm_scan_rows(ix.bwt, lo, hi, (uint32_t)lane, 32u, [&](uint32_t c) {
+                        if (c >= ga && c < ge) {
+                            const uint32_t tk = (uint32_t)((int64_t)c - shift);
+                            atomicOr(&row[tk >> 5], 1u << (tk & 31u));  // RED: fire and forget
+                        }
+                    });
                 }
                 return;
             }
@@ -893,7 +901,8 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
             bool fresh1 = false;
             if (inside) {
                 const uint32_t bit = 1u << ((uint32_t)tk & 31u);
-                fresh1 = !(atomicOr(&row[(uint32_t)tk >> 5], bit) & bit);
+                if (count_here) fresh1 = !(atomicOr(&row[(uint32_t)tk >> 5], bit) & bit);
+                else atomicOr(&row[(uint32_t)tk >> 5], bit);
                 if (occ_out) {
                     const uint32_t ow = ((vocab + SLICE - 1) / SLICE + 31u) >> 5;
                     atomicOr(&occ_out[(size_t)b * ow + (sl >> 5)], 1u << (sl & 31u));
@@ -2016,126 +2025,111 @@ __global__ void __launch_bounds__(256) k_or_pieces(const uint4 *__restrict__ pie
 // occupied 4096-token slices (512 B each, one LDG.128 per lane, four slices in flight) straight out of the peer's
 // bitmap buffer over NVLink, OR-ing them into this rank's own rows in place.  When every peer has been read the warps
 // sum the occurrence counts of all B prefixes.  No acknowledgement: the buffer sets ping-pong (fmidx_shard.cu).
-__global__ void __launch_bounds__(128)
-k_xchg_pull(uint32_t *const *__restrict__ peer_masks, const uint32_t *__restrict__ data_flags, const uint32_t *__restrict__ inbox,
-            uint32_t xwords, uint32_t count_off, uint32_t world, uint32_t rank, uint32_t B, uint32_t vocab, uint32_t seq_arg,
-            uint64_t *__restrict__ counts_out, unsigned long long *__restrict__ trace, const uint32_t *__restrict__ seq_ptr) {
+// k_xchg_wait: ONE small CTA, warp p spins (system-scope acquire loads, backing off to ~0.5 us) until peer p has published
+// this step.  The waiting is separated from the pulling so that nothing that spins ever holds more than one CTA: the pull
+// kernels of all buffer sets used to spin with their whole grids, which capped their size (deadlock otherwise) and left the
+// pull itself with too few loads in flight for NVLink's loaded latency (4 GPUs: 220 us of pulling per step).
+__global__ void __launch_bounds__(1024)
+k_xchg_wait(const uint32_t *__restrict__ data_flags, uint32_t world, uint32_t rank, uint32_t seq_arg, const uint32_t *__restrict__ seq_ptr,
+            unsigned long long *__restrict__ trace) {
     const uint32_t seq = seq_ptr ? __ldcg(seq_ptr) : seq_arg;
+    const uint32_t p = threadIdx.x >> 5;
+    if (p >= world || p == rank || (threadIdx.x & 31)) return;
+    unsigned long long w0 = 0, w1 = 0;
+    if (trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(w0));
+    const long long t0 = clock64();
+    unsigned ns = 64;
+    while ((int32_t)(fm_ld_acquire_sys(data_flags + p) - seq) < 0) {
+        __nanosleep(ns);
+        if (ns < 512) ns <<= 1;
+        if (clock64() - t0 > 20000000000ll) __trap();
+    }
+    if (trace) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(w1));
+        atomicAdd(trace + 0, w1 - w0);
+        atomicAdd(trace + 3, 1ull);
+    }
+}
+
+// k_xchg_pull: one WARP per (owned row, peer): reads the peer's occupancy word(s) of the row from the local inbox and pulls just
+// the occupied 4096-token slices (512 B each) straight out of the peer's bitmap buffer over NVLink -- every octet of lanes one
+// slice (4 x LDG.128 per lane), two per octet and round, i.e. 8 slices in flight per warp -- and ORs the non-zero words into this
+// rank's own row with L2 atomics (the warps of the other peers work on the same row).  The first CTAs also sum the occurrence
+// counts of all B prefixes.  Runs after k_xchg_wait on the same stream; no acknowledgement: the buffer sets ping-pong
+// (fmidx_shard.cu).
+__global__ void __launch_bounds__(128)
+k_xchg_pull(uint32_t *const *__restrict__ peer_masks, const uint32_t *__restrict__ inbox,
+            uint32_t xwords, uint32_t count_off, uint32_t world, uint32_t rank, uint32_t B, uint32_t vocab,
+            uint64_t *__restrict__ counts_out, unsigned long long *__restrict__ trace) {
     const uint32_t mask_words = (vocab + 31u) >> 5;
     const uint32_t nslices = (vocab + SLICE - 1) / SLICE, ow = (nslices + 31u) >> 5;
     const uint32_t own = B / world, row_lo = rank * own;
-    const int lane = threadIdx.x & 31;
-    // $FMIDX_PULL_TRACE (measurement): warp 0 of every CTA adds its flag-wait time and its total time (ns)
-    unsigned long long tr0 = 0, tr_wait = 0;
-    if (trace && (threadIdx.x >> 5) == 0 && lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr0));
+    const int lane = threadIdx.x & 31, oct = lane >> 3, l8 = lane & 7;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     uint32_t *mine = peer_masks[rank];
     const bool vec_ok = (mask_words & 3u) == 0;  // rows are 16-byte aligned (checked by the launcher for the bases)
-    const int oct = lane >> 3, l8 = lane & 7;
-    constexpr int RB = 8;  // rows per batch: their occupancy words are fetched together, their slices pulled 8 at a time
-    for (uint32_t k = 1; k < world; ++k) {
+    unsigned long long tr0 = 0;
+    if (trace && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr0));
+    const uint32_t npairs = own * (world - 1u);
+    for (uint32_t pr = gw; pr < npairs; pr += nwarps) {
+        const uint32_t r = pr / (world - 1u), k = pr % (world - 1u) + 1u;
         const uint32_t p = rank + k < world ? rank + k : rank + k - world;
-        // ONE thread per CTA polls the peer's flag (system-scope acquire loads are L2 round trips: with every warp of every
-        // waiting pull kernel of every buffer set polling, the polls alone took a measurable share of the L2), backing off
-        // to ~0.5 us between polls; the CTA's other warps sleep at the barrier
-        if (threadIdx.x == 0) {
-            const long long t0 = clock64();
-            unsigned long long w0 = 0, w1 = 0;
-            if (trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(w0));
-            unsigned ns = 64;
-            while ((int32_t)(fm_ld_acquire_sys(data_flags + p) - seq) < 0) {
-                __nanosleep(ns);
-                if (ns < 512) ns <<= 1;
-                if (clock64() - t0 > 20000000000ll) __trap();
-            }
-            if (trace) {
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(w1));
-                tr_wait += w1 - w0;
-            }
-        }
-        __syncthreads();
-        const uint32_t *occ_p = inbox + (size_t)p * xwords;
-        const uint32_t *theirs = peer_masks[p];
-        for (uint32_t r0 = gw; r0 < own; r0 += nwarps * RB) {
-            for (uint32_t ws = 0; ws < ow; ++ws) {
-                // one round trip for the occupancy words of the batch's rows (r0, r0 + nwarps, ...)
-                uint32_t occ[RB], cum[RB + 1];
+        const uint32_t row = row_lo + r;
+        const uint32_t *theirs = peer_masks[p] + (size_t)row * mask_words;
+        uint32_t *dst_row = mine + (size_t)row * mask_words;
+        for (uint32_t ws = 0; ws < ow; ++ws) {
+            const uint32_t occ = __ldcg(inbox + (size_t)p * xwords + (size_t)row * ow + ws);
+            const uint32_t total = (uint32_t)__popc(occ);
+            for (uint32_t t0 = 0; t0 < total; t0 += 8) {
+                uint4 v[2][4];
+                uint32_t wofs[2];
+                bool act[2];
 #pragma unroll
-                for (int j = 0; j < RB; ++j) {
-                    const uint32_t r = r0 + (uint32_t)j * nwarps;
-                    occ[j] = r < own ? __ldcg(occ_p + (size_t)(row_lo + r) * ow + ws) : 0u;
-                }
-                cum[0] = 0;
+                for (int u = 0; u < 2; ++u) {
+                    const uint32_t t = t0 + (uint32_t)u * 4u + (uint32_t)oct;
+                    act[u] = t < total;
+                    const uint32_t sl = act[u] ? ws * 32u + (uint32_t)__fns(occ, 0u, (int)t + 1) : 0u;
+                    wofs[u] = sl * (SLICE / 32) + 4u * (uint32_t)l8;
 #pragma unroll
-                for (int j = 0; j < RB; ++j) cum[j + 1] = cum[j] + (uint32_t)__popc(occ[j]);
-                const uint32_t total = cum[RB];
-                // every octet of lanes pulls one occupied slice (512 B = 4 x 128-B lines) per pair; two pairs per octet and
-                // round = 8 slices (32 x LDG.128 per warp) in flight over NVLink
-                for (uint32_t t0 = 0; t0 < total; t0 += 8) {
-                    uint4 v[2][4];
-                    uint32_t wofs[2];
-                    size_t rofs[2];
-                    bool act[2];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const uint32_t t = t0 + (uint32_t)u * 4u + (uint32_t)oct;
-                        act[u] = t < total;
-                        uint32_t word = 0, base = 0, jj = 0;
-#pragma unroll
-                        for (int j = 0; j < RB; ++j)
-                            if (t >= cum[j] && t < cum[j + 1]) { word = occ[j]; base = cum[j]; jj = (uint32_t)j; }
-                        const uint32_t sl = act[u] ? ws * 32u + (uint32_t)__fns(word, 0u, (int)(t - base) + 1) : 0u;
-                        rofs[u] = (size_t)(row_lo + r0 + jj * nwarps) * mask_words;
-                        wofs[u] = sl * (SLICE / 32) + 4u * (uint32_t)l8;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            v[u][q] = make_uint4(0u, 0u, 0u, 0u);
-                            const uint32_t w = wofs[u] + 32u * (uint32_t)q;
-                            if (act[u]) {
-                                const uint32_t *src = theirs + rofs[u] + w;
-                                if (vec_ok && w + 4u <= mask_words) {
-                                    v[u][q] = __ldcs(reinterpret_cast<const uint4 *>(src));
-                                } else {
-                                    if (w < mask_words) v[u][q].x = __ldcs(src);
-                                    if (w + 1 < mask_words) v[u][q].y = __ldcs(src + 1);
-                                    if (w + 2 < mask_words) v[u][q].z = __ldcs(src + 2);
-                                    if (w + 3 < mask_words) v[u][q].w = __ldcs(src + 3);
-                                }
+                    for (int q = 0; q < 4; ++q) {
+                        v[u][q] = make_uint4(0u, 0u, 0u, 0u);
+                        const uint32_t w = wofs[u] + 32u * (uint32_t)q;
+                        if (act[u]) {
+                            const uint32_t *src = theirs + w;
+                            if (vec_ok && w + 4u <= mask_words) {
+                                v[u][q] = __ldcs(reinterpret_cast<const uint4 *>(src));
+                            } else {
+                                if (w < mask_words) v[u][q].x = __ldcs(src);
+                                if (w + 1 < mask_words) v[u][q].y = __ldcs(src + 1);
+                                if (w + 2 < mask_words) v[u][q].z = __ldcs(src + 2);
+                                if (w + 3 < mask_words) v[u][q].w = __ldcs(src + 3);
                             }
                         }
                     }
-#pragma unroll
-                    for (int u = 0; u < 2; ++u)
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const uint4 x = v[u][q];
-                            if (act[u] && (x.x | x.y | x.z | x.w)) {
-                                const uint32_t w = wofs[u] + 32u * (uint32_t)q;
-                                uint32_t *dst = mine + rofs[u] + w;
-                                if (vec_ok && w + 4u <= mask_words) {
-                                    uint4 o = *reinterpret_cast<uint4 *>(dst);
-                                    o.x |= x.x; o.y |= x.y; o.z |= x.z; o.w |= x.w;
-                                    *reinterpret_cast<uint4 *>(dst) = o;
-                                } else {
-                                    if (w < mask_words) dst[0] |= x.x;
-                                    if (w + 1 < mask_words) dst[1] |= x.y;
-                                    if (w + 2 < mask_words) dst[2] |= x.z;
-                                    if (w + 3 < mask_words) dst[3] |= x.w;
-                                }
-                            }
-                        }
                 }
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint4 x = v[u][q];
+                        if (act[u] && (x.x | x.y | x.z | x.w)) {
+                            uint32_t *dst = dst_row + wofs[u] + 32u * (uint32_t)q;  // words past the row's end were loaded as 0
+                            if (x.x) atomicOr(dst, x.x);
+                            if (x.y) atomicOr(dst + 1, x.y);
+                            if (x.z) atomicOr(dst + 2, x.z);
+                            if (x.w) atomicOr(dst + 3, x.w);
+                        }
+                    }
             }
         }
     }
-    if (trace && (threadIdx.x >> 5) == 0 && lane == 0) {
+    if (trace && threadIdx.x == 0) {
         unsigned long long t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        atomicAdd(trace + 0, tr_wait);
         atomicAdd(trace + 1, t1 - tr0);
         atomicAdd(trace + 2, 1ull);
     }
-    if (counts_out) {  // every peer's side data has arrived by now (each warp waited for all of them)
+    if (counts_out) {  // every peer's side data has arrived (k_xchg_wait)
         for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
             uint64_t acc = 0;
             for (uint32_t p = 0; p < world; ++p)
@@ -2781,19 +2775,18 @@ int fm_launch_or(fmidx *h, const uint32_t *d_pieces, uint32_t n_pieces, size_t n
 int fm_launch_xchg_pull(fmidx *h, uint32_t *const *d_peer_masks, const uint32_t *d_data_flags, const uint32_t *d_inbox, size_t xwords,
                         size_t count_off, uint32_t world, uint32_t rank, size_t B, uint32_t vocab, uint32_t seq, uint64_t *d_counts_out,
                         cudaStream_t s, unsigned long long *d_trace, uint32_t n_sets, const uint32_t *d_seq) {
+    (void)h; (void)n_sets;
     if (B == 0 || world == 0) return FMIDX_OK;
+    if (world > 32) { fm_set_error("the peer-memory exchange supports up to 32 shards"); return FMIDX_EINVAL; }
+    if (world > 1) FM_LAUNCH(k_xchg_wait, 1, 32 * world, 0, s, d_data_flags, world, rank, seq, d_seq, d_trace);
     const size_t own = B / world;
-    const size_t warps = std::max<size_t>(own, (B + 31) / 32);
-    // $FMIDX_PULL_CTAS: CTAs of the pull kernel (default: half the SMs -- its warps spin on the peers' flags first)
+    const size_t warps = std::max<size_t>(own * (world > 1 ? world - 1 : 1), (B + 31) / 32);
+    // $FMIDX_PULL_CTAS caps the grid (measurement); default: one warp per (owned row, peer)
     static const long pull_ctas = [] { const char *e = getenv("FMIDX_PULL_CTAS"); return e && *e ? atol(e) : 0l; }();
-    // the CTAs of a pull kernel spin until the peers have published: the pull kernels of ALL buffer sets together may hold at most
-    // ~40% of the GPU's thread slots, or the kernels that produce what the peers are waiting for starve (with 32 sets x 148 CTAs
-    // the step deadlocked into the kernel's 10-second trap)
-    const size_t fair = std::max<size_t>(8, (size_t)h->sm_count * 6 / std::max<uint32_t>(1u, n_sets));
-    const size_t cap_ctas = pull_ctas > 0 ? (size_t)pull_ctas : std::min<size_t>((size_t)std::max(1, h->sm_count / 2), fair);
-    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((warps + 3) / 4, cap_ctas));
-    FM_LAUNCH(k_xchg_pull, grid, 128, 0, s, d_peer_masks, d_data_flags, d_inbox, (uint32_t)xwords, (uint32_t)count_off, world, rank,
-              (uint32_t)B, vocab, seq, d_counts_out, d_trace, d_seq);
+    size_t ctas = (warps + 3) / 4;
+    if (pull_ctas > 0) ctas = std::min<size_t>(ctas, (size_t)pull_ctas);
+    FM_LAUNCH(k_xchg_pull, (unsigned)std::max<size_t>(1, ctas), 128, 0, s, d_peer_masks, d_inbox, (uint32_t)xwords, (uint32_t)count_off, world,
+              rank, (uint32_t)B, vocab, d_counts_out, d_trace);
     FM_CUDA(cudaGetLastError());
     return FMIDX_OK;
 }

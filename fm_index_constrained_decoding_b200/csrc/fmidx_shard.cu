@@ -62,8 +62,8 @@ int fmidx_shard_create(fmidx_t *h, uint32_t world, uint32_t rank, size_t B, uint
                        fmidx_shard_t **out) {
     if (!h || !out) { fm_set_error("null argument"); return FMIDX_EINVAL; }
     *out = nullptr;
-    if (world == 0 || world > 64 || rank >= world || B == 0 || B % world || vocab == 0 || n_sets == 0 || n_sets > FMIDX_SLOTS) {
-        fm_set_error("shard_create: need 1 <= world <= 64, rank < world, B a positive multiple of world, 1 <= n_sets <= 32");
+    if (world == 0 || world > 32 || rank >= world || B == 0 || B % world || vocab == 0 || n_sets == 0 || n_sets > FMIDX_SLOTS) {
+        fm_set_error("shard_create: need 1 <= world <= 32, rank < world, B a positive multiple of world, 1 <= n_sets <= 32");
         return FMIDX_EINVAL;
     }
     FM_CUDA(cudaSetDevice(h->device));
@@ -293,8 +293,10 @@ void fmidx_shard_destroy(fmidx_shard_t *x) {
     if (x->trace) {
         unsigned long long t[3] = {0, 0, 0};
         cudaMemcpy(t, x->trace, 24, cudaMemcpyDeviceToHost);
-        if (t[2]) fprintf(stderr, "fmidx pull trace (rank %u): %.1f us flag wait, %.1f us total per pull-kernel CTA (warp 0), %llu samples\n",
-                          x->rank, t[0] / 1e3 / t[2], t[1] / 1e3 / t[2], t[2]);
+        unsigned long long t3 = 0;
+        cudaMemcpy(&t3, x->trace + 3, 8, cudaMemcpyDeviceToHost);
+        if (t[2] && t3) fprintf(stderr, "fmidx pull trace (rank %u): %.1f us flag wait per peer (k_xchg_wait), %.1f us per CTA of k_xchg_pull\n",
+                                x->rank, t[0] / 1e3 / t3, t[1] / 1e3 / t[2]);
         cudaFree(x->trace);
     }
     for (void *p : x->opened) cudaIpcCloseMemHandle(p);
