@@ -126,14 +126,15 @@ class FMIndex:
         # 2 * (max_sym + 1) u64 allocation and an fmidx_info call per scalar query
         buf = getattr(self, "_dbuf", None)
         if buf is None:
-            buf = self._dbuf = np.empty(4096, dtype=np.uint64)
+            buf = self._dbuf = (C.c_uint64 * 8192)()  # a ctypes array: no numpy / .ctypes round trip per call
         k = C.c_size_t()
-        rc = fn(self._h, low, high, buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(k))
-        if rc == N.FMIDX_ERANGE and k.value > buf.size:
-            buf = self._dbuf = np.empty(int(k.value) + 1024, dtype=np.uint64)
-            rc = fn(self._h, low, high, buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(k))
-        N.check(rc)
-        return tuple(buf[:k.value].tolist())
+        rc = fn(self._h, low, high, buf, len(buf), C.byref(k))
+        if rc == N.FMIDX_ERANGE and k.value > len(buf):
+            buf = self._dbuf = (C.c_uint64 * (int(k.value) + 1024))()
+            rc = fn(self._h, low, high, buf, len(buf), C.byref(k))
+        if rc != 0:
+            N.check(rc)
+        return tuple(buf[:k.value])
 
     def distinct(self, low, high):
         """fm_index.cpp:99-117."""

@@ -126,7 +126,25 @@ class FMIndex(_FMIndex):
 
     # ---- search (index.py:103-137) -----------------------------------------------------------------------
     def get_range(self, sequence):
-        """One kernel launch for the whole prefix instead of one SWIG call per token."""
+        """One kernel launch for the whole prefix instead of one SWIG call per token.  Prefixes of up to 96 tokens go
+        through preallocated ctypes scratch (the numpy round trip of the general path costs more than the GPU call)."""
+        n = len(sequence)
+        if n <= 96:
+            sc = getattr(self, "_rq", None)
+            if sc is None:
+                sc = self._rq = ((C.c_int32 * 96)(), (C.c_int64 * 2)(), C.c_uint64(), C.c_uint64(), N.lib().fmidx_search_host)
+            toks, offs, sp, ep, fn = sc
+            try:
+                if n and (max(sequence) > 0x7FFFFFFF or min(sequence) < -0x80000000):
+                    raise OverflowError  # ctypes would wrap silently
+                toks[:n] = sequence if isinstance(sequence, list) else list(sequence)
+            except (TypeError, ValueError, OverflowError):
+                n = -1  # not int32 material: the general path raises what it always raised
+            if n >= 0:
+                offs[1] = n
+                if fn(self._h, toks, offs, 1, SHIFT, C.byref(sp), C.byref(ep)) != 0:
+                    N.check(-1)
+                return sp.value, ep.value
         toks, offs = ragged([list(sequence)])
         sp = np.empty(1, dtype=np.uint64)
         ep = np.empty(1, dtype=np.uint64)
