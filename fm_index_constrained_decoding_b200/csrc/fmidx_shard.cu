@@ -5,7 +5,7 @@
 //              raises the data flags)
 //   k_xchg_pull (per peer: wait for its data flag -> pull its occupied 4096-token slices over NVLink -> OR into the rows this
 //              rank owns; total counts)
-// on one stream: five launches, no NCCL, no host synchronisation.  Buffer sets are independent (own buffers, flags, step
+// on one stream: six launches (k_xchg_wait, one small CTA, precedes the pull), no NCCL, no host synchronisation.  Buffer sets are independent (own buffers, flags, step
 // counters, scratch slot), so several steps overlap on several streams.
 // No acknowledgements are needed: every set PING-PONGS between two bitmap buffers and two inboxes (step parity).  When this
 // rank's pull of step s-1 has returned, every peer has published step s-1, hence (stream order on the peer) finished its

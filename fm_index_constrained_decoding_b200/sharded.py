@@ -190,7 +190,7 @@ class ShardStep:
     step(set, toks, offs) enqueues ONE whole step -- search of all B replicated prefixes on this shard, enumeration
     into peer-visible bitmaps (+ slice-occupancy words and occurrence counts), publication into every shard's inbox
     at the tail of the last enumeration kernel, and the fused wait + pull + OR + total-counts + ack kernel -- with one
-    host call and five launches, no NCCL.  Afterwards rank r owns the final bitmaps of prefixes
+    host call and six launches (or ONE graph launch: graph_prepare / graph_launch), no NCCL.  Afterwards rank r owns the final bitmaps of prefixes
     [r*B/world, (r+1)*B/world) and the total occurrence counts of all B prefixes.  `n_sets` independent buffer sets:
     steps on different sets may be in flight on different streams; every rank must issue the same steps on the same
     sets in the same order.  `group`: the process group whose ranks hold the shards (hybrid: one group per replica).

@@ -140,7 +140,7 @@ int fmidx_distinct_mask_batch_occ(fmidx_t *h, const uint64_t *d_sp, const uint64
  * 64-byte handles of its buffers (kind 0 = bitmap buffer buf, 1 = inbox buf, buf = 2 * set + parity; 2 = the flag block),
  * the host language exchanges them (torch.distributed all_gather_object), every rank imports every peer's, then
  * fmidx_shard_ready.
- * fmidx_shard_step enqueues ONE whole step of set `set` on `stream` (NULL: the set's own stream) with five launches and
+ * fmidx_shard_step enqueues ONE whole step of set `set` on `stream` (NULL: the set's own stream) with six launches and
  * no NCCL: search -> enumeration into bitmaps + occupancy + counts (the CTA that finishes last publishes the side data
  * into every shard's inbox and raises the data flags) -> per peer: wait for its data flag, pull its occupied 4096-token
  * slices over NVLink, OR them into the rows this rank owns; total counts.  No acknowledgements: when this rank's pull of
