@@ -1,19 +1,23 @@
-// fmidx_shard.cu -- one document shard's side of a sharded step: ONE host call enqueues
-//   k_search  (ranges of all B replicated prefixes on this shard; also zeroes the bitmap rows this rank owns)
-//   k_mask_top / k_mask_expand / k_mask_bytes  (bitmaps + slice-occupancy words + occurrence counts into peer-visible
-//              buffers; the CTA of k_mask_bytes that finishes last PUBLISHES the side data into every shard's inbox and
-//              raises the data flags)
-//   k_xchg_pull (per peer: wait for its data flag -> pull its occupied 4096-token slices over NVLink -> OR into the rows this
-//              rank owns; total counts)
-// on one stream: six launches (k_xchg_wait, one small CTA, precedes the pull), no NCCL, no host synchronisation.  Buffer sets are independent (own buffers, flags, step
-// counters, scratch slot), so several steps overlap on several streams.
+// fmidx_shard.cu -- one document shard's side of a sharded step: ONE host call (fmidx_shard_step) or ONE
+// CUDA-graph launch (fmidx_shard_graph_launch) enqueues, on the buffer set's stream,
+//   k_search     ranges of all B replicated prefixes on this shard
+//   k_mask_top / k_mask_expand / k_mask_bytes   bitmaps + slice-occupancy words + occurrence counts into peer-visible buffers;
+//                k_mask_top advances the set's step number IN DEVICE MEMORY (no per-step host argument: the step is capturable);
+//                the CTA of k_mask_bytes that finishes last PUBLISHES the side data into every shard's inbox and raises the flags
+//   k_xchg_wait  one small CTA: warp p spins until peer p has published this step
+//   k_xchg_pull  one warp per (owned row, peer): the peer's occupied 4096-token slices over NVLink, ORed into the own row;
+//                total counts
+// -- six kernels, no NCCL, no host synchronisation.  Buffer sets are independent (own buffers, flags, step numbers, scratch slot,
+// stream), so many steps overlap (bench.py keeps 24 in flight: the ranks' pipelines are coupled set by set).
 // No acknowledgements are needed: every set PING-PONGS between two bitmap buffers and two inboxes (step parity).  When this
-// rank's pull of step s-1 has returned, every peer has published step s-1, hence (stream order on the peer) finished its
-// pull of step s-2 -- the last reader of the buffers that step s is about to overwrite.  (Round 1 and the first version of
-// this file waited for ack flags at the head of the 1024-CTA k_mask_top; spinning CTAs then held every thread slot of the GPU
-// whenever a peer was a little late, and the ranks slowed each other down: 59 M q/s on 4 GPUs against 131 M on one.)  The reference has no distributed path
-// (its only parallelism is one std::async per range, fm_index.cpp:146-166); parity for the sharded configuration is
-// "one reference index per shard, results OR/sum-reduced on the host".
+// rank's wait of step s-1 has returned, every peer has published step s-1, hence (stream order on the peer) finished its
+// pull of step s-2 -- the last reader of the buffers that step s is about to overwrite.  History of what did NOT work: ack
+// flags awaited at the head of the 1024-CTA k_mask_top (spinning CTAs held every thread slot whenever a peer was a little
+// late: 59 M q/s on 4 GPUs against 131 M on one); a fused wait+pull kernel (its grid had to stay small because every CTA spun
+// first -- 32 sets x 148 spinning CTAs deadlocked into the trap -- and a small grid has too few loads in flight for NVLink's
+// loaded latency: 220 us of pulling per step on 4 GPUs, 79 M q/s; split: 8-10 us, 150 M q/s).  The reference has no
+// distributed path (its only parallelism is one std::async per range, fm_index.cpp:146-166); parity for the sharded
+// configuration is "one reference index per shard, results OR/sum-reduced on the host".
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
