@@ -674,7 +674,11 @@ __device__ __forceinline__ void fm_eval_byte_node(const FmDev &ix, uint32_t lo, 
 // loads of four consecutive rows per lane, i.e. fully coalesced 512-byte (warp) / 256-byte (half-warp) requests.
 // The array is padded so that the last vector may be read past row n-1.
 constexpr uint32_t NDIST_PENDING = 0xFFFFFFFFu;  // k_mask_top -> k_popcount_pending: this row's count must come from its bitmap
-constexpr uint32_t SCAN_INLINE = 1024;  // ranges up to this many rows are scanned by the warp / CTA that owns the prefix
+constexpr uint32_t SCAN_INLINE = 1024;
+// logits mode: a whole CTA reads a range of up to this many rows (<= 64 KB, coalesced; the beam's other slice-CTAs hit the L2)
+// rather than walking the matrix with ~10 dependent probes, like the bitmap pipeline's scan_max.  (Measured neutral on the
+// 256-beam decode step, profiles/r2_decode_probe.log: that kernel's time is set by the logits stream, not by the few wide beams.)
+constexpr uint32_t SCAN_CTA = 16384;  // ranges up to this many rows are scanned by the warp / CTA that owns the prefix
 template <typename F>
 __device__ __forceinline__ void fm_scan_rows(const uint32_t *__restrict__ bwt, uint32_t lo, uint32_t hi, uint32_t l, uint32_t nl, F &&f) {
 #pragma unroll 2
@@ -1143,7 +1147,7 @@ __device__ __forceinline__ void fm_enum_slice(const FmDev &ix, const uint2 *__re
         // same few hundred bytes, L2 hits after the first) and filtered to the slice -- no table, no dependent probes
         if (e64 > ix.n) e64 = ix.n;
         if (s64 >= e64) return;
-        if (e64 - s64 <= (uint64_t)SCAN_INLINE) {
+        if (e64 - s64 <= (uint64_t)SCAN_CTA) {
             __syncthreads();  // S.bm was zeroed by all threads
             fm_scan_rows(ix.bwt, (uint32_t)s64, (uint32_t)e64, threadIdx.x, blockDim.x, [&](uint32_t c) {
                 if (c >= sa && c < se) {
@@ -1767,7 +1771,7 @@ k_mask_logits_row(FmDev ix, uint32_t LT, int64_t shift, uint32_t vocab, const vo
                 if (tid == 0 && (uint32_t)ovr >= t0 && (uint32_t)ovr < t1) gbm[((uint32_t)ovr - t0) >> 5] = 1u << (((uint32_t)ovr - t0) & 31u);
             } else if (s64 < e64) {
                 bool done = false;
-                if (ix.bwt && e64 - s64 <= (uint64_t)SCAN_INLINE) {
+                if (ix.bwt && e64 - s64 <= (uint64_t)SCAN_CTA) {
                     // narrow range: read the rows' symbols off the resident BWT, keep the group's tokens
                     fm_scan_rows(ix.bwt, (uint32_t)s64, (uint32_t)e64, (uint32_t)tid, (uint32_t)MASK_THREADS, [&](uint32_t c) {
                         if (c >= sa && c < se) {
