@@ -56,6 +56,7 @@ int fm_scratch(fmidx *h, FmBuf &b, size_t bytes, bool pinned_host) {
 }
 
 void fm_release_index(fmidx *h) {
+    h->scalar_spec_seq = 0;  // a speculated enumeration belongs to the index it ran on
     for (void *p : h->owned) cudaFree(p);
     h->owned.clear();
     h->dev_bytes = 0;
@@ -157,6 +158,7 @@ int fmidx_new(int device, fmidx_t **out) {
     h->tune_bytes_occ = (int)env_long("FMIDX_BYTES_OCC", 5);
     h->tune_unigram = env_long("FMIDX_UNIGRAM_TABLE", 1) ? 1 : 0;
     h->tune_scalar_fast = env_long("FMIDX_SCALAR_FAST", 1) ? 1 : 0;
+    h->tune_scalar_speculate = env_long("FMIDX_SCALAR_SPECULATE", 1) ? 1 : 0;
     h->tune_unigram_max = (uint32_t)std::min<long>(std::max<long>(env_long("FMIDX_UNIGRAM_MAX", 1024), 0), 65536);
     *out = h.release();
     return FMIDX_OK;
@@ -168,6 +170,7 @@ void fmidx_free(fmidx_t *h) {
     fm_release_index(h);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->scalar_out) cudaFreeHost(h->scalar_out);
+    if (h->scalar_d_range) cudaFree(h->scalar_d_range);
     for (auto &b : h->d_scratch) if (b.p) cudaFree(b.p);
     for (FmBuf *b : {&h->mask_ws, &h->mask_ws_host}) {
         if (b->last_use) { cudaEventSynchronize(b->last_use); cudaEventDestroy(b->last_use); }
@@ -206,6 +209,7 @@ int fmidx_tune(fmidx_t *h, const char *key, int64_t value) {
     else if (!strcmp(key, "unigram_table")) h->tune_unigram = value ? 1 : 0;
     else if (!strcmp(key, "probe_phase")) h->tune_probe_phase = (int)value;
     else if (!strcmp(key, "scalar_fast")) h->tune_scalar_fast = value ? 1 : 0;
+    else if (!strcmp(key, "scalar_speculate")) { h->tune_scalar_speculate = value ? 1 : 0; h->scalar_spec_seq = 0; }
     else { fm_set_error("fmidx_tune: unknown key '%s'", key); return FMIDX_EINVAL; }
     return FMIDX_OK;
 }

@@ -106,6 +106,13 @@ struct fmidx {
     void *scalar_out = nullptr;
     uint32_t scalar_seq = 0;
     size_t scalar_cap_u64 = 0;
+    // speculative enumeration behind a scalar search (fm_scalar_search): its result block, its sequence number (0: none) and the
+    // range it was launched for
+    void *scalar_spec_out = nullptr;
+    void *scalar_d_range = nullptr;
+    uint32_t scalar_spec_seq = 0;
+    uint64_t scalar_spec_lo = 0, scalar_spec_hi = 0;
+    int tune_scalar_speculate = 1;   // $FMIDX_SCALAR_SPECULATE
     int tune_scalar_fast = 1;        // scalar calls take the zero-copy single-launch kernels ($FMIDX_SCALAR_FAST)
     int tune_probe_phase = 0;        // measurement only: fmidx_query_batch runs one phase alone (1 search, 2 enumeration)
     uint32_t tune_unigram_max = 1024;  // table entries built at most ($FMIDX_UNIGRAM_MAX; 0: none)

@@ -242,14 +242,72 @@ __device__ __forceinline__ void fm_scalar_done(FmScalarOut *out, uint32_t seq) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&out->flag), "r"(seq) : "memory");
 }
 
+__device__ __forceinline__ uint32_t fm_access1(const uint4 *__restrict__ level_cells, uint32_t pos, uint32_t &dig_out);  // below
+
 template <bool RAW>
-__global__ void __launch_bounds__(32) k_search1(FmDev ix, FmToksParam tp, int len, int64_t shift, FmScalarOut *out, uint32_t seq) {
+__global__ void __launch_bounds__(32) k_search1(FmDev ix, FmToksParam tp, int len, int64_t shift, FmScalarOut *out, uint32_t seq,
+                                                uint64_t *d_range, FmScalarOut *spec_out, uint32_t spec_seq) {
     __shared__ int32_t st[FM_SCALAR_MAX_TOKENS];
+    __shared__ uint64_t res[2];
     for (int i = threadIdx.x; i < len; i += 32) st[i] = tp.t[i];
     __syncwarp();
-    fm_search_one<RAW>(ix, FmToksShared{st}, 0, len, threadIdx.x < 16, 0u, shift, &out->v[0], &out->v[1], nullptr, 0u, 0u, 0u);
+    fm_search_one<RAW>(ix, FmToksShared{st}, 0, len, threadIdx.x < 16, 0u, shift, &res[0], &res[1], nullptr, 0u, 0u, 0u);
     __syncwarp();
-    if (threadIdx.x == 0) fm_scalar_done(out, seq);
+    if (threadIdx.x == 0) {
+        out->v[0] = res[0];
+        out->v[1] = res[1];
+        fm_scalar_done(out, seq);
+    }
+    if (!d_range) return;
+    // Speculative enumeration of the range just found (see fm_scalar_search).  Up to 32 rows -- the usual case once a history
+    // has a few tokens -- are finished by this warp right here: one lane per row, the row's symbol, then rank-by-counting over
+    // the warp (distinct symbols ascending, with their multiplicities) straight into the second pinned block.  Wider ranges are
+    // left to the k_distinct1 that follows on the stream (it sees d_range[2] != spec_seq and runs).
+    const uint64_t lo = res[0], hi = res[1];
+    const uint32_t w = hi > lo ? (uint32_t)min(hi - lo, (uint64_t)64) : 0u;
+    if (threadIdx.x == 0) {
+        d_range[0] = lo;
+        d_range[1] = hi;
+    }
+    if (w > 32u) return;
+    const int lane = threadIdx.x;
+    const bool has = (uint32_t)lane < w;
+    uint32_t c = 0xFFFFFFFFu;
+    if (has) {
+        uint32_t pos = (uint32_t)lo + (uint32_t)lane;
+        if (ix.bwt) c = __ldg(ix.bwt + pos);
+        else {
+            c = 0;
+            for (uint32_t l = 0; l < ix.levels; ++l) {
+                uint32_t dig;
+                pos = fm_access1(ix.cells + l * ix.level_stride, pos, dig);
+                c = (c << 4) | dig;
+            }
+            c = (c << 8) | fm_byte_at(ix.bcells, pos);
+        }
+    }
+    const uint32_t same = __match_any_sync(FULL, c);
+    const bool head = has && (uint32_t)(__ffs(same) - 1) == (uint32_t)lane;
+    uint32_t rank = 0;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+        const uint32_t cj = __shfl_sync(FULL, c, j);
+        const bool hj = __shfl_sync(FULL, (int)head, j) != 0;
+        rank += (hj && cj < c) ? 1u : 0u;
+    }
+    const uint32_t nd = (uint32_t)__popc(__ballot_sync(FULL, head));
+    if (head) {
+        spec_out->data[2u * rank] = c;
+        spec_out->data[2u * rank + 1u] = (uint64_t)__popc(same);
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) {
+        spec_out->status = 0u;
+        spec_out->k = 2u * nd;
+        d_range[2] = spec_seq;  // tells the k_distinct1 behind us that its work is done
+        fm_scalar_done(spec_out, spec_seq);
+    }
 }
 
 // B independent FMIndex::backward_search_step calls (inclusive [low,high] in, half-open out).
@@ -2297,7 +2355,12 @@ __global__ void __launch_bounds__(32) k_locate1(FmDev ix, uint64_t row, FmScalar
 // host memory.  Wider ranges report status 1 and the caller takes the bitmap path.
 constexpr int DISTINCT1_MAX = 4096, DISTINCT1_THREADS = 512;
 __global__ void __launch_bounds__(DISTINCT1_THREADS) k_distinct1(FmDev ix, uint64_t low, uint64_t high, int with_counts, uint32_t cap_u64,
-                                                                FmScalarOut *out, uint32_t seq) {
+                                                                FmScalarOut *out, uint32_t seq, const uint64_t *__restrict__ d_range) {
+    if (d_range) {  // speculative form: the range the preceding k_search1 found (narrow ranges: already enumerated there)
+        if ((uint32_t)__ldcg(d_range + 2) == seq) return;
+        low = __ldcg(d_range);
+        high = __ldcg(d_range + 1);
+    }
     __shared__ uint32_t key[DISTINCT1_MAX];
     __shared__ uint32_t head[DISTINCT1_MAX];  // sorted index of the k-th run head
     __shared__ uint32_t wsum[DISTINCT1_THREADS / 32];
@@ -2894,10 +2957,15 @@ int fm_launch_compact(fmidx *h, const uint32_t *d_mask, const uint32_t *d_counts
 static int fm_scalar_prepare(fmidx *h, FmScalarOut **out, uint32_t *seq) {
     FM_TRY(check_ready(h));
     if (!h->scalar_out) {
-        const size_t bytes = sizeof(FmScalarOut) + (size_t)2 * DISTINCT1_MAX * 8;
-        FM_CUDA(cudaHostAlloc(&h->scalar_out, bytes, cudaHostAllocMapped | cudaHostAllocPortable));
-        memset(h->scalar_out, 0, bytes);
+        // two result blocks (the call's own + the speculative enumeration's) in one pinned allocation, and 16 bytes of device memory
+        // through which k_search1 hands its range to the speculative k_distinct1
+        const size_t block = (sizeof(FmScalarOut) + (size_t)2 * DISTINCT1_MAX * 8 + 255) & ~(size_t)255;
+        FM_CUDA(cudaHostAlloc(&h->scalar_out, 2 * block, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(h->scalar_out, 0, 2 * block);
+        h->scalar_spec_out = (char *)h->scalar_out + block;
         h->scalar_cap_u64 = (size_t)2 * DISTINCT1_MAX;
+        FM_CUDA(cudaMalloc(&h->scalar_d_range, 64));
+        FM_CUDA(cudaMemset(h->scalar_d_range, 0, 64));
     }
     *out = (FmScalarOut *)h->scalar_out;
     *seq = ++h->scalar_seq;
@@ -2926,17 +2994,39 @@ static int fm_scalar_wait(fmidx *h, FmScalarOut *out, uint32_t seq) {
 
 int fm_scalar_max_tokens() { return FM_SCALAR_MAX_TOKENS; }
 
+// get_range of ONE prefix.  speculate: the decode loop of the reference asks for the continuations of exactly this range next
+// (get_range, then get_distinct_count on what it returned: document_constrained_generation_vllm.py:91-92), so the enumeration is
+// launched right behind the search on the same stream, reading the range out of device memory; the host returns as soon as the
+// SEARCH has answered, and a following fm_scalar_distinct(low, high, with_counts) with the same range finds its answer already
+// in (or on its way into) the second pinned block -- one launch latency per pair instead of two.
 int fm_scalar_search(fmidx *h, const int64_t *toks, int n, int64_t shift, int raw, uint64_t res[2]) {
     FmScalarOut *out;
     uint32_t seq;
     FM_TRY(fm_scalar_prepare(h, &out, &seq));
     FmToksParam tp;
     for (int i = 0; i < n; ++i) tp.t[i] = (toks[i] < -0x7FFFFFFFll || toks[i] > 0x7FFFFFFFll) ? -0x7FFFFFFF - 1 : (int32_t)toks[i];
-    if (raw) FM_LAUNCH(k_search1<true>, 1, 32, 0, h->stream, h->dev, tp, n, shift, out, seq);
-    else FM_LAUNCH(k_search1<false>, 1, 32, 0, h->stream, h->dev, tp, n, shift, out, seq);
+    const bool speculate = !raw && h->tune_scalar_speculate;
+    uint64_t *d_range = speculate ? (uint64_t *)h->scalar_d_range : nullptr;
+    h->scalar_spec_seq = 0;  // whatever was speculated before is about to be overwritten
+    uint32_t seq2 = 0;
+    if (speculate) {
+        seq2 = ++h->scalar_seq;
+        if (seq2 == 0) seq2 = ++h->scalar_seq;
+    }
+    if (raw) FM_LAUNCH(k_search1<true>, 1, 32, 0, h->stream, h->dev, tp, n, shift, out, seq, d_range, (FmScalarOut *)h->scalar_spec_out, seq2);
+    else FM_LAUNCH(k_search1<false>, 1, 32, 0, h->stream, h->dev, tp, n, shift, out, seq, d_range, (FmScalarOut *)h->scalar_spec_out, seq2);
+    if (speculate) {
+        FM_LAUNCH(k_distinct1, 1, DISTINCT1_THREADS, 0, h->stream, h->dev, 0ull, 0ull, 1, (uint32_t)h->scalar_cap_u64,
+                  (FmScalarOut *)h->scalar_spec_out, seq2, d_range);
+    }
     FM_TRY(fm_scalar_wait(h, out, seq));
     res[0] = out->v[0];
     res[1] = out->v[1];
+    if (speculate) {
+        h->scalar_spec_seq = seq2;
+        h->scalar_spec_lo = res[0];
+        h->scalar_spec_hi = res[1];
+    }
     return FMIDX_OK;
 }
 
@@ -2966,10 +3056,23 @@ int fm_scalar_distinct(fmidx *h, uint64_t low, uint64_t high, int with_counts, u
     FmScalarOut *out;
     uint32_t seq;
     *fallback = false;
+    if (with_counts && h->scalar_spec_seq && h->scalar_out && low == h->scalar_spec_lo && high == h->scalar_spec_hi) {
+        // the enumeration of exactly this range was launched behind the search that returned it
+        FmScalarOut *sp = (FmScalarOut *)h->scalar_spec_out;
+        FM_TRY(fm_scalar_wait(h, sp, h->scalar_spec_seq));
+        if (sp->status == 0) {
+            *k = sp->k;
+            if (sp->k > cap) { fm_set_error("output buffer too small: need %u", sp->k); return FMIDX_ERANGE; }
+            if (sp->k) memcpy(dst, (const void *)sp->data, (size_t)sp->k * 8);
+            return FMIDX_OK;
+        }
+        // too wide for the scalar kernel: the bitmap path below
+    }
     FM_TRY(fm_scalar_prepare(h, &out, &seq));
     const uint64_t e = high > h->dev.n ? h->dev.n : high;
     if (e > low && e - low > (uint64_t)DISTINCT1_MAX) { *fallback = true; return FMIDX_OK; }
-    FM_LAUNCH(k_distinct1, 1, DISTINCT1_THREADS, 0, h->stream, h->dev, low, high, with_counts, (uint32_t)h->scalar_cap_u64, out, seq);
+    FM_LAUNCH(k_distinct1, 1, DISTINCT1_THREADS, 0, h->stream, h->dev, low, high, with_counts, (uint32_t)h->scalar_cap_u64, out, seq,
+              (const uint64_t *)nullptr);
     FM_TRY(fm_scalar_wait(h, out, seq));
     if (out->status != 0) { *fallback = true; return FMIDX_OK; }
     *k = out->k;

@@ -311,6 +311,20 @@ def test_scalar_fast_paths_match_batched_paths_and_oracle(cuda, layout):
         i = rng.randrange(len(d) - 1)
         cases.append(d[i:i + rng.randint(1, 12)])
     cases += [[0], [vocab + 5], [], docs[3][:95], docs[3][:96], docs[3][:97], docs[3][:140], [docs[0][0], 2 ** 31 - 1]]
+    # get_range followed by get_distinct_count of the returned range (the decode loop's pair): the enumeration is launched
+    # speculatively behind the search; other ranges in between, repeated requests and a rebuilt index must not see stale answers
+    for spec in (1, 0):
+        ix.tune(scalar_speculate=spec)
+        prev = None
+        for q in cases:
+            lo, hi = ix.get_range(q)
+            if prev is not None and rng.random() < 0.3:
+                assert ix.get_distinct_count(*prev) == o.get_distinct_count(*prev)   # not the speculated range
+            assert ix.get_distinct_count(lo, hi) == o.get_distinct_count(lo, hi), (spec, q[:5])
+            assert ix.get_distinct_count(lo, hi) == o.get_distinct_count(lo, hi)     # asked twice
+            assert ix.distinct(lo, hi) == o.distinct(lo, hi)
+            prev = (lo, hi)
+    ix.tune(scalar_speculate=1)
     for fast in (1, 0):
         ix.tune(scalar_fast=fast)
         for q in cases:
