@@ -138,6 +138,10 @@ def workload_config(tokens, batch, mode="single"):
                         "backward search + distinct next-token mask" % (tokens // 1_000_000, batch),
             "tokens_per_gpu": tokens, "batch": batch, "prefix_len": "U{1..32} clipped at document end",
             "corpus": "Zipf(1.1) token ids, docs U[64,1024] ending in EOS 128009, 1% planted repeats",
+            "mask_rows": ("lazy clearing: the step's mask buffers belong to the bench and nothing else writes them, so only the 4096-token "
+                          "slices a buffer's previous batch dirtied are zeroed (fmidx_tune lazy_clear=2); every buffer sees all 8 prefix "
+                          "batches in turn; BENCH_LAZY=0 / ablation.full_row_zeroing: every 16-KB row zeroed in full each step"
+                          if os.environ.get("BENCH_LAZY", "1") == "1" else "every 16-KB row zeroed in full each step"),
             "l2": "index (>= 14x L2) larger than L2; %d distinct prefix batches rotated" % N_QUERY_SETS,
             "mode": mode}
 
@@ -338,6 +342,9 @@ class LocalEngine:
         from fm_index_constrained_decoding_b200 import _native
         self.N, self.L = _native, _native.lib()
         self.ix, self.qsets, self.device, self.B = ix, qsets, device, B
+        # the engine's mask buffers are its own and nothing else writes them: lazy clearing (see run_single)
+        self.lazy = os.environ.get("BENCH_LAZY", "1") == "1"
+        ix.tune(lazy_clear=2 if self.lazy else 1)
         self.NPIPE = int(os.environ.get("BENCH_NPIPE", "8"))
         self.pstreams = [torch.cuda.Stream(device=device) for _ in range(self.NPIPE)]
         self.pbufs = [(torch.empty(B, dtype=torch.int64, device=device), torch.empty(B, dtype=torch.int64, device=device),
@@ -359,7 +366,9 @@ class LocalEngine:
             ps.wait_event(e)
         nq, npipe, qb, args = len(self.qsets), self.NPIPE, self._qb, self.pipe_args
         for k in range(k0, k0 + n):
-            if qb(*args[(k % nq, k % npipe)]) != 0:
+            # the pairing (prefix batch, buffer) rotates: every mask buffer sees all 8 batches in turn (with lazy clearing a
+            # buffer that always received the same batch would be cleared of exactly what is written back)
+            if qb(*args[((k + k // npipe) % nq, k % npipe)]) != 0:
                 self.N.check(-1)
         for ps in self.pstreams:
             e = torch.cuda.Event()
@@ -444,7 +453,7 @@ BYTE_PROBE_B = 32 + 32 * 8.5     # header-word sector + E[payload sectors below 
 STEP_B = 2 * (3 * NIB_PROBE_B + BYTE_PROBE_B)  # two boundaries; = 1,086 B (SURVEY 8(d) quotes 1,088 B for the reference layout)
 
 
-def algorithmic_bytes(ix, qsets, device, B, info, table=True):
+def algorithmic_bytes(ix, qsets, device, B, info, table=True, lazy=False):
     """Per step, from the actual results: what K1 and K2 must read and write at the granularity of DRAM sectors.
     K1  probe steps (range still > 16 rows; resident layout) x STEP_B; the first token costs two C[] sectors; the tail
         of a prefix costs ceil(4w/32) SA sectors, w x ceil(4 rem/32) text sectors and one ISA sector per survivor; plus
@@ -495,7 +504,21 @@ def algorithmic_bytes(ix, qsets, device, B, info, table=True):
                              C.c_void_p(sp.data_ptr()), C.c_void_p(ep.data_ptr()), sptr)
         w = ep - sp
         scan = (w <= SCAN_MAX) if resident else torch.zeros_like(w, dtype=torch.bool)
-        k2 = B * MASK_BYTES + float((torch.ceil(w[scan] * 4 / 32) * 32).sum())
+        if lazy:
+            # lazy clearing: a row costs the slices its PREVIOUS content dirtied (512 B each; a row whose range was wider than
+            # 1,024 rows counts as all 32, like the kernel book-keeps it) + the 32-B sectors that receive bits + 8 B of state
+            _, _, m = ix.query_batch(q, offs, VOCAB)
+            mw = torch.zeros((B, 32 * 128), dtype=torch.int32, device=device)
+            mw[:, :m.shape[1]] = m
+            slices = (mw.view(B, 32, 128) != 0).any(-1).sum(-1)
+            slices = torch.where((w > 1024), torch.full_like(slices, 32), slices)
+            sectors = (mw.view(B, -1, 8) != 0).any(-1).sum(-1)
+            row_bytes = float((slices * 512 + sectors * 32 + 8).sum())
+            tot["row_slices"] = tot.get("row_slices", 0.0) + float(slices.sum())
+            del mw, m
+        else:
+            row_bytes = B * MASK_BYTES
+        k2 = row_bytes + float((torch.ceil(w[scan] * 4 / 32) * 32).sum())
         tot["scan_rows"] += float(w[scan].sum())
         heavy_m = ~scan & (w > 0)
         if resident and table:
@@ -525,14 +548,16 @@ def algorithmic_bytes(ix, qsets, device, B, info, table=True):
     return {k: v / len(qsets) for k, v in tot.items()}
 
 
-def ncu_traffic():
+def ncu_traffic(lazy=False):
     """DRAM traffic of one step from the committed ncu captures of THIS workload (100M tokens, batch 4,096, 8 steps in flight).
     Preferred: profiles/r2_range_replay_phase0.csv -- `ncu --replay-mode range` over 64 overlapped steps (benchmarks/
     range_probe.py), i.e. dram__bytes_read.sum + dram__bytes_write.sum of the multi-stream region as it is timed here, / 64.
     Else the per-kernel `ncu --set full` summary (profiles/r2_ncu_full_summary.csv; serial, cold caches: dirty mask rows still
     in L2 when a kernel ends are not counted).  (total, per-part) or (None, None)."""
     import csv
-    p = os.path.join(ROOT, "profiles", "r2_range_replay_phase0.csv")
+    p = os.path.join(ROOT, "profiles", "r2_range_replay_lazy.csv" if lazy else "r2_range_replay_phase0.csv")
+    if lazy and not os.path.exists(p):
+        return None, None
     if os.path.exists(p):
         try:
             vals = {}
@@ -606,6 +631,13 @@ def run_single(args, device, local):
     log("corpus %.1fs, index build %.1fs, %d levels, %.0f MB on device" % (t_gen, t_build, info["levels"], info["device_bytes"] / 1e6))
     eng = LocalEngine(ix, qsets, device, B)
     timer = BlockTimer(device)
+    # The mask buffers of the timed loop belong to this program and nothing else writes them: lazy clearing (fmidx_tune
+    # "lazy_clear" 2 -- only the 4096-token slices a buffer's previous batch dirtied are zeroed, not whole 16-KB rows).
+    # `ablation.full_row_zeroing` is the same loop with every row zeroed in full.
+    lazy = os.environ.get("BENCH_LAZY", "1") == "1"
+    ix.tune(lazy_clear=1)
+    full_ms, _, _ = timer.run(eng.block, args.steps, args.warmup)
+    ix.tune(lazy_clear=2 if lazy else 1)
     sampler = ClockSampler(local)
     launches0 = L.fmidx_launch_count()
     sampler.start()
@@ -621,31 +653,49 @@ def run_single(args, device, local):
     abl_ms, _, _ = timer.run(eng.block, args.steps, args.warmup)
     t_search_off, t_mask_off = eng.serial_kernel_times(200)
     ix.tune(unigram_table=1)
-    ablation = {"unigram_table_off": {"value": B * args.steps / (abl_ms * 1e-3), "ms_per_step": abl_ms / args.steps,
+    ablation = {"full_row_zeroing": {"value": B * args.steps / (full_ms * 1e-3), "ms_per_step": full_ms / args.steps,
+                                     "what": "fmidx_tune lazy_clear = 1: every 16-KB mask row of the caller's buffers is zeroed in full each step "
+                                             "(65.7 MB of stores per step)"},
+                "unigram_table_off": {"value": B * args.steps / (abl_ms * 1e-3), "ms_per_step": abl_ms / args.steps,
                                       "serial_kernel_ms": {"k_search": t_search_off, "k_mask": t_mask_off}},
                 "note": "the table holds, for the <= 1024 most frequent symbols, the distinct symbols of the symbol's BWT block (built by the "
                         "library's own enumeration at index build; the reference precomputes the same for the empty prefix, index.py:206)"}
 
     # ---- roofline of the step, live ------------------------------------------------------------------------------------
     peak, peak_src = measured_peaks()
-    ab = algorithmic_bytes(ix, qsets, device, B, info)
+    ab = algorithmic_bytes(ix, qsets, device, B, info, lazy=lazy)
     step_bytes = ab["k1"] + ab["k2"]
-    traffic, traffic_per = ncu_traffic()
+    traffic, traffic_per = ncu_traffic(lazy)
+    if lazy:  # the same accounting for the full-row ablation
+        ab_full = algorithmic_bytes(ix, qsets, device, B, info, lazy=False)
+        tr_full, _ = ncu_traffic(False)
+        fb = ab_full["k1"] + ab_full["k2"]
+        ablation["full_row_zeroing"]["roofline"] = {
+            "algorithmic_bytes_per_launch": fb, "achieved": fb / (full_ms / args.steps * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": fb / (full_ms / args.steps * 1e-3) / 1e9 / peak, "traffic": tr_full,
+            "frac_of_traffic": (tr_full / (full_ms / args.steps * 1e-3) / 1e9 / peak) if tr_full else None}
     roof = {"kernel": "one step = k_search + k_mask_top + k_mask_expand + k_mask_bytes (%d independent batches in flight on as many streams)" % eng.NPIPE + "",
             "bound": "hbm", "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "peak_source": peak_src,
             "traffic": traffic, "algorithmic_bytes_per_launch": step_bytes, "avg_launch_ms": ms_per_step,
             "time_source": "the timed (overlapped) region: median K-step block / K",
             "per_unit": "K1: %.0f B per probe step (2 boundaries x (3 nibble probes of 32-B header sector + 1.49 plane sectors, 1 byte-level "
-                        "probe of 32-B header sector + 8.5 payload sectors)); tail of a prefix: SA/text/ISA sectors; K2: 16,032 B mask row + "
+                        "probe of 32-B header sector + 8.5 payload sectors)); tail of a prefix: SA/text/ISA sectors; K2: %s + "
                         "4 B per row of ranges <= %d rows (resident BWT) + 16,032 B table row per frequent one-token prefix + tree walk of the other "
-                        "wide ranges (2 x 128 B per nibble node, payload bytes or 2,560 B per byte-level node)" % (STEP_B, SCAN_MAX),
+                        "wide ranges (2 x 128 B per nibble node, payload bytes or 2,560 B per byte-level node)"
+                        % (STEP_B, "per mask row the 512-B slices its previous content dirtied (lazy clearing; 16,032 B for a row whose range "
+                                   "was wider than 1,024 rows) + the 32-B sectors that receive bits + 8 B of occupancy state" if lazy
+                           else "16,032 B mask row", SCAN_MAX),
             "traffic_detail": traffic_per,
             "per_kernel": {"k_search": {"algorithmic_bytes": ab["k1"], "serial_ms": t_search, "GBps_serial": ab["k1"] / (t_search * 1e-3) / 1e9},
                            "k_mask": {"algorithmic_bytes": ab["k2"], "serial_ms": t_mask, "GBps_serial": ab["k2"] / (t_mask * 1e-3) / 1e9}},
             "other_kernel_ms": {"k_search": t_search, "k_mask": t_mask},
             "counts_per_step": {k: ab[k] for k in ("search_steps", "probe_steps", "scan_rows", "table_rows", "tree_prefixes", "byte_nodes")},
             "reference_layout_bytes_per_step": 1088 * ab["search_steps"] + B * MASK_BYTES,
-            "note": "the mask rows (65.7 MB per step, written once: ncu's range replay of the overlapped step sees 66.2 MB written and "
+            "note": ("LAZY CLEARING (headline): only the slices a buffer's previous batch dirtied are zeroed, so the 65.7 MB of row stores "
+                     "per step shrink to a few MB and what is left is random access -- the step then runs at the DRAM's random-sector rate "
+                     "(see sector_rate), far below the streaming roofline by construction.  With full-row zeroing (ablation.full_row_zeroing, "
+                     "the form whose traffic is 3/4 streaming writes): " if lazy else "") +
+                    "the mask rows (65.7 MB per step, written once: ncu's range replay of the overlapped step sees 66.2 MB written and "
                     "18.2 MB read per step, i.e. the traffic IS the algorithmic minimum) dominate the bytes.  Phase-isolated graph replays "
                     "(profiles/r2_phase_probe.log): the row zeroing alone runs at 9.8 us per step (7.3 TB/s of pure writes), the search "
                     "alone at 5.2 us, the enumeration without zeroing at 7.6 us, and the three ADD (24 us): the random 32-B-sector reads of "
@@ -654,6 +704,7 @@ def run_single(args, device, local):
                     "65,536, profiles/r2_batch_sweep.log)"}
     roof["frac"] = roof["achieved"] / peak
     roof["frac_of_traffic"] = (traffic / (ms_per_step * 1e-3) / 1e9 / peak) if traffic else None
+    roof["mask_rows"] = "lazy clearing (fmidx_tune lazy_clear=2)" if lazy else "zeroed in full every step"
     try:
         gp = {}
         for unit in (32, 128):
@@ -661,6 +712,12 @@ def run_single(args, device, local):
             _native.check(L.fmidx_gather_peak(ix._h, unit, 1 << 25, C.byref(v)))
             gp["%dB_GBps" % unit] = v.value
         roof["random_gather_peak"] = gp
+        sect = (traffic if traffic else step_bytes) / 32.0 / (ms_per_step * 1e-3)
+        roof["sector_rate"] = {"G_sectors_per_s": sect / 1e9, "random_gather_32B_G_sectors_per_s": gp["32B_GBps"] / 32.0,
+                               "frac_of_random_gather": sect / 1e9 / (gp["32B_GBps"] / 32.0),
+                               "basis": "ncu traffic" if traffic else "algorithmic bytes",
+                               "what": "32-byte DRAM sectors moved per second by the step against the rate at which this GPU serves isolated random "
+                                       "32-byte sectors (fmidx_gather_peak): the roofline a random-access integer path lives under"}
     except Exception as e:  # noqa: BLE001
         roof["random_gather_peak"] = {"error": repr(e)}
 

@@ -16,6 +16,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--phase", type=int, default=0)
 ap.add_argument("--steps", type=int, default=64)
 ap.add_argument("--pipes", type=int, default=8)
+ap.add_argument("--lazy", type=int, default=0, help="fmidx_tune lazy_clear level for the profiled steps")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 V, SHIFT, B, NP = 128256, 10, 4096, args.pipes
@@ -34,14 +35,15 @@ for qi, (q, offs) in enumerate(qsets):
         sp, ep, m = bufs[pi]
         cargs[(qi, pi)] = (ix._h, pi, C.c_void_p(q.data_ptr()), C.c_void_p(offs.data_ptr()), B, SHIFT, V, C.c_void_p(sp.data_ptr()),
                            C.c_void_p(ep.data_ptr()), C.c_void_p(m.data_ptr()), C.c_void_p(streams[pi].cuda_stream))
+ix.tune(lazy_clear=args.lazy)
 for k in range(4 * NP):
-    L.fmidx_query_batch(*cargs[(k % 8, k % NP)])
+    L.fmidx_query_batch(*cargs[((k + k // NP) % 8, k % NP)])
 torch.cuda.synchronize()
 ix.tune(probe_phase=args.phase)
 rt = torch.cuda.cudart()
 rt.cudaProfilerStart()
-for k in range(args.steps):
-    L.fmidx_query_batch(*cargs[(k % 8, k % NP)])
+for k in range(4 * NP, 4 * NP + args.steps):
+    L.fmidx_query_batch(*cargs[((k + k // NP) % 8, k % NP)])
 torch.cuda.synchronize()
 rt.cudaProfilerStop()
 print("range done: %d steps, %d in flight, phase %d" % (args.steps, NP, args.phase))

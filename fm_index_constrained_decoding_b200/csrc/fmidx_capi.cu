@@ -77,6 +77,28 @@ static int enter(fmidx *h, bool need_ready) {
     return FMIDX_OK;
 }
 
+// Lazy clearing (k_mask_top): the per-row slice occupancy of what slot `sl` last left in `d_mask`, or nullptr when this call must
+// zero whole rows (feature off for this kind of buffer, or more than 32 slices per row).  A new (buffer, shape) association
+// starts from "everything may be dirty".  `owned`: the buffer belongs to the library (level 1) or to the caller (level 2).
+static int lazy_state(fmidx *h, fmidx::Slot &sl, const uint32_t *d_mask, size_t B, uint32_t vocab, bool owned, cudaStream_t s,
+                      uint32_t **out) {
+    *out = nullptr;
+    if (h->tune_lazy_clear < (owned ? 1 : 2) || !d_mask || B == 0 || (vocab + 4095u) / 4096u > 32u) {
+        sl.lazy_ptr = nullptr;  // the rows are about to be rewritten without book-keeping
+        return FMIDX_OK;
+    }
+    if (sl.lazy_ptr != d_mask || sl.lazy_B != B || sl.lazy_vocab != vocab || !sl.occ.p) {
+        if (sl.occ.p && B * 4 > sl.occ.cap) FM_CUDA(cudaStreamSynchronize(s));  // growing frees the old array
+        FM_TRY(fm_scratch(h, sl.occ, B * 4, false));
+        FM_CUDA(cudaMemsetAsync(sl.occ.p, 0xFF, B * 4, s));
+        sl.lazy_ptr = d_mask;
+        sl.lazy_B = B;
+        sl.lazy_vocab = vocab;
+    }
+    *out = (uint32_t *)sl.occ.p;
+    return FMIDX_OK;
+}
+
 // Unigram continuation table (fmidx_layout.cuh): built with the library's own enumeration kernels, once per index.
 int fm_build_unigram_table(fmidx *h, cudaStream_t s) {
     FmDev &d = h->dev;
@@ -158,6 +180,7 @@ int fmidx_new(int device, fmidx_t **out) {
     h->tune_bytes_occ = (int)env_long("FMIDX_BYTES_OCC", 5);
     h->tune_unigram = env_long("FMIDX_UNIGRAM_TABLE", 1) ? 1 : 0;
     h->tune_scalar_fast = env_long("FMIDX_SCALAR_FAST", 1) ? 1 : 0;
+    h->tune_lazy_clear = (int)std::min<long>(2, std::max<long>(0, env_long("FMIDX_LAZY_CLEAR", 1)));
     h->tune_scalar_speculate = env_long("FMIDX_SCALAR_SPECULATE", 1) ? 1 : 0;
     h->tune_unigram_max = (uint32_t)std::min<long>(std::max<long>(env_long("FMIDX_UNIGRAM_MAX", 1024), 0), 65536);
     *out = h.release();
@@ -184,6 +207,7 @@ void fmidx_free(fmidx_t *h) {
         if (sl.g_din) cudaFree(sl.g_din);
         if (sl.g_dout) cudaFree(sl.g_dout);
         if (sl.in.p) cudaFree(sl.in.p);
+        if (sl.occ.p) cudaFree(sl.occ.p);
         if (sl.mask.p) cudaFree(sl.mask.p);
         if (sl.ws.p) cudaFree(sl.ws.p);
     }
@@ -209,6 +233,7 @@ int fmidx_tune(fmidx_t *h, const char *key, int64_t value) {
     else if (!strcmp(key, "unigram_table")) h->tune_unigram = value ? 1 : 0;
     else if (!strcmp(key, "probe_phase")) h->tune_probe_phase = (int)value;
     else if (!strcmp(key, "scalar_fast")) h->tune_scalar_fast = value ? 1 : 0;
+    else if (!strcmp(key, "lazy_clear")) h->tune_lazy_clear = value < 0 ? 0 : (value > 2 ? 2 : (int)value);
     else if (!strcmp(key, "scalar_speculate")) { h->tune_scalar_speculate = value ? 1 : 0; h->scalar_spec_seq = 0; }
     else { fm_set_error("fmidx_tune: unknown key '%s'", key); return FMIDX_EINVAL; }
     return FMIDX_OK;
@@ -629,8 +654,12 @@ int fmidx_query_batch(fmidx_t *h, int ws_slot, const int32_t *d_toks, const int6
     if (!d_mask || vocab == 0 || h->tune_probe_phase == 1) return FMIDX_OK;
     h->mask_ws_override = &h->slots[ws_slot].ws;  // calls on different streams must not share the node lists
     struct Reset { fmidx_t *h; ~Reset() { h->mask_ws_override = nullptr; } } reset{h};
+    // fmidx_tune("lazy_clear", 2): the caller promises that nobody else writes d_mask between this slot's calls -- then only the
+    // slices the previous call dirtied are zeroed
+    uint32_t *occ_state = nullptr;
+    FM_TRY(lazy_state(h, h->slots[ws_slot], d_mask, B, vocab, false, (cudaStream_t)stream, &occ_state));
     return fm_launch_mask(h, d_sp, d_ep, B, shift, vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, d_mask, nullptr,
-                          (cudaStream_t)stream, nullptr, 0, ~(size_t)0, kz);
+                          (cudaStream_t)stream, nullptr, 0, ~(size_t)0, kz, nullptr, nullptr, kz ? nullptr : occ_state);
 }
 
 int fmidx_distinct_mask_batch_occ(fmidx_t *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t B, int64_t shift,
@@ -774,8 +803,10 @@ static int query_host_impl(fmidx_t *h, const int32_t *toks, const int64_t *offs,
     if (want_mask) {
         // the distinct-token counts come out of the enumeration itself (rows it finishes by scanning count their newly set bits;
         // only the few wide rows are re-read by k_popcount_pending) instead of a popcount pass over all B x 16 KB
+        uint32_t *occ_state = nullptr;  // pipelined slots own their mask buffer: lazy clearing
+        if (slot >= 0 && !kz) FM_TRY(lazy_state(h, h->slots[slot], d_mask, B, vocab, true, s, &occ_state));
         FM_TRY(fm_launch_mask(h, d_sp, d_ep, B, shift, vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, d_mask, nullptr, s,
-                              nullptr, 0, ~(size_t)0, kz, nullptr, n_distinct ? d_n : nullptr));
+                              nullptr, 0, ~(size_t)0, kz, nullptr, n_distinct ? d_n : nullptr, occ_state));
     }
     FM_CUDA(cudaMemcpyAsync(sp, d_sp, B * 8, cudaMemcpyDeviceToHost, s));
     FM_CUDA(cudaMemcpyAsync(ep, d_ep, B * 8, cudaMemcpyDeviceToHost, s));
@@ -798,7 +829,8 @@ static int graph_sequence(fmidx_t *h, fmidx::Slot &sl, int64_t shift, uint32_t v
         FM_TRY(fm_launch_search(h, sl.g_dev_toks, sl.g_dev_offs, B, shift, sl.g_dev_sp, sl.g_dev_ep, 0, s, kz ? sl.g_dev_mask : nullptr, words));
         if (h->tune_probe_phase == 1) return FMIDX_OK;
         return fm_launch_mask(h, sl.g_dev_sp, sl.g_dev_ep, B, shift, vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, sl.g_dev_mask,
-                              nullptr, s, nullptr, 0, ~(size_t)0, kz);
+                              nullptr, s, nullptr, 0, ~(size_t)0, kz, nullptr, nullptr,
+                              (!kz && sl.lazy_ptr == sl.g_dev_mask) ? (uint32_t *)sl.occ.p : nullptr);
     }
     int64_t *d_offs = (int64_t *)sl.g_din;
     int32_t *d_toks = (int32_t *)((char *)sl.g_din + (B + 1) * 8);
@@ -810,7 +842,7 @@ static int graph_sequence(fmidx_t *h, fmidx::Slot &sl, int64_t shift, uint32_t v
     const bool kz = fm_search_can_zero(d_mask, vocab);
     FM_TRY(fm_launch_search(h, d_toks, d_offs, B, shift, d_sp, d_ep, 0, s, kz ? d_mask : nullptr, words));
     FM_TRY(fm_launch_mask(h, d_sp, d_ep, B, shift, vocab, nullptr, nullptr, 3, 0, nullptr, -1, nullptr, 0, d_mask, nullptr, s, nullptr, 0,
-                          ~(size_t)0, kz, nullptr, d_n));
+                          ~(size_t)0, kz, nullptr, d_n, (!kz && sl.lazy_ptr == d_mask) ? (uint32_t *)sl.occ.p : nullptr));
     FM_CUDA(cudaMemcpyAsync(sl.g_hout, sl.g_dout, B * 20, cudaMemcpyDeviceToHost, s));
     return FMIDX_OK;
 }
@@ -856,6 +888,8 @@ int fmidx_query_graph_prepare(fmidx_t *h, int slot, size_t B, size_t max_tokens,
     FM_CUDA(cudaMalloc(&sl.g_dout, B * 20 + 16));
     memset(sl.g_hin, 0, in_bytes);  // B empty prefixes: a valid input
     FM_TRY(fm_scratch(h, sl.mask, B * (size_t)((vocab + 31) / 32) * 4, false));
+    uint32_t *occ_state = nullptr;  // the slot owns its mask buffer: lazy clearing, decided here and baked into the captures
+    FM_TRY(lazy_state(h, sl, (const uint32_t *)sl.mask.p, B, vocab, true, sl.stream, &occ_state));
     FM_TRY(graph_capture(h, sl, shift, vocab));
     *h_in = sl.g_hin;
     *h_out = sl.g_hout;
@@ -873,6 +907,8 @@ int fmidx_query_graph_prepare_device(fmidx_t *h, int slot, const int32_t *d_toks
     FM_CUDA(cudaStreamSynchronize(sl.stream));
     sl.g_B = B;
     sl.g_dev_toks = d_toks; sl.g_dev_offs = d_offs; sl.g_dev_sp = d_sp; sl.g_dev_ep = d_ep; sl.g_dev_mask = d_mask;
+    uint32_t *occ_state = nullptr;  // the caller's buffer: lazy clearing only on request (fmidx_tune "lazy_clear" 2)
+    FM_TRY(lazy_state(h, sl, d_mask, B, vocab, false, sl.stream, &occ_state));
     int rc = graph_capture(h, sl, shift, vocab);
     if (rc != FMIDX_OK) sl.g_dev_mask = nullptr;
     return rc;

@@ -84,6 +84,12 @@ struct fmidx {
     struct Slot {                // fmidx_query_submit / fmidx_query_wait: independent in-flight host batches
         cudaStream_t stream = nullptr;
         FmBuf in, mask, ws;
+        // lazy clearing of the slot's mask rows (k_mask_top): per-row slice occupancy of what the slot's last call left in the
+        // buffer `lazy_ptr` ([lazy_B] rows of a lazy_vocab-bit mask); the association is dropped whenever a call cannot use it
+        FmBuf occ;
+        const uint32_t *lazy_ptr = nullptr;
+        size_t lazy_B = 0;
+        uint32_t lazy_vocab = 0;
         // graph-captured form (fmidx_query_graph_*): the whole step of the slot as two executable graphs (the mask kernels
         // alternate between two work-list counter pairs, so consecutive steps alternate between the two captures)
         cudaGraphExec_t gexec[2] = {nullptr, nullptr};
@@ -114,6 +120,8 @@ struct fmidx {
     uint64_t scalar_spec_lo = 0, scalar_spec_hi = 0;
     int tune_scalar_speculate = 1;   // $FMIDX_SCALAR_SPECULATE
     int tune_scalar_fast = 1;        // scalar calls take the zero-copy single-launch kernels ($FMIDX_SCALAR_FAST)
+    int tune_lazy_clear = 1;         // 0 never; 1 mask buffers the library owns (pipelined / captured host forms); 2 also the caller's
+                                     // buffers of fmidx_query_batch / fmidx_query_graph_prepare_device ($FMIDX_LAZY_CLEAR)
     int tune_probe_phase = 0;        // measurement only: fmidx_query_batch runs one phase alone (1 search, 2 enumeration)
     uint32_t tune_unigram_max = 1024;  // table entries built at most ($FMIDX_UNIGRAM_MAX; 0: none)
 };
@@ -141,7 +149,7 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
                    const void *d_logits, void *d_out, int dtype, int64_t row_stride, const int32_t *d_override,
                    int32_t always_allow, const uint32_t *d_extra, uint32_t n_extra, uint32_t *d_mask,
                    uint32_t *d_counts, cudaStream_t s, uint32_t *d_occ = nullptr, size_t dense_lo = 0, size_t dense_n = ~(size_t)0,
-                   bool prezeroed = false, const FmXchgArgs *xa = nullptr, uint32_t *d_ndist = nullptr);
+                   bool prezeroed = false, const FmXchgArgs *xa = nullptr, uint32_t *d_ndist = nullptr, uint32_t *d_occ_state = nullptr);
 int fm_launch_xchg_pull(fmidx *h, uint32_t *const *d_peer_masks, const uint32_t *d_data_flags, const uint32_t *d_inbox, size_t xwords,
                         size_t count_off, uint32_t world, uint32_t rank, size_t B, uint32_t vocab, uint32_t seq, uint64_t *d_counts_out,
                         cudaStream_t s, unsigned long long *d_trace = nullptr, uint32_t n_sets = 1, const uint32_t *d_seq = nullptr);

@@ -800,7 +800,11 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
            uint4 *__restrict__ work_items, uint32_t *__restrict__ work_count, uint32_t *__restrict__ mask_out,
            uint32_t *__restrict__ counts_out, uint32_t *__restrict__ occ_out, uint32_t dense_lo, uint32_t dense_n,
            uint32_t zflags, uint64_t *__restrict__ xcounts, uint32_t scan_max, uint32_t *__restrict__ ndist_out,
-           uint32_t *__restrict__ seq_inc) {
+           uint32_t *__restrict__ seq_inc, uint32_t *__restrict__ occ_state) {
+    // occ_state (nullable; bitmap mode, every row dense, <= 32 slices): LAZY CLEARING.  occ_state[b] says which 4096-token slices
+    // of row b may hold bits from the buffer's previous use; only those are zeroed here (a narrow prefix dirties 1-3 of its
+    // 32 slices: ~1 KB of stores instead of 16 KB -- the row writes were 3/4 of the step's DRAM traffic), and the row's new
+    // occupancy is left for the next use (all ones for the paths that do not know better: table rows, wide scans, walks).
     // sharded step: this kernel -- the first of the step that nobody reads the step number in -- advances the buffer set's
     // step number in device memory; the publication at the tail of k_mask_bytes and the pull kernel read it there, so the
     // whole step has no per-step host argument and can be captured in a CUDA graph
@@ -830,6 +834,15 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
         if (xcounts && lane == 0) xcounts[b] = e > s ? e - s : 0ull;  // occurrence count of the prefix on this shard
         if (ndist_out && lane == 0) ndist_out[b] = (s >= e && !override_tok) ? 0u : NDIST_PENDING;
         const bool count_here = ndist_out && !override_tok;
+        const bool lazy = occ_state != nullptr;
+        const uint32_t nsl_all = (vocab + SLICE - 1) / SLICE;
+        const uint32_t all_occ = nsl_all >= 32u ? ~0u : ((1u << nsl_all) - 1u);
+        uint32_t old_occ = all_occ;
+        if (lazy) {
+            old_occ = occ_state[b] & all_occ;
+            __syncwarp();
+            if (lane == 0) occ_state[b] = s < e ? all_occ : 0u;  // the exact paths below overwrite this
+        }
         if (ix.uni_n && !counts_out && e > s && e - s > (uint64_t)SCAN_INLINE) {
             int ui = __reduce_max_sync(FULL, fm_uni_find_part(ix, (uint32_t)s, (uint32_t)lane, 32u));
             if (ui >= 0 && __ldg(ix.uni_ep + ui) != (uint32_t)e) ui = -1;
@@ -850,7 +863,19 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
             }
         }
         if (dense && !(zflags & 1u)) {  // bit 0: the rows were zeroed by k_search (fmidx_query_batch)
-            if (zflags & 2u) {           // bit 1: 16-byte stores are legal
+            if (lazy && old_occ != all_occ) {
+                uint32_t todo = old_occ;  // only the slices the previous use may have dirtied
+                while (todo) {
+                    const uint32_t w0 = ((uint32_t)__ffs(todo) - 1u) * (SLICE / 32), w1 = min(w0 + SLICE / 32, mw);
+                    if (zflags & 2u) {
+                        const uint32_t i = w0 + 4u * (uint32_t)lane;
+                        if (i < w1) *reinterpret_cast<uint4 *>(row + i) = make_uint4(0u, 0u, 0u, 0u);
+                    } else {
+                        for (uint32_t i = w0 + (uint32_t)lane; i < w1; i += 32) row[i] = 0u;
+                    }
+                    todo &= todo - 1u;
+                }
+            } else if (zflags & 2u) {    // bit 1: 16-byte stores are legal
                 uint4 *row4 = reinterpret_cast<uint4 *>(row);
                 for (uint32_t i = (uint32_t)lane; i < (mw >> 2); i += 32) row4[i] = make_uint4(0u, 0u, 0u, 0u);
             } else {
@@ -895,6 +920,7 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
                     }
                     __syncwarp();
                 }
+                uint32_t occ_new = 0;  // slices that receive bits (lazy clearing; tk / SLICE < 32 there)
                 if (count_here) {
                     // the atomics' return values tell which bits were new (ATOM: a round trip per row -- only when asked for)
                     uint32_t fresh = 0;
@@ -903,6 +929,7 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
                             const uint32_t tk = (uint32_t)((int64_t)c - shift);
                             const uint32_t bit = 1u << (tk & 31u);
                             fresh += (atomicOr(&row[tk >> 5], bit) & bit) ? 0u : 1u;
+                            occ_new |= 1u << ((tk / SLICE) & 31u);
                         }
                     });
                     fresh = __reduce_add_sync(FULL, fresh);
@@ -912,8 +939,13 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
                         if (c >= ga && c < ge) {
                             const uint32_t tk = (uint32_t)((int64_t)c - shift);
                             atomicOr(&row[tk >> 5], 1u << (tk & 31u));  // RED: fire and forget
+                            occ_new |= 1u << ((tk / SLICE) & 31u);
                         }
                     });
+                }
+                if (lazy) {
+                    occ_new = __reduce_or_sync(FULL, occ_new);
+                    if (lane == 0) occ_state[b] = occ_new;
                 }
                 return;
             }
@@ -977,6 +1009,10 @@ k_mask_top(FmDev ix, const uint64_t *__restrict__ sp, const uint64_t *__restrict
             if (count_here) {
                 const uint32_t nf = (uint32_t)__popc(__ballot_sync(FULL, fresh1));
                 if (lane == 0) ndist_out[b] = nf;
+            }
+            if (lazy) {
+                const uint32_t occ_new = __reduce_or_sync(FULL, inside ? 1u << (sl & 31u) : 0u);
+                if (lane == 0) occ_state[b] = occ_new;
             }
             return;
         }
@@ -2589,10 +2625,15 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
                    const void *d_logits, void *d_out, int dtype, int64_t row_stride, const int32_t *d_override,
                    int32_t always_allow, const uint32_t *d_extra, uint32_t n_extra, uint32_t *d_mask,
                    uint32_t *d_counts, cudaStream_t s, uint32_t *d_occ, size_t dense_lo, size_t dense_n, bool prezeroed,
-                   const FmXchgArgs *xa, uint32_t *d_ndist) {
+                   const FmXchgArgs *xa, uint32_t *d_ndist, uint32_t *d_occ_state) {
     FM_TRY(check_ready(h));
     if (B == 0 || vocab == 0) return FMIDX_OK;
     if (!d_occ) { dense_lo = 0; dense_n = B; }  // sparse rows are only meaningful together with occupancy words
+    if (d_occ_state && (d_logits || d_occ || d_counts || d_override || prezeroed || (vocab + SLICE - 1) / SLICE > 32u)) {
+        // lazy clearing does not cover this call: whoever owns the state must treat the rows as unknown afterwards
+        FM_CUDA(cudaMemsetAsync(d_occ_state, 0xFF, B * sizeof(uint32_t), s));
+        d_occ_state = nullptr;
+    }
     const uint32_t nslices = (vocab + SLICE - 1) / SLICE;
     const size_t nblk = (size_t)nslices * B;
     if (nblk > 0x7FFFFFFFull) { fm_set_error("mask batch too large: split the call"); return FMIDX_EINVAL; }
@@ -2666,7 +2707,7 @@ int fm_launch_mask(fmidx *h, const uint64_t *d_sp, const uint64_t *d_ep, size_t 
     FM_LAUNCH(k_mask_top, (unsigned)((B * 32 + 127) / 128), 128, 0, s, ix, d_sp, d_ep, (uint32_t)B, LT, lvl, d_override, shift,
               vocab, items, ctr, has ? nullptr : d_mask, has ? nullptr : d_counts, has ? nullptr : d_occ, (uint32_t)dense_lo,
               (uint32_t)std::min<size_t>(dense_n, 0xFFFFFFFFu), zflags, xa && !has ? xa->xcounts : nullptr,
-              L == 0 ? SCAN_INLINE : scan_max, d_occ ? nullptr : d_ndist, xa ? xa->seq_dev : nullptr);
+              L == 0 ? SCAN_INLINE : scan_max, d_occ ? nullptr : d_ndist, xa ? xa->seq_dev : nullptr, d_occ_state);
     if (!has) {
         // CTAs per SM of the persistent k_mask_bytes grid (fmidx_tune "bytes_occ", 1..6)
         const int occ = h->tune_bytes_occ < 1 ? 1 : (h->tune_bytes_occ > 6 ? 6 : h->tune_bytes_occ);

@@ -344,3 +344,73 @@ def test_scalar_fast_paths_match_batched_paths_and_oracle(cuda, layout):
             assert ix.backward_search_step(s, lo, hi) == o.backward_search_step(s, lo, hi), (fast, s, lo, hi)
         for r in [0, 1, n - 1, n, n + 9, 2 ** 40] + [rng.randrange(n) for _ in range(30)]:
             assert ix.locate(r) == o.locate(r), (fast, r)
+
+
+@pytest.mark.parametrize("layout", ["resident", "sampled"])
+def test_lazy_clearing_of_mask_rows(cuda, layout):
+    """fmidx_tune("lazy_clear", 2): only the slices a buffer's previous use dirtied are zeroed.  The same two buffers see a
+    rotation of very different batches (wide one-token prefixes, narrow histories, empty and absent prefixes) through
+    fmidx_query_batch and through the captured device step; every mask must equal the oracle's, whatever was there before;
+    switching the feature off and on again, another buffer on the same slot and a different batch size must not leave
+    stale bits either."""
+    from fm_index_constrained_decoding_b200 import FMIndex
+    from fm_index_constrained_decoding_b200.index import DeviceGraphSteps, ragged
+    from oracle.oracle import OracleFMIndex
+    rng = random.Random(53)
+    vocab = 50000
+    weights = [1.0 / (r + 1) ** 1.05 for r in range(vocab)]
+    docs = [rng.choices(range(vocab), weights=weights, k=rng.randint(100, 500)) + [EOS] for _ in range(150)]
+    o = OracleFMIndex()
+    o.initialize(docs)
+    ix = FMIndex(layout=layout)
+    ix.tune(scan_max=2048, lazy_clear=2)
+    ix.initialize(docs, in_memory=True)
+    B = 192
+
+    def batch(kind):
+        seqs = []
+        for j in range(B):
+            d = rng.choice(docs)
+            i = rng.randrange(len(d) - 1)
+            if kind == "wide":
+                seqs.append([d[i]] if j % 3 else [rng.randrange(5)])
+            elif kind == "narrow":
+                seqs.append(d[i:i + rng.randint(3, 9)])
+            elif kind == "empty":
+                seqs.append([] if j % 2 else [vocab + 7, 3])
+            else:
+                seqs.append(d[i:i + rng.randint(1, 6)])
+        toks, offs = ragged(seqs)
+        osp, oep, om, _ = o.query_batch(toks, offs, want_mask=True, vocab=V, nthreads=4)
+        return torch.from_numpy(toks).cuda(), torch.from_numpy(offs).cuda(), om.view(np.int32)
+    kinds = ["wide", "narrow", "mixed", "empty", "narrow", "wide", "mixed", "narrow", "narrow", "empty", "mixed"]
+    batches = [batch(k) for k in kinds]
+    bufs = [torch.full((B, (V + 31) // 32), -1, dtype=torch.int32, device="cuda") for _ in range(2)]  # start dirty
+    spb, epb = torch.empty(B, dtype=torch.int64, device="cuda"), torch.empty(B, dtype=torch.int64, device="cuda")
+    for step, (toks, offs, om) in enumerate(batches):
+        i = step % 2
+        if step == 6:
+            ix.tune(lazy_clear=1)   # one call without book-keeping ...
+        if step == 7:
+            ix.tune(lazy_clear=2)   # ... must not leave a stale state behind
+        sp, ep, m = ix.query_batch(toks, offs, V, ws_slot=i, out=(spb, epb, bufs[i]))
+        torch.cuda.synchronize()
+        assert (m.cpu().numpy() == om).all(), (layout, step, kinds[step])
+    # another buffer and another batch size on the same slot
+    other = torch.full((B, (V + 31) // 32), -1, dtype=torch.int32, device="cuda")
+    toks, offs, om = batches[1]
+    _, _, m = ix.query_batch(toks, offs, V, ws_slot=0, out=(spb, epb, other))
+    assert (m.cpu().numpy() == om).all()
+    half = ragged([[int(t) for t in toks[offs[j]:offs[j + 1]].tolist()] for j in range(B // 2)])
+    _, _, m = ix.query_batch(torch.from_numpy(half[0]).cuda(), torch.from_numpy(half[1]).cuda(), V, ws_slot=0, out=(spb[:B // 2], epb[:B // 2], bufs[0][:B // 2]))
+    assert (m.cpu().numpy() == om[:B // 2]).all()
+    # captured device step with in-place input rewrites
+    maxtok = max(t.numel() for t, _, _ in batches)
+    gs = DeviceGraphSteps(ix, 1, B, maxtok, V, first_slot=9)
+    for step, (toks, offs, om) in enumerate(batches):
+        gs.toks[0][:toks.numel()].copy_(toks)
+        gs.offs[0].copy_(offs)
+        torch.cuda.synchronize()
+        gs.launch(0)
+        gs.wait(0)
+        assert (gs.mask[0].cpu().numpy() == om).all(), (layout, "graph", step, kinds[step])
