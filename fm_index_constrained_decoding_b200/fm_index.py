@@ -180,7 +180,9 @@ class FMIndex:
 
     # ---- extras (not in the SWIG surface) ------------------------------------------------------------
     def tune(self, **kw):
-        """Run-time tunables (fmidx_tune): scan_max, bytes_occ, unigram_table.  Results never depend on them."""
+        """Run-time tunables (fmidx_tune, see include/fmidx.h): scan_max, bytes_occ, unigram_table, scalar_fast,
+        scalar_speculate, lazy_clear (2 = also the caller's mask buffers: nothing else may write them between the calls of
+        their slot).  Results never depend on them."""
         for k, v in kw.items():
             N.check(N.lib().fmidx_tune(self._h, k.encode(), int(v)))
 

@@ -55,7 +55,13 @@ int fmidx_set_options(fmidx_t *h, uint32_t sa_dens, uint32_t isa_dens, int keep_
 /* run-time tunables of a handle (defaults come from the environment when the handle is created): "scan_max" -- ranges of up
  * to this many rows are read off the resident BWT instead of walking the matrix ($FMIDX_SCAN_MAX, 16384); "bytes_occ" -- CTAs
  * per SM of the byte-level enumeration kernel ($FMIDX_BYTES_OCC, 5); "unigram_table" -- 1/0: use / ignore the unigram
- * continuation table at query time ($FMIDX_UNIGRAM_TABLE, 1).  Results never depend on them. */
+ * continuation table at query time ($FMIDX_UNIGRAM_TABLE, 1); "scalar_fast" -- 1/0: scalar calls as one zero-copy launch with the
+ * result polled from mapped pinned memory ($FMIDX_SCALAR_FAST, 1); "scalar_speculate" -- 1/0: a scalar search also enumerates the
+ * range it returns, for the distinct_count call that usually follows ($FMIDX_SCALAR_SPECULATE, 1); "lazy_clear" -- 0/1/2: zero
+ * only the mask slices a buffer's previous use dirtied: 1 = buffers the library owns (pipelined / captured host forms), 2 = also
+ * the caller's d_mask of fmidx_query_batch / fmidx_query_graph_prepare_device, under the caller's promise that nothing else
+ * writes that buffer between the calls of its slot ($FMIDX_LAZY_CLEAR, 1); "probe_phase" -- measurement only.  Results never
+ * depend on them (lazy_clear 2: as long as the promise holds). */
 int fmidx_tune(fmidx_t *h, const char *key, int64_t value);
 
 /* ---- build: FMIndex::initialize (fm_index.cpp:33-41), initialize_from_file (:43-48) ------- */
