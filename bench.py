@@ -869,8 +869,40 @@ def other_decode(ix, toks, beg, device, o):
         torch.cuda.synchronize()
         ms_k = e0.elapsed_time(e1) / n
         bytes_ = R * VOCAB * esz * 2
+        # the step as the logits processors run it in steady state: per-beam (sp, ep) of history[:-1] kept on the device, ONE
+        # backward-search step per beam with the newest token (fmidx_decode_step), then the fused kernel
+        from fm_index_constrained_decoding_b200 import _native as _N
+        lens = offs[1:] - offs[:-1]
+        last = q[(offs[1:] - 1).clamp(min=0)].to(torch.int64).contiguous()
+        hoffs = torch.zeros_like(offs)
+        hoffs[1:] = torch.cumsum((lens - 1).clamp(min=0), 0)
+        keep = torch.ones(q.numel(), dtype=torch.bool, device=device)
+        keep[(offs[1:] - 1)[lens > 0]] = False
+        psp, pep = ix.get_range_batch(q[keep].contiguous(), hoffs)
+        sbuf = torch.empty((4, R), dtype=torch.int64, device=device)
+        ovr = torch.empty(R, dtype=torch.int32, device=device)
+        cs = C.c_void_p(st.cuda_stream)
+
+        def inc_step(k):
+            _N.check(_N.lib().fmidx_decode_step(ix._h, C.c_void_p(last.data_ptr()), 1, None, C.c_void_p(psp.data_ptr()), C.c_void_p(pep.data_ptr()),
+                                                C.c_void_p(sbuf[0].data_ptr()), C.c_void_p(sbuf[1].data_ptr()), R, SHIFT, -1, -2, 0,
+                                                C.c_void_p(sbuf[2].data_ptr()), C.c_void_p(sbuf[3].data_ptr()), C.c_void_p(ovr.data_ptr()), cs))
+            ix.mask_logits(sbuf[2], sbuf[3], bufs[k % 8], out=outb, override_tok=ovr, always_allow=EOS)
+        for k in range(5):
+            inc_step(k)
+        torch.cuda.synchronize()
+        e0.record(st)
+        for k in range(n):
+            inc_step(k)
+        e1.record(st)
+        torch.cuda.synchronize()
+        ms_inc = e0.elapsed_time(e1) / n
+        inc_ok = bool(torch.equal(sbuf[2], sp) and torch.equal(sbuf[3], ep))
         res = {"ms_per_step": ms, "steps_per_s": 1e3 / ms, "fused_kernel_ms": ms_k, "fused_kernel_GBps": bytes_ / (ms_k * 1e-3) / 1e9,
-               "fused_kernel_frac_of_hbm": bytes_ / (ms_k * 1e-3) / 1e9 / peak, "algorithmic_bytes": bytes_}
+               "fused_kernel_frac_of_hbm": bytes_ / (ms_k * 1e-3) / 1e9 / peak, "algorithmic_bytes": bytes_,
+               "ms_per_step_incremental": ms_inc, "incremental_matches_full_search": inc_ok,
+               "incremental_note": "fmidx_decode_step (device-resident per-beam state, one backward-search step per beam) + the fused kernel: "
+                                   "the steady-state step of processors.IndexBasedLogitsProcessor; ms_per_step re-searches every history"}
         if o is not None:
             from oracle.oracle import SHIFT as _S  # noqa: F401
             qn, on = q.cpu().numpy(), offs.cpu().numpy()
